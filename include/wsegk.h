@@ -1,0 +1,132 @@
+/* wsegk — C ABI of the B200 (sm_100a) kernels behind wseg's Step-1 contrast hot path.
+ *
+ * The reference (obeychoi0120/wseg) is pure PyTorch and has NO FFI for this path; its only
+ * plugin point is `--network <module>` (contrast_train.py:40,60; contrast_infer.py:21,32) and the loss is
+ * an inline script body (contrast_train.py:129-395).  Each entry point below therefore cites the chain of
+ * ATen calls in the reference that it replaces.  INTEGRATION.md shows the ctypes binding a maintainer adds.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is DEVICE memory unless named `host_*`;
+ *  - tensors are contiguous fp32 NCHW exactly as PyTorch lays them out; indices/labels are int32;
+ *  - the caller owns every buffer (inputs, outputs, workspace); nothing is allocated, freed or retained;
+ *  - all work is enqueued on `stream` (a CUstream / cudaStream_t); no host synchronisation; graph-capturable;
+ *  - return 0 on success or a negative wsegk_status; wsegk_last_error() gives a thread-local message;
+ *  - there is no CPU path: on a device that is not sm_100 every call returns WSEGK_ERR_DEVICE.
+ */
+#ifndef WSEGK_H_
+#define WSEGK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* wsegk_stream_t;
+
+enum wsegk_status {
+    WSEGK_OK = 0,
+    WSEGK_ERR_BAD_SHAPE = -1,
+    WSEGK_ERR_BAD_ALIGN = -2,
+    WSEGK_ERR_WORKSPACE_TOO_SMALL = -3,
+    WSEGK_ERR_CUDA = -4,
+    WSEGK_ERR_DEVICE = -5,
+    WSEGK_ERR_NULL = -6
+};
+
+/* operations, for wsegk_workspace_bytes() */
+enum wsegk_op {
+    WSEGK_OP_CAM_NORM = 1,
+    WSEGK_OP_PCM = 2,        /* one workspace shared by pcm_fwd and pcm_bwd (bwd reads what fwd left) */
+    WSEGK_OP_FULLRES_NORM = 3,
+    WSEGK_OP_SEED_LABELS = 4,
+    WSEGK_OP_PROTO = 5,
+    WSEGK_OP_CONTRAST_LOSS = 6
+};
+
+int wsegk_version(void);
+const char* wsegk_last_error(void);
+
+/* Bytes of workspace `op` needs.  Unused dims may be 0.
+ *   N batch, C classes (21), K PCM channels (192), D projection dim, h,w grid, P = pixels on the loss grid. */
+size_t wsegk_workspace_bytes(int op, int N, int C, int K, int D, int h, int w);
+
+/* K1a — replaces network/resnet38_contrast.py:41-48 (relu, per-(n,c) max-norm, background = 1-max fg,
+ * keep only the arg-max foreground class).  cam [N,C,h,w] -> cam_norm [N,C,h,w].  Needs C >= 2. */
+int wsegk_cam_norm_fwd(const float* cam, float* cam_norm, int N, int C, int h, int w,
+                       void* workspace, size_t workspace_bytes, wsegk_stream_t stream);
+
+/* K2 forward — replaces network/resnet38_contrast.py:70-73 (PCM after the f9 conv):
+ *   fh = f/(|f|_2+1e-5); aff = relu(fh^T fh); aff /= colsum(aff)+1e-5; cam_rv = cam_norm @ aff.
+ * f [N,K,h,w], cam_norm [N,C,h,w] -> cam_rv [N,C,h,w].  The HWxHW affinity lives only in TMEM.
+ * BF16 operands (cam_norm as a hi+lo BF16 pair), FP32 accumulation.  K % 16 == 0, K <= 192, C <= 23.
+ * The workspace is left holding what pcm_bwd needs (normalised features, norms, column sums). */
+int wsegk_pcm_fwd(const float* f, const float* cam_norm, float* cam_rv, int N, int C, int K, int h, int w,
+                  void* workspace, size_t workspace_bytes, wsegk_stream_t stream);
+
+/* K2 backward — autograd of the lines above w.r.t. f only (cam_norm carries no gradient, :41).
+ * grad_cam_rv [N,C,h,w] -> grad_f [N,K,h,w].  `workspace` must be the one pcm_fwd filled for the same
+ * f / cam_norm (cam_rv is the forward output). */
+int wsegk_pcm_bwd(const float* f, const float* cam_norm, const float* cam_rv, const float* grad_cam_rv,
+                  float* grad_f, int N, int C, int K, int h, int w, void* workspace, size_t workspace_bytes,
+                  wsegk_stream_t stream);
+
+/* K1b forward — replaces tool/visualization.py:62-67 + contrast_train.py:145-152 / 157-158:
+ *   y = relu(relu(p)-min-1e-5)/(max-min+1e-5) per (n,c) plane; bilinear(align_corners) to (oh,ow); * label.
+ * p [N,C,H,W], label [N,C] -> out [N,C,oh,ow]; minmax [N,C,4] receives {min, max, argmin, argmax} (the two
+ * indices stored as int32 bit patterns) for the backward. */
+int wsegk_fullres_norm_fwd(const float* p, const float* label, float* out, float* minmax, int N, int C,
+                           int H, int W, int oh, int ow, void* workspace, size_t workspace_bytes,
+                           wsegk_stream_t stream);
+
+/* K1b backward — grad_out [N,C,oh,ow] -> grad_p [N,C,H,W], including the gradient routed to each plane's
+ * arg-min / arg-max pixel (torch.max/min(dim) backward; first flat index on ties). */
+int wsegk_fullres_norm_bwd(const float* p, const float* label, const float* minmax, const float* grad_out,
+                           float* grad_p, int N, int C, int H, int W, int oh, int ow, void* workspace,
+                           size_t workspace_bytes, wsegk_stream_t stream);
+
+/* K1c — replaces contrast_train.py:186-197 / 215-226: relu, per-plane min/max normalisation (no outer relu),
+ * channel 0 := bg_threshold, pseudo label = argmax_c(norm_cam*label) (lowest class on ties).
+ * cam_rv_down [N,C,g_h,g_w], label [N,C] -> norm_cam [N,C,g_h,g_w], pseudo [N*g_h*g_w] int32. */
+int wsegk_seed_labels_fwd(const float* cam_rv_down, const float* label, float bg_threshold, float* norm_cam,
+                          int32_t* pseudo, int N, int C, int h, int w, void* workspace,
+                          size_t workspace_bytes, wsegk_stream_t stream);
+
+/* K3 — replaces contrast_train.py:199-209 / 229-241.  Per class, the k largest norm_cam values over the whole
+ * batch (value desc, then lowest flat index n*h*w + y*w + x), and the value-weighted feature sums.
+ *   proto_topk_local : norm_cam [N,C,h,w], f_proj [N,D,h,w] -> top_val [C,k], top_idx [C,k] (int32, local
+ *                      pixel index + pixel_offset), top_fea [C,k,D] (gathered un-normalised features).
+ *   proto_finalize   : from R*k candidates per class (concatenated over ranks in rank order) select the global
+ *                      top k in canonical order and emit prototypes [C,D] (L2-normalised), sel_idx [C,k]. */
+int wsegk_proto_topk_local(const float* norm_cam, const float* f_proj, int pixel_offset, int k, float* top_val,
+                           int32_t* top_idx, float* top_fea, int N, int C, int D, int h, int w, void* workspace,
+                           size_t workspace_bytes, wsegk_stream_t stream);
+int wsegk_proto_finalize(const float* cand_val, const int32_t* cand_idx, const float* cand_fea, int n_cand,
+                         int k, float* proto, int32_t* sel_idx, int C, int D, wsegk_stream_t stream);
+
+/* K4 — replaces contrast_train.py:244-389: the four cross-view NCE terms and the two intra-view NCE terms
+ * (semi-hard prototypes = ranks 3..12, hard-pixel mining), forward and backward in one call.
+ *   x1,x2   [N,D,h,w]  projected features of the two views on the common loss grid (un-normalised)
+ *   proto1/2 [C,D], pl1/pl2 [P] int32 pseudo labels (P = N*h*w)
+ *   rand_key1/2 [P] uint32: the "random 50 %" of a class = its pixels with the len//2 smallest
+ *            (key, index); pass keys reproducing the reference's Python RNG for bit parity, or any hash.
+ *   losses  [8] fp32: {cross_a, cross_b, cross2_a, cross2_b, intra1, intra2, loss_cross_nce, loss_cross_nce2}
+ *           then losses[8] = loss_intra_nce, losses[9] = loss_nce (10 floats)
+ *   grad_x1/2 [N,D,h,w] = d(loss_nce)/dx * grad_scale_ptr[0] (device scalar; NULL = 1)
+ *   mined1/2 [P] int32 (optional, may be NULL): how many times the pixel entered its class's mined set (0..2)
+ */
+int wsegk_contrast_loss_fwd_bwd(const float* x1, const float* x2, const float* proto1, const float* proto2,
+                                const int32_t* pl1, const int32_t* pl2, const uint32_t* rand_key1,
+                                const uint32_t* rand_key2, float* losses, float* grad_x1, float* grad_x2,
+                                int32_t* mined1, int32_t* mined2, const float* grad_scale, int N, int C, int D,
+                                int h, int w, void* workspace, size_t workspace_bytes, wsegk_stream_t stream);
+
+/* Test aid: byte offsets of the PCM workspace sections, in the order
+ * {fhat, camb, inv_norm, dsum, part, uaug, vaug, dfhat, total_bytes, nsplit, T, HWp}.  Returns how many were written. */
+int wsegk_debug_pcm_layout(int N, int C, int K, int h, int w, size_t* out, int n_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WSEGK_H_ */

@@ -1,0 +1,80 @@
+"""ctypes binding of ``libwsegk.so`` (include/wsegk.h).  There is no fallback: if the library is missing
+or a call fails, a RuntimeError is raised — the product never routes through PyTorch ops or the oracle."""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int32, c_size_t, c_uint32, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libwsegk.so")
+
+OP_CAM_NORM, OP_PCM, OP_FULLRES_NORM, OP_SEED_LABELS, OP_PROTO, OP_CONTRAST_LOSS = 1, 2, 3, 4, 5, 6
+
+_P = c_void_p
+_SIGNATURES = {
+    "wsegk_version": (c_int, []),
+    "wsegk_last_error": (c_char_p, []),
+    "wsegk_workspace_bytes": (c_size_t, [c_int] * 7),
+    "wsegk_debug_pcm_layout": (c_int, [c_int] * 5 + [ctypes.POINTER(c_size_t), c_int]),
+    "wsegk_cam_norm_fwd": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
+    "wsegk_pcm_fwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
+    "wsegk_pcm_bwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
+    "wsegk_fullres_norm_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
+    "wsegk_fullres_norm_bwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P,
+                                       c_size_t, _P]),
+    "wsegk_seed_labels_fwd": (c_int, [_P, _P, c_float, _P, _P, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
+    "wsegk_proto_topk_local": (c_int, [_P, _P, c_int, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P,
+                                       c_size_t, _P]),
+    "wsegk_proto_finalize": (c_int, [_P, _P, _P, c_int, c_int, _P, _P, c_int, c_int, _P]),
+    "wsegk_contrast_loss_fwd_bwd": (c_int, [_P] * 14 + [c_int] * 5 + [_P, c_size_t, _P]),
+}
+
+_lib = None
+MISSING = []
+
+
+def _missing_symbol(name):
+    def raiser(*_a, **_k):
+        raise RuntimeError(f"libwsegk.so does not export `{name}` (stale build?); there is no fallback")
+    return raiser
+
+
+def symbols():
+    """Entry points declared in include/wsegk.h (tests check the built library exports each one)."""
+    return tuple(_SIGNATURES)
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m wseg_b200.build` "
+                "(wseg_b200 has no CPU or PyTorch fallback)")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            try:
+                fn = getattr(handle, name)
+            except AttributeError:
+                MISSING.append(name)            # tests assert this stays empty; calling it raises below
+                setattr(handle, name, _missing_symbol(name))
+                continue
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def last_error() -> str:
+    msg = lib().wsegk_last_error()
+    return msg.decode() if msg else ""
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise RuntimeError(f"{what} failed (wsegk status {rc}): {last_error()}")
+
+
+def workspace_bytes(op: int, N: int = 0, C: int = 0, K: int = 0, D: int = 0, h: int = 0, w: int = 0) -> int:
+    return int(lib().wsegk_workspace_bytes(op, N, C, K, D, h, w))
