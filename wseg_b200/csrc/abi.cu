@@ -88,22 +88,19 @@ extern "C" const char* wsegk_last_error(void) { return g_err; }
 
 extern "C" size_t wsegk_workspace_bytes(int op, int N, int C, int K, int D, int h, int w) {
     if (N <= 0 || h <= 0 || w <= 0) return 0;
-    const size_t P = static_cast<size_t>(N) * h * w;
     switch (op) {
         case WSEGK_OP_CAM_NORM:
             return align_up(static_cast<size_t>(N) * C * sizeof(float), 1024);
         case WSEGK_OP_PCM:
             return make_pcm_plan(nullptr, N, C, K, h, w).bytes;
         case WSEGK_OP_FULLRES_NORM:
-            return 1024;
+            return fullres_workspace_bytes(N, C);
         case WSEGK_OP_SEED_LABELS:
             return align_up(static_cast<size_t>(N) * C * 2 * sizeof(float), 1024);
         case WSEGK_OP_PROTO:
-            return align_up(static_cast<size_t>(C) * 64 * sizeof(uint32_t), 1024) + 1024;
+            return proto_workspace_bytes(N, C, h, w);
         case WSEGK_OP_CONTRAST_LOSS:
-            // per view: pixel records (sim, loss terms, rank scratch) + class tables
-            return align_up(2 * (P * 16 * sizeof(float) + static_cast<size_t>(C) * 64 * sizeof(float)) + 4096,
-                            1024);
+            return contrast_workspace_bytes(N, C, D, h, w);
         default:
             set_error("unknown op %d", op);
             return 0;

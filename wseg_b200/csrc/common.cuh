@@ -41,6 +41,10 @@ int check_device();   // WSEGK_OK if the current device is sm_100, else WSEGK_ER
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+__host__ __device__ inline int ceil_div_dev(int a, int b) { return (a + b - 1) / b; }
+size_t fullres_workspace_bytes(int N, int C);
+size_t proto_workspace_bytes(int N, int C, int h, int w);
+size_t contrast_workspace_bytes(int N, int C, int D, int h, int w);
 
 // Bump allocator over the caller's workspace; every section is 1 KiB aligned.
 struct Carver {

@@ -1,0 +1,399 @@
+// K1b — full-resolution min/max normalisation + bilinear(align_corners) resize + label mask, fwd and bwd
+//        (replaces tool/visualization.py:62-67 and contrast_train.py:145-152 / 157-158).
+// K1c — seed labels on the loss grid (replaces contrast_train.py:186-197 / 215-226).
+// All HBM-bound; planes whose image-level label is 0 are never read (their output is exactly 0).
+#include <algorithm>
+#include <cfloat>
+#include <climits>
+
+#include "common.cuh"
+
+namespace wsegk {
+
+struct MinMax {
+    float lo, hi;
+    int ilo, ihi;
+};
+
+__device__ __forceinline__ MinMax mm_merge(MinMax a, MinMax b) {
+    // first flat index wins ties (torch.max/min(dim) backward routes to one index)
+    MinMax r = a;
+    if (b.lo < r.lo || (b.lo == r.lo && b.ilo < r.ilo)) { r.lo = b.lo; r.ilo = b.ilo; }
+    if (b.hi > r.hi || (b.hi == r.hi && b.ihi < r.ihi)) { r.hi = b.hi; r.ihi = b.ihi; }
+    return r;
+}
+
+__device__ __forceinline__ MinMax mm_warp(MinMax v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        MinMax w;
+        w.lo = __shfl_xor_sync(0xffffffffu, v.lo, o);
+        w.hi = __shfl_xor_sync(0xffffffffu, v.hi, o);
+        w.ilo = __shfl_xor_sync(0xffffffffu, v.ilo, o);
+        w.ihi = __shfl_xor_sync(0xffffffffu, v.ihi, o);
+        v = mm_merge(v, w);
+    }
+    return v;
+}
+
+__device__ __forceinline__ MinMax mm_block(MinMax v, MinMax* s_red) {
+    v = mm_warp(v);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    if (lane == 0) s_red[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        MinMax w = lane < nw ? s_red[lane] : MinMax{FLT_MAX, -FLT_MAX, INT_MAX, INT_MAX};
+        w = mm_warp(w);
+        if (lane == 0) s_red[0] = w;
+    }
+    __syncthreads();
+    MinMax r = s_red[0];
+    __syncthreads();
+    return r;
+}
+
+constexpr int kPlaneSplit = 8;   // CTAs per (n,c) plane in the min/max pass
+
+// partial min/max (+ first arg) of relu(p) over a slice of one plane; masked planes exit immediately
+__global__ void __launch_bounds__(512) plane_minmax_partial_kernel(const float* __restrict__ p,
+                                                                   const float* __restrict__ label,
+                                                                   MinMax* __restrict__ partial, int HW) {
+    const int plane = blockIdx.y, part = blockIdx.x;
+    __shared__ MinMax s_red[16];
+    MinMax v{FLT_MAX, -FLT_MAX, INT_MAX, INT_MAX};
+    if (label == nullptr || label[plane] != 0.f) {
+        const float* src = p + static_cast<size_t>(plane) * HW;
+        const int per = ceil_div_dev(HW, static_cast<int>(gridDim.x));
+        const int per4 = (per + 3) & ~3;
+        const int begin = part * per4, end = min(HW, begin + per4);
+        const bool vec = ((HW & 3) == 0);
+        if (vec) {
+            const float4* s4 = reinterpret_cast<const float4*>(src);
+            for (int i = (begin >> 2) + threadIdx.x; i < (end >> 2); i += blockDim.x) {
+                const float4 x = __ldg(s4 + i);
+                const float e[4] = {fmaxf(x.x, 0.f), fmaxf(x.y, 0.f), fmaxf(x.z, 0.f), fmaxf(x.w, 0.f)};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int idx = 4 * i + j;
+                    if (e[j] < v.lo) { v.lo = e[j]; v.ilo = idx; }
+                    if (e[j] > v.hi) { v.hi = e[j]; v.ihi = idx; }
+                }
+            }
+        } else {
+            for (int i = begin + threadIdx.x; i < end; i += blockDim.x) {
+                const float e = fmaxf(__ldg(src + i), 0.f);
+                if (e < v.lo) { v.lo = e; v.ilo = i; }
+                if (e > v.hi) { v.hi = e; v.ihi = i; }
+            }
+        }
+    }
+    v = mm_block(v, s_red);
+    if (threadIdx.x == 0) partial[plane * gridDim.x + part] = v;
+}
+
+__device__ __forceinline__ MinMax plane_minmax_final(const MinMax* partial, int plane, int nsplit) {
+    MinMax v = partial[plane * nsplit];
+    for (int s = 1; s < nsplit; ++s) v = mm_merge(v, partial[plane * nsplit + s]);
+    return v;
+}
+
+// bilinear, align_corners=True source coordinate (ATen area_pixel_compute_source_index)
+__device__ __forceinline__ void src_coord(int o, float scale, int in_size, int& i0, int& i1, float& l0, float& l1) {
+    const float s = scale * static_cast<float>(o);
+    i0 = static_cast<int>(s);
+    if (i0 > in_size - 1) i0 = in_size - 1;
+    i1 = i0 + ((i0 < in_size - 1) ? 1 : 0);
+    l1 = s - static_cast<float>(i0);
+    l0 = 1.f - l1;
+}
+
+__device__ __forceinline__ float norm_val(float p, float lo, float inv_den) {
+    return fmaxf(fmaxf(p, 0.f) - lo - 1e-5f, 0.f) * inv_den;
+}
+
+// out[n,c,oy,ox] = label * bilinear( relu(relu(p)-lo-e) / (hi-lo+e) )
+__global__ void __launch_bounds__(256) fullres_resample_kernel(const float* __restrict__ p,
+                                                               const float* __restrict__ label,
+                                                               const MinMax* __restrict__ partial,
+                                                               float* __restrict__ out,
+                                                               float* __restrict__ minmax, int H, int W,
+                                                               int oh, int ow, int nsplit) {
+    const int plane = blockIdx.y;
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    const float lab = label[plane];
+    float* dst = out + static_cast<size_t>(plane) * oh * ow;
+    if (lab == 0.f) {
+        if (o < oh * ow) dst[o] = 0.f;
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            minmax[plane * 4 + 0] = 0.f; minmax[plane * 4 + 1] = 0.f;
+            minmax[plane * 4 + 2] = __int_as_float(0); minmax[plane * 4 + 3] = __int_as_float(0);
+        }
+        return;
+    }
+    const MinMax mm = plane_minmax_final(partial, plane, nsplit);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        minmax[plane * 4 + 0] = mm.lo; minmax[plane * 4 + 1] = mm.hi;
+        minmax[plane * 4 + 2] = __int_as_float(mm.ilo); minmax[plane * 4 + 3] = __int_as_float(mm.ihi);
+    }
+    if (o >= oh * ow) return;
+    const float den = mm.hi - mm.lo + 1e-5f;
+    const float* src = p + static_cast<size_t>(plane) * H * W;
+    float val;
+    if (oh == H && ow == W) {
+        val = fmaxf(fmaxf(__ldg(src + o), 0.f) - mm.lo - 1e-5f, 0.f) / den;
+    } else {
+        const int oy = o / ow, ox = o - oy * ow;
+        const float sy = oh > 1 ? static_cast<float>(H - 1) / static_cast<float>(oh - 1) : 0.f;
+        const float sx = ow > 1 ? static_cast<float>(W - 1) / static_cast<float>(ow - 1) : 0.f;
+        int y0, y1, x0, x1; float hy0, hy1, wx0, wx1;
+        src_coord(oy, sy, H, y0, y1, hy0, hy1);
+        src_coord(ox, sx, W, x0, x1, wx0, wx1);
+        auto at = [&](int y, int x) {
+            return fmaxf(fmaxf(__ldg(src + static_cast<size_t>(y) * W + x), 0.f) - mm.lo - 1e-5f, 0.f) / den;
+        };
+        val = hy0 * (wx0 * at(y0, x0) + wx1 * at(y0, x1)) + hy1 * (wx0 * at(y1, x0) + wx1 * at(y1, x1));
+    }
+    dst[o] = val * lab;
+}
+
+// ---- backward ----------------------------------------------------------------------------------
+// gy(y,x) = sum over outputs (oy,ox) whose taps include (y,x) of weight * grad_out * label  (gather form)
+__device__ __forceinline__ float tap_weight(int o, int i, float scale, int in_size) {
+    int i0, i1; float l0, l1;
+    src_coord(o, scale, in_size, i0, i1, l0, l1);
+    float wgt = 0.f;
+    if (i0 == i) wgt += l0;
+    if (i1 == i) wgt += l1;
+    return wgt;
+}
+
+// candidate output coordinates whose taps may include input coordinate i (scale >= 1)
+__device__ __forceinline__ void tap_candidates(int i, float scale, int out_size, int& first, int& last) {
+    if (scale <= 0.f) { first = 0; last = out_size - 1; return; }
+    int a = static_cast<int>(floorf(static_cast<float>(i - 1) / scale)) - 1;
+    int b = static_cast<int>(ceilf(static_cast<float>(i) / scale)) + 1;
+    first = max(a, 0);
+    last = min(b, out_size - 1);
+}
+
+// pass 1: per plane, S1 = sum gy*relu(z)/den^2 and S0 = sum gy*[z>0]/den  (block partials -> atomics-free two-stage)
+// pass 2: grad_p = [p>0] * ( gy*[z>0]/den + [idx==argmax]*(-S1) + [idx==argmin]*(S1 - S0) )
+template <bool kWrite>
+__global__ void __launch_bounds__(256) fullres_bwd_kernel(const float* __restrict__ p,
+                                                          const float* __restrict__ label,
+                                                          const float* __restrict__ minmax,
+                                                          const float* __restrict__ gout,
+                                                          float* __restrict__ grad_p,
+                                                          float* __restrict__ sums, int H, int W, int oh,
+                                                          int ow, int nblk) {
+    const int plane = blockIdx.y;
+    const int HW = H * W;
+    const float lab = label[plane];
+    float* dst = grad_p + static_cast<size_t>(plane) * HW;
+    __shared__ float s_a[8], s_b[8];
+    if (lab == 0.f) {
+        if (kWrite) {
+            for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) dst[i] = 0.f;
+        } else if (threadIdx.x == 0) {
+            sums[(plane * nblk + blockIdx.x) * 2] = 0.f;
+            sums[(plane * nblk + blockIdx.x) * 2 + 1] = 0.f;
+        }
+        return;
+    }
+    const float lo = minmax[plane * 4], hi = minmax[plane * 4 + 1];
+    const int ilo = __float_as_int(minmax[plane * 4 + 2]), ihi = __float_as_int(minmax[plane * 4 + 3]);
+    const float den = hi - lo + 1e-5f;
+    const float* src = p + static_cast<size_t>(plane) * HW;
+    const float* g = gout + static_cast<size_t>(plane) * oh * ow;
+    const bool same = (oh == H && ow == W);
+    const float sy = oh > 1 ? static_cast<float>(H - 1) / static_cast<float>(oh - 1) : 0.f;
+    const float sx = ow > 1 ? static_cast<float>(W - 1) / static_cast<float>(ow - 1) : 0.f;
+    float S0 = 0.f, S1 = 0.f;
+    if (kWrite) {
+        // final plane sums from the pass-1 partials (fixed order => deterministic)
+        for (int b = 0; b < nblk; ++b) { S0 += sums[(plane * nblk + b) * 2]; S1 += sums[(plane * nblk + b) * 2 + 1]; }
+    }
+    float acc0 = 0.f, acc1 = 0.f;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+        const float pv = __ldg(src + i);
+        const float z = fmaxf(pv, 0.f) - lo - 1e-5f;
+        float gy = 0.f;
+        if (same) {
+            gy = __ldg(g + i) * lab;
+        } else {
+            const int y = i / W, x = i - y * W;
+            int oy0, oy1, ox0, ox1;
+            tap_candidates(y, sy, oh, oy0, oy1);
+            tap_candidates(x, sx, ow, ox0, ox1);
+            for (int oy = oy0; oy <= oy1; ++oy) {
+                const float wy = tap_weight(oy, y, sy, H);
+                if (wy == 0.f) continue;
+                for (int ox = ox0; ox <= ox1; ++ox) {
+                    const float wx = tap_weight(ox, x, sx, W);
+                    if (wx != 0.f) gy = fmaf(wy * wx, __ldg(g + oy * ow + ox), gy);
+                }
+            }
+            gy *= lab;
+        }
+        if (!kWrite) {
+            if (z > 0.f) { acc0 += gy / den; acc1 += gy * z / (den * den); }
+        } else {
+            float d = (z > 0.f) ? gy / den : 0.f;
+            if (i == ihi) d -= S1;
+            if (i == ilo) d += S1 - S0;
+            dst[i] = (pv > 0.f) ? d : 0.f;
+        }
+    }
+    if (!kWrite) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            acc0 += __shfl_xor_sync(0xffffffffu, acc0, o);
+            acc1 += __shfl_xor_sync(0xffffffffu, acc1, o);
+        }
+        if ((threadIdx.x & 31) == 0) { s_a[threadIdx.x >> 5] = acc0; s_b[threadIdx.x >> 5] = acc1; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float a = 0.f, b = 0.f;
+            for (int wv = 0; wv < (blockDim.x >> 5); ++wv) { a += s_a[wv]; b += s_b[wv]; }
+            sums[(plane * nblk + blockIdx.x) * 2] = a;
+            sums[(plane * nblk + blockIdx.x) * 2 + 1] = b;
+        }
+    }
+}
+
+// ---- K1c ---------------------------------------------------------------------------------------
+// one warp per (n,c) plane: min/max of relu(x)
+__global__ void __launch_bounds__(256) seed_minmax_kernel(const float* __restrict__ x, float* __restrict__ lohi,
+                                                          int planes, int HW) {
+    const int plane = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (plane >= planes) return;
+    const int lane = threadIdx.x & 31;
+    const float* src = x + static_cast<size_t>(plane) * HW;
+    float lo = FLT_MAX, hi = 0.f;
+    for (int i = lane; i < HW; i += 32) {
+        const float v = fmaxf(__ldg(src + i), 0.f);
+        lo = fminf(lo, v);
+        hi = fmaxf(hi, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if (lane == 0) { lohi[2 * plane] = lo; lohi[2 * plane + 1] = hi; }
+}
+
+// thread per pixel: normalise every class plane, write norm_cam, argmax_c(norm*label) with lowest class on ties
+__global__ void __launch_bounds__(128) seed_pixel_kernel(const float* __restrict__ x, const float* __restrict__ label,
+                                                         const float* __restrict__ lohi, float bg,
+                                                         float* __restrict__ norm_cam, int32_t* __restrict__ pseudo,
+                                                         int C, int HW) {
+    const int n = blockIdx.y;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ float s_lo[32], s_hi[32], s_lab[32];
+    if (threadIdx.x < C) {
+        s_lo[threadIdx.x] = lohi[2 * (n * C + threadIdx.x)];
+        s_hi[threadIdx.x] = lohi[2 * (n * C + threadIdx.x) + 1];
+        s_lab[threadIdx.x] = label[n * C + threadIdx.x];
+    }
+    __syncthreads();
+    if (q >= HW) return;
+    const float* src = x + static_cast<size_t>(n) * C * HW + q;
+    float* dst = norm_cam + static_cast<size_t>(n) * C * HW + q;
+    float best = bg * s_lab[0];
+    int arg = 0;
+    dst[0] = bg;
+    for (int c = 1; c < C; ++c) {
+        float v = fmaxf(__ldg(src + static_cast<size_t>(c) * HW), 0.f);
+        const float lo = s_lo[c], hi = s_hi[c];
+        if (v < lo + 1e-5f) v = 0.f;
+        v = (v - lo - 1e-5f) / (hi - lo + 1e-5f);
+        dst[static_cast<size_t>(c) * HW] = v;
+        const float s = v * s_lab[c];
+        if (s > best) { best = s; arg = c; }
+    }
+    pseudo[n * HW + q] = arg;
+}
+
+}  // namespace wsegk
+
+using namespace wsegk;
+
+static int fullres_check(const char* who, int N, int C, int H, int W, int oh, int ow) {
+    WSEGK_REQUIRE(N > 0 && C > 0 && H > 0 && W > 0 && oh > 0 && ow > 0, WSEGK_ERR_BAD_SHAPE,
+                  "%s: all dims must be positive", who);
+    WSEGK_REQUIRE(oh <= H && ow <= W, WSEGK_ERR_BAD_SHAPE,
+                  "%s: output (%d,%d) larger than input (%d,%d) is not supported (the reference only shrinks)", who,
+                  oh, ow, H, W);
+    WSEGK_REQUIRE(static_cast<long long>(H) * W < (1ll << 30), WSEGK_ERR_BAD_SHAPE, "%s: plane too large", who);
+    return WSEGK_OK;
+}
+
+static size_t fullres_ws_bytes(int N, int C) {
+    // min/max partials + backward block sums
+    return align_up(static_cast<size_t>(N) * C * kPlaneSplit * sizeof(MinMax), 1024) +
+           align_up(static_cast<size_t>(N) * C * 64 * 2 * sizeof(float), 1024);
+}
+
+namespace wsegk {
+size_t fullres_workspace_bytes(int N, int C) { return fullres_ws_bytes(N, C); }
+}
+
+extern "C" int wsegk_fullres_norm_fwd(const float* p, const float* label, float* out, float* minmax, int N, int C,
+                                      int H, int W, int oh, int ow, void* workspace, size_t workspace_bytes,
+                                      wsegk_stream_t stream) {
+    if (int rc = check_device()) return rc;
+    WSEGK_REQUIRE(p && label && out && minmax && workspace, WSEGK_ERR_NULL, "fullres_norm_fwd: null pointer");
+    if (int rc = fullres_check("fullres_norm_fwd", N, C, H, W, oh, ow)) return rc;
+    WSEGK_REQUIRE((reinterpret_cast<uintptr_t>(p) & 15) == 0, WSEGK_ERR_BAD_ALIGN, "fullres_norm_fwd: p unaligned");
+    WSEGK_REQUIRE(workspace_bytes >= fullres_ws_bytes(N, C), WSEGK_ERR_WORKSPACE_TOO_SMALL,
+                  "fullres_norm_fwd: workspace %zu < %zu", workspace_bytes, fullres_ws_bytes(N, C));
+    MinMax* partial = static_cast<MinMax*>(workspace);
+    const int planes = N * C;
+    plane_minmax_partial_kernel<<<dim3(kPlaneSplit, planes), 512, 0, stream>>>(p, label, partial, H * W);
+    fullres_resample_kernel<<<dim3(ceil_div(oh * ow, 256), planes), 256, 0, stream>>>(p, label, partial, out, minmax,
+                                                                                       H, W, oh, ow, kPlaneSplit);
+    WSEGK_CUDA_OK(cudaGetLastError());
+    return WSEGK_OK;
+}
+
+extern "C" int wsegk_fullres_norm_bwd(const float* p, const float* label, const float* minmax, const float* grad_out,
+                                      float* grad_p, int N, int C, int H, int W, int oh, int ow, void* workspace,
+                                      size_t workspace_bytes, wsegk_stream_t stream) {
+    if (int rc = check_device()) return rc;
+    WSEGK_REQUIRE(p && label && minmax && grad_out && grad_p && workspace, WSEGK_ERR_NULL,
+                  "fullres_norm_bwd: null pointer");
+    if (int rc = fullres_check("fullres_norm_bwd", N, C, H, W, oh, ow)) return rc;
+    WSEGK_REQUIRE(workspace_bytes >= fullres_ws_bytes(N, C), WSEGK_ERR_WORKSPACE_TOO_SMALL,
+                  "fullres_norm_bwd: workspace %zu < %zu", workspace_bytes, fullres_ws_bytes(N, C));
+    float* sums = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) +
+                                           align_up(static_cast<size_t>(N) * C * kPlaneSplit * sizeof(MinMax), 1024));
+    const int planes = N * C;
+    const int nblk = std::min(64, ceil_div(H * W, 256 * 4));
+    fullres_bwd_kernel<false><<<dim3(nblk, planes), 256, 0, stream>>>(p, label, minmax, grad_out, grad_p, sums, H, W,
+                                                                     oh, ow, nblk);
+    fullres_bwd_kernel<true><<<dim3(nblk, planes), 256, 0, stream>>>(p, label, minmax, grad_out, grad_p, sums, H, W,
+                                                                    oh, ow, nblk);
+    WSEGK_CUDA_OK(cudaGetLastError());
+    return WSEGK_OK;
+}
+
+extern "C" int wsegk_seed_labels_fwd(const float* cam_rv_down, const float* label, float bg_threshold,
+                                     float* norm_cam, int32_t* pseudo, int N, int C, int h, int w, void* workspace,
+                                     size_t workspace_bytes, wsegk_stream_t stream) {
+    if (int rc = check_device()) return rc;
+    WSEGK_REQUIRE(cam_rv_down && label && norm_cam && pseudo && workspace, WSEGK_ERR_NULL,
+                  "seed_labels_fwd: null pointer");
+    WSEGK_REQUIRE(N > 0 && h > 0 && w > 0 && C >= 1 && C <= 32, WSEGK_ERR_BAD_SHAPE,
+                  "seed_labels_fwd: need N,h,w > 0 and 1 <= C <= 32");
+    const size_t need = wsegk_workspace_bytes(WSEGK_OP_SEED_LABELS, N, C, 0, 0, h, w);
+    WSEGK_REQUIRE(workspace_bytes >= need, WSEGK_ERR_WORKSPACE_TOO_SMALL, "seed_labels_fwd: workspace %zu < %zu",
+                  workspace_bytes, need);
+    float* lohi = static_cast<float*>(workspace);
+    const int planes = N * C, HW = h * w;
+    seed_minmax_kernel<<<ceil_div(planes, 8), 256, 0, stream>>>(cam_rv_down, lohi, planes, HW);
+    seed_pixel_kernel<<<dim3(ceil_div(HW, 128), N), 128, 0, stream>>>(cam_rv_down, label, lohi, bg_threshold,
+                                                                      norm_cam, pseudo, C, HW);
+    WSEGK_CUDA_OK(cudaGetLastError());
+    return WSEGK_OK;
+}

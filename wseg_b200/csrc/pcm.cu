@@ -293,6 +293,250 @@ __global__ void __launch_bounds__(128) pcm_fwd_finalize_kernel(const float* __re
         if (c < C) dst[static_cast<size_t>(c) * HW] = (acc[c] + acc[kCamHalf + c]) / d;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------
+// With G = dL/d(out), g_j = G_j / D_j, delta_j = sum_c out[c,j] G[c,j], d_j = delta_j / D_j:
+//   dL/dA_ij = cam_i . g_j - d_j,   dL/dS = dL/dA * [S > 0],   dL/dfh = (dS + dS^T) fh
+// and (dS + dS^T)_ji = [S_ji > 0] * (U_j . V_i) with the rank-(2C+2) factors
+//   U_j = [ g_j ; cam_j ; -d_j ; 1 ],   V_i = [ cam_i ; g_i ; 1 ; -d_i ]              
+// so a CTA owning a j-tile needs, per i-tile: S = Fj Fi^T (K), Tt = Uj Vi^T (48), the masked product E in
+// TMEM, and dFh_j += E Fi (Fi read MN-major from the same shared-memory tile).  No atomics.
+
+// U/V tiles: [128 pixels x 48] bf16, canonical K-major (chunk (pixel r, group g) at g*128 + r).
+__global__ void __launch_bounds__(128) pcm_bwd_prep_kernel(const float* __restrict__ cam,
+                                                           const float* __restrict__ out,
+                                                           const float* __restrict__ gout,
+                                                           const float* __restrict__ dsum,
+                                                           uint16_t* __restrict__ uaug,
+                                                           uint16_t* __restrict__ vaug, int C, int HW,
+                                                           int T, int HWp) {
+    __shared__ float s_u[kAugRows][kTile];
+    __shared__ float s_v[kAugRows][kTile];
+    const int t = blockIdx.x, n = blockIdx.y;
+    const int px = threadIdx.x;
+    const int p = t * kTile + px;
+    for (int i = 0; i < kAugRows; ++i) { s_u[i][px] = 0.f; s_v[i][px] = 0.f; }
+    if (p < HW) {
+        const float invd = 1.f / dsum[static_cast<size_t>(n) * HWp + p];
+        const size_t base = static_cast<size_t>(n) * C * HW + p;
+        float delta = 0.f;
+        for (int c = 0; c < C; ++c) {
+            const float cm = __ldg(cam + base + static_cast<size_t>(c) * HW);
+            const float g = __ldg(gout + base + static_cast<size_t>(c) * HW);
+            const float o = __ldg(out + base + static_cast<size_t>(c) * HW);
+            delta = fmaf(o, g, delta);
+            const float gs = g * invd;
+            s_u[c][px] = gs;      s_v[c][px] = cm;
+            s_u[C + c][px] = cm;  s_v[C + c][px] = gs;
+        }
+        const float dj = delta * invd;
+        s_u[2 * C][px] = -dj;     s_v[2 * C][px] = 1.f;
+        s_u[2 * C + 1][px] = 1.f; s_v[2 * C + 1][px] = -dj;
+    }
+    // each thread only reads back its own column: no barrier needed
+    uint4* du = reinterpret_cast<uint4*>(uaug + (static_cast<size_t>(n) * T + t) * kTile * kAugRows);
+    uint4* dv = reinterpret_cast<uint4*>(vaug + (static_cast<size_t>(n) * T + t) * kTile * kAugRows);
+#pragma unroll
+    for (int g = 0; g < kAugRows / 8; ++g) {
+        uint4 a, b;
+        a.x = pack_bf16x2(s_u[8 * g + 0][px], s_u[8 * g + 1][px]); a.y = pack_bf16x2(s_u[8 * g + 2][px], s_u[8 * g + 3][px]);
+        a.z = pack_bf16x2(s_u[8 * g + 4][px], s_u[8 * g + 5][px]); a.w = pack_bf16x2(s_u[8 * g + 6][px], s_u[8 * g + 7][px]);
+        b.x = pack_bf16x2(s_v[8 * g + 0][px], s_v[8 * g + 1][px]); b.y = pack_bf16x2(s_v[8 * g + 2][px], s_v[8 * g + 3][px]);
+        b.z = pack_bf16x2(s_v[8 * g + 4][px], s_v[8 * g + 5][px]); b.w = pack_bf16x2(s_v[8 * g + 6][px], s_v[8 * g + 7][px]);
+        du[g * kTile + px] = a;
+        dv[g * kTile + px] = b;
+    }
+}
+
+constexpr uint32_t kAugTileBytes = kTile * kAugRows * 2;   // 12288
+// TMEM columns (backward)
+constexpr uint32_t kColBS = 0;      // 128: S tile
+constexpr uint32_t kColBT = 128;    // 128: Tt = U V^T tile
+constexpr uint32_t kColBG = 256;    // K (<=192): dFh accumulator
+constexpr uint32_t kColBE = 448;    // 64: masked product as packed bf16
+
+struct BwdBars {
+    uint64_t fj, full[kStages], empty[kStages], st_full, e_full, g_full;
+    uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kFwdThreads, 1)
+pcm_bwd_kernel(const uint16_t* __restrict__ fhat, const uint16_t* __restrict__ uaug,
+               const uint16_t* __restrict__ vaug, float* __restrict__ dfhat, int K, int T, int HWp,
+               int nsplit) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t tile_bytes = kTile * K * 2;
+    uint8_t* s_fj = smem;
+    uint8_t* s_uj = smem + tile_bytes;
+    uint8_t* s_stage = s_uj + kAugTileBytes;
+    const uint32_t stage_bytes = tile_bytes + kAugTileBytes;
+    BwdBars* bars = reinterpret_cast<BwdBars*>(s_stage + kStages * stage_bytes);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tj = blockIdx.x, sp = blockIdx.y, n = blockIdx.z;
+    const int i_begin = (T * sp) / nsplit, i_end = (T * (sp + 1)) / nsplit;
+    const int ntiles = i_end - i_begin;
+
+    if (threadIdx.x == 0) {
+        mbar_init(smem_u32(&bars->fj), 1);
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(smem_u32(&bars->full[s]), 1);
+            mbar_init(smem_u32(&bars->empty[s]), 1);
+        }
+        mbar_init(smem_u32(&bars->st_full), 1);
+        mbar_init(smem_u32(&bars->e_full), 4);
+        mbar_init(smem_u32(&bars->g_full), 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(smem_u32(&bars->tmem_base), kTmemCols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = bars->tmem_base;
+
+    const uint8_t* g_f = reinterpret_cast<const uint8_t*>(fhat) + static_cast<size_t>(n) * T * tile_bytes;
+    const uint8_t* g_u = reinterpret_cast<const uint8_t*>(uaug) + static_cast<size_t>(n) * T * kAugTileBytes;
+    const uint8_t* g_v = reinterpret_cast<const uint8_t*>(vaug) + static_cast<size_t>(n) * T * kAugTileBytes;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(smem_u32(&bars->fj), tile_bytes + kAugTileBytes);
+            tma_load_1d(smem_u32(s_fj), g_f + static_cast<size_t>(tj) * tile_bytes, tile_bytes, smem_u32(&bars->fj));
+            tma_load_1d(smem_u32(s_uj), g_u + static_cast<size_t>(tj) * kAugTileBytes, kAugTileBytes,
+                        smem_u32(&bars->fj));
+            for (int t = 0; t < ntiles; ++t) {
+                const int s = t % kStages, u = t / kStages;
+                mbar_wait(smem_u32(&bars->empty[s]), (u & 1) ^ 1);
+                const uint32_t bar = smem_u32(&bars->full[s]);
+                uint8_t* dst = s_stage + s * stage_bytes;
+                mbar_arrive_expect_tx(bar, stage_bytes);
+                tma_load_1d(smem_u32(dst), g_f + static_cast<size_t>(i_begin + t) * tile_bytes, tile_bytes, bar);
+                tma_load_1d(smem_u32(dst + tile_bytes), g_v + static_cast<size_t>(i_begin + t) * kAugTileBytes,
+                            kAugTileBytes, bar);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc_s = umma_idesc_bf16(kTile, kTile, 0, 0);
+            const uint32_t idesc_g = umma_idesc_bf16(kTile, K, 0, 1);     // B = Fi read MN-major (N = channel)
+            const uint32_t lbo = kTile * 16;                              // 2048: K-direction step of a 128-row tile
+            mbar_wait(smem_u32(&bars->fj), 0);
+            for (int t = 0; t < ntiles; ++t) {
+                const int s = t % kStages, u = t / kStages;
+                mbar_wait(smem_u32(&bars->full[s]), u & 1);
+                tc_fence_after();
+                const uint32_t fj0 = smem_u32(s_fj), uj0 = smem_u32(s_uj);
+                const uint32_t fi0 = smem_u32(s_stage + s * stage_bytes), vi0 = fi0 + tile_bytes;
+                // (MMAs execute in issue order, so these overwrite S/Tt only after the previous E was consumed)
+                for (int ks = 0; ks < (K >> 4); ++ks)
+                    umma_ss(tmem + kColBS, umma_smem_desc(fj0 + ks * 2 * lbo, lbo, 128),
+                            umma_smem_desc(fi0 + ks * 2 * lbo, lbo, 128), idesc_s, ks > 0);
+                for (int ks = 0; ks < kAugRows / 16; ++ks)
+                    umma_ss(tmem + kColBT, umma_smem_desc(uj0 + ks * 2 * lbo, lbo, 128),
+                            umma_smem_desc(vi0 + ks * 2 * lbo, lbo, 128), idesc_s, ks > 0);
+                umma_commit(smem_u32(&bars->st_full));
+                mbar_wait(smem_u32(&bars->e_full), t & 1);
+                tc_fence_after();
+                // dFh[j, ch] += E[j, i] * Fi[i, ch]: B is N(ch) x K(pixel), MN-major: LBO = pixel-group step,
+                // SBO = channel-group step
+                for (int ks = 0; ks < kTile / 16; ++ks)
+                    umma_ts(tmem + kColBG, tmem + kColBE + ks * 8, umma_smem_desc(fi0 + ks * 256, 128, lbo),
+                            idesc_g, (t > 0) || (ks > 0));
+                umma_commit(smem_u32(&bars->empty[s]));
+            }
+            umma_commit(smem_u32(&bars->g_full));
+        }
+    } else {
+        const int q = warp & 3;
+        const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+        for (int t = 0; t < ntiles; ++t) {
+            mbar_wait(smem_u32(&bars->st_full), t & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+                uint32_t sv[32], tv[32], pk[16];
+                tmem_ld32(tmem + lane_addr + kColBS + c4 * 32, sv);
+                tmem_ld32(tmem + lane_addr + kColBT + c4 * 32, tv);
+                tmem_ld_wait();
+#pragma unroll
+                for (int m = 0; m < 16; ++m) {
+                    const float a = __uint_as_float(sv[2 * m]) > 0.f ? __uint_as_float(tv[2 * m]) : 0.f;
+                    const float b = __uint_as_float(sv[2 * m + 1]) > 0.f ? __uint_as_float(tv[2 * m + 1]) : 0.f;
+                    pk[m] = pack_bf16x2(a, b);
+                }
+                tmem_st16(tmem + lane_addr + kColBE + c4 * 16, pk);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bars->e_full));
+        }
+        mbar_wait(smem_u32(&bars->g_full), 0);
+        tc_fence_after();
+        const int row = tj * kTile + q * 32 + lane;
+        float4* dst = reinterpret_cast<float4*>(dfhat + ((static_cast<size_t>(n) * nsplit + sp) * HWp + row) * K);
+        for (int c = 0; c < (K >> 4); ++c) {
+            uint32_t r[16];
+            tmem_ld16(tmem + lane_addr + kColBG + c * 16, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int v = 0; v < 4; ++v)
+                dst[c * 4 + v] = make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]),
+                                             __uint_as_float(r[4 * v + 2]), __uint_as_float(r[4 * v + 3]));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, kTmemCols);
+}
+
+// grad_f[n,k,p] = dfh[k] * inv - f[k] * (sum_k dfh[k] f[k]) * inv^2 / |f|,  inv = 1/(|f| + 1e-5)
+// (autograd of f / (norm(f) + 1e-5), network/resnet38_contrast.py:70); dfh summed over the i-splits.
+__global__ void __launch_bounds__(256) pcm_bwd_post_kernel(const float* __restrict__ dfhat,
+                                                           const float* __restrict__ f,
+                                                           const float* __restrict__ inv_norm,
+                                                           float* __restrict__ grad_f, int K, int HW,
+                                                           int HWp, int nsplit) {
+    extern __shared__ float s_g[];        // [K][129]
+    __shared__ float s_dot[2][kTile];
+    const int t = blockIdx.x, n = blockIdx.y;
+    // coalesced read of the pixel-major gradient rows
+    for (int idx = threadIdx.x; idx < kTile * K; idx += blockDim.x) {
+        const int r = idx / K, k = idx - r * K;
+        float acc = 0.f;
+        for (int sp = 0; sp < nsplit; ++sp)
+            acc += __ldg(dfhat + ((static_cast<size_t>(n) * nsplit + sp) * HWp + t * kTile + r) * K + k);
+        s_g[k * 129 + r] = acc;
+    }
+    __syncthreads();
+    const int px = threadIdx.x & 127, half = threadIdx.x >> 7;
+    const int p = t * kTile + px;
+    const bool live = p < HW;
+    const float* fp = f + static_cast<size_t>(n) * K * HW + p;
+    float dot = 0.f;
+    if (live)
+        for (int k = half; k < K; k += 2) dot = fmaf(s_g[k * 129 + px], __ldg(fp + static_cast<size_t>(k) * HW), dot);
+    s_dot[half][px] = dot;
+    __syncthreads();
+    if (!live) return;
+    dot = s_dot[0][px] + s_dot[1][px];
+    const float inv = inv_norm[static_cast<size_t>(n) * HWp + p];
+    const float nrm = 1.f / inv - 1e-5f;
+    const float coef = nrm > 0.f ? dot * inv * inv / nrm : 0.f;
+    float* gp = grad_f + static_cast<size_t>(n) * K * HW + p;
+    for (int k = half; k < K; k += 2)
+        gp[static_cast<size_t>(k) * HW] = s_g[k * 129 + px] * inv - __ldg(fp + static_cast<size_t>(k) * HW) * coef;
+}
+
+static size_t bwd_smem_bytes(int K) {
+    return static_cast<size_t>(kTile) * K * 2 * (1 + kStages) + (1 + kStages) * kAugTileBytes + sizeof(BwdBars) + 64;
+}
+
 static size_t fwd_smem_bytes(int K) {
     return static_cast<size_t>(kTile) * K * 2 * (1 + kStages) + kStages * kCamTileBytes + sizeof(FwdBars) + 64;
 }
@@ -338,6 +582,39 @@ extern "C" int wsegk_pcm_fwd(const float* f, const float* cam_norm, float* cam_r
     }
     pcm_fwd_finalize_kernel<<<dim3(ceil_div(pl.HWp, 128), N), 128, 0, stream>>>(pl.part, cam_rv, pl.dsum, C,
                                                                                  pl.HW, pl.HWp, pl.nsplit);
+    WSEGK_CUDA_OK(cudaGetLastError());
+    return WSEGK_OK;
+}
+
+extern "C" int wsegk_pcm_bwd(const float* f, const float* cam_norm, const float* cam_rv, const float* grad_cam_rv,
+                             float* grad_f, int N, int C, int K, int h, int w, void* workspace,
+                             size_t workspace_bytes, wsegk_stream_t stream) {
+    if (int rc = check_device()) return rc;
+    WSEGK_REQUIRE(f && cam_norm && cam_rv && grad_cam_rv && grad_f && workspace, WSEGK_ERR_NULL,
+                  "pcm_bwd: null pointer");
+    if (int rc = pcm_check("pcm_bwd", N, C, K, h, w)) return rc;
+    WSEGK_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, WSEGK_ERR_BAD_ALIGN,
+                  "pcm_bwd: workspace must be 1024-byte aligned");
+    PcmPlan pl = make_pcm_plan(workspace, N, C, K, h, w);
+    WSEGK_REQUIRE(workspace_bytes >= pl.bytes, WSEGK_ERR_WORKSPACE_TOO_SMALL, "pcm_bwd: workspace %zu < %zu",
+                  workspace_bytes, pl.bytes);
+    pcm_bwd_prep_kernel<<<dim3(pl.T, N), 128, 0, stream>>>(cam_norm, cam_rv, grad_cam_rv, pl.dsum, pl.uaug,
+                                                           pl.vaug, C, pl.HW, pl.T, pl.HWp);
+    {
+        const size_t smem = bwd_smem_bytes(K);
+        WSEGK_CUDA_OK(cudaFuncSetAttribute(pcm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(smem)));
+        pcm_bwd_kernel<<<dim3(pl.T, pl.nsplit, N), kFwdThreads, smem, stream>>>(pl.fhat, pl.uaug, pl.vaug,
+                                                                                pl.dfhat, K, pl.T, pl.HWp,
+                                                                                pl.nsplit);
+    }
+    {
+        const size_t smem = static_cast<size_t>(K) * 129 * sizeof(float);
+        WSEGK_CUDA_OK(cudaFuncSetAttribute(pcm_bwd_post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(smem)));
+        pcm_bwd_post_kernel<<<dim3(pl.T, N), 256, smem, stream>>>(pl.dfhat, f, pl.inv_norm, grad_f, K, pl.HW,
+                                                                  pl.HWp, pl.nsplit);
+    }
     WSEGK_CUDA_OK(cudaGetLastError());
     return WSEGK_OK;
 }

@@ -1,0 +1,588 @@
+// K3 — per-class top-k of CAM-confident pixels + CAM-weighted prototypes   (contrast_train.py:199-209 / 229-241)
+// K4 — pixel-to-prototype NCE losses, forward and backward fused            (contrast_train.py:244-389)
+//
+// Selection semantics are canonical (value, then lowest flat index) so results are bit-reproducible; every
+// floating-point reduction is done in a fixed order (no float atomics).
+#include <algorithm>
+#include <cfloat>
+
+#include "common.cuh"
+
+namespace wsegk {
+
+// ================================================================================================
+// K3
+// ================================================================================================
+__device__ __forceinline__ uint32_t ordered_bits(float v) {
+    if (v == 0.f) v = 0.f;                       // -0 -> +0 (torch.sort treats them as equal)
+    uint32_t u = __float_as_uint(v);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float unordered_bits(uint32_t u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+// larger key == earlier in the canonical order (value desc, index asc); keys are unique
+__device__ __forceinline__ unsigned long long topk_key(float v, uint32_t idx) {
+    return (static_cast<unsigned long long>(ordered_bits(v)) << 32) | (0xFFFFFFFFu - idx);
+}
+
+// in-place bitonic sort of n (power of two) 64-bit keys in shared memory, descending, with an optional payload
+template <bool kPayload>
+__device__ void bitonic_desc(unsigned long long* keys, uint32_t* pay, int n) {
+    for (int size = 2; size <= n; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (int t = threadIdx.x; t < (n >> 1); t += blockDim.x) {
+                const int lo = 2 * t - (t & (stride - 1));
+                const int hi = lo + stride;
+                const bool desc = ((lo & size) == 0);
+                const unsigned long long a = keys[lo], b = keys[hi];
+                if ((a < b) == desc) {
+                    keys[lo] = b; keys[hi] = a;
+                    if (kPayload) { const uint32_t x = pay[lo]; pay[lo] = pay[hi]; pay[hi] = x; }
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+constexpr int kTopkThreads = 1024;
+constexpr int kTopkMaxK = 4096;
+
+// one CTA per class: radix-select the k largest keys over the whole batch plane, sort them, gather features
+__global__ void __launch_bounds__(kTopkThreads) proto_topk_kernel(const float* __restrict__ norm_cam,
+                                                                  const float* __restrict__ f_proj,
+                                                                  int pixel_offset, int k, int kpad,
+                                                                  float* __restrict__ top_val,
+                                                                  int32_t* __restrict__ top_idx,
+                                                                  float* __restrict__ top_fea, int N, int C,
+                                                                  int D, int HW) {
+    extern __shared__ unsigned long long s_keys[];      // kpad
+    __shared__ uint32_t s_hist[256];
+    __shared__ unsigned long long s_prefix;
+    __shared__ int s_need, s_done, s_count;
+    const int c = blockIdx.x;
+    const int P = N * HW;
+    auto value_at = [&](int i) {
+        const int n = i / HW, q = i - n * HW;
+        return __ldg(norm_cam + (static_cast<size_t>(n) * C + c) * HW + q);
+    };
+    if (threadIdx.x == 0) { s_prefix = 0ull; s_need = k; s_done = 0; s_count = 0; }
+    int shift = 56;
+    for (int pass = 0; pass < 8; ++pass) {
+        shift = 56 - 8 * pass;
+        for (int b = threadIdx.x; b < 256; b += blockDim.x) s_hist[b] = 0;
+        __syncthreads();
+        const unsigned long long prefix = s_prefix;
+        for (int i = threadIdx.x; i < P; i += blockDim.x) {
+            const unsigned long long key = topk_key(value_at(i), static_cast<uint32_t>(i));
+            if (pass == 0 || (key >> (shift + 8)) == prefix) atomicAdd(&s_hist[(key >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int need = s_need, cum = 0, digit = 0;
+            for (int b = 255; b >= 0; --b) {
+                const int hcount = static_cast<int>(s_hist[b]);
+                if (cum + hcount >= need) { digit = b; need -= cum; s_done = (hcount == need) ? 1 : 0; break; }
+                cum += hcount;
+            }
+            s_need = need;
+            s_prefix = (prefix << 8) | static_cast<unsigned long long>(digit);
+        }
+        __syncthreads();
+        if (s_done) break;
+    }
+    // every key whose top bits are >= the prefix is selected (exactly k of them)
+    const unsigned long long prefix = s_prefix;
+    for (int i = threadIdx.x; i < kpad; i += blockDim.x) s_keys[i] = 0ull;
+    __syncthreads();
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        const unsigned long long key = topk_key(value_at(i), static_cast<uint32_t>(i));
+        if ((key >> shift) >= prefix) {
+            const int slot = atomicAdd(&s_count, 1);
+            if (slot < kpad) s_keys[slot] = key;
+        }
+    }
+    bitonic_desc<false>(s_keys, nullptr, kpad);
+    for (int t = threadIdx.x; t < k; t += blockDim.x) {
+        const unsigned long long key = s_keys[t];
+        const uint32_t idx = 0xFFFFFFFFu - static_cast<uint32_t>(key & 0xFFFFFFFFull);
+        top_val[c * k + t] = value_at(static_cast<int>(idx));
+        top_idx[c * k + t] = static_cast<int32_t>(idx) + pixel_offset;
+    }
+    // gather the (un-normalised) features of the selected pixels: top_fea[c][t][d] = f_proj[n][d][q]
+    for (int e = threadIdx.x; e < k * D; e += blockDim.x) {
+        const int t = e / D, d = e - t * D;
+        const uint32_t idx = 0xFFFFFFFFu - static_cast<uint32_t>(s_keys[t] & 0xFFFFFFFFull);
+        const int n = idx / HW, q = idx - n * HW;
+        top_fea[(static_cast<size_t>(c) * k + t) * D + d] = __ldg(f_proj + (static_cast<size_t>(n) * D + d) * HW + q);
+    }
+}
+
+// one CTA per class: global top-k among n_cand candidates, prototype = sum(val*fea)/sum(val), L2-normalised
+__global__ void __launch_bounds__(1024) proto_finalize_kernel(const float* __restrict__ cand_val,
+                                                              const int32_t* __restrict__ cand_idx,
+                                                              const float* __restrict__ cand_fea, int n_cand,
+                                                              int npad, int k, float* __restrict__ proto,
+                                                              int32_t* __restrict__ sel_idx, int D) {
+    extern __shared__ unsigned long long s_buf[];
+    unsigned long long* s_keys = s_buf;                                   // npad
+    uint32_t* s_pos = reinterpret_cast<uint32_t*>(s_buf + npad);          // npad
+    __shared__ float s_red[32];
+    __shared__ float s_scale;
+    const int c = blockIdx.x;
+    for (int i = threadIdx.x; i < npad; i += blockDim.x) {
+        if (i < n_cand) {
+            s_keys[i] = topk_key(cand_val[c * n_cand + i], static_cast<uint32_t>(cand_idx[c * n_cand + i]));
+            s_pos[i] = i;
+        } else {
+            s_keys[i] = 0ull;
+            s_pos[i] = 0;
+        }
+    }
+    bitonic_desc<true>(s_keys, s_pos, npad);
+    for (int t = threadIdx.x; t < k; t += blockDim.x)
+        sel_idx[c * k + t] = static_cast<int32_t>(0xFFFFFFFFu - static_cast<uint32_t>(s_keys[t] & 0xFFFFFFFFull));
+    // weight sum (fixed order: thread 0 walks the sorted list)
+    if (threadIdx.x == 0) {
+        float wsum = 0.f;
+        for (int t = 0; t < k; ++t) wsum += cand_val[c * n_cand + s_pos[t]];
+        s_scale = wsum;
+    }
+    __syncthreads();
+    const float wsum = s_scale;
+    float sq = 0.f;
+    float mine[4] = {0.f, 0.f, 0.f, 0.f};          // D <= 4 * blockDim
+    int slot = 0;
+    for (int d = threadIdx.x; d < D; d += blockDim.x, ++slot) {
+        float acc = 0.f;
+        for (int t = 0; t < k; ++t) {
+            const uint32_t pos = s_pos[t];
+            acc = fmaf(cand_val[c * n_cand + pos], __ldg(cand_fea + (static_cast<size_t>(c) * n_cand + pos) * D + d), acc);
+        }
+        acc /= wsum;
+        mine[slot] = acc;
+        sq = fmaf(acc, acc, sq);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = sq;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float tot = 0.f;
+        for (int wv = 0; wv < (blockDim.x >> 5); ++wv) tot += s_red[wv];
+        s_scale = fmaxf(sqrtf(tot), 1e-12f);          // F.normalize eps
+    }
+    __syncthreads();
+    const float nrm = s_scale;
+    slot = 0;
+    for (int d = threadIdx.x; d < D; d += blockDim.x, ++slot) proto[c * D + d] = mine[slot] / nrm;
+}
+
+size_t proto_workspace_bytes(int, int, int, int) { return 1024; }
+
+// ================================================================================================
+// K4
+// ================================================================================================
+constexpr int kNceMaxC = 24;
+constexpr int kNceThreads = 128;
+constexpr float kInvT = 10.f;          // 1 / temperature 0.1
+
+struct NceView {
+    const float* x;            // [N,D,HW]
+    const float* proto_own;    // [C,D]
+    const float* proto_oth;
+    const int32_t* pl_own;     // [P]
+    const int32_t* pl_oth;
+    const uint32_t* rkey;      // [P]
+    float* grad_x;             // [N,D,HW]
+    int32_t* mined;            // [P] or null
+    // workspace (per view)
+    float* inv_norm;           // [P]
+    float* sim;                // [P]
+    float* ell;                // [P]  unweighted intra loss of the pixel
+    uint32_t* setmask;         // [P]  classes at ranks 3..12 of q.proto_own
+    float* s_own;              // [C][P]
+    float* s_oth;              // [C][P]
+    int* rank_sim;             // [P]
+    int* rank_rnd;             // [P]
+    int* cls_count;            // [32]
+    float* partial;            // [nblk][4]: cross, cross2, intra(weighted), unused
+};
+struct NceParams {
+    NceView v[2];
+    int N, C, D, HW, P, nblk;
+    const float* grad_scale;
+    float* losses;
+};
+
+// ---- A: per-pixel similarities and unweighted loss terms ----------------------------------------
+__global__ void __launch_bounds__(kNceThreads) nce_pixel_kernel(NceParams prm) {
+    extern __shared__ float s_proto[];               // own [C][D] then oth [C][D]
+    const NceView& V = prm.v[blockIdx.y];
+    const int C = prm.C, D = prm.D, HW = prm.HW, P = prm.P;
+    for (int i = threadIdx.x; i < C * D; i += blockDim.x) {
+        s_proto[i] = V.proto_own[i];
+        s_proto[C * D + i] = V.proto_oth[i];
+    }
+    __syncthreads();
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    float cross = 0.f, cross2 = 0.f;
+    if (p < P) {
+        const int n = p / HW, q = p - n * HW;
+        const float* xp = V.x + static_cast<size_t>(n) * D * HW + q;
+        float own[kNceMaxC], oth[kNceMaxC];
+#pragma unroll
+        for (int c = 0; c < kNceMaxC; ++c) { own[c] = 0.f; oth[c] = 0.f; }
+        float ss = 0.f;
+        for (int d = 0; d < D; ++d) {
+            const float xv = __ldg(xp + static_cast<size_t>(d) * HW);
+            ss = fmaf(xv, xv, ss);
+#pragma unroll
+            for (int c = 0; c < kNceMaxC; ++c) {
+                if (c < C) {
+                    own[c] = fmaf(xv, s_proto[c * D + d], own[c]);
+                    oth[c] = fmaf(xv, s_proto[(C + c) * D + d], oth[c]);
+                }
+            }
+        }
+        const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);          // F.normalize
+        const int lo = V.pl_own[p], lt = V.pl_oth[p];
+        float z_own = 0.f, z_oth = 0.f, pos_own = 0.f, pos_oth_lo = 0.f, pos_own_lt = 0.f;
+#pragma unroll
+        for (int c = 0; c < kNceMaxC; ++c) {
+            if (c < C) {
+                own[c] *= inv; oth[c] *= inv;
+                V.s_own[static_cast<size_t>(c) * P + p] = own[c];
+                V.s_oth[static_cast<size_t>(c) * P + p] = oth[c];
+                z_own += expf(own[c] * kInvT);
+                z_oth += expf(oth[c] * kInvT);
+                if (c == lo) { pos_own = own[c]; pos_oth_lo = oth[c]; }
+                if (c == lt) pos_own_lt = own[c];
+            }
+        }
+        // cross: other view's prototypes, own label (:261-267); cross2: own prototypes, other view's label (:272-279)
+        cross = logf(z_oth) - pos_oth_lo * kInvT;
+        cross2 = logf(z_own) - pos_own_lt * kInvT;
+        // intra (:285-299): positive + the prototypes at ranks 3..12 of q.proto_own (value desc, class asc)
+        uint32_t mask = 0u;
+        float a2 = expf(pos_own * kInvT);
+#pragma unroll
+        for (int c = 0; c < kNceMaxC; ++c) {
+            if (c < C) {
+                int rank = 0;
+#pragma unroll
+                for (int e = 0; e < kNceMaxC; ++e)
+                    if (e < C) rank += (own[e] > own[c] || (own[e] == own[c] && e < c)) ? 1 : 0;
+                if (rank >= 3 && rank < 13) { mask |= (1u << c); a2 += expf(own[c] * kInvT); }
+            }
+        }
+        V.setmask[p] = mask;
+        V.ell[p] = logf(a2) - pos_own * kInvT;
+        V.sim[p] = (pos_own + 1.f) * 0.5f;
+        V.inv_norm[p] = inv;
+        atomicAdd(&V.cls_count[lo], 1);
+    }
+    // deterministic block partials
+    __shared__ float s_a[kNceThreads / 32], s_b[kNceThreads / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        cross += __shfl_xor_sync(0xffffffffu, cross, o);
+        cross2 += __shfl_xor_sync(0xffffffffu, cross2, o);
+    }
+    if ((threadIdx.x & 31) == 0) { s_a[threadIdx.x >> 5] = cross; s_b[threadIdx.x >> 5] = cross2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = 0.f, b = 0.f;
+        for (int wv = 0; wv < kNceThreads / 32; ++wv) { a += s_a[wv]; b += s_b[wv]; }
+        V.partial[blockIdx.x * 4 + 0] = a;
+        V.partial[blockIdx.x * 4 + 1] = b;
+    }
+}
+
+// ---- B: ranks inside each pseudo-class (hard-pixel mining, :302-322) -----------------------------
+// rank_sim[p] = #{p' same class : (sim', p') < (sim, p)},  rank_rnd likewise on (key, p).  Integer atomics only.
+constexpr int kMineThreads = 256;
+constexpr int kMineChunk = 1024;
+__global__ void __launch_bounds__(kMineThreads) nce_mine_kernel(NceParams prm) {
+    const NceView& V = prm.v[blockIdx.z];
+    const int P = prm.P;
+    __shared__ int s_cls[kMineChunk];
+    __shared__ float s_sim[kMineChunk];
+    __shared__ uint32_t s_key[kMineChunk];
+    const int base = blockIdx.y * kMineChunk;
+    for (int i = threadIdx.x; i < kMineChunk; i += blockDim.x) {
+        const int pp = base + i;
+        s_cls[i] = pp < P ? V.pl_own[pp] : -1;
+        s_sim[i] = pp < P ? V.sim[pp] : 0.f;
+        s_key[i] = pp < P ? V.rkey[pp] : 0u;
+    }
+    __syncthreads();
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const int cls = V.pl_own[p];
+    const float sim = V.sim[p];
+    const uint32_t key = V.rkey[p];
+    int rs = 0, rr = 0;
+    const int lim = min(kMineChunk, P - base);
+    for (int i = 0; i < lim; ++i) {
+        if (s_cls[i] == cls) {
+            const int pp = base + i;
+            rs += (s_sim[i] < sim || (s_sim[i] == sim && pp < p)) ? 1 : 0;
+            rr += (s_key[i] < key || (s_key[i] == key && pp < p)) ? 1 : 0;
+        }
+    }
+    if (rs) atomicAdd(&V.rank_sim[p], rs);
+    if (rr) atomicAdd(&V.rank_rnd[p], rr);
+}
+
+// ---- C: weights, loss partials and gradient w.r.t. the un-normalised features ---------------------
+__global__ void __launch_bounds__(kNceThreads) nce_grad_kernel(NceParams prm) {
+    extern __shared__ float s_proto[];
+    const NceView& V = prm.v[blockIdx.y];
+    const int C = prm.C, D = prm.D, HW = prm.HW, P = prm.P;
+    for (int i = threadIdx.x; i < C * D; i += blockDim.x) {
+        s_proto[i] = V.proto_own[i];
+        s_proto[C * D + i] = V.proto_oth[i];
+    }
+    __shared__ int s_present;
+    if (threadIdx.x == 0) {
+        int pres = 0;
+        for (int c = 0; c < C; ++c) pres += V.cls_count[c] > 0 ? 1 : 0;
+        s_present = pres;
+    }
+    __syncthreads();
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    float intra = 0.f;
+    if (p < P) {
+        const int n = p / HW, q = p - n * HW;
+        const int lo = V.pl_own[p], lt = V.pl_oth[p];
+        const int len = V.cls_count[lo];
+        const int half = len >> 1;
+        int cnt = 0;
+        if (len >= 2) {
+            const int kk = static_cast<int>(static_cast<double>(len) * 0.6);      // int(len_class * 0.6)
+            const int rs = V.rank_sim[p], rr = V.rank_rnd[p];
+            cnt = (rr < half ? 1 : 0) + ((rs >= kk - half && rs < kk) ? 1 : 0);
+        }
+        if (V.mined) V.mined[p] = cnt;
+        const float w_x = 0.05f / static_cast<float>(P);                            // 0.1 * mean / 2
+        const float w_i = cnt ? 0.05f * static_cast<float>(cnt) /
+                                    (static_cast<float>(2 * half) * static_cast<float>(s_present))
+                              : 0.f;
+        intra = w_i * V.ell[p];
+        const uint32_t mask = V.setmask[p];
+        float a[kNceMaxC], b[kNceMaxC];
+        float z_own = 0.f, z_oth = 0.f, z_set = 0.f;
+#pragma unroll
+        for (int c = 0; c < kNceMaxC; ++c) {
+            if (c < C) {
+                a[c] = expf(V.s_own[static_cast<size_t>(c) * P + p] * kInvT);
+                b[c] = expf(V.s_oth[static_cast<size_t>(c) * P + p] * kInvT);
+                z_own += a[c];
+                z_oth += b[c];
+                const int mult = ((mask >> c) & 1u) + (c == lo ? 1 : 0);
+                z_set += static_cast<float>(mult) * a[c];
+            }
+        }
+        float qdq = 0.f;
+#pragma unroll
+        for (int c = 0; c < kNceMaxC; ++c) {
+            if (c < C) {
+                const int mult = ((mask >> c) & 1u) + (c == lo ? 1 : 0);
+                const float ac = w_x * (a[c] / z_own - (c == lt ? 1.f : 0.f)) +
+                                 w_i * (static_cast<float>(mult) * a[c] / z_set - (c == lo ? 1.f : 0.f));
+                const float bc = w_x * (b[c] / z_oth - (c == lo ? 1.f : 0.f));
+                qdq = fmaf(ac, V.s_own[static_cast<size_t>(c) * P + p], qdq);
+                qdq = fmaf(bc, V.s_oth[static_cast<size_t>(c) * P + p], qdq);
+                a[c] = ac * kInvT;
+                b[c] = bc * kInvT;
+            }
+        }
+        qdq *= kInvT;
+        const float inv = V.inv_norm[p];
+        const float gs = prm.grad_scale ? prm.grad_scale[0] : 1.f;
+        const float* xp = V.x + static_cast<size_t>(n) * D * HW + q;
+        float* gp = V.grad_x + static_cast<size_t>(n) * D * HW + q;
+        for (int d = 0; d < D; ++d) {
+            float dq = 0.f;
+#pragma unroll
+            for (int c = 0; c < kNceMaxC; ++c) {
+                if (c < C) {
+                    dq = fmaf(a[c], s_proto[c * D + d], dq);
+                    dq = fmaf(b[c], s_proto[(C + c) * D + d], dq);
+                }
+            }
+            const float qd = __ldg(xp + static_cast<size_t>(d) * HW) * inv;
+            gp[static_cast<size_t>(d) * HW] = (dq - qd * qdq) * inv * gs;
+        }
+    }
+    __shared__ float s_a[kNceThreads / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) intra += __shfl_xor_sync(0xffffffffu, intra, o);
+    if ((threadIdx.x & 31) == 0) s_a[threadIdx.x >> 5] = intra;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int wv = 0; wv < kNceThreads / 32; ++wv) t += s_a[wv];
+        V.partial[blockIdx.x * 4 + 2] = t;
+    }
+}
+
+// ---- D: fixed-order final sums ---------------------------------------------------------------------
+__global__ void nce_finalize_kernel(NceParams prm) {
+    if (threadIdx.x != 0) return;
+    float s[2][3];
+    for (int v = 0; v < 2; ++v) {
+        s[v][0] = s[v][1] = s[v][2] = 0.f;
+        for (int b = 0; b < prm.nblk; ++b)
+            for (int j = 0; j < 3; ++j) s[v][j] += prm.v[v].partial[b * 4 + j];
+    }
+    const float invP = 1.f / static_cast<float>(prm.P);
+    float* L = prm.losses;
+    L[0] = s[0][0] * invP;            // nce(q1, proto2, pl1)
+    L[1] = s[1][0] * invP;            // nce(q2, proto1, pl2)
+    L[2] = s[0][1] * invP;            // nce(q1, proto1, pl2)
+    L[3] = s[1][1] * invP;            // nce(q2, proto2, pl1)
+    L[4] = s[0][2] / 0.05f;           // loss_intra_nce1 (the partials carry the 0.1/2 weight)
+    L[5] = s[1][2] / 0.05f;
+    L[6] = 0.1f * (L[0] + L[1]) / 2.f;
+    L[7] = 0.1f * (L[2] + L[3]) / 2.f;
+    L[8] = 0.1f * (L[4] + L[5]) / 2.f;
+    L[9] = L[6] + L[7] + L[8];
+}
+
+struct NceLayout {
+    size_t per_view, total;
+    size_t off_inv, off_sim, off_ell, off_mask, off_sown, off_soth, off_rs, off_rr, off_cls, off_part;
+    int nblk;
+};
+static NceLayout nce_layout(int N, int C, int h, int w) {
+    NceLayout L{};
+    const size_t P = static_cast<size_t>(N) * h * w;
+    L.nblk = static_cast<int>((P + kNceThreads - 1) / kNceThreads);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    L.off_rs = take(P * 4);            // rank arrays + class counts first: one memset clears them
+    L.off_rr = take(P * 4);
+    L.off_cls = take(32 * 4);
+    L.off_inv = take(P * 4);
+    L.off_sim = take(P * 4);
+    L.off_ell = take(P * 4);
+    L.off_mask = take(P * 4);
+    L.off_sown = take(P * 4 * C);
+    L.off_soth = take(P * 4 * C);
+    L.off_part = take(static_cast<size_t>(L.nblk) * 4 * 4);
+    L.per_view = align_up(off, 1024);
+    L.total = 2 * L.per_view;
+    return L;
+}
+size_t contrast_workspace_bytes(int N, int C, int, int h, int w) { return nce_layout(N, C, h, w).total; }
+
+}  // namespace wsegk
+
+using namespace wsegk;
+
+static int next_pow2(int v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+extern "C" int wsegk_proto_topk_local(const float* norm_cam, const float* f_proj, int pixel_offset, int k,
+                                      float* top_val, int32_t* top_idx, float* top_fea, int N, int C, int D, int h,
+                                      int w, void* workspace, size_t workspace_bytes, wsegk_stream_t stream) {
+    (void)workspace; (void)workspace_bytes;
+    if (int rc = check_device()) return rc;
+    WSEGK_REQUIRE(norm_cam && f_proj && top_val && top_idx && top_fea, WSEGK_ERR_NULL, "proto_topk_local: null pointer");
+    WSEGK_REQUIRE(N > 0 && C > 0 && D > 0 && h > 0 && w > 0, WSEGK_ERR_BAD_SHAPE, "proto_topk_local: bad dims");
+    const long long P = static_cast<long long>(N) * h * w;
+    WSEGK_REQUIRE(k >= 1 && k <= P && k <= kTopkMaxK, WSEGK_ERR_BAD_SHAPE,
+                  "proto_topk_local: need 1 <= k <= min(P, %d) (k=%d, P=%lld)", kTopkMaxK, k, P);
+    WSEGK_REQUIRE(P + pixel_offset < (1ll << 31), WSEGK_ERR_BAD_SHAPE, "proto_topk_local: pixel index overflow");
+    const int kpad = next_pow2(k);
+    const size_t smem = static_cast<size_t>(kpad) * sizeof(unsigned long long);
+    WSEGK_CUDA_OK(cudaFuncSetAttribute(proto_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem)));
+    proto_topk_kernel<<<C, kTopkThreads, smem, stream>>>(norm_cam, f_proj, pixel_offset, k, kpad, top_val, top_idx,
+                                                         top_fea, N, C, D, h * w);
+    WSEGK_CUDA_OK(cudaGetLastError());
+    return WSEGK_OK;
+}
+
+extern "C" int wsegk_proto_finalize(const float* cand_val, const int32_t* cand_idx, const float* cand_fea, int n_cand,
+                                    int k, float* proto, int32_t* sel_idx, int C, int D, wsegk_stream_t stream) {
+    if (int rc = check_device()) return rc;
+    WSEGK_REQUIRE(cand_val && cand_idx && cand_fea && proto && sel_idx, WSEGK_ERR_NULL, "proto_finalize: null pointer");
+    WSEGK_REQUIRE(C > 0 && D > 0 && D <= 4096 && k >= 1 && k <= n_cand && n_cand <= 16384, WSEGK_ERR_BAD_SHAPE,
+                  "proto_finalize: need 1 <= k <= n_cand <= 16384, D <= 4096 (k=%d n_cand=%d D=%d)", k, n_cand, D);
+    const int npad = next_pow2(n_cand);
+    const size_t smem = static_cast<size_t>(npad) * (sizeof(unsigned long long) + sizeof(uint32_t));
+    WSEGK_CUDA_OK(cudaFuncSetAttribute(proto_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem)));
+    proto_finalize_kernel<<<C, 1024, smem, stream>>>(cand_val, cand_idx, cand_fea, n_cand, npad, k, proto, sel_idx, D);
+    WSEGK_CUDA_OK(cudaGetLastError());
+    return WSEGK_OK;
+}
+
+extern "C" int wsegk_contrast_loss_fwd_bwd(const float* x1, const float* x2, const float* proto1, const float* proto2,
+                                           const int32_t* pl1, const int32_t* pl2, const uint32_t* rand_key1,
+                                           const uint32_t* rand_key2, float* losses, float* grad_x1, float* grad_x2,
+                                           int32_t* mined1, int32_t* mined2, const float* grad_scale, int N, int C,
+                                           int D, int h, int w, void* workspace, size_t workspace_bytes,
+                                           wsegk_stream_t stream) {
+    if (int rc = check_device()) return rc;
+    WSEGK_REQUIRE(x1 && x2 && proto1 && proto2 && pl1 && pl2 && rand_key1 && rand_key2 && losses && grad_x1 &&
+                      grad_x2 && workspace,
+                  WSEGK_ERR_NULL, "contrast_loss_fwd_bwd: null pointer");
+    WSEGK_REQUIRE(N > 0 && h > 0 && w > 0 && D > 0 && C >= 13 && C <= kNceMaxC, WSEGK_ERR_BAD_SHAPE,
+                  "contrast_loss_fwd_bwd: need 13 <= C <= %d (semi-hard mining takes ranks 3..12), got C=%d",
+                  kNceMaxC, C);
+    const long long P = static_cast<long long>(N) * h * w;
+    WSEGK_REQUIRE(P <= (1 << 17), WSEGK_ERR_BAD_SHAPE,
+                  "contrast_loss_fwd_bwd: P=%lld pixels exceeds the pairwise mining limit of 131072", P);
+    const size_t proto_smem = static_cast<size_t>(2) * C * D * sizeof(float);
+    WSEGK_REQUIRE(proto_smem <= 200 * 1024, WSEGK_ERR_BAD_SHAPE, "contrast_loss_fwd_bwd: D too large");
+    const NceLayout L = nce_layout(N, C, h, w);
+    WSEGK_REQUIRE(workspace_bytes >= L.total, WSEGK_ERR_WORKSPACE_TOO_SMALL,
+                  "contrast_loss_fwd_bwd: workspace %zu < %zu", workspace_bytes, L.total);
+    NceParams prm{};
+    prm.N = N; prm.C = C; prm.D = D; prm.HW = h * w; prm.P = static_cast<int>(P); prm.nblk = L.nblk;
+    prm.grad_scale = grad_scale;
+    prm.losses = losses;
+    uint8_t* ws = static_cast<uint8_t*>(workspace);
+    for (int v = 0; v < 2; ++v) {
+        uint8_t* b = ws + v * L.per_view;
+        NceView& V = prm.v[v];
+        V.x = v ? x2 : x1;
+        V.proto_own = v ? proto2 : proto1;
+        V.proto_oth = v ? proto1 : proto2;
+        V.pl_own = v ? pl2 : pl1;
+        V.pl_oth = v ? pl1 : pl2;
+        V.rkey = v ? rand_key2 : rand_key1;
+        V.grad_x = v ? grad_x2 : grad_x1;
+        V.mined = v ? mined2 : mined1;
+        V.inv_norm = reinterpret_cast<float*>(b + L.off_inv);
+        V.sim = reinterpret_cast<float*>(b + L.off_sim);
+        V.ell = reinterpret_cast<float*>(b + L.off_ell);
+        V.setmask = reinterpret_cast<uint32_t*>(b + L.off_mask);
+        V.s_own = reinterpret_cast<float*>(b + L.off_sown);
+        V.s_oth = reinterpret_cast<float*>(b + L.off_soth);
+        V.rank_sim = reinterpret_cast<int*>(b + L.off_rs);
+        V.rank_rnd = reinterpret_cast<int*>(b + L.off_rr);
+        V.cls_count = reinterpret_cast<int*>(b + L.off_cls);
+        V.partial = reinterpret_cast<float*>(b + L.off_part);
+        WSEGK_CUDA_OK(cudaMemsetAsync(b + L.off_rs, 0, L.off_inv - L.off_rs, stream));
+    }
+    WSEGK_CUDA_OK(cudaFuncSetAttribute(nce_pixel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(proto_smem)));
+    WSEGK_CUDA_OK(cudaFuncSetAttribute(nce_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(proto_smem)));
+    nce_pixel_kernel<<<dim3(L.nblk, 2), kNceThreads, proto_smem, stream>>>(prm);
+    nce_mine_kernel<<<dim3(ceil_div(prm.P, kMineThreads), ceil_div(prm.P, kMineChunk), 2), kMineThreads, 0, stream>>>(prm);
+    nce_grad_kernel<<<dim3(L.nblk, 2), kNceThreads, proto_smem, stream>>>(prm);
+    nce_finalize_kernel<<<1, 32, 0, stream>>>(prm);
+    WSEGK_CUDA_OK(cudaGetLastError());
+    return WSEGK_OK;
+}

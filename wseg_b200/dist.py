@@ -1,0 +1,34 @@
+"""Data-parallel plumbing for the one collective on the path: the prototype candidate exchange
+(SURVEY.md §8e).  One process per GPU, ``torch.distributed`` (NCCL on GPUs, gloo in the CPU tests)."""
+from __future__ import annotations
+
+from typing import Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def rank_world(group=None) -> Tuple[int, int]:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def gather_candidates(top_val: torch.Tensor, top_idx: torch.Tensor, top_fea: torch.Tensor, group=None):
+    """All-gather every rank's [C,k] candidates (values, global pixel ids, features) and concatenate them in rank
+    order along dim 1 -> [C, R*k(,D)].  Same bytes on every rank, so the finalised prototypes are bit-identical."""
+    _, world = rank_world(group)
+    c, k = top_val.shape
+    d = top_fea.shape[-1]
+    # one packed message per rank: [C, k, D + 2] (value, index bits, features)
+    packed = torch.empty(c, k, d + 2, dtype=torch.float32, device=top_val.device)
+    packed[:, :, 0] = top_val
+    packed[:, :, 1] = top_idx.view(torch.float32)
+    packed[:, :, 2:] = top_fea
+    out = torch.empty(world, c, k, d + 2, dtype=torch.float32, device=top_val.device)
+    dist.all_gather_into_tensor(out, packed, group=group)
+    out = out.permute(1, 0, 2, 3).reshape(c, world * k, d + 2)
+    val = out[:, :, 0].contiguous()
+    idx = out[:, :, 1].contiguous().view(torch.int32)
+    fea = out[:, :, 2:].contiguous()
+    return val, idx, fea

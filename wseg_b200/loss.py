@@ -1,0 +1,143 @@
+"""The contrast training-step loss as a function (the reference has it inline, contrast_train.py:129-395).
+
+``contrast_step_loss`` takes what ``Net.forward`` returns for both views plus the image-level labels and
+returns the 8 scalars the reference logs (contrast_train.py:111-118).  The hot path — label-masked CAM
+normalisation (K1b), seed labels (K1c), per-class top-k prototypes (K3) and the six NCE terms with hard-pixel
+mining, forward and backward fused (K4) — runs in the wsegk CUDA kernels; the two bilinear shrinks of view 1
+(:179-180) and the auxiliary SEAM losses (:142-144,156,159-174; SURVEY.md §8f-1 "next") stay in PyTorch.
+"""
+from __future__ import annotations
+
+import random as _pyrandom
+from typing import Dict, Optional, Tuple, Union
+
+import torch
+import torch.nn.functional as F
+
+from . import ops
+
+LOSS_KEYS = ('loss', 'loss_cls', 'loss_er', 'loss_ecr', 'loss_nce', 'loss_intra_nce',
+             'loss_cross_nce', 'loss_cross_nce2')          # contrast_train.py:111-118
+
+
+def reference_rng_keys(pl1: torch.Tensor, pl2: torch.Tensor, rng: Union[int, _pyrandom.Random, None],
+                       n_classes: int = 21) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Mining keys that reproduce the reference's Python-RNG draws (contrast_train.py:291,316,344,370): per view,
+    P dead ``sample(range(21),10)`` calls, then ``sample(range(len), len//2)`` for each class with >= 2 pixels in
+    ascending class order; view 1 before view 2.  Chosen pixels get key 0, the others key 1, so the kernel's rule
+    "the len//2 smallest (key, index)" selects exactly the reference's random half.  Needs the pseudo labels on
+    the host (one sync) — the default device-hash keys (``ops.hash_keys``) do not."""
+    if not isinstance(rng, _pyrandom.Random):
+        rng = _pyrandom.Random(rng)
+    keys = []
+    for pl in (pl1, pl2):
+        pl_h = pl.detach().to("cpu", torch.int64)
+        for _ in range(pl_h.numel()):
+            rng.sample(range(n_classes), 10)
+        key = torch.ones(pl_h.numel(), dtype=torch.int32)
+        for c in range(n_classes):
+            members = torch.nonzero(pl_h == c).reshape(-1)
+            ln = int(members.numel())
+            if ln < 2:
+                continue
+            picks = rng.sample(range(ln), ln // 2)
+            key[members[torch.as_tensor(picks, dtype=torch.long)]] = 0
+        keys.append(key.to(pl.device))
+    return keys[0], keys[1]
+
+
+def contrast_terms(f_proj1: torch.Tensor, cam_rv1_down: torch.Tensor, f_proj2: torch.Tensor,
+                   cam_rv2_down: torch.Tensor, label: torch.Tensor, bg_threshold: float,
+                   grid: Optional[Tuple[int, int]] = None, rng: Union[int, _pyrandom.Random, None] = None,
+                   mining_seed: int = 0, group=None, want_mined: bool = False) -> Dict[str, torch.Tensor]:
+    """contrast_train.py:176-392.  ``label``: [N,21] (or [N,21,1,1]) with background = 1.
+    ``rng``: None -> device-hash mining keys (no host sync); an int / ``random.Random`` -> reproduce the reference's
+    Python-RNG draws.  ``group``: process group over which prototypes are whole-batch (data parallel)."""
+    if grid is None:
+        grid = tuple(f_proj2.shape[-2:])
+    if tuple(f_proj1.shape[-2:]) != tuple(grid):
+        f1 = F.interpolate(f_proj1, size=grid, mode='bilinear', align_corners=True)           # :179
+        c1 = F.interpolate(cam_rv1_down, size=grid, mode='bilinear', align_corners=True)      # :180
+    else:
+        f1, c1 = f_proj1, cam_rv1_down
+    f2, c2 = f_proj2, cam_rv2_down
+    norm1, pl1 = ops.seed_labels(c1, label, bg_threshold)
+    norm2, pl2 = ops.seed_labels(c2, label, bg_threshold)
+    proto1, ti1 = ops.prototypes(norm1, f1, group=group)
+    proto2, ti2 = ops.prototypes(norm2, f2, group=group)
+    if rng is None:
+        p = pl1.numel()
+        key1 = ops.hash_keys(p, 2 * mining_seed + 1, pl1.device)
+        key2 = ops.hash_keys(p, 2 * mining_seed + 2, pl1.device)
+    else:
+        key1, key2 = reference_rng_keys(pl1, pl2, rng, proto1.shape[0])
+    out: Dict[str, torch.Tensor] = {}
+    if want_mined:
+        losses, g1, g2, m1, m2 = ops.contrast_loss_raw(f1, f2, proto1, proto2, pl1, pl2, key1, key2, want_mined=True)
+        out.update({'grad_f1': g1, 'grad_f2': g2, 'mined1': m1, 'mined2': m2})
+    else:
+        losses = ops.contrast_loss(f1, f2, proto1, proto2, pl1, pl2, key1, key2)
+    out.update({
+        'loss_nce': losses[9], 'loss_intra_nce': losses[8], 'loss_cross_nce': losses[6],
+        'loss_cross_nce2': losses[7], 'losses_raw': losses,
+        'pseudo_label1': pl1, 'pseudo_label2': pl2, 'norm_cam1': norm1, 'norm_cam2': norm2,
+        'top_indices1': ti1, 'top_indices2': ti2, 'prototypes1': proto1, 'prototypes2': proto2,
+    })
+    return out
+
+
+# ---- auxiliary SEAM losses, PyTorch (contrast_train.py:16-32,142-144,156,159-174) ------------------
+def _min_pool_loss(x: torch.Tensor) -> torch.Tensor:
+    n, c, h, w = x.shape
+    k = h * w // 4
+    low = torch.topk(x.max(dim=1)[0].reshape(n, -1), k=k, dim=-1, largest=False)[0]
+    return F.relu(low).sum() / (k * n)
+
+
+def _argmax_fg_only(x: torch.Tensor) -> torch.Tensor:
+    fg = x[:, 1:]
+    peak = fg.max(dim=1, keepdim=True)[0]
+    return torch.cat([x[:, :1], torch.where(fg != peak, torch.zeros_like(fg), fg)], dim=1)
+
+
+def _with_bg(cam: torch.Tensor) -> torch.Tensor:
+    return torch.cat([1.0 - cam[:, 1:].max(dim=1, keepdim=True)[0], cam[:, 1:]], dim=1)
+
+
+def contrast_step_loss(cam1, cam_rv1, f_proj1, cam_rv1_down, cam2, cam_rv2, f_proj2, cam_rv2_down,
+                       label20: torch.Tensor, bg_threshold: float = 0.20,
+                       view2_size: Tuple[int, int] = (128, 128),
+                       rng: Union[int, _pyrandom.Random, None] = None, mining_seed: int = 0,
+                       group=None) -> Dict[str, torch.Tensor]:
+    """Everything in contrast_train.py:138-395 given both views' network outputs.  ``label20``: [N,20] multi-hot.
+    Differentiable w.r.t. the eight network outputs; returns the 8 logged scalars (plus diagnostics)."""
+    n = label20.shape[0]
+    label = torch.cat([torch.ones(n, 1, dtype=torch.float32, device=cam1.device),
+                       label20.to(cam1.device, torch.float32)], dim=1)
+    lab4 = label.reshape(n, -1, 1, 1)
+    gap1 = F.adaptive_avg_pool2d(cam1, (1, 1))                                            # :142
+    rvmin1 = _min_pool_loss((cam_rv1 * lab4)[:, 1:])                                      # :143
+    n1 = ops.fullres_norm(cam1, label, view2_size)                                        # :145-148  (K1b)
+    rv1 = ops.fullres_norm(cam_rv1, label, view2_size)                                    # :149-152  (K1b)
+    gap2 = F.adaptive_avg_pool2d(cam2, (1, 1))                                            # :155
+    rvmin2 = _min_pool_loss((cam_rv2 * lab4)[:, 1:])                                      # :156
+    n2 = ops.fullres_norm(cam2, label, None)                                              # :157      (K1b)
+    rv2 = ops.fullres_norm(cam_rv2, label, None)                                          # :158      (K1b)
+    cls1 = F.multilabel_soft_margin_loss(gap1[:, 1:], lab4[:, 1:])                        # :159
+    cls2 = F.multilabel_soft_margin_loss(gap2[:, 1:], lab4[:, 1:])                        # :160
+    ns, cs, hs, ws = n2.shape
+    loss_er = torch.mean(torch.abs(n1[:, 1:] - n2[:, 1:]))                                # :163
+    n1b, n2b = _with_bg(n1), _with_bg(n2)                                                 # :165-166
+    k_ecr = int(21 * hs * ws * 0.2)
+    e1 = torch.abs(_argmax_fg_only(n2b.detach()) - rv1)                                   # :168
+    e2 = torch.abs(_argmax_fg_only(n1b.detach()) - rv2)                                   # :169
+    loss_ecr = (torch.mean(torch.topk(e1.reshape(ns, -1), k=k_ecr, dim=-1)[0])
+                + torch.mean(torch.topk(e2.reshape(ns, -1), k=k_ecr, dim=-1)[0]))         # :170-172
+    loss_cls = (cls1 + cls2) / 2 + (rvmin1 + rvmin2) / 2                                  # :174
+    grid = (view2_size[0] // 8, view2_size[1] // 8)                                       # :179
+    terms = contrast_terms(f_proj1, cam_rv1_down, f_proj2, cam_rv2_down, label, bg_threshold, grid=grid,
+                           rng=rng, mining_seed=mining_seed, group=group)
+    out = dict(terms)
+    out.update({'loss': loss_cls + loss_er + loss_ecr + terms['loss_nce'], 'loss_cls': loss_cls,
+                'loss_er': loss_er, 'loss_ecr': loss_ecr})
+    return out

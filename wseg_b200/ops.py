@@ -109,3 +109,185 @@ def pcm_layout(n: int, c: int, k: int, h: int, w: int) -> dict:
     got = _lib.lib().wsegk_debug_pcm_layout(n, c, k, h, w, buf, 12)
     names = ["fhat", "camb", "inv_norm", "dsum", "part", "uaug", "vaug", "dfhat", "bytes", "nsplit", "T", "HWp"]
     return {names[i]: int(buf[i]) for i in range(got)}
+
+
+# --------------------------------------------------------------------------------------------- K1b
+def _label_nc(label: torch.Tensor, n: int, c: int) -> torch.Tensor:
+    lab = label.detach().reshape(n, -1).to(torch.float32)
+    if lab.shape[1] != c:
+        raise RuntimeError(f"label has {lab.shape[1]} classes per image, tensor has {c} channels")
+    return lab.contiguous()
+
+
+class _FullresNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, p, label, size):
+        p = _require_cuda_f32("p", p)
+        n, c, H, W = p.shape
+        oh, ow = (H, W) if size is None else (int(size[0]), int(size[1]))
+        lab = _label_nc(label, n, c).to(p.device)
+        out = torch.empty(n, c, oh, ow, dtype=torch.float32, device=p.device)
+        minmax = torch.empty(n, c, 4, dtype=torch.float32, device=p.device)
+        with torch.cuda.device(p.device):
+            ws = _workspace(_lib.OP_FULLRES_NORM, p.device, N=n, C=c, h=H, w=W)
+            check(_lib.lib().wsegk_fullres_norm_fwd(_ptr(p), _ptr(lab), _ptr(out), _ptr(minmax), n, c, H, W, oh, ow,
+                                                    _ptr(ws), ws.numel(), _stream(p)), "wsegk_fullres_norm_fwd")
+        ctx.save_for_backward(p, lab, minmax)
+        ctx.dims = (n, c, H, W, oh, ow)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        p, lab, minmax = ctx.saved_tensors
+        n, c, H, W, oh, ow = ctx.dims
+        grad_out = _require_cuda_f32("grad_out", grad_out)
+        grad_p = torch.empty_like(p)
+        with torch.cuda.device(p.device):
+            ws = _workspace(_lib.OP_FULLRES_NORM, p.device, N=n, C=c, h=H, w=W)
+            check(_lib.lib().wsegk_fullres_norm_bwd(_ptr(p), _ptr(lab), _ptr(minmax), _ptr(grad_out), _ptr(grad_p),
+                                                    n, c, H, W, oh, ow, _ptr(ws), ws.numel(), _stream(p)),
+                  "wsegk_fullres_norm_bwd")
+        return grad_p, None, None
+
+
+def fullres_norm(p: torch.Tensor, label: torch.Tensor, size: Optional[Tuple[int, int]] = None) -> torch.Tensor:
+    """visualization.max_norm(p) -> bilinear(align_corners) to ``size`` -> * label
+    (tool/visualization.py:62-67, contrast_train.py:145-152,157-158).  label: [N,C] or [N,C,1,1]."""
+    return _FullresNorm.apply(p, label, size)
+
+
+# --------------------------------------------------------------------------------------------- K1c
+def seed_labels(cam_rv_down: torch.Tensor, label: torch.Tensor, bg_threshold: float
+                ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """contrast_train.py:186-197.  Returns (norm_cam [N,C,g,g] with channel 0 = bg_threshold,
+    pseudo_label [N*g*g] int32)."""
+    x = _require_cuda_f32("cam_rv_down", cam_rv_down.detach())
+    n, c, h, w = x.shape
+    lab = _label_nc(label, n, c).to(x.device)
+    norm = torch.empty_like(x)
+    pseudo = torch.empty(n * h * w, dtype=torch.int32, device=x.device)
+    with torch.cuda.device(x.device):
+        ws = _workspace(_lib.OP_SEED_LABELS, x.device, N=n, C=c, h=h, w=w)
+        check(_lib.lib().wsegk_seed_labels_fwd(_ptr(x), _ptr(lab), float(bg_threshold), _ptr(norm), _ptr(pseudo),
+                                               n, c, h, w, _ptr(ws), ws.numel(), _stream(x)),
+              "wsegk_seed_labels_fwd")
+    return norm, pseudo
+
+
+# --------------------------------------------------------------------------------------------- K3
+def proto_topk_local(norm_cam: torch.Tensor, f_proj: torch.Tensor, k: Optional[int] = None,
+                     pixel_offset: int = 0):
+    """This rank's k best pixels per class: (top_val [C,k], top_idx [C,k] int32 global pixel ids,
+    top_fea [C,k,D])."""
+    norm_cam = _require_cuda_f32("norm_cam", norm_cam.detach())
+    f_proj = _require_cuda_f32("f_proj", f_proj.detach())
+    n, c, h, w = norm_cam.shape
+    d = f_proj.shape[1]
+    if k is None:
+        k = h * w // 8
+    dev = norm_cam.device
+    tv = torch.empty(c, k, dtype=torch.float32, device=dev)
+    ti = torch.empty(c, k, dtype=torch.int32, device=dev)
+    tf = torch.empty(c, k, d, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        ws = _workspace(_lib.OP_PROTO, dev, N=n, C=c, D=d, h=h, w=w)
+        check(_lib.lib().wsegk_proto_topk_local(_ptr(norm_cam), _ptr(f_proj), int(pixel_offset), int(k), _ptr(tv),
+                                                _ptr(ti), _ptr(tf), n, c, d, h, w, _ptr(ws), ws.numel(),
+                                                _stream(norm_cam)), "wsegk_proto_topk_local")
+    return tv, ti, tf
+
+
+def proto_finalize(cand_val: torch.Tensor, cand_idx: torch.Tensor, cand_fea: torch.Tensor, k: int):
+    """Global top-k among candidates [C,n_cand] (+features [C,n_cand,D]) -> (prototypes [C,D], sel_idx [C,k])."""
+    cand_val = _require_cuda_f32("cand_val", cand_val)
+    cand_fea = _require_cuda_f32("cand_fea", cand_fea)
+    cand_idx = cand_idx.to(torch.int32).contiguous()
+    c, n_cand = cand_val.shape
+    d = cand_fea.shape[-1]
+    dev = cand_val.device
+    proto = torch.empty(c, d, dtype=torch.float32, device=dev)
+    sel = torch.empty(c, k, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.lib().wsegk_proto_finalize(_ptr(cand_val), _ptr(cand_idx), _ptr(cand_fea), n_cand, int(k),
+                                              _ptr(proto), _ptr(sel), c, d, _stream(cand_val)),
+              "wsegk_proto_finalize")
+    return proto, sel
+
+
+def prototypes(norm_cam: torch.Tensor, f_proj: torch.Tensor, k: Optional[int] = None, group=None):
+    """contrast_train.py:199-209 with whole-batch semantics.  With a process group the batch is the union of all
+    ranks' shards (rank r owns pixels [r*P_local, (r+1)*P_local)): local candidates are all-gathered (the only
+    collective on the path) and every rank finalises the same global prototypes, bit-identically.
+    Returns (prototypes [C,D], top_idx [C,k] int32 global pixel ids)."""
+    n, c, h, w = norm_cam.shape
+    if k is None:
+        k = h * w // 8
+    from . import dist as _dist
+    rank, world = _dist.rank_world(group)
+    tv, ti, tf = proto_topk_local(norm_cam, f_proj, k, pixel_offset=rank * n * h * w)
+    if world > 1:
+        tv, ti, tf = _dist.gather_candidates(tv, ti, tf, group)
+    return proto_finalize(tv, ti, tf, k)
+
+
+# --------------------------------------------------------------------------------------------- K4
+LOSS_SLOTS = ("nce_q1_p2_l1", "nce_q2_p1_l2", "nce_q1_p1_l2", "nce_q2_p2_l1", "intra1", "intra2",
+              "loss_cross_nce", "loss_cross_nce2", "loss_intra_nce", "loss_nce")
+
+
+def hash_keys(n_pixels: int, seed: int, device) -> torch.Tensor:
+    """Per-pixel uint32 keys for the 'random 50 %' of the hard-pixel mining (stored as int32 bit patterns)."""
+    g = torch.Generator(device="cpu")
+    g.manual_seed(int(seed))
+    keys = torch.randint(-2 ** 31, 2 ** 31 - 1, (n_pixels,), dtype=torch.int64, generator=g).to(torch.int32)
+    return keys.to(device)
+
+
+def contrast_loss_raw(x1, x2, proto1, proto2, pl1, pl2, key1, key2, grad_scale: Optional[torch.Tensor] = None,
+                      want_mined: bool = False):
+    """One call of wsegk_contrast_loss_fwd_bwd.  Returns (losses [10], grad_x1, grad_x2, mined1, mined2)."""
+    x1 = _require_cuda_f32("x1", x1.detach())
+    x2 = _require_cuda_f32("x2", x2.detach())
+    n, d, h, w = x1.shape
+    if tuple(x2.shape) != (n, d, h, w):
+        raise RuntimeError("contrast loss: both views must be on the same grid "
+                           f"(got {tuple(x1.shape)} vs {tuple(x2.shape)}; contrast_train.py:179-180)")
+    c = proto1.shape[0]
+    dev = x1.device
+    losses = torch.empty(10, dtype=torch.float32, device=dev)
+    g1 = torch.empty_like(x1)
+    g2 = torch.empty_like(x2)
+    m1 = torch.empty(n * h * w, dtype=torch.int32, device=dev) if want_mined else None
+    m2 = torch.empty(n * h * w, dtype=torch.int32, device=dev) if want_mined else None
+    args = [_require_cuda_f32("proto1", proto1), _require_cuda_f32("proto2", proto2),
+            pl1.to(torch.int32).contiguous(), pl2.to(torch.int32).contiguous(),
+            key1.to(torch.int32).contiguous(), key2.to(torch.int32).contiguous()]
+    with torch.cuda.device(dev):
+        ws = _workspace(_lib.OP_CONTRAST_LOSS, dev, N=n, C=c, D=d, h=h, w=w)
+        check(_lib.lib().wsegk_contrast_loss_fwd_bwd(
+            _ptr(x1), _ptr(x2), *[_ptr(a) for a in args], _ptr(losses), _ptr(g1), _ptr(g2), _ptr(m1), _ptr(m2),
+            _ptr(grad_scale), n, c, d, h, w, _ptr(ws), ws.numel(), _stream(x1)), "wsegk_contrast_loss_fwd_bwd")
+    return losses, g1, g2, m1, m2
+
+
+class _ContrastLoss(torch.autograd.Function):
+    """losses[10] as a differentiable function of (x1, x2); the gradient of ``loss_nce`` (slot 9) is produced by
+    the same fused call, so backward only rescales it.  The other slots are reported values (no gradient)."""
+
+    @staticmethod
+    def forward(ctx, x1, x2, proto1, proto2, pl1, pl2, key1, key2):
+        losses, g1, g2, _, _ = contrast_loss_raw(x1, x2, proto1, proto2, pl1, pl2, key1, key2)
+        ctx.save_for_backward(g1, g2)
+        return losses
+
+    @staticmethod
+    def backward(ctx, grad_losses):
+        g1, g2 = ctx.saved_tensors
+        # d(loss_nce) flows through slot 9; slots 6,7,8 are its parts and may carry gradient too when a caller
+        # sums them instead — support the reference's usage (only loss_nce enters the total, :392-395).
+        scale = grad_losses[9]
+        return g1 * scale, g2 * scale, None, None, None, None, None, None
+
+
+def contrast_loss(x1, x2, proto1, proto2, pl1, pl2, key1, key2) -> torch.Tensor:
+    return _ContrastLoss.apply(x1, x2, proto1, proto2, pl1, pl2, key1, key2)
