@@ -1,0 +1,77 @@
+"""Host-side logic that needs no GPU: reference-RNG mining keys, network surface, candidate exchange semantics."""
+import json
+import os
+import random
+
+import numpy as np
+import torch
+
+from oracle import reference_fn as R
+from wseg_b200 import loss as L
+from wseg_b200 import ops
+
+
+def _select_by_keys(pl, key, c):
+    members = torch.nonzero(pl == c).reshape(-1)
+    ln = members.numel()
+    order = sorted(range(ln), key=lambda i: (int(key[members[i]]) & 0xFFFFFFFF, int(members[i])))
+    return set(int(members[i]) for i in order[: ln // 2])
+
+
+def test_reference_rng_keys_reproduce_python_draws():
+    g = torch.Generator().manual_seed(3)
+    pl1 = torch.randint(0, 21, (300,), generator=g)
+    pl2 = torch.randint(0, 5, (300,), generator=g)
+    pl2[7] = 20                                   # a class with a single pixel: skipped, no draw consumed
+    k1, k2 = L.reference_rng_keys(pl1, pl2, 11)
+    sampler = R.ReferenceSampler(11)
+    for pl, key in ((pl1, k1), (pl2, k2)):
+        sampler.burn_dead_draws(pl.numel())
+        sim = torch.zeros(pl.numel())
+        _, sets = R.hard_pixel_sets(sim, pl, 21, sampler)
+        for c, rnd, _hard in sets:
+            assert set(rnd.tolist()) == _select_by_keys(pl, key, c), c
+    # the same object can be a shared random.Random (the driver's --reference-rng mode)
+    rng = random.Random(11)
+    k1b, _ = L.reference_rng_keys(pl1, pl2, rng)
+    assert torch.equal(k1, k1b)
+
+
+def test_hash_keys_deterministic():
+    a = ops.hash_keys(1000, 5, "cpu")
+    b = ops.hash_keys(1000, 5, "cpu")
+    c = ops.hash_keys(1000, 6, "cpu")
+    assert torch.equal(a, b) and not torch.equal(a, c) and a.dtype == torch.int32
+
+
+def test_net_surface_matches_reference_checkpoint_format(golden_dir):
+    from wseg_b200.network import resnet38_contrast
+    net = resnet38_contrast.Net()
+    want = json.load(open(os.path.join(golden_dir, "state_dict_shapes.json")))
+    got = {k: list(v.shape) for k, v in net.state_dict().items()}
+    assert list(got) == list(want) and got == want
+    net.train()
+    groups = net.get_parameter_groups()
+    assert [len(g) for g in groups] == [35, 0, 5, 0]
+    assert all(not m.training for m in net.modules() if isinstance(m, torch.nn.BatchNorm2d))
+    assert not net.conv1a.weight.requires_grad and not net.b2_2.conv_branch2a.weight.requires_grad
+    assert net.f9.weight.requires_grad and net.f9.weight.shape == (192, 195, 1, 1)
+    assert hasattr(net, "normalize") and hasattr(net, "PCM") and len(net.from_scratch_layers) == 5
+
+
+def test_union_of_local_topk_contains_global_topk():
+    """The exchange step relies on: global top-k (canonical order) is a subset of the ranks' local top-k's."""
+    g = torch.Generator().manual_seed(0)
+    c, p_local, world, k = 5, 64, 4, 8
+    planes = [torch.randint(0, 6, (c, p_local), generator=g).float() / 5 for _ in range(world)]   # many ties
+    full = torch.cat(planes, dim=1)
+    gv, gi = R.canonical_topk(full, k)
+    cand_v, cand_i = [], []
+    for r, pl in enumerate(planes):
+        v, i = R.canonical_topk(pl, k)
+        cand_v.append(v)
+        cand_i.append(i + r * p_local)
+    cv, ci = torch.cat(cand_v, 1), torch.cat(cand_i, 1)
+    order = np.lexsort((ci.numpy(), -cv.numpy()), axis=1)[:, :k]
+    sel_i = np.take_along_axis(ci.numpy(), order, 1)
+    assert np.array_equal(sel_i, gi.numpy())

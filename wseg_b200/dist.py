@@ -25,9 +25,9 @@ def gather_candidates(top_val: torch.Tensor, top_idx: torch.Tensor, top_fea: tor
     packed[:, :, 0] = top_val
     packed[:, :, 1] = top_idx.view(torch.float32)
     packed[:, :, 2:] = top_fea
-    out = torch.empty(world, c, k, d + 2, dtype=torch.float32, device=top_val.device)
+    out = torch.empty(world * c, k, d + 2, dtype=torch.float32, device=top_val.device)   # rank-major concat
     dist.all_gather_into_tensor(out, packed, group=group)
-    out = out.permute(1, 0, 2, 3).reshape(c, world * k, d + 2)
+    out = out.reshape(world, c, k, d + 2).permute(1, 0, 2, 3).reshape(c, world * k, d + 2)
     val = out[:, :, 0].contiguous()
     idx = out[:, :, 1].contiguous().view(torch.int32)
     fea = out[:, :, 2:].contiguous()
