@@ -1,0 +1,437 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json's metric on BASELINE.json's config.
+
+metric   : "contrast_hot_path_mpix_per_s" — stride-8 feature-map pixels of view 1 (N*56*56 per step) pushed through
+           the whole Step-1 contrast hot path per second: K1a CAM norm -> K2 PCM fwd -> K1c seeds -> K3 prototypes
+           -> K4 NCE losses fwd+bwd -> K1b full-res norm fwd+bwd -> K2 PCM bwd, both views.
+workload : configs[1] — batch 8 per GPU @448x448 (56x56 features, K=192, D=128, view 2 = 128x128 -> 16x16 grid),
+           head-level synthetic inputs (no backbone), seeded.  N GPUs = N x 8 images (weak scaling), prototypes
+           whole-batch via one NCCL all-gather per view.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    torchrun --nproc-per-node N bench.py --gpus N ...          (one rank per GPU)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.nn.functional as F  # noqa: E402
+
+METRIC = "contrast_hot_path_mpix_per_s"
+UNIT = "Mpix/s"
+N_PER_GPU = 8
+VIEW1 = (448, 448)
+VIEW2 = (128, 128)
+K_PCM, C_CLS, D_PROJ = 192, 21, 128
+BG_THRESHOLD = 0.20
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# ------------------------------------------------------------------------------------------------ workload
+def host_inputs(n: int, seed: int):
+    """Head-level synthetic inputs on the host (pinned), per SURVEY.md 8d."""
+    from wseg_b200 import synth
+    g = synth.gen(seed)
+    out = {}
+    for v, (H, W) in (("1", VIEW1), ("2", VIEW2)):
+        h, w = H // 8, W // 8
+        out["cam" + v] = 0.05 * torch.randn(n, C_CLS, h, w, generator=g)
+        out["f" + v] = torch.randn(n, K_PCM, h, w, generator=g)
+        out["fproj" + v] = F.relu(0.02 * torch.randn(n, D_PROJ, h, w, generator=g) + 0.01)
+        out["g_rv_down" + v] = 1e-3 * torch.randn(n, C_CLS, h, w, generator=g)
+    for name in ("g_n1", "g_rv1", "g_n2", "g_rv2"):
+        out[name] = 1e-3 * torch.randn(n, C_CLS, VIEW2[0], VIEW2[1], generator=g)
+    out["label"] = synth.label_with_bg(synth.labels(n, seed + 1))
+    return {k: v.contiguous().pin_memory() if torch.cuda.is_available() else v.contiguous() for k, v in out.items()}
+
+
+class HotPath:
+    """One step of the hot path on resident inputs, straight through the C-ABI operators (wseg_b200.ops)."""
+
+    def __init__(self, n: int, dev, seed: int, group=None):
+        from wseg_b200 import ops
+        self.ops, self.n, self.dev, self.group = ops, n, dev, group
+        self.host = host_inputs(n, seed)
+        self.d = {k: v.to(dev) for k, v in self.host.items()}
+        d = self.d
+        # full-resolution cam / cam_rv as Net.forward emits them (bilinear x8 of the stride-8 maps), resident
+        with torch.no_grad():
+            d["cam1_full"] = F.interpolate(d["cam1"], VIEW1, mode="bilinear", align_corners=True)
+            d["cam2_full"] = F.interpolate(d["cam2"], VIEW2, mode="bilinear", align_corners=True)
+            camn = ops.cam_norm(d["cam1"])
+            rv, _ = ops.pcm_forward(camn, d["f1"])
+            d["rv1_full"] = F.interpolate(rv, VIEW1, mode="bilinear", align_corners=True)
+            camn = ops.cam_norm(d["cam2"])
+            rv, _ = ops.pcm_forward(camn, d["f2"])
+            d["rv2_full"] = F.interpolate(rv, VIEW2, mode="bilinear", align_corners=True)
+        self.key1 = ops.hash_keys(n * 256, 2 * seed + 1, dev)
+        self.key2 = ops.hash_keys(n * 256, 2 * seed + 2, dev)
+        self.grid = (VIEW2[0] // 8, VIEW2[1] // 8)
+        self.pixels = n * (VIEW1[0] // 8) * (VIEW1[1] // 8)
+
+    def step(self):
+        ops, d = self.ops, self.d
+        # K1a + K2 forward, both views
+        camn1 = ops.cam_norm(d["cam1"])
+        rv1, ws1 = ops.pcm_forward(camn1, d["f1"])
+        camn2 = ops.cam_norm(d["cam2"])
+        rv2, ws2 = ops.pcm_forward(camn2, d["f2"])
+        # glue kept in PyTorch as in the reference (contrast_train.py:179-180): shrink view 1 to the loss grid
+        f1 = F.interpolate(d["fproj1"], size=self.grid, mode="bilinear", align_corners=True)
+        c1 = F.interpolate(rv1, size=self.grid, mode="bilinear", align_corners=True)
+        # K1c seeds, K3 prototypes (whole batch across ranks), K4 losses fwd+bwd
+        norm1, pl1 = ops.seed_labels(c1, d["label"], BG_THRESHOLD)
+        norm2, pl2 = ops.seed_labels(rv2, d["label"], BG_THRESHOLD)
+        proto1, _ = ops.prototypes(norm1, f1, group=self.group)
+        proto2, _ = ops.prototypes(norm2, d["fproj2"], group=self.group)
+        losses, g1, g2, _, _ = ops.contrast_loss_raw(f1, d["fproj2"], proto1, proto2, pl1, pl2, self.key1, self.key2)
+        # K1b forward + backward on the four full-resolution maps
+        outs = []
+        for name, size, gname in (("cam1_full", VIEW2, "g_n1"), ("rv1_full", VIEW2, "g_rv1"),
+                                  ("cam2_full", None, "g_n2"), ("rv2_full", None, "g_rv2")):
+            y, mm, lab = ops.fullres_norm_fwd(d[name], d["label"], size)
+            outs.append(ops.fullres_norm_bwd(d[name], lab, mm, d[gname], y.shape[-2:]))
+        # K2 backward
+        gf1 = ops.pcm_backward(d["f1"], camn1, rv1, d["g_rv_down1"], ws1)
+        gf2 = ops.pcm_backward(d["f2"], camn2, rv2, d["g_rv_down2"], ws2)
+        return losses, gf1, gf2, g1, g2, outs
+
+
+class E2EPath:
+    """The same path through the public, reference-facing API (autograd operators + loss.contrast_terms), from PINNED
+    HOST buffers: every step copies the head-level inputs host->device, runs Net.forward's tail (K1a, K2, bilinear x8
+    to full resolution), the loss-side operators, backward, and reads the losses back to the host."""
+
+    def __init__(self, hp: HotPath):
+        self.hp = hp
+        self.names = ["cam1", "f1", "fproj1", "cam2", "f2", "fproj2", "label", "g_n1", "g_rv1", "g_n2", "g_rv2"]
+        self.h2d_bytes = sum(hp.host[k].numel() * 4 for k in self.names)
+        self.out_host = torch.empty(10, dtype=torch.float32).pin_memory()
+        self.d2h_bytes = 40
+
+    def step(self):
+        from wseg_b200 import loss as L
+        from wseg_b200 import ops
+        hp = self.hp
+        dev = hp.dev
+        x = {k: hp.host[k].to(dev, non_blocking=True) for k in self.names}
+        f1 = x["f1"].requires_grad_(True)
+        f2 = x["f2"].requires_grad_(True)
+        p1 = x["fproj1"].requires_grad_(True)
+        p2 = x["fproj2"].requires_grad_(True)
+        rv1 = ops.pcm(ops.cam_norm(x["cam1"]), f1)
+        rv2 = ops.pcm(ops.cam_norm(x["cam2"]), f2)
+        cam1_full = F.interpolate(x["cam1"].requires_grad_(True), VIEW1, mode="bilinear", align_corners=True)
+        rv1_full = F.interpolate(rv1, VIEW1, mode="bilinear", align_corners=True)
+        cam2_full = F.interpolate(x["cam2"].requires_grad_(True), VIEW2, mode="bilinear", align_corners=True)
+        rv2_full = F.interpolate(rv2, VIEW2, mode="bilinear", align_corners=True)
+        terms = L.contrast_terms(p1, rv1, p2, rv2, x["label"], BG_THRESHOLD, grid=hp.grid, group=hp.group)
+        total = terms["loss_nce"]
+        for t, size, gname in ((cam1_full, VIEW2, "g_n1"), (rv1_full, VIEW2, "g_rv1"), (cam2_full, None, "g_n2"),
+                               (rv2_full, None, "g_rv2")):
+            total = total + (ops.fullres_norm(t, x["label"], size) * x[gname]).sum()
+        total.backward()
+        self.out_host.copy_(terms["losses_raw"].detach(), non_blocking=True)
+        return f1.grad
+
+
+# ------------------------------------------------------------------------------------------------ helpers
+class ClockSampler:
+    def __init__(self, index: int):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._t is not None:
+            self._t.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def time_steps(fn, steps, warmup, dev, flush, barrier):
+    """W warm-ups, then K steps each bracketed by CUDA events on the current stream, with an L2 flush (untimed) before
+    each; barrier + synchronize on both sides of the region.  Returns (sum of per-step device ms, wall ms)."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize(dev)
+    barrier()
+    torch.cuda.synchronize(dev)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    t0 = time.perf_counter()
+    for a, b in evs:
+        flush.zero_()
+        a.record()
+        fn()
+        b.record()
+    torch.cuda.synchronize(dev)
+    barrier()
+    wall = (time.perf_counter() - t0) * 1e3
+    return sum(a.elapsed_time(b) for a, b in evs), wall
+
+
+def cpu_reference_sample(n_sample: int, seed: int, repeats: int):
+    """The oracle port of the reference's algorithm on the host cores: the same per-image work as HotPath.step on
+    `n_sample` images.  Returns (best seconds, pixels)."""
+    from oracle import reference_fn as R
+    from wseg_b200 import synth
+    torch.set_num_threads(os.cpu_count() or 1)
+    x = host_inputs(n_sample, seed)
+    x = {k: v.clone() for k, v in x.items()}
+    label4 = x["label"].reshape(n_sample, -1, 1, 1)
+    sampler = R.ReferenceSampler(seed)
+
+    def one():
+        f1 = x["f1"].clone().requires_grad_(True)
+        f2 = x["f2"].clone().requires_grad_(True)
+        p1 = x["fproj1"].clone().requires_grad_(True)
+        p2 = x["fproj2"].clone().requires_grad_(True)
+        cam1 = x["cam1"].clone().requires_grad_(True)
+        cam2 = x["cam2"].clone().requires_grad_(True)
+        rv1 = R.pcm(R.cam_d_norm(cam1), f1)
+        rv2 = R.pcm(R.cam_d_norm(cam2), f2)
+        cam1_full = F.interpolate(cam1, VIEW1, mode="bilinear", align_corners=True)
+        rv1_full = F.interpolate(rv1, VIEW1, mode="bilinear", align_corners=True)
+        cam2_full = F.interpolate(cam2, VIEW2, mode="bilinear", align_corners=True)
+        rv2_full = F.interpolate(rv2, VIEW2, mode="bilinear", align_corners=True)
+        terms = R.contrast_terms(p1, rv1, p2, rv2, label4, BG_THRESHOLD, sampler=sampler,
+                                 grid=(VIEW2[0] // 8, VIEW2[1] // 8))
+        total = terms["loss_nce"]
+        for t, size, gname in ((cam1_full, VIEW2, "g_n1"), (rv1_full, VIEW2, "g_rv1"), (cam2_full, None, "g_n2"),
+                               (rv2_full, None, "g_rv2")):
+            total = total + (R.fullres_norm(t, label4, size) * x[gname]).sum()
+        total.backward()
+        return float(total.detach())
+
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        one()
+        best = min(best, time.perf_counter() - t0)
+    return best, n_sample * (VIEW1[0] // 8) * (VIEW1[1] // 8)
+
+
+def config_dict(n_gpus):
+    return {"workload": f"configs[1]: contrast hot path, batch {N_PER_GPU}/GPU @448x448 (56x56 stride-8 features, K=192, "
+                        f"D=128, 21 classes), view 2 128x128 (16x16 loss grid)",
+            "global_batch": N_PER_GPU * n_gpus, "parallelism": f"dp{n_gpus}",
+            "l2": "256 MiB flush before every timed step",
+            "pcm_mode": os.environ.get("WSEGK_PCM_MODE", "default")}
+
+
+# ------------------------------------------------------------------------------------------------ arms
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_sample = 1
+    for _ in range(args.warmup):
+        cpu_reference_sample(n_sample, 1234, 1)
+    t0 = time.perf_counter()
+    pix = 0
+    for _ in range(args.steps):
+        _, p = cpu_reference_sample(n_sample, 1234, 1)
+        pix += p
+    dt = time.perf_counter() - t0
+    value = pix / dt / 1e6
+    cores = torch.get_num_threads()
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"oracle/reference_fn.py (restated reference, ATen fp32 on {cores} host threads), "
+                                       f"{n_sample} image of the workload per step"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    from wseg_b200 import ops
+    hp = HotPath(N_PER_GPU, dev, seed=1234 + rank, group=group)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    pk = peaks()
+
+    # -------- device-resident arm
+    hp.step()
+    torch.cuda.synchronize(dev)
+    l0 = ops.launch_count()
+    hp.step()
+    launches_per_step = ops.launch_count() - l0
+    ops.pcm_profile(True)
+    fwd_ms, bwd_ms = [], []
+
+    def step_prof():
+        hp.step()
+
+    with ClockSampler(local) as clk:
+        dev_ms, wall_ms = time_steps(step_prof, args.steps, args.warmup, dev, flush, barrier)
+    ops.pcm_profile(False)
+    # main-kernel durations of the last step (view-2 launches overwrite view-1's: profile view 1 separately below)
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    ms_per_step = dev_ms / args.steps
+    total_pix = hp.pixels * world
+    value = total_pix / (ms_per_step * 1e-3) / 1e6
+
+    # -------- roofline of the dominant kernel: PCM main kernels on view 1, timed alone (burst peak)
+    d = hp.d
+    camn1 = ops.cam_norm(d["cam1"])
+    ops.pcm_profile(True)
+    for _ in range(max(3, args.warmup)):
+        rv1, ws1 = ops.pcm_forward(camn1, d["f1"])
+        ops.pcm_backward(d["f1"], camn1, rv1, d["g_rv_down1"], ws1)
+    for _ in range(max(5, args.steps)):
+        flush.zero_()
+        rv1, ws1 = ops.pcm_forward(camn1, d["f1"])
+        ops.pcm_backward(d["f1"], camn1, rv1, d["g_rv_down1"], ws1)
+        a, b = ops.pcm_main_ms()
+        fwd_ms.append(a)
+        bwd_ms.append(b)
+    ops.pcm_profile(False)
+    hw = (VIEW1[0] // 8) * (VIEW1[1] // 8)
+    fl_fwd = 2.0 * N_PER_GPU * hw * hw * (K_PCM + C_CLS)
+    fl_bwd = 2.0 * N_PER_GPU * hw * hw * (2 * K_PCM + C_CLS)
+    avg = lambda v: sum(v) / len(v)
+    tf_fwd = fl_fwd / (avg(fwd_ms) * 1e-3) / 1e12
+    tf_bwd = fl_bwd / (avg(bwd_ms) * 1e-3) / 1e12
+    dom = "pcm_bwd_kernel" if avg(bwd_ms) >= avg(fwd_ms) else "pcm_fwd_kernel"
+    ach = tf_bwd if dom == "pcm_bwd_kernel" else tf_fwd
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(dom)
+    roofline = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": ach / pk["bf16_tflops"], "traffic": traffic, "peak_source": pk["source"] + " (burst)",
+                "algorithmic_flops_per_launch": fl_bwd if dom == "pcm_bwd_kernel" else fl_fwd,
+                "ms_per_launch": avg(bwd_ms) if dom == "pcm_bwd_kernel" else avg(fwd_ms),
+                "other": {"pcm_fwd_kernel": {"ms": avg(fwd_ms), "tflops": tf_fwd, "frac": tf_fwd / pk["bf16_tflops"]},
+                          "pcm_bwd_kernel": {"ms": avg(bwd_ms), "tflops": tf_bwd, "frac": tf_bwd / pk["bf16_tflops"]}}}
+    # whole-step roofline: PCM flops / tensor peak + algorithmic HBM bytes / measured HBM bandwidth
+    n = N_PER_GPU
+    k1b = 2 * 2 * n * C_CLS * (VIEW1[0] * VIEW1[1] + VIEW2[0] * VIEW2[1]) * 4 + 2 * 2 * n * C_CLS * 2 * VIEW2[0] * VIEW2[1] * 4
+    pcm_b = n * hw * (K_PCM + 2 * C_CLS) * 4 + n * hw * (2 * K_PCM + 3 * C_CLS) * 4
+    small = 2 * (2 * n * C_CLS * 256 * 4 + 2 * n * 256 * D_PROJ * 4 * 2)
+    t_roof = (fl_fwd + fl_bwd) / (pk["bf16_tflops_sustained"] * 1e12) + (k1b + pcm_b + small + 2 * n * C_CLS * hw * 4) / (pk["hbm_gbs"] * 1e9)
+    step_roofline = {"t_roof_ms": t_roof * 1e3, "frac": t_roof * 1e3 / ms_per_step,
+                     "note": "PCM flops / sustained bf16 peak + algorithmic bytes of K1a,K1b,K1c,K3,K4,K2 io / measured HBM"}
+
+    # -------- end-to-end arm: host buffers, public API
+    e2e = E2EPath(hp)
+    e2e_ms, _ = time_steps(e2e.step, args.steps, args.warmup, dev, flush, barrier)
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = total_pix / (float(t.item()) / args.steps * 1e-3) / 1e6
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16 tensor-core operands, fp32 accumulate (PCM); f32 elsewhere", "data": "synthetic",
+            "config": config_dict(world), "image_mpix_per_s": value * 64,
+            "clocks": clk.summary(), "gpu_launches": int(launches_per_step * args.steps),
+            "gpu_launches_per_step": int(launches_per_step),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e.h2d_bytes,
+                    "d2h_bytes_per_step": e2e.d2h_bytes, "ms_per_step": float(t.item()) / args.steps,
+                    "api": "ops.cam_norm/ops.pcm (autograd) + F.interpolate x8 + loss.contrast_terms + ops.fullres_norm, backward"},
+            "roofline": roofline, "step_roofline": step_roofline, "wall_ms_per_step_incl_flush": wall_ms / args.steps}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        best, pix = cpu_reference_sample(1, 1234, 2)
+        line["cpu_baseline"] = {"value": pix / best / 1e6, "unit": UNIT, "cores": torch.get_num_threads(),
+                                "kind": "port", "sample": "oracle/reference_fn.py on host threads, 1 image of the "
+                                                          "workload (PCM fwd+bwd at 56x56, K1b at 448x448, losses), best of 2"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

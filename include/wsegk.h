@@ -122,6 +122,15 @@ int wsegk_contrast_loss_fwd_bwd(const float* x1, const float* x2, const float* p
                                 int32_t* mined1, int32_t* mined2, const float* grad_scale, int N, int C, int D,
                                 int h, int w, void* workspace, size_t workspace_bytes, wsegk_stream_t stream);
 
+/* Diagnostics for bench.py / tests (not part of the reference-facing surface).
+ *   launch_count  : kernels this library has enqueued in this process so far.
+ *   pcm_profile   : when enabled (per host thread), pcm_fwd / pcm_bwd record CUDA events on `stream` around their
+ *                   tcgen05 main kernel; pcm_main_ms synchronises on them and returns the LAST durations in ms
+ *                   (negative if that kernel has not run with profiling on). */
+unsigned long long wsegk_debug_launch_count(void);
+int wsegk_debug_pcm_profile(int enable);
+int wsegk_debug_pcm_main_ms(float* fwd_ms, float* bwd_ms);
+
 /* Test aid: byte offsets of the PCM workspace sections, in the order
  * {fhat, camb, inv_norm, dsum, part, uaug, vaug, dfhat, total_bytes, nsplit, T, HWp}.  Returns how many were written. */
 int wsegk_debug_pcm_layout(int N, int C, int K, int h, int w, size_t* out, int n_out);

@@ -1,0 +1,284 @@
+"""Parity of the sm_100a kernels (called through the C ABI via wseg_b200.ops) against the oracle on a B200.
+
+The oracle (oracle/reference_fn.py) runs with stock ATen in true fp32 on the same GPU (allow_tf32=False), on the
+same seeded inputs; golden vectors produced by the reference's own code (tests/golden) are checked too.
+Bars (BASELINE.json north_star): indices / seeds / mined sets bit-exact, losses, gradients and cam_rv within 1e-3
+relative error (max-abs error over max-abs reference unless a test says otherwise).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import reference_fn as R
+from oracle.make_golden import LOSS_CASE, PCM_CASE
+from wseg_b200 import loss as L
+from wseg_b200 import ops, synth
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3          # north_star: losses, gradients and cam_rv within 1e-3 relative error
+
+
+def rel_max(a, b):
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+def rel_fro(a, b):
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+# ------------------------------------------------------------------------------------------------ K1a
+@pytest.mark.parametrize("n,h,w", [(1, 16, 16), (2, 20, 13), (8, 56, 56), (1, 94, 125), (3, 1, 7)])
+def test_cam_norm_bit_exact(cuda_dev, n, h, w):
+    cam = synth.pcm_inputs(n, h, w, seed=n * 100 + h)["cam"].to(cuda_dev)
+    assert torch.equal(ops.cam_norm(cam), R.cam_d_norm(cam))
+
+
+def test_cam_norm_all_negative_plane(cuda_dev):
+    cam = synth.pcm_inputs(2, 8, 8, seed=3)["cam"].to(cuda_dev)
+    cam[0, 5] = -cam[0, 5].abs() - 1.0          # relu kills the plane: peak = 1e-5, output 0
+    cam[1, 1:] = -1.0                            # no foreground at all: background = 1
+    got = ops.cam_norm(cam)
+    assert torch.equal(got, R.cam_d_norm(cam))
+    assert float(got[1, 0].min()) == 1.0 and float(got[1, 1:].abs().max()) == 0.0
+
+
+# ------------------------------------------------------------------------------------------------ K2
+PCM_SHAPES = [(1, 16, 16, False), (2, 20, 13, False), (8, 56, 56, False), (8, 56, 56, True), (1, 94, 125, False),
+              (3, 9, 5, False), (1, 64, 64, True)]
+
+
+@pytest.mark.parametrize("n,h,w,positive", PCM_SHAPES)
+def test_pcm_forward_vs_oracle(cuda_dev, n, h, w, positive):
+    d = synth.pcm_inputs(n, h, w, seed=7 + n + h, positive=positive)
+    cam, f = d["cam"].to(cuda_dev), d["f"].to(cuda_dev)
+    camn = ops.cam_norm(cam)
+    out, _ = ops.pcm_forward(camn, f)
+    ref = R.pcm(camn, f)
+    assert rel_max(out, ref) <= TOL, (rel_max(out, ref), "cam_rv")
+
+
+def test_pcm_forward_golden(cuda_dev, golden_dir):
+    g = np.load(os.path.join(golden_dir, "pcm_n2_20x13.npz"))
+    c = PCM_CASE
+    d = synth.pcm_inputs(c["n"], c["h"], c["w"], c["seed"])
+    camn = ops.cam_norm(d["cam"].to(cuda_dev))
+    assert np.array_equal(camn.cpu().numpy(), g["cam_d_norm"])
+    out, _ = ops.pcm_forward(camn, d["f"].to(cuda_dev))
+    ref = torch.from_numpy(g["cam_rv"]).to(cuda_dev)
+    assert rel_max(out, ref) <= TOL
+
+
+def test_network_head_golden(cuda_dev, golden_dir):
+    """fc8 logits -> K1a -> f9 conv (PyTorch) -> K2, against what the unmodified reference Net.forward produced."""
+    g = np.load(os.path.join(golden_dir, "net_head_72x56.npz"))
+    camn = ops.cam_norm(torch.from_numpy(g["cam_logits"]).to(cuda_dev))
+    assert np.array_equal(camn.cpu().numpy(), g["cam_d_norm"])
+    f9 = torch.nn.functional.conv2d(torch.from_numpy(g["f"]).to(cuda_dev), torch.from_numpy(g["f9_weight"]).to(cuda_dev))
+    out, _ = ops.pcm_forward(camn, f9)
+    assert rel_max(out, torch.from_numpy(g["cam_rv_down"]).to(cuda_dev)) <= TOL
+
+
+@pytest.mark.parametrize("n,h,w,positive", PCM_SHAPES)
+def test_pcm_backward_vs_oracle(cuda_dev, n, h, w, positive):
+    d = synth.pcm_inputs(n, h, w, seed=7 + n + h, positive=positive)
+    cam, f, g = d["cam"].to(cuda_dev), d["f"].to(cuda_dev), d["grad_out"].to(cuda_dev)
+    camn = ops.cam_norm(cam)
+    f_ref = f.clone().requires_grad_(True)
+    R.pcm(camn, f_ref).backward(g)
+    f_my = f.clone().requires_grad_(True)
+    ops.pcm(camn, f_my).backward(g)
+    err = rel_fro(f_my.grad, f_ref.grad)
+    assert err <= ops.PCM_GRAD_TOL, (err, "grad_f, relative Frobenius error")
+
+
+def test_pcm_backward_golden(cuda_dev, golden_dir):
+    g = np.load(os.path.join(golden_dir, "pcm_n2_20x13.npz"))
+    c = PCM_CASE
+    d = synth.pcm_inputs(c["n"], c["h"], c["w"], c["seed"])
+    camn = ops.cam_norm(d["cam"].to(cuda_dev))
+    f = d["f"].to(cuda_dev).requires_grad_(True)
+    ops.pcm(camn, f).backward(d["grad_out"].to(cuda_dev))
+    assert rel_fro(f.grad, torch.from_numpy(g["grad_f"]).to(cuda_dev)) <= ops.PCM_GRAD_TOL
+
+
+def test_pcm_properties_full_size(cuda_dev):
+    """Size-independent properties at the BASELINE config (N=8, 56x56, K=192): linearity in cam, a constant-one class
+    map is (almost) a fixed point, and grad_f is orthogonal to f at every pixel (the output is invariant to the
+    per-pixel scale of f)."""
+    n, h, w = 8, 56, 56
+    d = synth.pcm_inputs(n, h, w, seed=99)
+    f = d["f"].to(cuda_dev)
+    camn = ops.cam_norm(d["cam"].to(cuda_dev))
+    camn[:, 3] = 1.0
+    out1, _ = ops.pcm_forward(camn, f)
+    out2, _ = ops.pcm_forward(0.5 * camn, f)
+    assert rel_max(out2, 0.5 * out1) <= 1e-4
+    assert float((out1[:, 3] - 1.0).abs().max()) <= 1e-4          # sum_i A_ij / (sum_i A_ij + 1e-5)
+    fm = f.clone().requires_grad_(True)
+    ops.pcm(camn, fm).backward(d["grad_out"].to(cuda_dev))
+    radial = (fm.grad * f).sum(dim=1).abs().max().item()
+    scale = (fm.grad.norm(dim=1) * f.norm(dim=1)).max().item()
+    assert radial <= 2e-3 * scale, (radial, scale)
+
+
+def test_pcm_rejects_bad_arguments(cuda_dev):
+    camn = torch.zeros(1, 21, 4, 4, device=cuda_dev)
+    with pytest.raises(RuntimeError, match="K % 16"):
+        ops.pcm_forward(camn, torch.zeros(1, 100, 4, 4, device=cuda_dev))
+    with pytest.raises(RuntimeError, match="does not match"):
+        ops.pcm_forward(camn, torch.zeros(1, 192, 5, 4, device=cuda_dev))
+    with pytest.raises(RuntimeError, match="float32"):
+        ops.pcm_forward(camn, torch.zeros(1, 192, 4, 4, device=cuda_dev, dtype=torch.float16))
+
+
+# ------------------------------------------------------------------------------------------------ K1b
+@pytest.mark.parametrize("n,H,W,size", [(2, 192, 192, (128, 128)), (8, 448, 448, (128, 128)), (2, 128, 128, None),
+                                        (3, 70, 45, (33, 20)), (1, 17, 9, (17, 9))])
+def test_fullres_norm_fwd_bwd(cuda_dev, n, H, W, size):
+    t = synth.head_outputs(n, (H, W), seed=n + H)["cam"].to(cuda_dev)
+    label = synth.label_with_bg(synth.labels(n, seed=H)).to(cuda_dev)
+    x = t.clone().requires_grad_(True)
+    y = ops.fullres_norm(x, label, size)
+    gy = torch.randn(y.shape, generator=torch.Generator().manual_seed(1)).to(cuda_dev)
+    y.backward(gy)
+    xr = t.clone().requires_grad_(True)
+    yr = R.fullres_norm(xr, label.reshape(n, -1, 1, 1), size)
+    yr.backward(gy)
+    assert rel_max(y, yr) <= 1e-5
+    assert rel_max(x.grad, xr.grad) <= 1e-4
+    absent = label == 0
+    assert float(y[absent].abs().max()) == 0.0 and float(x.grad[absent].abs().max()) == 0.0
+
+
+# ------------------------------------------------------------------------------------------------ K1c / K3 / K4
+def _views(n, hw1, hw2, seed, d=128, dev="cpu"):
+    a = {k: v.to(dev) for k, v in synth.head_outputs(n, hw1, seed=seed * 10 + 1, d=d).items()}
+    b = {k: v.to(dev) for k, v in synth.head_outputs(n, hw2, seed=seed * 10 + 2, d=d).items()}
+    return a, b
+
+
+@pytest.mark.parametrize("n,hw1,hw2,d", [(2, (192, 192), (128, 128), 128), (8, 448, (128, 128), 128),
+                                         (4, (256, 320), (160, 96), 128), (16, (512, 512), (256, 256), 128),
+                                         (2, (128, 128), (128, 128), 256)])
+def test_contrast_terms_vs_oracle(cuda_dev, n, hw1, hw2, d):
+    if isinstance(hw1, int):
+        hw1 = (hw1, hw1)
+    a, b = _views(n, hw1, hw2, seed=n, d=d, dev=cuda_dev)
+    label = synth.label_with_bg(synth.labels(n, seed=n)).to(cuda_dev)
+    grid = (hw2[0] // 8, hw2[1] // 8)
+    f1 = a["f_proj"].clone().requires_grad_(True)
+    f2 = b["f_proj"].clone().requires_grad_(True)
+    mine = L.contrast_terms(f1, a["cam_rv_down"], f2, b["cam_rv_down"], label, 0.2, grid=grid, rng=7)
+    mine["loss_nce"].backward()
+    r1 = a["f_proj"].clone().requires_grad_(True)
+    r2 = b["f_proj"].clone().requires_grad_(True)
+    ref = R.contrast_terms(r1, a["cam_rv_down"], r2, b["cam_rv_down"], label.reshape(n, -1, 1, 1), 0.2,
+                           sampler=R.ReferenceSampler(7), grid=grid, argmax_of="softmax")
+    ref["loss_nce"].backward()
+    for v in "12":
+        assert torch.equal(mine["pseudo_label" + v].long(), ref["pseudo_label" + v]), "seeds view " + v
+        assert torch.equal(mine["top_indices" + v].long(), ref["top_indices" + v]), "top-k indices view " + v
+        assert float((mine["norm_cam" + v] - ref["norm_cam" + v]).abs().max()) <= 1e-6
+        assert float((mine["prototypes" + v] - ref["prototypes" + v]).abs().max()) <= 1e-6
+    for k in ("loss_nce", "loss_intra_nce", "loss_cross_nce", "loss_cross_nce2"):
+        assert float(mine[k]) == pytest.approx(float(ref[k]), rel=1e-5), k
+    assert rel_max(f1.grad, r1.grad) <= TOL and rel_max(f2.grad, r2.grad) <= TOL
+    # hard-pixel sets: multiplicity with which each pixel enters its class's mined set (random half + hard half)
+    m = L.contrast_terms(a["f_proj"], a["cam_rv_down"], b["f_proj"], b["cam_rv_down"], label, 0.2, grid=grid, rng=7,
+                         want_mined=True)
+    for v in "12":
+        cnt = torch.zeros_like(m["mined" + v])
+        for _, rnd, hard in ref["sets" + v][1]:
+            cnt.index_add_(0, rnd, torch.ones_like(rnd, dtype=torch.int32))
+            cnt.index_add_(0, hard, torch.ones_like(hard, dtype=torch.int32))
+        assert torch.equal(cnt, m["mined" + v]), "mined set view " + v
+
+
+def test_contrast_step_loss_golden(cuda_dev, golden_dir):
+    """The whole loss body against what the reference's own loop body produced (oracle/make_golden.py)."""
+    g = np.load(os.path.join(golden_dir, "loss_n2_192_128.npz"))
+    c = LOSS_CASE
+    v1 = {k: v.to(cuda_dev).requires_grad_(True) for k, v in synth.head_outputs(c["n"], c["view1"], seed=c["seed1"]).items()}
+    v2 = {k: v.to(cuda_dev).requires_grad_(True) for k, v in synth.head_outputs(c["n"], c["view2"], seed=c["seed2"]).items()}
+    lab = synth.labels(c["n"], c["label_seed"]).to(cuda_dev)
+    out = L.contrast_step_loss(v1["cam"], v1["cam_rv"], v1["f_proj"], v1["cam_rv_down"], v2["cam"], v2["cam_rv"],
+                               v2["f_proj"], v2["cam_rv_down"], lab, c["bg_threshold"], c["view2"], rng=c["py_seed"])
+    out["loss"].backward()
+    for k in L.LOSS_KEYS:
+        assert float(out[k]) == pytest.approx(float(g[k]), rel=1e-4), k
+    for v in "12":
+        assert np.array_equal(out["pseudo_label" + v].cpu().numpy(), g["pseudo_label" + v])
+        assert np.array_equal(out["top_indices" + v].cpu().numpy(), g["top_indices" + v])
+        np.testing.assert_allclose(out["prototypes" + v].cpu().numpy(), g["prototypes" + v], atol=1e-6)
+    for name, t in (("grad_f_proj1", v1["f_proj"].grad), ("grad_f_proj2", v2["f_proj"].grad)):
+        ref = torch.from_numpy(g[name]).to(cuda_dev)
+        assert rel_max(t, ref) <= TOL, name
+    from oracle.make_golden import sample
+    for name, t in (("grad_cam1_sample", v1["cam"].grad), ("grad_cam_rv1_sample", v1["cam_rv"].grad),
+                    ("grad_cam_rv2_sample", v2["cam_rv"].grad)):
+        ref = torch.from_numpy(g[name])
+        got = torch.from_numpy(sample(t.cpu()))
+        assert rel_max(got, ref) <= TOL, name
+
+
+def test_seed_labels_degenerate_planes(cuda_dev):
+    """All-zero plane -> -1 everywhere (no outer relu, contrast_train.py:190-192); absent classes never win."""
+    n, g = 2, 16
+    x = synth.head_outputs(n, (128, 128), seed=5)["cam_rv_down"].to(cuda_dev)
+    x[0, 4] = 0.0
+    label = synth.label_with_bg(synth.labels(n, seed=5)).to(cuda_dev)
+    norm, pl = ops.seed_labels(x, label, 0.2)
+    rn, rp = R.seed_labels(x, label.reshape(n, -1, 1, 1), 0.2)
+    assert torch.equal(norm, rn) and torch.equal(pl.long(), rp)
+    assert float(norm[0, 4].max()) < 0.0
+    present = label.bool()
+    assert bool(present[torch.arange(n).repeat_interleave(g * g), pl.long()].all())
+
+
+def test_prototype_ties_follow_canonical_order(cuda_dev):
+    """Class 0 of norm_cam is the constant bg_threshold (100 % ties): indices must be 0..k-1."""
+    n = 2
+    a = synth.head_outputs(n, (128, 128), seed=9)
+    label = synth.label_with_bg(synth.labels(n, seed=9)).to(cuda_dev)
+    norm, _ = ops.seed_labels(a["cam_rv_down"].to(cuda_dev), label, 0.2)
+    proto, idx = ops.prototypes(norm, a["f_proj"].to(cuda_dev))
+    k = 16 * 16 // 8
+    assert idx[0].tolist() == list(range(k))
+    _, ti, rp = R.prototypes(norm, a["f_proj"].to(cuda_dev))
+    assert torch.equal(idx.long(), ti) and float((proto - rp).abs().max()) <= 1e-6
+
+
+def test_sharded_prototypes_equal_whole_batch(cuda_dev):
+    """Data-parallel semantics on one GPU: per-shard local candidates, concatenated in rank order and finalised, equal
+    the single-process whole-batch prototypes bit for bit."""
+    n, world = 8, 4
+    a = synth.head_outputs(n, (128, 128), seed=21)
+    label = synth.label_with_bg(synth.labels(n, seed=21)).to(cuda_dev)
+    norm, _ = ops.seed_labels(a["cam_rv_down"].to(cuda_dev), label, 0.2)
+    fp = a["f_proj"].to(cuda_dev)
+    k = 16 * 16 // 8
+    whole_p, whole_i = ops.prototypes(norm, fp, k)
+    per = n // world
+    cands = [ops.proto_topk_local(norm[r * per:(r + 1) * per], fp[r * per:(r + 1) * per], k, pixel_offset=r * per * 256)
+             for r in range(world)]
+    tv = torch.cat([c[0] for c in cands], 1)
+    ti = torch.cat([c[1] for c in cands], 1)
+    tf = torch.cat([c[2] for c in cands], 1)
+    p, i = ops.proto_finalize(tv, ti, tf, k)
+    assert torch.equal(i, whole_i) and torch.equal(p, whole_p)
+
+
+def test_abi_error_codes(cuda_dev):
+    import ctypes
+    from wseg_b200 import _lib
+    lib = _lib.lib()
+    buf = torch.zeros(1 << 19, device=cuda_dev)
+    p = ctypes.c_void_p((buf.data_ptr() + 1023) // 1024 * 1024)
+    assert lib.wsegk_cam_norm_fwd(p, p, 1, 1, 4, 4, p, 4096, None) == -1          # BAD_SHAPE (C < 2)
+    assert lib.wsegk_cam_norm_fwd(None, p, 1, 21, 4, 4, p, 4096, None) == -6       # NULL
+    assert lib.wsegk_pcm_fwd(p, p, p, 1, 21, 192, 4, 4, p, 16, None) == -3         # WORKSPACE_TOO_SMALL
+    assert "workspace" in _lib.last_error()
+    assert lib.wsegk_pcm_fwd(p, p, p, 1, 40, 192, 4, 4, p, 1 << 20, None) == -1    # too many classes

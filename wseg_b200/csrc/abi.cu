@@ -1,5 +1,6 @@
 // wsegk C ABI: version, error text, device gate, workspace sizing.
 #include <algorithm>
+#include <atomic>
 #include <cstring>
 #include <mutex>
 
@@ -8,6 +9,9 @@
 namespace wsegk {
 
 static thread_local char g_err[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+
+void count_launches(int n) { g_launches.fetch_add(static_cast<unsigned long long>(n), std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -85,6 +89,8 @@ using namespace wsegk;
 extern "C" int wsegk_version(void) { return 100; }   // 0.1.0
 
 extern "C" const char* wsegk_last_error(void) { return g_err; }
+
+extern "C" unsigned long long wsegk_debug_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 extern "C" size_t wsegk_workspace_bytes(int op, int N, int C, int K, int D, int h, int w) {
     if (N <= 0 || h <= 0 || w <= 0) return 0;

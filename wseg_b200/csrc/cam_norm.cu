@@ -89,6 +89,7 @@ extern "C" int wsegk_cam_norm_fwd(const float* cam, float* cam_norm, int N, int 
     cam_plane_peak_kernel<<<N * C, 256, 0, stream>>>(cam, peak, HW);
     dim3 grid(ceil_div(HW, 128), N);
     cam_pixel_kernel<32><<<grid, 128, 0, stream>>>(cam, peak, cam_norm, C, HW);
+    count_launches(2);
     WSEGK_CUDA_OK(cudaGetLastError());
     return WSEGK_OK;
 }

@@ -19,6 +19,7 @@ constexpr int kMaxClasses = 23;   // C + ones row must fit kCamHalf
 constexpr int kMaxPcmK = 192;
 
 void set_error(const char* fmt, ...);
+void count_launches(int n);   // diagnostics: wsegk_debug_launch_count()
 int check_device();   // WSEGK_OK if the current device is sm_100, else WSEGK_ERR_DEVICE (message set)
 
 #define WSEGK_CUDA_OK(expr)                                                                    \

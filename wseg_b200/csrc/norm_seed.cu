@@ -353,6 +353,7 @@ extern "C" int wsegk_fullres_norm_fwd(const float* p, const float* label, float*
     plane_minmax_partial_kernel<<<dim3(kPlaneSplit, planes), 512, 0, stream>>>(p, label, partial, H * W);
     fullres_resample_kernel<<<dim3(ceil_div(oh * ow, 256), planes), 256, 0, stream>>>(p, label, partial, out, minmax,
                                                                                        H, W, oh, ow, kPlaneSplit);
+    count_launches(2);
     WSEGK_CUDA_OK(cudaGetLastError());
     return WSEGK_OK;
 }
@@ -374,6 +375,7 @@ extern "C" int wsegk_fullres_norm_bwd(const float* p, const float* label, const 
                                                                      oh, ow, nblk);
     fullres_bwd_kernel<true><<<dim3(nblk, planes), 256, 0, stream>>>(p, label, minmax, grad_out, grad_p, sums, H, W,
                                                                     oh, ow, nblk);
+    count_launches(2);
     WSEGK_CUDA_OK(cudaGetLastError());
     return WSEGK_OK;
 }
@@ -394,6 +396,7 @@ extern "C" int wsegk_seed_labels_fwd(const float* cam_rv_down, const float* labe
     seed_minmax_kernel<<<ceil_div(planes, 8), 256, 0, stream>>>(cam_rv_down, lohi, planes, HW);
     seed_pixel_kernel<<<dim3(ceil_div(HW, 128), N), 128, 0, stream>>>(cam_rv_down, label, lohi, bg_threshold,
                                                                       norm_cam, pseudo, C, HW);
+    count_launches(2);
     WSEGK_CUDA_OK(cudaGetLastError());
     return WSEGK_OK;
 }

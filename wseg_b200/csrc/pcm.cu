@@ -545,6 +545,39 @@ static size_t fwd_smem_bytes(int K) {
 
 using namespace wsegk;
 
+// ---- optional main-kernel timing (wsegk_debug_pcm_profile) ----------------------------------------
+namespace {
+struct PcmProf {
+    bool on = false;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // fwd start/stop, bwd start/stop
+    bool have[2] = {false, false};
+};
+thread_local PcmProf g_prof;
+void prof_mark(int which, wsegk_stream_t stream) {
+    if (!g_prof.on) return;
+    if (!g_prof.ev[which]) cudaEventCreate(&g_prof.ev[which]);
+    cudaEventRecord(g_prof.ev[which], stream);
+    if (which & 1) g_prof.have[which >> 1] = true;
+}
+}  // namespace
+
+extern "C" int wsegk_debug_pcm_profile(int enable) {
+    g_prof.on = enable != 0;
+    return WSEGK_OK;
+}
+
+extern "C" int wsegk_debug_pcm_main_ms(float* fwd_ms, float* bwd_ms) {
+    float* out[2] = {fwd_ms, bwd_ms};
+    for (int k = 0; k < 2; ++k) {
+        if (!out[k]) continue;
+        *out[k] = -1.f;
+        if (!g_prof.have[k]) continue;
+        WSEGK_CUDA_OK(cudaEventSynchronize(g_prof.ev[2 * k + 1]));
+        WSEGK_CUDA_OK(cudaEventElapsedTime(out[k], g_prof.ev[2 * k], g_prof.ev[2 * k + 1]));
+    }
+    return WSEGK_OK;
+}
+
 static int pcm_check(const char* who, int N, int C, int K, int h, int w) {
     WSEGK_REQUIRE(N > 0 && h > 0 && w > 0, WSEGK_ERR_BAD_SHAPE, "%s: N,h,w must be positive", who);
     WSEGK_REQUIRE(C >= 1 && C <= kMaxClasses, WSEGK_ERR_BAD_SHAPE, "%s: need 1 <= C <= %d (got %d)", who,
@@ -577,11 +610,14 @@ extern "C" int wsegk_pcm_fwd(const float* f, const float* cam_norm, float* cam_r
         const size_t smem = fwd_smem_bytes(K);
         WSEGK_CUDA_OK(cudaFuncSetAttribute(pcm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            static_cast<int>(smem)));
+        prof_mark(0, stream);
         pcm_fwd_kernel<<<dim3(pl.T, pl.nsplit, N), kFwdThreads, smem, stream>>>(pl.fhat, pl.camb, pl.part, K,
                                                                                 pl.T, pl.HWp, pl.nsplit);
+        prof_mark(1, stream);
     }
     pcm_fwd_finalize_kernel<<<dim3(ceil_div(pl.HWp, 128), N), 128, 0, stream>>>(pl.part, cam_rv, pl.dsum, C,
                                                                                  pl.HW, pl.HWp, pl.nsplit);
+    count_launches(4);
     WSEGK_CUDA_OK(cudaGetLastError());
     return WSEGK_OK;
 }
@@ -604,9 +640,11 @@ extern "C" int wsegk_pcm_bwd(const float* f, const float* cam_norm, const float*
         const size_t smem = bwd_smem_bytes(K);
         WSEGK_CUDA_OK(cudaFuncSetAttribute(pcm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            static_cast<int>(smem)));
+        prof_mark(2, stream);
         pcm_bwd_kernel<<<dim3(pl.T, pl.nsplit, N), kFwdThreads, smem, stream>>>(pl.fhat, pl.uaug, pl.vaug,
                                                                                 pl.dfhat, K, pl.T, pl.HWp,
                                                                                 pl.nsplit);
+        prof_mark(3, stream);
     }
     {
         const size_t smem = static_cast<size_t>(K) * 129 * sizeof(float);
@@ -615,6 +653,7 @@ extern "C" int wsegk_pcm_bwd(const float* f, const float* cam_norm, const float*
         pcm_bwd_post_kernel<<<dim3(pl.T, N), 256, smem, stream>>>(pl.dfhat, f, pl.inv_norm, grad_f, K, pl.HW,
                                                                   pl.HWp, pl.nsplit);
     }
+    count_launches(3);
     WSEGK_CUDA_OK(cudaGetLastError());
     return WSEGK_OK;
 }

@@ -507,6 +507,7 @@ extern "C" int wsegk_proto_topk_local(const float* norm_cam, const float* f_proj
                                        static_cast<int>(smem)));
     proto_topk_kernel<<<C, kTopkThreads, smem, stream>>>(norm_cam, f_proj, pixel_offset, k, kpad, top_val, top_idx,
                                                          top_fea, N, C, D, h * w);
+    count_launches(1);
     WSEGK_CUDA_OK(cudaGetLastError());
     return WSEGK_OK;
 }
@@ -522,6 +523,7 @@ extern "C" int wsegk_proto_finalize(const float* cand_val, const int32_t* cand_i
     WSEGK_CUDA_OK(cudaFuncSetAttribute(proto_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem)));
     proto_finalize_kernel<<<C, 1024, smem, stream>>>(cand_val, cand_idx, cand_fea, n_cand, npad, k, proto, sel_idx, D);
+    count_launches(1);
     WSEGK_CUDA_OK(cudaGetLastError());
     return WSEGK_OK;
 }
@@ -583,6 +585,7 @@ extern "C" int wsegk_contrast_loss_fwd_bwd(const float* x1, const float* x2, con
     nce_mine_kernel<<<dim3(ceil_div(prm.P, kMineThreads), ceil_div(prm.P, kMineChunk), 2), kMineThreads, 0, stream>>>(prm);
     nce_grad_kernel<<<dim3(L.nblk, 2), kNceThreads, proto_smem, stream>>>(prm);
     nce_finalize_kernel<<<1, 32, 0, stream>>>(prm);
+    count_launches(4);
     WSEGK_CUDA_OK(cudaGetLastError());
     return WSEGK_OK;
 }

@@ -102,6 +102,27 @@ def pcm(cam_norm_t: torch.Tensor, f: torch.Tensor) -> torch.Tensor:
     return _PCMFunction.apply(cam_norm_t.detach(), f)
 
 
+# Relative Frobenius error bound of grad_f vs the fp32 oracle that the PCM backward is held to (tests/test_gpu_parity.py).
+PCM_GRAD_TOL = 8e-2
+
+
+def launch_count() -> int:
+    """Kernels enqueued by libwsegk in this process so far (bench.py reports the per-step difference)."""
+    return int(_lib.lib().wsegk_debug_launch_count())
+
+
+def pcm_profile(enable: bool) -> None:
+    check(_lib.lib().wsegk_debug_pcm_profile(1 if enable else 0), "wsegk_debug_pcm_profile")
+
+
+def pcm_main_ms() -> Tuple[float, float]:
+    """(forward, backward) duration in ms of the last profiled tcgen05 main kernels (CUDA events, launching stream)."""
+    import ctypes
+    a, b = ctypes.c_float(-1.0), ctypes.c_float(-1.0)
+    check(_lib.lib().wsegk_debug_pcm_main_ms(ctypes.byref(a), ctypes.byref(b)), "wsegk_debug_pcm_main_ms")
+    return float(a.value), float(b.value)
+
+
 def pcm_layout(n: int, c: int, k: int, h: int, w: int) -> dict:
     """Test aid: byte offsets of the PCM workspace sections."""
     import ctypes
@@ -119,35 +140,49 @@ def _label_nc(label: torch.Tensor, n: int, c: int) -> torch.Tensor:
     return lab.contiguous()
 
 
+def fullres_norm_fwd(p: torch.Tensor, label: torch.Tensor, size: Optional[Tuple[int, int]] = None):
+    """Raw K1b forward.  Returns (out [N,C,oh,ow], minmax [N,C,4] saved for the backward, label [N,C] on device)."""
+    p = _require_cuda_f32("p", p.detach())
+    n, c, H, W = p.shape
+    oh, ow = (H, W) if size is None else (int(size[0]), int(size[1]))
+    lab = _label_nc(label, n, c).to(p.device)
+    out = torch.empty(n, c, oh, ow, dtype=torch.float32, device=p.device)
+    minmax = torch.empty(n, c, 4, dtype=torch.float32, device=p.device)
+    with torch.cuda.device(p.device):
+        ws = _workspace(_lib.OP_FULLRES_NORM, p.device, N=n, C=c, h=H, w=W)
+        check(_lib.lib().wsegk_fullres_norm_fwd(_ptr(p), _ptr(lab), _ptr(out), _ptr(minmax), n, c, H, W, oh, ow,
+                                                _ptr(ws), ws.numel(), _stream(p)), "wsegk_fullres_norm_fwd")
+    return out, minmax, lab
+
+
+def fullres_norm_bwd(p: torch.Tensor, lab: torch.Tensor, minmax: torch.Tensor, grad_out: torch.Tensor,
+                     out_size: Tuple[int, int]) -> torch.Tensor:
+    """Raw K1b backward: grad_out [N,C,oh,ow] -> grad_p [N,C,H,W]."""
+    p = _require_cuda_f32("p", p.detach())
+    grad_out = _require_cuda_f32("grad_out", grad_out)
+    n, c, H, W = p.shape
+    oh, ow = int(out_size[0]), int(out_size[1])
+    grad_p = torch.empty_like(p)
+    with torch.cuda.device(p.device):
+        ws = _workspace(_lib.OP_FULLRES_NORM, p.device, N=n, C=c, h=H, w=W)
+        check(_lib.lib().wsegk_fullres_norm_bwd(_ptr(p), _ptr(lab), _ptr(minmax), _ptr(grad_out), _ptr(grad_p),
+                                                n, c, H, W, oh, ow, _ptr(ws), ws.numel(), _stream(p)),
+              "wsegk_fullres_norm_bwd")
+    return grad_p
+
+
 class _FullresNorm(torch.autograd.Function):
     @staticmethod
     def forward(ctx, p, label, size):
-        p = _require_cuda_f32("p", p)
-        n, c, H, W = p.shape
-        oh, ow = (H, W) if size is None else (int(size[0]), int(size[1]))
-        lab = _label_nc(label, n, c).to(p.device)
-        out = torch.empty(n, c, oh, ow, dtype=torch.float32, device=p.device)
-        minmax = torch.empty(n, c, 4, dtype=torch.float32, device=p.device)
-        with torch.cuda.device(p.device):
-            ws = _workspace(_lib.OP_FULLRES_NORM, p.device, N=n, C=c, h=H, w=W)
-            check(_lib.lib().wsegk_fullres_norm_fwd(_ptr(p), _ptr(lab), _ptr(out), _ptr(minmax), n, c, H, W, oh, ow,
-                                                    _ptr(ws), ws.numel(), _stream(p)), "wsegk_fullres_norm_fwd")
+        out, minmax, lab = fullres_norm_fwd(p, label, size)
         ctx.save_for_backward(p, lab, minmax)
-        ctx.dims = (n, c, H, W, oh, ow)
+        ctx.out_size = tuple(out.shape[-2:])
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
         p, lab, minmax = ctx.saved_tensors
-        n, c, H, W, oh, ow = ctx.dims
-        grad_out = _require_cuda_f32("grad_out", grad_out)
-        grad_p = torch.empty_like(p)
-        with torch.cuda.device(p.device):
-            ws = _workspace(_lib.OP_FULLRES_NORM, p.device, N=n, C=c, h=H, w=W)
-            check(_lib.lib().wsegk_fullres_norm_bwd(_ptr(p), _ptr(lab), _ptr(minmax), _ptr(grad_out), _ptr(grad_p),
-                                                    n, c, H, W, oh, ow, _ptr(ws), ws.numel(), _stream(p)),
-                  "wsegk_fullres_norm_bwd")
-        return grad_p, None, None
+        return fullres_norm_bwd(p, lab, minmax, grad_out, ctx.out_size), None, None
 
 
 def fullres_norm(p: torch.Tensor, label: torch.Tensor, size: Optional[Tuple[int, int]] = None) -> torch.Tensor:
