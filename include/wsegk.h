@@ -60,8 +60,9 @@ int wsegk_cam_norm_fwd(const float* cam, float* cam_norm, int N, int C, int h, i
 /* K2 forward — replaces network/resnet38_contrast.py:70-73 (PCM after the f9 conv):
  *   fh = f/(|f|_2+1e-5); aff = relu(fh^T fh); aff /= colsum(aff)+1e-5; cam_rv = cam_norm @ aff.
  * f [N,K,h,w], cam_norm [N,C,h,w] -> cam_rv [N,C,h,w].  The HWxHW affinity lives only in TMEM.
- * BF16 operands (cam_norm as a hi+lo BF16 pair), FP32 accumulation.  K % 16 == 0, K <= 192, C <= 23.
- * The workspace is left holding what pcm_bwd needs (normalised features, norms, column sums). */
+ * FP16 tensor-core operands (hi+lo pairs in precise mode, see wsegk_pcm_set_mode), FP32 accumulation.
+ * K % 32 == 0, K <= 192, C <= 23.  The workspace is left holding what pcm_bwd needs (normalised features,
+ * norms, column sums and the sign bits of S). */
 int wsegk_pcm_fwd(const float* f, const float* cam_norm, float* cam_rv, int N, int C, int K, int h, int w,
                   void* workspace, size_t workspace_bytes, wsegk_stream_t stream);
 
@@ -130,9 +131,20 @@ int wsegk_contrast_loss_fwd_bwd(const float* x1, const float* x2, const float* p
 unsigned long long wsegk_debug_launch_count(void);
 int wsegk_debug_pcm_profile(int enable);
 int wsegk_debug_pcm_main_ms(float* fwd_ms, float* bwd_ms);
+/* Timeline aid: when non-null (per host thread), CTA (0,0,0) of the next pcm_fwd main kernels writes clock64() stamps
+ * into this DEVICE buffer of 768 int64: [role 0 producer | 1 MMA issuer | 2 first TMEM warp][stage < 64][4 events]. */
+int wsegk_debug_pcm_trace(long long* device_buffer);
+
+/* PCM precision mode, process-wide (default 1):
+ *   1 "precise": FP16 hi+lo split operands, S = hi.hi + hi.lo + lo.hi (~2^-21), backward factors split in BF16;
+ *                the sign mask of S that the backward consumes then agrees with an FP32 evaluation.
+ *   0 "fast"   : single FP16 / BF16 products (cam_rv still within 1e-3; gradient terms with |S| < ~1e-4 may flip). */
+int wsegk_pcm_set_mode(int mode);
+int wsegk_pcm_get_mode(void);
 
 /* Test aid: byte offsets of the PCM workspace sections, in the order
- * {fhat, camb, inv_norm, dsum, part, uaug, vaug, dfhat, total_bytes, nsplit, T, HWp}.  Returns how many were written. */
+ * {fa_hi, fa_lo, fb_hi, fb_lo, camb, inv_norm, dsum, part, mask, ua, vb, dfhat, bound, total_bytes, nsplit, PJ, HWpj,
+ *  wb, NS, HWpi}.  Returns how many were written. */
 int wsegk_debug_pcm_layout(int N, int C, int K, int h, int w, size_t* out, int n_out);
 
 #ifdef __cplusplus

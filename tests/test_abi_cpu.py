@@ -37,10 +37,13 @@ def test_every_declared_symbol_is_exported(lib):
 def test_version_and_workspace_sizes(lib):
     assert lib.wsegk_version() >= 100
     pcm = _lib.workspace_bytes(_lib.OP_PCM, N=8, C=21, K=192, h=56, w=56)
-    assert pcm % 1024 == 0 and 40e6 < pcm < 120e6
+    assert pcm % 1024 == 0 and 60e6 < pcm < 200e6
     lay = ops.pcm_layout(8, 21, 192, 56, 56)
-    assert lay["T"] == 25 and lay["HWp"] == 3200 and lay["bytes"] == pcm
-    assert lay["camb"] - lay["fhat"] == 8 * 25 * 128 * 192 * 2
+    # 56x56 = 3136 pixels: 13 CTA pairs of 256 rows, B tiles of 56 rows -> 28 stages of 112 columns, no padding along i
+    assert (lay["PJ"], lay["HWpj"], lay["wb"], lay["NS"], lay["HWpi"]) == (13, 3328, 56, 28, 3136)
+    assert lay["bytes"] == pcm and lay["fa_lo"] - lay["fa_hi"] == 8 * 26 * 128 * 192 * 2
+    lay = ops.pcm_layout(1, 21, 192, 64, 64)
+    assert (lay["wb"], lay["NS"], lay["HWpi"]) == (64, 32, 4096)
     assert _lib.workspace_bytes(_lib.OP_CONTRAST_LOSS, N=8, C=21, D=128, h=16, w=16) > 2 * 2048 * 4 * 42
     assert _lib.workspace_bytes(99, N=1, C=1, K=16, h=1, w=1) == 0
     assert "unknown op" in _lib.last_error()

@@ -94,6 +94,48 @@ def test_pcm_backward_vs_oracle(cuda_dev, n, h, w, positive):
     assert err <= ops.PCM_GRAD_TOL, (err, "grad_f, relative Frobenius error")
 
 
+def test_pcm_fast_mode(cuda_dev):
+    """The single-product mode: cam_rv still within 1e-3; the gradient only up to sign flips of near-zero affinities."""
+    d = synth.pcm_inputs(2, 56, 56, seed=11)
+    cam, f, g = d["cam"].to(cuda_dev), d["f"].to(cuda_dev), d["grad_out"].to(cuda_dev)
+    camn = ops.cam_norm(cam)
+    f_ref = f.clone().requires_grad_(True)
+    ref = R.pcm(camn, f_ref)
+    ref.backward(g)
+    ops.set_pcm_mode("fast")
+    try:
+        assert ops.get_pcm_mode() == "fast"
+        f_my = f.clone().requires_grad_(True)
+        out = ops.pcm(camn, f_my)
+        out.backward(g)
+    finally:
+        ops.set_pcm_mode("precise")
+    assert rel_max(out, ref) <= TOL
+    assert rel_fro(f_my.grad, f_ref.grad) <= ops.PCM_GRAD_TOL_FAST
+
+
+def test_pcm_sign_mask_matches_fp64(cuda_dev):
+    """Precise mode: the sign bits of S the forward hands to the backward agree with an fp64 evaluation except where
+    |S| is at fp32 rounding level (< 5e-7), for at most 1e-5 of the entries."""
+    n, h, w, k, c = 2, 40, 36, 192, 21
+    d = synth.pcm_inputs(n, h, w, seed=13)
+    f = d["f"].to(cuda_dev)
+    camn = ops.cam_norm(d["cam"].to(cuda_dev))
+    _, ws = ops.pcm_forward(camn, f)
+    lay = ops.pcm_layout(n, c, k, h, w)
+    HW, HWpj, HWpi, NS, wb = h * w, lay["HWpj"], lay["HWpi"], lay["NS"], lay["wb"]
+    fh = f.reshape(n, k, HW).double()
+    fh = (fh / (fh.norm(dim=1, keepdim=True) + 1e-5)).transpose(1, 2)
+    S = torch.matmul(fh, fh.transpose(1, 2))
+    raw = ws[lay["mask"]:lay["mask"] + n * NS * HWpj * 16].view(torch.int32).reshape(n, NS, HWpj, 4)
+    order = torch.stack([torch.arange(16), torch.arange(16) + 16], 1).reshape(-1).to(cuda_dev).int()
+    bits = ((raw.unsqueeze(-1) >> order) & 1).reshape(n, NS, HWpj, 128)[..., :2 * wb]
+    bits = bits.permute(0, 2, 1, 3).reshape(n, HWpj, HWpi)[:, :HW, :HW].bool()
+    bad = bits != (S > 0)
+    assert int(bad.sum()) <= 1e-5 * bad.numel()
+    assert int(bad.sum()) == 0 or float(S[bad].abs().max()) < 5e-7
+
+
 def test_pcm_backward_golden(cuda_dev, golden_dir):
     g = np.load(os.path.join(golden_dir, "pcm_n2_20x13.npz"))
     c = PCM_CASE
@@ -126,7 +168,7 @@ def test_pcm_properties_full_size(cuda_dev):
 
 def test_pcm_rejects_bad_arguments(cuda_dev):
     camn = torch.zeros(1, 21, 4, 4, device=cuda_dev)
-    with pytest.raises(RuntimeError, match="K % 16"):
+    with pytest.raises(RuntimeError, match="K % 32"):
         ops.pcm_forward(camn, torch.zeros(1, 100, 4, 4, device=cuda_dev))
     with pytest.raises(RuntimeError, match="does not match"):
         ops.pcm_forward(camn, torch.zeros(1, 192, 5, 4, device=cuda_dev))

@@ -1,5 +1,7 @@
-"""First-light diagnostics for the PCM forward on a B200: checks each stage against torch on the GPU."""
-import sys, os, time
+"""Bring-up diagnostics for the CTA-pair PCM kernels on a B200: every stage against torch on the GPU.
+usage: python tools/diag_pcm.py [fast|precise] [case ...]"""
+import os
+import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from wseg_b200 import ops, synth
@@ -9,71 +11,102 @@ dev = torch.device("cuda:0")
 torch.backends.cuda.matmul.allow_tf32 = False
 
 
-def decode_tiles(raw_u8, n, T, rows, cols):
-    """[n][T] canonical K-major tiles of rows x cols bf16 -> [n, T*rows(if rows is pixel) ...]"""
-    x = raw_u8.view(torch.bfloat16).reshape(n, T, cols // 8, rows, 8)      # [n,T,g,r,e]
-    return x.permute(0, 1, 3, 2, 4).reshape(n, T, rows, cols).float()
+def section(ws, lay, name, nbytes):
+    return ws[lay[name]:lay[name] + nbytes]
 
 
-def run(n, h, w, k=192, c=21, seed=0, positive=False):
+def decode_tiles(raw_u8, n, tiles, rows, cols, dtype=torch.float16):
+    x = raw_u8.view(dtype).reshape(n, tiles, cols // 8, rows, 8)          # [n,T,g,r,e]
+    return x.permute(0, 1, 3, 2, 4).reshape(n, tiles * rows, cols).float()
+
+
+def run(n, h, w, k=192, c=21, seed=0, positive=False, time_it=True):
+    mode = ops.get_pcm_mode()
     d = synth.pcm_inputs(n, h, w, seed, k=k, c=c, positive=positive)
-    cam, f = d["cam"].to(dev), d["f"].to(dev)
+    cam, f, g = d["cam"].to(dev), d["f"].to(dev), d["grad_out"].to(dev)
     camn = ops.cam_norm(cam)
-    ref_camn = R.cam_d_norm(cam)
-    print(f"[{n}x{h}x{w}] cam_norm max abs err {(camn - ref_camn).abs().max().item():.3e}")
+    lay = ops.pcm_layout(n, c, k, h, w)
+    PJ, HWpj, wb, NS, HWpi, ns = lay["PJ"], lay["HWpj"], lay["wb"], lay["NS"], lay["HWpi"], lay["nsplit"]
+    HW = h * w
+    print(f"[{mode} {n}x{h}x{w} pos={positive}] PJ={PJ} wb={wb} NS={NS} nsplit={ns} ws={lay['bytes'] / 1e6:.1f} MB")
     out, ws = ops.pcm_forward(camn, f)
     torch.cuda.synchronize()
-    lay = ops.pcm_layout(n, c, k, h, w)
-    T, HWp, ns = lay["T"], lay["HWp"], lay["nsplit"]
-    HW = h * w
-    fh = f.reshape(n, k, HW)
+    # ---- prep
+    fh = f.reshape(n, k, HW).double()
     fh = fh / (fh.norm(dim=1, keepdim=True) + 1e-5)
-    fh_p = torch.zeros(n, HWp, k, device=dev)
-    fh_p[:, :HW] = fh.transpose(1, 2)
-    fh_bf = fh_p.bfloat16().float()
-    got_f = decode_tiles(ws[lay["fhat"]:lay["fhat"] + n * T * 128 * k * 2], n, T, 128, k).reshape(n, HWp, k)
-    print(f"  prep f: max abs diff vs bf16(fhat) {(got_f - fh_bf).abs().max().item():.3e}")
-    camb_raw = ws[lay["camb"]:lay["camb"] + n * T * 48 * 128 * 2].view(torch.bfloat16).reshape(n, T, 16, 48, 8)
-    camb = camb_raw.permute(0, 3, 1, 2, 4).reshape(n, 48, HWp).float()       # [n,row,pixel]
-    cam_p = torch.zeros(n, c, HWp, device=dev)
-    cam_p[:, :, :HW] = ref_camn.reshape(n, c, HW)
-    hi = cam_p.bfloat16().float()
-    lo = (cam_p - hi).bfloat16().float()
-    print(f"  prep cam: hi {(camb[:, :c] - hi).abs().max().item():.3e} lo {(camb[:, 24:24 + c] - lo).abs().max().item():.3e}"
-          f" ones {(camb[:, c, :HW] - 1).abs().max().item():.3e}")
-    S = torch.matmul(fh_bf, fh_bf.transpose(1, 2))                              # [n, j, i]
-    P = torch.relu(S).bfloat16().float()
-    num = torch.matmul(P, camb.transpose(1, 2))                                 # [n, j, 48]
-    part = ws[lay["part"]:lay["part"] + n * ns * HWp * 48 * 4].view(torch.float32).reshape(n, ns, HWp, 48).sum(1)
-    err = (part - num).abs()
-    print(f"  main: partial sums max abs err {err.max().item():.3e} (scale {num.abs().max().item():.3e}); "
-          f"colsum err {(part[..., c] - num[..., c]).abs().max().item():.3e}")
-    if err.max().item() > 1e-2 * num.abs().max().item():
-        bad = (err > 1e-2 * num.abs().max()).nonzero()
-        print("  first bad entries (n, j, col):", bad[:8].tolist(), " count", bad.shape[0])
-        print("  got ", part[0, :4, :6].tolist())
-        print("  want", num[0, :4, :6].tolist())
-    ref = R.pcm(ref_camn, f)
+    fhp = torch.zeros(n, max(HWpj, HWpi), k, device=dev, dtype=torch.float64)
+    fhp[:, :HW] = fh.transpose(1, 2)
+    hi = fhp.float().half().double()
+    a_hi = decode_tiles(section(ws, lay, "fa_hi", n * 2 * PJ * 128 * k * 2), n, 2 * PJ, 128, k).double()
+    b_hi = decode_tiles(section(ws, lay, "fb_hi", n * 2 * NS * wb * k * 2), n, 2 * NS, wb, k).double()
+    print(f"  prep: A-hi err {(a_hi - hi[:, :HWpj]).abs().max().item():.2e}  B-hi err {(b_hi - hi[:, :HWpi]).abs().max().item():.2e}")
+    if mode == "precise":
+        a_lo = decode_tiles(section(ws, lay, "fa_lo", n * 2 * PJ * 128 * k * 2), n, 2 * PJ, 128, k).double()
+        print(f"  prep: hi+lo residual {(a_hi + a_lo - fhp[:, :HWpj]).abs().max().item():.2e} (hi alone {(a_hi - fhp[:, :HWpj]).abs().max().item():.2e})")
+    # ---- S sign mask
+    S = torch.matmul(fhp[:, :HWpj], fhp[:, :HWpi].transpose(1, 2))              # [n, j, i] fp64
+    mask_raw = section(ws, lay, "mask", n * NS * HWpj * 16).view(torch.int32).reshape(n, NS, HWpj, 4)
+    # word c, bit m = column 32c + 2m, bit 16+m = column 32c + 2m + 1
+    order = torch.stack([torch.arange(16), torch.arange(16) + 16], 1).reshape(-1).to(dev).int()
+    bits = ((mask_raw.unsqueeze(-1) >> order) & 1).reshape(n, NS, HWpj, 128)
+    bits = bits[..., :2 * wb].permute(0, 2, 1, 3).reshape(n, HWpj, HWpi).bool()
+    want = S > 0
+    live = torch.zeros_like(want)
+    live[:, :HW, :HW] = True
+    bad = (bits != want) & live
+    nbad = int(bad.sum())
+    print(f"  mask: {nbad} of {int(live.sum())} sign bits differ from fp64 ({nbad / max(1, int(live.sum())):.2e})"
+          + (f"; max |S| among them {S[bad].abs().max().item():.2e}" if nbad else ""))
+    # ---- partial sums
+    part = section(ws, lay, "part", n * ns * HWpj * 64 * 4).view(torch.float32).reshape(n, ns, HWpj, 64).sum(1).double()
+    camp = torch.zeros(n, c, HWpi, device=dev, dtype=torch.float64)
+    camp[:, :, :HW] = camn.reshape(n, c, HW).double()
+    P = torch.relu(S)
+    num = torch.matmul(P, camp.transpose(1, 2))                                   # [n, j, c]
+    colsum = P[:, :, :HW].sum(-1)
+    got_num = part[..., :c] + part[..., 32:32 + c]
+    e_num = (got_num[:, :HW] - num[:, :HW]).abs().max().item()
+    e_col = (part[:, :HW, c] - colsum[:, :HW]).abs().max().item()
+    print(f"  main: numerator err {e_num:.2e} (scale {num.abs().max().item():.2e}); colsum err {e_col:.2e} (scale {colsum.max().item():.2e})")
+    ref = R.pcm(camn, f)
     e = (out - ref).abs().max().item()
-    print(f"  cam_rv: max abs err {e:.3e}, max |ref| {ref.abs().max().item():.3e}, rel(max) {e / ref.abs().max().item():.3e}")
-    # timing
-    for _ in range(3):
-        ops.pcm_forward(camn, f)
+    print(f"  cam_rv: max abs err {e:.3e}, rel(max) {e / ref.abs().max().item():.3e}")
+    # ---- backward
+    f_ref = f.clone().requires_grad_(True)
+    R.pcm(camn, f_ref).backward(g)
+    gm = ops.pcm_backward(f, camn, out, g, ws)
     torch.cuda.synchronize()
-    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
-    t0.record()
-    for _ in range(10):
-        ops.pcm_forward(camn, f)
-    t1.record(); torch.cuda.synchronize()
-    ms = t0.elapsed_time(t1) / 10
-    fl = 2.0 * n * HW * HW * (k + c)
-    print(f"  fwd {ms * 1e3:.1f} us  -> {fl / ms / 1e9:.1f} TFLOP/s algorithmic")
+    gr = f_ref.grad
+    print(f"  grad_f: rel(fro) {((gr - gm).norm() / gr.norm()).item():.3e}  rel(max) {((gr - gm).abs().max() / gr.abs().max()).item():.3e}")
+    if time_it:
+        ops.pcm_profile(True)
+        fw, bw = [], []
+        for i in range(8):
+            o2, ws2 = ops.pcm_forward(camn, f)
+            ops.pcm_backward(f, camn, o2, g, ws2)
+            a, b = ops.pcm_main_ms()
+            if i >= 3:
+                fw.append(a); bw.append(b)
+        ops.pcm_profile(False)
+        fl_f = 2.0 * n * HW * HW * (k + c); fl_b = 2.0 * n * HW * HW * (2 * k + c)
+        a, b = sum(fw) / len(fw), sum(bw) / len(bw)
+        print(f"  main kernels: fwd {a * 1e3:.1f} us ({fl_f / a / 1e9:.0f} TF/s alg)  bwd {b * 1e3:.1f} us ({fl_b / b / 1e9:.0f} TF/s alg)")
 
+
+CASES = {
+    "a": dict(n=1, h=16, w=16, seed=1),
+    "b": dict(n=2, h=20, w=13, seed=2),
+    "c": dict(n=1, h=64, w=64, seed=6, positive=True),
+    "d": dict(n=8, h=56, w=56, seed=3),
+    "e": dict(n=8, h=56, w=56, seed=4, positive=True),
+    "f": dict(n=1, h=94, w=125, seed=5),
+}
 
 if __name__ == "__main__":
-    print(torch.cuda.get_device_name(0))
-    run(1, 16, 16, seed=1)
-    run(2, 20, 13, seed=2)
-    run(8, 56, 56, seed=3)
-    run(8, 56, 56, seed=4, positive=True)
-    run(1, 94, 125, seed=5)
+    args = sys.argv[1:]
+    if args and args[0] in ("fast", "precise"):
+        ops.set_pcm_mode(args[0])
+        args = args[1:]
+    print(torch.cuda.get_device_name(0), "mode", ops.get_pcm_mode())
+    for name in (args or list(CASES)):
+        run(**CASES[name])

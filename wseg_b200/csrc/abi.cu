@@ -53,31 +53,65 @@ int check_device() {
     return WSEGK_OK;
 }
 
-// How many CTAs split one j-tile's loop over i-tiles, chosen so the grid covers the 148 SMs about twice.
-int pcm_split(int N, int T) {
-    int ctas = std::max(1, N * T);
-    int s = (2 * 148 + ctas - 1) / ctas;
-    s = std::max(1, std::min(s, std::min(T, 8)));
-    return s;
+static std::atomic<int> g_pcm_mode{1};
+int pcm_mode() { return g_pcm_mode.load(std::memory_order_relaxed); }
+
+// B-tile rows per CTA: the candidate that pads the i sweep least (ties: the larger tile, fewer stages).
+static int pick_wb(int HW) {
+    const int cands[3] = {64, 56, 48};
+    int best = 64;
+    long long best_pad = -1;
+    for (int wb : cands) {
+        const long long ns = (HW + 2 * wb - 1) / (2 * wb);
+        const long long padded = ns * 2 * wb;
+        if (best_pad < 0 || padded < best_pad) { best_pad = padded; best = wb; }
+    }
+    return best;
 }
 
-PcmPlan make_pcm_plan(void* ws, int N, int C, int K, int h, int w) {
+// How many CTA pairs split one j pair's sweep over the i stages: minimise (waves x stages per CTA + fixed cost).
+static int pick_nsplit(int N, int PJ, int NS) {
+    const int slots = 74;                 // CTA pairs resident at once (148 SMs, 1 CTA per SM)
+    int best = 1;
+    double best_cost = 1e30;
+    for (int s = 1; s <= 8 && s <= NS; ++s) {
+        const long long ctas = static_cast<long long>(N) * PJ * s;
+        const long long waves = (ctas + slots - 1) / slots;
+        const int per = (NS + s - 1) / s;
+        const double cost = static_cast<double>(waves) * (per + 2.5);     // ~2.5 stage-times of prologue/epilogue
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
+    }
+    return best;
+}
+
+PcmPlan make_pcm_plan(void* ws, int N, int C, int K, int h, int w, int precise) {
     PcmPlan p{};
     p.N = N; p.C = C; p.K = K; p.HW = h * w;
-    p.T = ceil_div(p.HW, kTile);
-    p.HWp = p.T * kTile;
-    p.nsplit = pcm_split(N, p.T);
-    p.tile_bytes = static_cast<size_t>(kTile) * K * 2;
+    p.PJ = ceil_div(p.HW, 2 * kTile);
+    p.HWpj = p.PJ * 2 * kTile;
+    p.wb = pick_wb(p.HW);
+    p.NS = ceil_div(p.HW, 2 * p.wb);
+    p.HWpi = p.NS * 2 * p.wb;
+    p.nsplit = pick_nsplit(N, p.PJ, p.NS);
+    p.precise = precise ? 1 : 0;
+    p.Ku = precise ? 3 * kAugK : kAugK;
+    p.a_tile_bytes = static_cast<size_t>(kTile) * K * 2;
+    p.b_tile_bytes = static_cast<size_t>(p.wb) * K * 2;
     Carver c(ws);
-    const size_t tiles = static_cast<size_t>(N) * p.T;
-    p.fhat = c.take<uint16_t>(tiles * kTile * K);
-    p.camb = c.take<uint16_t>(tiles * kCamRows * kTile);
-    p.inv_norm = c.take<float>(static_cast<size_t>(N) * p.HWp);
-    p.dsum = c.take<float>(static_cast<size_t>(N) * p.HWp);
-    p.part = c.take<float>(static_cast<size_t>(N) * p.nsplit * p.HWp * kCamRows);
-    p.uaug = c.take<uint16_t>(tiles * kTile * kAugRows);
-    p.vaug = c.take<uint16_t>(tiles * kTile * kAugRows);
-    p.dfhat = c.take<float>(static_cast<size_t>(N) * p.nsplit * p.HWp * K);
+    const size_t at = static_cast<size_t>(N) * 2 * p.PJ, bt = static_cast<size_t>(N) * 2 * p.NS;
+    p.fa_hi = c.take<uint16_t>(at * kTile * K);
+    p.fa_lo = c.take<uint16_t>(at * kTile * K);
+    p.fb_hi = c.take<uint16_t>(bt * p.wb * K);
+    p.fb_lo = c.take<uint16_t>(bt * p.wb * K);
+    p.camb = c.take<uint16_t>(static_cast<size_t>(N) * p.NS * 2 * (2 * p.wb) * kCamRows);
+    p.inv_norm = c.take<float>(static_cast<size_t>(N) * p.HWpj);
+    p.dsum = c.take<float>(static_cast<size_t>(N) * p.HWpj);
+    p.part = c.take<float>(static_cast<size_t>(N) * p.nsplit * p.HWpj * kONum);
+    p.mask = c.take<uint32_t>(static_cast<size_t>(N) * p.NS * p.HWpj * kMaskWords);
+    p.ua = c.take<uint16_t>(at * kTile * 3 * kAugK);
+    p.vb = c.take<uint16_t>(bt * p.wb * 3 * kAugK);
+    p.dfhat = c.take<float>(static_cast<size_t>(N) * p.nsplit * K * p.HWpj);
+    p.bound = c.take<float>(256);
     p.bytes = c.total();
     return p;
 }
@@ -98,7 +132,7 @@ extern "C" size_t wsegk_workspace_bytes(int op, int N, int C, int K, int D, int 
         case WSEGK_OP_CAM_NORM:
             return align_up(static_cast<size_t>(N) * C * sizeof(float), 1024);
         case WSEGK_OP_PCM:
-            return make_pcm_plan(nullptr, N, C, K, h, w).bytes;
+            return make_pcm_plan(nullptr, N, C, K, h, w, 1).bytes;   // mode-independent (sized for precise)
         case WSEGK_OP_FULLRES_NORM:
             return fullres_workspace_bytes(N, C);
         case WSEGK_OP_SEED_LABELS:
@@ -113,14 +147,27 @@ extern "C" size_t wsegk_workspace_bytes(int op, int N, int C, int K, int D, int 
     }
 }
 
+extern "C" int wsegk_pcm_set_mode(int mode) {
+    if (mode != 0 && mode != 1) {
+        set_error("pcm_set_mode: mode must be 0 (fast) or 1 (precise), got %d", mode);
+        return WSEGK_ERR_BAD_SHAPE;
+    }
+    g_pcm_mode.store(mode, std::memory_order_relaxed);
+    return WSEGK_OK;
+}
+
+extern "C" int wsegk_pcm_get_mode(void) { return pcm_mode(); }
+
 extern "C" int wsegk_debug_pcm_layout(int N, int C, int K, int h, int w, size_t* out, int n_out) {
     if (!out || N <= 0 || h <= 0 || w <= 0) return 0;
-    PcmPlan p = make_pcm_plan(nullptr, N, C, K, h, w);
+    PcmPlan p = make_pcm_plan(nullptr, N, C, K, h, w, 1);
     auto off = [](const void* q) { return reinterpret_cast<size_t>(q); };   // base is nullptr => offsets
-    const size_t v[12] = {off(p.fhat), off(p.camb), off(p.inv_norm), off(p.dsum), off(p.part), off(p.uaug),
-                          off(p.vaug), off(p.dfhat), p.bytes, static_cast<size_t>(p.nsplit),
-                          static_cast<size_t>(p.T), static_cast<size_t>(p.HWp)};
+    const size_t v[20] = {off(p.fa_hi), off(p.fa_lo), off(p.fb_hi), off(p.fb_lo), off(p.camb), off(p.inv_norm),
+                          off(p.dsum), off(p.part), off(p.mask), off(p.ua), off(p.vb), off(p.dfhat), off(p.bound),
+                          p.bytes, static_cast<size_t>(p.nsplit), static_cast<size_t>(p.PJ),
+                          static_cast<size_t>(p.HWpj), static_cast<size_t>(p.wb), static_cast<size_t>(p.NS),
+                          static_cast<size_t>(p.HWpi)};
     int k = 0;
-    for (; k < n_out && k < 12; ++k) out[k] = v[k];
+    for (; k < n_out && k < 20; ++k) out[k] = v[k];
     return k;
 }

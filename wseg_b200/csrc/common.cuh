@@ -11,12 +11,13 @@
 
 namespace wsegk {
 
-constexpr int kTile = 128;        // pixels per PCM tile (UMMA M and N)
-constexpr int kCamRows = 48;      // PCM forward B-operand rows: 24 "hi" rows (21 classes + ones row) + 24 "lo"
-constexpr int kCamHalf = 24;
-constexpr int kAugRows = 48;      // PCM backward rank-44 factor, padded
-constexpr int kMaxClasses = 23;   // C + ones row must fit kCamHalf
+constexpr int kTile = 128;        // pixels per A-side (j) PCM tile = rows one CTA owns (UMMA M = 256 over the CTA pair)
+constexpr int kCamRows = 32;      // PCM forward: cam operand rows per CTA (rank 0: cam hi + ones row, rank 1: cam lo)
+constexpr int kONum = 64;         // forward accumulator columns (2 x kCamRows)
+constexpr int kAugK = 48;         // PCM backward rank-(2C+2) factor, padded to a multiple of 16
+constexpr int kMaxClasses = 23;   // 2C + 2 <= kAugK
 constexpr int kMaxPcmK = 192;
+constexpr int kMaskWords = 4;     // sign-mask words per (stage, row): up to 128 columns
 
 void set_error(const char* fmt, ...);
 void count_launches(int n);   // diagnostics: wsegk_debug_launch_count()
@@ -63,21 +64,36 @@ struct Carver {
 };
 
 // ---- PCM workspace (shared by forward and backward) -------------------------------------------
+// A CTA pair owns 256 consecutive "j" pixels (two 128-row A tiles) and sweeps the "i" pixels in stages of
+// 2*wb pixels (one wb-row B tile per CTA).  All operand tiles are stored pre-tiled in the UMMA canonical
+// no-swizzle K-major layout so each is ONE contiguous bulk copy:
+//   chunk (row r, 8-element K group g) of an R-row tile lives at byte (g*R + r)*16.
 struct PcmPlan {
-    int N, C, K, HW, T, HWp, nsplit;
-    size_t tile_bytes;       // one 128-pixel x K bf16 operand tile
+    int N, C, K, HW;
+    int PJ;          // CTA pairs along j:  ceil(HW / 256)
+    int HWpj;        // PJ * 256
+    int wb;          // B-tile rows per CTA (64, 56 or 48)
+    int NS;          // stages along i: ceil(HW / (2*wb))
+    int HWpi;        // NS * 2 * wb
+    int nsplit;      // CTAs (pairs) splitting one j pair's sweep
+    int precise;     // 1: fp16 hi+lo split operands (3 S products, 3 T products); 0: single pass
+    size_t a_tile_bytes, b_tile_bytes;
     // sections
-    uint16_t* fhat;          // [N][T] tiles, canonical no-swizzle K-major layout, bf16
-    uint16_t* camb;          // [N][T] tiles of [48 x 128] bf16 (cam hi / ones / cam lo), K-major
-    float* inv_norm;         // [N][HWp]   1/(|f|+1e-5)
-    float* dsum;             // [N][HWp]   column sums of relu(S) + 1e-5
-    float* part;             // [N][nsplit][HWp][48] forward partial numerators
-    uint16_t* uaug;          // [N][T] tiles of [128 x 48] bf16   backward factor U (K-major)
-    uint16_t* vaug;          // [N][T] tiles of [128 x 48] bf16   backward factor V (K-major)
-    float* dfhat;            // [N][HWp][K] fp32 gradient w.r.t. normalised features (pixel-major)
+    uint16_t* fa_hi;  uint16_t* fa_lo;    // [N][2*PJ] A tiles of normalised features (fp16 hi / residual)
+    uint16_t* fb_hi;  uint16_t* fb_lo;    // [N][2*NS] B tiles (wb rows) of the same
+    uint16_t* camb;                        // [N][NS][2 ranks][2wb/8][32 rows][8] fp16 cam operand blocks
+    float* inv_norm;                       // [N][HWpj]   1/(|f|+1e-5)
+    float* dsum;                           // [N][HWpj]   column sums of relu(S) + 1e-5
+    float* part;                           // [N][nsplit][HWpj][64] forward partial numerators
+    uint32_t* mask;                        // [N][NS][HWpj][4] sign bits of S (row j, stage columns)
+    uint16_t* ua;                          // [N][2*PJ] A tiles [128 x Ku] bf16 backward factor U
+    uint16_t* vb;                          // [N][2*NS] B tiles [wb x Ku] bf16 backward factor V
+    float* dfhat;                          // [N][nsplit][K][HWpj] fp32 partial gradient w.r.t. normalised features
+    float* bound;                          // [1] upper bound of |T| (as float bits, atomicMax)
+    int Ku;                                // 48 (fast) or 144 (precise: [hi|hi|lo] x [hi|lo|hi])
     size_t bytes;
 };
-PcmPlan make_pcm_plan(void* ws, int N, int C, int K, int h, int w);
-int pcm_split(int N, int T);
+PcmPlan make_pcm_plan(void* ws, int N, int C, int K, int h, int w, int precise);
+int pcm_mode();     // current process-wide mode (wsegk_pcm_set_mode): 1 precise (default), 0 fast
 
 }  // namespace wsegk

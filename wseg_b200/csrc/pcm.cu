@@ -4,13 +4,25 @@
 //   S    = fh fh^T  (HW x HW, symmetric),  A = relu(S),  D_j = sum_i A_ij + 1e-5
 //   out[c,j] = sum_i cam[c,i] A_ij / D_j
 //
-// Design (B200): the HWxHW affinity never exists in HBM.  A CTA owns a 128-pixel j-tile and streams
-// 128-pixel i-tiles through shared memory with bulk TMA copies; tcgen05 computes S^T tile = Fj Fi^T into
-// TMEM, four warps apply ReLU and write the BF16 result back into TMEM, and a second tcgen05 MMA with the
-// A operand in TMEM multiplies it by the [cam_hi ; 1 ; cam_lo] rows of the same i-tile, so numerators and
-// the column sum D_j come out of one accumulator.  Operands are stored by the prep kernels directly in
-// the UMMA canonical no-swizzle layout, so every tile is one contiguous bulk copy (no tensor maps).
+// Design (B200).  The HW x HW affinity never exists in HBM.  A CTA PAIR (thread-block cluster of 2, tcgen05
+// cta_group::2, UMMA M = 256) owns 256 "j" pixels and sweeps the "i" pixels in stages of 2*wb pixels: each CTA
+// bulk-copies ONE wb-row tile per stage (half the L2 traffic of two independent CTAs), the leader CTA issues
+//   S^T tile [256 x 2wb] = Fj Fi^T                      (SS MMA, FP16 operands, FP32 accumulators in TMEM)
+// four warps per CTA turn their 128 TMEM lanes into relu(S) as packed FP16 IN PLACE (aliasing the accumulator)
+// and record the sign bits of S, and a second MMA with the A operand in TMEM multiplies by the
+// [cam_hi ; 1 | cam_lo] rows of the same pixels, so numerators and the column sum D_j share one accumulator.
+//
+// Precision modes (wsegk_pcm_set_mode).  "precise" (default) splits fh into FP16 hi + residual lo and accumulates
+// hi*hi + hi*lo + lo*hi (about 2^-21 relative), because the BACKWARD needs the sign of S: d relu is a step, and a
+// sign flipped by operand rounding adds or drops a whole term of the gradient.  The forward stores the sign bits
+// (16 bytes per row and stage); the backward reads them instead of recomputing S, so it only does the rank-(2C+2)
+// product T = U V^T and dFh_j += (mask .* T) Fi on the tensor cores.  "fast" uses single FP16 products.
+//
+// Operands are stored by the prep kernels directly in the UMMA canonical no-swizzle layout, so every tile is one
+// contiguous bulk copy (cp.async.bulk, no tensor maps).
+#include <algorithm>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -20,21 +32,27 @@ namespace wsegk {
 // ------------------------------------------------------------------------------------------------
 // operand preparation
 // ------------------------------------------------------------------------------------------------
-// Canonical K-major tile of R rows x KK bf16 columns: 16-byte chunk (row r, column group g) lives at
-// chunk index g*R + r, i.e. core matrices (8 rows x 16 B) are 128 contiguous bytes, SBO = 128 B,
-// LBO = R*16 B.
+// Canonical K-major tile of R rows x KK 16-bit columns: 16-byte chunk (row r, column group g) lives at
+// chunk index g*R + r, i.e. core matrices (8 rows x 16 B) are 128 contiguous bytes, SBO = 128 B, LBO = R*16 B.
 
-// f [N,K,HW] fp32 -> fhat tiles (bf16) + inv_norm.  One CTA per (tile, image); 256 threads.
-__global__ void __launch_bounds__(256) pcm_prep_f_kernel(const float* __restrict__ f,
-                                                         uint16_t* __restrict__ fhat,
-                                                         float* __restrict__ inv_norm, int K, int HW,
-                                                         int T, int HWp) {
+__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
+    return static_cast<uint32_t>(__half_as_ushort(a)) | (static_cast<uint32_t>(__half_as_ushort(b)) << 16);
+}
+
+// f [N,K,HW] fp32 -> normalised features as A tiles (128 rows) and B tiles (wb rows), FP16 hi (+ lo), + inv_norm.
+// One CTA per (128 pixels, image); 256 threads.
+template <bool kLo>
+__global__ void __launch_bounds__(256) pcm_prep_f_kernel(const float* __restrict__ f, uint4* __restrict__ fa_hi,
+                                                         uint4* __restrict__ fa_lo, uint4* __restrict__ fb_hi,
+                                                         uint4* __restrict__ fb_lo, float* __restrict__ inv_norm,
+                                                         int K, int HW, int PJ, int NS, int wb) {
     extern __shared__ float s_val[];            // [K][129]
     __shared__ float s_part[2][kTile];
     __shared__ float s_inv[kTile];
     const int t = blockIdx.x, n = blockIdx.y;
     const int px = threadIdx.x & 127, half = threadIdx.x >> 7;
     const int p = t * kTile + px;
+    const int HWpj = PJ * 2 * kTile, HWpi = NS * 2 * wb;
     const float* src = f + static_cast<size_t>(n) * K * HW + p;
     float ss = 0.f;
     for (int k = half; k < K; k += 2) {
@@ -48,205 +66,324 @@ __global__ void __launch_bounds__(256) pcm_prep_f_kernel(const float* __restrict
         float nrm = sqrtf(s_part[0][px] + s_part[1][px]);
         float inv = 1.f / (nrm + 1e-5f);
         s_inv[px] = inv;
-        inv_norm[static_cast<size_t>(n) * HWp + p] = (p < HW) ? inv : 0.f;
+        if (p < HWpj) inv_norm[static_cast<size_t>(n) * HWpj + p] = (p < HW) ? inv : 0.f;
     }
     __syncthreads();
-    uint4* dst = reinterpret_cast<uint4*>(fhat + (static_cast<size_t>(n) * T + t) * kTile * K);
     const int groups = K >> 3;
     for (int chunk = threadIdx.x; chunk < groups * kTile; chunk += blockDim.x) {
         const int g = chunk >> 7, r = chunk & 127;
+        const int pp = t * kTile + r;
         const float inv = s_inv[r];
         const float* v = s_val + (g * 8) * 129 + r;
-        uint4 o;
-        o.x = pack_bf16x2(v[0 * 129] * inv, v[1 * 129] * inv);
-        o.y = pack_bf16x2(v[2 * 129] * inv, v[3 * 129] * inv);
-        o.z = pack_bf16x2(v[4 * 129] * inv, v[5 * 129] * inv);
-        o.w = pack_bf16x2(v[6 * 129] * inv, v[7 * 129] * inv);
-        dst[chunk] = o;
+        __half hi[8], lo[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float x = v[e * 129] * inv;
+            hi[e] = __float2half_rn(x);
+            lo[e] = __float2half_rn(x - __half2float(hi[e]));
+        }
+        const uint4 ohi = make_uint4(pack_h2(hi[0], hi[1]), pack_h2(hi[2], hi[3]), pack_h2(hi[4], hi[5]),
+                                     pack_h2(hi[6], hi[7]));
+        const uint4 olo = make_uint4(pack_h2(lo[0], lo[1]), pack_h2(lo[2], lo[3]), pack_h2(lo[4], lo[5]),
+                                     pack_h2(lo[6], lo[7]));
+        if (pp < HWpj) {
+            const size_t ia = ((static_cast<size_t>(n) * 2 * PJ + t) * groups + g) * kTile + r;
+            fa_hi[ia] = ohi;
+            if (kLo) fa_lo[ia] = olo;
+        }
+        if (pp < HWpi) {
+            const int tb = pp / wb, rb = pp - tb * wb;
+            const size_t ib = ((static_cast<size_t>(n) * 2 * NS + tb) * groups + g) * wb + rb;
+            fb_hi[ib] = ohi;
+            if (kLo) fb_lo[ib] = olo;
+        }
     }
 }
 
-// cam_norm [N,C,HW] fp32 -> B-operand tiles [48 rows x 128 pixels] bf16, K-major (K = pixel):
-//   rows 0..C-1 = bf16(cam), row C = 1 (column-sum row), rows 24..24+C-1 = bf16(cam - hi), others 0.
-__global__ void __launch_bounds__(128) pcm_prep_cam_kernel(const float* __restrict__ cam,
-                                                           uint16_t* __restrict__ camb, int C, int HW,
-                                                           int T) {
-    __shared__ __align__(16) uint16_t s_tile[kCamRows * kTile];   // chunk (row, pixel group g) at g*48 + row
-    const int t = blockIdx.x, n = blockIdx.y;
-    const int px = threadIdx.x;
-    const int p = t * kTile + px;
-    const bool live = p < HW;
+// cam_norm [N,C,HW] fp32 -> per (image, stage) two operand blocks of [32 rows x 2wb pixels] fp16, K-major (K = pixel):
+//   rank 0 block: rows 0..C-1 = fp16(cam), row C = 1 (column-sum row), others 0;   rank 1 block: rows 0..C-1 = cam - hi.
+__global__ void __launch_bounds__(128) pcm_prep_cam_kernel(const float* __restrict__ cam, uint4* __restrict__ camb,
+                                                           int C, int HW, int NS, int wb) {
+    __shared__ __align__(16) uint16_t s_blk[2 * 16 * kCamRows * 8];   // [rank][pixel group g][row][8]
+    const int s = blockIdx.x, n = blockIdx.y;
+    const int q = threadIdx.x;
+    const int ncol = 2 * wb;
+    const int p = s * ncol + q;
+    const bool live = q < ncol && p < HW;
     const float* src = cam + static_cast<size_t>(n) * C * HW + p;
-    const int g = px >> 3, e = px & 7;
-    auto put = [&](int row, float v) {
-        s_tile[(g * kCamRows + row) * 8 + e] = __bfloat16_as_ushort(__float2bfloat16_rn(v));
-    };
-    for (int c = 0; c < kCamHalf; ++c) {
-        float hi = 0.f, lo = 0.f;
-        if (live && c < C) {
-            float v = __ldg(src + static_cast<size_t>(c) * HW);
-            hi = __bfloat162float(__float2bfloat16_rn(v));
-            lo = v - hi;
-        } else if (live && c == C) {
-            hi = 1.f;
+    if (q < ncol) {
+        const int g = q >> 3, e = q & 7;
+        const int G = ncol >> 3;
+        for (int c = 0; c < kCamRows; ++c) {
+            float hi = 0.f, lo = 0.f;
+            if (live && c < C) {
+                const float v = __ldg(src + static_cast<size_t>(c) * HW);
+                hi = __half2float(__float2half_rn(v));
+                lo = v - hi;
+            } else if (live && c == C) {
+                hi = 1.f;
+            }
+            s_blk[((0 * G + g) * kCamRows + c) * 8 + e] = __half_as_ushort(__float2half_rn(hi));
+            s_blk[((1 * G + g) * kCamRows + c) * 8 + e] = __half_as_ushort(__float2half_rn(lo));
         }
-        put(c, hi);
-        put(kCamHalf + c, lo);
     }
     __syncthreads();
-    uint4* dst = reinterpret_cast<uint4*>(camb + (static_cast<size_t>(n) * T + t) * kCamRows * kTile);
-    const uint4* s4 = reinterpret_cast<const uint4*>(s_tile);
-    for (int chunk = threadIdx.x; chunk < kCamRows * (kTile / 8); chunk += blockDim.x) dst[chunk] = s4[chunk];
+    const int chunks = 2 * (ncol >> 3) * kCamRows;                 // uint4 chunks in both blocks
+    uint4* dst = camb + (static_cast<size_t>(n) * NS + s) * chunks;
+    const uint4* s4 = reinterpret_cast<const uint4*>(s_blk);
+    for (int i = threadIdx.x; i < chunks; i += blockDim.x) dst[i] = s4[i];
 }
 
 // ------------------------------------------------------------------------------------------------
-// forward main kernel
+// forward main kernel (CTA pair)
 // ------------------------------------------------------------------------------------------------
-constexpr int kFwdThreads = 192;   // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: ReLU/convert + epilogue
-constexpr int kStages = 2;
-constexpr uint32_t kCamTileBytes = kCamRows * kTile * 2;   // 12288
-// TMEM columns
-constexpr uint32_t kColS = 0;      // 2 x 128 fp32 columns: S^T tile, double buffered
-constexpr uint32_t kColP = 256;    // 2 x 64 columns: relu(S) as packed bf16 (A operand of the 2nd MMA)
-constexpr uint32_t kColO = 384;    // 48 fp32 columns: [num_hi | colsum | num_lo] accumulator
+// warp 0: bulk-copy producer A, warp 1: MMA issuer (leader CTA) / relay (peer CTA), warps 2-5: TMEM warps,
+// warps 6-7: bulk-copy producers B and C.  One warp keeps only ~2 bulk copies in flight (tools/ubench/bulkcp2.cu:
+// 630 clk per copy per issuing warp whatever its size, perfectly overlapped across warps), so every stream of
+// tiles gets its own issuing warp.
+constexpr int kMainThreads = 256;
+constexpr int kCamStages = 4;
 constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kColO = 256;     // forward: 64 fp32 columns [num_hi | colsum | num_lo]
+constexpr uint32_t kColG = 256;     // backward: K (<= 192) fp32 columns dFh accumulator
 
+template <bool PRECISE> struct FwdCfg { static constexpr int kFStages = PRECISE ? 2 : 4; };
+
+template <int FS>
 struct FwdBars {
-    uint64_t fj, full[kStages], empty[kStages], s_full[2], s_free[2], p_full[2], p_free[2], o_full;
+    // full_* / fj of the LEADER also count one arrival relayed from the peer CTA ("my copy of this stage landed too")
+    uint64_t fj, full_f[FS], empty_f[FS], full_c[kCamStages], empty_c[kCamStages], s_full[2], p_full[2], o_full;
     uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(kFwdThreads, 1)
-pcm_fwd_kernel(const uint16_t* __restrict__ fhat, const uint16_t* __restrict__ camb,
-               float* __restrict__ part, int K, int T, int HWp, int nsplit) {
+// relu + fp16 pack of NV fp32 accumulator values, and their sign bits: bit m = [value 2m > 0], bit 16+m = [value 2m+1 > 0].
+// The bits are taken from the packed halves (adding 0x7fff carries into bit 15 iff the half is non-zero), i.e. "S rounds
+// to a positive fp16" — values below 2^-25 count as zero, far inside the accumulation error of S.
+template <int NV>
+__device__ __forceinline__ uint32_t relu_pack_bits(const uint32_t* r, uint32_t* pk) {
+    uint32_t bits = 0;
+#pragma unroll
+    for (int m = 0; m < NV / 2; ++m) {
+        pk[m] = pack_f16x2_relu(__uint_as_float(r[2 * m]), __uint_as_float(r[2 * m + 1]));
+        bits |= ((pk[m] + 0x7fff7fffu) >> (15 - m)) & (0x00010001u << m);
+    }
+    return bits;
+}
+
+template <int WB, bool PRECISE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMainThreads, 1)
+pcm_fwd_kernel(const uint8_t* __restrict__ fa_hi, const uint8_t* __restrict__ fa_lo,
+               const uint8_t* __restrict__ fb_hi, const uint8_t* __restrict__ fb_lo,
+               const uint8_t* __restrict__ camb, float* __restrict__ part, uint4* __restrict__ mask, int K, int PJ,
+               int NS, int nsplit, long long* __restrict__ trace) {
+    constexpr int FS = FwdCfg<PRECISE>::kFStages;
+    // optional timeline of CTA (0,0,0): trace[role*256 + t*4 + k] = clock64()   (wsegk_debug_pcm_trace)
+    const bool tr = trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+#define TRACE(role, t, k) do { if (tr && (t) < 64) trace[(role) * 256 + (t) * 4 + (k)] = clock64(); } while (0)
+    constexpr int NCOL = 2 * WB;
+    constexpr uint32_t kCamBytes = NCOL * 64;                  // (NCOL/8) groups x 32 rows x 16 B per CTA
+    using Bars = FwdBars<FS>;
     extern __shared__ __align__(1024) uint8_t smem[];
-    const uint32_t tile_bytes = kTile * K * 2;
-    uint8_t* s_fj = smem;
-    uint8_t* s_stage = smem + tile_bytes;                         // kStages x (Fi tile + cam tile)
-    const uint32_t stage_bytes = tile_bytes + kCamTileBytes;
-    FwdBars* bars = reinterpret_cast<FwdBars*>(s_stage + kStages * stage_bytes);
+    const uint32_t a_bytes = kTile * K * 2, b_bytes = WB * K * 2;
+    const uint32_t f_stage = PRECISE ? 2 * b_bytes : b_bytes;
+    uint8_t* s_fj_hi = smem;
+    uint8_t* s_fj_lo = smem + a_bytes;                         // only PRECISE
+    uint8_t* s_f = smem + (PRECISE ? 2 : 1) * a_bytes;         // FS x [Fi_hi | Fi_lo]
+    uint8_t* s_c = s_f + FS * f_stage;                         // kCamStages x cam block
+    Bars* bars = reinterpret_cast<Bars*>(s_c + kCamStages * kCamBytes);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tj = blockIdx.x, sp = blockIdx.y, n = blockIdx.z;
-    const int i_begin = (T * sp) / nsplit, i_end = (T * (sp + 1)) / nsplit;
-    const int ntiles = i_end - i_begin;
+    const uint32_t rank = cluster_ctarank();
+    const int jp = blockIdx.x >> 1, sp = blockIdx.y, n = blockIdx.z;
+    const int HWpj = PJ * 2 * kTile;
+    const int s_begin = (NS * sp) / nsplit, s_end = (NS * (sp + 1)) / nsplit;
+    const int nt = s_end - s_begin;
 
     if (threadIdx.x == 0) {
-        mbar_init(smem_u32(&bars->fj), 1);
-        for (int s = 0; s < kStages; ++s) {
-            mbar_init(smem_u32(&bars->full[s]), 1);
-            mbar_init(smem_u32(&bars->empty[s]), 1);
+        const uint32_t relay = rank == 0 ? 1u : 0u, nf = PRECISE ? 2u : 1u;
+        mbar_init(smem_u32(&bars->fj), nf + relay);
+        for (int s = 0; s < FS; ++s) {
+            mbar_init(smem_u32(&bars->full_f[s]), nf + relay);
+            mbar_init(smem_u32(&bars->empty_f[s]), 1);
+        }
+        for (int s = 0; s < kCamStages; ++s) {
+            mbar_init(smem_u32(&bars->full_c[s]), 1 + relay);
+            mbar_init(smem_u32(&bars->empty_c[s]), 1);
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(smem_u32(&bars->s_full[b]), 1);
-            mbar_init(smem_u32(&bars->s_free[b]), 4);
-            mbar_init(smem_u32(&bars->p_full[b]), 4);
-            mbar_init(smem_u32(&bars->p_free[b]), 1);
+            mbar_init(smem_u32(&bars->p_full[b]), 8);          // 4 warps x 2 CTAs
         }
         mbar_init(smem_u32(&bars->o_full), 1);
         mbar_fence_init();
     }
     if (warp == 1) {
-        tmem_alloc(smem_u32(&bars->tmem_base), kTmemCols);
-        tmem_relinquish();
+        tmem_alloc_2cta(smem_u32(&bars->tmem_base), kTmemCols);
+        tmem_relinquish_2cta();
     }
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem = bars->tmem_base;
 
-    const uint8_t* g_f = reinterpret_cast<const uint8_t*>(fhat) + static_cast<size_t>(n) * T * tile_bytes;
-    const uint8_t* g_c = reinterpret_cast<const uint8_t*>(camb) + static_cast<size_t>(n) * T * kCamTileBytes;
+    const size_t a_tile = static_cast<size_t>(n) * 2 * PJ + 2 * jp + rank;        // this CTA's j tile
+    const size_t b_tile0 = static_cast<size_t>(n) * 2 * NS;
+    const uint8_t* g_cam = camb + (static_cast<size_t>(n) * NS) * 2 * kCamBytes;
 
-    if (warp == 0) {
-        // ---------------------------------------------------------------- TMA producer
+    if (warp == 0 || warp == 6) {
+        // ---------------------------------------------------------------- F producers: warp 0 = hi parts, warp 6 = lo parts
+        const bool lo = warp == 6;
+        if (lane == 0 && (!lo || PRECISE)) {
+            const uint8_t* ga = lo ? fa_lo : fa_hi;
+            const uint8_t* gb = lo ? fb_lo : fb_hi;
+            mbar_arrive_expect_tx(smem_u32(&bars->fj), a_bytes);
+            tma_load_1d(smem_u32(lo ? s_fj_lo : s_fj_hi), ga + a_tile * a_bytes, a_bytes, smem_u32(&bars->fj));
+            for (int t = 0; t < nt; ++t) {
+                const size_t bt = b_tile0 + 2 * (s_begin + t) + rank;
+                const int s = t % FS, u = t / FS;
+                mbar_wait(smem_u32(&bars->empty_f[s]), (u & 1) ^ 1);
+                if (!lo) TRACE(0, t, 0);
+                const uint32_t bar = smem_u32(&bars->full_f[s]);
+                mbar_arrive_expect_tx(bar, b_bytes);
+                tma_load_1d(smem_u32(s_f + s * f_stage + (lo ? b_bytes : 0)), gb + bt * b_bytes, b_bytes, bar);
+            }
+        }
+    } else if (warp == 7) {
+        // ---------------------------------------------------------------- cam-block producer
         if (lane == 0) {
-            mbar_arrive_expect_tx(smem_u32(&bars->fj), tile_bytes);
-            tma_load_1d(smem_u32(s_fj), g_f + static_cast<size_t>(tj) * tile_bytes, tile_bytes,
-                        smem_u32(&bars->fj));
-            for (int t = 0; t < ntiles; ++t) {
-                const int s = t % kStages, u = t / kStages;
-                mbar_wait(smem_u32(&bars->empty[s]), (u & 1) ^ 1);
-                const uint32_t bar = smem_u32(&bars->full[s]);
-                uint8_t* dst = s_stage + s * stage_bytes;
-                mbar_arrive_expect_tx(bar, stage_bytes);
-                tma_load_1d(smem_u32(dst), g_f + static_cast<size_t>(i_begin + t) * tile_bytes, tile_bytes, bar);
-                tma_load_1d(smem_u32(dst + tile_bytes), g_c + static_cast<size_t>(i_begin + t) * kCamTileBytes,
-                            kCamTileBytes, bar);
+            for (int t = 0; t < nt; ++t) {
+                const int s = t % kCamStages, u = t / kCamStages;
+                mbar_wait(smem_u32(&bars->empty_c[s]), (u & 1) ^ 1);
+                const uint32_t bar = smem_u32(&bars->full_c[s]);
+                mbar_arrive_expect_tx(bar, kCamBytes);
+                tma_load_1d(smem_u32(s_c + s * kCamBytes),
+                            g_cam + (static_cast<size_t>(s_begin + t) * 2 + rank) * kCamBytes, kCamBytes, bar);
             }
         }
     } else if (warp == 1) {
-        // ---------------------------------------------------------------- MMA issuer (one thread)
-        if (lane == 0) {
-            const uint32_t idesc1 = umma_idesc_bf16(kTile, kTile, 0, 0);
-            const uint32_t idesc2 = umma_idesc_bf16(kTile, kCamRows, 0, 0);
-            const uint32_t lbo_f = kTile * 16;        // bytes between the two K halves of an MMA (16 row groups)
-            const uint32_t lbo_c = kCamRows * 16;
-            const int ksteps = K >> 4;
+        if (lane == 0 && rank == 1) {
+            // ------------------------------------------------------------ relay: tell the leader my tiles have landed
             mbar_wait(smem_u32(&bars->fj), 0);
-            auto issue_s = [&](int t) {
-                const int s = t % kStages, u = t / kStages, b = t & 1, ub = t >> 1;
-                mbar_wait(smem_u32(&bars->full[s]), u & 1);
-                mbar_wait(smem_u32(&bars->s_free[b]), (ub & 1) ^ 1);
-                tc_fence_after();
-                const uint32_t a0 = smem_u32(s_fj), b0 = smem_u32(s_stage + s * stage_bytes);
-                for (int ks = 0; ks < ksteps; ++ks) {
-                    umma_ss(tmem + kColS + b * 128, umma_smem_desc(a0 + ks * 2 * lbo_f, lbo_f, 128),
-                            umma_smem_desc(b0 + ks * 2 * lbo_f, lbo_f, 128), idesc1, ks > 0);
+            mbar_arrive_cluster(mapa_shared(smem_u32(&bars->fj), 0));
+            for (int t = 0; t < nt; ++t) {
+                {
+                    const int s = t % FS, u = t / FS;
+                    mbar_wait(smem_u32(&bars->full_f[s]), u & 1);
+                    mbar_arrive_cluster(mapa_shared(smem_u32(&bars->full_f[s]), 0));
                 }
-                umma_commit(smem_u32(&bars->s_full[b]));
+                {
+                    const int s = t % kCamStages, u = t / kCamStages;
+                    mbar_wait(smem_u32(&bars->full_c[s]), u & 1);
+                    mbar_arrive_cluster(mapa_shared(smem_u32(&bars->full_c[s]), 0));
+                }
+            }
+        } else if (rank == 0) {
+            // ------------------------------------------------------------ MMA issuer: the whole warp of the leader CTA
+            // stays converged (waits), one ELECTED lane issues; descriptors advance by adding to their address field.
+            const uint32_t id_s = umma_idesc_f16(0, 2 * kTile, NCOL, 0, 0);
+            const uint32_t id_o = umma_idesc_f16(0, 2 * kTile, kONum, 0, 0);
+            constexpr uint32_t lbo_a = kTile * 16, lbo_b = WB * 16, lbo_c = kCamRows * 16;
+            const int ksteps = K >> 4;
+            const uint64_t da_hi = umma_smem_desc(smem_u32(s_fj_hi), lbo_a, 128);
+            const uint64_t da_lo = umma_smem_desc(smem_u32(s_fj_lo), lbo_a, 128);
+            mbar_wait_cluster(smem_u32(&bars->fj), 0);
+            auto issue_s = [&](int t) {
+                const int s = t % FS, u = t / FS, b = t & 1;
+                if (lane == 0) TRACE(1, t, 0);
+                mbar_wait_cluster(smem_u32(&bars->full_f[s]), u & 1);
+                if (lane == 0) TRACE(1, t, 1);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint64_t db_hi = umma_smem_desc(smem_u32(s_f + s * f_stage), lbo_b, 128);
+                    const uint64_t db_lo = umma_smem_desc(smem_u32(s_f + s * f_stage) + b_bytes, lbo_b, 128);
+                    const uint32_t d = tmem + b * 128;
+#pragma unroll 4
+                    for (int ks = 0; ks < ksteps; ++ks)
+                        umma2_ss(d, da_hi + static_cast<uint64_t>(ks * (2 * lbo_a / 16)),
+                                 db_hi + static_cast<uint64_t>(ks * (2 * lbo_b / 16)), id_s, ks > 0);
+                    if (PRECISE) {
+#pragma unroll 4
+                        for (int ks = 0; ks < ksteps; ++ks)
+                            umma2_ss(d, da_hi + static_cast<uint64_t>(ks * (2 * lbo_a / 16)),
+                                     db_lo + static_cast<uint64_t>(ks * (2 * lbo_b / 16)), id_s, 1);
+#pragma unroll 4
+                        for (int ks = 0; ks < ksteps; ++ks)
+                            umma2_ss(d, da_lo + static_cast<uint64_t>(ks * (2 * lbo_a / 16)),
+                                     db_hi + static_cast<uint64_t>(ks * (2 * lbo_b / 16)), id_s, 1);
+                    }
+                    umma2_commit(smem_u32(&bars->s_full[b]));
+                    umma2_commit(smem_u32(&bars->empty_f[s]));
+                }
+                __syncwarp();
             };
             issue_s(0);
-            for (int t = 0; t < ntiles; ++t) {
-                if (t + 1 < ntiles) issue_s(t + 1);
-                const int s = t % kStages, b = t & 1, ub = t >> 1;
-                mbar_wait(smem_u32(&bars->p_full[b]), ub & 1);
+            if (nt > 1) issue_s(1);
+            for (int t = 0; t < nt; ++t) {
+                const int b = t & 1, sc = t % kCamStages, uc = t / kCamStages;
+                if (lane == 0) TRACE(1, t, 2);
+                mbar_wait_cluster(smem_u32(&bars->p_full[b]), (t >> 1) & 1);
+                if (lane == 0) TRACE(1, t, 3);
+                mbar_wait_cluster(smem_u32(&bars->full_c[sc]), uc & 1);
                 tc_fence_after();
-                const uint32_t c0 = smem_u32(s_stage + s * stage_bytes + tile_bytes);
-                for (int ks = 0; ks < kTile / 16; ++ks) {
-                    umma_ts(tmem + kColO, tmem + kColP + b * 64 + ks * 8,
-                            umma_smem_desc(c0 + ks * 2 * lbo_c, lbo_c, 128), idesc2, (t > 0) || (ks > 0));
+                if (elect_one()) {
+                    const uint64_t dc = umma_smem_desc(smem_u32(s_c + sc * kCamBytes), lbo_c, 128);
+#pragma unroll
+                    for (int ks = 0; ks < NCOL / 16; ++ks)
+                        umma2_ts(tmem + kColO, tmem + b * 128 + ks * 8, dc + static_cast<uint64_t>(ks * (2 * lbo_c / 16)),
+                                 id_o, (t > 0) || (ks > 0));
+                    umma2_commit(smem_u32(&bars->empty_c[sc]));
                 }
-                umma_commit(smem_u32(&bars->empty[s]));
-                umma_commit(smem_u32(&bars->p_free[b]));
+                __syncwarp();
+                if (t + 2 < nt) issue_s(t + 2);
             }
-            umma_commit(smem_u32(&bars->o_full));
+            if (elect_one()) umma2_commit(smem_u32(&bars->o_full));
+            __syncwarp();
         }
-    } else {
-        // ---------------------------------------------------------------- ReLU / convert warps
+    } else if (warp < 6) {
+        // ---------------------------------------------------------------- ReLU / sign / convert warps (own 128 lanes)
         const int q = warp & 3;                         // TMEM lane quarter this warp may touch
         const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-        for (int t = 0; t < ntiles; ++t) {
-            const int b = t & 1, ub = t >> 1;
-            mbar_wait(smem_u32(&bars->s_full[b]), ub & 1);
-            mbar_wait(smem_u32(&bars->p_free[b]), (ub & 1) ^ 1);
+        const int row = jp * 2 * kTile + static_cast<int>(rank) * kTile + q * 32 + lane;
+        const uint32_t p_full0 = mapa_shared(smem_u32(&bars->p_full[0]), 0);
+        const uint32_t p_full1 = mapa_shared(smem_u32(&bars->p_full[1]), 0);
+        for (int t = 0; t < nt; ++t) {
+            const int b = t & 1;
+            if (warp == 2 && lane == 0) TRACE(2, t, 0);
+            mbar_wait(smem_u32(&bars->s_full[b]), (t >> 1) & 1);
+            if (warp == 2 && lane == 0) TRACE(2, t, 1);
             tc_fence_after();
+            uint32_t mw[4] = {0u, 0u, 0u, 0u};
+            const uint32_t base = tmem + lane_addr + b * 128;
 #pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4) {
+            for (int c = 0; c < NCOL / 32; ++c) {
                 uint32_t r[32], pk[16];
-                tmem_ld32(tmem + lane_addr + kColS + b * 128 + c4 * 32, r);
+                tmem_ld32(base + c * 32, r);
                 tmem_ld_wait();
-#pragma unroll
-                for (int m = 0; m < 16; ++m)
-                    pk[m] = pack_bf16x2_relu(__uint_as_float(r[2 * m]), __uint_as_float(r[2 * m + 1]));
-                tmem_st16(tmem + lane_addr + kColP + b * 64 + c4 * 16, pk);
+                mw[c] = relu_pack_bits<32>(r, pk);
+                tmem_st16(base + c * 16, pk);
+            }
+            if (NCOL % 32) {
+                constexpr int c = NCOL / 32;
+                uint32_t r[16], pk[8];
+                tmem_ld16(base + c * 32, r);
+                tmem_ld_wait();
+                mw[c & 3] = relu_pack_bits<16>(r, pk);
+                tmem_st8(base + c * 16, pk);
             }
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(smem_u32(&bars->s_free[b]));
-                mbar_arrive(smem_u32(&bars->p_full[b]));
-            }
+            if (lane == 0) mbar_arrive_cluster(b ? p_full1 : p_full0);
+            if (warp == 2 && lane == 0) TRACE(2, t, 2);
+            mask[(static_cast<size_t>(n) * NS + (s_begin + t)) * HWpj + row] = make_uint4(mw[0], mw[1], mw[2], mw[3]);
         }
-        // epilogue: accumulator rows -> partial buffer [n][sp][HWp][48]
+        // epilogue: accumulator rows -> partial buffer [n][sp][HWpj][64]
         mbar_wait(smem_u32(&bars->o_full), 0);
         tc_fence_after();
-        const int row = tj * kTile + q * 32 + lane;
-        float4* dst = reinterpret_cast<float4*>(
-            part + ((static_cast<size_t>(n) * nsplit + sp) * HWp + row) * kCamRows);
+        float4* dst = reinterpret_cast<float4*>(part + ((static_cast<size_t>(n) * nsplit + sp) * HWpj + row) * kONum);
 #pragma unroll
-        for (int c = 0; c < kCamRows / 16; ++c) {
+        for (int c = 0; c < kONum / 16; ++c) {
             uint32_t r[16];
             tmem_ld16(tmem + lane_addr + kColO + c * 16, r);
             tmem_ld_wait();
@@ -258,41 +395,42 @@ pcm_fwd_kernel(const uint16_t* __restrict__ fhat, const uint16_t* __restrict__ c
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem, kTmemCols);
+    cluster_sync_all();
+    if (warp == 1) tmem_dealloc_2cta(tmem, kTmemCols);
+#undef TRACE
 }
 
 // out[n,c,j] = (sum_sp hi[c] + lo[c]) / (sum_sp colsum + 1e-5)
 __global__ void __launch_bounds__(128) pcm_fwd_finalize_kernel(const float* __restrict__ part,
                                                                float* __restrict__ out,
                                                                float* __restrict__ dsum, int C, int HW,
-                                                               int HWp, int nsplit) {
+                                                               int HWpj, int nsplit) {
     const int n = blockIdx.y;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= HWp) return;
-    float acc[kCamRows];
+    if (j >= HWpj) return;
+    float acc[kONum];
 #pragma unroll
-    for (int c = 0; c < kCamRows; ++c) acc[c] = 0.f;
+    for (int c = 0; c < kONum; ++c) acc[c] = 0.f;
     for (int sp = 0; sp < nsplit; ++sp) {
         const float4* src = reinterpret_cast<const float4*>(
-            part + ((static_cast<size_t>(n) * nsplit + sp) * HWp + j) * kCamRows);
+            part + ((static_cast<size_t>(n) * nsplit + sp) * HWpj + j) * kONum);
 #pragma unroll
-        for (int v = 0; v < kCamRows / 4; ++v) {
+        for (int v = 0; v < kONum / 4; ++v) {
             float4 x = __ldg(src + v);
             acc[4 * v] += x.x; acc[4 * v + 1] += x.y; acc[4 * v + 2] += x.z; acc[4 * v + 3] += x.w;
         }
     }
     float d = 0.f;
 #pragma unroll
-    for (int c = 0; c < kCamHalf; ++c) if (c == C) d = acc[c];
+    for (int c = 0; c < kCamRows; ++c) if (c == C) d = acc[c];
     d += 1e-5f;
-    dsum[static_cast<size_t>(n) * HWp + j] = d;
+    dsum[static_cast<size_t>(n) * HWpj + j] = d;
     if (j >= HW) return;
     float* dst = out + static_cast<size_t>(n) * C * HW + j;
 #pragma unroll
-    for (int c = 0; c < kCamHalf; ++c)
-        if (c < C) dst[static_cast<size_t>(c) * HW] = (acc[c] + acc[kCamHalf + c]) / d;
+    for (int c = 0; c < kCamRows; ++c)
+        if (c < C) dst[static_cast<size_t>(c) * HW] = (acc[c] + acc[kCamRows + c]) / d;
 }
-
 
 // ------------------------------------------------------------------------------------------------
 // backward
@@ -301,25 +439,28 @@ __global__ void __launch_bounds__(128) pcm_fwd_finalize_kernel(const float* __re
 //   dL/dA_ij = cam_i . g_j - d_j,   dL/dS = dL/dA * [S > 0],   dL/dfh = (dS + dS^T) fh
 // and (dS + dS^T)_ji = [S_ji > 0] * (U_j . V_i) with the rank-(2C+2) factors
 //   U_j = [ g_j ; cam_j ; -d_j ; 1 ],   V_i = [ cam_i ; g_i ; 1 ; -d_i ]              
-// so a CTA owning a j-tile needs, per i-tile: S = Fj Fi^T (K), Tt = Uj Vi^T (48), the masked product E in
-// TMEM, and dFh_j += E Fi (Fi read MN-major from the same shared-memory tile).  No atomics.
+// A CTA pair owning 256 j pixels needs, per stage: Tt = Uj Vi^T (K = 48, or 144 with the bf16 hi/lo split), the sign
+// mask the forward stored, E = mask .* Tt * 2^e as packed FP16 in TMEM (in place), and dFh_j += E Fi with Fi read
+// MN-major (each CTA supplies half of the channels).  No atomics; S is never recomputed.
 
-// U/V tiles: [128 pixels x 48] bf16, canonical K-major (chunk (pixel r, group g) at g*128 + r).
-__global__ void __launch_bounds__(128) pcm_bwd_prep_kernel(const float* __restrict__ cam,
-                                                           const float* __restrict__ out,
+// U tiles: [128 pixels x Ku] bf16 (A layout); V tiles: [wb pixels x Ku] bf16 (B layout).
+// SPLIT: U' = [hi | hi | lo], V' = [hi | lo | hi] so that U'.V' = hi.hi + hi.lo + lo.hi.
+template <bool SPLIT>
+__global__ void __launch_bounds__(128) pcm_bwd_prep_kernel(const float* __restrict__ cam, const float* __restrict__ out,
                                                            const float* __restrict__ gout,
-                                                           const float* __restrict__ dsum,
-                                                           uint16_t* __restrict__ uaug,
-                                                           uint16_t* __restrict__ vaug, int C, int HW,
-                                                           int T, int HWp) {
-    __shared__ float s_u[kAugRows][kTile];
-    __shared__ float s_v[kAugRows][kTile];
+                                                           const float* __restrict__ dsum, uint4* __restrict__ ua,
+                                                           uint4* __restrict__ vb, unsigned int* __restrict__ bound,
+                                                           int C, int HW, int PJ, int NS, int wb) {
+    __shared__ float s_u[kAugK][kTile];
+    __shared__ float s_v[kAugK][kTile];
     const int t = blockIdx.x, n = blockIdx.y;
     const int px = threadIdx.x;
     const int p = t * kTile + px;
-    for (int i = 0; i < kAugRows; ++i) { s_u[i][px] = 0.f; s_v[i][px] = 0.f; }
+    const int HWpj = PJ * 2 * kTile, HWpi = NS * 2 * wb;
+    for (int i = 0; i < kAugK; ++i) { s_u[i][px] = 0.f; s_v[i][px] = 0.f; }
+    float bnd = 0.f;
     if (p < HW) {
-        const float invd = 1.f / dsum[static_cast<size_t>(n) * HWp + p];
+        const float invd = 1.f / dsum[static_cast<size_t>(n) * HWpj + p];
         const size_t base = static_cast<size_t>(n) * C * HW + p;
         float delta = 0.f;
         for (int c = 0; c < C; ++c) {
@@ -328,217 +469,342 @@ __global__ void __launch_bounds__(128) pcm_bwd_prep_kernel(const float* __restri
             const float o = __ldg(out + base + static_cast<size_t>(c) * HW);
             delta = fmaf(o, g, delta);
             const float gs = g * invd;
+            bnd += fabsf(gs);
             s_u[c][px] = gs;      s_v[c][px] = cm;
             s_u[C + c][px] = cm;  s_v[C + c][px] = gs;
         }
         const float dj = delta * invd;
+        bnd += fabsf(dj);
         s_u[2 * C][px] = -dj;     s_v[2 * C][px] = 1.f;
         s_u[2 * C + 1][px] = 1.f; s_v[2 * C + 1][px] = -dj;
     }
-    // each thread only reads back its own column: no barrier needed
-    uint4* du = reinterpret_cast<uint4*>(uaug + (static_cast<size_t>(n) * T + t) * kTile * kAugRows);
-    uint4* dv = reinterpret_cast<uint4*>(vaug + (static_cast<size_t>(n) * T + t) * kTile * kAugRows);
+    // |T_ji| <= 2 * max_p (sum_c |g_p[c]| + |d_p|) since 0 <= cam <= 1
 #pragma unroll
-    for (int g = 0; g < kAugRows / 8; ++g) {
-        uint4 a, b;
-        a.x = pack_bf16x2(s_u[8 * g + 0][px], s_u[8 * g + 1][px]); a.y = pack_bf16x2(s_u[8 * g + 2][px], s_u[8 * g + 3][px]);
-        a.z = pack_bf16x2(s_u[8 * g + 4][px], s_u[8 * g + 5][px]); a.w = pack_bf16x2(s_u[8 * g + 6][px], s_u[8 * g + 7][px]);
-        b.x = pack_bf16x2(s_v[8 * g + 0][px], s_v[8 * g + 1][px]); b.y = pack_bf16x2(s_v[8 * g + 2][px], s_v[8 * g + 3][px]);
-        b.z = pack_bf16x2(s_v[8 * g + 4][px], s_v[8 * g + 5][px]); b.w = pack_bf16x2(s_v[8 * g + 6][px], s_v[8 * g + 7][px]);
-        du[g * kTile + px] = a;
-        dv[g * kTile + px] = b;
+    for (int o = 16; o > 0; o >>= 1) bnd = fmaxf(bnd, __shfl_xor_sync(0xffffffffu, bnd, o));
+    if ((threadIdx.x & 31) == 0 && bnd > 0.f)
+        atomicMax(bound, __float_as_uint(2.f * bnd));       // non-negative floats order like their bit patterns
+    // each thread only reads back its own column of s_u / s_v
+    constexpr int GU = (SPLIT ? 3 : 1) * (kAugK / 8);
+    const bool in_a = p < HWpj, in_b = p < HWpi;
+    const int tb = p / wb, rb = p - tb * wb;
+    uint4* du = ua + (static_cast<size_t>(n) * 2 * PJ + t) * GU * kTile + px;
+    uint4* dv = vb + (static_cast<size_t>(n) * 2 * NS + tb) * GU * wb + rb;
+#pragma unroll
+    for (int g = 0; g < kAugK / 8; ++g) {
+        uint32_t uh[4], ul[4], vh[4], vl[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float u0 = s_u[8 * g + 2 * e][px], u1 = s_u[8 * g + 2 * e + 1][px];
+            const float v0 = s_v[8 * g + 2 * e][px], v1 = s_v[8 * g + 2 * e + 1][px];
+            const float u0h = __bfloat162float(__float2bfloat16_rn(u0)), u1h = __bfloat162float(__float2bfloat16_rn(u1));
+            const float v0h = __bfloat162float(__float2bfloat16_rn(v0)), v1h = __bfloat162float(__float2bfloat16_rn(v1));
+            uh[e] = pack_bf16x2(u0h, u1h);  ul[e] = pack_bf16x2(u0 - u0h, u1 - u1h);
+            vh[e] = pack_bf16x2(v0h, v1h);  vl[e] = pack_bf16x2(v0 - v0h, v1 - v1h);
+        }
+        const uint4 UH = make_uint4(uh[0], uh[1], uh[2], uh[3]), UL = make_uint4(ul[0], ul[1], ul[2], ul[3]);
+        const uint4 VH = make_uint4(vh[0], vh[1], vh[2], vh[3]), VL = make_uint4(vl[0], vl[1], vl[2], vl[3]);
+        if (in_a) {
+            du[static_cast<size_t>(g) * kTile] = UH;
+            if (SPLIT) {
+                du[static_cast<size_t>(kAugK / 8 + g) * kTile] = UH;
+                du[static_cast<size_t>(2 * (kAugK / 8) + g) * kTile] = UL;
+            }
+        }
+        if (in_b) {
+            dv[static_cast<size_t>(g) * wb] = VH;
+            if (SPLIT) {
+                dv[static_cast<size_t>(kAugK / 8 + g) * wb] = VL;
+                dv[static_cast<size_t>(2 * (kAugK / 8) + g) * wb] = VH;
+            }
+        }
     }
 }
 
-constexpr uint32_t kAugTileBytes = kTile * kAugRows * 2;   // 12288
-// TMEM columns (backward)
-constexpr uint32_t kColBS = 0;      // 128: S tile
-constexpr uint32_t kColBT = 128;    // 128: Tt = U V^T tile
-constexpr uint32_t kColBG = 256;    // K (<=192): dFh accumulator
-constexpr uint32_t kColBE = 448;    // 64: masked product as packed bf16
+// power-of-two scale that brings |T| below 2^14 so E = T * scale is representable in FP16 with full precision
+__device__ __forceinline__ float pcm_grad_scale(const float* bound) {
+    const float b = *bound;
+    if (!(b > 0.f) || !isfinite(b)) return 1.f;
+    int e;
+    frexpf(b, &e);                       // b = m * 2^e, 0.5 <= m < 1  =>  b < 2^e
+    return exp2f(static_cast<float>(14 - e));
+}
+
+constexpr int kBwdStages = 4;
 
 struct BwdBars {
-    uint64_t fj, full[kStages], empty[kStages], st_full, e_full, g_full;
+    uint64_t uj, full_v[kBwdStages], empty_v[kBwdStages], full_f[kBwdStages], empty_f[kBwdStages], t_full[2], e_full[2],
+        g_full;
     uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(kFwdThreads, 1)
-pcm_bwd_kernel(const uint16_t* __restrict__ fhat, const uint16_t* __restrict__ uaug,
-               const uint16_t* __restrict__ vaug, float* __restrict__ dfhat, int K, int T, int HWp,
-               int nsplit) {
+template <int NV>
+__device__ __forceinline__ void mask_scale_pack(const uint32_t* r, uint32_t bits, float scale, uint32_t* pk) {
+#pragma unroll
+    for (int m = 0; m < NV / 2; ++m) {
+        const float a = ((bits >> m) & 1u) ? __uint_as_float(r[2 * m]) * scale : 0.f;
+        const float b = ((bits >> (16 + m)) & 1u) ? __uint_as_float(r[2 * m + 1]) * scale : 0.f;
+        pk[m] = pack_f16x2(a, b);
+    }
+}
+
+template <int WB, bool SPLIT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMainThreads, 1)
+pcm_bwd_kernel(const uint8_t* __restrict__ ua, const uint8_t* __restrict__ vb, const uint8_t* __restrict__ fb_hi,
+               const uint4* __restrict__ mask, const float* __restrict__ bound, float* __restrict__ dfhat, int K,
+               int PJ, int NS, int nsplit) {
+    constexpr int NCOL = 2 * WB;
+    constexpr int KU = SPLIT ? 3 * kAugK : kAugK;
+    constexpr uint32_t kUBytes = kTile * KU * 2, kVBytes = WB * KU * 2;
     extern __shared__ __align__(1024) uint8_t smem[];
-    const uint32_t tile_bytes = kTile * K * 2;
-    uint8_t* s_fj = smem;
-    uint8_t* s_uj = smem + tile_bytes;
-    uint8_t* s_stage = s_uj + kAugTileBytes;
-    const uint32_t stage_bytes = tile_bytes + kAugTileBytes;
-    BwdBars* bars = reinterpret_cast<BwdBars*>(s_stage + kStages * stage_bytes);
+    const uint32_t f_part = (K >> 4) * WB * 16;                // one tile's channel half: K/16 groups x WB rows x 16 B
+    const uint32_t f_stage = 2 * f_part;
+    uint8_t* s_u = smem;
+    uint8_t* s_v = smem + kUBytes;
+    uint8_t* s_f = s_v + kBwdStages * kVBytes;
+    BwdBars* bars = reinterpret_cast<BwdBars*>(s_f + kBwdStages * f_stage);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tj = blockIdx.x, sp = blockIdx.y, n = blockIdx.z;
-    const int i_begin = (T * sp) / nsplit, i_end = (T * (sp + 1)) / nsplit;
-    const int ntiles = i_end - i_begin;
+    const uint32_t rank = cluster_ctarank();
+    const int jp = blockIdx.x >> 1, sp = blockIdx.y, n = blockIdx.z;
+    const int HWpj = PJ * 2 * kTile;
+    const int s_begin = (NS * sp) / nsplit, s_end = (NS * (sp + 1)) / nsplit;
+    const int nt = s_end - s_begin;
 
     if (threadIdx.x == 0) {
-        mbar_init(smem_u32(&bars->fj), 1);
-        for (int s = 0; s < kStages; ++s) {
-            mbar_init(smem_u32(&bars->full[s]), 1);
-            mbar_init(smem_u32(&bars->empty[s]), 1);
+        const uint32_t relay = rank == 0 ? 1u : 0u;
+        mbar_init(smem_u32(&bars->uj), 1 + relay);
+        for (int s = 0; s < kBwdStages; ++s) {
+            mbar_init(smem_u32(&bars->full_v[s]), 1 + relay);
+            mbar_init(smem_u32(&bars->empty_v[s]), 1);
+            mbar_init(smem_u32(&bars->full_f[s]), 2 + relay);        // two producer warps (X part, Y part)
+            mbar_init(smem_u32(&bars->empty_f[s]), 1);
         }
-        mbar_init(smem_u32(&bars->st_full), 1);
-        mbar_init(smem_u32(&bars->e_full), 4);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(smem_u32(&bars->t_full[b]), 1);
+            mbar_init(smem_u32(&bars->e_full[b]), 8);
+        }
         mbar_init(smem_u32(&bars->g_full), 1);
         mbar_fence_init();
     }
     if (warp == 1) {
-        tmem_alloc(smem_u32(&bars->tmem_base), kTmemCols);
-        tmem_relinquish();
+        tmem_alloc_2cta(smem_u32(&bars->tmem_base), kTmemCols);
+        tmem_relinquish_2cta();
     }
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem = bars->tmem_base;
 
-    const uint8_t* g_f = reinterpret_cast<const uint8_t*>(fhat) + static_cast<size_t>(n) * T * tile_bytes;
-    const uint8_t* g_u = reinterpret_cast<const uint8_t*>(uaug) + static_cast<size_t>(n) * T * kAugTileBytes;
-    const uint8_t* g_v = reinterpret_cast<const uint8_t*>(vaug) + static_cast<size_t>(n) * T * kAugTileBytes;
+    const size_t a_tile = static_cast<size_t>(n) * 2 * PJ + 2 * jp + rank;
+    const size_t b_tile0 = static_cast<size_t>(n) * 2 * NS;
+    const size_t b_bytes = static_cast<size_t>(WB) * K * 2;
 
     if (warp == 0) {
+        // ---------------------------------------------------------------- producer A: U tile (once) and the V tiles
         if (lane == 0) {
-            mbar_arrive_expect_tx(smem_u32(&bars->fj), tile_bytes + kAugTileBytes);
-            tma_load_1d(smem_u32(s_fj), g_f + static_cast<size_t>(tj) * tile_bytes, tile_bytes, smem_u32(&bars->fj));
-            tma_load_1d(smem_u32(s_uj), g_u + static_cast<size_t>(tj) * kAugTileBytes, kAugTileBytes,
-                        smem_u32(&bars->fj));
-            for (int t = 0; t < ntiles; ++t) {
-                const int s = t % kStages, u = t / kStages;
-                mbar_wait(smem_u32(&bars->empty[s]), (u & 1) ^ 1);
-                const uint32_t bar = smem_u32(&bars->full[s]);
-                uint8_t* dst = s_stage + s * stage_bytes;
-                mbar_arrive_expect_tx(bar, stage_bytes);
-                tma_load_1d(smem_u32(dst), g_f + static_cast<size_t>(i_begin + t) * tile_bytes, tile_bytes, bar);
-                tma_load_1d(smem_u32(dst + tile_bytes), g_v + static_cast<size_t>(i_begin + t) * kAugTileBytes,
-                            kAugTileBytes, bar);
+            mbar_arrive_expect_tx(smem_u32(&bars->uj), kUBytes);
+            tma_load_1d(smem_u32(s_u), ua + a_tile * kUBytes, kUBytes, smem_u32(&bars->uj));
+            for (int t = 0; t < nt; ++t) {
+                const int st = s_begin + t, s = t % kBwdStages, u = t / kBwdStages;
+                mbar_wait(smem_u32(&bars->empty_v[s]), (u & 1) ^ 1);
+                const uint32_t bar = smem_u32(&bars->full_v[s]);
+                mbar_arrive_expect_tx(bar, kVBytes);
+                tma_load_1d(smem_u32(s_v + s * kVBytes), vb + (b_tile0 + 2 * st + rank) * kVBytes, kVBytes, bar);
+            }
+        }
+    } else if (warp >= 6) {
+        // ---------------------------------------------------------------- producers B, C: my half of the channels (groups
+        // [rank*K/16, (rank+1)*K/16)) of the stage's X tile (warp 6) and Y tile (warp 7)
+        if (lane == 0) {
+            const int part = warp - 6;
+            for (int t = 0; t < nt; ++t) {
+                const int st = s_begin + t, s = t % kBwdStages, u = t / kBwdStages;
+                mbar_wait(smem_u32(&bars->empty_f[s]), (u & 1) ^ 1);
+                const uint32_t bar = smem_u32(&bars->full_f[s]);
+                mbar_arrive_expect_tx(bar, f_part);
+                const uint8_t* x = fb_hi + (b_tile0 + 2 * st + part) * b_bytes + static_cast<size_t>(rank) * f_part;
+                tma_load_1d(smem_u32(s_f + s * f_stage + part * f_part), x, f_part, bar);
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc_s = umma_idesc_bf16(kTile, kTile, 0, 0);
-            const uint32_t idesc_g = umma_idesc_bf16(kTile, K, 0, 1);     // B = Fi read MN-major (N = channel)
-            const uint32_t lbo = kTile * 16;                              // 2048: K-direction step of a 128-row tile
-            mbar_wait(smem_u32(&bars->fj), 0);
-            for (int t = 0; t < ntiles; ++t) {
-                const int s = t % kStages, u = t / kStages;
-                mbar_wait(smem_u32(&bars->full[s]), u & 1);
-                tc_fence_after();
-                const uint32_t fj0 = smem_u32(s_fj), uj0 = smem_u32(s_uj);
-                const uint32_t fi0 = smem_u32(s_stage + s * stage_bytes), vi0 = fi0 + tile_bytes;
-                // (MMAs execute in issue order, so these overwrite S/Tt only after the previous E was consumed)
-                for (int ks = 0; ks < (K >> 4); ++ks)
-                    umma_ss(tmem + kColBS, umma_smem_desc(fj0 + ks * 2 * lbo, lbo, 128),
-                            umma_smem_desc(fi0 + ks * 2 * lbo, lbo, 128), idesc_s, ks > 0);
-                for (int ks = 0; ks < kAugRows / 16; ++ks)
-                    umma_ss(tmem + kColBT, umma_smem_desc(uj0 + ks * 2 * lbo, lbo, 128),
-                            umma_smem_desc(vi0 + ks * 2 * lbo, lbo, 128), idesc_s, ks > 0);
-                umma_commit(smem_u32(&bars->st_full));
-                mbar_wait(smem_u32(&bars->e_full), t & 1);
-                tc_fence_after();
-                // dFh[j, ch] += E[j, i] * Fi[i, ch]: B is N(ch) x K(pixel), MN-major: LBO = pixel-group step,
-                // SBO = channel-group step
-                for (int ks = 0; ks < kTile / 16; ++ks)
-                    umma_ts(tmem + kColBG, tmem + kColBE + ks * 8, umma_smem_desc(fi0 + ks * 256, 128, lbo),
-                            idesc_g, (t > 0) || (ks > 0));
-                umma_commit(smem_u32(&bars->empty[s]));
+        if (lane == 0 && rank == 1) {
+            mbar_wait(smem_u32(&bars->uj), 0);
+            mbar_arrive_cluster(mapa_shared(smem_u32(&bars->uj), 0));
+            for (int t = 0; t < nt; ++t) {
+                const int s = t % kBwdStages, u = t / kBwdStages;
+                mbar_wait(smem_u32(&bars->full_v[s]), u & 1);
+                mbar_arrive_cluster(mapa_shared(smem_u32(&bars->full_v[s]), 0));
+                mbar_wait(smem_u32(&bars->full_f[s]), u & 1);
+                mbar_arrive_cluster(mapa_shared(smem_u32(&bars->full_f[s]), 0));
             }
-            umma_commit(smem_u32(&bars->g_full));
+        } else if (rank == 0) {
+            const uint32_t id_t = umma_idesc_f16(1, 2 * kTile, NCOL, 0, 0);       // bf16 factors
+            const uint32_t id_g = umma_idesc_f16(0, 2 * kTile, K, 0, 1);          // fp16, B = Fi read MN-major (N = channel)
+            constexpr uint32_t lbo_a = kTile * 16, lbo_b = WB * 16;
+            const uint64_t du = umma_smem_desc(smem_u32(s_u), lbo_a, 128);
+            mbar_wait_cluster(smem_u32(&bars->uj), 0);
+            auto issue_t = [&](int t) {
+                const int s = t % kBwdStages, u = t / kBwdStages, b = t & 1;
+                mbar_wait_cluster(smem_u32(&bars->full_v[s]), u & 1);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint64_t dv = umma_smem_desc(smem_u32(s_v + s * kVBytes), lbo_b, 128);
+#pragma unroll
+                    for (int ks = 0; ks < KU / 16; ++ks)
+                        umma2_ss(tmem + b * 128, du + static_cast<uint64_t>(ks * (2 * lbo_a / 16)),
+                                 dv + static_cast<uint64_t>(ks * (2 * lbo_b / 16)), id_t, ks > 0);
+                    umma2_commit(smem_u32(&bars->t_full[b]));
+                    umma2_commit(smem_u32(&bars->empty_v[s]));
+                }
+                __syncwarp();
+            };
+            issue_t(0);
+            if (nt > 1) issue_t(1);
+            for (int t = 0; t < nt; ++t) {
+                const int s = t % kBwdStages, u = t / kBwdStages, b = t & 1;
+                mbar_wait_cluster(smem_u32(&bars->e_full[b]), (t >> 1) & 1);
+                mbar_wait_cluster(smem_u32(&bars->full_f[s]), u & 1);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t f0 = smem_u32(s_f + s * f_stage);
+                    // dFh[j, ch] += E[j, q] * F[q, ch] over the stage's pixels q = [X(0:WB) | Y(0:WB)]; B is N(ch) x K(q),
+                    // MN-major: LBO = step between the two 8-pixel groups of the k-step, SBO = channel-group step
+#pragma unroll
+                    for (int ks = 0; ks < NCOL / 16; ++ks) {
+                        constexpr int dummy = 0; (void)dummy;
+                        const int q0 = 16 * ks, q1 = q0 + 8;
+                        const uint32_t a0 = f0 + (q0 / WB) * f_part + (q0 % WB) * 16;
+                        const uint32_t a1 = f0 + (q1 / WB) * f_part + (q1 % WB) * 16;
+                        umma2_ts(tmem + kColG, tmem + b * 128 + ks * 8, umma_smem_desc(a0, a1 - a0, lbo_b), id_g,
+                                 (t > 0) || (ks > 0));
+                    }
+                    umma2_commit(smem_u32(&bars->empty_f[s]));
+                }
+                __syncwarp();
+                if (t + 2 < nt) issue_t(t + 2);
+            }
+            if (elect_one()) umma2_commit(smem_u32(&bars->g_full));
+            __syncwarp();
         }
-    } else {
+    } else if (warp < 6) {
         const int q = warp & 3;
         const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-        for (int t = 0; t < ntiles; ++t) {
-            mbar_wait(smem_u32(&bars->st_full), t & 1);
+        const int row = jp * 2 * kTile + static_cast<int>(rank) * kTile + q * 32 + lane;
+        const uint32_t e_full0 = mapa_shared(smem_u32(&bars->e_full[0]), 0);
+        const uint32_t e_full1 = mapa_shared(smem_u32(&bars->e_full[1]), 0);
+        const float scale = pcm_grad_scale(bound);
+        const uint4* mrow = mask + (static_cast<size_t>(n) * NS + s_begin) * HWpj + row;
+        uint4 mw_next = nt > 0 ? __ldg(mrow) : make_uint4(0, 0, 0, 0);
+        for (int t = 0; t < nt; ++t) {
+            const int b = t & 1;
+            const uint4 mw4 = mw_next;
+            if (t + 1 < nt) mw_next = __ldg(mrow + static_cast<size_t>(t + 1) * HWpj);
+            const uint32_t mw[4] = {mw4.x, mw4.y, mw4.z, mw4.w};
+            mbar_wait(smem_u32(&bars->t_full[b]), (t >> 1) & 1);
             tc_fence_after();
+            const uint32_t base = tmem + lane_addr + b * 128;
 #pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4) {
-                uint32_t sv[32], tv[32], pk[16];
-                tmem_ld32(tmem + lane_addr + kColBS + c4 * 32, sv);
-                tmem_ld32(tmem + lane_addr + kColBT + c4 * 32, tv);
+            for (int c = 0; c < NCOL / 32; ++c) {
+                uint32_t r[32], pk[16];
+                tmem_ld32(base + c * 32, r);
                 tmem_ld_wait();
-#pragma unroll
-                for (int m = 0; m < 16; ++m) {
-                    const float a = __uint_as_float(sv[2 * m]) > 0.f ? __uint_as_float(tv[2 * m]) : 0.f;
-                    const float b = __uint_as_float(sv[2 * m + 1]) > 0.f ? __uint_as_float(tv[2 * m + 1]) : 0.f;
-                    pk[m] = pack_bf16x2(a, b);
-                }
-                tmem_st16(tmem + lane_addr + kColBE + c4 * 16, pk);
+                mask_scale_pack<32>(r, mw[c], scale, pk);
+                tmem_st16(base + c * 16, pk);
+            }
+            if (NCOL % 32) {
+                constexpr int c = NCOL / 32;
+                uint32_t r[16], pk[8];
+                tmem_ld16(base + c * 32, r);
+                tmem_ld_wait();
+                mask_scale_pack<16>(r, mw[c & 3], scale, pk);
+                tmem_st8(base + c * 16, pk);
             }
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&bars->e_full));
+            if (lane == 0) mbar_arrive_cluster(b ? e_full1 : e_full0);
         }
         mbar_wait(smem_u32(&bars->g_full), 0);
         tc_fence_after();
-        const int row = tj * kTile + q * 32 + lane;
-        float4* dst = reinterpret_cast<float4*>(dfhat + ((static_cast<size_t>(n) * nsplit + sp) * HWp + row) * K);
+        // dfhat [n][sp][K][HWpj]: for a fixed channel the 32 lanes of a warp write 32 consecutive pixels
+        float* dst = dfhat + ((static_cast<size_t>(n) * nsplit + sp) * K) * HWpj + row;
         for (int c = 0; c < (K >> 4); ++c) {
             uint32_t r[16];
-            tmem_ld16(tmem + lane_addr + kColBG + c * 16, r);
+            tmem_ld16(tmem + lane_addr + kColG + c * 16, r);
             tmem_ld_wait();
 #pragma unroll
-            for (int v = 0; v < 4; ++v)
-                dst[c * 4 + v] = make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]),
-                                             __uint_as_float(r[4 * v + 2]), __uint_as_float(r[4 * v + 3]));
+            for (int v = 0; v < 16; ++v) dst[static_cast<size_t>(c * 16 + v) * HWpj] = __uint_as_float(r[v]);
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem, kTmemCols);
+    cluster_sync_all();
+    if (warp == 1) tmem_dealloc_2cta(tmem, kTmemCols);
 }
 
 // grad_f[n,k,p] = dfh[k] * inv - f[k] * (sum_k dfh[k] f[k]) * inv^2 / |f|,  inv = 1/(|f| + 1e-5)
-// (autograd of f / (norm(f) + 1e-5), network/resnet38_contrast.py:70); dfh summed over the i-splits.
-__global__ void __launch_bounds__(256) pcm_bwd_post_kernel(const float* __restrict__ dfhat,
-                                                           const float* __restrict__ f,
+// (autograd of f / (norm(f) + 1e-5), network/resnet38_contrast.py:70); dfh = sum over the i-splits / 2^e.
+// CTA = 64 pixels x 4 channel phases; every global access is coalesced along the pixel axis.
+constexpr int kPostPix = 64;
+template <int KMAX>
+__global__ void __launch_bounds__(256) pcm_bwd_post_kernel(const float* __restrict__ dfhat, const float* __restrict__ f,
                                                            const float* __restrict__ inv_norm,
-                                                           float* __restrict__ grad_f, int K, int HW,
-                                                           int HWp, int nsplit) {
-    extern __shared__ float s_g[];        // [K][129]
-    __shared__ float s_dot[2][kTile];
-    const int t = blockIdx.x, n = blockIdx.y;
-    // coalesced read of the pixel-major gradient rows
-    for (int idx = threadIdx.x; idx < kTile * K; idx += blockDim.x) {
-        const int r = idx / K, k = idx - r * K;
-        float acc = 0.f;
-        for (int sp = 0; sp < nsplit; ++sp)
-            acc += __ldg(dfhat + ((static_cast<size_t>(n) * nsplit + sp) * HWp + t * kTile + r) * K + k);
-        s_g[k * 129 + r] = acc;
-    }
-    __syncthreads();
-    const int px = threadIdx.x & 127, half = threadIdx.x >> 7;
-    const int p = t * kTile + px;
+                                                           const float* __restrict__ bound, float* __restrict__ grad_f,
+                                                           int K, int HW, int HWpj, int nsplit) {
+    __shared__ float s_dot[4][kPostPix];
+    const int n = blockIdx.y;
+    const int px = threadIdx.x & (kPostPix - 1), ph = threadIdx.x >> 6;
+    const int p = blockIdx.x * kPostPix + px;
     const bool live = p < HW;
-    const float* fp = f + static_cast<size_t>(n) * K * HW + p;
+    const float unscale = 1.f / pcm_grad_scale(bound);
+    float g[KMAX / 4], fv[KMAX / 4];
     float dot = 0.f;
-    if (live)
-        for (int k = half; k < K; k += 2) dot = fmaf(s_g[k * 129 + px], __ldg(fp + static_cast<size_t>(k) * HW), dot);
-    s_dot[half][px] = dot;
+#pragma unroll
+    for (int i = 0; i < KMAX / 4; ++i) {
+        const int k = 4 * i + ph;
+        g[i] = 0.f;
+        fv[i] = (live && k < K) ? __ldg(f + (static_cast<size_t>(n) * K + k) * HW + p) : 0.f;
+    }
+    for (int sp = 0; sp < nsplit; ++sp) {
+        const float* src = dfhat + (static_cast<size_t>(n) * nsplit + sp) * K * HWpj + p;
+#pragma unroll
+        for (int i = 0; i < KMAX / 4; ++i) {
+            const int k = 4 * i + ph;
+            if (live && k < K) g[i] += __ldg(src + static_cast<size_t>(k) * HWpj);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < KMAX / 4; ++i) {
+        g[i] *= unscale;
+        dot = fmaf(g[i], fv[i], dot);
+    }
+    s_dot[ph][px] = dot;
     __syncthreads();
     if (!live) return;
-    dot = s_dot[0][px] + s_dot[1][px];
-    const float inv = inv_norm[static_cast<size_t>(n) * HWp + p];
+    dot = s_dot[0][px] + s_dot[1][px] + s_dot[2][px] + s_dot[3][px];
+    const float inv = inv_norm[static_cast<size_t>(n) * HWpj + p];
     const float nrm = 1.f / inv - 1e-5f;
     const float coef = nrm > 0.f ? dot * inv * inv / nrm : 0.f;
-    float* gp = grad_f + static_cast<size_t>(n) * K * HW + p;
-    for (int k = half; k < K; k += 2)
-        gp[static_cast<size_t>(k) * HW] = s_g[k * 129 + px] * inv - __ldg(fp + static_cast<size_t>(k) * HW) * coef;
+#pragma unroll
+    for (int i = 0; i < KMAX / 4; ++i) {
+        const int k = 4 * i + ph;
+        if (k < K) grad_f[(static_cast<size_t>(n) * K + k) * HW + p] = g[i] * inv - fv[i] * coef;
+    }
 }
 
-static size_t bwd_smem_bytes(int K) {
-    return static_cast<size_t>(kTile) * K * 2 * (1 + kStages) + (1 + kStages) * kAugTileBytes + sizeof(BwdBars) + 64;
+template <bool PRECISE>
+static size_t fwd_smem_bytes(int K, int wb) {
+    constexpr int FS = FwdCfg<PRECISE>::kFStages;
+    const size_t a = static_cast<size_t>(kTile) * K * 2, b = static_cast<size_t>(wb) * K * 2;
+    return (PRECISE ? 2 : 1) * a + FS * (PRECISE ? 2 : 1) * b + kCamStages * static_cast<size_t>(2 * wb) * 64 +
+           sizeof(FwdBars<FS>) + 64;
 }
 
-static size_t fwd_smem_bytes(int K) {
-    return static_cast<size_t>(kTile) * K * 2 * (1 + kStages) + kStages * kCamTileBytes + sizeof(FwdBars) + 64;
+static size_t bwd_smem_bytes(int K, int wb, bool split) {
+    const size_t ku = split ? 3 * kAugK : kAugK;
+    return static_cast<size_t>(kTile) * ku * 2 + kBwdStages * (static_cast<size_t>(wb) * ku * 2 + static_cast<size_t>(wb) * K * 2) +
+           sizeof(BwdBars) + 64;
 }
 
 }  // namespace wsegk
@@ -553,6 +819,7 @@ struct PcmProf {
     bool have[2] = {false, false};
 };
 thread_local PcmProf g_prof;
+thread_local long long* g_trace = nullptr;   // device buffer of 768 int64 for the forward kernel's timeline, or null
 void prof_mark(int which, wsegk_stream_t stream) {
     if (!g_prof.on) return;
     if (!g_prof.ev[which]) cudaEventCreate(&g_prof.ev[which]);
@@ -563,6 +830,11 @@ void prof_mark(int which, wsegk_stream_t stream) {
 
 extern "C" int wsegk_debug_pcm_profile(int enable) {
     g_prof.on = enable != 0;
+    return WSEGK_OK;
+}
+
+extern "C" int wsegk_debug_pcm_trace(long long* device_buffer) {
+    g_trace = device_buffer;
     return WSEGK_OK;
 }
 
@@ -582,12 +854,48 @@ static int pcm_check(const char* who, int N, int C, int K, int h, int w) {
     WSEGK_REQUIRE(N > 0 && h > 0 && w > 0, WSEGK_ERR_BAD_SHAPE, "%s: N,h,w must be positive", who);
     WSEGK_REQUIRE(C >= 1 && C <= kMaxClasses, WSEGK_ERR_BAD_SHAPE, "%s: need 1 <= C <= %d (got %d)", who,
                   kMaxClasses, C);
-    WSEGK_REQUIRE(K >= 16 && K <= kMaxPcmK && (K % 16) == 0, WSEGK_ERR_BAD_SHAPE,
-                  "%s: need K %% 16 == 0 and 16 <= K <= %d (got %d)", who, kMaxPcmK, K);
-    WSEGK_REQUIRE(static_cast<long long>(N) * ceil_div(h * w, kTile) < (1ll << 30), WSEGK_ERR_BAD_SHAPE,
-                  "%s: problem too large", who);
+    WSEGK_REQUIRE(K >= 32 && K <= kMaxPcmK && (K % 32) == 0, WSEGK_ERR_BAD_SHAPE,
+                  "%s: need K %% 32 == 0 and 32 <= K <= %d (got %d)", who, kMaxPcmK, K);
+    WSEGK_REQUIRE(static_cast<long long>(h) * w <= (1 << 22) && static_cast<long long>(N) * h * w < (1ll << 28),
+                  WSEGK_ERR_BAD_SHAPE, "%s: problem too large", who);
     return WSEGK_OK;
 }
+
+template <int WB, bool PRECISE>
+static int launch_fwd(const PcmPlan& pl, int N, wsegk_stream_t stream) {
+    const size_t smem = fwd_smem_bytes<PRECISE>(pl.K, WB);
+    WSEGK_REQUIRE(smem <= 232448, WSEGK_ERR_BAD_SHAPE, "pcm_fwd: %zu bytes of shared memory needed", smem);
+    WSEGK_CUDA_OK(cudaFuncSetAttribute(pcm_fwd_kernel<WB, PRECISE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem)));
+    pcm_fwd_kernel<WB, PRECISE><<<dim3(2 * pl.PJ, pl.nsplit, N), kMainThreads, smem, stream>>>(
+        reinterpret_cast<const uint8_t*>(pl.fa_hi), reinterpret_cast<const uint8_t*>(pl.fa_lo),
+        reinterpret_cast<const uint8_t*>(pl.fb_hi), reinterpret_cast<const uint8_t*>(pl.fb_lo),
+        reinterpret_cast<const uint8_t*>(pl.camb), pl.part, reinterpret_cast<uint4*>(pl.mask), pl.K, pl.PJ, pl.NS,
+        pl.nsplit, g_trace);
+    return WSEGK_OK;
+}
+
+template <int WB, bool SPLIT>
+static int launch_bwd(const PcmPlan& pl, int N, wsegk_stream_t stream) {
+    const size_t smem = bwd_smem_bytes(pl.K, WB, SPLIT);
+    WSEGK_REQUIRE(smem <= 232448, WSEGK_ERR_BAD_SHAPE, "pcm_bwd: %zu bytes of shared memory needed", smem);
+    WSEGK_CUDA_OK(cudaFuncSetAttribute(pcm_bwd_kernel<WB, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem)));
+    pcm_bwd_kernel<WB, SPLIT><<<dim3(2 * pl.PJ, pl.nsplit, N), kMainThreads, smem, stream>>>(
+        reinterpret_cast<const uint8_t*>(pl.ua), reinterpret_cast<const uint8_t*>(pl.vb),
+        reinterpret_cast<const uint8_t*>(pl.fb_hi), reinterpret_cast<const uint4*>(pl.mask), pl.bound, pl.dfhat, pl.K,
+        pl.PJ, pl.NS, pl.nsplit);
+    return WSEGK_OK;
+}
+
+#define WSEGK_DISPATCH_WB(fn, flag, ...)                                                                 \
+    do {                                                                                                 \
+        int _rc;                                                                                         \
+        if (pl.wb == 64) _rc = (flag) ? fn<64, true>(__VA_ARGS__) : fn<64, false>(__VA_ARGS__);          \
+        else if (pl.wb == 56) _rc = (flag) ? fn<56, true>(__VA_ARGS__) : fn<56, false>(__VA_ARGS__);     \
+        else _rc = (flag) ? fn<48, true>(__VA_ARGS__) : fn<48, false>(__VA_ARGS__);                      \
+        if (_rc) return _rc;                                                                             \
+    } while (0)
 
 extern "C" int wsegk_pcm_fwd(const float* f, const float* cam_norm, float* cam_rv, int N, int C, int K, int h,
                              int w, void* workspace, size_t workspace_bytes, wsegk_stream_t stream) {
@@ -596,27 +904,34 @@ extern "C" int wsegk_pcm_fwd(const float* f, const float* cam_norm, float* cam_r
     if (int rc = pcm_check("pcm_fwd", N, C, K, h, w)) return rc;
     WSEGK_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, WSEGK_ERR_BAD_ALIGN,
                   "pcm_fwd: workspace must be 1024-byte aligned");
-    PcmPlan pl = make_pcm_plan(workspace, N, C, K, h, w);
+    const int precise = pcm_mode();
+    PcmPlan pl = make_pcm_plan(workspace, N, C, K, h, w, precise);
     WSEGK_REQUIRE(workspace_bytes >= pl.bytes, WSEGK_ERR_WORKSPACE_TOO_SMALL, "pcm_fwd: workspace %zu < %zu",
                   workspace_bytes, pl.bytes);
     {
         const size_t smem = static_cast<size_t>(K) * 129 * sizeof(float);
-        WSEGK_CUDA_OK(cudaFuncSetAttribute(pcm_prep_f_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           static_cast<int>(smem)));
-        pcm_prep_f_kernel<<<dim3(pl.T, N), 256, smem, stream>>>(f, pl.fhat, pl.inv_norm, K, pl.HW, pl.T, pl.HWp);
-        pcm_prep_cam_kernel<<<dim3(pl.T, N), 128, 0, stream>>>(cam_norm, pl.camb, C, pl.HW, pl.T);
+        const int tiles = ceil_div(std::max(pl.HWpj, pl.HWpi), kTile);
+        uint4 *a_hi = reinterpret_cast<uint4*>(pl.fa_hi), *a_lo = reinterpret_cast<uint4*>(pl.fa_lo);
+        uint4 *b_hi = reinterpret_cast<uint4*>(pl.fb_hi), *b_lo = reinterpret_cast<uint4*>(pl.fb_lo);
+        if (precise) {
+            WSEGK_CUDA_OK(cudaFuncSetAttribute(pcm_prep_f_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               static_cast<int>(smem)));
+            pcm_prep_f_kernel<true><<<dim3(tiles, N), 256, smem, stream>>>(f, a_hi, a_lo, b_hi, b_lo, pl.inv_norm, K,
+                                                                            pl.HW, pl.PJ, pl.NS, pl.wb);
+        } else {
+            WSEGK_CUDA_OK(cudaFuncSetAttribute(pcm_prep_f_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               static_cast<int>(smem)));
+            pcm_prep_f_kernel<false><<<dim3(tiles, N), 256, smem, stream>>>(f, a_hi, a_lo, b_hi, b_lo, pl.inv_norm, K,
+                                                                             pl.HW, pl.PJ, pl.NS, pl.wb);
+        }
+        pcm_prep_cam_kernel<<<dim3(pl.NS, N), 128, 0, stream>>>(cam_norm, reinterpret_cast<uint4*>(pl.camb), C, pl.HW,
+                                                                pl.NS, pl.wb);
     }
-    {
-        const size_t smem = fwd_smem_bytes(K);
-        WSEGK_CUDA_OK(cudaFuncSetAttribute(pcm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           static_cast<int>(smem)));
-        prof_mark(0, stream);
-        pcm_fwd_kernel<<<dim3(pl.T, pl.nsplit, N), kFwdThreads, smem, stream>>>(pl.fhat, pl.camb, pl.part, K,
-                                                                                pl.T, pl.HWp, pl.nsplit);
-        prof_mark(1, stream);
-    }
-    pcm_fwd_finalize_kernel<<<dim3(ceil_div(pl.HWp, 128), N), 128, 0, stream>>>(pl.part, cam_rv, pl.dsum, C,
-                                                                                 pl.HW, pl.HWp, pl.nsplit);
+    prof_mark(0, stream);
+    WSEGK_DISPATCH_WB(launch_fwd, precise, pl, N, stream);
+    prof_mark(1, stream);
+    pcm_fwd_finalize_kernel<<<dim3(ceil_div(pl.HWpj, 128), N), 128, 0, stream>>>(pl.part, cam_rv, pl.dsum, C, pl.HW,
+                                                                                  pl.HWpj, pl.nsplit);
     count_launches(4);
     WSEGK_CUDA_OK(cudaGetLastError());
     return WSEGK_OK;
@@ -631,28 +946,27 @@ extern "C" int wsegk_pcm_bwd(const float* f, const float* cam_norm, const float*
     if (int rc = pcm_check("pcm_bwd", N, C, K, h, w)) return rc;
     WSEGK_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, WSEGK_ERR_BAD_ALIGN,
                   "pcm_bwd: workspace must be 1024-byte aligned");
-    PcmPlan pl = make_pcm_plan(workspace, N, C, K, h, w);
+    const int precise = pcm_mode();
+    PcmPlan pl = make_pcm_plan(workspace, N, C, K, h, w, precise);
     WSEGK_REQUIRE(workspace_bytes >= pl.bytes, WSEGK_ERR_WORKSPACE_TOO_SMALL, "pcm_bwd: workspace %zu < %zu",
                   workspace_bytes, pl.bytes);
-    pcm_bwd_prep_kernel<<<dim3(pl.T, N), 128, 0, stream>>>(cam_norm, cam_rv, grad_cam_rv, pl.dsum, pl.uaug,
-                                                           pl.vaug, C, pl.HW, pl.T, pl.HWp);
+    WSEGK_CUDA_OK(cudaMemsetAsync(pl.bound, 0, sizeof(float), stream));
     {
-        const size_t smem = bwd_smem_bytes(K);
-        WSEGK_CUDA_OK(cudaFuncSetAttribute(pcm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           static_cast<int>(smem)));
-        prof_mark(2, stream);
-        pcm_bwd_kernel<<<dim3(pl.T, pl.nsplit, N), kFwdThreads, smem, stream>>>(pl.fhat, pl.uaug, pl.vaug,
-                                                                                pl.dfhat, K, pl.T, pl.HWp,
-                                                                                pl.nsplit);
-        prof_mark(3, stream);
+        const int tiles = ceil_div(std::max(pl.HWpj, pl.HWpi), kTile);
+        if (precise)
+            pcm_bwd_prep_kernel<true><<<dim3(tiles, N), 128, 0, stream>>>(
+                cam_norm, cam_rv, grad_cam_rv, pl.dsum, reinterpret_cast<uint4*>(pl.ua), reinterpret_cast<uint4*>(pl.vb),
+                reinterpret_cast<unsigned int*>(pl.bound), C, pl.HW, pl.PJ, pl.NS, pl.wb);
+        else
+            pcm_bwd_prep_kernel<false><<<dim3(tiles, N), 128, 0, stream>>>(
+                cam_norm, cam_rv, grad_cam_rv, pl.dsum, reinterpret_cast<uint4*>(pl.ua), reinterpret_cast<uint4*>(pl.vb),
+                reinterpret_cast<unsigned int*>(pl.bound), C, pl.HW, pl.PJ, pl.NS, pl.wb);
     }
-    {
-        const size_t smem = static_cast<size_t>(K) * 129 * sizeof(float);
-        WSEGK_CUDA_OK(cudaFuncSetAttribute(pcm_bwd_post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           static_cast<int>(smem)));
-        pcm_bwd_post_kernel<<<dim3(pl.T, N), 256, smem, stream>>>(pl.dfhat, f, pl.inv_norm, grad_f, K, pl.HW,
-                                                                  pl.HWp, pl.nsplit);
-    }
+    prof_mark(2, stream);
+    WSEGK_DISPATCH_WB(launch_bwd, precise, pl, N, stream);
+    prof_mark(3, stream);
+    pcm_bwd_post_kernel<kMaxPcmK><<<dim3(ceil_div(pl.HW, kPostPix), N), 256, 0, stream>>>(
+        pl.dfhat, f, pl.inv_norm, pl.bound, grad_f, K, pl.HW, pl.HWpj, pl.nsplit);
     count_launches(3);
     WSEGK_CUDA_OK(cudaGetLastError());
     return WSEGK_OK;

@@ -57,6 +57,49 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
 }
 
+// ------------------------------------------------------------------ thread-block clusters (CTA pairs)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+// shared::cta address of this CTA -> shared::cluster address of the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+// arrive on an mbarrier that may live in the peer CTA (shared::cluster address).  Default semantics
+// (release at CTA scope): a cluster-scope release compiles to MEMBAR.ALL.GPU, which made every stage wait for
+// its outstanding global stores (ncu r01: 25 % of the forward's stall samples).  The data the barrier guards
+// lives in TMEM / shared memory and is ordered by tcgen05.fence / the async proxy, not by this fence.
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
+// wait on a local mbarrier whose arrivals may come from the peer CTA (cluster-scope acquire)
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait_cluster(bar, parity)) {
+        if (++spins > WSEGK_SPIN_LIMIT) __trap();
+    }
+}
+
 // ------------------------------------------------------------------ bulk TMA (1-D, no tensor map)
 // global -> shared, completion signalled on an mbarrier via complete_tx::bytes.
 // size must be a multiple of 16 bytes, both addresses 16-byte aligned.
@@ -67,6 +110,20 @@ __device__ __forceinline__ void tma_load_1d(uint32_t dst_smem, const void* src, 
             "r"(dst_smem),
         "l"(src), "r"(bytes), "r"(bar)
         : "memory");
+}
+// the same copy issued as several independent bulk operations (the copy engine keeps only a few requests of ONE
+// operation in flight; ncu/trace r01: a single 21 KB operation streams at ~12 B/clk)
+#ifndef WSEGK_TMA_SPLIT
+#define WSEGK_TMA_SPLIT 2048u
+#endif
+__device__ __forceinline__ void tma_load_1d_split(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+    const uint8_t* s = static_cast<const uint8_t*>(src);
+    uint32_t off = 0;
+    while (off < bytes) {
+        const uint32_t n = (bytes - off < WSEGK_TMA_SPLIT) ? (bytes - off) : WSEGK_TMA_SPLIT;
+        tma_load_1d(dst_smem + off, s + off, n, bar);
+        off += n;
+    }
 }
 // shared -> global bulk store (bulk async-group completion)
 __device__ __forceinline__ void tma_store_1d(void* dst, uint32_t src_smem, uint32_t bytes) {
@@ -156,6 +213,55 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
                  : "memory");
 }
 
+// ------------------------------------------------------------------ CTA-pair (cta_group::2) variants
+// TMEM allocation for a CTA pair: one warp of EACH CTA executes it with the same shared-memory offset.
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(dst_smem),
+                 "r"(ncols)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2cta() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(ncols)
+                 : "memory");
+}
+// Instruction descriptor, kind::f16: fmt 0 = F16, 1 = BF16 (A and B), FP32 accumulation.
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int fmt_ab, int M, int N, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | (static_cast<uint32_t>(fmt_ab) << 7) | (static_cast<uint32_t>(fmt_ab) << 10) |
+           (static_cast<uint32_t>(a_mn_major) << 15) | (static_cast<uint32_t>(b_mn_major) << 16) |
+           (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+// D[tmem, 256 x N over the CTA pair] (+)= A[smem of each CTA: its 128 rows] * B[smem: N/2 rows from each CTA]
+// Issued by ONE thread of the leader CTA (rank 0).
+__device__ __forceinline__ void umma2_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma2_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive (once all previously issued tcgen05 ops of this thread completed) on the mbarrier at the same
+// shared-memory offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma2_commit(uint32_t bar) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(bar),
+        "h"(static_cast<uint16_t>(3))
+        : "memory");
+}
+
 // ------------------------------------------------------------------ TMEM <-> registers
 // 32x32b: thread L of the warp touches TMEM lane (warp%4)*32 + L, N consecutive 32-bit columns.
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -206,6 +312,24 @@ __device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
     uint32_t d;
     asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;\n" : "=r"(d) : "f"(hi), "f"(lo));
     return d;
+}
+
+// two fp32 -> packed f16x2 (element 0 in the low half)
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;\n" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+__device__ __forceinline__ uint32_t pack_f16x2_relu(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;\n" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+        : "memory");
 }
 
 }  // namespace wsegk

@@ -102,8 +102,12 @@ def pcm(cam_norm_t: torch.Tensor, f: torch.Tensor) -> torch.Tensor:
     return _PCMFunction.apply(cam_norm_t.detach(), f)
 
 
-# Relative Frobenius error bound of grad_f vs the fp32 oracle that the PCM backward is held to (tests/test_gpu_parity.py).
-PCM_GRAD_TOL = 8e-2
+# Relative Frobenius error bound of grad_f vs the fp32 oracle that the PCM backward is held to in the default
+# ("precise") mode (tests/test_gpu_parity.py; BASELINE.json north_star: gradients within 1e-3).
+PCM_GRAD_TOL = 1e-3
+# "fast" mode: the sign of S is decided from single FP16 products, so entries with |S| < ~1e-4 (about 1e-4 of all
+# entries for random-sign features) can flip and each flip adds/drops a whole gradient term.
+PCM_GRAD_TOL_FAST = 1e-1
 
 
 def launch_count() -> int:
@@ -123,12 +127,24 @@ def pcm_main_ms() -> Tuple[float, float]:
     return float(a.value), float(b.value)
 
 
+def set_pcm_mode(mode: str) -> None:
+    """'precise' (default): split-FP16 operands, sign mask of S exact to ~2^-21; 'fast': single products."""
+    if mode not in ("precise", "fast"):
+        raise ValueError("mode must be 'precise' or 'fast'")
+    check(_lib.lib().wsegk_pcm_set_mode(1 if mode == "precise" else 0), "wsegk_pcm_set_mode")
+
+
+def get_pcm_mode() -> str:
+    return "precise" if _lib.lib().wsegk_pcm_get_mode() == 1 else "fast"
+
+
 def pcm_layout(n: int, c: int, k: int, h: int, w: int) -> dict:
-    """Test aid: byte offsets of the PCM workspace sections."""
+    """Test aid: byte offsets of the PCM workspace sections and the tiling parameters."""
     import ctypes
-    buf = (ctypes.c_size_t * 12)()
-    got = _lib.lib().wsegk_debug_pcm_layout(n, c, k, h, w, buf, 12)
-    names = ["fhat", "camb", "inv_norm", "dsum", "part", "uaug", "vaug", "dfhat", "bytes", "nsplit", "T", "HWp"]
+    buf = (ctypes.c_size_t * 20)()
+    got = _lib.lib().wsegk_debug_pcm_layout(n, c, k, h, w, buf, 20)
+    names = ["fa_hi", "fa_lo", "fb_hi", "fb_lo", "camb", "inv_norm", "dsum", "part", "mask", "ua", "vb", "dfhat",
+             "bound", "bytes", "nsplit", "PJ", "HWpj", "wb", "NS", "HWpi"]
     return {names[i]: int(buf[i]) for i in range(got)}
 
 
