@@ -114,6 +114,30 @@ class HotPath:
         return losses, gf1, gf2, g1, g2, outs
 
 
+class GraphedStep:
+    """The resident step captured once into a CUDA graph and replayed (the C ABI only enqueues on the caller's stream
+    and never synchronises, so the whole path — NCCL all-gather included — is capturable)."""
+
+    def __init__(self, hp: HotPath):
+        self.hp = hp
+        side = torch.cuda.Stream(device=hp.dev)
+        side.wait_stream(torch.cuda.current_stream(hp.dev))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                hp.step()
+        torch.cuda.current_stream(hp.dev).wait_stream(side)
+        torch.cuda.synchronize(hp.dev)
+        self.graph = torch.cuda.CUDAGraph()
+        l0 = hp.ops.launch_count()
+        with torch.cuda.graph(self.graph):
+            self.out = hp.step()
+        self.launches = hp.ops.launch_count() - l0
+
+    def step(self):
+        self.graph.replay()
+        return self.out
+
+
 class E2EPath:
     """The same path through the public, reference-facing API (autograd operators + loss.contrast_terms), from PINNED
     HOST buffers: every step copies the head-level inputs host->device, runs Net.forward's tail (K1a, K2, bilinear x8
@@ -182,7 +206,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            self._stop.wait(0.02)
+            self._stop.wait(0.004)
 
     def __enter__(self):
         if self.nv is not None:
@@ -329,15 +353,18 @@ def run_ours(args):
     l0 = ops.launch_count()
     hp.step()
     launches_per_step = ops.launch_count() - l0
-    ops.pcm_profile(True)
     fwd_ms, bwd_ms = [], []
-
-    def step_prof():
-        hp.step()
-
+    stepper, mode = hp, "eager"
+    if not args.no_graph:
+        try:
+            stepper = GraphedStep(hp)
+            launches_per_step, mode = stepper.launches, "cuda_graph"
+        except Exception as exc:          # e.g. a collective that cannot be captured on this stack
+            if rank == 0:
+                print(f"bench.py: CUDA graph capture failed ({type(exc).__name__}: {exc}); timing eagerly", file=sys.stderr)
+            stepper, mode = hp, "eager"
     with ClockSampler(local) as clk:
-        dev_ms, wall_ms = time_steps(step_prof, args.steps, args.warmup, dev, flush, barrier)
-    ops.pcm_profile(False)
+        dev_ms, wall_ms = time_steps(stepper.step, args.steps, args.warmup, dev, flush, barrier)
     # main-kernel durations of the last step (view-2 launches overwrite view-1's: profile view 1 separately below)
     t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -400,7 +427,7 @@ def run_ours(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16 tensor-core operands, fp32 accumulate (PCM); f32 elsewhere", "data": "synthetic",
-            "config": config_dict(world), "image_mpix_per_s": value * 64,
+            "config": dict(config_dict(world), launch=mode), "image_mpix_per_s": value * 64,
             "clocks": clk.summary(), "gpu_launches": int(launches_per_step * args.steps),
             "gpu_launches_per_step": int(launches_per_step),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e.h2d_bytes,
@@ -426,6 +453,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time the resident step eagerly instead of as a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -10,6 +10,7 @@ import os
 import numpy as np
 import pytest
 import torch
+import torch.nn.functional as F
 
 from oracle import reference_fn as R
 from oracle.make_golden import LOSS_CASE, PCM_CASE
@@ -227,16 +228,49 @@ def test_contrast_terms_vs_oracle(cuda_dev, n, hw1, hw2, d):
         assert float((mine["prototypes" + v] - ref["prototypes" + v]).abs().max()) <= 1e-6
     for k in ("loss_nce", "loss_intra_nce", "loss_cross_nce", "loss_cross_nce2"):
         assert float(mine[k]) == pytest.approx(float(ref[k]), rel=1e-5), k
-    assert rel_max(f1.grad, r1.grad) <= TOL and rel_max(f2.grad, r2.grad) <= TOL
-    # hard-pixel sets: multiplicity with which each pixel enters its class's mined set (random half + hard half)
-    m = L.contrast_terms(a["f_proj"], a["cam_rv_down"], b["f_proj"], b["cam_rv_down"], label, 0.2, grid=grid, rng=7,
-                         want_mined=True)
-    for v in "12":
-        cnt = torch.zeros_like(m["mined" + v])
-        for _, rnd, hard in ref["sets" + v][1]:
-            cnt.index_add_(0, rnd, torch.ones_like(rnd, dtype=torch.int32))
-            cnt.index_add_(0, hard, torch.ones_like(hard, dtype=torch.int32))
-        assert torch.equal(cnt, m["mined" + v]), "mined set view " + v
+    # Two selections depend on the ORDER of nearly equal fp32 scores, which the kernel (sequential fma) and ATen (GEMM)
+    # round differently by ~1e-7:
+    #  (i)  the semi-hard prototype set of a pixel = ranks 3..12 of its 21 scores (contrast_train.py:293-294): pixels
+    #       whose scores at a set boundary (ranks 2|3 or 12|13) differ by less than 1e-6 may pick the other prototype;
+    #  (ii) the hard-pixel set of a class = an order-statistic window of sim (contrast_train.py:321-322): pixels whose
+    #       sim is within 1e-6 of another pixel's at the window edge may swap.
+    # Such pixels are identified from the ORACLE's values, must be rare, and are excluded from the gradient comparison;
+    # every other pixel must match: mined multiplicity exactly, gradient within TOL.
+    gm = L.contrast_terms(a["f_proj"], a["cam_rv_down"], b["f_proj"], b["cam_rv_down"], label, 0.2, grid=grid, rng=7,
+                          want_mined=True)
+    x1 = F.interpolate(a["f_proj"], size=grid, mode="bilinear", align_corners=True).requires_grad_(True)
+    x2 = b["f_proj"].clone().requires_grad_(True)
+    c1 = F.interpolate(a["cam_rv_down"], size=grid, mode="bilinear", align_corners=True)
+    rr = R.contrast_terms(x1, c1, x2, b["cam_rv_down"], label.reshape(n, -1, 1, 1), 0.2, sampler=R.ReferenceSampler(7),
+                          grid=grid, argmax_of="softmax")
+    rr["loss_nce"].backward()
+    all_clean = True
+    for v, xr, mine_g in (("1", x1, gm["grad_f1"]), ("2", x2, gm["grad_f2"])):
+        with torch.no_grad():
+            q = F.normalize(xr.detach().permute(0, 2, 3, 1).reshape(-1, d), dim=-1)
+            pl = rr["pseudo_label" + v]
+            sc = q @ rr["prototypes" + v].t()
+            srt = torch.sort(sc, dim=-1, descending=True)[0]
+            gap = torch.minimum(srt[:, 2] - srt[:, 3], srt[:, 12] - srt[:, 13])
+            keep = (gap > 1e-6) | (gap == 0)          # exact ties (identical prototypes) resolve by class index in both
+            cnt = torch.zeros_like(gm["mined" + v])
+            for _, rnd, hard in rr["sets" + v][1]:
+                cnt.index_add_(0, rnd, torch.ones_like(rnd, dtype=torch.int32))
+                cnt.index_add_(0, hard, torch.ones_like(hard, dtype=torch.int32))
+            mism = cnt != gm["mined" + v]
+            assert int(mism.sum()) <= 8, "mined set view " + v
+            sim = sc.gather(1, pl.reshape(-1, 1)).reshape(-1)
+            for cls in pl[mism].unique().tolist():
+                sims = sim[mism & (pl == cls)]
+                assert sims.numel() >= 2 and float(sims.max() - sims.min()) < 2e-6, "mined set view " + v
+            keep &= ~mism
+            assert int((~keep).sum()) <= max(2, keep.numel() // 200)          # < 0.5 % of the pixels
+            all_clean &= bool(keep.all())
+        mg = mine_g.permute(0, 2, 3, 1).reshape(-1, d)[keep]
+        rg = xr.grad.permute(0, 2, 3, 1).reshape(-1, d)[keep]
+        assert rel_max(mg, rg) <= TOL
+    if all_clean:
+        assert rel_max(f1.grad, r1.grad) <= TOL and rel_max(f2.grad, r2.grad) <= TOL
 
 
 def test_contrast_step_loss_golden(cuda_dev, golden_dir):

@@ -157,27 +157,33 @@ __global__ void __launch_bounds__(256) fullres_resample_kernel(const float* __re
 }
 
 // ---- backward ----------------------------------------------------------------------------------
-// gy(y,x) = sum over outputs (oy,ox) whose taps include (y,x) of weight * grad_out * label  (gather form)
-__device__ __forceinline__ float tap_weight(int o, int i, float scale, int in_size) {
-    int i0, i1; float l0, l1;
-    src_coord(o, scale, in_size, i0, i1, l0, l1);
-    float wgt = 0.f;
-    if (i0 == i) wgt += l0;
-    if (i1 == i) wgt += l1;
-    return wgt;
+// gy(y,x) = sum over outputs (oy,ox) whose taps include (y,x) of weight * grad_out * label.  Shrinking (scale >= 1) makes
+// i0(o) strictly increasing, so an input coordinate is the FIRST tap of at most one output and the SECOND tap of at
+// most one output: two (output index, weight) slots per coordinate, built in shared memory without atomics.
+struct TapSlot {
+    int o;
+    float w;
+};
+
+__device__ __forceinline__ void build_tap_table(TapSlot* tab, int in_size, int out_size, float scale) {
+    for (int i = threadIdx.x; i < 2 * in_size; i += blockDim.x) tab[i] = TapSlot{0, 0.f};
+    __syncthreads();
+    for (int o = threadIdx.x; o < out_size; o += blockDim.x) {
+        int i0, i1; float l0, l1;
+        src_coord(o, scale, in_size, i0, i1, l0, l1);
+        if (i1 == i0) {
+            tab[2 * i0] = TapSlot{o, l0 + l1};
+        } else {
+            tab[2 * i0] = TapSlot{o, l0};
+            tab[2 * i1 + 1] = TapSlot{o, l1};
+        }
+    }
+    __syncthreads();
 }
 
-// candidate output coordinates whose taps may include input coordinate i (scale >= 1)
-__device__ __forceinline__ void tap_candidates(int i, float scale, int out_size, int& first, int& last) {
-    if (scale <= 0.f) { first = 0; last = out_size - 1; return; }
-    int a = static_cast<int>(floorf(static_cast<float>(i - 1) / scale)) - 1;
-    int b = static_cast<int>(ceilf(static_cast<float>(i) / scale)) + 1;
-    first = max(a, 0);
-    last = min(b, out_size - 1);
-}
-
-// pass 1: per plane, S1 = sum gy*relu(z)/den^2 and S0 = sum gy*[z>0]/den  (block partials -> atomics-free two-stage)
-// pass 2: grad_p = [p>0] * ( gy*[z>0]/den + [idx==argmax]*(-S1) + [idx==argmin]*(S1 - S0) )
+// pass 1 (kWrite = false): per plane, S1 = sum gy*relu(z)/den^2 and S0 = sum gy*[z>0]/den  (block partials, fixed order)
+// pass 2 (kWrite = true) : grad_p = [p>0] * ( gy*[z>0]/den + [idx==argmax]*(-S1) + [idx==argmin]*(S1 - S0) )
+// Planes whose label is 0 carry no gradient: pass 1 skips them, pass 2 only writes zeros (vectorised).
 template <bool kWrite>
 __global__ void __launch_bounds__(256) fullres_bwd_kernel(const float* __restrict__ p,
                                                           const float* __restrict__ label,
@@ -186,6 +192,7 @@ __global__ void __launch_bounds__(256) fullres_bwd_kernel(const float* __restric
                                                           float* __restrict__ grad_p,
                                                           float* __restrict__ sums, int H, int W, int oh,
                                                           int ow, int nblk) {
+    extern __shared__ TapSlot s_tab[];            // [2*H] rows then [2*W] columns (resampling case only)
     const int plane = blockIdx.y;
     const int HW = H * W;
     const float lab = label[plane];
@@ -193,7 +200,13 @@ __global__ void __launch_bounds__(256) fullres_bwd_kernel(const float* __restric
     __shared__ float s_a[8], s_b[8];
     if (lab == 0.f) {
         if (kWrite) {
-            for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) dst[i] = 0.f;
+            if ((HW & 3) == 0) {
+                float4* d4 = reinterpret_cast<float4*>(dst);
+                for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (HW >> 2); i += gridDim.x * blockDim.x)
+                    d4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+                for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) dst[i] = 0.f;
+            }
         } else if (threadIdx.x == 0) {
             sums[(plane * nblk + blockIdx.x) * 2] = 0.f;
             sums[(plane * nblk + blockIdx.x) * 2 + 1] = 0.f;
@@ -206,8 +219,14 @@ __global__ void __launch_bounds__(256) fullres_bwd_kernel(const float* __restric
     const float* src = p + static_cast<size_t>(plane) * HW;
     const float* g = gout + static_cast<size_t>(plane) * oh * ow;
     const bool same = (oh == H && ow == W);
-    const float sy = oh > 1 ? static_cast<float>(H - 1) / static_cast<float>(oh - 1) : 0.f;
-    const float sx = ow > 1 ? static_cast<float>(W - 1) / static_cast<float>(ow - 1) : 0.f;
+    TapSlot* ty = s_tab;
+    TapSlot* tx = s_tab + 2 * H;
+    if (!same) {
+        const float sy = oh > 1 ? static_cast<float>(H - 1) / static_cast<float>(oh - 1) : 0.f;
+        const float sx = ow > 1 ? static_cast<float>(W - 1) / static_cast<float>(ow - 1) : 0.f;
+        build_tap_table(ty, H, oh, sy);
+        build_tap_table(tx, W, ow, sx);
+    }
     float S0 = 0.f, S1 = 0.f;
     if (kWrite) {
         // final plane sums from the pass-1 partials (fixed order => deterministic)
@@ -222,16 +241,14 @@ __global__ void __launch_bounds__(256) fullres_bwd_kernel(const float* __restric
             gy = __ldg(g + i) * lab;
         } else {
             const int y = i / W, x = i - y * W;
-            int oy0, oy1, ox0, ox1;
-            tap_candidates(y, sy, oh, oy0, oy1);
-            tap_candidates(x, sx, ow, ox0, ox1);
-            for (int oy = oy0; oy <= oy1; ++oy) {
-                const float wy = tap_weight(oy, y, sy, H);
-                if (wy == 0.f) continue;
-                for (int ox = ox0; ox <= ox1; ++ox) {
-                    const float wx = tap_weight(ox, x, sx, W);
-                    if (wx != 0.f) gy = fmaf(wy * wx, __ldg(g + oy * ow + ox), gy);
-                }
+            const TapSlot ya = ty[2 * y], yb = ty[2 * y + 1], xa = tx[2 * x], xb = tx[2 * x + 1];
+            if (ya.w != 0.f) {
+                if (xa.w != 0.f) gy = fmaf(ya.w * xa.w, __ldg(g + ya.o * ow + xa.o), gy);
+                if (xb.w != 0.f) gy = fmaf(ya.w * xb.w, __ldg(g + ya.o * ow + xb.o), gy);
+            }
+            if (yb.w != 0.f) {
+                if (xa.w != 0.f) gy = fmaf(yb.w * xa.w, __ldg(g + yb.o * ow + xa.o), gy);
+                if (xb.w != 0.f) gy = fmaf(yb.w * xb.w, __ldg(g + yb.o * ow + xb.o), gy);
             }
             gy *= lab;
         }
@@ -371,10 +388,17 @@ extern "C" int wsegk_fullres_norm_bwd(const float* p, const float* label, const 
                                            align_up(static_cast<size_t>(N) * C * kPlaneSplit * sizeof(MinMax), 1024));
     const int planes = N * C;
     const int nblk = std::min(64, ceil_div(H * W, 256 * 4));
-    fullres_bwd_kernel<false><<<dim3(nblk, planes), 256, 0, stream>>>(p, label, minmax, grad_out, grad_p, sums, H, W,
-                                                                     oh, ow, nblk);
-    fullres_bwd_kernel<true><<<dim3(nblk, planes), 256, 0, stream>>>(p, label, minmax, grad_out, grad_p, sums, H, W,
-                                                                    oh, ow, nblk);
+    const size_t tab = (oh == H && ow == W) ? 0 : static_cast<size_t>(2) * (H + W) * sizeof(TapSlot);
+    WSEGK_REQUIRE(tab <= 200 * 1024, WSEGK_ERR_BAD_SHAPE, "fullres_norm_bwd: H + W = %d too large for the tap tables",
+                  H + W);
+    WSEGK_CUDA_OK(cudaFuncSetAttribute(fullres_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(tab)));
+    WSEGK_CUDA_OK(cudaFuncSetAttribute(fullres_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(tab)));
+    fullres_bwd_kernel<false><<<dim3(nblk, planes), 256, tab, stream>>>(p, label, minmax, grad_out, grad_p, sums, H,
+                                                                       W, oh, ow, nblk);
+    fullres_bwd_kernel<true><<<dim3(nblk, planes), 256, tab, stream>>>(p, label, minmax, grad_out, grad_p, sums, H, W,
+                                                                      oh, ow, nblk);
     count_launches(2);
     WSEGK_CUDA_OK(cudaGetLastError());
     return WSEGK_OK;

@@ -745,51 +745,59 @@ pcm_bwd_kernel(const uint8_t* __restrict__ ua, const uint8_t* __restrict__ vb, c
 
 // grad_f[n,k,p] = dfh[k] * inv - f[k] * (sum_k dfh[k] f[k]) * inv^2 / |f|,  inv = 1/(|f| + 1e-5)
 // (autograd of f / (norm(f) + 1e-5), network/resnet38_contrast.py:70); dfh = sum over the i-splits / 2^e.
-// CTA = 64 pixels x 4 channel phases; every global access is coalesced along the pixel axis.
-constexpr int kPostPix = 64;
-template <int KMAX>
+// CTA = 32 pixels x 8 channel phases; every global access is a coalesced 128-byte row segment.  Pass 1 computes the
+// per-pixel dot product, pass 2 re-reads (L2) and writes; loads are issued in batches of 8 independent requests.
+constexpr int kPostPix = 32;
+constexpr int kPostPhases = 8;
 __global__ void __launch_bounds__(256) pcm_bwd_post_kernel(const float* __restrict__ dfhat, const float* __restrict__ f,
                                                            const float* __restrict__ inv_norm,
                                                            const float* __restrict__ bound, float* __restrict__ grad_f,
                                                            int K, int HW, int HWpj, int nsplit) {
-    __shared__ float s_dot[4][kPostPix];
+    __shared__ float s_dot[kPostPhases][kPostPix];
     const int n = blockIdx.y;
-    const int px = threadIdx.x & (kPostPix - 1), ph = threadIdx.x >> 6;
+    const int px = threadIdx.x & (kPostPix - 1), ph = threadIdx.x >> 5;
     const int p = blockIdx.x * kPostPix + px;
     const bool live = p < HW;
     const float unscale = 1.f / pcm_grad_scale(bound);
-    float g[KMAX / 4], fv[KMAX / 4];
+    const size_t split_stride = static_cast<size_t>(K) * HWpj;
+    const float* gsrc = dfhat + static_cast<size_t>(n) * nsplit * split_stride + p;
+    const float* fsrc = f + static_cast<size_t>(n) * K * HW + p;
+    const int per = K / kPostPhases;                      // channels per phase (K % 32 == 0 => per % 4 == 0)
+    const int k0 = ph * per;
     float dot = 0.f;
+    if (live) {
+        for (int kk = 0; kk < per; kk += 4) {
+            float g[4] = {0.f, 0.f, 0.f, 0.f}, fv[4];
 #pragma unroll
-    for (int i = 0; i < KMAX / 4; ++i) {
-        const int k = 4 * i + ph;
-        g[i] = 0.f;
-        fv[i] = (live && k < K) ? __ldg(f + (static_cast<size_t>(n) * K + k) * HW + p) : 0.f;
-    }
-    for (int sp = 0; sp < nsplit; ++sp) {
-        const float* src = dfhat + (static_cast<size_t>(n) * nsplit + sp) * K * HWpj + p;
+            for (int j = 0; j < 4; ++j) fv[j] = __ldg(fsrc + static_cast<size_t>(k0 + kk + j) * HW);
+            for (int sp = 0; sp < nsplit; ++sp) {
 #pragma unroll
-        for (int i = 0; i < KMAX / 4; ++i) {
-            const int k = 4 * i + ph;
-            if (live && k < K) g[i] += __ldg(src + static_cast<size_t>(k) * HWpj);
+                for (int j = 0; j < 4; ++j) g[j] += __ldg(gsrc + sp * split_stride + static_cast<size_t>(k0 + kk + j) * HWpj);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dot = fmaf(g[j] * unscale, fv[j], dot);
         }
-    }
-#pragma unroll
-    for (int i = 0; i < KMAX / 4; ++i) {
-        g[i] *= unscale;
-        dot = fmaf(g[i], fv[i], dot);
     }
     s_dot[ph][px] = dot;
     __syncthreads();
     if (!live) return;
-    dot = s_dot[0][px] + s_dot[1][px] + s_dot[2][px] + s_dot[3][px];
+    dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < kPostPhases; ++i) dot += s_dot[i][px];
     const float inv = inv_norm[static_cast<size_t>(n) * HWpj + p];
     const float nrm = 1.f / inv - 1e-5f;
     const float coef = nrm > 0.f ? dot * inv * inv / nrm : 0.f;
+    float* dst = grad_f + static_cast<size_t>(n) * K * HW + p;
+    for (int kk = 0; kk < per; kk += 4) {
+        float g[4] = {0.f, 0.f, 0.f, 0.f}, fv[4];
 #pragma unroll
-    for (int i = 0; i < KMAX / 4; ++i) {
-        const int k = 4 * i + ph;
-        if (k < K) grad_f[(static_cast<size_t>(n) * K + k) * HW + p] = g[i] * inv - fv[i] * coef;
+        for (int j = 0; j < 4; ++j) fv[j] = __ldg(fsrc + static_cast<size_t>(k0 + kk + j) * HW);
+        for (int sp = 0; sp < nsplit; ++sp) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) g[j] += __ldg(gsrc + sp * split_stride + static_cast<size_t>(k0 + kk + j) * HWpj);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dst[static_cast<size_t>(k0 + kk + j) * HW] = g[j] * unscale * inv - fv[j] * coef;
     }
 }
 
@@ -965,7 +973,7 @@ extern "C" int wsegk_pcm_bwd(const float* f, const float* cam_norm, const float*
     prof_mark(2, stream);
     WSEGK_DISPATCH_WB(launch_bwd, precise, pl, N, stream);
     prof_mark(3, stream);
-    pcm_bwd_post_kernel<kMaxPcmK><<<dim3(ceil_div(pl.HW, kPostPix), N), 256, 0, stream>>>(
+    pcm_bwd_post_kernel<<<dim3(ceil_div(pl.HW, kPostPix), N), 256, 0, stream>>>(
         pl.dfhat, f, pl.inv_norm, pl.bound, grad_f, K, pl.HW, pl.HWpj, pl.nsplit);
     count_launches(3);
     WSEGK_CUDA_OK(cudaGetLastError());

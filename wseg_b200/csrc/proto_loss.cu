@@ -217,43 +217,70 @@ struct NceParams {
     float* losses;
 };
 
+// Work split of kernels A and C: a CTA owns kNcePix pixels; each pixel is served by kNceGroups threads.  The
+// (prototype set, class) pairs form 48 "slots" (0..23 own prototypes, 24..47 the other view's); thread group g owns
+// slots 6g..6g+5 in A (dot products over all D) and D/8-strided channels in C (gradient rows).  Every dot product is
+// still accumulated sequentially over d by ONE thread, so values do not depend on the launch geometry.
+constexpr int kNcePix = 16;
+constexpr int kNceGroups = 8;
+constexpr int kNceSlots = 48;
+constexpr int kSlotHalf = 24;
+static_assert(kNcePix * kNceGroups == kNceThreads, "thread mapping");
+
+__device__ __forceinline__ void nce_load_protos(const NceView& V, float* s_proto, int C, int D) {
+    for (int i = threadIdx.x; i < kNceSlots * D; i += blockDim.x) {
+        const int slot = i / D, d = i - slot * D;
+        const int c = slot % kSlotHalf;
+        const float* src = slot < kSlotHalf ? V.proto_own : V.proto_oth;
+        s_proto[slot * (D + 1) + d] = c < C ? __ldg(src + c * D + d) : 0.f;
+    }
+}
+
 // ---- A: per-pixel similarities and unweighted loss terms ----------------------------------------
 __global__ void __launch_bounds__(kNceThreads) nce_pixel_kernel(NceParams prm) {
-    extern __shared__ float s_proto[];               // own [C][D] then oth [C][D]
+    extern __shared__ float s_dyn[];
     const NceView& V = prm.v[blockIdx.y];
     const int C = prm.C, D = prm.D, HW = prm.HW, P = prm.P;
-    for (int i = threadIdx.x; i < C * D; i += blockDim.x) {
-        s_proto[i] = V.proto_own[i];
-        s_proto[C * D + i] = V.proto_oth[i];
-    }
+    float* s_proto = s_dyn;                                   // [48][D+1]
+    float* s_sc = s_dyn + kNceSlots * (D + 1);                // [kNcePix][49]
+    nce_load_protos(V, s_proto, C, D);
     __syncthreads();
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    float cross = 0.f, cross2 = 0.f;
+    const int pix = threadIdx.x & (kNcePix - 1), grp = threadIdx.x / kNcePix;
+    const int p = blockIdx.x * kNcePix + pix;
+    float inv = 0.f;
     if (p < P) {
         const int n = p / HW, q = p - n * HW;
         const float* xp = V.x + static_cast<size_t>(n) * D * HW + q;
-        float own[kNceMaxC], oth[kNceMaxC];
-#pragma unroll
-        for (int c = 0; c < kNceMaxC; ++c) { own[c] = 0.f; oth[c] = 0.f; }
+        const float* pr = s_proto + (grp * 6) * (D + 1);
+        float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         float ss = 0.f;
-        for (int d = 0; d < D; ++d) {
-            const float xv = __ldg(xp + static_cast<size_t>(d) * HW);
-            ss = fmaf(xv, xv, ss);
+        for (int d0 = 0; d0 < D; d0 += 8) {               // batches of 8 independent loads (D % 8 == 0)
+            float xb[8];
 #pragma unroll
-            for (int c = 0; c < kNceMaxC; ++c) {
-                if (c < C) {
-                    own[c] = fmaf(xv, s_proto[c * D + d], own[c]);
-                    oth[c] = fmaf(xv, s_proto[(C + c) * D + d], oth[c]);
-                }
+            for (int e = 0; e < 8; ++e) xb[e] = __ldg(xp + static_cast<size_t>(d0 + e) * HW);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float xv = xb[e];
+                ss = fmaf(xv, xv, ss);
+#pragma unroll
+                for (int j = 0; j < 6; ++j) acc[j] = fmaf(xv, pr[j * (D + 1) + d0 + e], acc[j]);
             }
         }
-        const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);          // F.normalize
+        inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);          // F.normalize
+#pragma unroll
+        for (int j = 0; j < 6; ++j) s_sc[pix * 49 + grp * 6 + j] = acc[j] * inv;
+    }
+    __syncthreads();
+    float cross = 0.f, cross2 = 0.f;
+    if (grp == 0 && p < P) {
+        float own[kNceMaxC], oth[kNceMaxC];
+#pragma unroll
+        for (int c = 0; c < kNceMaxC; ++c) { own[c] = s_sc[pix * 49 + c]; oth[c] = s_sc[pix * 49 + kSlotHalf + c]; }
         const int lo = V.pl_own[p], lt = V.pl_oth[p];
         float z_own = 0.f, z_oth = 0.f, pos_own = 0.f, pos_oth_lo = 0.f, pos_own_lt = 0.f;
 #pragma unroll
         for (int c = 0; c < kNceMaxC; ++c) {
             if (c < C) {
-                own[c] *= inv; oth[c] *= inv;
                 V.s_own[static_cast<size_t>(c) * P + p] = own[c];
                 V.s_oth[static_cast<size_t>(c) * P + p] = oth[c];
                 z_own += expf(own[c] * kInvT);
@@ -284,27 +311,24 @@ __global__ void __launch_bounds__(kNceThreads) nce_pixel_kernel(NceParams prm) {
         V.inv_norm[p] = inv;
         atomicAdd(&V.cls_count[lo], 1);
     }
-    // deterministic block partials
-    __shared__ float s_a[kNceThreads / 32], s_b[kNceThreads / 32];
+    // deterministic block partials: the kNcePix scalar threads are the first lanes of warp 0
+    if (threadIdx.x < 32) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        cross += __shfl_xor_sync(0xffffffffu, cross, o);
-        cross2 += __shfl_xor_sync(0xffffffffu, cross2, o);
-    }
-    if ((threadIdx.x & 31) == 0) { s_a[threadIdx.x >> 5] = cross; s_b[threadIdx.x >> 5] = cross2; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float a = 0.f, b = 0.f;
-        for (int wv = 0; wv < kNceThreads / 32; ++wv) { a += s_a[wv]; b += s_b[wv]; }
-        V.partial[blockIdx.x * 4 + 0] = a;
-        V.partial[blockIdx.x * 4 + 1] = b;
+        for (int o = 16; o > 0; o >>= 1) {
+            cross += __shfl_xor_sync(0xffffffffu, cross, o);
+            cross2 += __shfl_xor_sync(0xffffffffu, cross2, o);
+        }
+        if (threadIdx.x == 0) {
+            V.partial[blockIdx.x * 4 + 0] = cross;
+            V.partial[blockIdx.x * 4 + 1] = cross2;
+        }
     }
 }
 
 // ---- B: ranks inside each pseudo-class (hard-pixel mining, :302-322) -----------------------------
 // rank_sim[p] = #{p' same class : (sim', p') < (sim, p)},  rank_rnd likewise on (key, p).  Integer atomics only.
 constexpr int kMineThreads = 256;
-constexpr int kMineChunk = 1024;
+constexpr int kMineChunk = 256;
 __global__ void __launch_bounds__(kMineThreads) nce_mine_kernel(NceParams prm) {
     const NceView& V = prm.v[blockIdx.z];
     const int P = prm.P;
@@ -339,13 +363,13 @@ __global__ void __launch_bounds__(kMineThreads) nce_mine_kernel(NceParams prm) {
 
 // ---- C: weights, loss partials and gradient w.r.t. the un-normalised features ---------------------
 __global__ void __launch_bounds__(kNceThreads) nce_grad_kernel(NceParams prm) {
-    extern __shared__ float s_proto[];
+    extern __shared__ float s_dyn[];
     const NceView& V = prm.v[blockIdx.y];
     const int C = prm.C, D = prm.D, HW = prm.HW, P = prm.P;
-    for (int i = threadIdx.x; i < C * D; i += blockDim.x) {
-        s_proto[i] = V.proto_own[i];
-        s_proto[C * D + i] = V.proto_oth[i];
-    }
+    float* s_proto = s_dyn;                                   // [48][D+1]
+    float* s_coef = s_dyn + kNceSlots * (D + 1);              // [kNcePix][49]: d loss / d score per slot (times 1/T)
+    __shared__ float s_qdq[kNcePix], s_scale[kNcePix];
+    nce_load_protos(V, s_proto, C, D);
     __shared__ int s_present;
     if (threadIdx.x == 0) {
         int pres = 0;
@@ -353,10 +377,10 @@ __global__ void __launch_bounds__(kNceThreads) nce_grad_kernel(NceParams prm) {
         s_present = pres;
     }
     __syncthreads();
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int pix = threadIdx.x & (kNcePix - 1), grp = threadIdx.x / kNcePix;
+    const int p = blockIdx.x * kNcePix + pix;
     float intra = 0.f;
-    if (p < P) {
-        const int n = p / HW, q = p - n * HW;
+    if (grp == 0 && p < P) {
         const int lo = V.pl_own[p], lt = V.pl_oth[p];
         const int len = V.cls_count[lo];
         const int half = len >> 1;
@@ -377,6 +401,7 @@ __global__ void __launch_bounds__(kNceThreads) nce_grad_kernel(NceParams prm) {
         float z_own = 0.f, z_oth = 0.f, z_set = 0.f;
 #pragma unroll
         for (int c = 0; c < kNceMaxC; ++c) {
+            a[c] = 0.f; b[c] = 0.f;
             if (c < C) {
                 a[c] = expf(V.s_own[static_cast<size_t>(c) * P + p] * kInvT);
                 b[c] = expf(V.s_oth[static_cast<size_t>(c) * P + p] * kInvT);
@@ -389,56 +414,72 @@ __global__ void __launch_bounds__(kNceThreads) nce_grad_kernel(NceParams prm) {
         float qdq = 0.f;
 #pragma unroll
         for (int c = 0; c < kNceMaxC; ++c) {
+            float ac = 0.f, bc = 0.f;
             if (c < C) {
                 const int mult = ((mask >> c) & 1u) + (c == lo ? 1 : 0);
-                const float ac = w_x * (a[c] / z_own - (c == lt ? 1.f : 0.f)) +
-                                 w_i * (static_cast<float>(mult) * a[c] / z_set - (c == lo ? 1.f : 0.f));
-                const float bc = w_x * (b[c] / z_oth - (c == lo ? 1.f : 0.f));
+                ac = w_x * (a[c] / z_own - (c == lt ? 1.f : 0.f)) +
+                     w_i * (static_cast<float>(mult) * a[c] / z_set - (c == lo ? 1.f : 0.f));
+                bc = w_x * (b[c] / z_oth - (c == lo ? 1.f : 0.f));
                 qdq = fmaf(ac, V.s_own[static_cast<size_t>(c) * P + p], qdq);
                 qdq = fmaf(bc, V.s_oth[static_cast<size_t>(c) * P + p], qdq);
-                a[c] = ac * kInvT;
-                b[c] = bc * kInvT;
             }
+            s_coef[pix * 49 + c] = ac * kInvT;
+            s_coef[pix * 49 + kSlotHalf + c] = bc * kInvT;
         }
-        qdq *= kInvT;
-        const float inv = V.inv_norm[p];
+        s_qdq[pix] = qdq * kInvT;
+        s_scale[pix] = V.inv_norm[p];
+    }
+    __syncthreads();
+    if (p < P) {
+        const int n = p / HW, q = p - n * HW;
+        float coef[kNceSlots];
+#pragma unroll
+        for (int i = 0; i < kNceSlots; ++i) coef[i] = s_coef[pix * 49 + i];
+        const float qdq = s_qdq[pix], inv = s_scale[pix];
         const float gs = prm.grad_scale ? prm.grad_scale[0] : 1.f;
         const float* xp = V.x + static_cast<size_t>(n) * D * HW + q;
         float* gp = V.grad_x + static_cast<size_t>(n) * D * HW + q;
-        for (int d = 0; d < D; ++d) {
-            float dq = 0.f;
+        // channel d = grp + 8*i: the 16 pixels of a CTA are contiguous in memory for a fixed d.  The order of the 42
+        // terms matches the previous kernel: own c=0, other c=0, own c=1, ...
+        for (int d0 = grp; d0 < D; d0 += 4 * kNceGroups) {          // D % 32 == 0: 4 channels per batch
+            float xb[4];
 #pragma unroll
-            for (int c = 0; c < kNceMaxC; ++c) {
-                if (c < C) {
-                    dq = fmaf(a[c], s_proto[c * D + d], dq);
-                    dq = fmaf(b[c], s_proto[(C + c) * D + d], dq);
+            for (int e = 0; e < 4; ++e) xb[e] = __ldg(xp + static_cast<size_t>(d0 + e * kNceGroups) * HW);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int d = d0 + e * kNceGroups;
+                float dq = 0.f;
+#pragma unroll
+                for (int c = 0; c < kNceMaxC; ++c) {
+                    dq = fmaf(coef[c], s_proto[c * (D + 1) + d], dq);
+                    dq = fmaf(coef[kSlotHalf + c], s_proto[(kSlotHalf + c) * (D + 1) + d], dq);
                 }
+                const float qd = xb[e] * inv;
+                gp[static_cast<size_t>(d) * HW] = (dq - qd * qdq) * inv * gs;
             }
-            const float qd = __ldg(xp + static_cast<size_t>(d) * HW) * inv;
-            gp[static_cast<size_t>(d) * HW] = (dq - qd * qdq) * inv * gs;
         }
     }
-    __shared__ float s_a[kNceThreads / 32];
+    if (threadIdx.x < 32) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) intra += __shfl_xor_sync(0xffffffffu, intra, o);
-    if ((threadIdx.x & 31) == 0) s_a[threadIdx.x >> 5] = intra;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float t = 0.f;
-        for (int wv = 0; wv < kNceThreads / 32; ++wv) t += s_a[wv];
-        V.partial[blockIdx.x * 4 + 2] = t;
+        for (int o = 16; o > 0; o >>= 1) intra += __shfl_xor_sync(0xffffffffu, intra, o);
+        if (threadIdx.x == 0) V.partial[blockIdx.x * 4 + 2] = intra;
     }
 }
 
-// ---- D: fixed-order final sums ---------------------------------------------------------------------
+// ---- D: fixed-order final sums (one warp; lane l adds blocks l, l+32, ... then a shuffle tree) -------------
 __global__ void nce_finalize_kernel(NceParams prm) {
-    if (threadIdx.x != 0) return;
+    const int lane = threadIdx.x;
     float s[2][3];
     for (int v = 0; v < 2; ++v) {
-        s[v][0] = s[v][1] = s[v][2] = 0.f;
-        for (int b = 0; b < prm.nblk; ++b)
-            for (int j = 0; j < 3; ++j) s[v][j] += prm.v[v].partial[b * 4 + j];
+        for (int j = 0; j < 3; ++j) {
+            float acc = 0.f;
+            for (int b = lane; b < prm.nblk; b += 32) acc += prm.v[v].partial[b * 4 + j];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            s[v][j] = acc;
+        }
     }
+    if (lane != 0) return;
     const float invP = 1.f / static_cast<float>(prm.P);
     float* L = prm.losses;
     L[0] = s[0][0] * invP;            // nce(q1, proto2, pl1)
@@ -461,7 +502,7 @@ struct NceLayout {
 static NceLayout nce_layout(int N, int C, int h, int w) {
     NceLayout L{};
     const size_t P = static_cast<size_t>(N) * h * w;
-    L.nblk = static_cast<int>((P + kNceThreads - 1) / kNceThreads);
+    L.nblk = static_cast<int>((P + kNcePix - 1) / kNcePix);
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
     L.off_rs = take(P * 4);            // rank arrays + class counts first: one memset clears them
@@ -538,13 +579,14 @@ extern "C" int wsegk_contrast_loss_fwd_bwd(const float* x1, const float* x2, con
     WSEGK_REQUIRE(x1 && x2 && proto1 && proto2 && pl1 && pl2 && rand_key1 && rand_key2 && losses && grad_x1 &&
                       grad_x2 && workspace,
                   WSEGK_ERR_NULL, "contrast_loss_fwd_bwd: null pointer");
+    WSEGK_REQUIRE((D % 32) == 0, WSEGK_ERR_BAD_SHAPE, "contrast_loss_fwd_bwd: D must be a multiple of 32 (got %d)", D);
     WSEGK_REQUIRE(N > 0 && h > 0 && w > 0 && D > 0 && C >= 13 && C <= kNceMaxC, WSEGK_ERR_BAD_SHAPE,
                   "contrast_loss_fwd_bwd: need 13 <= C <= %d (semi-hard mining takes ranks 3..12), got C=%d",
                   kNceMaxC, C);
     const long long P = static_cast<long long>(N) * h * w;
     WSEGK_REQUIRE(P <= (1 << 17), WSEGK_ERR_BAD_SHAPE,
                   "contrast_loss_fwd_bwd: P=%lld pixels exceeds the pairwise mining limit of 131072", P);
-    const size_t proto_smem = static_cast<size_t>(2) * C * D * sizeof(float);
+    const size_t proto_smem = (static_cast<size_t>(kNceSlots) * (D + 1) + kNcePix * 49) * sizeof(float);
     WSEGK_REQUIRE(proto_smem <= 200 * 1024, WSEGK_ERR_BAD_SHAPE, "contrast_loss_fwd_bwd: D too large");
     const NceLayout L = nce_layout(N, C, h, w);
     WSEGK_REQUIRE(workspace_bytes >= L.total, WSEGK_ERR_WORKSPACE_TOO_SMALL,

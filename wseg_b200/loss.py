@@ -27,7 +27,7 @@ def reference_rng_keys(pl1: torch.Tensor, pl2: torch.Tensor, rng: Union[int, _py
     ascending class order; view 1 before view 2.  Chosen pixels get key 0, the others key 1, so the kernel's rule
     "the len//2 smallest (key, index)" selects exactly the reference's random half.  Needs the pseudo labels on
     the host (one sync) — the default device-hash keys (``ops.hash_keys``) do not."""
-    if not isinstance(rng, _pyrandom.Random):
+    if not hasattr(rng, "sample"):                 # an int seed; a random.Random or the `random` module is used as is
         rng = _pyrandom.Random(rng)
     keys = []
     for pl in (pl1, pl2):
