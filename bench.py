@@ -87,31 +87,69 @@ class HotPath:
         self.pixels = n * (VIEW1[0] // 8) * (VIEW1[1] // 8)
 
     def step(self):
+        """One pass.  Independent chains run on forked streams (captured as parallel branches of the CUDA graph) with
+        the dependencies a training step has: view-1 chain K1a -> K2 fwd -> K1b(cam_rv) fwd/bwd -> K2 bwd, the same for
+        view 2, the seed/prototype/NCE chain after both K2 forwards, and K1b on the two `cam` maps (which do not depend
+        on the PCM).  Every intermediate is returned so nothing is recycled before the join."""
         ops, d = self.ops, self.d
-        # K1a + K2 forward, both views
+        cur = torch.cuda.current_stream(self.dev)
+        if not hasattr(self, "_streams"):
+            self._streams = [torch.cuda.Stream(device=self.dev) for _ in range(3)]
+        s2, s3, s4 = self._streams
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        for s in (s2, s3, s4):
+            s.wait_event(fork)
+        keep = []
+
+        def k1b(name, size, gname):
+            y, mm, lab = ops.fullres_norm_fwd(d[name], d["label"], size)
+            g = ops.fullres_norm_bwd(d[name], lab, mm, d[gname], y.shape[-2:])
+            keep.extend([y, mm, lab, g])
+            return g
+
+        # ---- view 1: K1a + K2 forward
         camn1 = ops.cam_norm(d["cam1"])
         rv1, ws1 = ops.pcm_forward(camn1, d["f1"])
-        camn2 = ops.cam_norm(d["cam2"])
-        rv2, ws2 = ops.pcm_forward(camn2, d["f2"])
-        # glue kept in PyTorch as in the reference (contrast_train.py:179-180): shrink view 1 to the loss grid
-        f1 = F.interpolate(d["fproj1"], size=self.grid, mode="bilinear", align_corners=True)
-        c1 = F.interpolate(rv1, size=self.grid, mode="bilinear", align_corners=True)
-        # K1c seeds, K3 prototypes (whole batch across ranks), K4 losses fwd+bwd
-        norm1, pl1 = ops.seed_labels(c1, d["label"], BG_THRESHOLD)
-        norm2, pl2 = ops.seed_labels(rv2, d["label"], BG_THRESHOLD)
-        proto1, _ = ops.prototypes(norm1, f1, group=self.group)
-        proto2, _ = ops.prototypes(norm2, d["fproj2"], group=self.group)
-        losses, g1, g2, _, _ = ops.contrast_loss_raw(f1, d["fproj2"], proto1, proto2, pl1, pl2, self.key1, self.key2)
-        # K1b forward + backward on the four full-resolution maps
-        outs = []
-        for name, size, gname in (("cam1_full", VIEW2, "g_n1"), ("rv1_full", VIEW2, "g_rv1"),
-                                  ("cam2_full", None, "g_n2"), ("rv2_full", None, "g_rv2")):
-            y, mm, lab = ops.fullres_norm_fwd(d[name], d["label"], size)
-            outs.append(ops.fullres_norm_bwd(d[name], lab, mm, d[gname], y.shape[-2:]))
-        # K2 backward
+        f1_done = torch.cuda.Event()
+        f1_done.record(cur)
+        # ---- view 2 chain
+        with torch.cuda.stream(s2):
+            camn2 = ops.cam_norm(d["cam2"])
+            rv2, ws2 = ops.pcm_forward(camn2, d["f2"])
+            f2_done = torch.cuda.Event()
+            f2_done.record(s2)
+            g_rv2 = k1b("rv2_full", None, "g_rv2")
+            gf2 = ops.pcm_backward(d["f2"], camn2, rv2, d["g_rv_down2"], ws2)
+            s2_done = torch.cuda.Event()
+            s2_done.record(s2)
+        # ---- loss chain: glue kept in PyTorch as in the reference (contrast_train.py:179-180), K1c, K3 (whole batch
+        # across ranks), K4 forward+backward
+        with torch.cuda.stream(s3):
+            s3.wait_event(f1_done)
+            s3.wait_event(f2_done)
+            f1 = F.interpolate(d["fproj1"], size=self.grid, mode="bilinear", align_corners=True)
+            c1 = F.interpolate(rv1, size=self.grid, mode="bilinear", align_corners=True)
+            norm1, pl1 = ops.seed_labels(c1, d["label"], BG_THRESHOLD)
+            norm2, pl2 = ops.seed_labels(rv2, d["label"], BG_THRESHOLD)
+            proto1, ti1 = ops.prototypes(norm1, f1, group=self.group)
+            proto2, ti2 = ops.prototypes(norm2, d["fproj2"], group=self.group)
+            losses, g1, g2, _, _ = ops.contrast_loss_raw(f1, d["fproj2"], proto1, proto2, pl1, pl2, self.key1, self.key2)
+            keep.extend([f1, c1, norm1, pl1, norm2, pl2, proto1, ti1, proto2, ti2])
+            s3_done = torch.cuda.Event()
+            s3_done.record(s3)
+        # ---- K1b on the plain CAMs (independent of the PCM)
+        with torch.cuda.stream(s4):
+            g_n1 = k1b("cam1_full", VIEW2, "g_n1")
+            g_n2 = k1b("cam2_full", None, "g_n2")
+            s4_done = torch.cuda.Event()
+            s4_done.record(s4)
+        # ---- view 1: K1b on cam_rv, then K2 backward
+        g_rv1 = k1b("rv1_full", VIEW2, "g_rv1")
         gf1 = ops.pcm_backward(d["f1"], camn1, rv1, d["g_rv_down1"], ws1)
-        gf2 = ops.pcm_backward(d["f2"], camn2, rv2, d["g_rv_down2"], ws2)
-        return losses, gf1, gf2, g1, g2, outs
+        for e in (s2_done, s3_done, s4_done):
+            cur.wait_event(e)
+        return losses, gf1, gf2, g1, g2, (g_n1, g_rv1, g_n2, g_rv2), keep, (camn1, camn2, rv1, rv2, ws1, ws2)
 
 
 class GraphedStep:

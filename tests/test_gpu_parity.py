@@ -250,9 +250,14 @@ def test_contrast_terms_vs_oracle(cuda_dev, n, hw1, hw2, d):
             q = F.normalize(xr.detach().permute(0, 2, 3, 1).reshape(-1, d), dim=-1)
             pl = rr["pseudo_label" + v]
             sc = q @ rr["prototypes" + v].t()
-            srt = torch.sort(sc, dim=-1, descending=True)[0]
-            gap = torch.minimum(srt[:, 2] - srt[:, 3], srt[:, 12] - srt[:, 13])
-            keep = (gap > 1e-6) | (gap == 0)          # exact ties (identical prototypes) resolve by class index in both
+            proto = rr["prototypes" + v]
+            srt, idx = torch.sort(sc, dim=-1, descending=True, stable=True)
+            keep = torch.ones(sc.shape[0], dtype=torch.bool, device=sc.device)
+            for lo_r, hi_r in ((2, 3), (12, 13)):
+                # a small gap is harmless only between bit-identical prototypes (both sides then tie and fall back to
+                # the class index)
+                same = (proto[idx[:, lo_r]] == proto[idx[:, hi_r]]).all(dim=-1)
+                keep &= ((srt[:, lo_r] - srt[:, hi_r]) > 1e-6) | same
             cnt = torch.zeros_like(gm["mined" + v])
             for _, rnd, hard in rr["sets" + v][1]:
                 cnt.index_add_(0, rnd, torch.ones_like(rnd, dtype=torch.int32))

@@ -39,3 +39,24 @@ for v, xr, gm in (("1", x1, m["grad_f1"]), ("2", x2, m["grad_f2"])):
         print(f"     gaps 2|3 {float(srt[2]-srt[3]):.2e} 12|13 {float(srt[12]-srt[13]):.2e}  ref mined count {cnt_ref}  ratio mine/ref {(gm.permute(0,2,3,1).reshape(P,d)[p].norm()/r[p]).item():.4f}")
         print(f"  px {p}: |err| {e[p].item():.3e} |ref| {r[p].item():.3e} pl {pl[p].item()} pl_other {plo[p].item()} mined {m['mined' + v][p].item()} "
               f"rank of pos {order.index(pl[p].item())} cls count {(pl == pl[p]).sum().item()}  xnorm {(f1 if v == '1' else f2).permute(0,2,3,1).reshape(P,d)[p].norm().item():.3e}")
+
+print("---- mined-set analysis")
+for v in "12":
+    P_ = m["mined" + v].numel()
+    rnd_c = torch.zeros(P_, dtype=torch.int32, device=dev); hard_c = torch.zeros(P_, dtype=torch.int32, device=dev)
+    for _, rnd, hard in ref["sets" + v][1]:
+        rnd_c.index_add_(0, rnd, torch.ones_like(rnd, dtype=torch.int32))
+        hard_c.index_add_(0, hard, torch.ones_like(hard, dtype=torch.int32))
+    mine_c = m["mined" + v]
+    mism = (rnd_c + hard_c) != mine_c
+    pl = ref["pseudo_label" + v]
+    print(f"view {v}: mismatches {int(mism.sum())}; by class: {[(c, int((mism & (pl == c)).sum()), int((pl == c).sum())) for c in pl[mism].unique().tolist()]}")
+    q = F.normalize((x1 if v == "1" else x2).detach().permute(0, 2, 3, 1).reshape(P_, d), dim=-1)
+    sim = ((q * ref["prototypes" + v][pl]).sum(-1) + 1) / 2
+    for c in pl[mism].unique().tolist()[:3]:
+        mem = (pl == c).nonzero().reshape(-1)
+        s_sorted, order = torch.sort(sim[mem], stable=True)
+        ln = mem.numel(); kk = int(ln * 0.6); half = ln // 2
+        bad = mism[mem][order].nonzero().reshape(-1).tolist()
+        print(f"   class {c}: len {ln} kk {kk} half {half} window [{kk - half},{kk}); mismatching sorted positions {bad[:12]}; "
+              f"exact-duplicate sims in class: {ln - torch.unique(sim[mem]).numel()}; sum mine {int(mine_c[mem].sum())} sum ref {int((rnd_c + hard_c)[mem].sum())}")
