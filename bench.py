@@ -481,10 +481,29 @@ def run_ours(args):
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Tearing NCCL down while CUDA graphs that captured its kernels are alive hung at exit (r01, 2 GPUs): drop the
+        # graph, drain, agree that everyone is done, and leave without the communicator destructor.
+        del stepper
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+
+
+def _watchdog(seconds: float):
+    """Hard deadline: a wedged collective must not hold the GPU box."""
+    def fire():
+        sys.stderr.write(f"bench.py: watchdog fired after {seconds:.0f} s\n")
+        sys.stderr.flush()
+        os._exit(3)
+    t = threading.Timer(seconds, fire)
+    t.daemon = True
+    t.start()
 
 
 def main():
+    _watchdog(float(os.environ.get("WSEG_BENCH_DEADLINE_S", "900")))
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
