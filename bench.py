@@ -128,8 +128,8 @@ class HotPath:
         with torch.cuda.stream(s3):
             s3.wait_event(f1_done)
             s3.wait_event(f2_done)
-            f1 = F.interpolate(d["fproj1"], size=self.grid, mode="bilinear", align_corners=True)
-            c1 = F.interpolate(rv1, size=self.grid, mode="bilinear", align_corners=True)
+            f1 = ops.resize_fwd(d["fproj1"], self.grid)
+            c1 = ops.resize_fwd(rv1, self.grid)
             norm1, pl1 = ops.seed_labels(c1, d["label"], BG_THRESHOLD)
             norm2, pl2 = ops.seed_labels(rv2, d["label"], BG_THRESHOLD)
             proto1, ti1 = ops.prototypes(norm1, f1, group=self.group)

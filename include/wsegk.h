@@ -94,6 +94,13 @@ int wsegk_seed_labels_fwd(const float* cam_rv_down, const float* label, float bg
                           int32_t* pseudo, int N, int C, int h, int w, void* workspace,
                           size_t workspace_bytes, wsegk_stream_t stream);
 
+/* Glue — replaces the two F.interpolate(..., mode='bilinear', align_corners=True) shrinks of view 1 to the loss grid,
+ * contrast_train.py:179-180 (f_proj1 and cam_rv1_down).  x [planes,H,W] -> y [planes,oh,ow], oh <= H, ow <= W; and its
+ * autograd: grad_y -> grad_x (deterministic gather, no atomics). */
+int wsegk_bilinear_resize_fwd(const float* x, float* y, int planes, int H, int W, int oh, int ow, wsegk_stream_t stream);
+int wsegk_bilinear_resize_bwd(const float* grad_y, float* grad_x, int planes, int H, int W, int oh, int ow,
+                              wsegk_stream_t stream);
+
 /* K3 — replaces contrast_train.py:199-209 / 229-241.  Per class, the k largest norm_cam values over the whole
  * batch (value desc, then lowest flat index n*h*w + y*w + x), and the value-weighted feature sums.
  *   proto_topk_local : norm_cam [N,C,h,w], f_proj [N,D,h,w] -> top_val [C,k], top_idx [C,k] (int32, local

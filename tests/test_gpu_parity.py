@@ -363,3 +363,20 @@ def test_abi_error_codes(cuda_dev):
     assert lib.wsegk_pcm_fwd(p, p, p, 1, 21, 192, 4, 4, p, 16, None) == -3         # WORKSPACE_TOO_SMALL
     assert "workspace" in _lib.last_error()
     assert lib.wsegk_pcm_fwd(p, p, p, 1, 40, 192, 4, 4, p, 1 << 20, None) == -1    # too many classes
+
+
+@pytest.mark.parametrize("shape,size", [((8, 128, 56, 56), (16, 16)), ((2, 21, 64, 64), (32, 32)), ((3, 5, 23, 40), (20, 12)),
+                                        ((1, 4, 9, 9), (9, 9)), ((2, 3, 7, 5), (1, 1))])
+def test_bilinear_resize_matches_aten(cuda_dev, shape, size):
+    """contrast_train.py:179-180: F.interpolate(..., mode='bilinear', align_corners=True), forward and backward."""
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(*shape, generator=g).to(cuda_dev)
+    gy = torch.randn(shape[0], shape[1], *size, generator=g).to(cuda_dev)
+    a = x.clone().requires_grad_(True)
+    ya = ops.bilinear_resize(a, size)
+    ya.backward(gy)
+    b = x.clone().requires_grad_(True)
+    yb = F.interpolate(b, size=size, mode="bilinear", align_corners=True)
+    yb.backward(gy)
+    assert float((ya - yb).abs().max()) <= 1e-6
+    assert float((a.grad - b.grad).abs().max()) <= 1e-5

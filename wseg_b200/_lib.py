@@ -29,6 +29,8 @@ _SIGNATURES = {
     "wsegk_fullres_norm_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
     "wsegk_fullres_norm_bwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P,
                                        c_size_t, _P]),
+    "wsegk_bilinear_resize_fwd": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
+    "wsegk_bilinear_resize_bwd": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "wsegk_seed_labels_fwd": (c_int, [_P, _P, c_float, _P, _P, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
     "wsegk_proto_topk_local": (c_int, [_P, _P, c_int, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P,
                                        c_size_t, _P]),

@@ -278,6 +278,59 @@ __global__ void __launch_bounds__(256) fullres_bwd_kernel(const float* __restric
     }
 }
 
+// ---- glue: bilinear(align_corners) shrink of small maps (contrast_train.py:179-180) -----------------------------------
+// ATen's NCHW bilinear kernel parallelises over the OUTPUT PIXELS only and loops over N*C inside a thread: for
+// [8,128,56,56] -> 16x16 that is 256 threads and 0.3 ms.  One thread per output element here.
+__global__ void __launch_bounds__(256) resize_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int planes,
+                                                         int H, int W, int oh, int ow) {
+    const long long total = static_cast<long long>(planes) * oh * ow;
+    const float sy = oh > 1 ? static_cast<float>(H - 1) / static_cast<float>(oh - 1) : 0.f;
+    const float sx = ow > 1 ? static_cast<float>(W - 1) / static_cast<float>(ow - 1) : 0.f;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int ox = static_cast<int>(i % ow);
+        const int oy = static_cast<int>((i / ow) % oh);
+        const long long plane = i / (static_cast<long long>(ow) * oh);
+        int y0, y1, x0, x1; float hy0, hy1, wx0, wx1;
+        src_coord(oy, sy, H, y0, y1, hy0, hy1);
+        src_coord(ox, sx, W, x0, x1, wx0, wx1);
+        const float* src = x + plane * H * W;
+        y[i] = hy0 * (wx0 * __ldg(src + y0 * W + x0) + wx1 * __ldg(src + y0 * W + x1)) +
+               hy1 * (wx0 * __ldg(src + y1 * W + x0) + wx1 * __ldg(src + y1 * W + x1));
+    }
+}
+
+// gx[plane,y,x] = sum of the (at most four) output gradients whose taps include (y,x); one CTA per plane group
+__global__ void __launch_bounds__(256) resize_bwd_kernel(const float* __restrict__ gy, float* __restrict__ gx, int planes,
+                                                         int H, int W, int oh, int ow) {
+    extern __shared__ TapSlot s_tab[];
+    TapSlot* ty = s_tab;
+    TapSlot* tx = s_tab + 2 * H;
+    const float sy = oh > 1 ? static_cast<float>(H - 1) / static_cast<float>(oh - 1) : 0.f;
+    const float sx = ow > 1 ? static_cast<float>(W - 1) / static_cast<float>(ow - 1) : 0.f;
+    build_tap_table(ty, H, oh, sy);
+    build_tap_table(tx, W, ow, sx);
+    const long long total = static_cast<long long>(planes) * H * W;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int xq = static_cast<int>(i % W);
+        const int yq = static_cast<int>((i / W) % H);
+        const long long plane = i / (static_cast<long long>(W) * H);
+        const float* g = gy + plane * oh * ow;
+        const TapSlot ya = ty[2 * yq], yb = ty[2 * yq + 1], xa = tx[2 * xq], xb = tx[2 * xq + 1];
+        float acc = 0.f;
+        if (ya.w != 0.f) {
+            if (xa.w != 0.f) acc = fmaf(ya.w * xa.w, __ldg(g + ya.o * ow + xa.o), acc);
+            if (xb.w != 0.f) acc = fmaf(ya.w * xb.w, __ldg(g + ya.o * ow + xb.o), acc);
+        }
+        if (yb.w != 0.f) {
+            if (xa.w != 0.f) acc = fmaf(yb.w * xa.w, __ldg(g + yb.o * ow + xa.o), acc);
+            if (xb.w != 0.f) acc = fmaf(yb.w * xb.w, __ldg(g + yb.o * ow + xb.o), acc);
+        }
+        gx[i] = acc;
+    }
+}
+
 // ---- K1c ---------------------------------------------------------------------------------------
 // one warp per (n,c) plane: min/max of relu(x)
 __global__ void __launch_bounds__(256) seed_minmax_kernel(const float* __restrict__ x, float* __restrict__ lohi,
@@ -421,6 +474,43 @@ extern "C" int wsegk_seed_labels_fwd(const float* cam_rv_down, const float* labe
     seed_pixel_kernel<<<dim3(ceil_div(HW, 128), N), 128, 0, stream>>>(cam_rv_down, label, lohi, bg_threshold,
                                                                       norm_cam, pseudo, C, HW);
     count_launches(2);
+    WSEGK_CUDA_OK(cudaGetLastError());
+    return WSEGK_OK;
+}
+
+static int resize_check(const char* who, int planes, int H, int W, int oh, int ow) {
+    WSEGK_REQUIRE(planes > 0 && H > 0 && W > 0 && oh > 0 && ow > 0, WSEGK_ERR_BAD_SHAPE, "%s: dims must be positive", who);
+    WSEGK_REQUIRE(oh <= H && ow <= W, WSEGK_ERR_BAD_SHAPE, "%s: only shrinking is supported ((%d,%d) -> (%d,%d))", who, H,
+                  W, oh, ow);
+    WSEGK_REQUIRE(static_cast<size_t>(2) * (H + W) * sizeof(TapSlot) <= 200 * 1024, WSEGK_ERR_BAD_SHAPE,
+                  "%s: H + W = %d too large", who, H + W);
+    return WSEGK_OK;
+}
+
+extern "C" int wsegk_bilinear_resize_fwd(const float* x, float* y, int planes, int H, int W, int oh, int ow,
+                                         wsegk_stream_t stream) {
+    if (int rc = check_device()) return rc;
+    WSEGK_REQUIRE(x && y, WSEGK_ERR_NULL, "bilinear_resize_fwd: null pointer");
+    if (int rc = resize_check("bilinear_resize_fwd", planes, H, W, oh, ow)) return rc;
+    const long long total = static_cast<long long>(planes) * oh * ow;
+    const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 16));
+    resize_fwd_kernel<<<blocks, 256, 0, stream>>>(x, y, planes, H, W, oh, ow);
+    count_launches(1);
+    WSEGK_CUDA_OK(cudaGetLastError());
+    return WSEGK_OK;
+}
+
+extern "C" int wsegk_bilinear_resize_bwd(const float* grad_y, float* grad_x, int planes, int H, int W, int oh, int ow,
+                                         wsegk_stream_t stream) {
+    if (int rc = check_device()) return rc;
+    WSEGK_REQUIRE(grad_y && grad_x, WSEGK_ERR_NULL, "bilinear_resize_bwd: null pointer");
+    if (int rc = resize_check("bilinear_resize_bwd", planes, H, W, oh, ow)) return rc;
+    const long long total = static_cast<long long>(planes) * H * W;
+    const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 16));
+    const size_t tab = static_cast<size_t>(2) * (H + W) * sizeof(TapSlot);
+    WSEGK_CUDA_OK(cudaFuncSetAttribute(resize_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(tab)));
+    resize_bwd_kernel<<<blocks, 256, tab, stream>>>(grad_y, grad_x, planes, H, W, oh, ow);
+    count_launches(1);
     WSEGK_CUDA_OK(cudaGetLastError());
     return WSEGK_OK;
 }

@@ -207,6 +207,42 @@ def fullres_norm(p: torch.Tensor, label: torch.Tensor, size: Optional[Tuple[int,
     return _FullresNorm.apply(p, label, size)
 
 
+# --------------------------------------------------------------------------------------------- glue (:179-180)
+def resize_fwd(x: torch.Tensor, size: Tuple[int, int]) -> torch.Tensor:
+    x = _require_cuda_f32("x", x.detach())
+    n, c, H, W = x.shape
+    oh, ow = int(size[0]), int(size[1])
+    y = torch.empty(n, c, oh, ow, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_lib.lib().wsegk_bilinear_resize_fwd(_ptr(x), _ptr(y), n * c, H, W, oh, ow, _stream(x)),
+              "wsegk_bilinear_resize_fwd")
+    return y
+
+
+class _Resize(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, size):
+        ctx.in_shape = tuple(x.shape)
+        return resize_fwd(x, size)
+
+    @staticmethod
+    def backward(ctx, grad_y):
+        n, c, H, W = ctx.in_shape
+        grad_y = _require_cuda_f32("grad_y", grad_y)
+        oh, ow = grad_y.shape[-2:]
+        gx = torch.empty(n, c, H, W, dtype=torch.float32, device=grad_y.device)
+        with torch.cuda.device(grad_y.device):
+            check(_lib.lib().wsegk_bilinear_resize_bwd(_ptr(grad_y), _ptr(gx), n * c, H, W, oh, ow, _stream(grad_y)),
+                  "wsegk_bilinear_resize_bwd")
+        return gx, None
+
+
+def bilinear_resize(x: torch.Tensor, size: Tuple[int, int]) -> torch.Tensor:
+    """F.interpolate(x, size, mode='bilinear', align_corners=True) for shrinking (contrast_train.py:179-180),
+    differentiable.  ATen's kernel loops over N*C inside each thread (0.3 ms for [8,128,56,56] -> 16x16)."""
+    return _Resize.apply(x, size)
+
+
 # --------------------------------------------------------------------------------------------- K1c
 def seed_labels(cam_rv_down: torch.Tensor, label: torch.Tensor, bg_threshold: float
                 ) -> Tuple[torch.Tensor, torch.Tensor]:
