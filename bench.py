@@ -103,9 +103,9 @@ class HotPath:
         keep = []
 
         def k1b(name, size, gname):
-            y, mm, lab = ops.fullres_norm_fwd(d[name], d["label"], size)
-            g = ops.fullres_norm_bwd(d[name], lab, mm, d[gname], y.shape[-2:])
-            keep.extend([y, mm, lab, g])
+            y, saved = ops.fullres_norm_fwd(d[name], d["label"], size)
+            g = ops.fullres_norm_bwd(d[name], y, saved, d[gname])
+            keep.extend([y, saved, g])
             return g
 
         # ---- view 1: K1a + K2 forward

@@ -76,16 +76,19 @@ int wsegk_pcm_bwd(const float* f, const float* cam_norm, const float* cam_rv, co
 /* K1b forward — replaces tool/visualization.py:62-67 + contrast_train.py:145-152 / 157-158:
  *   y = relu(relu(p)-min-1e-5)/(max-min+1e-5) per (n,c) plane; bilinear(align_corners) to (oh,ow); * label.
  * p [N,C,H,W], label [N,C] -> out [N,C,oh,ow]; minmax [N,C,4] receives {min, max, argmin, argmax} (the two
- * indices stored as int32 bit patterns) for the backward. */
-int wsegk_fullres_norm_fwd(const float* p, const float* label, float* out, float* minmax, int N, int C,
-                           int H, int W, int oh, int ow, void* workspace, size_t workspace_bytes,
+ * indices stored as int32 bit patterns) for the backward; tapsum [N,C,oh,ow] (may be NULL when no backward follows)
+ * receives, per output, the sum of the bilinear weights of its taps whose normalised input is positive. */
+int wsegk_fullres_norm_fwd(const float* p, const float* label, float* out, float* minmax, float* tapsum, int N,
+                           int C, int H, int W, int oh, int ow, void* workspace, size_t workspace_bytes,
                            wsegk_stream_t stream);
 
 /* K1b backward — grad_out [N,C,oh,ow] -> grad_p [N,C,H,W], including the gradient routed to each plane's
- * arg-min / arg-max pixel (torch.max/min(dim) backward; first flat index on ties). */
-int wsegk_fullres_norm_bwd(const float* p, const float* label, const float* minmax, const float* grad_out,
-                           float* grad_p, int N, int C, int H, int W, int oh, int ow, void* workspace,
-                           size_t workspace_bytes, wsegk_stream_t stream);
+ * arg-min / arg-max pixel (torch.max/min(dim) backward; first flat index on ties).  `out` and `tapsum` are the
+ * forward's outputs: with them the two plane sums of that gradient come from the output-sized tensors, so the
+ * full-resolution input is read once. */
+int wsegk_fullres_norm_bwd(const float* p, const float* label, const float* minmax, const float* out,
+                           const float* tapsum, const float* grad_out, float* grad_p, int N, int C, int H, int W, int oh,
+                           int ow, void* workspace, size_t workspace_bytes, wsegk_stream_t stream);
 
 /* K1c — replaces contrast_train.py:186-197 / 215-226: relu, per-plane min/max normalisation (no outer relu),
  * channel 0 := bg_threshold, pseudo label = argmax_c(norm_cam*label) (lowest class on ties).

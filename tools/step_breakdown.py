@@ -34,8 +34,8 @@ def one():
     timed("K4", lambda: ops.contrast_loss_raw(f1, d["fproj2"], proto1, proto2, pl1, pl2, hp.key1, hp.key2))
     for name, size, gname in (("cam1_full", bench.VIEW2, "g_n1"), ("rv1_full", bench.VIEW2, "g_rv1"),
                               ("cam2_full", None, "g_n2"), ("rv2_full", None, "g_rv2")):
-        y, mm, lab = timed("K1b fwd " + name, lambda: ops.fullres_norm_fwd(d[name], d["label"], size))
-        timed("K1b bwd " + name, lambda: ops.fullres_norm_bwd(d[name], lab, mm, d[gname], y.shape[-2:]))
+        y, saved = timed("K1b fwd " + name, lambda: ops.fullres_norm_fwd(d[name], d["label"], size))
+        timed("K1b bwd " + name, lambda: ops.fullres_norm_bwd(d[name], y, saved, d[gname]))
     timed("K2 bwd v1 (3 kernels)", lambda: ops.pcm_backward(d["f1"], camn1, rv1, d["g_rv_down1"], ws1))
     timed("K2 bwd v2", lambda: ops.pcm_backward(d["f2"], camn2, rv2, d["g_rv_down2"], ws2))
 

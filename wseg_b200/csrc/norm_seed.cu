@@ -116,14 +116,18 @@ __global__ void __launch_bounds__(256) fullres_resample_kernel(const float* __re
                                                                const float* __restrict__ label,
                                                                const MinMax* __restrict__ partial,
                                                                float* __restrict__ out,
-                                                               float* __restrict__ minmax, int H, int W,
+                                                               float* __restrict__ minmax,
+                                                               float* __restrict__ tapsum, int H, int W,
                                                                int oh, int ow, int nsplit) {
     const int plane = blockIdx.y;
     const int o = blockIdx.x * blockDim.x + threadIdx.x;
     const float lab = label[plane];
     float* dst = out + static_cast<size_t>(plane) * oh * ow;
     if (lab == 0.f) {
-        if (o < oh * ow) dst[o] = 0.f;
+        if (o < oh * ow) {
+            dst[o] = 0.f;
+            if (tapsum) tapsum[static_cast<size_t>(plane) * oh * ow + o] = 0.f;
+        }
         if (blockIdx.x == 0 && threadIdx.x == 0) {
             minmax[plane * 4 + 0] = 0.f; minmax[plane * 4 + 1] = 0.f;
             minmax[plane * 4 + 2] = __int_as_float(0); minmax[plane * 4 + 3] = __int_as_float(0);
@@ -138,9 +142,10 @@ __global__ void __launch_bounds__(256) fullres_resample_kernel(const float* __re
     if (o >= oh * ow) return;
     const float den = mm.hi - mm.lo + 1e-5f;
     const float* src = p + static_cast<size_t>(plane) * H * W;
-    float val;
+    float val, taps = 0.f;
     if (oh == H && ow == W) {
         val = fmaxf(fmaxf(__ldg(src + o), 0.f) - mm.lo - 1e-5f, 0.f) / den;
+        taps = val > 0.f ? 1.f : 0.f;
     } else {
         const int oy = o / ow, ox = o - oy * ow;
         const float sy = oh > 1 ? static_cast<float>(H - 1) / static_cast<float>(oh - 1) : 0.f;
@@ -151,9 +156,15 @@ __global__ void __launch_bounds__(256) fullres_resample_kernel(const float* __re
         auto at = [&](int y, int x) {
             return fmaxf(fmaxf(__ldg(src + static_cast<size_t>(y) * W + x), 0.f) - mm.lo - 1e-5f, 0.f) / den;
         };
-        val = hy0 * (wx0 * at(y0, x0) + wx1 * at(y0, x1)) + hy1 * (wx0 * at(y1, x0) + wx1 * at(y1, x1));
+        const float v00 = at(y0, x0), v01 = at(y0, x1), v10 = at(y1, x0), v11 = at(y1, x1);
+        val = hy0 * (wx0 * v00 + wx1 * v01) + hy1 * (wx0 * v10 + wx1 * v11);
+        // sum of the tap weights whose (normalised) input is positive: what the backward needs to form
+        // S0 = sum_pixels gy*[z>0]/den from the OUTPUT-sized tensors alone
+        taps = hy0 * (wx0 * (v00 > 0.f ? 1.f : 0.f) + wx1 * (v01 > 0.f ? 1.f : 0.f)) +
+               hy1 * (wx0 * (v10 > 0.f ? 1.f : 0.f) + wx1 * (v11 > 0.f ? 1.f : 0.f));
     }
     dst[o] = val * lab;
+    if (tapsum) tapsum[static_cast<size_t>(plane) * oh * ow + o] = taps;
 }
 
 // ---- backward ----------------------------------------------------------------------------------
@@ -181,41 +192,72 @@ __device__ __forceinline__ void build_tap_table(TapSlot* tab, int in_size, int o
     __syncthreads();
 }
 
-// pass 1 (kWrite = false): per plane, S1 = sum gy*relu(z)/den^2 and S0 = sum gy*[z>0]/den  (block partials, fixed order)
-// pass 2 (kWrite = true) : grad_p = [p>0] * ( gy*[z>0]/den + [idx==argmax]*(-S1) + [idx==argmin]*(S1 - S0) )
-// Planes whose label is 0 carry no gradient: pass 1 skips them, pass 2 only writes zeros (vectorised).
-template <bool kWrite>
+// Plane sums the gradient of max/min needs, from the OUTPUT-sized tensors only (one CTA per labelled plane):
+//   S1 = sum_pix gy*relu(z)/den^2 = sum_o gout_o * out_o / den          (out_o = lab * sum_taps w*relu(z)/den)
+//   S0 = sum_pix gy*[z>0]/den     = lab/den * sum_o gout_o * tapsum_o   (tapsum_o = sum_taps w*[z>0])
+// Fixed-order block reduction => deterministic.
+__global__ void __launch_bounds__(256) fullres_bwd_sums_kernel(const float* __restrict__ label,
+                                                               const float* __restrict__ minmax,
+                                                               const float* __restrict__ out,
+                                                               const float* __restrict__ tapsum,
+                                                               const float* __restrict__ gout, float* __restrict__ sums,
+                                                               int osz) {
+    const int plane = blockIdx.x;
+    const float lab = label[plane];
+    if (lab == 0.f) return;
+    const float den = minmax[plane * 4 + 1] - minmax[plane * 4] + 1e-5f;
+    const float* o = out + static_cast<size_t>(plane) * osz;
+    const float* t = tapsum + static_cast<size_t>(plane) * osz;
+    const float* g = gout + static_cast<size_t>(plane) * osz;
+    float a0 = 0.f, a1 = 0.f;
+    for (int i = threadIdx.x; i < osz; i += blockDim.x) {
+        const float gv = __ldg(g + i);
+        a0 = fmaf(gv, __ldg(t + i), a0);
+        a1 = fmaf(gv, __ldg(o + i), a1);
+    }
+    __shared__ float s_a[8], s_b[8];
+#pragma unroll
+    for (int ofs = 16; ofs > 0; ofs >>= 1) {
+        a0 += __shfl_xor_sync(0xffffffffu, a0, ofs);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, ofs);
+    }
+    if ((threadIdx.x & 31) == 0) { s_a[threadIdx.x >> 5] = a0; s_b[threadIdx.x >> 5] = a1; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float x0 = 0.f, x1 = 0.f;
+        for (int wv = 0; wv < (blockDim.x >> 5); ++wv) { x0 += s_a[wv]; x1 += s_b[wv]; }
+        sums[plane * 2] = x0 * lab / den;       // S0
+        sums[plane * 2 + 1] = x1 / den;         // S1
+    }
+}
+
+// grad_p = [p>0] * ( gy*[z>0]/den + [idx==argmax]*(-S1) + [idx==argmin]*(S1 - S0) ); planes whose label is 0 are a
+// vectorised zero fill.
 __global__ void __launch_bounds__(256) fullres_bwd_kernel(const float* __restrict__ p,
                                                           const float* __restrict__ label,
                                                           const float* __restrict__ minmax,
                                                           const float* __restrict__ gout,
                                                           float* __restrict__ grad_p,
-                                                          float* __restrict__ sums, int H, int W, int oh,
-                                                          int ow, int nblk) {
+                                                          const float* __restrict__ sums, int H, int W, int oh,
+                                                          int ow) {
     extern __shared__ TapSlot s_tab[];            // [2*H] rows then [2*W] columns (resampling case only)
     const int plane = blockIdx.y;
     const int HW = H * W;
     const float lab = label[plane];
     float* dst = grad_p + static_cast<size_t>(plane) * HW;
-    __shared__ float s_a[8], s_b[8];
     if (lab == 0.f) {
-        if (kWrite) {
-            if ((HW & 3) == 0) {
-                float4* d4 = reinterpret_cast<float4*>(dst);
-                for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (HW >> 2); i += gridDim.x * blockDim.x)
-                    d4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            } else {
-                for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) dst[i] = 0.f;
-            }
-        } else if (threadIdx.x == 0) {
-            sums[(plane * nblk + blockIdx.x) * 2] = 0.f;
-            sums[(plane * nblk + blockIdx.x) * 2 + 1] = 0.f;
+        if ((HW & 3) == 0) {
+            float4* d4 = reinterpret_cast<float4*>(dst);
+            for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (HW >> 2); i += gridDim.x * blockDim.x)
+                d4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+            for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) dst[i] = 0.f;
         }
         return;
     }
     const float lo = minmax[plane * 4], hi = minmax[plane * 4 + 1];
     const int ilo = __float_as_int(minmax[plane * 4 + 2]), ihi = __float_as_int(minmax[plane * 4 + 3]);
-    const float den = hi - lo + 1e-5f;
+    const float inv_den = 1.f / (hi - lo + 1e-5f);
     const float* src = p + static_cast<size_t>(plane) * HW;
     const float* g = gout + static_cast<size_t>(plane) * oh * ow;
     const bool same = (oh == H && ow == W);
@@ -227,54 +269,31 @@ __global__ void __launch_bounds__(256) fullres_bwd_kernel(const float* __restric
         build_tap_table(ty, H, oh, sy);
         build_tap_table(tx, W, ow, sx);
     }
-    float S0 = 0.f, S1 = 0.f;
-    if (kWrite) {
-        // final plane sums from the pass-1 partials (fixed order => deterministic)
-        for (int b = 0; b < nblk; ++b) { S0 += sums[(plane * nblk + b) * 2]; S1 += sums[(plane * nblk + b) * 2 + 1]; }
-    }
-    float acc0 = 0.f, acc1 = 0.f;
+    const float S0 = sums[plane * 2], S1 = sums[plane * 2 + 1];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
         const float pv = __ldg(src + i);
         const float z = fmaxf(pv, 0.f) - lo - 1e-5f;
         float gy = 0.f;
-        if (same) {
-            gy = __ldg(g + i) * lab;
-        } else {
-            const int y = i / W, x = i - y * W;
-            const TapSlot ya = ty[2 * y], yb = ty[2 * y + 1], xa = tx[2 * x], xb = tx[2 * x + 1];
-            if (ya.w != 0.f) {
-                if (xa.w != 0.f) gy = fmaf(ya.w * xa.w, __ldg(g + ya.o * ow + xa.o), gy);
-                if (xb.w != 0.f) gy = fmaf(ya.w * xb.w, __ldg(g + ya.o * ow + xb.o), gy);
+        if (z > 0.f) {
+            if (same) {
+                gy = __ldg(g + i);
+            } else {
+                const int y = i / W, x = i - y * W;
+                const TapSlot ya = ty[2 * y], yb = ty[2 * y + 1], xa = tx[2 * x], xb = tx[2 * x + 1];
+                if (ya.w != 0.f) {
+                    if (xa.w != 0.f) gy = fmaf(ya.w * xa.w, __ldg(g + ya.o * ow + xa.o), gy);
+                    if (xb.w != 0.f) gy = fmaf(ya.w * xb.w, __ldg(g + ya.o * ow + xb.o), gy);
+                }
+                if (yb.w != 0.f) {
+                    if (xa.w != 0.f) gy = fmaf(yb.w * xa.w, __ldg(g + yb.o * ow + xa.o), gy);
+                    if (xb.w != 0.f) gy = fmaf(yb.w * xb.w, __ldg(g + yb.o * ow + xb.o), gy);
+                }
             }
-            if (yb.w != 0.f) {
-                if (xa.w != 0.f) gy = fmaf(yb.w * xa.w, __ldg(g + yb.o * ow + xa.o), gy);
-                if (xb.w != 0.f) gy = fmaf(yb.w * xb.w, __ldg(g + yb.o * ow + xb.o), gy);
-            }
-            gy *= lab;
         }
-        if (!kWrite) {
-            if (z > 0.f) { acc0 += gy / den; acc1 += gy * z / (den * den); }
-        } else {
-            float d = (z > 0.f) ? gy / den : 0.f;
-            if (i == ihi) d -= S1;
-            if (i == ilo) d += S1 - S0;
-            dst[i] = (pv > 0.f) ? d : 0.f;
-        }
-    }
-    if (!kWrite) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            acc0 += __shfl_xor_sync(0xffffffffu, acc0, o);
-            acc1 += __shfl_xor_sync(0xffffffffu, acc1, o);
-        }
-        if ((threadIdx.x & 31) == 0) { s_a[threadIdx.x >> 5] = acc0; s_b[threadIdx.x >> 5] = acc1; }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            float a = 0.f, b = 0.f;
-            for (int wv = 0; wv < (blockDim.x >> 5); ++wv) { a += s_a[wv]; b += s_b[wv]; }
-            sums[(plane * nblk + blockIdx.x) * 2] = a;
-            sums[(plane * nblk + blockIdx.x) * 2 + 1] = b;
-        }
+        float d = gy * lab * inv_den;
+        if (i == ihi) d -= S1;
+        if (i == ilo) d += S1 - S0;
+        dst[i] = (pv > 0.f) ? d : 0.f;
     }
 }
 
@@ -409,9 +428,9 @@ namespace wsegk {
 size_t fullres_workspace_bytes(int N, int C) { return fullres_ws_bytes(N, C); }
 }
 
-extern "C" int wsegk_fullres_norm_fwd(const float* p, const float* label, float* out, float* minmax, int N, int C,
-                                      int H, int W, int oh, int ow, void* workspace, size_t workspace_bytes,
-                                      wsegk_stream_t stream) {
+extern "C" int wsegk_fullres_norm_fwd(const float* p, const float* label, float* out, float* minmax, float* tapsum,
+                                      int N, int C, int H, int W, int oh, int ow, void* workspace,
+                                      size_t workspace_bytes, wsegk_stream_t stream) {
     if (int rc = check_device()) return rc;
     WSEGK_REQUIRE(p && label && out && minmax && workspace, WSEGK_ERR_NULL, "fullres_norm_fwd: null pointer");
     if (int rc = fullres_check("fullres_norm_fwd", N, C, H, W, oh, ow)) return rc;
@@ -422,17 +441,18 @@ extern "C" int wsegk_fullres_norm_fwd(const float* p, const float* label, float*
     const int planes = N * C;
     plane_minmax_partial_kernel<<<dim3(kPlaneSplit, planes), 512, 0, stream>>>(p, label, partial, H * W);
     fullres_resample_kernel<<<dim3(ceil_div(oh * ow, 256), planes), 256, 0, stream>>>(p, label, partial, out, minmax,
-                                                                                       H, W, oh, ow, kPlaneSplit);
+                                                                                       tapsum, H, W, oh, ow, kPlaneSplit);
     count_launches(2);
     WSEGK_CUDA_OK(cudaGetLastError());
     return WSEGK_OK;
 }
 
-extern "C" int wsegk_fullres_norm_bwd(const float* p, const float* label, const float* minmax, const float* grad_out,
-                                      float* grad_p, int N, int C, int H, int W, int oh, int ow, void* workspace,
-                                      size_t workspace_bytes, wsegk_stream_t stream) {
+extern "C" int wsegk_fullres_norm_bwd(const float* p, const float* label, const float* minmax, const float* out,
+                                      const float* tapsum, const float* grad_out, float* grad_p, int N, int C, int H,
+                                      int W, int oh, int ow, void* workspace, size_t workspace_bytes,
+                                      wsegk_stream_t stream) {
     if (int rc = check_device()) return rc;
-    WSEGK_REQUIRE(p && label && minmax && grad_out && grad_p && workspace, WSEGK_ERR_NULL,
+    WSEGK_REQUIRE(p && label && minmax && out && tapsum && grad_out && grad_p && workspace, WSEGK_ERR_NULL,
                   "fullres_norm_bwd: null pointer");
     if (int rc = fullres_check("fullres_norm_bwd", N, C, H, W, oh, ow)) return rc;
     WSEGK_REQUIRE(workspace_bytes >= fullres_ws_bytes(N, C), WSEGK_ERR_WORKSPACE_TOO_SMALL,
@@ -444,14 +464,10 @@ extern "C" int wsegk_fullres_norm_bwd(const float* p, const float* label, const 
     const size_t tab = (oh == H && ow == W) ? 0 : static_cast<size_t>(2) * (H + W) * sizeof(TapSlot);
     WSEGK_REQUIRE(tab <= 200 * 1024, WSEGK_ERR_BAD_SHAPE, "fullres_norm_bwd: H + W = %d too large for the tap tables",
                   H + W);
-    WSEGK_CUDA_OK(cudaFuncSetAttribute(fullres_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    WSEGK_CUDA_OK(cudaFuncSetAttribute(fullres_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(tab)));
-    WSEGK_CUDA_OK(cudaFuncSetAttribute(fullres_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(tab)));
-    fullres_bwd_kernel<false><<<dim3(nblk, planes), 256, tab, stream>>>(p, label, minmax, grad_out, grad_p, sums, H,
-                                                                       W, oh, ow, nblk);
-    fullres_bwd_kernel<true><<<dim3(nblk, planes), 256, tab, stream>>>(p, label, minmax, grad_out, grad_p, sums, H, W,
-                                                                      oh, ow, nblk);
+    fullres_bwd_sums_kernel<<<planes, 256, 0, stream>>>(label, minmax, out, tapsum, grad_out, sums, oh * ow);
+    fullres_bwd_kernel<<<dim3(nblk, planes), 256, tab, stream>>>(p, label, minmax, grad_out, grad_p, sums, H, W, oh, ow);
     count_launches(2);
     WSEGK_CUDA_OK(cudaGetLastError());
     return WSEGK_OK;

@@ -40,45 +40,50 @@ __device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
 }
 
 // f [N,K,HW] fp32 -> normalised features as A tiles (128 rows) and B tiles (wb rows), FP16 hi (+ lo), + inv_norm.
-// One CTA per (128 pixels, image); 256 threads.
+// One CTA per (128 pixels, image), 256 threads: thread (pixel, half) keeps its K/2 channel values in registers
+// (channel groups half, half+2, ...), so global loads are coalesced along the pixel axis, the 16-byte chunks a thread
+// writes are already in tile order (row = pixel), and no shared-memory transpose is needed.
 template <bool kLo>
 __global__ void __launch_bounds__(256) pcm_prep_f_kernel(const float* __restrict__ f, uint4* __restrict__ fa_hi,
                                                          uint4* __restrict__ fa_lo, uint4* __restrict__ fb_hi,
                                                          uint4* __restrict__ fb_lo, float* __restrict__ inv_norm,
                                                          int K, int HW, int PJ, int NS, int wb) {
-    extern __shared__ float s_val[];            // [K][129]
+    constexpr int GMAX = kMaxPcmK / 16;          // channel groups per thread
     __shared__ float s_part[2][kTile];
-    __shared__ float s_inv[kTile];
     const int t = blockIdx.x, n = blockIdx.y;
     const int px = threadIdx.x & 127, half = threadIdx.x >> 7;
     const int p = t * kTile + px;
     const int HWpj = PJ * 2 * kTile, HWpi = NS * 2 * wb;
+    const int groups = K >> 3;
     const float* src = f + static_cast<size_t>(n) * K * HW + p;
+    float v[GMAX][8];
     float ss = 0.f;
-    for (int k = half; k < K; k += 2) {
-        float v = (p < HW) ? __ldg(src + static_cast<size_t>(k) * HW) : 0.f;
-        s_val[k * 129 + px] = v;
-        ss = fmaf(v, v, ss);
+#pragma unroll
+    for (int gi = 0; gi < GMAX; ++gi) {
+        const int g = half + 2 * gi;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            v[gi][e] = (g < groups && p < HW) ? __ldg(src + static_cast<size_t>(g * 8 + e) * HW) : 0.f;
+            ss = fmaf(v[gi][e], v[gi][e], ss);
+        }
     }
     s_part[half][px] = ss;
     __syncthreads();
-    if (threadIdx.x < kTile) {
-        float nrm = sqrtf(s_part[0][px] + s_part[1][px]);
-        float inv = 1.f / (nrm + 1e-5f);
-        s_inv[px] = inv;
-        if (p < HWpj) inv_norm[static_cast<size_t>(n) * HWpj + p] = (p < HW) ? inv : 0.f;
-    }
-    __syncthreads();
-    const int groups = K >> 3;
-    for (int chunk = threadIdx.x; chunk < groups * kTile; chunk += blockDim.x) {
-        const int g = chunk >> 7, r = chunk & 127;
-        const int pp = t * kTile + r;
-        const float inv = s_inv[r];
-        const float* v = s_val + (g * 8) * 129 + r;
+    const float nrm = sqrtf(s_part[0][px] + s_part[1][px]);
+    const float inv = 1.f / (nrm + 1e-5f);
+    if (half == 0 && p < HWpj) inv_norm[static_cast<size_t>(n) * HWpj + p] = (p < HW) ? inv : 0.f;
+    const bool in_a = p < HWpj, in_b = p < HWpi;
+    const int tb = p / wb, rb = p - tb * wb;
+    const size_t base_a = (static_cast<size_t>(n) * 2 * PJ + t) * groups * kTile + px;
+    const size_t base_b = (static_cast<size_t>(n) * 2 * NS + tb) * groups * wb + rb;
+#pragma unroll
+    for (int gi = 0; gi < GMAX; ++gi) {
+        const int g = half + 2 * gi;
+        if (g >= groups) break;
         __half hi[8], lo[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            const float x = v[e * 129] * inv;
+            const float x = v[gi][e] * inv;
             hi[e] = __float2half_rn(x);
             lo[e] = __float2half_rn(x - __half2float(hi[e]));
         }
@@ -86,16 +91,13 @@ __global__ void __launch_bounds__(256) pcm_prep_f_kernel(const float* __restrict
                                      pack_h2(hi[6], hi[7]));
         const uint4 olo = make_uint4(pack_h2(lo[0], lo[1]), pack_h2(lo[2], lo[3]), pack_h2(lo[4], lo[5]),
                                      pack_h2(lo[6], lo[7]));
-        if (pp < HWpj) {
-            const size_t ia = ((static_cast<size_t>(n) * 2 * PJ + t) * groups + g) * kTile + r;
-            fa_hi[ia] = ohi;
-            if (kLo) fa_lo[ia] = olo;
+        if (in_a) {
+            fa_hi[base_a + static_cast<size_t>(g) * kTile] = ohi;
+            if (kLo) fa_lo[base_a + static_cast<size_t>(g) * kTile] = olo;
         }
-        if (pp < HWpi) {
-            const int tb = pp / wb, rb = pp - tb * wb;
-            const size_t ib = ((static_cast<size_t>(n) * 2 * NS + tb) * groups + g) * wb + rb;
-            fb_hi[ib] = ohi;
-            if (kLo) fb_lo[ib] = olo;
+        if (in_b) {
+            fb_hi[base_b + static_cast<size_t>(g) * wb] = ohi;
+            if (kLo) fb_lo[base_b + static_cast<size_t>(g) * wb] = olo;
         }
     }
 }
@@ -917,18 +919,14 @@ extern "C" int wsegk_pcm_fwd(const float* f, const float* cam_norm, float* cam_r
     WSEGK_REQUIRE(workspace_bytes >= pl.bytes, WSEGK_ERR_WORKSPACE_TOO_SMALL, "pcm_fwd: workspace %zu < %zu",
                   workspace_bytes, pl.bytes);
     {
-        const size_t smem = static_cast<size_t>(K) * 129 * sizeof(float);
+        const size_t smem = 0;
         const int tiles = ceil_div(std::max(pl.HWpj, pl.HWpi), kTile);
         uint4 *a_hi = reinterpret_cast<uint4*>(pl.fa_hi), *a_lo = reinterpret_cast<uint4*>(pl.fa_lo);
         uint4 *b_hi = reinterpret_cast<uint4*>(pl.fb_hi), *b_lo = reinterpret_cast<uint4*>(pl.fb_lo);
         if (precise) {
-            WSEGK_CUDA_OK(cudaFuncSetAttribute(pcm_prep_f_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               static_cast<int>(smem)));
             pcm_prep_f_kernel<true><<<dim3(tiles, N), 256, smem, stream>>>(f, a_hi, a_lo, b_hi, b_lo, pl.inv_norm, K,
                                                                             pl.HW, pl.PJ, pl.NS, pl.wb);
         } else {
-            WSEGK_CUDA_OK(cudaFuncSetAttribute(pcm_prep_f_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               static_cast<int>(smem)));
             pcm_prep_f_kernel<false><<<dim3(tiles, N), 256, smem, stream>>>(f, a_hi, a_lo, b_hi, b_lo, pl.inv_norm, K,
                                                                              pl.HW, pl.PJ, pl.NS, pl.wb);
         }

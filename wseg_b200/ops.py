@@ -157,48 +157,49 @@ def _label_nc(label: torch.Tensor, n: int, c: int) -> torch.Tensor:
 
 
 def fullres_norm_fwd(p: torch.Tensor, label: torch.Tensor, size: Optional[Tuple[int, int]] = None):
-    """Raw K1b forward.  Returns (out [N,C,oh,ow], minmax [N,C,4] saved for the backward, label [N,C] on device)."""
+    """Raw K1b forward.  Returns (out [N,C,oh,ow], saved) where saved = (minmax [N,C,4], tapsum [N,C,oh,ow],
+    label [N,C] on device) is what the backward needs besides p and out."""
     p = _require_cuda_f32("p", p.detach())
     n, c, H, W = p.shape
     oh, ow = (H, W) if size is None else (int(size[0]), int(size[1]))
     lab = _label_nc(label, n, c).to(p.device)
     out = torch.empty(n, c, oh, ow, dtype=torch.float32, device=p.device)
+    tapsum = torch.empty(n, c, oh, ow, dtype=torch.float32, device=p.device)
     minmax = torch.empty(n, c, 4, dtype=torch.float32, device=p.device)
     with torch.cuda.device(p.device):
         ws = _workspace(_lib.OP_FULLRES_NORM, p.device, N=n, C=c, h=H, w=W)
-        check(_lib.lib().wsegk_fullres_norm_fwd(_ptr(p), _ptr(lab), _ptr(out), _ptr(minmax), n, c, H, W, oh, ow,
-                                                _ptr(ws), ws.numel(), _stream(p)), "wsegk_fullres_norm_fwd")
-    return out, minmax, lab
+        check(_lib.lib().wsegk_fullres_norm_fwd(_ptr(p), _ptr(lab), _ptr(out), _ptr(minmax), _ptr(tapsum), n, c, H, W,
+                                                oh, ow, _ptr(ws), ws.numel(), _stream(p)), "wsegk_fullres_norm_fwd")
+    return out, (minmax, tapsum, lab)
 
 
-def fullres_norm_bwd(p: torch.Tensor, lab: torch.Tensor, minmax: torch.Tensor, grad_out: torch.Tensor,
-                     out_size: Tuple[int, int]) -> torch.Tensor:
+def fullres_norm_bwd(p: torch.Tensor, out: torch.Tensor, saved, grad_out: torch.Tensor) -> torch.Tensor:
     """Raw K1b backward: grad_out [N,C,oh,ow] -> grad_p [N,C,H,W]."""
+    minmax, tapsum, lab = saved
     p = _require_cuda_f32("p", p.detach())
     grad_out = _require_cuda_f32("grad_out", grad_out)
     n, c, H, W = p.shape
-    oh, ow = int(out_size[0]), int(out_size[1])
+    oh, ow = out.shape[-2:]
     grad_p = torch.empty_like(p)
     with torch.cuda.device(p.device):
         ws = _workspace(_lib.OP_FULLRES_NORM, p.device, N=n, C=c, h=H, w=W)
-        check(_lib.lib().wsegk_fullres_norm_bwd(_ptr(p), _ptr(lab), _ptr(minmax), _ptr(grad_out), _ptr(grad_p),
-                                                n, c, H, W, oh, ow, _ptr(ws), ws.numel(), _stream(p)),
-              "wsegk_fullres_norm_bwd")
+        check(_lib.lib().wsegk_fullres_norm_bwd(_ptr(p), _ptr(lab), _ptr(minmax), _ptr(out), _ptr(tapsum),
+                                                _ptr(grad_out), _ptr(grad_p), n, c, H, W, oh, ow, _ptr(ws), ws.numel(),
+                                                _stream(p)), "wsegk_fullres_norm_bwd")
     return grad_p
 
 
 class _FullresNorm(torch.autograd.Function):
     @staticmethod
     def forward(ctx, p, label, size):
-        out, minmax, lab = fullres_norm_fwd(p, label, size)
-        ctx.save_for_backward(p, lab, minmax)
-        ctx.out_size = tuple(out.shape[-2:])
+        out, (minmax, tapsum, lab) = fullres_norm_fwd(p, label, size)
+        ctx.save_for_backward(p, out, minmax, tapsum, lab)
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
-        p, lab, minmax = ctx.saved_tensors
-        return fullres_norm_bwd(p, lab, minmax, grad_out, ctx.out_size), None, None
+        p, out, minmax, tapsum, lab = ctx.saved_tensors
+        return fullres_norm_bwd(p, out, (minmax, tapsum, lab), grad_out), None, None
 
 
 def fullres_norm(p: torch.Tensor, label: torch.Tensor, size: Optional[Tuple[int, int]] = None) -> torch.Tensor:
