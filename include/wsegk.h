@@ -97,9 +97,9 @@ int wsegk_seed_labels_fwd(const float* cam_rv_down, const float* label, float bg
                           int32_t* pseudo, int N, int C, int h, int w, void* workspace,
                           size_t workspace_bytes, wsegk_stream_t stream);
 
-/* Glue — replaces the two F.interpolate(..., mode='bilinear', align_corners=True) shrinks of view 1 to the loss grid,
- * contrast_train.py:179-180 (f_proj1 and cam_rv1_down).  x [planes,H,W] -> y [planes,oh,ow], oh <= H, ow <= W; and its
- * autograd: grad_y -> grad_x (deterministic gather, no atomics). */
+/* Glue — replaces F.interpolate(..., mode='bilinear', align_corners=True): the shrinks of view 1 to the loss grid
+ * (contrast_train.py:179-180) and the x8 enlargements at the end of Net.forward (network/resnet38_contrast.py:57-59).
+ * x [planes,H,W] -> y [planes,oh,ow], any sizes; and its autograd: grad_y -> grad_x (deterministic gather, no atomics). */
 int wsegk_bilinear_resize_fwd(const float* x, float* y, int planes, int H, int W, int oh, int ow, wsegk_stream_t stream);
 int wsegk_bilinear_resize_bwd(const float* grad_y, float* grad_x, int planes, int H, int W, int oh, int ow,
                               wsegk_stream_t stream);

@@ -366,7 +366,8 @@ def test_abi_error_codes(cuda_dev):
 
 
 @pytest.mark.parametrize("shape,size", [((8, 128, 56, 56), (16, 16)), ((2, 21, 64, 64), (32, 32)), ((3, 5, 23, 40), (20, 12)),
-                                        ((1, 4, 9, 9), (9, 9)), ((2, 3, 7, 5), (1, 1))])
+                                        ((1, 4, 9, 9), (9, 9)), ((2, 3, 7, 5), (1, 1)), ((2, 21, 56, 56), (448, 448)),
+                                        ((1, 3, 9, 7), (70, 45)), ((1, 2, 16, 5), (8, 40)), ((1, 2, 1, 1), (6, 4))])
 def test_bilinear_resize_matches_aten(cuda_dev, shape, size):
     """contrast_train.py:179-180: F.interpolate(..., mode='bilinear', align_corners=True), forward and backward."""
     g = torch.Generator().manual_seed(3)
@@ -379,4 +380,4 @@ def test_bilinear_resize_matches_aten(cuda_dev, shape, size):
     yb = F.interpolate(b, size=size, mode="bilinear", align_corners=True)
     yb.backward(gy)
     assert float((ya - yb).abs().max()) <= 1e-6
-    assert float((a.grad - b.grad).abs().max()) <= 1e-5
+    assert rel_max(a.grad, b.grad) <= 1e-5          # an enlargement's backward sums ~64 terms per input

@@ -350,6 +350,56 @@ __global__ void __launch_bounds__(256) resize_bwd_kernel(const float* __restrict
     }
 }
 
+// general gather (any scale, e.g. the x8 enlargement of Net.forward, network/resnet38_contrast.py:57-59): an input
+// coordinate i is touched by the outputs whose first tap is i-1 or i; first taps are monotone in o, so they form the
+// contiguous range below (padded by one on each side against float rounding); weights come from the forward's own
+// arithmetic (tap_weight), so the result is the exact transpose of the forward.
+__device__ __forceinline__ float tap_weight(int o, int i, float scale, int in_size) {
+    int i0, i1; float l0, l1;
+    src_coord(o, scale, in_size, i0, i1, l0, l1);
+    float wgt = 0.f;
+    if (i0 == i) wgt += l0;
+    if (i1 == i) wgt += l1;
+    return wgt;
+}
+
+__device__ __forceinline__ void out_range(int i, float scale, int out_size, int& first, int& last) {
+    if (scale <= 0.f) { first = 0; last = out_size - 1; return; }
+    const int a = static_cast<int>(floorf(static_cast<float>(i - 1) / scale)) - 1;
+    const int b = static_cast<int>(ceilf(static_cast<float>(i + 1) / scale)) + 1;
+    first = max(a, 0);
+    last = min(b, out_size - 1);
+}
+
+__global__ void __launch_bounds__(256) resize_bwd_gather_kernel(const float* __restrict__ gy, float* __restrict__ gx,
+                                                                int planes, int H, int W, int oh, int ow) {
+    const float sy = oh > 1 ? static_cast<float>(H - 1) / static_cast<float>(oh - 1) : 0.f;
+    const float sx = ow > 1 ? static_cast<float>(W - 1) / static_cast<float>(ow - 1) : 0.f;
+    const long long total = static_cast<long long>(planes) * H * W;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int xq = static_cast<int>(i % W);
+        const int yq = static_cast<int>((i / W) % H);
+        const long long plane = i / (static_cast<long long>(W) * H);
+        const float* g = gy + plane * oh * ow;
+        int oy0, oy1, ox0, ox1;
+        out_range(yq, sy, oh, oy0, oy1);
+        out_range(xq, sx, ow, ox0, ox1);
+        float acc = 0.f;
+        for (int oy = oy0; oy <= oy1; ++oy) {
+            const float wy = tap_weight(oy, yq, sy, H);
+            if (wy == 0.f) continue;
+            float row = 0.f;
+            for (int ox = ox0; ox <= ox1; ++ox) {
+                const float wx = tap_weight(ox, xq, sx, W);
+                if (wx != 0.f) row = fmaf(wx, __ldg(g + static_cast<size_t>(oy) * ow + ox), row);
+            }
+            acc = fmaf(wy, row, acc);
+        }
+        gx[i] = acc;
+    }
+}
+
 // ---- K1c ---------------------------------------------------------------------------------------
 // one warp per (n,c) plane: min/max of relu(x)
 __global__ void __launch_bounds__(256) seed_minmax_kernel(const float* __restrict__ x, float* __restrict__ lohi,
@@ -496,10 +546,8 @@ extern "C" int wsegk_seed_labels_fwd(const float* cam_rv_down, const float* labe
 
 static int resize_check(const char* who, int planes, int H, int W, int oh, int ow) {
     WSEGK_REQUIRE(planes > 0 && H > 0 && W > 0 && oh > 0 && ow > 0, WSEGK_ERR_BAD_SHAPE, "%s: dims must be positive", who);
-    WSEGK_REQUIRE(oh <= H && ow <= W, WSEGK_ERR_BAD_SHAPE, "%s: only shrinking is supported ((%d,%d) -> (%d,%d))", who, H,
-                  W, oh, ow);
-    WSEGK_REQUIRE(static_cast<size_t>(2) * (H + W) * sizeof(TapSlot) <= 200 * 1024, WSEGK_ERR_BAD_SHAPE,
-                  "%s: H + W = %d too large", who, H + W);
+    WSEGK_REQUIRE(static_cast<long long>(H) * W < (1ll << 30) && static_cast<long long>(oh) * ow < (1ll << 30),
+                  WSEGK_ERR_BAD_SHAPE, "%s: plane too large", who);
     return WSEGK_OK;
 }
 
@@ -509,7 +557,7 @@ extern "C" int wsegk_bilinear_resize_fwd(const float* x, float* y, int planes, i
     WSEGK_REQUIRE(x && y, WSEGK_ERR_NULL, "bilinear_resize_fwd: null pointer");
     if (int rc = resize_check("bilinear_resize_fwd", planes, H, W, oh, ow)) return rc;
     const long long total = static_cast<long long>(planes) * oh * ow;
-    const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 16));
+    const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 1 << 20));
     resize_fwd_kernel<<<blocks, 256, 0, stream>>>(x, y, planes, H, W, oh, ow);
     count_launches(1);
     WSEGK_CUDA_OK(cudaGetLastError());
@@ -524,8 +572,14 @@ extern "C" int wsegk_bilinear_resize_bwd(const float* grad_y, float* grad_x, int
     const long long total = static_cast<long long>(planes) * H * W;
     const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 16));
     const size_t tab = static_cast<size_t>(2) * (H + W) * sizeof(TapSlot);
-    WSEGK_CUDA_OK(cudaFuncSetAttribute(resize_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(tab)));
-    resize_bwd_kernel<<<blocks, 256, tab, stream>>>(grad_y, grad_x, planes, H, W, oh, ow);
+    if (oh <= H && ow <= W && tab <= 200 * 1024) {      // shrinking: <= 4 contributors per input, tap tables
+        WSEGK_CUDA_OK(cudaFuncSetAttribute(resize_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(tab)));
+        resize_bwd_kernel<<<blocks, 256, tab, stream>>>(grad_y, grad_x, planes, H, W, oh, ow);
+    } else {
+        const int gblocks = static_cast<int>(std::min<long long>((total + 255) / 256, 1 << 20));
+        resize_bwd_gather_kernel<<<gblocks, 256, 0, stream>>>(grad_y, grad_x, planes, H, W, oh, ow);
+    }
     count_launches(1);
     WSEGK_CUDA_OK(cudaGetLastError());
     return WSEGK_OK;

@@ -56,12 +56,8 @@ def contrast_terms(f_proj1: torch.Tensor, cam_rv1_down: torch.Tensor, f_proj2: t
     if grid is None:
         grid = tuple(f_proj2.shape[-2:])
     if tuple(f_proj1.shape[-2:]) != tuple(grid):
-        if grid[0] <= f_proj1.shape[-2] and grid[1] <= f_proj1.shape[-1]:
-            f1 = ops.bilinear_resize(f_proj1, grid)                                               # :179
-            c1 = ops.resize_fwd(cam_rv1_down, grid)                                               # :180 (no grad: seeds)
-        else:           # enlarging never happens in the reference; keep ATen for it
-            f1 = F.interpolate(f_proj1, size=grid, mode='bilinear', align_corners=True)
-            c1 = F.interpolate(cam_rv1_down, size=grid, mode='bilinear', align_corners=True)
+        f1 = ops.bilinear_resize(f_proj1, grid)                                                   # :179
+        c1 = ops.resize_fwd(cam_rv1_down, grid)                                                   # :180 (no grad: seeds)
     else:
         f1, c1 = f_proj1, cam_rv1_down
     f2, c2 = f_proj2, cam_rv2_down

@@ -44,8 +44,8 @@ class Net(resnet38d.Net):
         x_s = F.interpolate(x, (h, w), mode='bilinear', align_corners=True)
         f = torch.cat([x_s, f8_3, f8_4], dim=1)
         cam_rv_down = self.PCM(cam_d_norm, f)                                              # K2 (:63-75)
-        cam_rv = F.interpolate(cam_rv_down, (H, W), mode='bilinear', align_corners=True)
-        cam = F.interpolate(cam, (H, W), mode='bilinear', align_corners=True)
+        cam_rv = ops.bilinear_resize(cam_rv_down, (H, W))                                  # glue (:57-58)
+        cam = ops.bilinear_resize(cam, (H, W))                                             # glue (:59)
         return cam, cam_rv, f_proj, cam_rv_down
 
     def forward(self, x):
