@@ -192,25 +192,33 @@ __device__ __forceinline__ void build_tap_table(TapSlot* tab, int in_size, int o
     __syncthreads();
 }
 
-// Plane sums the gradient of max/min needs, from the OUTPUT-sized tensors only (one CTA per labelled plane):
+// Plane sums the gradient of max/min needs, from the OUTPUT-sized tensors only (kSumSplit CTAs per labelled plane):
 //   S1 = sum_pix gy*relu(z)/den^2 = sum_o gout_o * out_o / den          (out_o = lab * sum_taps w*relu(z)/den)
 //   S0 = sum_pix gy*[z>0]/den     = lab/den * sum_o gout_o * tapsum_o   (tapsum_o = sum_taps w*[z>0])
-// Fixed-order block reduction => deterministic.
+// Partials are combined in a fixed order by the consumer => deterministic.
+constexpr int kSumSplit = 8;
 __global__ void __launch_bounds__(256) fullres_bwd_sums_kernel(const float* __restrict__ label,
-                                                               const float* __restrict__ minmax,
                                                                const float* __restrict__ out,
                                                                const float* __restrict__ tapsum,
                                                                const float* __restrict__ gout, float* __restrict__ sums,
                                                                int osz) {
-    const int plane = blockIdx.x;
-    const float lab = label[plane];
-    if (lab == 0.f) return;
-    const float den = minmax[plane * 4 + 1] - minmax[plane * 4] + 1e-5f;
+    const int plane = blockIdx.y, part = blockIdx.x;
+    if (label[plane] == 0.f) return;
     const float* o = out + static_cast<size_t>(plane) * osz;
     const float* t = tapsum + static_cast<size_t>(plane) * osz;
     const float* g = gout + static_cast<size_t>(plane) * osz;
+    const int per = ceil_div_dev(osz, kSumSplit);
+    const int begin = part * per, end = min(osz, begin + per);
     float a0 = 0.f, a1 = 0.f;
-    for (int i = threadIdx.x; i < osz; i += blockDim.x) {
+    int i = begin + threadIdx.x;
+    for (; i + 3 * 256 < end; i += 4 * 256) {          // four independent triples of loads in flight
+        float gv[4], tv[4], ov[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { gv[j] = __ldg(g + i + j * 256); tv[j] = __ldg(t + i + j * 256); ov[j] = __ldg(o + i + j * 256); }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { a0 = fmaf(gv[j], tv[j], a0); a1 = fmaf(gv[j], ov[j], a1); }
+    }
+    for (; i < end; i += 256) {
         const float gv = __ldg(g + i);
         a0 = fmaf(gv, __ldg(t + i), a0);
         a1 = fmaf(gv, __ldg(o + i), a1);
@@ -226,8 +234,8 @@ __global__ void __launch_bounds__(256) fullres_bwd_sums_kernel(const float* __re
     if (threadIdx.x == 0) {
         float x0 = 0.f, x1 = 0.f;
         for (int wv = 0; wv < (blockDim.x >> 5); ++wv) { x0 += s_a[wv]; x1 += s_b[wv]; }
-        sums[plane * 2] = x0 * lab / den;       // S0
-        sums[plane * 2 + 1] = x1 / den;         // S1
+        sums[(plane * kSumSplit + part) * 2] = x0;
+        sums[(plane * kSumSplit + part) * 2 + 1] = x1;
     }
 }
 
@@ -269,7 +277,10 @@ __global__ void __launch_bounds__(256) fullres_bwd_kernel(const float* __restric
         build_tap_table(ty, H, oh, sy);
         build_tap_table(tx, W, ow, sx);
     }
-    const float S0 = sums[plane * 2], S1 = sums[plane * 2 + 1];
+    float S0 = 0.f, S1 = 0.f;
+    for (int k = 0; k < kSumSplit; ++k) { S0 += sums[(plane * kSumSplit + k) * 2]; S1 += sums[(plane * kSumSplit + k) * 2 + 1]; }
+    S0 *= lab * inv_den;
+    S1 *= inv_den;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
         const float pv = __ldg(src + i);
         const float z = fmaxf(pv, 0.f) - lo - 1e-5f;
@@ -302,20 +313,20 @@ __global__ void __launch_bounds__(256) fullres_bwd_kernel(const float* __restric
 // [8,128,56,56] -> 16x16 that is 256 threads and 0.3 ms.  One thread per output element here.
 __global__ void __launch_bounds__(256) resize_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int planes,
                                                          int H, int W, int oh, int ow) {
-    const long long total = static_cast<long long>(planes) * oh * ow;
     const float sy = oh > 1 ? static_cast<float>(H - 1) / static_cast<float>(oh - 1) : 0.f;
     const float sx = ow > 1 ? static_cast<float>(W - 1) / static_cast<float>(ow - 1) : 0.f;
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int ox = static_cast<int>(i % ow);
-        const int oy = static_cast<int>((i / ow) % oh);
-        const long long plane = i / (static_cast<long long>(ow) * oh);
-        int y0, y1, x0, x1; float hy0, hy1, wx0, wx1;
-        src_coord(oy, sy, H, y0, y1, hy0, hy1);
-        src_coord(ox, sx, W, x0, x1, wx0, wx1);
-        const float* src = x + plane * H * W;
-        y[i] = hy0 * (wx0 * __ldg(src + y0 * W + x0) + wx1 * __ldg(src + y0 * W + x1)) +
-               hy1 * (wx0 * __ldg(src + y1 * W + x0) + wx1 * __ldg(src + y1 * W + x1));
+    const int osz = oh * ow;
+    for (int plane = blockIdx.y; plane < planes; plane += gridDim.y) {
+        const float* src = x + static_cast<size_t>(plane) * H * W;
+        float* dst = y + static_cast<size_t>(plane) * osz;
+        for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < osz; o += gridDim.x * blockDim.x) {
+            const int oy = o / ow, ox = o - oy * ow;
+            int y0, y1, x0, x1; float hy0, hy1, wx0, wx1;
+            src_coord(oy, sy, H, y0, y1, hy0, hy1);
+            src_coord(ox, sx, W, x0, x1, wx0, wx1);
+            dst[o] = hy0 * (wx0 * __ldg(src + y0 * W + x0) + wx1 * __ldg(src + y0 * W + x1)) +
+                     hy1 * (wx0 * __ldg(src + y1 * W + x0) + wx1 * __ldg(src + y1 * W + x1));
+        }
     }
 }
 
@@ -329,24 +340,24 @@ __global__ void __launch_bounds__(256) resize_bwd_kernel(const float* __restrict
     const float sx = ow > 1 ? static_cast<float>(W - 1) / static_cast<float>(ow - 1) : 0.f;
     build_tap_table(ty, H, oh, sy);
     build_tap_table(tx, W, ow, sx);
-    const long long total = static_cast<long long>(planes) * H * W;
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int xq = static_cast<int>(i % W);
-        const int yq = static_cast<int>((i / W) % H);
-        const long long plane = i / (static_cast<long long>(W) * H);
-        const float* g = gy + plane * oh * ow;
-        const TapSlot ya = ty[2 * yq], yb = ty[2 * yq + 1], xa = tx[2 * xq], xb = tx[2 * xq + 1];
-        float acc = 0.f;
-        if (ya.w != 0.f) {
-            if (xa.w != 0.f) acc = fmaf(ya.w * xa.w, __ldg(g + ya.o * ow + xa.o), acc);
-            if (xb.w != 0.f) acc = fmaf(ya.w * xb.w, __ldg(g + ya.o * ow + xb.o), acc);
+    const int isz = H * W;
+    for (int plane = blockIdx.y; plane < planes; plane += gridDim.y) {
+        const float* g = gy + static_cast<size_t>(plane) * oh * ow;
+        float* dst = gx + static_cast<size_t>(plane) * isz;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < isz; i += gridDim.x * blockDim.x) {
+            const int yq = i / W, xq = i - yq * W;
+            const TapSlot ya = ty[2 * yq], yb = ty[2 * yq + 1], xa = tx[2 * xq], xb = tx[2 * xq + 1];
+            float acc = 0.f;
+            if (ya.w != 0.f) {
+                if (xa.w != 0.f) acc = fmaf(ya.w * xa.w, __ldg(g + ya.o * ow + xa.o), acc);
+                if (xb.w != 0.f) acc = fmaf(ya.w * xb.w, __ldg(g + ya.o * ow + xb.o), acc);
+            }
+            if (yb.w != 0.f) {
+                if (xa.w != 0.f) acc = fmaf(yb.w * xa.w, __ldg(g + yb.o * ow + xa.o), acc);
+                if (xb.w != 0.f) acc = fmaf(yb.w * xb.w, __ldg(g + yb.o * ow + xb.o), acc);
+            }
+            dst[i] = acc;
         }
-        if (yb.w != 0.f) {
-            if (xa.w != 0.f) acc = fmaf(yb.w * xa.w, __ldg(g + yb.o * ow + xa.o), acc);
-            if (xb.w != 0.f) acc = fmaf(yb.w * xb.w, __ldg(g + yb.o * ow + xb.o), acc);
-        }
-        gx[i] = acc;
     }
 }
 
@@ -371,32 +382,49 @@ __device__ __forceinline__ void out_range(int i, float scale, int out_size, int&
     last = min(b, out_size - 1);
 }
 
+constexpr int kMaxTapRange = 24;      // outputs touching one input coordinate along one axis (x8 enlargement: 18)
 __global__ void __launch_bounds__(256) resize_bwd_gather_kernel(const float* __restrict__ gy, float* __restrict__ gx,
                                                                 int planes, int H, int W, int oh, int ow) {
     const float sy = oh > 1 ? static_cast<float>(H - 1) / static_cast<float>(oh - 1) : 0.f;
     const float sx = ow > 1 ? static_cast<float>(W - 1) / static_cast<float>(ow - 1) : 0.f;
-    const long long total = static_cast<long long>(planes) * H * W;
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int xq = static_cast<int>(i % W);
-        const int yq = static_cast<int>((i / W) % H);
-        const long long plane = i / (static_cast<long long>(W) * H);
-        const float* g = gy + plane * oh * ow;
-        int oy0, oy1, ox0, ox1;
-        out_range(yq, sy, oh, oy0, oy1);
-        out_range(xq, sx, ow, ox0, ox1);
-        float acc = 0.f;
-        for (int oy = oy0; oy <= oy1; ++oy) {
-            const float wy = tap_weight(oy, yq, sy, H);
-            if (wy == 0.f) continue;
-            float row = 0.f;
-            for (int ox = ox0; ox <= ox1; ++ox) {
-                const float wx = tap_weight(ox, xq, sx, W);
-                if (wx != 0.f) row = fmaf(wx, __ldg(g + static_cast<size_t>(oy) * ow + ox), row);
+    const int isz = H * W;
+    for (int plane = blockIdx.y; plane < planes; plane += gridDim.y) {
+        const float* g = gy + static_cast<size_t>(plane) * oh * ow;
+        float* dst = gx + static_cast<size_t>(plane) * isz;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < isz; i += gridDim.x * blockDim.x) {
+            const int yq = i / W, xq = i - yq * W;
+            int oy0, oy1, ox0, ox1;
+            out_range(yq, sy, oh, oy0, oy1);
+            out_range(xq, sx, ow, ox0, ox1);
+            float acc = 0.f;
+            if (ox1 - ox0 < kMaxTapRange) {
+                float wx[kMaxTapRange];                 // column weights once per input pixel
+#pragma unroll
+                for (int j = 0; j < kMaxTapRange; ++j) wx[j] = (ox0 + j <= ox1) ? tap_weight(ox0 + j, xq, sx, W) : 0.f;
+                for (int oy = oy0; oy <= oy1; ++oy) {
+                    const float wy = tap_weight(oy, yq, sy, H);
+                    if (wy == 0.f) continue;
+                    const float* row_p = g + static_cast<size_t>(oy) * ow + ox0;
+                    float row = 0.f;
+#pragma unroll
+                    for (int j = 0; j < kMaxTapRange; ++j)
+                        if (wx[j] != 0.f) row = fmaf(wx[j], __ldg(row_p + j), row);
+                    acc = fmaf(wy, row, acc);
+                }
+            } else {
+                for (int oy = oy0; oy <= oy1; ++oy) {
+                    const float wy = tap_weight(oy, yq, sy, H);
+                    if (wy == 0.f) continue;
+                    float row = 0.f;
+                    for (int ox = ox0; ox <= ox1; ++ox) {
+                        const float wxv = tap_weight(ox, xq, sx, W);
+                        if (wxv != 0.f) row = fmaf(wxv, __ldg(g + static_cast<size_t>(oy) * ow + ox), row);
+                    }
+                    acc = fmaf(wy, row, acc);
+                }
             }
-            acc = fmaf(wy, row, acc);
+            dst[i] = acc;
         }
-        gx[i] = acc;
     }
 }
 
@@ -516,7 +544,7 @@ extern "C" int wsegk_fullres_norm_bwd(const float* p, const float* label, const 
                   H + W);
     WSEGK_CUDA_OK(cudaFuncSetAttribute(fullres_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(tab)));
-    fullres_bwd_sums_kernel<<<planes, 256, 0, stream>>>(label, minmax, out, tapsum, grad_out, sums, oh * ow);
+    fullres_bwd_sums_kernel<<<dim3(kSumSplit, planes), 256, 0, stream>>>(label, out, tapsum, grad_out, sums, oh * ow);
     fullres_bwd_kernel<<<dim3(nblk, planes), 256, tab, stream>>>(p, label, minmax, grad_out, grad_p, sums, H, W, oh, ow);
     count_launches(2);
     WSEGK_CUDA_OK(cudaGetLastError());
@@ -556,9 +584,8 @@ extern "C" int wsegk_bilinear_resize_fwd(const float* x, float* y, int planes, i
     if (int rc = check_device()) return rc;
     WSEGK_REQUIRE(x && y, WSEGK_ERR_NULL, "bilinear_resize_fwd: null pointer");
     if (int rc = resize_check("bilinear_resize_fwd", planes, H, W, oh, ow)) return rc;
-    const long long total = static_cast<long long>(planes) * oh * ow;
-    const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 1 << 20));
-    resize_fwd_kernel<<<blocks, 256, 0, stream>>>(x, y, planes, H, W, oh, ow);
+    const dim3 grid(std::min(ceil_div(oh * ow, 256), 1024), std::min(planes, 32768));
+    resize_fwd_kernel<<<grid, 256, 0, stream>>>(x, y, planes, H, W, oh, ow);
     count_launches(1);
     WSEGK_CUDA_OK(cudaGetLastError());
     return WSEGK_OK;
@@ -569,16 +596,14 @@ extern "C" int wsegk_bilinear_resize_bwd(const float* grad_y, float* grad_x, int
     if (int rc = check_device()) return rc;
     WSEGK_REQUIRE(grad_y && grad_x, WSEGK_ERR_NULL, "bilinear_resize_bwd: null pointer");
     if (int rc = resize_check("bilinear_resize_bwd", planes, H, W, oh, ow)) return rc;
-    const long long total = static_cast<long long>(planes) * H * W;
-    const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 16));
+    const dim3 grid(std::min(ceil_div(H * W, 256), 1024), std::min(planes, 32768));
     const size_t tab = static_cast<size_t>(2) * (H + W) * sizeof(TapSlot);
     if (oh <= H && ow <= W && tab <= 200 * 1024) {      // shrinking: <= 4 contributors per input, tap tables
         WSEGK_CUDA_OK(cudaFuncSetAttribute(resize_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            static_cast<int>(tab)));
-        resize_bwd_kernel<<<blocks, 256, tab, stream>>>(grad_y, grad_x, planes, H, W, oh, ow);
+        resize_bwd_kernel<<<grid, 256, tab, stream>>>(grad_y, grad_x, planes, H, W, oh, ow);
     } else {
-        const int gblocks = static_cast<int>(std::min<long long>((total + 255) / 256, 1 << 20));
-        resize_bwd_gather_kernel<<<gblocks, 256, 0, stream>>>(grad_y, grad_x, planes, H, W, oh, ow);
+        resize_bwd_gather_kernel<<<grid, 256, 0, stream>>>(grad_y, grad_x, planes, H, W, oh, ow);
     }
     count_launches(1);
     WSEGK_CUDA_OK(cudaGetLastError());

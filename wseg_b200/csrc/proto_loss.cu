@@ -80,15 +80,34 @@ __global__ void __launch_bounds__(kTopkThreads) proto_topk_kernel(const float* _
             if (pass == 0 || (key >> (shift + 8)) == prefix) atomicAdd(&s_hist[(key >> shift) & 255u], 1u);
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            int need = s_need, cum = 0, digit = 0;
-            for (int b = 255; b >= 0; --b) {
-                const int hcount = static_cast<int>(s_hist[b]);
-                if (cum + hcount >= need) { digit = b; need -= cum; s_done = (hcount == need) ? 1 : 0; break; }
-                cum += hcount;
+        if (threadIdx.x < 32) {
+            // warp 0 finds the bin holding the need-th largest key: lane l owns bins 255-8l .. 248-8l (descending),
+            // an inclusive scan over lanes locates the owner, which then walks its 8 bins
+            const int lane = threadIdx.x;
+            int local[8], sum = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { local[j] = static_cast<int>(s_hist[255 - (8 * lane + j)]); sum += local[j]; }
+            int incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
             }
-            s_need = need;
-            s_prefix = (prefix << 8) | static_cast<unsigned long long>(digit);
+            const int need = s_need, excl = incl - sum;
+            if (excl < need && need <= incl) {
+                int cum = excl;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (cum + local[j] >= need) {
+                        const int left = need - cum;
+                        s_need = left;
+                        s_done = (local[j] == left) ? 1 : 0;
+                        s_prefix = (prefix << 8) | static_cast<unsigned long long>(255 - (8 * lane + j));
+                        break;
+                    }
+                    cum += local[j];
+                }
+            }
         }
         __syncthreads();
         if (s_done) break;
