@@ -113,27 +113,27 @@ class HotPath:
         rv1, ws1 = ops.pcm_forward(camn1, d["f1"])
         f1_done = torch.cuda.Event()
         f1_done.record(cur)
-        # ---- view 2 chain
+        # ---- view 2 chain: K1a, K2 forward, its seeds and prototypes, then K1b(cam_rv2) and K2 backward
         with torch.cuda.stream(s2):
             camn2 = ops.cam_norm(d["cam2"])
             rv2, ws2 = ops.pcm_forward(camn2, d["f2"])
-            f2_done = torch.cuda.Event()
-            f2_done.record(s2)
+            norm2, pl2 = ops.seed_labels(rv2, d["label"], BG_THRESHOLD)
+            proto2, ti2 = ops.prototypes(norm2, d["fproj2"], group=self.group)
+            v2_done = torch.cuda.Event()
+            v2_done.record(s2)
             g_rv2 = k1b("rv2_full", None, "g_rv2")
             gf2 = ops.pcm_backward(d["f2"], camn2, rv2, d["g_rv_down2"], ws2)
             s2_done = torch.cuda.Event()
             s2_done.record(s2)
-        # ---- loss chain: glue kept in PyTorch as in the reference (contrast_train.py:179-180), K1c, K3 (whole batch
-        # across ranks), K4 forward+backward
+        # ---- loss chain: shrink view 1 to the loss grid (contrast_train.py:179-180), K1c, K3 (whole batch across
+        # ranks), then K4 forward+backward once view 2's prototypes are there
         with torch.cuda.stream(s3):
             s3.wait_event(f1_done)
-            s3.wait_event(f2_done)
             f1 = ops.resize_fwd(d["fproj1"], self.grid)
             c1 = ops.resize_fwd(rv1, self.grid)
             norm1, pl1 = ops.seed_labels(c1, d["label"], BG_THRESHOLD)
-            norm2, pl2 = ops.seed_labels(rv2, d["label"], BG_THRESHOLD)
             proto1, ti1 = ops.prototypes(norm1, f1, group=self.group)
-            proto2, ti2 = ops.prototypes(norm2, d["fproj2"], group=self.group)
+            s3.wait_event(v2_done)
             losses, g1, g2, _, _ = ops.contrast_loss_raw(f1, d["fproj2"], proto1, proto2, pl1, pl2, self.key1, self.key2)
             keep.extend([f1, c1, norm1, pl1, norm2, pl2, proto1, ti1, proto2, ti2])
             s3_done = torch.cuda.Event()

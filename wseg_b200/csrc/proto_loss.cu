@@ -290,40 +290,51 @@ __global__ void __launch_bounds__(kNceThreads) nce_pixel_kernel(NceParams prm) {
         for (int j = 0; j < 6; ++j) s_sc[pix * 49 + grp * 6 + j] = acc[j] * inv;
     }
     __syncthreads();
-    float cross = 0.f, cross2 = 0.f;
-    if (grp == 0 && p < P) {
-        float own[kNceMaxC], oth[kNceMaxC];
+    // per-pixel scalars, spread over the pixel's 8 threads: thread (pix, grp) owns classes grp, grp+8, grp+16
+    float* s_part = s_sc + kNcePix * 49;                      // [kNcePix][kNceGroups][4]
+    if (p < P) {
+        float z_own = 0.f, z_oth = 0.f, a2 = 0.f;
+        uint32_t mask = 0u;
 #pragma unroll
-        for (int c = 0; c < kNceMaxC; ++c) { own[c] = s_sc[pix * 49 + c]; oth[c] = s_sc[pix * 49 + kSlotHalf + c]; }
-        const int lo = V.pl_own[p], lt = V.pl_oth[p];
-        float z_own = 0.f, z_oth = 0.f, pos_own = 0.f, pos_oth_lo = 0.f, pos_own_lt = 0.f;
-#pragma unroll
-        for (int c = 0; c < kNceMaxC; ++c) {
+        for (int j = 0; j < 3; ++j) {
+            const int c = grp + kNceGroups * j;
             if (c < C) {
-                V.s_own[static_cast<size_t>(c) * P + p] = own[c];
-                V.s_oth[static_cast<size_t>(c) * P + p] = oth[c];
-                z_own += expf(own[c] * kInvT);
-                z_oth += expf(oth[c] * kInvT);
-                if (c == lo) { pos_own = own[c]; pos_oth_lo = oth[c]; }
-                if (c == lt) pos_own_lt = own[c];
+                const float own_c = s_sc[pix * 49 + c], oth_c = s_sc[pix * 49 + kSlotHalf + c];
+                V.s_own[static_cast<size_t>(c) * P + p] = own_c;
+                V.s_oth[static_cast<size_t>(c) * P + p] = oth_c;
+                const float e_own = expf(own_c * kInvT);
+                z_own += e_own;
+                z_oth += expf(oth_c * kInvT);
+                // rank of c among the pixel's own-prototype scores (value desc, class asc); ranks 3..12 are semi-hard
+                int rank = 0;
+                for (int e = 0; e < C; ++e) {
+                    const float own_e = s_sc[pix * 49 + e];
+                    rank += (own_e > own_c || (own_e == own_c && e < c)) ? 1 : 0;
+                }
+                if (rank >= 3 && rank < 13) { mask |= (1u << c); a2 += e_own; }
             }
         }
+        float* dstp = s_part + (pix * kNceGroups + grp) * 4;
+        dstp[0] = z_own; dstp[1] = z_oth; dstp[2] = a2; dstp[3] = __uint_as_float(mask);
+    }
+    __syncthreads();
+    float cross = 0.f, cross2 = 0.f;
+    if (grp == 0 && p < P) {
+        float z_own = 0.f, z_oth = 0.f, a2 = 0.f;
+        uint32_t mask = 0u;
+#pragma unroll
+        for (int g = 0; g < kNceGroups; ++g) {                 // fixed order
+            const float* sp = s_part + (pix * kNceGroups + g) * 4;
+            z_own += sp[0]; z_oth += sp[1]; a2 += sp[2]; mask |= __float_as_uint(sp[3]);
+        }
+        const int lo = V.pl_own[p], lt = V.pl_oth[p];
+        const float pos_own = s_sc[pix * 49 + lo], pos_oth_lo = s_sc[pix * 49 + kSlotHalf + lo];
+        const float pos_own_lt = s_sc[pix * 49 + lt];
         // cross: other view's prototypes, own label (:261-267); cross2: own prototypes, other view's label (:272-279)
         cross = logf(z_oth) - pos_oth_lo * kInvT;
         cross2 = logf(z_own) - pos_own_lt * kInvT;
-        // intra (:285-299): positive + the prototypes at ranks 3..12 of q.proto_own (value desc, class asc)
-        uint32_t mask = 0u;
-        float a2 = expf(pos_own * kInvT);
-#pragma unroll
-        for (int c = 0; c < kNceMaxC; ++c) {
-            if (c < C) {
-                int rank = 0;
-#pragma unroll
-                for (int e = 0; e < kNceMaxC; ++e)
-                    if (e < C) rank += (own[e] > own[c] || (own[e] == own[c] && e < c)) ? 1 : 0;
-                if (rank >= 3 && rank < 13) { mask |= (1u << c); a2 += expf(own[c] * kInvT); }
-            }
-        }
+        // intra (:285-299): positive + the prototypes at ranks 3..12 of q.proto_own
+        a2 += expf(pos_own * kInvT);
         V.setmask[p] = mask;
         V.ell[p] = logf(a2) - pos_own * kInvT;
         V.sim[p] = (pos_own + 1.f) * 0.5f;
@@ -399,8 +410,35 @@ __global__ void __launch_bounds__(kNceThreads) nce_grad_kernel(NceParams prm) {
     const int pix = threadIdx.x & (kNcePix - 1), grp = threadIdx.x / kNcePix;
     const int p = blockIdx.x * kNcePix + pix;
     float intra = 0.f;
+    // per-pixel scalars over the pixel's 8 threads (classes grp, grp+8, grp+16), reduced through shared memory in a
+    // fixed order
+    float* s_part = s_coef + kNcePix * 49;                    // [kNcePix][kNceGroups][4]
+    __shared__ float s_w[kNcePix][4];                         // w_x, w_i, lo, lt per pixel
+    float ea[3] = {0.f, 0.f, 0.f}, eb[3] = {0.f, 0.f, 0.f}, so[3] = {0.f, 0.f, 0.f}, st[3] = {0.f, 0.f, 0.f};
+    uint32_t mask = 0u;
+    int lo = 0, lt = 0;
+    if (p < P) {
+        lo = V.pl_own[p]; lt = V.pl_oth[p];
+        mask = V.setmask[p];
+        float z_own = 0.f, z_oth = 0.f, z_set = 0.f;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const int c = grp + kNceGroups * j;
+            if (c < C) {
+                so[j] = V.s_own[static_cast<size_t>(c) * P + p];
+                st[j] = V.s_oth[static_cast<size_t>(c) * P + p];
+                ea[j] = expf(so[j] * kInvT);
+                eb[j] = expf(st[j] * kInvT);
+                z_own += ea[j];
+                z_oth += eb[j];
+                const int mult = ((mask >> c) & 1u) + (c == lo ? 1 : 0);
+                z_set += static_cast<float>(mult) * ea[j];
+            }
+        }
+        float* dstp = s_part + (pix * kNceGroups + grp) * 4;
+        dstp[0] = z_own; dstp[1] = z_oth; dstp[2] = z_set; dstp[3] = 0.f;
+    }
     if (grp == 0 && p < P) {
-        const int lo = V.pl_own[p], lt = V.pl_oth[p];
         const int len = V.cls_count[lo];
         const int half = len >> 1;
         int cnt = 0;
@@ -415,38 +453,45 @@ __global__ void __launch_bounds__(kNceThreads) nce_grad_kernel(NceParams prm) {
                                     (static_cast<float>(2 * half) * static_cast<float>(s_present))
                               : 0.f;
         intra = w_i * V.ell[p];
-        const uint32_t mask = V.setmask[p];
-        float a[kNceMaxC], b[kNceMaxC];
+        s_w[pix][0] = w_x; s_w[pix][1] = w_i;
+        s_scale[pix] = V.inv_norm[p];
+    }
+    __syncthreads();
+    float qdq_part = 0.f;
+    if (p < P) {
         float z_own = 0.f, z_oth = 0.f, z_set = 0.f;
 #pragma unroll
-        for (int c = 0; c < kNceMaxC; ++c) {
-            a[c] = 0.f; b[c] = 0.f;
-            if (c < C) {
-                a[c] = expf(V.s_own[static_cast<size_t>(c) * P + p] * kInvT);
-                b[c] = expf(V.s_oth[static_cast<size_t>(c) * P + p] * kInvT);
-                z_own += a[c];
-                z_oth += b[c];
-                const int mult = ((mask >> c) & 1u) + (c == lo ? 1 : 0);
-                z_set += static_cast<float>(mult) * a[c];
+        for (int g = 0; g < kNceGroups; ++g) {                 // fixed order, identical in all 8 threads
+            const float* sp = s_part + (pix * kNceGroups + g) * 4;
+            z_own += sp[0]; z_oth += sp[1]; z_set += sp[2];
+        }
+        const float w_x = s_w[pix][0], w_i = s_w[pix][1];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const int c = grp + kNceGroups * j;
+            if (c < kSlotHalf) {
+                float ac = 0.f, bc = 0.f;
+                if (c < C) {
+                    const int mult = ((mask >> c) & 1u) + (c == lo ? 1 : 0);
+                    ac = w_x * (ea[j] / z_own - (c == lt ? 1.f : 0.f)) +
+                         w_i * (static_cast<float>(mult) * ea[j] / z_set - (c == lo ? 1.f : 0.f));
+                    bc = w_x * (eb[j] / z_oth - (c == lo ? 1.f : 0.f));
+                    qdq_part = fmaf(ac, so[j], qdq_part);
+                    qdq_part = fmaf(bc, st[j], qdq_part);
+                }
+                s_coef[pix * 49 + c] = ac * kInvT;
+                s_coef[pix * 49 + kSlotHalf + c] = bc * kInvT;
             }
         }
+    }
+    __syncthreads();           // everyone has read s_part: reuse it for the qdq partials
+    if (p < P) s_part[(pix * kNceGroups + grp) * 4 + 3] = qdq_part;
+    __syncthreads();
+    if (grp == 0 && p < P) {
         float qdq = 0.f;
 #pragma unroll
-        for (int c = 0; c < kNceMaxC; ++c) {
-            float ac = 0.f, bc = 0.f;
-            if (c < C) {
-                const int mult = ((mask >> c) & 1u) + (c == lo ? 1 : 0);
-                ac = w_x * (a[c] / z_own - (c == lt ? 1.f : 0.f)) +
-                     w_i * (static_cast<float>(mult) * a[c] / z_set - (c == lo ? 1.f : 0.f));
-                bc = w_x * (b[c] / z_oth - (c == lo ? 1.f : 0.f));
-                qdq = fmaf(ac, V.s_own[static_cast<size_t>(c) * P + p], qdq);
-                qdq = fmaf(bc, V.s_oth[static_cast<size_t>(c) * P + p], qdq);
-            }
-            s_coef[pix * 49 + c] = ac * kInvT;
-            s_coef[pix * 49 + kSlotHalf + c] = bc * kInvT;
-        }
+        for (int g = 0; g < kNceGroups; ++g) qdq += s_part[(pix * kNceGroups + g) * 4 + 3];
         s_qdq[pix] = qdq * kInvT;
-        s_scale[pix] = V.inv_norm[p];
     }
     __syncthreads();
     if (p < P) {
@@ -605,7 +650,7 @@ extern "C" int wsegk_contrast_loss_fwd_bwd(const float* x1, const float* x2, con
     const long long P = static_cast<long long>(N) * h * w;
     WSEGK_REQUIRE(P <= (1 << 17), WSEGK_ERR_BAD_SHAPE,
                   "contrast_loss_fwd_bwd: P=%lld pixels exceeds the pairwise mining limit of 131072", P);
-    const size_t proto_smem = (static_cast<size_t>(kNceSlots) * (D + 1) + kNcePix * 49) * sizeof(float);
+    const size_t proto_smem = (static_cast<size_t>(kNceSlots) * (D + 1) + kNcePix * 49 + kNcePix * kNceGroups * 4) * sizeof(float);
     WSEGK_REQUIRE(proto_smem <= 200 * 1024, WSEGK_ERR_BAD_SHAPE, "contrast_loss_fwd_bwd: D too large");
     const NceLayout L = nce_layout(N, C, h, w);
     WSEGK_REQUIRE(workspace_bytes >= L.total, WSEGK_ERR_WORKSPACE_TOO_SMALL,
