@@ -37,35 +37,33 @@ __global__ void __launch_bounds__(256) cam_plane_peak_kernel(const float* __rest
     }
 }
 
-// one thread per pixel; channels are strided by HW so every load/store is coalesced across the warp
+// one thread per pixel; channels are strided by HW so every load/store is coalesced across the warp.  Two short
+// passes over the channels (the second re-reads from L1/L2) keep the code small: at these sizes (2 MB) the kernel is
+// bound by launch and instruction-fetch latency, and a 32-way unrolled body took 13 us.
 template <int MAXC>
 __global__ void __launch_bounds__(128) cam_pixel_kernel(const float* __restrict__ cam,
                                                         const float* __restrict__ peak,
                                                         float* __restrict__ out, int C, int HW) {
     const int n = blockIdx.y;
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    __shared__ float s_peak[MAXC];
-    if (threadIdx.x < C) s_peak[threadIdx.x] = peak[n * C + threadIdx.x];
+    __shared__ float s_inv[MAXC];
+    if (threadIdx.x < C) s_inv[threadIdx.x] = peak[n * C + threadIdx.x];
     __syncthreads();
     if (p >= HW) return;
     const float* src = cam + static_cast<size_t>(n) * C * HW + p;
     float* dst = out + static_cast<size_t>(n) * C * HW + p;
-    float y[MAXC];
     float fg = 0.f;
-#pragma unroll
-    for (int c = 0; c < MAXC; ++c) {
-        if (c < C) {
-            float x = fmaxf(__ldg(src + static_cast<size_t>(c) * HW), 0.f);
-            y[c] = fmaxf(x - 1e-5f, 0.f) / s_peak[c];
-            if (c >= 1) fg = fmaxf(fg, y[c]);
-        }
+#pragma unroll 4
+    for (int c = 1; c < C; ++c) {
+        const float x = fmaxf(__ldg(src + static_cast<size_t>(c) * HW), 0.f);
+        fg = fmaxf(fg, fmaxf(x - 1e-5f, 0.f) / s_inv[c]);
     }
-#pragma unroll
-    for (int c = 0; c < MAXC; ++c) {
-        if (c < C) {
-            float v = (c == 0) ? (1.f - fg) : ((y[c] < fg) ? 0.f : y[c]);
-            dst[static_cast<size_t>(c) * HW] = v;
-        }
+    dst[0] = 1.f - fg;
+#pragma unroll 4
+    for (int c = 1; c < C; ++c) {
+        const float x = fmaxf(__ldg(src + static_cast<size_t>(c) * HW), 0.f);
+        const float y = fmaxf(x - 1e-5f, 0.f) / s_inv[c];
+        dst[static_cast<size_t>(c) * HW] = (y < fg) ? 0.f : y;
     }
 }
 

@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(512) plane_minmax_partial_kernel(const float* 
         const bool vec = ((HW & 3) == 0);
         if (vec) {
             const float4* s4 = reinterpret_cast<const float4*>(src);
+#pragma unroll 4
             for (int i = (begin >> 2) + threadIdx.x; i < (end >> 2); i += blockDim.x) {
                 const float4 x = __ldg(s4 + i);
                 const float e[4] = {fmaxf(x.x, 0.f), fmaxf(x.y, 0.f), fmaxf(x.z, 0.f), fmaxf(x.w, 0.f)};
@@ -470,14 +471,23 @@ __global__ void __launch_bounds__(128) seed_pixel_kernel(const float* __restrict
     float best = bg * s_lab[0];
     int arg = 0;
     dst[0] = bg;
-    for (int c = 1; c < C; ++c) {
-        float v = fmaxf(__ldg(src + static_cast<size_t>(c) * HW), 0.f);
-        const float lo = s_lo[c], hi = s_hi[c];
-        if (v < lo + 1e-5f) v = 0.f;
-        v = (v - lo - 1e-5f) / (hi - lo + 1e-5f);
-        dst[static_cast<size_t>(c) * HW] = v;
-        const float s = v * s_lab[c];
-        if (s > best) { best = s; arg = c; }
+    for (int c0 = 1; c0 < C; c0 += 8) {                       // eight independent loads in flight
+        float x[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = (c0 + j < C) ? __ldg(src + static_cast<size_t>(c0 + j) * HW) : 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = c0 + j;
+            if (c < C) {
+                float v = fmaxf(x[j], 0.f);
+                const float lo = s_lo[c], hi = s_hi[c];
+                if (v < lo + 1e-5f) v = 0.f;
+                v = (v - lo - 1e-5f) / (hi - lo + 1e-5f);
+                dst[static_cast<size_t>(c) * HW] = v;
+                const float s = v * s_lab[c];
+                if (s > best) { best = s; arg = c; }
+            }
+        }
     }
     pseudo[n * HW + q] = arg;
 }

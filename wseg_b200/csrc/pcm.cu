@@ -116,17 +116,23 @@ __global__ void __launch_bounds__(128) pcm_prep_cam_kernel(const float* __restri
     if (q < ncol) {
         const int g = q >> 3, e = q & 7;
         const int G = ncol >> 3;
-        for (int c = 0; c < kCamRows; ++c) {
-            float hi = 0.f, lo = 0.f;
-            if (live && c < C) {
-                const float v = __ldg(src + static_cast<size_t>(c) * HW);
-                hi = __half2float(__float2half_rn(v));
-                lo = v - hi;
-            } else if (live && c == C) {
-                hi = 1.f;
+        for (int c0 = 0; c0 < kCamRows; c0 += 8) {            // eight independent loads in flight
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = (live && c0 + j < C) ? __ldg(src + static_cast<size_t>(c0 + j) * HW) : 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int c = c0 + j;
+                float hi = 0.f, lo = 0.f;
+                if (live && c < C) {
+                    hi = __half2float(__float2half_rn(v[j]));
+                    lo = v[j] - hi;
+                } else if (live && c == C) {
+                    hi = 1.f;
+                }
+                s_blk[((0 * G + g) * kCamRows + c) * 8 + e] = __half_as_ushort(__float2half_rn(hi));
+                s_blk[((1 * G + g) * kCamRows + c) * 8 + e] = __half_as_ushort(__float2half_rn(lo));
             }
-            s_blk[((0 * G + g) * kCamRows + c) * 8 + e] = __half_as_ushort(__float2half_rn(hi));
-            s_blk[((1 * G + g) * kCamRows + c) * 8 + e] = __half_as_ushort(__float2half_rn(lo));
         }
     }
     __syncthreads();
@@ -465,15 +471,27 @@ __global__ void __launch_bounds__(128) pcm_bwd_prep_kernel(const float* __restri
         const float invd = 1.f / dsum[static_cast<size_t>(n) * HWpj + p];
         const size_t base = static_cast<size_t>(n) * C * HW + p;
         float delta = 0.f;
-        for (int c = 0; c < C; ++c) {
-            const float cm = __ldg(cam + base + static_cast<size_t>(c) * HW);
-            const float g = __ldg(gout + base + static_cast<size_t>(c) * HW);
-            const float o = __ldg(out + base + static_cast<size_t>(c) * HW);
-            delta = fmaf(o, g, delta);
-            const float gs = g * invd;
-            bnd += fabsf(gs);
-            s_u[c][px] = gs;      s_v[c][px] = cm;
-            s_u[C + c][px] = cm;  s_v[C + c][px] = gs;
+        for (int c0 = 0; c0 < C; c0 += 8) {                   // 24 independent loads in flight
+            float cm[8], g[8], o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const bool ok = c0 + j < C;
+                const size_t off = base + static_cast<size_t>(c0 + j) * HW;
+                cm[j] = ok ? __ldg(cam + off) : 0.f;
+                g[j] = ok ? __ldg(gout + off) : 0.f;
+                o[j] = ok ? __ldg(out + off) : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int c = c0 + j;
+                if (c < C) {
+                    delta = fmaf(o[j], g[j], delta);
+                    const float gs = g[j] * invd;
+                    bnd += fabsf(gs);
+                    s_u[c][px] = gs;        s_v[c][px] = cm[j];
+                    s_u[C + c][px] = cm[j]; s_v[C + c][px] = gs;
+                }
+            }
         }
         const float dj = delta * invd;
         bnd += fabsf(dj);

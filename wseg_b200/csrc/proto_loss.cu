@@ -163,10 +163,14 @@ __global__ void __launch_bounds__(1024) proto_finalize_kernel(const float* __res
     bitonic_desc<true>(s_keys, s_pos, npad);
     for (int t = threadIdx.x; t < k; t += blockDim.x)
         sel_idx[c * k + t] = static_cast<int32_t>(0xFFFFFFFFu - static_cast<uint32_t>(s_keys[t] & 0xFFFFFFFFull));
-    // weight sum (fixed order: thread 0 walks the sorted list)
+    // selected weights into shared memory (one load per thread), then a fixed-order sum by thread 0
+    float* s_w = reinterpret_cast<float*>(s_keys);             // the keys are no longer needed: reuse as k floats
+    __syncthreads();
+    for (int t = threadIdx.x; t < k; t += blockDim.x) s_w[t] = cand_val[c * n_cand + s_pos[t]];
+    __syncthreads();
     if (threadIdx.x == 0) {
         float wsum = 0.f;
-        for (int t = 0; t < k; ++t) wsum += cand_val[c * n_cand + s_pos[t]];
+        for (int t = 0; t < k; ++t) wsum += s_w[t];
         s_scale = wsum;
     }
     __syncthreads();
@@ -176,9 +180,14 @@ __global__ void __launch_bounds__(1024) proto_finalize_kernel(const float* __res
     int slot = 0;
     for (int d = threadIdx.x; d < D; d += blockDim.x, ++slot) {
         float acc = 0.f;
-        for (int t = 0; t < k; ++t) {
-            const uint32_t pos = s_pos[t];
-            acc = fmaf(cand_val[c * n_cand + pos], __ldg(cand_fea + (static_cast<size_t>(c) * n_cand + pos) * D + d), acc);
+        for (int t0 = 0; t0 < k; t0 += 8) {                   // eight independent loads in flight, fixed order of adds
+            float fv[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                fv[j] = (t0 + j < k) ? __ldg(cand_fea + (static_cast<size_t>(c) * n_cand + s_pos[t0 + j]) * D + d) : 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (t0 + j < k) acc = fmaf(s_w[t0 + j], fv[j], acc);
         }
         acc /= wsum;
         mine[slot] = acc;
@@ -246,12 +255,44 @@ constexpr int kNceSlots = 48;
 constexpr int kSlotHalf = 24;
 static_assert(kNcePix * kNceGroups == kNceThreads, "thread mapping");
 
+// 48 x D prototype values into shared memory, eight independent loads per thread in flight (a rolled loop of
+// dependent load->store pairs cost 48 L2 latencies, ~20 us, in both kernels)
 __device__ __forceinline__ void nce_load_protos(const NceView& V, float* s_proto, int C, int D) {
-    for (int i = threadIdx.x; i < kNceSlots * D; i += blockDim.x) {
-        const int slot = i / D, d = i - slot * D;
-        const int c = slot % kSlotHalf;
-        const float* src = slot < kSlotHalf ? V.proto_own : V.proto_oth;
-        s_proto[slot * (D + 1) + d] = c < C ? __ldg(src + c * D + d) : 0.f;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        for (int s0 = 0; s0 < kNceSlots; s0 += 8) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int slot = s0 + j, c = slot % kSlotHalf;
+                const float* src = slot < kSlotHalf ? V.proto_own : V.proto_oth;
+                v[j] = c < C ? __ldg(src + c * D + d) : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s_proto[(s0 + j) * (D + 1) + d] = v[j];
+        }
+    }
+}
+
+// x tile of kNcePix consecutive loss pixels: every thread issues its D/8 loads at once (one memory latency instead of
+// D dependent ones); for a fixed channel the pixels are contiguous in memory (they may straddle two images)
+__device__ __forceinline__ void nce_load_x(const NceView& V, float* s_x, int p0, int D, int HW, int P) {
+    const int pix = threadIdx.x & (kNcePix - 1), d0 = threadIdx.x / kNcePix;      // thread (pix, d0) takes d0, d0+8, ...
+    const int p = p0 + pix;
+    const bool live = p < P;
+    const int n = live ? p / HW : 0, q = live ? p - n * HW : 0;
+    const float* src = V.x + static_cast<size_t>(n) * D * HW + q;
+    for (int d = d0; d < D; d += 8 * kNceGroups) {                                 // D % 32 == 0
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int dd = d + j * kNceGroups;
+            v[j] = (live && dd < D) ? __ldg(src + static_cast<size_t>(dd) * HW) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int dd = d + j * kNceGroups;
+            if (dd < D) s_x[dd * kNcePix + pix] = v[j];
+        }
     }
 }
 
@@ -262,28 +303,23 @@ __global__ void __launch_bounds__(kNceThreads) nce_pixel_kernel(NceParams prm) {
     const int C = prm.C, D = prm.D, HW = prm.HW, P = prm.P;
     float* s_proto = s_dyn;                                   // [48][D+1]
     float* s_sc = s_dyn + kNceSlots * (D + 1);                // [kNcePix][49]
+    float* s_x = s_sc + kNcePix * 49 + kNcePix * kNceGroups * 4;   // [D][kNcePix] features of the CTA's pixels
     nce_load_protos(V, s_proto, C, D);
+    nce_load_x(V, s_x, blockIdx.x * kNcePix, D, HW, P);
     __syncthreads();
     const int pix = threadIdx.x & (kNcePix - 1), grp = threadIdx.x / kNcePix;
     const int p = blockIdx.x * kNcePix + pix;
     float inv = 0.f;
     if (p < P) {
-        const int n = p / HW, q = p - n * HW;
-        const float* xp = V.x + static_cast<size_t>(n) * D * HW + q;
         const float* pr = s_proto + (grp * 6) * (D + 1);
         float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         float ss = 0.f;
-        for (int d0 = 0; d0 < D; d0 += 8) {               // batches of 8 independent loads (D % 8 == 0)
-            float xb[8];
+#pragma unroll 4
+        for (int d = 0; d < D; ++d) {
+            const float xv = s_x[d * kNcePix + pix];
+            ss = fmaf(xv, xv, ss);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) xb[e] = __ldg(xp + static_cast<size_t>(d0 + e) * HW);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const float xv = xb[e];
-                ss = fmaf(xv, xv, ss);
-#pragma unroll
-                for (int j = 0; j < 6; ++j) acc[j] = fmaf(xv, pr[j * (D + 1) + d0 + e], acc[j]);
-            }
+            for (int j = 0; j < 6; ++j) acc[j] = fmaf(xv, pr[j * (D + 1) + d], acc[j]);
         }
         inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);          // F.normalize
 #pragma unroll
@@ -399,7 +435,9 @@ __global__ void __launch_bounds__(kNceThreads) nce_grad_kernel(NceParams prm) {
     float* s_proto = s_dyn;                                   // [48][D+1]
     float* s_coef = s_dyn + kNceSlots * (D + 1);              // [kNcePix][49]: d loss / d score per slot (times 1/T)
     __shared__ float s_qdq[kNcePix], s_scale[kNcePix];
+    float* s_x = s_coef + kNcePix * 49 + kNcePix * kNceGroups * 4;  // [D][kNcePix]
     nce_load_protos(V, s_proto, C, D);
+    nce_load_x(V, s_x, blockIdx.x * kNcePix, D, HW, P);
     __shared__ int s_present;
     if (threadIdx.x == 0) {
         int pres = 0;
@@ -501,26 +539,18 @@ __global__ void __launch_bounds__(kNceThreads) nce_grad_kernel(NceParams prm) {
         for (int i = 0; i < kNceSlots; ++i) coef[i] = s_coef[pix * 49 + i];
         const float qdq = s_qdq[pix], inv = s_scale[pix];
         const float gs = prm.grad_scale ? prm.grad_scale[0] : 1.f;
-        const float* xp = V.x + static_cast<size_t>(n) * D * HW + q;
         float* gp = V.grad_x + static_cast<size_t>(n) * D * HW + q;
-        // channel d = grp + 8*i: the 16 pixels of a CTA are contiguous in memory for a fixed d.  The order of the 42
-        // terms matches the previous kernel: own c=0, other c=0, own c=1, ...
-        for (int d0 = grp; d0 < D; d0 += 4 * kNceGroups) {          // D % 32 == 0: 4 channels per batch
-            float xb[4];
+        // channel d = grp + 8*i: the 16 pixels of a CTA are contiguous in memory for a fixed d.  Term order: own c=0,
+        // other c=0, own c=1, ...
+        for (int d = grp; d < D; d += kNceGroups) {
+            float dq = 0.f;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) xb[e] = __ldg(xp + static_cast<size_t>(d0 + e * kNceGroups) * HW);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int d = d0 + e * kNceGroups;
-                float dq = 0.f;
-#pragma unroll
-                for (int c = 0; c < kNceMaxC; ++c) {
-                    dq = fmaf(coef[c], s_proto[c * (D + 1) + d], dq);
-                    dq = fmaf(coef[kSlotHalf + c], s_proto[(kSlotHalf + c) * (D + 1) + d], dq);
-                }
-                const float qd = xb[e] * inv;
-                gp[static_cast<size_t>(d) * HW] = (dq - qd * qdq) * inv * gs;
+            for (int c = 0; c < kNceMaxC; ++c) {
+                dq = fmaf(coef[c], s_proto[c * (D + 1) + d], dq);
+                dq = fmaf(coef[kSlotHalf + c], s_proto[(kSlotHalf + c) * (D + 1) + d], dq);
             }
+            const float qd = s_x[d * kNcePix + pix] * inv;
+            gp[static_cast<size_t>(d) * HW] = (dq - qd * qdq) * inv * gs;
         }
     }
     if (threadIdx.x < 32) {
@@ -650,7 +680,8 @@ extern "C" int wsegk_contrast_loss_fwd_bwd(const float* x1, const float* x2, con
     const long long P = static_cast<long long>(N) * h * w;
     WSEGK_REQUIRE(P <= (1 << 17), WSEGK_ERR_BAD_SHAPE,
                   "contrast_loss_fwd_bwd: P=%lld pixels exceeds the pairwise mining limit of 131072", P);
-    const size_t proto_smem = (static_cast<size_t>(kNceSlots) * (D + 1) + kNcePix * 49 + kNcePix * kNceGroups * 4) * sizeof(float);
+    const size_t proto_smem = (static_cast<size_t>(kNceSlots) * (D + 1) + kNcePix * 49 + kNcePix * kNceGroups * 4 +
+                               static_cast<size_t>(D) * kNcePix) * sizeof(float);
     WSEGK_REQUIRE(proto_smem <= 200 * 1024, WSEGK_ERR_BAD_SHAPE, "contrast_loss_fwd_bwd: D too large");
     const NceLayout L = nce_layout(N, C, h, w);
     WSEGK_REQUIRE(workspace_bytes >= L.total, WSEGK_ERR_WORKSPACE_TOO_SMALL,
