@@ -409,35 +409,43 @@ pcm_fwd_kernel(const uint8_t* __restrict__ fa_hi, const uint8_t* __restrict__ fa
 }
 
 // out[n,c,j] = (sum_sp hi[c] + lo[c]) / (sum_sp colsum + 1e-5)
-__global__ void __launch_bounds__(128) pcm_fwd_finalize_kernel(const float* __restrict__ part,
+// One warp per 32 consecutive rows j: the 64-float partial rows are read coalesced (lane c gets hi[c] and lo[c]), a
+// 32x33 shared-memory tile transposes so the stores to the NCHW output run along j.
+__global__ void __launch_bounds__(256) pcm_fwd_finalize_kernel(const float* __restrict__ part,
                                                                float* __restrict__ out,
                                                                float* __restrict__ dsum, int C, int HW,
                                                                int HWpj, int nsplit) {
+    __shared__ float s_t[8][32][33];
+    __shared__ float s_d[8][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n = blockIdx.y;
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= HWpj) return;
-    float acc[kONum];
+    const int j0 = (blockIdx.x * 8 + warp) * 32;                 // HWpj is a multiple of 256
+    const size_t split_stride = static_cast<size_t>(HWpj) * kONum;
+    const float* base = part + (static_cast<size_t>(n) * nsplit * HWpj + j0) * kONum + lane;
+    for (int jj0 = 0; jj0 < 32; jj0 += 4) {                      // 4 rows x nsplit x 2 independent loads in flight
+        float hi[4] = {0.f, 0.f, 0.f, 0.f}, lo[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int sp = 0; sp < nsplit; ++sp) {
 #pragma unroll
-    for (int c = 0; c < kONum; ++c) acc[c] = 0.f;
-    for (int sp = 0; sp < nsplit; ++sp) {
-        const float4* src = reinterpret_cast<const float4*>(
-            part + ((static_cast<size_t>(n) * nsplit + sp) * HWpj + j) * kONum);
+            for (int r = 0; r < 4; ++r) {
+                const float* src = base + sp * split_stride + static_cast<size_t>(jj0 + r) * kONum;
+                hi[r] += __ldg(src);
+                lo[r] += __ldg(src + kCamRows);
+            }
+        }
 #pragma unroll
-        for (int v = 0; v < kONum / 4; ++v) {
-            float4 x = __ldg(src + v);
-            acc[4 * v] += x.x; acc[4 * v + 1] += x.y; acc[4 * v + 2] += x.z; acc[4 * v + 3] += x.w;
+        for (int r = 0; r < 4; ++r) {
+            const float d = __shfl_sync(0xffffffffu, hi[r], C) + 1e-5f;     // lane C holds the column sum
+            s_t[warp][lane][jj0 + r] = (hi[r] + lo[r]) / d;
+            if (lane == 0) s_d[warp][jj0 + r] = d;
         }
     }
-    float d = 0.f;
-#pragma unroll
-    for (int c = 0; c < kCamRows; ++c) if (c == C) d = acc[c];
-    d += 1e-5f;
-    dsum[static_cast<size_t>(n) * HWpj + j] = d;
-    if (j >= HW) return;
-    float* dst = out + static_cast<size_t>(n) * C * HW + j;
-#pragma unroll
-    for (int c = 0; c < kCamRows; ++c)
-        if (c < C) dst[static_cast<size_t>(c) * HW] = (acc[c] + acc[kCamRows + c]) / d;
+    __syncwarp();
+    const int j = j0 + lane;
+    dsum[static_cast<size_t>(n) * HWpj + j] = s_d[warp][lane];
+    if (j < HW) {
+        float* dst = out + static_cast<size_t>(n) * C * HW + j;
+        for (int c = 0; c < C; ++c) dst[static_cast<size_t>(c) * HW] = s_t[warp][c][lane];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -790,9 +798,20 @@ __global__ void __launch_bounds__(256) pcm_bwd_post_kernel(const float* __restri
             float g[4] = {0.f, 0.f, 0.f, 0.f}, fv[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) fv[j] = __ldg(fsrc + static_cast<size_t>(k0 + kk + j) * HW);
-            for (int sp = 0; sp < nsplit; ++sp) {
+            if (nsplit == 2) {                             // the common case: all 12 loads of the batch independent
+                float g2[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) g[j] += __ldg(gsrc + sp * split_stride + static_cast<size_t>(k0 + kk + j) * HWpj);
+                for (int j = 0; j < 4; ++j) {
+                    g[j] = __ldg(gsrc + static_cast<size_t>(k0 + kk + j) * HWpj);
+                    g2[j] = __ldg(gsrc + split_stride + static_cast<size_t>(k0 + kk + j) * HWpj);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) g[j] += g2[j];
+            } else {
+                for (int sp = 0; sp < nsplit; ++sp) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) g[j] += __ldg(gsrc + sp * split_stride + static_cast<size_t>(k0 + kk + j) * HWpj);
+                }
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) dot = fmaf(g[j] * unscale, fv[j], dot);
@@ -954,8 +973,8 @@ extern "C" int wsegk_pcm_fwd(const float* f, const float* cam_norm, float* cam_r
     prof_mark(0, stream);
     WSEGK_DISPATCH_WB(launch_fwd, precise, pl, N, stream);
     prof_mark(1, stream);
-    pcm_fwd_finalize_kernel<<<dim3(ceil_div(pl.HWpj, 128), N), 128, 0, stream>>>(pl.part, cam_rv, pl.dsum, C, pl.HW,
-                                                                                  pl.HWpj, pl.nsplit);
+    pcm_fwd_finalize_kernel<<<dim3(pl.HWpj / 256, N), 256, 0, stream>>>(pl.part, cam_rv, pl.dsum, C, pl.HW, pl.HWpj,
+                                                                         pl.nsplit);
     count_launches(4);
     WSEGK_CUDA_OK(cudaGetLastError());
     return WSEGK_OK;

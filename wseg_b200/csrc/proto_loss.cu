@@ -50,7 +50,11 @@ __device__ void bitonic_desc(unsigned long long* keys, uint32_t* pay, int n) {
 constexpr int kTopkThreads = 1024;
 constexpr int kTopkMaxK = 4096;
 
-// one CTA per class: radix-select the k largest keys over the whole batch plane, sort them, gather features
+// one CTA per class: radix-select the k largest keys over the whole batch plane, sort them, gather features.
+// kCached: the plane fits kTopkRegs keys per thread, so the keys are built once and live in registers; the select
+// passes then only touch shared memory (a pass that re-reads the plane costs a global-memory latency).
+constexpr int kTopkRegs = 8;
+template <bool kCached>
 __global__ void __launch_bounds__(kTopkThreads) proto_topk_kernel(const float* __restrict__ norm_cam,
                                                                   const float* __restrict__ f_proj,
                                                                   int pixel_offset, int k, int kpad,
@@ -64,9 +68,27 @@ __global__ void __launch_bounds__(kTopkThreads) proto_topk_kernel(const float* _
     __shared__ int s_need, s_done, s_count;
     const int c = blockIdx.x;
     const int P = N * HW;
-    auto value_at = [&](int i) {
+    auto key_of = [&](int i) {
         const int n = i / HW, q = i - n * HW;
-        return __ldg(norm_cam + (static_cast<size_t>(n) * C + c) * HW + q);
+        return topk_key(__ldg(norm_cam + (static_cast<size_t>(n) * C + c) * HW + q), static_cast<uint32_t>(i));
+    };
+    unsigned long long kreg[kTopkRegs];
+    if (kCached) {
+#pragma unroll
+        for (int j = 0; j < kTopkRegs; ++j) {
+            const int i = threadIdx.x + j * kTopkThreads;
+            kreg[j] = i < P ? key_of(i) : 0ull;
+        }
+    }
+    // visit every key of the plane: f(key)
+    auto for_each_key = [&](auto&& f) {
+        if (kCached) {
+#pragma unroll
+            for (int j = 0; j < kTopkRegs; ++j)
+                if (threadIdx.x + j * kTopkThreads < P) f(kreg[j]);
+        } else {
+            for (int i = threadIdx.x; i < P; i += blockDim.x) f(key_of(i));
+        }
     };
     if (threadIdx.x == 0) { s_prefix = 0ull; s_need = k; s_done = 0; s_count = 0; }
     int shift = 56;
@@ -75,10 +97,17 @@ __global__ void __launch_bounds__(kTopkThreads) proto_topk_kernel(const float* _
         for (int b = threadIdx.x; b < 256; b += blockDim.x) s_hist[b] = 0;
         __syncthreads();
         const unsigned long long prefix = s_prefix;
-        for (int i = threadIdx.x; i < P; i += blockDim.x) {
-            const unsigned long long key = topk_key(value_at(i), static_cast<uint32_t>(i));
-            if (pass == 0 || (key >> (shift + 8)) == prefix) atomicAdd(&s_hist[(key >> shift) & 255u], 1u);
-        }
+        // warp-aggregated histogram: CAM values share their sign/exponent byte, so plain shared-memory atomics would
+        // serialise thousands of increments on two or three bins in the first passes
+        for_each_key([&](unsigned long long key) {
+            const bool act = pass == 0 || (key >> (shift + 8)) == prefix;
+            const unsigned am = __ballot_sync(__activemask(), act);
+            if (act) {
+                const uint32_t bin = static_cast<uint32_t>(key >> shift) & 255u;
+                const unsigned peers = __match_any_sync(am, bin);
+                if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&s_hist[bin], static_cast<uint32_t>(__popc(peers)));
+            }
+        });
         __syncthreads();
         if (threadIdx.x < 32) {
             // warp 0 finds the bin holding the need-th largest key: lane l owns bins 255-8l .. 248-8l (descending),
@@ -116,18 +145,17 @@ __global__ void __launch_bounds__(kTopkThreads) proto_topk_kernel(const float* _
     const unsigned long long prefix = s_prefix;
     for (int i = threadIdx.x; i < kpad; i += blockDim.x) s_keys[i] = 0ull;
     __syncthreads();
-    for (int i = threadIdx.x; i < P; i += blockDim.x) {
-        const unsigned long long key = topk_key(value_at(i), static_cast<uint32_t>(i));
+    for_each_key([&](unsigned long long key) {
         if ((key >> shift) >= prefix) {
             const int slot = atomicAdd(&s_count, 1);
             if (slot < kpad) s_keys[slot] = key;
         }
-    }
+    });
     bitonic_desc<false>(s_keys, nullptr, kpad);
     for (int t = threadIdx.x; t < k; t += blockDim.x) {
         const unsigned long long key = s_keys[t];
         const uint32_t idx = 0xFFFFFFFFu - static_cast<uint32_t>(key & 0xFFFFFFFFull);
-        top_val[c * k + t] = value_at(static_cast<int>(idx));
+        top_val[c * k + t] = unordered_bits(static_cast<uint32_t>(key >> 32));     // the value the key was built from
         top_idx[c * k + t] = static_cast<int32_t>(idx) + pixel_offset;
     }
     // gather the (un-normalised) features of the selected pixels: top_fea[c][t][d] = f_proj[n][d][q]
@@ -638,10 +666,17 @@ extern "C" int wsegk_proto_topk_local(const float* norm_cam, const float* f_proj
     WSEGK_REQUIRE(P + pixel_offset < (1ll << 31), WSEGK_ERR_BAD_SHAPE, "proto_topk_local: pixel index overflow");
     const int kpad = next_pow2(k);
     const size_t smem = static_cast<size_t>(kpad) * sizeof(unsigned long long);
-    WSEGK_CUDA_OK(cudaFuncSetAttribute(proto_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(smem)));
-    proto_topk_kernel<<<C, kTopkThreads, smem, stream>>>(norm_cam, f_proj, pixel_offset, k, kpad, top_val, top_idx,
-                                                         top_fea, N, C, D, h * w);
+    if (P <= static_cast<long long>(kTopkRegs) * kTopkThreads) {
+        WSEGK_CUDA_OK(cudaFuncSetAttribute(proto_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(smem)));
+        proto_topk_kernel<true><<<C, kTopkThreads, smem, stream>>>(norm_cam, f_proj, pixel_offset, k, kpad, top_val,
+                                                                   top_idx, top_fea, N, C, D, h * w);
+    } else {
+        WSEGK_CUDA_OK(cudaFuncSetAttribute(proto_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(smem)));
+        proto_topk_kernel<false><<<C, kTopkThreads, smem, stream>>>(norm_cam, f_proj, pixel_offset, k, kpad, top_val,
+                                                                    top_idx, top_fea, N, C, D, h * w);
+    }
     count_launches(1);
     WSEGK_CUDA_OK(cudaGetLastError());
     return WSEGK_OK;
