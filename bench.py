@@ -92,15 +92,20 @@ class HotPath:
         view 2, the seed/prototype/NCE chain after both K2 forwards, and K1b on the two `cam` maps (which do not depend
         on the PCM).  Every intermediate is returned so nothing is recycled before the join."""
         ops, d = self.ops, self.d
-        cur = torch.cuda.current_stream(self.dev)
         if not hasattr(self, "_streams"):
-            self._streams = [torch.cuda.Stream(device=self.dev) for _ in range(3)]
-        s2, s3, s4 = self._streams
+            prio = int(os.environ.get("WSEG_BENCH_PRIO", "1"))
+            # the view-1 chain (K1a -> K2 fwd -> K1b -> K2 bwd) is the critical path: its stream gets the higher priority
+            self._streams = [torch.cuda.Stream(device=self.dev, priority=-1 if prio else 0)] + \
+                            [torch.cuda.Stream(device=self.dev) for _ in range(3)]
+        s1, s2, s3, s4 = self._streams
+        outer = torch.cuda.current_stream(self.dev)
         fork = torch.cuda.Event()
-        fork.record(cur)
-        for s in (s2, s3, s4):
+        fork.record(outer)
+        for s in (s1, s2, s3, s4):
             s.wait_event(fork)
         keep = []
+        cur = s1
+        torch.cuda.set_stream(s1)
 
         def k1b(name, size, gname):
             y, saved = ops.fullres_norm_fwd(d[name], d["label"], size)
@@ -147,8 +152,11 @@ class HotPath:
         # ---- view 1: K1b on cam_rv, then K2 backward
         g_rv1 = k1b("rv1_full", VIEW2, "g_rv1")
         gf1 = ops.pcm_backward(d["f1"], camn1, rv1, d["g_rv_down1"], ws1)
-        for e in (s2_done, s3_done, s4_done):
-            cur.wait_event(e)
+        s1_done = torch.cuda.Event()
+        s1_done.record(s1)
+        torch.cuda.set_stream(outer)
+        for e in (s1_done, s2_done, s3_done, s4_done):
+            outer.wait_event(e)
         return losses, gf1, gf2, g1, g2, (g_n1, g_rv1, g_n2, g_rv2), keep, (camn1, camn2, rv1, rv2, ws1, ws2)
 
 
