@@ -186,44 +186,73 @@ class GraphedStep:
 
 class E2EPath:
     """The same path through the public, reference-facing API (autograd operators + loss.contrast_terms), from PINNED
-    HOST buffers: every step copies the head-level inputs host->device, runs Net.forward's tail (K1a, K2, bilinear x8
-    to full resolution), the loss-side operators, backward, and reads the losses back to the host."""
+    HOST buffers: every step copies the path's inputs host->device, runs Net.forward's tail (K1a, K2, bilinear x8 to full
+    resolution), the loss-side operators and their backward, and reads the losses back to the host.  The device part
+    (public API calls, autograd included) is captured once in a CUDA graph and replayed; `--no-graph` runs it eagerly."""
 
-    def __init__(self, hp: HotPath):
+    # the path's inputs travel host -> device every step; the synthetic upstream gradients standing in for the rest of
+    # the loss (g_*) stay resident — they would be produced on the device
+    NAMES = ["cam1", "f1", "fproj1", "cam2", "f2", "fproj2", "label"]
+
+    def __init__(self, hp: HotPath, use_graph: bool):
         self.hp = hp
-        # the path's inputs travel host -> device every step; the synthetic upstream gradients standing in for the rest of
-        # the loss (g_*) stay resident — they would be produced on the device
-        self.names = ["cam1", "f1", "fproj1", "cam2", "f2", "fproj2", "label"]
-        self.h2d_bytes = sum(hp.host[k].numel() * 4 for k in self.names)
+        self.h2d_bytes = sum(hp.host[k].numel() * 4 for k in self.NAMES)
         self.out_host = torch.empty(10, dtype=torch.float32).pin_memory()
         self.d2h_bytes = 40
+        self.static = {k: torch.empty_like(hp.d[k]) for k in self.NAMES}
+        self.graph = None
+        self.mode = "eager"
+        if use_graph:
+            try:
+                side = torch.cuda.Stream(device=hp.dev)
+                side.wait_stream(torch.cuda.current_stream(hp.dev))
+                with torch.cuda.stream(side):
+                    for k in self.NAMES:
+                        self.static[k].copy_(hp.host[k], non_blocking=True)
+                    for _ in range(3):
+                        self._device_part()
+                torch.cuda.current_stream(hp.dev).wait_stream(side)
+                torch.cuda.synchronize(hp.dev)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self.result = self._device_part()
+                self.graph, self.mode = g, "cuda_graph"
+            except Exception as exc:
+                print(f"bench.py: e2e graph capture failed ({type(exc).__name__}: {exc}); running it eagerly", file=sys.stderr)
+                self.graph = None
 
-    def step(self):
+    def _device_part(self):
         from wseg_b200 import loss as L
         from wseg_b200 import ops
         hp = self.hp
-        dev = hp.dev
-        x = {k: hp.host[k].to(dev, non_blocking=True) for k in self.names}
-        for k in ("g_n1", "g_rv1", "g_n2", "g_rv2"):
-            x[k] = hp.d[k]
-        f1 = x["f1"].requires_grad_(True)
-        f2 = x["f2"].requires_grad_(True)
-        p1 = x["fproj1"].requires_grad_(True)
-        p2 = x["fproj2"].requires_grad_(True)
-        rv1 = ops.pcm(ops.cam_norm(x["cam1"]), f1)
-        rv2 = ops.pcm(ops.cam_norm(x["cam2"]), f2)
-        cam1_full = ops.bilinear_resize(x["cam1"].requires_grad_(True), VIEW1)        # Net.forward's tail (:57-59)
+        x = {k: v.detach() for k, v in self.static.items()}
+        leaves = {k: x[k].requires_grad_(True) for k in ("f1", "f2", "fproj1", "fproj2", "cam1", "cam2")}
+        rv1 = ops.pcm(ops.cam_norm(x["cam1"]), leaves["f1"])
+        rv2 = ops.pcm(ops.cam_norm(x["cam2"]), leaves["f2"])
+        cam1_full = ops.bilinear_resize(leaves["cam1"], VIEW1)                       # Net.forward's tail (:57-59)
         rv1_full = ops.bilinear_resize(rv1, VIEW1)
-        cam2_full = ops.bilinear_resize(x["cam2"].requires_grad_(True), VIEW2)
+        cam2_full = ops.bilinear_resize(leaves["cam2"], VIEW2)
         rv2_full = ops.bilinear_resize(rv2, VIEW2)
-        terms = L.contrast_terms(p1, rv1, p2, rv2, x["label"], BG_THRESHOLD, grid=hp.grid, group=hp.group)
+        terms = L.contrast_terms(leaves["fproj1"], rv1, leaves["fproj2"], rv2, x["label"], BG_THRESHOLD, grid=hp.grid,
+                                 group=hp.group, keys=(hp.key1, hp.key2))
         total = terms["loss_nce"]
         for t, size, gname in ((cam1_full, VIEW2, "g_n1"), (rv1_full, VIEW2, "g_rv1"), (cam2_full, None, "g_n2"),
                                (rv2_full, None, "g_rv2")):
-            total = total + (ops.fullres_norm(t, x["label"], size) * x[gname]).sum()
-        total.backward()
-        self.out_host.copy_(terms["losses_raw"].detach(), non_blocking=True)
-        return f1.grad
+            total = total + (ops.fullres_norm(t, x["label"], size) * hp.d[gname]).sum()
+        grads = torch.autograd.grad(total, list(leaves.values()))
+        return terms["losses_raw"].detach(), grads
+
+    def step(self):
+        hp = self.hp
+        for k in self.NAMES:
+            self.static[k].copy_(hp.host[k], non_blocking=True)
+        if self.graph is not None:
+            self.graph.replay()
+            losses = self.result[0]
+        else:
+            losses, _ = self._device_part()
+        self.out_host.copy_(losses, non_blocking=True)
+        return losses
 
 
 # ------------------------------------------------------------------------------------------------ helpers
@@ -467,7 +496,7 @@ def run_ours(args):
                      "note": "PCM flops / sustained bf16 peak + algorithmic bytes of K1a,K1b,K1c,K3,K4,K2 io / measured HBM"}
 
     # -------- end-to-end arm: host buffers, public API
-    e2e = E2EPath(hp)
+    e2e = E2EPath(hp, use_graph=not args.no_graph)
     e2e_ms, _ = time_steps(e2e.step, args.steps, args.warmup, dev, flush, barrier)
     t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -481,7 +510,7 @@ def run_ours(args):
             "clocks": clk.summary(), "gpu_launches": int(launches_per_step * args.steps),
             "gpu_launches_per_step": int(launches_per_step),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e.h2d_bytes,
-                    "d2h_bytes_per_step": e2e.d2h_bytes, "ms_per_step": float(t.item()) / args.steps,
+                    "d2h_bytes_per_step": e2e.d2h_bytes, "ms_per_step": float(t.item()) / args.steps, "launch": e2e.mode,
                     "api": "pinned host inputs (cam logits, f, f_proj, labels; both views) -> ops.cam_norm / ops.pcm / ops.bilinear_resize x8 / loss.contrast_terms / ops.fullres_norm through autograd, backward, losses -> host"},
             "roofline": roofline, "step_roofline": step_roofline, "wall_ms_per_step_incl_flush": wall_ms / args.steps}
 
@@ -496,6 +525,7 @@ def run_ours(args):
         # Tearing NCCL down while CUDA graphs that captured its kernels are alive hung at exit (r01, 2 GPUs): drop the
         # graph, drain, agree that everyone is done, and leave without the communicator destructor.
         del stepper
+        e2e.graph = None
         torch.cuda.synchronize(dev)
         dist.barrier()
         sys.stdout.flush()

@@ -312,6 +312,34 @@ __global__ void __launch_bounds__(256) fullres_bwd_kernel(const float* __restric
 // ---- glue: bilinear(align_corners) shrink of small maps (contrast_train.py:179-180) -----------------------------------
 // ATen's NCHW bilinear kernel parallelises over the OUTPUT PIXELS only and loops over N*C inside a thread: for
 // [8,128,56,56] -> 16x16 that is 256 threads and 0.3 ms.  One thread per output element here.
+// enlargement with ow % 4 == 0: four consecutive outputs of a row per thread, one 16-byte store (the x8 case writes
+// 135 MB per call and is bound by that store stream; the 12.5 KB source plane sits in L1)
+__global__ void __launch_bounds__(256) resize_fwd_vec4_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                              int planes, int H, int W, int oh, int ow) {
+    const float sy = oh > 1 ? static_cast<float>(H - 1) / static_cast<float>(oh - 1) : 0.f;
+    const float sx = ow > 1 ? static_cast<float>(W - 1) / static_cast<float>(ow - 1) : 0.f;
+    const int ow4 = ow >> 2, osz4 = oh * ow4;
+    for (int plane = blockIdx.y; plane < planes; plane += gridDim.y) {
+        const float* src = x + static_cast<size_t>(plane) * H * W;
+        float4* dst = reinterpret_cast<float4*>(y + static_cast<size_t>(plane) * oh * ow);
+        for (int o4 = blockIdx.x * blockDim.x + threadIdx.x; o4 < osz4; o4 += gridDim.x * blockDim.x) {
+            const int oy = o4 / ow4, ox0 = (o4 - oy * ow4) << 2;
+            int y0, y1; float hy0, hy1;
+            src_coord(oy, sy, H, y0, y1, hy0, hy1);
+            const float* r0 = src + y0 * W;
+            const float* r1 = src + y1 * W;
+            float v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                int x0, x1; float wx0, wx1;
+                src_coord(ox0 + j, sx, W, x0, x1, wx0, wx1);
+                v[j] = hy0 * (wx0 * __ldg(r0 + x0) + wx1 * __ldg(r0 + x1)) + hy1 * (wx0 * __ldg(r1 + x0) + wx1 * __ldg(r1 + x1));
+            }
+            dst[o4] = make_float4(v[0], v[1], v[2], v[3]);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) resize_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int planes,
                                                          int H, int W, int oh, int ow) {
     const float sy = oh > 1 ? static_cast<float>(H - 1) / static_cast<float>(oh - 1) : 0.f;
@@ -594,8 +622,13 @@ extern "C" int wsegk_bilinear_resize_fwd(const float* x, float* y, int planes, i
     if (int rc = check_device()) return rc;
     WSEGK_REQUIRE(x && y, WSEGK_ERR_NULL, "bilinear_resize_fwd: null pointer");
     if (int rc = resize_check("bilinear_resize_fwd", planes, H, W, oh, ow)) return rc;
-    const dim3 grid(std::min(ceil_div(oh * ow, 256), 1024), std::min(planes, 32768));
-    resize_fwd_kernel<<<grid, 256, 0, stream>>>(x, y, planes, H, W, oh, ow);
+    if ((ow & 3) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 && oh * ow >= 4096) {
+        const dim3 grid(std::min(ceil_div(oh * (ow >> 2), 256), 1024), std::min(planes, 32768));
+        resize_fwd_vec4_kernel<<<grid, 256, 0, stream>>>(x, y, planes, H, W, oh, ow);
+    } else {
+        const dim3 grid(std::min(ceil_div(oh * ow, 256), 1024), std::min(planes, 32768));
+        resize_fwd_kernel<<<grid, 256, 0, stream>>>(x, y, planes, H, W, oh, ow);
+    }
     count_launches(1);
     WSEGK_CUDA_OK(cudaGetLastError());
     return WSEGK_OK;

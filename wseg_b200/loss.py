@@ -49,10 +49,12 @@ def reference_rng_keys(pl1: torch.Tensor, pl2: torch.Tensor, rng: Union[int, _py
 def contrast_terms(f_proj1: torch.Tensor, cam_rv1_down: torch.Tensor, f_proj2: torch.Tensor,
                    cam_rv2_down: torch.Tensor, label: torch.Tensor, bg_threshold: float,
                    grid: Optional[Tuple[int, int]] = None, rng: Union[int, _pyrandom.Random, None] = None,
-                   mining_seed: int = 0, group=None, want_mined: bool = False) -> Dict[str, torch.Tensor]:
+                   mining_seed: int = 0, group=None, want_mined: bool = False,
+                   keys: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
     """contrast_train.py:176-392.  ``label``: [N,21] (or [N,21,1,1]) with background = 1.
-    ``rng``: None -> device-hash mining keys (no host sync); an int / ``random.Random`` -> reproduce the reference's
-    Python-RNG draws.  ``group``: process group over which prototypes are whole-batch (data parallel)."""
+    ``rng``: None -> hash mining keys (no host sync); an int / ``random.Random`` -> reproduce the reference's
+    Python-RNG draws.  ``keys``: two int32 [P] device tensors to use as mining keys instead (nothing is created on the host,
+    so the call can be captured in a CUDA graph).  ``group``: process group over which prototypes are whole-batch (data parallel)."""
     if grid is None:
         grid = tuple(f_proj2.shape[-2:])
     if tuple(f_proj1.shape[-2:]) != tuple(grid):
@@ -65,7 +67,9 @@ def contrast_terms(f_proj1: torch.Tensor, cam_rv1_down: torch.Tensor, f_proj2: t
     norm2, pl2 = ops.seed_labels(c2, label, bg_threshold)
     proto1, ti1 = ops.prototypes(norm1, f1, group=group)
     proto2, ti2 = ops.prototypes(norm2, f2, group=group)
-    if rng is None:
+    if keys is not None:            # precomputed device-resident mining keys (e.g. when the step is captured in a CUDA graph)
+        key1, key2 = keys
+    elif rng is None:
         p = pl1.numel()
         key1 = ops.hash_keys(p, 2 * mining_seed + 1, pl1.device)
         key2 = ops.hash_keys(p, 2 * mining_seed + 2, pl1.device)
