@@ -104,6 +104,35 @@ int wsegk_bilinear_resize_fwd(const float* x, float* y, int planes, int H, int W
 int wsegk_bilinear_resize_bwd(const float* grad_y, float* grad_x, int planes, int H, int W, int oh, int ow,
                               wsegk_stream_t stream);
 
+/* ---- auxiliary SEAM losses ------------------------------------------------------------------------
+ * select_kth: per row of x [rows,len], the k-th largest (largest=1) or smallest (0) value BY VALUE (radix select, no
+ * sort).  sel [rows,4] = {threshold t, sum of the k selected values, sum of max(selected,0), number of ties taken};
+ * idx_cut [rows]: element i with value v is selected iff v is strictly beyond t, or v == t and i < idx_cut[row]. */
+int wsegk_select_kth(const float* x, int rows, int len, int k, int largest, float* sel, int32_t* idx_cut,
+                     wsegk_stream_t stream);
+/* contrast_train.py:142/155 + 159/160: gap = adaptive_avg_pool2d(cam), loss = multilabel_soft_margin(gap[:,1:], label[:,1:]).
+ * cam [N,C,H,W], label [N,C] -> gap [N,C], dgap [N,C] (d loss / d gap, kept for the backward), loss [1]. */
+int wsegk_gap_mlsm_fwd(const float* cam, const float* label, float* gap, float* dgap, float* loss, int N, int C, int H,
+                       int W, void* workspace, size_t workspace_bytes, wsegk_stream_t stream);
+int wsegk_gap_mlsm_bwd(const float* dgap, const float* grad_loss, float* grad_cam, int N, int C, int H, int W,
+                       wsegk_stream_t stream);
+/* contrast_train.py:16-25 on (cam_rv*label)[:,1:]: m [N,H*W] = per-pixel class maximum, arg = its class, then the
+ * bottom H*W/4 per image by select_kth; loss = sum(sel[:,2]) / (k*N).  Backward: dense grad_x [N,C,H,W]. */
+int wsegk_minpool_fwd(const float* x, const float* label, float* m, int32_t* arg, float* sel, int32_t* idx_cut, int N,
+                      int C, int H, int W, wsegk_stream_t stream);
+int wsegk_minpool_bwd(const float* m, const int32_t* arg, const float* sel, const int32_t* idx_cut, const float* label,
+                      const float* grad_loss, float* grad_x, int N, int C, int H, int W, wsegk_stream_t stream);
+/* contrast_train.py:163-172 on the four normalised maps [N,C,h,w] (K1b outputs): losses[0] = loss_er,
+ * losses[1] = loss_ecr; e1,e2 [N,C*h*w] and sel/cut (see select_kth) are kept for the backward, which writes the
+ * gradients of both losses w.r.t. n1, n2 (ER) and rv1, rv2 (ECR). */
+int wsegk_er_ecr_fwd(const float* n1, const float* n2, const float* rv1, const float* rv2, float* e1, float* e2,
+                     float* sel1, int32_t* cut1, float* sel2, int32_t* cut2, float* losses, int N, int C, int h, int w,
+                     void* workspace, size_t workspace_bytes, wsegk_stream_t stream);
+int wsegk_er_ecr_bwd(const float* n1, const float* n2, const float* rv1, const float* rv2, const float* sel1,
+                     const int32_t* cut1, const float* sel2, const int32_t* cut2, const float* grad_er,
+                     const float* grad_ecr, float* gn1, float* gn2, float* grv1, float* grv2, int N, int C, int h, int w,
+                     wsegk_stream_t stream);
+
 /* K3 — replaces contrast_train.py:199-209 / 229-241.  Per class, the k largest norm_cam values over the whole
  * batch (value desc, then lowest flat index n*h*w + y*w + x), and the value-weighted feature sums.
  *   proto_topk_local : norm_cam [N,C,h,w], f_proj [N,D,h,w] -> top_val [C,k], top_idx [C,k] (int32, local

@@ -381,3 +381,82 @@ def test_bilinear_resize_matches_aten(cuda_dev, shape, size):
     yb.backward(gy)
     assert float((ya - yb).abs().max()) <= 1e-6
     assert rel_max(a.grad, b.grad) <= 1e-5          # an enlargement's backward sums ~64 terms per input
+
+
+# ------------------------------------------------------------------------------------------------ auxiliary SEAM losses
+@pytest.mark.parametrize("rows,ln,k,largest,ties", [(8, 200704, 50176, False, False), (8, 344064, 68812, True, False),
+                                                    (3, 5000, 1, True, False), (3, 5000, 5000, False, False),
+                                                    (4, 4097, 1000, True, True), (2, 70000, 30000, False, True)])
+def test_select_kth_matches_topk(cuda_dev, rows, ln, k, largest, ties):
+    """Selection by value equals torch.topk in threshold, sum of the selected values and (with the index cut for ties)
+    in the selected count."""
+    g = torch.Generator().manual_seed(ln + k)
+    x = torch.randn(rows, ln, generator=g)
+    if ties:
+        x = torch.round(x * 4) / 4                  # a few dozen distinct values: heavy ties at the threshold
+    x = x.to(cuda_dev)
+    sel, cut = ops.select_kth(x, k, largest)
+    tv = torch.topk(x, k, dim=-1, largest=largest)[0]
+    kth = tv[:, -1]
+    assert torch.equal(sel[:, 0], kth)
+    np.testing.assert_allclose(sel[:, 1].cpu().numpy(), tv.double().sum(-1).cpu().numpy(), rtol=2e-5, atol=1e-3)
+    np.testing.assert_allclose(sel[:, 2].cpu().numpy(), tv.clamp_min(0).double().sum(-1).cpu().numpy(), rtol=2e-5, atol=1e-3)
+    idx = torch.arange(ln, device=cuda_dev).expand(rows, ln)
+    beyond = (x > kth[:, None]) if largest else (x < kth[:, None])
+    chosen = beyond | ((x == kth[:, None]) & (idx < cut[:, None]))
+    assert torch.equal(chosen.sum(-1), torch.full((rows,), k, device=cuda_dev))
+
+
+def _aux_inputs(n, hw1, hw2, seed, dev):
+    a = {k: v.to(dev) for k, v in synth.head_outputs(n, hw1, seed=seed * 10 + 1).items()}
+    b = {k: v.to(dev) for k, v in synth.head_outputs(n, hw2, seed=seed * 10 + 2).items()}
+    lab = synth.label_with_bg(synth.labels(n, seed)).to(dev)
+    return a, b, lab
+
+
+@pytest.mark.parametrize("n,hw", [(2, (192, 192)), (8, (448, 448)), (3, (70, 45))])
+def test_cls_and_minpool_losses_vs_oracle(cuda_dev, n, hw):
+    a, _, lab = _aux_inputs(n, hw, (128, 128), seed=n, dev=cuda_dev)
+    lab4 = lab.reshape(n, -1, 1, 1)
+    # classification: contrast_train.py:142,159
+    x = a["cam"].clone().requires_grad_(True)
+    mine = ops.cls_loss(x, lab)
+    mine.backward()
+    xr = a["cam"].clone().requires_grad_(True)
+    ref = F.multilabel_soft_margin_loss(F.adaptive_avg_pool2d(xr, (1, 1))[:, 1:], lab4[:, 1:])
+    ref.backward()
+    assert float(mine) == pytest.approx(float(ref), rel=1e-5)
+    assert rel_max(x.grad, xr.grad) <= 1e-4
+    # min-pool: contrast_train.py:16-25,143
+    y = a["cam_rv"].clone().requires_grad_(True)
+    mine = ops.min_pool_loss(y, lab)
+    mine.backward()
+    yr = a["cam_rv"].clone().requires_grad_(True)
+    ref = R.min_pool_loss((yr * lab4)[:, 1:])
+    ref.backward()
+    assert float(mine) == pytest.approx(float(ref), rel=1e-5)
+    assert rel_max(y.grad, yr.grad) <= 1e-5
+
+
+@pytest.mark.parametrize("n,hw1,hw2", [(2, (192, 192), (128, 128)), (8, (448, 448), (128, 128)), (3, (96, 80), (40, 24))])
+def test_er_ecr_losses_vs_oracle(cuda_dev, n, hw1, hw2):
+    a, b, lab = _aux_inputs(n, hw1, hw2, seed=n + 1, dev=cuda_dev)
+    lab4 = lab.reshape(n, -1, 1, 1)
+    maps = [ops.fullres_norm(a["cam"], lab, hw2), ops.fullres_norm(b["cam"], lab, None),
+            ops.fullres_norm(a["cam_rv"], lab, hw2), ops.fullres_norm(b["cam_rv"], lab, None)]
+    mine_in = [t.detach().clone().requires_grad_(True) for t in maps]
+    er, ecr = ops.er_ecr_loss(*mine_in)
+    (er + ecr).backward()
+    n1, n2, rv1, rv2 = [t.detach().clone().requires_grad_(True) for t in maps]
+    ref_er = torch.mean(torch.abs(n1[:, 1:] - n2[:, 1:]))                                        # :163
+    n1b, n2b = R.with_bg_channel(n1), R.with_bg_channel(n2)                                      # :165-166
+    k = int(21 * hw2[0] * hw2[1] * 0.2)
+    e1 = torch.abs(R.keep_argmax_fg(n2b.detach()) - rv1)                                         # :168
+    e2 = torch.abs(R.keep_argmax_fg(n1b.detach()) - rv2)                                         # :169
+    ref_ecr = (torch.mean(torch.topk(e1.reshape(n, -1), k=k, dim=-1)[0])
+               + torch.mean(torch.topk(e2.reshape(n, -1), k=k, dim=-1)[0]))                      # :170-172
+    (ref_er + ref_ecr).backward()
+    assert float(er) == pytest.approx(float(ref_er), rel=1e-5)
+    assert float(ecr) == pytest.approx(float(ref_ecr), rel=1e-5)
+    for mine_t, ref_t, name in zip(mine_in, (n1, n2, rv1, rv2), ("n1", "n2", "rv1", "rv2")):
+        assert rel_max(mine_t.grad, ref_t.grad) <= 1e-5, name

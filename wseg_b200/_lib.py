@@ -31,6 +31,13 @@ _SIGNATURES = {
                                        c_size_t, _P]),
     "wsegk_bilinear_resize_fwd": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "wsegk_bilinear_resize_bwd": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
+    "wsegk_select_kth": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, _P]),
+    "wsegk_gap_mlsm_fwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
+    "wsegk_gap_mlsm_bwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P]),
+    "wsegk_minpool_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
+    "wsegk_minpool_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
+    "wsegk_er_ecr_fwd": (c_int, [_P] * 11 + [c_int] * 4 + [_P, c_size_t, _P]),
+    "wsegk_er_ecr_bwd": (c_int, [_P] * 14 + [c_int] * 4 + [_P]),
     "wsegk_seed_labels_fwd": (c_int, [_P, _P, c_float, _P, _P, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
     "wsegk_proto_topk_local": (c_int, [_P, _P, c_int, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P,
                                        c_size_t, _P]),

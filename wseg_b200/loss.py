@@ -3,8 +3,9 @@
 ``contrast_step_loss`` takes what ``Net.forward`` returns for both views plus the image-level labels and
 returns the 8 scalars the reference logs (contrast_train.py:111-118).  The hot path — label-masked CAM
 normalisation (K1b), seed labels (K1c), per-class top-k prototypes (K3) and the six NCE terms with hard-pixel
-mining, forward and backward fused (K4) — runs in the wsegk CUDA kernels; the two bilinear shrinks of view 1
-(:179-180) and the auxiliary SEAM losses (:142-144,156,159-174; SURVEY.md §8f-1 "next") stay in PyTorch.
+mining, forward and backward fused (K4) — runs in the wsegk CUDA kernels, and so do the two bilinear shrinks of view 1
+(:179-180) and the auxiliary SEAM losses (:142-144,156,159-174): classification (GAP + multilabel soft
+margin), min-pool, ER and ECR, the two top-k's done by value with a radix select.
 """
 from __future__ import annotations
 
@@ -90,24 +91,6 @@ def contrast_terms(f_proj1: torch.Tensor, cam_rv1_down: torch.Tensor, f_proj2: t
     return out
 
 
-# ---- auxiliary SEAM losses, PyTorch (contrast_train.py:16-32,142-144,156,159-174) ------------------
-def _min_pool_loss(x: torch.Tensor) -> torch.Tensor:
-    n, c, h, w = x.shape
-    k = h * w // 4
-    low = torch.topk(x.max(dim=1)[0].reshape(n, -1), k=k, dim=-1, largest=False)[0]
-    return F.relu(low).sum() / (k * n)
-
-
-def _argmax_fg_only(x: torch.Tensor) -> torch.Tensor:
-    fg = x[:, 1:]
-    peak = fg.max(dim=1, keepdim=True)[0]
-    return torch.cat([x[:, :1], torch.where(fg != peak, torch.zeros_like(fg), fg)], dim=1)
-
-
-def _with_bg(cam: torch.Tensor) -> torch.Tensor:
-    return torch.cat([1.0 - cam[:, 1:].max(dim=1, keepdim=True)[0], cam[:, 1:]], dim=1)
-
-
 def contrast_step_loss(cam1, cam_rv1, f_proj1, cam_rv1_down, cam2, cam_rv2, f_proj2, cam_rv2_down,
                        label20: torch.Tensor, bg_threshold: float = 0.20,
                        view2_size: Tuple[int, int] = (128, 128),
@@ -118,25 +101,15 @@ def contrast_step_loss(cam1, cam_rv1, f_proj1, cam_rv1_down, cam2, cam_rv2, f_pr
     n = label20.shape[0]
     label = torch.cat([torch.ones(n, 1, dtype=torch.float32, device=cam1.device),
                        label20.to(cam1.device, torch.float32)], dim=1)
-    lab4 = label.reshape(n, -1, 1, 1)
-    gap1 = F.adaptive_avg_pool2d(cam1, (1, 1))                                            # :142
-    rvmin1 = _min_pool_loss((cam_rv1 * lab4)[:, 1:])                                      # :143
+    cls1 = ops.cls_loss(cam1, label)                                                      # :142,159  GAP + soft margin
+    rvmin1 = ops.min_pool_loss(cam_rv1, label)                                            # :143      min-pool
     n1 = ops.fullres_norm(cam1, label, view2_size)                                        # :145-148  (K1b)
     rv1 = ops.fullres_norm(cam_rv1, label, view2_size)                                    # :149-152  (K1b)
-    gap2 = F.adaptive_avg_pool2d(cam2, (1, 1))                                            # :155
-    rvmin2 = _min_pool_loss((cam_rv2 * lab4)[:, 1:])                                      # :156
+    cls2 = ops.cls_loss(cam2, label)                                                      # :155,160
+    rvmin2 = ops.min_pool_loss(cam_rv2, label)                                            # :156
     n2 = ops.fullres_norm(cam2, label, None)                                              # :157      (K1b)
     rv2 = ops.fullres_norm(cam_rv2, label, None)                                          # :158      (K1b)
-    cls1 = F.multilabel_soft_margin_loss(gap1[:, 1:], lab4[:, 1:])                        # :159
-    cls2 = F.multilabel_soft_margin_loss(gap2[:, 1:], lab4[:, 1:])                        # :160
-    ns, cs, hs, ws = n2.shape
-    loss_er = torch.mean(torch.abs(n1[:, 1:] - n2[:, 1:]))                                # :163
-    n1b, n2b = _with_bg(n1), _with_bg(n2)                                                 # :165-166
-    k_ecr = int(21 * hs * ws * 0.2)
-    e1 = torch.abs(_argmax_fg_only(n2b.detach()) - rv1)                                   # :168
-    e2 = torch.abs(_argmax_fg_only(n1b.detach()) - rv2)                                   # :169
-    loss_ecr = (torch.mean(torch.topk(e1.reshape(ns, -1), k=k_ecr, dim=-1)[0])
-                + torch.mean(torch.topk(e2.reshape(ns, -1), k=k_ecr, dim=-1)[0]))         # :170-172
+    loss_er, loss_ecr = ops.er_ecr_loss(n1, n2, rv1, rv2)                                 # :163-172  ER + ECR
     loss_cls = (cls1 + cls2) / 2 + (rvmin1 + rvmin2) / 2                                  # :174
     grid = (view2_size[0] // 8, view2_size[1] // 8)                                       # :179
     terms = contrast_terms(f_proj1, cam_rv1_down, f_proj2, cam_rv2_down, label, bg_threshold, grid=grid,

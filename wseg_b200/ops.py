@@ -380,3 +380,131 @@ class _ContrastLoss(torch.autograd.Function):
 
 def contrast_loss(x1, x2, proto1, proto2, pl1, pl2, key1, key2) -> torch.Tensor:
     return _ContrastLoss.apply(x1, x2, proto1, proto2, pl1, pl2, key1, key2)
+
+
+# --------------------------------------------------------------------------------------------- auxiliary SEAM losses
+def select_kth(x: torch.Tensor, k: int, largest: bool = True):
+    """Per row of x [rows,len]: (sel [rows,4] = threshold, sum of the k selected, sum of relu(selected), ties taken;
+    idx_cut [rows] int32).  Selection is by value: no sort, no index tensor."""
+    x = _require_cuda_f32("x", x.detach())
+    rows, ln = x.shape
+    sel = torch.empty(rows, 4, dtype=torch.float32, device=x.device)
+    cut = torch.empty(rows, dtype=torch.int32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_lib.lib().wsegk_select_kth(_ptr(x), rows, ln, int(k), 1 if largest else 0, _ptr(sel), _ptr(cut), _stream(x)),
+              "wsegk_select_kth")
+    return sel, cut
+
+
+class _ClsLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cam, label):
+        cam = _require_cuda_f32("cam", cam)
+        n, c, H, W = cam.shape
+        lab = _label_nc(label, n, c).to(cam.device)
+        gap = torch.empty(n, c, dtype=torch.float32, device=cam.device)
+        dgap = torch.empty_like(gap)
+        loss = torch.empty(1, dtype=torch.float32, device=cam.device)
+        ws = torch.empty(n * c * 8, dtype=torch.float32, device=cam.device)
+        with torch.cuda.device(cam.device):
+            check(_lib.lib().wsegk_gap_mlsm_fwd(_ptr(cam), _ptr(lab), _ptr(gap), _ptr(dgap), _ptr(loss), n, c, H, W, _ptr(ws),
+                                                ws.numel() * 4, _stream(cam)), "wsegk_gap_mlsm_fwd")
+        ctx.save_for_backward(dgap)
+        ctx.dims = (n, c, H, W)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        (dgap,) = ctx.saved_tensors
+        n, c, H, W = ctx.dims
+        g = grad_loss.detach().reshape(1).to(torch.float32).contiguous()
+        grad_cam = torch.empty(n, c, H, W, dtype=torch.float32, device=dgap.device)
+        with torch.cuda.device(dgap.device):
+            check(_lib.lib().wsegk_gap_mlsm_bwd(_ptr(dgap), _ptr(g), _ptr(grad_cam), n, c, H, W, _stream(dgap)),
+                  "wsegk_gap_mlsm_bwd")
+        return grad_cam, None
+
+
+def cls_loss(cam: torch.Tensor, label: torch.Tensor) -> torch.Tensor:
+    """multilabel_soft_margin_loss(adaptive_avg_pool2d(cam,1)[:,1:], label[:,1:])  (contrast_train.py:142,159)."""
+    return _ClsLoss.apply(cam, label)
+
+
+class _MinPoolLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, label):
+        x = _require_cuda_f32("cam_rv", x)
+        n, c, H, W = x.shape
+        lab = _label_nc(label, n, c).to(x.device)
+        m = torch.empty(n, H * W, dtype=torch.float32, device=x.device)
+        arg = torch.empty(n, H * W, dtype=torch.int32, device=x.device)
+        sel = torch.empty(n, 4, dtype=torch.float32, device=x.device)
+        cut = torch.empty(n, dtype=torch.int32, device=x.device)
+        with torch.cuda.device(x.device):
+            check(_lib.lib().wsegk_minpool_fwd(_ptr(x), _ptr(lab), _ptr(m), _ptr(arg), _ptr(sel), _ptr(cut), n, c, H, W,
+                                               _stream(x)), "wsegk_minpool_fwd")
+        ctx.save_for_backward(m, arg, sel, cut, lab)
+        ctx.dims = (n, c, H, W)
+        k = (H * W) // 4
+        return sel[:, 2].sum() / (k * n)
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        m, arg, sel, cut, lab = ctx.saved_tensors
+        n, c, H, W = ctx.dims
+        g = grad_loss.detach().reshape(1).to(torch.float32).contiguous()
+        grad_x = torch.empty(n, c, H, W, dtype=torch.float32, device=m.device)
+        with torch.cuda.device(m.device):
+            check(_lib.lib().wsegk_minpool_bwd(_ptr(m), _ptr(arg), _ptr(sel), _ptr(cut), _ptr(lab), _ptr(g), _ptr(grad_x), n, c,
+                                               H, W, _stream(m)), "wsegk_minpool_bwd")
+        return grad_x, None
+
+
+def min_pool_loss(cam_rv: torch.Tensor, label: torch.Tensor) -> torch.Tensor:
+    """adaptive_min_pooling_loss((cam_rv * label)[:, 1:])  (contrast_train.py:16-25,143)."""
+    return _MinPoolLoss.apply(cam_rv, label)
+
+
+class _ErEcrLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, n1, n2, rv1, rv2):
+        n1, n2 = _require_cuda_f32("n1", n1), _require_cuda_f32("n2", n2)
+        rv1, rv2 = _require_cuda_f32("rv1", rv1), _require_cuda_f32("rv2", rv2)
+        n, c, h, w = n1.shape
+        for t in (n2, rv1, rv2):
+            if tuple(t.shape) != (n, c, h, w):
+                raise RuntimeError("er_ecr_loss: the four maps must have the same shape")
+        dev = n1.device
+        e1 = torch.empty(n, c * h * w, dtype=torch.float32, device=dev)
+        e2 = torch.empty_like(e1)
+        sel1 = torch.empty(n, 4, dtype=torch.float32, device=dev)
+        sel2 = torch.empty_like(sel1)
+        cut1 = torch.empty(n, dtype=torch.int32, device=dev)
+        cut2 = torch.empty_like(cut1)
+        losses = torch.empty(2, dtype=torch.float32, device=dev)
+        ws = torch.empty(n * ((h * w + 127) // 128), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(_lib.lib().wsegk_er_ecr_fwd(_ptr(n1), _ptr(n2), _ptr(rv1), _ptr(rv2), _ptr(e1), _ptr(e2), _ptr(sel1),
+                                              _ptr(cut1), _ptr(sel2), _ptr(cut2), _ptr(losses), n, c, h, w, _ptr(ws),
+                                              ws.numel() * 4, _stream(n1)), "wsegk_er_ecr_fwd")
+        ctx.save_for_backward(n1, n2, rv1, rv2, sel1, cut1, sel2, cut2)
+        return losses[0], losses[1]
+
+    @staticmethod
+    def backward(ctx, g_er, g_ecr):
+        n1, n2, rv1, rv2, sel1, cut1, sel2, cut2 = ctx.saved_tensors
+        n, c, h, w = n1.shape
+        ge = g_er.detach().reshape(1).to(torch.float32).contiguous()
+        gc = g_ecr.detach().reshape(1).to(torch.float32).contiguous()
+        outs = [torch.empty_like(n1) for _ in range(4)]
+        with torch.cuda.device(n1.device):
+            check(_lib.lib().wsegk_er_ecr_bwd(_ptr(n1), _ptr(n2), _ptr(rv1), _ptr(rv2), _ptr(sel1), _ptr(cut1), _ptr(sel2),
+                                              _ptr(cut2), _ptr(ge), _ptr(gc), *[_ptr(o) for o in outs], n, c, h, w,
+                                              _stream(n1)), "wsegk_er_ecr_bwd")
+        return tuple(outs)
+
+
+def er_ecr_loss(n1: torch.Tensor, n2: torch.Tensor, rv1: torch.Tensor, rv2: torch.Tensor):
+    """(loss_er, loss_ecr) of contrast_train.py:163-172 from the four label-masked normalised maps (K1b outputs):
+    n1/rv1 of view 1 resized to view 2's resolution, n2/rv2 of view 2."""
+    return _ErEcrLoss.apply(n1, n2, rv1, rv2)
