@@ -66,6 +66,12 @@ int wsegk_cam_norm_fwd(const float* cam, float* cam_norm, int N, int C, int h, i
 int wsegk_pcm_fwd(const float* f, const float* cam_norm, float* cam_rv, int N, int C, int K, int h, int w,
                   void* workspace, size_t workspace_bytes, wsegk_stream_t stream);
 
+/* K2 forward when NO backward will follow (contrast_infer.py, torch.no_grad): always single FP16 products — the sign
+ * mask that the split products protect is only consumed by pcm_bwd; cam_rv is within 1e-3 either way.  The workspace
+ * it leaves must not be handed to pcm_bwd. */
+int wsegk_pcm_fwd_infer(const float* f, const float* cam_norm, float* cam_rv, int N, int C, int K, int h, int w,
+                        void* workspace, size_t workspace_bytes, wsegk_stream_t stream);
+
 /* K2 backward — autograd of the lines above w.r.t. f only (cam_norm carries no gradient, :41).
  * grad_cam_rv [N,C,h,w] -> grad_f [N,K,h,w].  `workspace` must be the one pcm_fwd filled for the same
  * f / cam_norm (cam_rv is the forward output). */

@@ -460,3 +460,16 @@ def test_er_ecr_losses_vs_oracle(cuda_dev, n, hw1, hw2):
     assert float(ecr) == pytest.approx(float(ref_ecr), rel=1e-5)
     for mine_t, ref_t, name in zip(mine_in, (n1, n2, rv1, rv2), ("n1", "n2", "rv1", "rv2")):
         assert rel_max(mine_t.grad, ref_t.grad) <= 1e-5, name
+
+
+def test_pcm_inference_path(cuda_dev):
+    """contrast_infer.py runs Net.forward under torch.no_grad(): ops.pcm then takes the forward-only kernel."""
+    d = synth.pcm_inputs(2, 44, 60, seed=17)                     # an MSF-like non-square grid
+    f = d["f"].to(cuda_dev)
+    camn = ops.cam_norm(d["cam"].to(cuda_dev))
+    ref = R.pcm(camn, f)
+    with torch.no_grad():
+        out = ops.pcm(camn, f.clone().requires_grad_(True))
+    assert not out.requires_grad and rel_max(out, ref) <= TOL
+    out2 = ops.pcm(camn, f)                                       # f without grad: same path
+    assert torch.equal(out, out2)

@@ -944,14 +944,26 @@ static int launch_bwd(const PcmPlan& pl, int N, wsegk_stream_t stream) {
         if (_rc) return _rc;                                                                             \
     } while (0)
 
+static int pcm_fwd_impl(const float* f, const float* cam_norm, float* cam_rv, int N, int C, int K, int h, int w,
+                        void* workspace, size_t workspace_bytes, wsegk_stream_t stream, int precise);
+
 extern "C" int wsegk_pcm_fwd(const float* f, const float* cam_norm, float* cam_rv, int N, int C, int K, int h,
                              int w, void* workspace, size_t workspace_bytes, wsegk_stream_t stream) {
+    return pcm_fwd_impl(f, cam_norm, cam_rv, N, C, K, h, w, workspace, workspace_bytes, stream, pcm_mode());
+}
+
+extern "C" int wsegk_pcm_fwd_infer(const float* f, const float* cam_norm, float* cam_rv, int N, int C, int K, int h,
+                                   int w, void* workspace, size_t workspace_bytes, wsegk_stream_t stream) {
+    return pcm_fwd_impl(f, cam_norm, cam_rv, N, C, K, h, w, workspace, workspace_bytes, stream, 0);
+}
+
+static int pcm_fwd_impl(const float* f, const float* cam_norm, float* cam_rv, int N, int C, int K, int h, int w,
+                        void* workspace, size_t workspace_bytes, wsegk_stream_t stream, int precise) {
     if (int rc = check_device()) return rc;
     WSEGK_REQUIRE(f && cam_norm && cam_rv && workspace, WSEGK_ERR_NULL, "pcm_fwd: null pointer");
     if (int rc = pcm_check("pcm_fwd", N, C, K, h, w)) return rc;
     WSEGK_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, WSEGK_ERR_BAD_ALIGN,
                   "pcm_fwd: workspace must be 1024-byte aligned");
-    const int precise = pcm_mode();
     PcmPlan pl = make_pcm_plan(workspace, N, C, K, h, w, precise);
     WSEGK_REQUIRE(workspace_bytes >= pl.bytes, WSEGK_ERR_WORKSPACE_TOO_SMALL, "pcm_fwd: workspace %zu < %zu",
                   workspace_bytes, pl.bytes);

@@ -52,8 +52,9 @@ def cam_norm(cam: torch.Tensor) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------------------------- K2
-def pcm_forward(cam_norm_t: torch.Tensor, f: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-    """network/resnet38_contrast.py:70-73.  Returns (cam_rv [N,C,h,w], workspace kept for the backward)."""
+def pcm_forward(cam_norm_t: torch.Tensor, f: torch.Tensor, inference: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
+    """network/resnet38_contrast.py:70-73.  Returns (cam_rv [N,C,h,w], workspace kept for the backward).
+    ``inference=True``: no backward will follow (single-product kernel, workspace not reusable for pcm_backward)."""
     f = _require_cuda_f32("f", f)
     cam_norm_t = _require_cuda_f32("cam_norm", cam_norm_t)
     n, k, h, w = f.shape
@@ -63,8 +64,9 @@ def pcm_forward(cam_norm_t: torch.Tensor, f: torch.Tensor) -> Tuple[torch.Tensor
     out = torch.empty(n, c, h, w, dtype=torch.float32, device=f.device)
     with torch.cuda.device(f.device):
         ws = _workspace(_lib.OP_PCM, f.device, N=n, C=c, K=k, h=h, w=w)
-        check(_lib.lib().wsegk_pcm_fwd(_ptr(f), _ptr(cam_norm_t), _ptr(out), n, c, k, h, w, _ptr(ws),
-                                       ws.numel(), _stream(f)), "wsegk_pcm_fwd")
+        fn = _lib.lib().wsegk_pcm_fwd_infer if inference else _lib.lib().wsegk_pcm_fwd
+        check(fn(_ptr(f), _ptr(cam_norm_t), _ptr(out), n, c, k, h, w, _ptr(ws), ws.numel(), _stream(f)),
+              "wsegk_pcm_fwd_infer" if inference else "wsegk_pcm_fwd")
     return out, ws
 
 
@@ -98,7 +100,10 @@ class _PCMFunction(torch.autograd.Function):
 
 
 def pcm(cam_norm_t: torch.Tensor, f: torch.Tensor) -> torch.Tensor:
-    """Differentiable (w.r.t. ``f``) pixel correlation module; ``f`` is the output of the f9 conv."""
+    """Differentiable (w.r.t. ``f``) pixel correlation module; ``f`` is the output of the f9 conv.  When no gradient can
+    flow (torch.no_grad() as in contrast_infer.py, or f does not require grad) the forward-only kernel is used."""
+    if not (torch.is_grad_enabled() and f.requires_grad):
+        return pcm_forward(cam_norm_t.detach(), f.detach(), inference=True)[0]
     return _PCMFunction.apply(cam_norm_t.detach(), f)
 
 
