@@ -70,6 +70,28 @@ __global__ void __launch_bounds__(kSelThreads) select_kth_kernel(const float* __
     const int row = blockIdx.x;
     const float* src = x + static_cast<size_t>(row) * len;
     const bool lg = largest != 0;
+    // eight elements per thread and step: two float4 when the row allows it, scalars otherwise; idx = element index
+    const bool vec = (len & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+    auto load8 = [&](int base, float (&v)[8], int (&idx)[8]) {
+        if (vec) {
+            const float4* s4 = reinterpret_cast<const float4*>(src);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int q = (base >> 2) + threadIdx.x + h * kSelThreads;
+                const bool ok = 4 * q < len;
+                const float4 t4 = ok ? __ldg(s4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                v[4 * h] = t4.x; v[4 * h + 1] = t4.y; v[4 * h + 2] = t4.z; v[4 * h + 3] = t4.w;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) idx[4 * h + e] = ok ? 4 * q + e : len;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                idx[j] = base + threadIdx.x + j * kSelThreads;
+                v[j] = idx[j] < len ? __ldg(src + idx[j]) : 0.f;
+            }
+        }
+    };
     if (threadIdx.x == 0) { s_prefix = 0u; s_need = k; }
     // three digit passes, most significant first: 11 + 11 + 10 bits
     const int shifts[3] = {21, 10, 0}, widths[3] = {11, 11, 10};
@@ -79,20 +101,26 @@ __global__ void __launch_bounds__(kSelThreads) select_kth_kernel(const float* __
         __syncthreads();
         const uint32_t prefix = s_prefix;
         for (int base = 0; base < len; base += 8 * kSelThreads) {          // warp-uniform trip count (ballots inside)
-            const int i0 = base + threadIdx.x;                              // eight independent loads in flight
             float v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = (i0 + j * kSelThreads < len) ? __ldg(src + i0 + j * kSelThreads) : 0.f;
+            int idx[8];
+            load8(base, v, idx);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const bool in = i0 + j * kSelThreads < len;
+                const bool in = idx[j] < len;
                 const uint32_t key = sel_key(v[j], lg);
                 const bool act = in && (pass == 0 || (key >> (shift + width)) == prefix);
-                const unsigned am = __ballot_sync(0xffffffffu, act);
-                if (act) {
-                    const uint32_t bin = (key >> shift) & ((1u << width) - 1u);
-                    const unsigned peers = __match_any_sync(am, bin);
-                    if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&s_hist[bin], static_cast<uint32_t>(__popc(peers)));
+                const uint32_t bin = (key >> shift) & ((1u << width) - 1u);
+                if (pass == 0) {
+                    // every element takes part and the leading digit (sign, exponent, 2 mantissa bits) takes few values:
+                    // aggregate equal bins inside the warp before touching shared memory
+                    const unsigned am = __ballot_sync(0xffffffffu, act);
+                    if (act) {
+                        const unsigned peers = __match_any_sync(am, bin);
+                        if ((threadIdx.x & 31) == __ffs(peers) - 1)
+                            atomicAdd(&s_hist[bin], static_cast<uint32_t>(__popc(peers)));
+                    }
+                } else if (act) {
+                    atomicAdd(&s_hist[bin], 1u);           // few survivors, digits spread out
                 }
             }
         }
@@ -132,13 +160,13 @@ __global__ void __launch_bounds__(kSelThreads) select_kth_kernel(const float* __
     // sums over the strictly-beyond elements, count of ties
     float sum = 0.f, sum_relu = 0.f;
     int ceq = 0;
-    for (int i0 = threadIdx.x; i0 < len; i0 += 8 * kSelThreads) {
+    for (int base = 0; base < len; base += 8 * kSelThreads) {
         float v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = (i0 + j * kSelThreads < len) ? __ldg(src + i0 + j * kSelThreads) : 0.f;
+        int idx[8];
+        load8(base, v, idx);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            if (i0 + j * kSelThreads < len) {
+            if (idx[j] < len) {
                 const uint32_t key = sel_key(v[j], lg);
                 if (key > tkey) { sum += v[j]; sum_relu += fmaxf(v[j], 0.f); }
                 ceq += key == tkey ? 1 : 0;
