@@ -42,7 +42,9 @@ enum wsegk_op {
     WSEGK_OP_FULLRES_NORM = 3,
     WSEGK_OP_SEED_LABELS = 4,
     WSEGK_OP_PROTO = 5,
-    WSEGK_OP_CONTRAST_LOSS = 6
+    WSEGK_OP_CONTRAST_LOSS = 6,
+    WSEGK_OP_SELECT = 7,     /* select_kth and minpool_fwd: N = rows */
+    WSEGK_OP_ER_ECR = 8
 };
 
 int wsegk_version(void);
@@ -115,7 +117,7 @@ int wsegk_bilinear_resize_bwd(const float* grad_y, float* grad_x, int planes, in
  * sort).  sel [rows,4] = {threshold t, sum of the k selected values, sum of max(selected,0), number of ties taken};
  * idx_cut [rows]: element i with value v is selected iff v is strictly beyond t, or v == t and i < idx_cut[row]. */
 int wsegk_select_kth(const float* x, int rows, int len, int k, int largest, float* sel, int32_t* idx_cut,
-                     wsegk_stream_t stream);
+                     void* workspace, size_t workspace_bytes, wsegk_stream_t stream);
 /* contrast_train.py:142/155 + 159/160: gap = adaptive_avg_pool2d(cam), loss = multilabel_soft_margin(gap[:,1:], label[:,1:]).
  * cam [N,C,H,W], label [N,C] -> gap [N,C], dgap [N,C] (d loss / d gap, kept for the backward), loss [1]. */
 int wsegk_gap_mlsm_fwd(const float* cam, const float* label, float* gap, float* dgap, float* loss, int N, int C, int H,
@@ -125,7 +127,7 @@ int wsegk_gap_mlsm_bwd(const float* dgap, const float* grad_loss, float* grad_ca
 /* contrast_train.py:16-25 on (cam_rv*label)[:,1:]: m [N,H*W] = per-pixel class maximum, arg = its class, then the
  * bottom H*W/4 per image by select_kth; loss = sum(sel[:,2]) / (k*N).  Backward: dense grad_x [N,C,H,W]. */
 int wsegk_minpool_fwd(const float* x, const float* label, float* m, int32_t* arg, float* sel, int32_t* idx_cut, int N,
-                      int C, int H, int W, wsegk_stream_t stream);
+                      int C, int H, int W, void* workspace, size_t workspace_bytes, wsegk_stream_t stream);
 int wsegk_minpool_bwd(const float* m, const int32_t* arg, const float* sel, const int32_t* idx_cut, const float* label,
                       const float* grad_loss, float* grad_x, int N, int C, int H, int W, wsegk_stream_t stream);
 /* contrast_train.py:163-172 on the four normalised maps [N,C,h,w] (K1b outputs): losses[0] = loss_er,

@@ -9,7 +9,7 @@ from ctypes import c_char_p, c_float, c_int, c_int32, c_size_t, c_uint32, c_void
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libwsegk.so")
 
-OP_CAM_NORM, OP_PCM, OP_FULLRES_NORM, OP_SEED_LABELS, OP_PROTO, OP_CONTRAST_LOSS = 1, 2, 3, 4, 5, 6
+OP_CAM_NORM, OP_PCM, OP_FULLRES_NORM, OP_SEED_LABELS, OP_PROTO, OP_CONTRAST_LOSS, OP_SELECT, OP_ER_ECR = 1, 2, 3, 4, 5, 6, 7, 8
 
 _P = c_void_p
 _SIGNATURES = {
@@ -32,10 +32,10 @@ _SIGNATURES = {
                                        c_size_t, _P]),
     "wsegk_bilinear_resize_fwd": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "wsegk_bilinear_resize_bwd": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
-    "wsegk_select_kth": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, _P]),
+    "wsegk_select_kth": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, _P, c_size_t, _P]),
     "wsegk_gap_mlsm_fwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
     "wsegk_gap_mlsm_bwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P]),
-    "wsegk_minpool_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
+    "wsegk_minpool_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
     "wsegk_minpool_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "wsegk_er_ecr_fwd": (c_int, [_P] * 11 + [c_int] * 4 + [_P, c_size_t, _P]),
     "wsegk_er_ecr_bwd": (c_int, [_P] * 14 + [c_int] * 4 + [_P]),

@@ -141,6 +141,10 @@ extern "C" size_t wsegk_workspace_bytes(int op, int N, int C, int K, int D, int 
             return proto_workspace_bytes(N, C, h, w);
         case WSEGK_OP_CONTRAST_LOSS:
             return contrast_workspace_bytes(N, C, D, h, w);
+        case WSEGK_OP_SELECT:          // N = rows (also what minpool_fwd needs)
+            return select_workspace_bytes(N);
+        case WSEGK_OP_ER_ECR:          // N images on an h x w grid
+            return align_up(static_cast<size_t>(N) * ceil_div(h * w, 128) * sizeof(float), 256) + select_workspace_bytes(N);
         default:
             set_error("unknown op %d", op);
             return 0;

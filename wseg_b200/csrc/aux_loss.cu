@@ -57,116 +57,131 @@ __device__ __forceinline__ int block_sum_int(int v, int* s_red) {
 // out[row] = { threshold t, sum of the k selected values, sum of max(selected, 0), (float) number of ties taken };
 // idx_cut[row]: elements equal to t are selected iff their index is < idx_cut (== len when all ties are taken).
 // Element i with value v is selected iff  key(v) > key(t)  ||  (v == t && i < idx_cut[row]).
-constexpr int kSelThreads = 1024;
+//
+// A row (200 704 or 344 064 values) is split over S CTAs; a digit pass is two small launches: every CTA histograms its
+// chunk in shared memory and adds the non-empty bins to the row's global histogram (integer atomics: deterministic),
+// then one warp per row picks the digit.  (A single CTA per row took 218 us per call.)
+constexpr int kSelThreads = 256;
 constexpr int kSelBins = 2048;
+constexpr int kSelMaxSplit = 64;
 
-__global__ void __launch_bounds__(kSelThreads) select_kth_kernel(const float* __restrict__ x, int len, int k, int largest,
-                                                                 float4* __restrict__ out, int* __restrict__ idx_cut) {
+struct SelState {
+    uint32_t prefix;
+    int need;
+};
+
+__global__ void sel_init_kernel(SelState* __restrict__ st, uint32_t* __restrict__ hist, int rows, int k) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < rows) { st[i].prefix = 0u; st[i].need = k; }
+    for (int j = i; j < rows * kSelBins; j += gridDim.x * blockDim.x) hist[j] = 0u;
+}
+
+__device__ __forceinline__ void sel_chunk(int len, int nsplit, int part, int& begin, int& end) {
+    const int per = ((ceil_div_dev(len, nsplit) + 3) & ~3);
+    begin = min(len, part * per);
+    end = min(len, begin + per);
+}
+
+__global__ void __launch_bounds__(kSelThreads) sel_hist_kernel(const float* __restrict__ x, int len, int largest, int shift,
+                                                               int width, int first, const SelState* __restrict__ st,
+                                                               uint32_t* __restrict__ hist) {
     __shared__ uint32_t s_hist[kSelBins];
-    __shared__ uint32_t s_prefix;
-    __shared__ int s_need, s_cut;
-    __shared__ float s_redf[32];
-    __shared__ int s_redi[32];
-    const int row = blockIdx.x;
+    const int row = blockIdx.y;
     const float* src = x + static_cast<size_t>(row) * len;
     const bool lg = largest != 0;
-    // eight elements per thread and step: two float4 when the row allows it, scalars otherwise; idx = element index
-    const bool vec = (len & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
-    auto load8 = [&](int base, float (&v)[8], int (&idx)[8]) {
-        if (vec) {
-            const float4* s4 = reinterpret_cast<const float4*>(src);
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int q = (base >> 2) + threadIdx.x + h * kSelThreads;
-                const bool ok = 4 * q < len;
-                const float4 t4 = ok ? __ldg(s4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-                v[4 * h] = t4.x; v[4 * h + 1] = t4.y; v[4 * h + 2] = t4.z; v[4 * h + 3] = t4.w;
-#pragma unroll
-                for (int e = 0; e < 4; ++e) idx[4 * h + e] = ok ? 4 * q + e : len;
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                idx[j] = base + threadIdx.x + j * kSelThreads;
-                v[j] = idx[j] < len ? __ldg(src + idx[j]) : 0.f;
-            }
-        }
-    };
-    if (threadIdx.x == 0) { s_prefix = 0u; s_need = k; }
-    // three digit passes, most significant first: 11 + 11 + 10 bits
-    const int shifts[3] = {21, 10, 0}, widths[3] = {11, 11, 10};
-    for (int pass = 0; pass < 3; ++pass) {
-        const int shift = shifts[pass], width = widths[pass];
-        for (int b = threadIdx.x; b < kSelBins; b += blockDim.x) s_hist[b] = 0u;
-        __syncthreads();
-        const uint32_t prefix = s_prefix;
-        for (int base = 0; base < len; base += 8 * kSelThreads) {          // warp-uniform trip count (ballots inside)
-            float v[8];
-            int idx[8];
-            load8(base, v, idx);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const bool in = idx[j] < len;
-                const uint32_t key = sel_key(v[j], lg);
-                const bool act = in && (pass == 0 || (key >> (shift + width)) == prefix);
-                const uint32_t bin = (key >> shift) & ((1u << width) - 1u);
-                if (pass == 0) {
-                    // every element takes part and the leading digit (sign, exponent, 2 mantissa bits) takes few values:
-                    // aggregate equal bins inside the warp before touching shared memory
-                    const unsigned am = __ballot_sync(0xffffffffu, act);
-                    if (act) {
-                        const unsigned peers = __match_any_sync(am, bin);
-                        if ((threadIdx.x & 31) == __ffs(peers) - 1)
-                            atomicAdd(&s_hist[bin], static_cast<uint32_t>(__popc(peers)));
-                    }
-                } else if (act) {
-                    atomicAdd(&s_hist[bin], 1u);           // few survivors, digits spread out
-                }
-            }
-        }
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            // bins in DESCENDING order; lane l owns 64 of them
-            const int lane = threadIdx.x;
-            const int nb = 1 << width, per = nb / 32;
-            int sum = 0;
-            for (int j = 0; j < per; ++j) sum += static_cast<int>(s_hist[nb - 1 - (lane * per + j)]);
-            int incl = sum;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += t;
-            }
-            const int need = s_need, excl = incl - sum;
-            if (excl < need && need <= incl) {
-                int cum = excl;
-                for (int j = 0; j < per; ++j) {
-                    const int bin = nb - 1 - (lane * per + j);
-                    const int h = static_cast<int>(s_hist[bin]);
-                    if (cum + h >= need) {
-                        s_need = need - cum;
-                        s_prefix = (prefix << width) | static_cast<uint32_t>(bin);
-                        break;
-                    }
-                    cum += h;
-                }
-            }
-        }
-        __syncthreads();
-    }
-    const uint32_t tkey = s_prefix;                        // key of the k-th element
-    const int need = s_need;                               // how many elements equal to it are taken (>= 1)
-    const float t = aux_unordered_bits(lg ? tkey : ~tkey);
-    // sums over the strictly-beyond elements, count of ties
-    float sum = 0.f, sum_relu = 0.f;
-    int ceq = 0;
-    for (int base = 0; base < len; base += 8 * kSelThreads) {
+    int begin, end;
+    sel_chunk(len, gridDim.x, blockIdx.x, begin, end);
+    for (int b = threadIdx.x; b < kSelBins; b += blockDim.x) s_hist[b] = 0u;
+    __syncthreads();
+    const uint32_t prefix = st[row].prefix;
+    for (int base = begin; base < end; base += 8 * kSelThreads) {          // warp-uniform trip count (ballots inside)
         float v[8];
-        int idx[8];
-        load8(base, v, idx);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            if (idx[j] < len) {
+            const int i = base + threadIdx.x + j * kSelThreads;
+            v[j] = i < end ? __ldg(src + i) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const bool in = base + threadIdx.x + j * kSelThreads < end;
+            const uint32_t key = sel_key(v[j], lg);
+            const bool act = in && (first || (key >> (shift + width)) == prefix);
+            const uint32_t bin = (key >> shift) & ((1u << width) - 1u);
+            if (first) {
+                // every element takes part and the leading digit (sign, exponent, 2 mantissa bits) takes few values:
+                // aggregate equal bins inside the warp before touching shared memory
+                const unsigned am = __ballot_sync(0xffffffffu, act);
+                if (act) {
+                    const unsigned peers = __match_any_sync(am, bin);
+                    if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&s_hist[bin], static_cast<uint32_t>(__popc(peers)));
+                }
+            } else if (act) {
+                atomicAdd(&s_hist[bin], 1u);               // few survivors, digits spread out
+            }
+        }
+    }
+    __syncthreads();
+    uint32_t* g = hist + static_cast<size_t>(row) * kSelBins;
+    for (int b = threadIdx.x; b < kSelBins; b += blockDim.x)
+        if (s_hist[b]) atomicAdd(g + b, s_hist[b]);
+}
+
+// one warp per row: the bin (descending) holding the need-th key; clears the histogram for the next pass
+__global__ void __launch_bounds__(32) sel_scan_kernel(SelState* __restrict__ st, uint32_t* __restrict__ hist, int width) {
+    const int row = blockIdx.x, lane = threadIdx.x;
+    uint32_t* g = hist + static_cast<size_t>(row) * kSelBins;
+    const int nb = 1 << width, per = nb / 32;
+    int sum = 0;
+    for (int j = 0; j < per; ++j) sum += static_cast<int>(g[nb - 1 - (lane * per + j)]);
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const int need = st[row].need, excl = incl - sum;
+    const uint32_t prefix = st[row].prefix;
+    __syncwarp();
+    if (excl < need && need <= incl) {
+        int cum = excl;
+        for (int j = 0; j < per; ++j) {
+            const int bin = nb - 1 - (lane * per + j);
+            const int h = static_cast<int>(g[bin]);
+            if (cum + h >= need) {
+                st[row].need = need - cum;
+                st[row].prefix = (prefix << width) | static_cast<uint32_t>(bin);
+                break;
+            }
+            cum += h;
+        }
+    }
+    __syncwarp();
+    for (int b = lane; b < kSelBins; b += 32) g[b] = 0u;
+}
+
+// per chunk: sum / relu-sum over the strictly-beyond elements and the number of ties
+__global__ void __launch_bounds__(kSelThreads) sel_sum_kernel(const float* __restrict__ x, int len, int largest,
+                                                              const SelState* __restrict__ st, float4* __restrict__ partial) {
+    __shared__ float s_redf[32];
+    __shared__ int s_redi[32];
+    const int row = blockIdx.y;
+    const float* src = x + static_cast<size_t>(row) * len;
+    const bool lg = largest != 0;
+    int begin, end;
+    sel_chunk(len, gridDim.x, blockIdx.x, begin, end);
+    const uint32_t tkey = st[row].prefix;
+    float sum = 0.f, sum_relu = 0.f;
+    int ceq = 0;
+    for (int base = begin; base < end; base += 8 * kSelThreads) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int i = base + threadIdx.x + j * kSelThreads;
+            v[j] = i < end ? __ldg(src + i) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (base + threadIdx.x + j * kSelThreads < end) {
                 const uint32_t key = sel_key(v[j], lg);
                 if (key > tkey) { sum += v[j]; sum_relu += fmaxf(v[j], 0.f); }
                 ceq += key == tkey ? 1 : 0;
@@ -176,15 +191,37 @@ __global__ void __launch_bounds__(kSelThreads) select_kth_kernel(const float* __
     sum = block_sum(sum, s_redf);
     sum_relu = block_sum(sum_relu, s_redf);
     ceq = block_sum_int(ceq, s_redi);
-    // which ties: the lowest indices.  Only when there are more ties than needed does the order matter.
+    if (threadIdx.x == 0)
+        partial[row * kSelMaxSplit + blockIdx.x] = make_float4(sum, sum_relu, __int_as_float(ceq), 0.f);
+}
+
+// one CTA per row: fixed-order sum of the chunk partials; if there are more ties than needed, an ordered scan of the row
+// finds the index cut (lowest indices first)
+__global__ void __launch_bounds__(1024) sel_final_kernel(const float* __restrict__ x, int len, int largest, int nsplit,
+                                                         const SelState* __restrict__ st,
+                                                         const float4* __restrict__ partial, float4* __restrict__ out,
+                                                         int* __restrict__ idx_cut) {
+    __shared__ int s_redi[32];
+    __shared__ int s_cut;
+    const int row = blockIdx.x;
+    const float* src = x + static_cast<size_t>(row) * len;
+    const bool lg = largest != 0;
+    const uint32_t tkey = st[row].prefix;
+    const int need = st[row].need;
+    const float t = aux_unordered_bits(lg ? tkey : ~tkey);
+    float sum = 0.f, sum_relu = 0.f;
+    int ceq = 0;
+    for (int p = 0; p < nsplit; ++p) {                         // every thread: same order, same result
+        const float4 q = partial[row * kSelMaxSplit + p];
+        sum += q.x; sum_relu += q.y; ceq += __float_as_int(q.z);
+    }
     if (threadIdx.x == 0) s_cut = len;
     __syncthreads();
     if (ceq > need) {
-        int seen = 0;                                      // ties in earlier chunks (uniform across the block)
-        for (int base = 0; base < len; base += kSelThreads) {
+        int seen = 0;                                          // ties in earlier chunks (uniform across the block)
+        for (int base = 0; base < len; base += 1024) {
             const int i = base + threadIdx.x;
             const int flag = (i < len && sel_key(__ldg(src + i), lg) == tkey) ? 1 : 0;
-            // inclusive prefix of flag over the block in index order
             int incl = flag;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -194,11 +231,12 @@ __global__ void __launch_bounds__(kSelThreads) select_kth_kernel(const float* __
             __syncthreads();
             if ((threadIdx.x & 31) == 31) s_redi[threadIdx.x >> 5] = incl;
             __syncthreads();
-            int woff = 0;
-            for (int w = 0; w < (threadIdx.x >> 5); ++w) woff += s_redi[w];
-            int total = 0;
-            for (int w = 0; w < (kSelThreads >> 5); ++w) total += s_redi[w];
-            const int rank = seen + woff + incl;           // 1-based rank of this tie among all ties
+            int woff = 0, total = 0;
+            for (int w = 0; w < 32; ++w) {
+                if (w < (threadIdx.x >> 5)) woff += s_redi[w];
+                total += s_redi[w];
+            }
+            const int rank = seen + woff + incl;               // 1-based rank of this tie among all ties
             if (flag && rank == need) s_cut = i + 1;
             seen += total;
             __syncthreads();
@@ -211,6 +249,34 @@ __global__ void __launch_bounds__(kSelThreads) select_kth_kernel(const float* __
                                static_cast<float>(need));
         idx_cut[row] = s_cut;
     }
+}
+
+static size_t select_ws_bytes(int rows) {
+    return align_up(static_cast<size_t>(rows) * kSelBins * sizeof(uint32_t), 256) +
+           align_up(static_cast<size_t>(rows) * sizeof(SelState), 256) +
+           align_up(static_cast<size_t>(rows) * kSelMaxSplit * sizeof(float4), 256);
+}
+size_t select_workspace_bytes(int rows) { return select_ws_bytes(rows); }
+
+static int select_launch(const float* x, int rows, int len, int k, int largest, float* sel, int32_t* idx_cut, void* workspace,
+                         wsegk_stream_t stream) {
+    uint8_t* ws = static_cast<uint8_t*>(workspace);
+    uint32_t* hist = reinterpret_cast<uint32_t*>(ws);
+    SelState* st = reinterpret_cast<SelState*>(ws + align_up(static_cast<size_t>(rows) * kSelBins * sizeof(uint32_t), 256));
+    float4* partial = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(st) +
+                                                align_up(static_cast<size_t>(rows) * sizeof(SelState), 256));
+    const int nsplit = std::max(1, std::min(kSelMaxSplit, ceil_div(len, 8192)));
+    sel_init_kernel<<<std::min(64, ceil_div(rows * kSelBins, 256)), 256, 0, stream>>>(st, hist, rows, k);
+    const int shifts[3] = {21, 10, 0}, widths[3] = {11, 11, 10};
+    for (int pass = 0; pass < 3; ++pass) {
+        sel_hist_kernel<<<dim3(nsplit, rows), kSelThreads, 0, stream>>>(x, len, largest, shifts[pass], widths[pass],
+                                                                        pass == 0 ? 1 : 0, st, hist);
+        sel_scan_kernel<<<rows, 32, 0, stream>>>(st, hist, widths[pass]);
+    }
+    sel_sum_kernel<<<dim3(nsplit, rows), kSelThreads, 0, stream>>>(x, len, largest, st, partial);
+    sel_final_kernel<<<rows, 1024, 0, stream>>>(x, len, largest, nsplit, st, partial, reinterpret_cast<float4*>(sel), idx_cut);
+    count_launches(9);
+    return WSEGK_OK;
 }
 
 __device__ __forceinline__ bool is_selected(float v, int i, float t, int cut, bool largest) {
@@ -446,14 +512,16 @@ __global__ void __launch_bounds__(128) er_ecr_bwd_kernel(const float* __restrict
 using namespace wsegk;
 
 extern "C" int wsegk_select_kth(const float* x, int rows, int len, int k, int largest, float* sel, int32_t* idx_cut,
-                                wsegk_stream_t stream) {
+                                void* workspace, size_t workspace_bytes, wsegk_stream_t stream) {
     if (int rc = check_device()) return rc;
-    WSEGK_REQUIRE(x && sel && idx_cut, WSEGK_ERR_NULL, "select_kth: null pointer");
+    WSEGK_REQUIRE(x && sel && idx_cut && workspace, WSEGK_ERR_NULL, "select_kth: null pointer");
     WSEGK_REQUIRE(rows > 0 && len > 0 && k >= 1 && k <= len, WSEGK_ERR_BAD_SHAPE,
                   "select_kth: need rows, len > 0 and 1 <= k <= len (rows=%d len=%d k=%d)", rows, len, k);
-    WSEGK_REQUIRE((reinterpret_cast<uintptr_t>(sel) & 15) == 0, WSEGK_ERR_BAD_ALIGN, "select_kth: sel must be 16-byte aligned");
-    select_kth_kernel<<<rows, kSelThreads, 0, stream>>>(x, len, k, largest, reinterpret_cast<float4*>(sel), idx_cut);
-    count_launches(1);
+    WSEGK_REQUIRE((reinterpret_cast<uintptr_t>(sel) & 15) == 0 && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0,
+                  WSEGK_ERR_BAD_ALIGN, "select_kth: sel must be 16-byte and workspace 256-byte aligned");
+    WSEGK_REQUIRE(workspace_bytes >= select_ws_bytes(rows), WSEGK_ERR_WORKSPACE_TOO_SMALL, "select_kth: workspace %zu < %zu",
+                  workspace_bytes, select_ws_bytes(rows));
+    select_launch(x, rows, len, k, largest, sel, idx_cut, workspace, stream);
     WSEGK_CUDA_OK(cudaGetLastError());
     return WSEGK_OK;
 }
@@ -487,15 +555,16 @@ extern "C" int wsegk_gap_mlsm_bwd(const float* dgap, const float* grad_loss, flo
 }
 
 extern "C" int wsegk_minpool_fwd(const float* x, const float* label, float* m, int32_t* arg, float* sel, int32_t* idx_cut,
-                                 int N, int C, int H, int W, wsegk_stream_t stream) {
+                                 int N, int C, int H, int W, void* workspace, size_t workspace_bytes,
+                                 wsegk_stream_t stream) {
     if (int rc = check_device()) return rc;
-    WSEGK_REQUIRE(x && label && m && arg && sel && idx_cut, WSEGK_ERR_NULL, "minpool_fwd: null pointer");
+    WSEGK_REQUIRE(x && label && m && arg && sel && idx_cut && workspace, WSEGK_ERR_NULL, "minpool_fwd: null pointer");
     WSEGK_REQUIRE(N > 0 && C >= 2 && C <= 32 && H > 0 && W > 0 && H * W >= 4, WSEGK_ERR_BAD_SHAPE, "minpool_fwd: bad dims");
     const int HW = H * W;
     minpool_max_kernel<<<dim3(ceil_div(HW, 256), N), 256, 0, stream>>>(x, label, m, arg, C, HW);
     count_launches(1);
     WSEGK_CUDA_OK(cudaGetLastError());
-    return wsegk_select_kth(m, N, HW, HW / 4, 0, sel, idx_cut, stream);
+    return wsegk_select_kth(m, N, HW, HW / 4, 0, sel, idx_cut, workspace, workspace_bytes, stream);
 }
 
 extern "C" int wsegk_minpool_bwd(const float* m, const int32_t* arg, const float* sel, const int32_t* idx_cut,
@@ -524,13 +593,18 @@ extern "C" int wsegk_er_ecr_fwd(const float* n1, const float* n2, const float* r
     const int k = static_cast<int>(static_cast<double>(C) * hw * 0.2);          // int(21 * hs * ws * 0.2)
     WSEGK_REQUIRE(k >= 1, WSEGK_ERR_BAD_SHAPE, "er_ecr_fwd: map too small");
     const int nblk = ceil_div(hw, 128);
-    WSEGK_REQUIRE(workspace_bytes >= static_cast<size_t>(N) * nblk * sizeof(float), WSEGK_ERR_WORKSPACE_TOO_SMALL,
-                  "er_ecr_fwd: workspace too small");
+    const size_t part_bytes = align_up(static_cast<size_t>(N) * nblk * sizeof(float), 256);
+    WSEGK_REQUIRE(workspace_bytes >= part_bytes + select_ws_bytes(N), WSEGK_ERR_WORKSPACE_TOO_SMALL,
+                  "er_ecr_fwd: workspace %zu < %zu", workspace_bytes, part_bytes + select_ws_bytes(N));
+    WSEGK_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, WSEGK_ERR_BAD_ALIGN,
+                  "er_ecr_fwd: workspace must be 256-byte aligned");
     float* part = static_cast<float*>(workspace);
+    void* sel_ws = static_cast<uint8_t*>(workspace) + part_bytes;
     er_ecr_fwd_kernel<<<dim3(nblk, N), 128, 0, stream>>>(n1, n2, rv1, rv2, e1, e2, part, C, hw);
     count_launches(1);
-    if (int rc = wsegk_select_kth(e1, N, C * hw, k, 1, sel1, cut1, stream)) return rc;
-    if (int rc = wsegk_select_kth(e2, N, C * hw, k, 1, sel2, cut2, stream)) return rc;
+    // the two selects run one after the other on the stream, so they can share the scratch
+    if (int rc = wsegk_select_kth(e1, N, C * hw, k, 1, sel1, cut1, sel_ws, select_ws_bytes(N), stream)) return rc;
+    if (int rc = wsegk_select_kth(e2, N, C * hw, k, 1, sel2, cut2, sel_ws, select_ws_bytes(N), stream)) return rc;
     er_ecr_finalize_kernel<<<1, 256, 0, stream>>>(part, N * nblk, reinterpret_cast<const float4*>(sel1),
                                                   reinterpret_cast<const float4*>(sel2), losses, N, C, hw, k);
     count_launches(1);

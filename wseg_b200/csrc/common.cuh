@@ -47,6 +47,7 @@ __host__ __device__ inline int ceil_div_dev(int a, int b) { return (a + b - 1) /
 size_t fullres_workspace_bytes(int N, int C);
 size_t proto_workspace_bytes(int N, int C, int h, int w);
 size_t contrast_workspace_bytes(int N, int C, int D, int h, int w);
+size_t select_workspace_bytes(int rows);
 
 // Bump allocator over the caller's workspace; every section is 1 KiB aligned.
 struct Carver {

@@ -396,8 +396,9 @@ def select_kth(x: torch.Tensor, k: int, largest: bool = True):
     sel = torch.empty(rows, 4, dtype=torch.float32, device=x.device)
     cut = torch.empty(rows, dtype=torch.int32, device=x.device)
     with torch.cuda.device(x.device):
-        check(_lib.lib().wsegk_select_kth(_ptr(x), rows, ln, int(k), 1 if largest else 0, _ptr(sel), _ptr(cut), _stream(x)),
-              "wsegk_select_kth")
+        ws = _workspace(_lib.OP_SELECT, x.device, N=rows, h=1, w=1)
+        check(_lib.lib().wsegk_select_kth(_ptr(x), rows, ln, int(k), 1 if largest else 0, _ptr(sel), _ptr(cut), _ptr(ws),
+                                          ws.numel(), _stream(x)), "wsegk_select_kth")
     return sel, cut
 
 
@@ -446,8 +447,9 @@ class _MinPoolLoss(torch.autograd.Function):
         sel = torch.empty(n, 4, dtype=torch.float32, device=x.device)
         cut = torch.empty(n, dtype=torch.int32, device=x.device)
         with torch.cuda.device(x.device):
+            ws = _workspace(_lib.OP_SELECT, x.device, N=n, h=1, w=1)
             check(_lib.lib().wsegk_minpool_fwd(_ptr(x), _ptr(lab), _ptr(m), _ptr(arg), _ptr(sel), _ptr(cut), n, c, H, W,
-                                               _stream(x)), "wsegk_minpool_fwd")
+                                               _ptr(ws), ws.numel(), _stream(x)), "wsegk_minpool_fwd")
         ctx.save_for_backward(m, arg, sel, cut, lab)
         ctx.dims = (n, c, H, W)
         k = (H * W) // 4
@@ -487,11 +489,11 @@ class _ErEcrLoss(torch.autograd.Function):
         cut1 = torch.empty(n, dtype=torch.int32, device=dev)
         cut2 = torch.empty_like(cut1)
         losses = torch.empty(2, dtype=torch.float32, device=dev)
-        ws = torch.empty(n * ((h * w + 127) // 128), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
+            ws = _workspace(_lib.OP_ER_ECR, dev, N=n, C=c, h=h, w=w)
             check(_lib.lib().wsegk_er_ecr_fwd(_ptr(n1), _ptr(n2), _ptr(rv1), _ptr(rv2), _ptr(e1), _ptr(e2), _ptr(sel1),
                                               _ptr(cut1), _ptr(sel2), _ptr(cut2), _ptr(losses), n, c, h, w, _ptr(ws),
-                                              ws.numel() * 4, _stream(n1)), "wsegk_er_ecr_fwd")
+                                              ws.numel(), _stream(n1)), "wsegk_er_ecr_fwd")
         ctx.save_for_backward(n1, n2, rv1, rv2, sel1, cut1, sel2, cut2)
         return losses[0], losses[1]
 
