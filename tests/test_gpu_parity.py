@@ -473,3 +473,45 @@ def test_pcm_inference_path(cuda_dev):
     assert not out.requires_grad and rel_max(out, ref) <= TOL
     out2 = ops.pcm(camn, f)                                       # f without grad: same path
     assert torch.equal(out, out2)
+
+
+def test_net_training_step_end_to_end(cuda_dev):
+    """configs[0] in miniature: the drop-in Net (random-init ResNet-38, eval-mode BN as in the reference's train()),
+    both views, the whole loss body and its backward on the GPU — against the oracle evaluated on the SAME network
+    outputs (head recomputed with ATen from the backbone taps), and gradients reaching the parameters."""
+    from wseg_b200.network import resnet38_contrast
+    torch.manual_seed(7)
+    net = resnet38_contrast.Net().to(cuda_dev)
+    net.train()
+    n = 2
+    g = torch.Generator().manual_seed(8)
+    img1 = torch.randn(n, 3, 160, 176, generator=g).to(cuda_dev)
+    img2 = F.interpolate(img1, size=(128, 128), mode="bilinear", align_corners=True)        # contrast_train.py:131-134
+    lab20 = synth.labels(n, seed=9).to(cuda_dev)
+    taps = {}
+    hooks = [net.fc8.register_forward_hook(lambda m, i, o: taps.setdefault("logits", []).append(o.detach())),
+             net.f9.register_forward_hook(lambda m, i, o: taps.setdefault("f9", []).append(o.detach())),
+             net.dropout7.register_forward_hook(lambda m, i, o: taps.setdefault("fea", []).append(o.detach()))]
+    out1 = net(img1)
+    out2 = net(img2)
+    for h in hooks:
+        h.remove()
+    # the head against ATen on the same taps (network/resnet38_contrast.py:41-59)
+    for v, (out, img) in enumerate(((out1, img1), (out2, img2))):
+        cam, cam_rv, f_proj, cam_rv_down = out
+        H, W = img.shape[-2:]
+        camn = R.cam_d_norm(taps["logits"][v])
+        rv_down = R.pcm(camn, taps["f9"][v])
+        assert rel_max(cam_rv_down, rv_down) <= TOL
+        assert rel_max(cam_rv, F.interpolate(rv_down, (H, W), mode="bilinear", align_corners=True)) <= TOL
+        assert rel_max(cam, F.interpolate(taps["logits"][v], (H, W), mode="bilinear", align_corners=True)) <= 1e-5
+        assert tuple(f_proj.shape) == (n, 128, cam_rv_down.shape[-2], cam_rv_down.shape[-1])
+    mine = L.contrast_step_loss(*out1, *out2, lab20, 0.2, (128, 128), rng=3)
+    mine["loss"].backward()
+    ref_in = [t.detach().clone().requires_grad_(True) for t in (*out1, *out2)]
+    ref = R.contrast_step_loss(*ref_in, lab20, 0.2, (128, 128), sampler=R.ReferenceSampler(3))
+    for k in L.LOSS_KEYS:
+        assert float(mine[k]) == pytest.approx(float(ref[k]), rel=2e-4), k
+    grads = [p.grad for p in (net.fc8.weight, net.f9.weight, net.fc_proj.weight, net.f8_3.weight)]
+    assert all(gr is not None and bool(torch.isfinite(gr).all()) and float(gr.abs().max()) > 0 for gr in grads)
+    assert net.conv1a.weight.grad is None                                   # frozen layers (not_training) stay frozen
