@@ -123,7 +123,7 @@ class HotPath:
             camn2 = ops.cam_norm(d["cam2"])
             rv2, ws2 = ops.pcm_forward(camn2, d["f2"])
             norm2, pl2 = ops.seed_labels(rv2, d["label"], BG_THRESHOLD)
-            proto2, ti2 = ops.prototypes(norm2, d["fproj2"], group=self.group)
+            proto2, ti2 = ops.prototypes(norm2, d["fproj2"], group=self.group, view=1)
             v2_done = torch.cuda.Event()
             v2_done.record(s2)
             g_rv2 = k1b("rv2_full", None, "g_rv2")
@@ -137,7 +137,7 @@ class HotPath:
             f1 = ops.resize_fwd(d["fproj1"], self.grid)
             c1 = ops.resize_fwd(rv1, self.grid)
             norm1, pl1 = ops.seed_labels(c1, d["label"], BG_THRESHOLD)
-            proto1, ti1 = ops.prototypes(norm1, f1, group=self.group)
+            proto1, ti1 = ops.prototypes(norm1, f1, group=self.group, view=0)
             s3.wait_event(v2_done)
             losses, g1, g2, _, _ = ops.contrast_loss_raw(f1, d["fproj2"], proto1, proto2, pl1, pl2, self.key1, self.key2)
             keep.extend([f1, c1, norm1, pl1, norm2, pl2, proto1, ti1, proto2, ti2])

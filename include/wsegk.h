@@ -153,6 +153,22 @@ int wsegk_proto_topk_local(const float* norm_cam, const float* f_proj, int pixel
 int wsegk_proto_finalize(const float* cand_val, const int32_t* cand_idx, const float* cand_fea, int n_cand,
                          int k, float* proto, int32_t* sel_idx, int C, int D, wsegk_stream_t stream);
 
+/* K3 exchange without NCCL: a one-shot gather over NVLink peer memory.  Every rank allocates the same
+ * symmetric buffer of wsegk_proto_exchange_bytes(R,C,k,D) bytes, zero-filled once, mapped into every peer
+ * (e.g. torch.distributed._symmetric_memory); peer_bases[r] is rank r's buffer as seen from this process.
+ *   proto_push          : packs this rank's local top-k (outputs of proto_topk_local) and stores it into its slot of EVERY
+ *                         peer's buffer, then releases a per-rank flag carrying the step number (kept in local_state:
+ *                         4 uint32, zero-initialised, [view][last step, CTA counter]) — nothing host-side changes between
+ *                         steps, so the call is CUDA-graph capturable.
+ *   proto_finalize_symm : waits (device-side, bounded) until all R flags of `view` reach this rank's step, then does what
+ *                         proto_finalize does on the candidates in place.  Must follow this rank's proto_push of the same
+ *                         view on the same stream. */
+size_t wsegk_proto_exchange_bytes(int R, int C, int k, int D);
+int wsegk_proto_push(const float* top_val, const int32_t* top_idx, const float* top_fea, void* const* peer_bases, int R,
+                     int rank, int view, int C, int k, int D, uint32_t* local_state, wsegk_stream_t stream);
+int wsegk_proto_finalize_symm(const void* local_base, int R, int view, int k, float* proto, int32_t* sel_idx, int C, int D,
+                              const uint32_t* local_state, wsegk_stream_t stream);
+
 /* K4 — replaces contrast_train.py:244-389: the four cross-view NCE terms and the two intra-view NCE terms
  * (semi-hard prototypes = ranks 3..12, hard-pixel mining), forward and backward in one call.
  *   x1,x2   [N,D,h,w]  projected features of the two views on the common loss grid (un-normalised)

@@ -43,6 +43,9 @@ _SIGNATURES = {
     "wsegk_proto_topk_local": (c_int, [_P, _P, c_int, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P,
                                        c_size_t, _P]),
     "wsegk_proto_finalize": (c_int, [_P, _P, _P, c_int, c_int, _P, _P, c_int, c_int, _P]),
+    "wsegk_proto_exchange_bytes": (c_size_t, [c_int] * 4),
+    "wsegk_proto_push": (c_int, [_P, _P, _P, ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_int, _P, _P]),
+    "wsegk_proto_finalize_symm": (c_int, [_P, c_int, c_int, c_int, _P, _P, c_int, c_int, _P, _P]),
     "wsegk_contrast_loss_fwd_bwd": (c_int, [_P] * 14 + [c_int] * 5 + [_P, c_size_t, _P]),
 }
 

@@ -167,21 +167,65 @@ __global__ void __launch_bounds__(kTopkThreads) proto_topk_kernel(const float* _
     }
 }
 
-// one CTA per class: global top-k among n_cand candidates, prototype = sum(val*fea)/sum(val), L2-normalised
-__global__ void __launch_bounds__(1024) proto_finalize_kernel(const float* __restrict__ cand_val,
-                                                              const int32_t* __restrict__ cand_idx,
-                                                              const float* __restrict__ cand_fea, int n_cand,
-                                                              int npad, int k, float* __restrict__ proto,
-                                                              int32_t* __restrict__ sel_idx, int D) {
+// Where the candidates of all ranks live: either three plain tensors ([C][n_cand], [C][n_cand], [C][n_cand][D], what an
+// all-gather of the packed messages is unpacked into) or the rank-major packed exchange buffer that the peers' push
+// kernels wrote straight into this GPU's memory over NVLink ([R][C][k][D+2]: value, index bits, D features).
+struct CandSrc {
+    const float* val;
+    const int32_t* idx;
+    const float* fea;
+    const float* packed;
+    int n_cand, C, k, D;
+    __device__ __forceinline__ size_t row(int c, int j) const {
+        const int r = j / k, t = j - r * k;
+        return (static_cast<size_t>(r * C + c) * k + t) * (D + 2);
+    }
+    __device__ __forceinline__ float value(int c, int j) const { return packed ? packed[row(c, j)] : val[c * n_cand + j]; }
+    __device__ __forceinline__ uint32_t index(int c, int j) const {
+        return packed ? __float_as_uint(packed[row(c, j) + 1]) : static_cast<uint32_t>(idx[c * n_cand + j]);
+    }
+    __device__ __forceinline__ float feature(int c, int j, int d) const {
+        return packed ? packed[row(c, j) + 2 + d] : fea[(static_cast<size_t>(c) * n_cand + j) * D + d];
+    }
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+
+// one CTA per class: global top-k among n_cand candidates, prototype = sum(val*fea)/sum(val), L2-normalised.
+// wait_flags != nullptr: first wait until every rank's push of step `*wait_step` has landed (flags written by the peers).
+__global__ void __launch_bounds__(1024) proto_finalize_kernel(CandSrc src, int npad, float* __restrict__ proto,
+                                                              int32_t* __restrict__ sel_idx, const uint32_t* wait_flags,
+                                                              const uint32_t* wait_step, int n_ranks) {
     extern __shared__ unsigned long long s_buf[];
     unsigned long long* s_keys = s_buf;                                   // npad
     uint32_t* s_pos = reinterpret_cast<uint32_t*>(s_buf + npad);          // npad
     __shared__ float s_red[32];
     __shared__ float s_scale;
     const int c = blockIdx.x;
+    const int n_cand = src.n_cand, k = src.k, D = src.D;
+    if (wait_flags != nullptr) {
+        if (threadIdx.x < n_ranks) {
+            const uint32_t want = *wait_step;
+            unsigned long long spins = 0;
+            while (static_cast<int32_t>(ld_acquire_sys(wait_flags + threadIdx.x) - want) < 0) {
+                if (++spins > (1ull << 33)) __trap();          // a peer died: fail the launch instead of hanging
+                __nanosleep(64);
+            }
+        }
+        __syncthreads();
+        // the parity half of the exchange buffer that belongs to this step
+        src.packed += static_cast<size_t>(*wait_step & 1u) * 2 * n_ranks * src.C * k * (D + 2);
+    }
     for (int i = threadIdx.x; i < npad; i += blockDim.x) {
         if (i < n_cand) {
-            s_keys[i] = topk_key(cand_val[c * n_cand + i], static_cast<uint32_t>(cand_idx[c * n_cand + i]));
+            s_keys[i] = topk_key(src.value(c, i), src.index(c, i));
             s_pos[i] = i;
         } else {
             s_keys[i] = 0ull;
@@ -194,7 +238,7 @@ __global__ void __launch_bounds__(1024) proto_finalize_kernel(const float* __res
     // selected weights into shared memory (one load per thread), then a fixed-order sum by thread 0
     float* s_w = reinterpret_cast<float*>(s_keys);             // the keys are no longer needed: reuse as k floats
     __syncthreads();
-    for (int t = threadIdx.x; t < k; t += blockDim.x) s_w[t] = cand_val[c * n_cand + s_pos[t]];
+    for (int t = threadIdx.x; t < k; t += blockDim.x) s_w[t] = src.value(c, s_pos[t]);
     __syncthreads();
     if (threadIdx.x == 0) {
         float wsum = 0.f;
@@ -211,8 +255,7 @@ __global__ void __launch_bounds__(1024) proto_finalize_kernel(const float* __res
         for (int t0 = 0; t0 < k; t0 += 8) {                   // eight independent loads in flight, fixed order of adds
             float fv[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                fv[j] = (t0 + j < k) ? __ldg(cand_fea + (static_cast<size_t>(c) * n_cand + s_pos[t0 + j]) * D + d) : 0.f;
+            for (int j = 0; j < 8; ++j) fv[j] = (t0 + j < k) ? src.feature(c, s_pos[t0 + j], d) : 0.f;
 #pragma unroll
             for (int j = 0; j < 8; ++j)
                 if (t0 + j < k) acc = fmaf(s_w[t0 + j], fv[j], acc);
@@ -234,6 +277,57 @@ __global__ void __launch_bounds__(1024) proto_finalize_kernel(const float* __res
     const float nrm = s_scale;
     slot = 0;
     for (int d = threadIdx.x; d < D; d += blockDim.x, ++slot) proto[c * D + d] = mine[slot] / nrm;
+}
+
+// ---- one-shot candidate exchange over NVLink peer memory ------------------------------------------------
+// Every rank owns the same symmetric buffer: candidates [2 parities][2 views][R ranks][C][k][D+2] floats, then flags
+// [2 views][R] (the step number of the last complete push of that rank).  The push kernel packs this rank's local top-k
+// and stores it into slot (parity, view, my rank) of EVERY peer's buffer (plain stores to mapped peer addresses), fences,
+// and the last CTA to finish releases flag[view][my rank] = step on every peer.  proto_finalize then only waits for R flags
+// in its own memory.  No NCCL kernel, no host involvement, graph-capturable; the step number lives on the device.
+constexpr int kMaxRanks = 16;
+struct PushPeers {
+    float* cand[kMaxRanks];
+    uint32_t* flags[kMaxRanks];
+};
+constexpr int kPushChunks = 8;
+
+__global__ void __launch_bounds__(256) proto_push_kernel(const float* __restrict__ top_val, const int32_t* __restrict__ top_idx,
+                                                         const float* __restrict__ top_fea, PushPeers peers, int R, int rank,
+                                                         int view, int C, int k, int D, uint32_t* __restrict__ state) {
+    // state[view*2 + 0] = last completed step, state[view*2 + 1] = CTAs done in this launch
+    const uint32_t step = state[view * 2] + 1u;
+    const int peer = blockIdx.y;
+    const size_t slot_floats = static_cast<size_t>(C) * k * (D + 2);
+    float* dst = peers.cand[peer] + ((static_cast<size_t>(step & 1u) * 2 + view) * R + rank) * slot_floats;
+    const int rows = C * k, pairs = (D + 2) >> 1;                  // D even: a row is (D+2)/2 float2
+    const int per = ceil_div_dev(rows, static_cast<int>(gridDim.x));
+    const int r0 = blockIdx.x * per, r1 = min(rows, r0 + per);
+    for (int e = r0 * pairs + threadIdx.x; e < r1 * pairs; e += blockDim.x) {
+        const int row = e / pairs, u = e - row * pairs;
+        float2 v;
+        if (u == 0) {
+            v.x = top_val[row];
+            v.y = __int_as_float(top_idx[row]);
+        } else {
+            const float* f = top_fea + static_cast<size_t>(row) * D + 2 * (u - 1);
+            v.x = f[0];
+            v.y = f[1];
+        }
+        reinterpret_cast<float2*>(dst + static_cast<size_t>(row) * (D + 2))[u] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned total = gridDim.x * gridDim.y;
+        const unsigned done = atomicAdd(&state[view * 2 + 1], 1u);
+        if (done == total - 1) {                                   // last CTA: every store of this launch is fenced
+            state[view * 2 + 1] = 0u;
+            state[view * 2] = step;
+            __threadfence_system();
+            for (int p = 0; p < R; ++p) st_release_sys(peers.flags[p] + view * R + rank, step);
+        }
+    }
 }
 
 size_t proto_workspace_bytes(int, int, int, int) { return 1024; }
@@ -692,7 +786,63 @@ extern "C" int wsegk_proto_finalize(const float* cand_val, const int32_t* cand_i
     const size_t smem = static_cast<size_t>(npad) * (sizeof(unsigned long long) + sizeof(uint32_t));
     WSEGK_CUDA_OK(cudaFuncSetAttribute(proto_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem)));
-    proto_finalize_kernel<<<C, 1024, smem, stream>>>(cand_val, cand_idx, cand_fea, n_cand, npad, k, proto, sel_idx, D);
+    CandSrc src{cand_val, cand_idx, cand_fea, nullptr, n_cand, C, k, D};
+    proto_finalize_kernel<<<C, 1024, smem, stream>>>(src, npad, proto, sel_idx, nullptr, nullptr, 0);
+    count_launches(1);
+    WSEGK_CUDA_OK(cudaGetLastError());
+    return WSEGK_OK;
+}
+
+static size_t exchange_cand_floats(int R, int C, int k, int D) {
+    return static_cast<size_t>(2) * 2 * R * C * k * (D + 2);
+}
+
+extern "C" size_t wsegk_proto_exchange_bytes(int R, int C, int k, int D) {
+    if (R <= 0 || C <= 0 || k <= 0 || D <= 0) return 0;
+    return align_up(exchange_cand_floats(R, C, k, D) * sizeof(float), 256) + align_up(static_cast<size_t>(2) * R * 4, 256);
+}
+
+extern "C" int wsegk_proto_push(const float* top_val, const int32_t* top_idx, const float* top_fea, void* const* peer_bases,
+                                int R, int rank, int view, int C, int k, int D, uint32_t* local_state,
+                                wsegk_stream_t stream) {
+    if (int rc = check_device()) return rc;
+    WSEGK_REQUIRE(top_val && top_idx && top_fea && peer_bases && local_state, WSEGK_ERR_NULL, "proto_push: null pointer");
+    WSEGK_REQUIRE(R >= 1 && R <= kMaxRanks && rank >= 0 && rank < R && (view == 0 || view == 1) && C > 0 && k > 0 && D > 0 &&
+                      (D % 2) == 0,
+                  WSEGK_ERR_BAD_SHAPE, "proto_push: need 1 <= R <= %d, 0 <= rank < R, view in {0,1}, even D", kMaxRanks);
+    PushPeers peers{};
+    const size_t flag_off = align_up(exchange_cand_floats(R, C, k, D) * sizeof(float), 256);
+    for (int p = 0; p < R; ++p) {
+        WSEGK_REQUIRE(peer_bases[p] != nullptr, WSEGK_ERR_NULL, "proto_push: peer %d has no buffer", p);
+        peers.cand[p] = static_cast<float*>(peer_bases[p]);
+        peers.flags[p] = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(peer_bases[p]) + flag_off);
+    }
+    proto_push_kernel<<<dim3(kPushChunks, R), 256, 0, stream>>>(top_val, top_idx, top_fea, peers, R, rank, view, C, k, D,
+                                                                local_state);
+    count_launches(1);
+    WSEGK_CUDA_OK(cudaGetLastError());
+    return WSEGK_OK;
+}
+
+extern "C" int wsegk_proto_finalize_symm(const void* local_base, int R, int view, int k, float* proto, int32_t* sel_idx,
+                                         int C, int D, const uint32_t* local_state, wsegk_stream_t stream) {
+    if (int rc = check_device()) return rc;
+    WSEGK_REQUIRE(local_base && proto && sel_idx && local_state, WSEGK_ERR_NULL, "proto_finalize_symm: null pointer");
+    const int n_cand = R * k;
+    WSEGK_REQUIRE(R >= 1 && R <= kMaxRanks && (view == 0 || view == 1) && C > 0 && D > 0 && D <= 4096 && k >= 1 &&
+                      n_cand <= 16384,
+                  WSEGK_ERR_BAD_SHAPE, "proto_finalize_symm: bad dims (R=%d k=%d D=%d)", R, k, D);
+    const int npad = next_pow2(n_cand);
+    const size_t smem = static_cast<size_t>(npad) * (sizeof(unsigned long long) + sizeof(uint32_t));
+    WSEGK_CUDA_OK(cudaFuncSetAttribute(proto_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem)));
+    const float* base = static_cast<const float*>(local_base);
+    const size_t slot_floats = static_cast<size_t>(C) * k * (D + 2);
+    const size_t flag_off = align_up(exchange_cand_floats(R, C, k, D) * sizeof(float), 256);
+    const uint32_t* flags = reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(local_base) + flag_off) + view * R;
+    // parity offset is applied inside the kernel (the step number is only known on the device)
+    CandSrc src{nullptr, nullptr, nullptr, base + static_cast<size_t>(view) * R * slot_floats, n_cand, C, k, D};
+    proto_finalize_kernel<<<C, 1024, smem, stream>>>(src, npad, proto, sel_idx, flags, local_state + view * 2, R);
     count_launches(1);
     WSEGK_CUDA_OK(cudaGetLastError());
     return WSEGK_OK;

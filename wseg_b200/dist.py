@@ -32,3 +32,36 @@ def gather_candidates(top_val: torch.Tensor, top_idx: torch.Tensor, top_fea: tor
     idx = out[:, :, 1].contiguous().view(torch.int32)
     fea = out[:, :, 2:].contiguous()
     return val, idx, fea
+
+
+class SymmExchange:
+    """One-shot prototype-candidate exchange over NVLink peer memory (include/wsegk.h: wsegk_proto_push /
+    wsegk_proto_finalize_symm): every rank's top-k kernel output is stored straight into every peer's buffer, so a step has
+    no NCCL kernel and no host involvement on this path.  Built on ``torch.distributed._symmetric_memory`` for the
+    allocation and the peer mapping only."""
+
+    _cache = {}
+
+    def __init__(self, group, c: int, k: int, d: int, device):
+        import ctypes
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        nbytes = int(_lib.lib().wsegk_proto_exchange_bytes(self.world, c, k, d))
+        self.buf = symm_mem.empty(nbytes // 4, dtype=torch.float32, device=device)
+        self.hdl = symm_mem.rendezvous(self.buf, self.group)
+        self.buf.zero_()
+        self.state = torch.zeros(4, dtype=torch.int32, device=device)
+        torch.cuda.synchronize(device)
+        self.hdl.barrier()                       # everybody's flags are zero before anybody pushes
+        ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self.peer_bases = (ctypes.c_void_p * self.world)(*ptrs)
+        self.dims = (c, k, d)
+
+    @classmethod
+    def get(cls, group, c: int, k: int, d: int, device):
+        key = (id(group), c, k, d, str(device))
+        if key not in cls._cache:
+            cls._cache[key] = cls(group, c, k, d, device)
+        return cls._cache[key]

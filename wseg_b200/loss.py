@@ -66,8 +66,8 @@ def contrast_terms(f_proj1: torch.Tensor, cam_rv1_down: torch.Tensor, f_proj2: t
     f2, c2 = f_proj2, cam_rv2_down
     norm1, pl1 = ops.seed_labels(c1, label, bg_threshold)
     norm2, pl2 = ops.seed_labels(c2, label, bg_threshold)
-    proto1, ti1 = ops.prototypes(norm1, f1, group=group)
-    proto2, ti2 = ops.prototypes(norm2, f2, group=group)
+    proto1, ti1 = ops.prototypes(norm1, f1, group=group, view=0)
+    proto2, ti2 = ops.prototypes(norm2, f2, group=group, view=1)
     if keys is not None:            # precomputed device-resident mining keys (e.g. when the step is captured in a CUDA graph)
         key1, key2 = keys
     elif rng is None:

@@ -6,6 +6,7 @@ or CPU fallback: a missing library or a non-sm_100 device raises.
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -308,10 +309,14 @@ def proto_finalize(cand_val: torch.Tensor, cand_idx: torch.Tensor, cand_fea: tor
     return proto, sel
 
 
-def prototypes(norm_cam: torch.Tensor, f_proj: torch.Tensor, k: Optional[int] = None, group=None):
+def prototypes(norm_cam: torch.Tensor, f_proj: torch.Tensor, k: Optional[int] = None, group=None, view: int = 0,
+               exchange: Optional[str] = None):
     """contrast_train.py:199-209 with whole-batch semantics.  With a process group the batch is the union of all
-    ranks' shards (rank r owns pixels [r*P_local, (r+1)*P_local)): local candidates are all-gathered (the only
+    ranks' shards (rank r owns pixels [r*P_local, (r+1)*P_local)): local candidates are exchanged (the only
     collective on the path) and every rank finalises the same global prototypes, bit-identically.
+    ``exchange``: "nvlink" = one-shot stores into every peer's symmetric buffer from this rank's kernel (no NCCL
+    kernel; ``view`` in {0,1} selects the slot), "nccl" = one all_gather_into_tensor; default: $WSEG_EXCHANGE or
+    "nvlink" with a fall back to "nccl" if symmetric memory cannot be set up.
     Returns (prototypes [C,D], top_idx [C,k] int32 global pixel ids)."""
     n, c, h, w = norm_cam.shape
     if k is None:
@@ -319,9 +324,45 @@ def prototypes(norm_cam: torch.Tensor, f_proj: torch.Tensor, k: Optional[int] = 
     from . import dist as _dist
     rank, world = _dist.rank_world(group)
     tv, ti, tf = proto_topk_local(norm_cam, f_proj, k, pixel_offset=rank * n * h * w)
-    if world > 1:
-        tv, ti, tf = _dist.gather_candidates(tv, ti, tf, group)
+    if world == 1:
+        return proto_finalize(tv, ti, tf, k)
+    mode = exchange or os.environ.get("WSEG_EXCHANGE", "nvlink")
+    if mode == "nvlink":
+        ex = _symm_exchange(group, c, k, tf.shape[-1], norm_cam.device)
+        if ex is not None:
+            return _prototypes_nvlink(ex, tv, ti, tf, k, view)
+    tv, ti, tf = _dist.gather_candidates(tv, ti, tf, group)
     return proto_finalize(tv, ti, tf, k)
+
+
+_SYMM_FAILED = False
+
+
+def _symm_exchange(group, c, k, d, device):
+    global _SYMM_FAILED
+    if _SYMM_FAILED:
+        return None
+    from . import dist as _dist
+    try:
+        return _dist.SymmExchange.get(group, c, k, d, device)
+    except Exception as exc:          # no peer access / no symmetric-memory support on this stack: NCCL all-gather instead
+        import warnings
+        warnings.warn(f"wseg_b200: NVLink symmetric exchange unavailable ({type(exc).__name__}: {exc}); using NCCL")
+        _SYMM_FAILED = True
+        return None
+
+
+def _prototypes_nvlink(ex, tv, ti, tf, k: int, view: int):
+    c, _, d = tf.shape
+    dev = tv.device
+    proto = torch.empty(c, d, dtype=torch.float32, device=dev)
+    sel = torch.empty(c, k, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.lib().wsegk_proto_push(_ptr(tv), _ptr(ti), _ptr(tf), ex.peer_bases, ex.world, ex.rank, int(view), c, k, d,
+                                          _ptr(ex.state), _stream(tv)), "wsegk_proto_push")
+        check(_lib.lib().wsegk_proto_finalize_symm(_ptr(ex.buf), ex.world, int(view), k, _ptr(proto), _ptr(sel), c, d,
+                                                   _ptr(ex.state), _stream(tv)), "wsegk_proto_finalize_symm")
+    return proto, sel
 
 
 # --------------------------------------------------------------------------------------------- K4
