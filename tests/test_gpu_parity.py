@@ -205,7 +205,8 @@ def _views(n, hw1, hw2, seed, d=128, dev="cpu"):
 
 @pytest.mark.parametrize("n,hw1,hw2,d", [(2, (192, 192), (128, 128), 128), (8, 448, (128, 128), 128),
                                          (4, (256, 320), (160, 96), 128), (16, (512, 512), (256, 256), 128),
-                                         (2, (128, 128), (128, 128), 256)])
+                                         (2, (128, 128), (128, 128), 256),
+                                         (5, (512, 512), (512, 512), 128)])       # P = 20480: large-plane paths
 def test_contrast_terms_vs_oracle(cuda_dev, n, hw1, hw2, d):
     if isinstance(hw1, int):
         hw1 = (hw1, hw1)
@@ -276,6 +277,54 @@ def test_contrast_terms_vs_oracle(cuda_dev, n, hw1, hw2, d):
         assert rel_max(mg, rg) <= TOL
     if all_clean:
         assert rel_max(f1.grad, r1.grad) <= TOL and rel_max(f2.grad, r2.grad) <= TOL
+
+
+@pytest.mark.parametrize("n,g,d,rng", [(2, 16, 128, None), (3, 24, 128, 11), (8, 32, 256, None), (1, 8, 128, 5)])
+def test_large_plane_paths_equal_small_plane_paths(cuda_dev, n, g, d, rng):
+    """K3's top-k and K4's hard-pixel mining switch to a multi-CTA radix select (csrc/segselect.cuh) on large loss
+    grids; forced on at a small size it must reproduce the single-CTA / pairwise paths bit for bit — including the
+    {0,1} keys of the reference-RNG mode, where every membership is decided by the index tie-break."""
+    a, b = _views(n, (g * 8, g * 8), (g * 8, g * 8), seed=40 + n, d=d, dev=cuda_dev)
+    label = synth.label_with_bg(synth.labels(n, seed=n)).to(cuda_dev)
+    out = []
+    for forced in (False, True):
+        ops.force_radix(forced)
+        try:
+            tv, ti, tf = ops.proto_topk_local(ops.seed_labels(a["cam_rv_down"], label, 0.2)[0], a["f_proj"])
+            t = L.contrast_terms(a["f_proj"], a["cam_rv_down"], b["f_proj"], b["cam_rv_down"], label, 0.2,
+                                 grid=(g, g), rng=rng, want_mined=True)
+        finally:
+            ops.force_radix(False)
+        out.append((tv, ti, tf, t))
+    for x, y in zip(out[0][:3], out[1][:3]):
+        assert torch.equal(x, y)
+    for k in ("losses_raw", "grad_f1", "grad_f2", "mined1", "mined2", "top_indices1", "top_indices2", "prototypes1",
+              "prototypes2"):
+        assert torch.equal(out[0][3][k], out[1][3][k]), k
+    assert int(out[0][3]["mined1"].sum()) > 0
+
+
+def test_topk_large_plane_vs_torch(cuda_dev):
+    """P = 8 * 64 * 64 = 32768 pixels per class plane (above the single-CTA limit): indices against torch.topk on the
+    GPU (distinct values) and with heavy ties against the canonical (value, lowest index) order."""
+    g = torch.Generator(device="cpu").manual_seed(3)
+    n, c, h, w, d = 8, 21, 64, 64, 128
+    norm = torch.rand(n, c, h, w, generator=g).to(cuda_dev)
+    fea = torch.randn(n, d, h, w, generator=g).to(cuda_dev)
+    k = h * w // 8
+    tv, ti, tf = ops.proto_topk_local(norm, fea, k)
+    flat = norm.permute(1, 0, 2, 3).reshape(c, -1)
+    rv, ri = torch.topk(flat, k, dim=1)
+    assert torch.equal(tv, rv)
+    assert torch.equal(ti.long(), ri) or torch.equal(flat.gather(1, ti.long()), rv)       # equal values may swap in ATen
+    rows = fea.permute(0, 2, 3, 1).reshape(-1, d)
+    assert torch.equal(tf, rows[ti.long().reshape(-1)].reshape(c, k, d))
+    tied = (norm * 4).floor() / 4                               # 4 distinct values: ties everywhere
+    tv2, ti2, _ = ops.proto_topk_local(tied, fea, k)
+    flat2 = tied.permute(1, 0, 2, 3).reshape(c, -1)
+    order = torch.sort(flat2, dim=1, descending=True, stable=True)[1][:, :k]
+    assert torch.equal(ti2.long(), order)
+    assert torch.equal(tv2, flat2.gather(1, order))
 
 
 def test_contrast_step_loss_golden(cuda_dev, golden_dir):

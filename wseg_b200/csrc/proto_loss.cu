@@ -7,6 +7,7 @@
 #include <cfloat>
 
 #include "common.cuh"
+#include "segselect.cuh"
 
 namespace wsegk {
 
@@ -50,11 +51,29 @@ __device__ void bitonic_desc(unsigned long long* keys, uint32_t* pay, int n) {
 constexpr int kTopkThreads = 1024;
 constexpr int kTopkMaxK = 4096;
 
-// one CTA per class: radix-select the k largest keys over the whole batch plane, sort them, gather features.
-// kCached: the plane fits kTopkRegs keys per thread, so the keys are built once and live in registers; the select
-// passes then only touch shared memory (a pass that re-reads the plane costs a global-memory latency).
+// tail shared by both selection paths: s_keys holds the k selected keys (rest zero) -> sort (value desc, index asc),
+// write values and global pixel ids, gather the (un-normalised) features top_fea[c][t][d] = f_proj[n][d][q]
+__device__ void topk_emit(unsigned long long* s_keys, int c, int k, int kpad, int pixel_offset,
+                          const float* __restrict__ f_proj, float* __restrict__ top_val, int32_t* __restrict__ top_idx,
+                          float* __restrict__ top_fea, int D, int HW) {
+    bitonic_desc<false>(s_keys, nullptr, kpad);
+    for (int t = threadIdx.x; t < k; t += blockDim.x) {
+        const unsigned long long key = s_keys[t];
+        const uint32_t idx = 0xFFFFFFFFu - static_cast<uint32_t>(key & 0xFFFFFFFFull);
+        top_val[c * k + t] = unordered_bits(static_cast<uint32_t>(key >> 32));     // the value the key was built from
+        top_idx[c * k + t] = static_cast<int32_t>(idx) + pixel_offset;
+    }
+    for (int e = threadIdx.x; e < k * D; e += blockDim.x) {
+        const int t = e / D, d = e - t * D;
+        const uint32_t idx = 0xFFFFFFFFu - static_cast<uint32_t>(s_keys[t] & 0xFFFFFFFFull);
+        const int n = idx / HW, q = idx - n * HW;
+        top_fea[(static_cast<size_t>(c) * k + t) * D + d] = __ldg(f_proj + (static_cast<size_t>(n) * D + d) * HW + q);
+    }
+}
+
+// Small planes (P <= kTopkRegs * 1024): one CTA per class radix-selects the k largest keys over the whole batch plane;
+// the keys are built once and live in registers, the select passes only touch shared memory.
 constexpr int kTopkRegs = 8;
-template <bool kCached>
 __global__ void __launch_bounds__(kTopkThreads) proto_topk_kernel(const float* __restrict__ norm_cam,
                                                                   const float* __restrict__ f_proj,
                                                                   int pixel_offset, int k, int kpad,
@@ -68,27 +87,22 @@ __global__ void __launch_bounds__(kTopkThreads) proto_topk_kernel(const float* _
     __shared__ int s_need, s_done, s_count;
     const int c = blockIdx.x;
     const int P = N * HW;
-    auto key_of = [&](int i) {
-        const int n = i / HW, q = i - n * HW;
-        return topk_key(__ldg(norm_cam + (static_cast<size_t>(n) * C + c) * HW + q), static_cast<uint32_t>(i));
-    };
     unsigned long long kreg[kTopkRegs];
-    if (kCached) {
 #pragma unroll
-        for (int j = 0; j < kTopkRegs; ++j) {
-            const int i = threadIdx.x + j * kTopkThreads;
-            kreg[j] = i < P ? key_of(i) : 0ull;
+    for (int j = 0; j < kTopkRegs; ++j) {
+        const int i = threadIdx.x + j * kTopkThreads;
+        if (i < P) {
+            const int n = i / HW, q = i - n * HW;
+            kreg[j] = topk_key(__ldg(norm_cam + (static_cast<size_t>(n) * C + c) * HW + q), static_cast<uint32_t>(i));
+        } else {
+            kreg[j] = 0ull;
         }
     }
     // visit every key of the plane: f(key)
     auto for_each_key = [&](auto&& f) {
-        if (kCached) {
 #pragma unroll
-            for (int j = 0; j < kTopkRegs; ++j)
-                if (threadIdx.x + j * kTopkThreads < P) f(kreg[j]);
-        } else {
-            for (int i = threadIdx.x; i < P; i += blockDim.x) f(key_of(i));
-        }
+        for (int j = 0; j < kTopkRegs; ++j)
+            if (threadIdx.x + j * kTopkThreads < P) f(kreg[j]);
     };
     if (threadIdx.x == 0) { s_prefix = 0ull; s_need = k; s_done = 0; s_count = 0; }
     int shift = 56;
@@ -151,20 +165,80 @@ __global__ void __launch_bounds__(kTopkThreads) proto_topk_kernel(const float* _
             if (slot < kpad) s_keys[slot] = key;
         }
     });
-    bitonic_desc<false>(s_keys, nullptr, kpad);
-    for (int t = threadIdx.x; t < k; t += blockDim.x) {
-        const unsigned long long key = s_keys[t];
-        const uint32_t idx = 0xFFFFFFFFu - static_cast<uint32_t>(key & 0xFFFFFFFFull);
-        top_val[c * k + t] = unordered_bits(static_cast<uint32_t>(key >> 32));     // the value the key was built from
-        top_idx[c * k + t] = static_cast<int32_t>(idx) + pixel_offset;
+    topk_emit(s_keys, c, k, kpad, pixel_offset, f_proj, top_val, top_idx, top_fea, D, HW);
+}
+
+// Large planes: the thresholds come from the multi-CTA select (segselect.cuh) over all N*C*HW values at once.  Ascending
+// composite key = (~ordered(value)) above the flat pixel id: rank k-1 in ascending order is the k-th best pixel of the
+// canonical order (value desc, index asc), and the members are exactly the keys <= that threshold.
+struct TopkSrc {
+    const float* norm_cam;
+    int C, HW, idx_bits;
+    long long total;                  // N * C * HW
+    static constexpr int kSel = 1;
+    struct Elem { float v; };
+    __device__ long long count() const { return total; }
+    __device__ Elem load(long long e) const { return Elem{__ldg(norm_cam + e)}; }
+    __device__ void get(const Elem& x, long long e, int, int& slot, unsigned long long& key) const {
+        const long long plane = static_cast<long long>(C) * HW;
+        const long long n = e / plane, r = e - n * plane;
+        const int c = static_cast<int>(r / HW), q = static_cast<int>(r - static_cast<long long>(c) * HW);
+        slot = c;
+        key = (static_cast<unsigned long long>(static_cast<uint32_t>(~ordered_bits(x.v))) << idx_bits) |
+              static_cast<unsigned long long>(n * HW + q);
     }
-    // gather the (un-normalised) features of the selected pixels: top_fea[c][t][d] = f_proj[n][d][q]
-    for (int e = threadIdx.x; e < k * D; e += blockDim.x) {
-        const int t = e / D, d = e - t * D;
-        const uint32_t idx = 0xFFFFFFFFu - static_cast<uint32_t>(s_keys[t] & 0xFFFFFFFFull);
-        const int n = idx / HW, q = idx - n * HW;
-        top_fea[(static_cast<size_t>(c) * k + t) * D + d] = __ldg(f_proj + (static_cast<size_t>(n) * D + d) * HW + q);
+};
+__global__ void topk_sel_init_kernel(SegSel* __restrict__ state, int C, int k) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < C) state[c] = SegSel{0ull, k - 1, 1};
+}
+__global__ void __launch_bounds__(256) topk_compact_kernel(TopkSrc src, const SegSel* __restrict__ state,
+                                                           int* __restrict__ count, unsigned long long* __restrict__ cand,
+                                                           int k) {
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; e < src.total; e += stride) {
+        int c;
+        unsigned long long key;
+        src.get(src.load(e), e, 0, c, key);
+        if (key <= state[c].prefix) {
+            const int slot = atomicAdd(count + c, 1);
+            if (slot < k) cand[static_cast<size_t>(c) * k + slot] = key;
+        }
     }
+}
+__global__ void __launch_bounds__(kTopkThreads) topk_tail_kernel(const unsigned long long* __restrict__ cand,
+                                                                 const float* __restrict__ f_proj, int pixel_offset,
+                                                                 int k, int kpad, int idx_bits,
+                                                                 float* __restrict__ top_val,
+                                                                 int32_t* __restrict__ top_idx,
+                                                                 float* __restrict__ top_fea, int D, int HW) {
+    extern __shared__ unsigned long long s_keys[];      // kpad
+    const int c = blockIdx.x;
+    for (int i = threadIdx.x; i < kpad; i += blockDim.x) {
+        unsigned long long key = 0ull;
+        if (i < k) {
+            const unsigned long long a = cand[static_cast<size_t>(c) * k + i];
+            const uint32_t ordv = ~static_cast<uint32_t>(a >> idx_bits);
+            const uint32_t idx = static_cast<uint32_t>(a & ((1ull << idx_bits) - 1ull));
+            key = (static_cast<unsigned long long>(ordv) << 32) | (0xFFFFFFFFu - idx);
+        }
+        s_keys[i] = key;
+    }
+    topk_emit(s_keys, c, k, kpad, pixel_offset, f_proj, top_val, top_idx, top_fea, D, HW);
+}
+
+struct TopkLayout { size_t off_state, off_count, off_hist, off_cand, clear_bytes, total; };
+static TopkLayout topk_layout(int C) {
+    TopkLayout L{};
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    L.off_state = take(static_cast<size_t>(C) * sizeof(SegSel));
+    L.off_count = take(static_cast<size_t>(C) * sizeof(int));
+    L.off_hist = take(static_cast<size_t>(C) * kSegBins * sizeof(uint32_t));
+    L.clear_bytes = off;
+    L.off_cand = take(static_cast<size_t>(C) * kTopkMaxK * sizeof(unsigned long long));
+    L.total = align_up(off, 1024);
+    return L;
 }
 
 // Where the candidates of all ranks live: either three plain tensors ([C][n_cand], [C][n_cand], [C][n_cand][D], what an
@@ -249,20 +323,51 @@ __global__ void __launch_bounds__(1024) proto_finalize_kernel(CandSrc src, int n
     const float wsum = s_scale;
     float sq = 0.f;
     float mine[4] = {0.f, 0.f, 0.f, 0.f};          // D <= 4 * blockDim
-    int slot = 0;
-    for (int d = threadIdx.x; d < D; d += blockDim.x, ++slot) {
-        float acc = 0.f;
-        for (int t0 = 0; t0 < k; t0 += 8) {                   // eight independent loads in flight, fixed order of adds
-            float fv[8];
+    const int Dp = (D + 31) & ~31;
+    if (Dp <= 512 && blockDim.x == 1024) {
+        // thread (part, d): the k candidates are split into 1024/Dp contiguous parts so all threads gather; the parts
+        // are combined in a fixed order
+        __shared__ float s_acc[1024];
+        const int nparts = 1024 / Dp;
+        const int part = threadIdx.x / Dp, d = threadIdx.x - part * Dp;
+        const int per = (k + nparts - 1) / nparts;
+        if (part < nparts && d < D) {
+            const int t_end = min(k, (part + 1) * per);
+            float acc = 0.f;
+            for (int t0 = part * per; t0 < t_end; t0 += 8) {  // eight independent loads in flight, fixed order of adds
+                float fv[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) fv[j] = (t0 + j < k) ? src.feature(c, s_pos[t0 + j], d) : 0.f;
+                for (int j = 0; j < 8; ++j) fv[j] = (t0 + j < t_end) ? src.feature(c, s_pos[t0 + j], d) : 0.f;
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (t0 + j < k) acc = fmaf(s_w[t0 + j], fv[j], acc);
+                for (int j = 0; j < 8; ++j)
+                    if (t0 + j < t_end) acc = fmaf(s_w[t0 + j], fv[j], acc);
+            }
+            s_acc[part * Dp + d] = acc;
         }
-        acc /= wsum;
-        mine[slot] = acc;
-        sq = fmaf(acc, acc, sq);
+        __syncthreads();
+        if (threadIdx.x < D) {
+            float acc = 0.f;
+            for (int q = 0; q < nparts; ++q) acc += s_acc[q * Dp + threadIdx.x];
+            acc /= wsum;
+            mine[0] = acc;
+            sq = acc * acc;
+        }
+    } else {
+        int slot = 0;
+        for (int d = threadIdx.x; d < D; d += blockDim.x, ++slot) {
+            float acc = 0.f;
+            for (int t0 = 0; t0 < k; t0 += 8) {               // eight independent loads in flight, fixed order of adds
+                float fv[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) fv[j] = (t0 + j < k) ? src.feature(c, s_pos[t0 + j], d) : 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (t0 + j < k) acc = fmaf(s_w[t0 + j], fv[j], acc);
+            }
+            acc /= wsum;
+            mine[slot] = acc;
+            sq = fmaf(acc, acc, sq);
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
@@ -275,7 +380,7 @@ __global__ void __launch_bounds__(1024) proto_finalize_kernel(CandSrc src, int n
     }
     __syncthreads();
     const float nrm = s_scale;
-    slot = 0;
+    int slot = 0;
     for (int d = threadIdx.x; d < D; d += blockDim.x, ++slot) proto[c * D + d] = mine[slot] / nrm;
 }
 
@@ -330,7 +435,7 @@ __global__ void __launch_bounds__(256) proto_push_kernel(const float* __restrict
     }
 }
 
-size_t proto_workspace_bytes(int, int, int, int) { return 1024; }
+size_t proto_workspace_bytes(int, int C, int, int) { return topk_layout(C).total; }
 
 // ================================================================================================
 // K4
@@ -358,11 +463,14 @@ struct NceView {
     int* rank_sim;             // [P]
     int* rank_rnd;             // [P]
     int* cls_count;            // [32]
+    SegSel* sel_state;         // [3][kNceMaxC] thresholds of the large-P mining path (keys at ranks half, kk-half, kk)
+    uint32_t* sel_hist;        // [3][kNceMaxC][kSegBins]
     float* partial;            // [nblk][4]: cross, cross2, intra(weighted), unused
 };
 struct NceParams {
     NceView v[2];
     int N, C, D, HW, P, nblk;
+    int idx_bits;              // > 0: mining by thresholds (sel_state) instead of pairwise ranks
     const float* grad_scale;
     float* losses;
 };
@@ -549,6 +657,40 @@ __global__ void __launch_bounds__(kMineThreads) nce_mine_kernel(NceParams prm) {
     if (rr) atomicAdd(&V.rank_rnd[p], rr);
 }
 
+// ---- B (large P): the same membership as THRESHOLDS -----------------------------------------------
+// rank_rnd < half  <=>  (key, p) < [element at rank half];   kk-half <= rank_sim < kk  <=>  [rank kk-half] <= (sim, p) < [rank kk]
+// The three order statistics per class come from the multi-CTA select (segselect.cuh): O(P) per pass instead of O(P^2).
+__device__ __forceinline__ unsigned long long mine_key(uint32_t value_bits, int p, int idx_bits) {
+    return (static_cast<unsigned long long>(value_bits) << idx_bits) | static_cast<unsigned long long>(p);
+}
+struct MineSrc {
+    const int32_t* pl;
+    const float* sim;
+    const uint32_t* rkey;
+    int P, idx_bits;
+    static constexpr int kSel = 3;
+    struct Elem { int cls; unsigned long long ks, kr; };
+    __device__ long long count() const { return P; }
+    __device__ Elem load(long long e) const {
+        const int p = static_cast<int>(e);
+        return Elem{pl[p], mine_key(ordered_bits(sim[p]), p, idx_bits), mine_key(rkey[p], p, idx_bits)};
+    }
+    __device__ void get(const Elem& x, long long, int s, int& slot, unsigned long long& key) const {
+        slot = s * kNceMaxC + x.cls;
+        key = s == 0 ? x.kr : x.ks;
+    }
+};
+__global__ void mine_sel_init_kernel(NceParams prm) {       // <<<2, 96>>>
+    const NceView& V = prm.v[blockIdx.x];
+    const int sel = threadIdx.x >> 5, c = threadIdx.x & 31;
+    if (sel >= 3 || c >= kNceMaxC) return;
+    const int len = c < prm.C ? V.cls_count[c] : 0;
+    const int half = len >> 1;
+    const int kk = static_cast<int>(static_cast<double>(len) * 0.6);      // int(len_class * 0.6)
+    const int r = sel == 0 ? half : (sel == 1 ? kk - half : kk);
+    V.sel_state[sel * kNceMaxC + c] = SegSel{0ull, r, len >= 2 ? 1 : 0};
+}
+
 // ---- C: weights, loss partials and gradient w.r.t. the un-normalised features ---------------------
 __global__ void __launch_bounds__(kNceThreads) nce_grad_kernel(NceParams prm) {
     extern __shared__ float s_dyn[];
@@ -603,9 +745,17 @@ __global__ void __launch_bounds__(kNceThreads) nce_grad_kernel(NceParams prm) {
         const int half = len >> 1;
         int cnt = 0;
         if (len >= 2) {
-            const int kk = static_cast<int>(static_cast<double>(len) * 0.6);      // int(len_class * 0.6)
-            const int rs = V.rank_sim[p], rr = V.rank_rnd[p];
-            cnt = (rr < half ? 1 : 0) + ((rs >= kk - half && rs < kk) ? 1 : 0);
+            if (prm.idx_bits > 0) {
+                const unsigned long long ks = mine_key(ordered_bits(V.sim[p]), p, prm.idx_bits);
+                const unsigned long long kr = mine_key(V.rkey[p], p, prm.idx_bits);
+                const SegSel* st = V.sel_state + lo;
+                cnt = (kr < st[0].prefix ? 1 : 0) +
+                      ((ks >= st[kNceMaxC].prefix && ks < st[2 * kNceMaxC].prefix) ? 1 : 0);
+            } else {
+                const int kk = static_cast<int>(static_cast<double>(len) * 0.6);  // int(len_class * 0.6)
+                const int rs = V.rank_sim[p], rr = V.rank_rnd[p];
+                cnt = (rr < half ? 1 : 0) + ((rs >= kk - half && rs < kk) ? 1 : 0);
+            }
         }
         if (V.mined) V.mined[p] = cnt;
         const float w_x = 0.05f / static_cast<float>(P);                            // 0.1 * mean / 2
@@ -683,19 +833,30 @@ __global__ void __launch_bounds__(kNceThreads) nce_grad_kernel(NceParams prm) {
 }
 
 // ---- D: fixed-order final sums (one warp; lane l adds blocks l, l+32, ... then a shuffle tree) -------------
-__global__ void nce_finalize_kernel(NceParams prm) {
-    const int lane = threadIdx.x;
-    float s[2][3];
-    for (int v = 0; v < 2; ++v) {
-        for (int j = 0; j < 3; ++j) {
-            float acc = 0.f;
-            for (int b = lane; b < prm.nblk; b += 32) acc += prm.v[v].partial[b * 4 + j];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            s[v][j] = acc;
+__global__ void __launch_bounds__(192) nce_finalize_kernel(NceParams prm) {
+    // warp (v, j) sums partial j of view v: lane l adds blocks l, l+32, ... (four independent loads in flight, added in
+    // block order), then a shuffle tree; thread 0 combines
+    __shared__ float s_sum[6];
+    const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
+    {
+        const int v = wv / 3, j = wv - 3 * v;
+        const float* part = prm.v[v].partial + j;
+        float acc = 0.f;
+        int b = lane;
+        for (; b + 96 < prm.nblk; b += 128) {
+            const float x0 = part[b * 4], x1 = part[(b + 32) * 4], x2 = part[(b + 64) * 4], x3 = part[(b + 96) * 4];
+            acc += x0; acc += x1; acc += x2; acc += x3;
         }
+        for (; b < prm.nblk; b += 32) acc += part[b * 4];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) s_sum[wv] = acc;
     }
-    if (lane != 0) return;
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    float s[2][3];
+    for (int v = 0; v < 2; ++v)
+        for (int j = 0; j < 3; ++j) s[v][j] = s_sum[v * 3 + j];
     const float invP = 1.f / static_cast<float>(prm.P);
     float* L = prm.losses;
     L[0] = s[0][0] * invP;            // nce(q1, proto2, pl1)
@@ -710,9 +871,10 @@ __global__ void nce_finalize_kernel(NceParams prm) {
     L[9] = L[6] + L[7] + L[8];
 }
 
+constexpr int kMinePairwiseMaxP = 16384;      // above this the O(P^2) pairwise ranks lose to the multi-pass select
 struct NceLayout {
-    size_t per_view, total;
-    size_t off_inv, off_sim, off_ell, off_mask, off_sown, off_soth, off_rs, off_rr, off_cls, off_part;
+    size_t per_view, total, clear_bytes;
+    size_t off_inv, off_sim, off_ell, off_mask, off_sown, off_soth, off_rs, off_rr, off_cls, off_state, off_hist, off_part;
     int nblk;
 };
 static NceLayout nce_layout(int N, int C, int h, int w) {
@@ -721,9 +883,15 @@ static NceLayout nce_layout(int N, int C, int h, int w) {
     L.nblk = static_cast<int>((P + kNcePix - 1) / kNcePix);
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
-    L.off_rs = take(P * 4);            // rank arrays + class counts first: one memset clears them
-    L.off_rr = take(P * 4);
+    // what one memset clears: pairwise path = rank arrays + class counts, select path = class counts + state + histograms
+    // (both regions are always carved so the size does not depend on the debug switch)
+    const size_t small = P <= static_cast<size_t>(kMinePairwiseMaxP) ? P : static_cast<size_t>(kMinePairwiseMaxP);
+    L.off_rs = take(small * 4);
+    L.off_rr = take(small * 4);
     L.off_cls = take(32 * 4);
+    L.off_state = take(3 * kNceMaxC * sizeof(SegSel));
+    L.off_hist = take(static_cast<size_t>(3) * kNceMaxC * kSegBins * sizeof(uint32_t));
+    L.clear_bytes = off;
     L.off_inv = take(P * 4);
     L.off_sim = take(P * 4);
     L.off_ell = take(P * 4);
@@ -741,6 +909,13 @@ size_t contrast_workspace_bytes(int N, int C, int, int h, int w) { return nce_la
 
 using namespace wsegk;
 
+// tests: take the large-plane (multi-CTA select) paths of K3 and K4 whatever the size (wsegk_debug_force_radix)
+static int g_force_radix = 0;
+extern "C" int wsegk_debug_force_radix(int on) {
+    g_force_radix = on ? 1 : 0;
+    return WSEGK_OK;
+}
+
 static int next_pow2(int v) {
     int p = 1;
     while (p < v) p <<= 1;
@@ -750,7 +925,6 @@ static int next_pow2(int v) {
 extern "C" int wsegk_proto_topk_local(const float* norm_cam, const float* f_proj, int pixel_offset, int k,
                                       float* top_val, int32_t* top_idx, float* top_fea, int N, int C, int D, int h,
                                       int w, void* workspace, size_t workspace_bytes, wsegk_stream_t stream) {
-    (void)workspace; (void)workspace_bytes;
     if (int rc = check_device()) return rc;
     WSEGK_REQUIRE(norm_cam && f_proj && top_val && top_idx && top_fea, WSEGK_ERR_NULL, "proto_topk_local: null pointer");
     WSEGK_REQUIRE(N > 0 && C > 0 && D > 0 && h > 0 && w > 0, WSEGK_ERR_BAD_SHAPE, "proto_topk_local: bad dims");
@@ -760,18 +934,35 @@ extern "C" int wsegk_proto_topk_local(const float* norm_cam, const float* f_proj
     WSEGK_REQUIRE(P + pixel_offset < (1ll << 31), WSEGK_ERR_BAD_SHAPE, "proto_topk_local: pixel index overflow");
     const int kpad = next_pow2(k);
     const size_t smem = static_cast<size_t>(kpad) * sizeof(unsigned long long);
-    if (P <= static_cast<long long>(kTopkRegs) * kTopkThreads) {
-        WSEGK_CUDA_OK(cudaFuncSetAttribute(proto_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (P <= static_cast<long long>(kTopkRegs) * kTopkThreads && !g_force_radix) {
+        WSEGK_CUDA_OK(cudaFuncSetAttribute(proto_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            static_cast<int>(smem)));
-        proto_topk_kernel<true><<<C, kTopkThreads, smem, stream>>>(norm_cam, f_proj, pixel_offset, k, kpad, top_val,
-                                                                   top_idx, top_fea, N, C, D, h * w);
+        proto_topk_kernel<<<C, kTopkThreads, smem, stream>>>(norm_cam, f_proj, pixel_offset, k, kpad, top_val, top_idx,
+                                                             top_fea, N, C, D, h * w);
+        count_launches(1);
     } else {
-        WSEGK_CUDA_OK(cudaFuncSetAttribute(proto_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        // multi-CTA select over all N*C*HW values, compaction of the k winners per class, then sort + gather per class
+        const TopkLayout L = topk_layout(C);
+        WSEGK_REQUIRE(workspace && workspace_bytes >= L.total, WSEGK_ERR_WORKSPACE_TOO_SMALL,
+                      "proto_topk_local: workspace %zu < %zu", workspace_bytes, L.total);
+        uint8_t* ws = static_cast<uint8_t*>(workspace);
+        SegSel* state = reinterpret_cast<SegSel*>(ws + L.off_state);
+        int* count = reinterpret_cast<int*>(ws + L.off_count);
+        uint32_t* hist = reinterpret_cast<uint32_t*>(ws + L.off_hist);
+        unsigned long long* cand = reinterpret_cast<unsigned long long*>(ws + L.off_cand);
+        TopkSrc src{norm_cam, C, h * w, index_bits(P), P * C};
+        WSEGK_CUDA_OK(cudaMemsetAsync(ws, 0, L.clear_bytes, stream));
+        topk_sel_init_kernel<<<1, 32 * ceil_div(C, 32), 0, stream>>>(state, C, k);
+        int launches = 1 + seg_select_run(src, src.total, 32 + src.idx_bits, C, state, hist, stream);
+        long long blocks = (src.total + 255) / 256;
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        topk_compact_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(src, state, count, cand, k);
+        WSEGK_CUDA_OK(cudaFuncSetAttribute(topk_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            static_cast<int>(smem)));
-        proto_topk_kernel<false><<<C, kTopkThreads, smem, stream>>>(norm_cam, f_proj, pixel_offset, k, kpad, top_val,
-                                                                    top_idx, top_fea, N, C, D, h * w);
+        topk_tail_kernel<<<C, kTopkThreads, smem, stream>>>(cand, f_proj, pixel_offset, k, kpad, src.idx_bits, top_val,
+                                                            top_idx, top_fea, D, h * w);
+        count_launches(launches + 2);
     }
-    count_launches(1);
     WSEGK_CUDA_OK(cudaGetLastError());
     return WSEGK_OK;
 }
@@ -863,8 +1054,8 @@ extern "C" int wsegk_contrast_loss_fwd_bwd(const float* x1, const float* x2, con
                   "contrast_loss_fwd_bwd: need 13 <= C <= %d (semi-hard mining takes ranks 3..12), got C=%d",
                   kNceMaxC, C);
     const long long P = static_cast<long long>(N) * h * w;
-    WSEGK_REQUIRE(P <= (1 << 17), WSEGK_ERR_BAD_SHAPE,
-                  "contrast_loss_fwd_bwd: P=%lld pixels exceeds the pairwise mining limit of 131072", P);
+    WSEGK_REQUIRE(P < (1ll << 30), WSEGK_ERR_BAD_SHAPE, "contrast_loss_fwd_bwd: P=%lld pixels is too many", P);
+    const bool radix = P > kMinePairwiseMaxP || (g_force_radix && P >= 2);
     const size_t proto_smem = (static_cast<size_t>(kNceSlots) * (D + 1) + kNcePix * 49 + kNcePix * kNceGroups * 4 +
                                static_cast<size_t>(D) * kNcePix) * sizeof(float);
     WSEGK_REQUIRE(proto_smem <= 200 * 1024, WSEGK_ERR_BAD_SHAPE, "contrast_loss_fwd_bwd: D too large");
@@ -875,6 +1066,7 @@ extern "C" int wsegk_contrast_loss_fwd_bwd(const float* x1, const float* x2, con
     prm.N = N; prm.C = C; prm.D = D; prm.HW = h * w; prm.P = static_cast<int>(P); prm.nblk = L.nblk;
     prm.grad_scale = grad_scale;
     prm.losses = losses;
+    prm.idx_bits = radix ? index_bits(P) : 0;
     uint8_t* ws = static_cast<uint8_t*>(workspace);
     for (int v = 0; v < 2; ++v) {
         uint8_t* b = ws + v * L.per_view;
@@ -896,18 +1088,36 @@ extern "C" int wsegk_contrast_loss_fwd_bwd(const float* x1, const float* x2, con
         V.rank_sim = reinterpret_cast<int*>(b + L.off_rs);
         V.rank_rnd = reinterpret_cast<int*>(b + L.off_rr);
         V.cls_count = reinterpret_cast<int*>(b + L.off_cls);
+        V.sel_state = reinterpret_cast<SegSel*>(b + L.off_state);
+        V.sel_hist = reinterpret_cast<uint32_t*>(b + L.off_hist);
         V.partial = reinterpret_cast<float*>(b + L.off_part);
-        WSEGK_CUDA_OK(cudaMemsetAsync(b + L.off_rs, 0, L.off_inv - L.off_rs, stream));
+        if (radix)
+            WSEGK_CUDA_OK(cudaMemsetAsync(b + L.off_cls, 0, L.clear_bytes - L.off_cls, stream));
+        else
+            WSEGK_CUDA_OK(cudaMemsetAsync(b + L.off_rs, 0, L.off_state - L.off_rs, stream));
     }
     WSEGK_CUDA_OK(cudaFuncSetAttribute(nce_pixel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(proto_smem)));
     WSEGK_CUDA_OK(cudaFuncSetAttribute(nce_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(proto_smem)));
     nce_pixel_kernel<<<dim3(L.nblk, 2), kNceThreads, proto_smem, stream>>>(prm);
-    nce_mine_kernel<<<dim3(ceil_div(prm.P, kMineThreads), ceil_div(prm.P, kMineChunk), 2), kMineThreads, 0, stream>>>(prm);
+    int launches = 3;
+    if (radix) {
+        mine_sel_init_kernel<<<2, 96, 0, stream>>>(prm);
+        ++launches;
+        for (int v = 0; v < 2; ++v) {
+            const NceView& V = prm.v[v];
+            const MineSrc src{V.pl_own, V.sim, V.rkey, prm.P, prm.idx_bits};
+            launches += seg_select_run(src, prm.P, 32 + prm.idx_bits, 3 * kNceMaxC, V.sel_state, V.sel_hist, stream);
+        }
+    } else {
+        nce_mine_kernel<<<dim3(ceil_div(prm.P, kMineThreads), ceil_div(prm.P, kMineChunk), 2), kMineThreads, 0,
+                          stream>>>(prm);
+        ++launches;
+    }
     nce_grad_kernel<<<dim3(L.nblk, 2), kNceThreads, proto_smem, stream>>>(prm);
-    nce_finalize_kernel<<<1, 32, 0, stream>>>(prm);
-    count_launches(4);
+    nce_finalize_kernel<<<1, 32 * 6, 0, stream>>>(prm);
+    count_launches(launches);
     WSEGK_CUDA_OK(cudaGetLastError());
     return WSEGK_OK;
 }

@@ -121,6 +121,11 @@ def launch_count() -> int:
     return int(_lib.lib().wsegk_debug_launch_count())
 
 
+def force_radix(on: bool) -> None:
+    """Test aid: route K3's top-k and K4's mining through their large-plane (multi-CTA select) paths at any size."""
+    check(_lib.lib().wsegk_debug_force_radix(1 if on else 0), "wsegk_debug_force_radix")
+
+
 def pcm_profile(enable: bool) -> None:
     check(_lib.lib().wsegk_debug_pcm_profile(1 if enable else 0), "wsegk_debug_pcm_profile")
 
