@@ -282,7 +282,8 @@ def test_contrast_terms_vs_oracle(cuda_dev, n, hw1, hw2, d):
 @pytest.mark.parametrize("n,g,d,rng", [(2, 16, 128, None), (3, 24, 128, 11), (8, 32, 256, None), (1, 8, 128, 5)])
 def test_large_plane_paths_equal_small_plane_paths(cuda_dev, n, g, d, rng):
     """K3's top-k and K4's hard-pixel mining switch to a multi-CTA radix select (csrc/segselect.cuh) on large loss
-    grids; forced on at a small size it must reproduce the single-CTA / pairwise paths bit for bit — including the
+    grids, and K4's per-pixel kernels to 64-pixel tiles; forced on at a small size they must reproduce the single-CTA /
+    pairwise / 16-pixel paths bit for bit (per-pixel gradients, mined sets, indices, prototypes) — including the
     {0,1} keys of the reference-RNG mode, where every membership is decided by the index tie-break."""
     a, b = _views(n, (g * 8, g * 8), (g * 8, g * 8), seed=40 + n, d=d, dev=cuda_dev)
     label = synth.label_with_bg(synth.labels(n, seed=n)).to(cuda_dev)
@@ -298,9 +299,10 @@ def test_large_plane_paths_equal_small_plane_paths(cuda_dev, n, g, d, rng):
         out.append((tv, ti, tf, t))
     for x, y in zip(out[0][:3], out[1][:3]):
         assert torch.equal(x, y)
-    for k in ("losses_raw", "grad_f1", "grad_f2", "mined1", "mined2", "top_indices1", "top_indices2", "prototypes1",
-              "prototypes2"):
+    for k in ("grad_f1", "grad_f2", "mined1", "mined2", "top_indices1", "top_indices2", "prototypes1", "prototypes2"):
         assert torch.equal(out[0][3][k], out[1][3][k]), k
+    # the forced variant also uses the 64-pixel-tile kernels, whose per-block loss partials group the pixels differently
+    assert torch.allclose(out[0][3]["losses_raw"], out[1][3]["losses_raw"], rtol=2e-6, atol=0)
     assert int(out[0][3]["mined1"].sum()) > 0
 
 

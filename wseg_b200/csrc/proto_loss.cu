@@ -63,11 +63,26 @@ __device__ void topk_emit(unsigned long long* s_keys, int c, int k, int kpad, in
         top_val[c * k + t] = unordered_bits(static_cast<uint32_t>(key >> 32));     // the value the key was built from
         top_idx[c * k + t] = static_cast<int32_t>(idx) + pixel_offset;
     }
-    for (int e = threadIdx.x; e < k * D; e += blockDim.x) {
-        const int t = e / D, d = e - t * D;
-        const uint32_t idx = 0xFFFFFFFFu - static_cast<uint32_t>(s_keys[t] & 0xFFFFFFFFull);
-        const int n = idx / HW, q = idx - n * HW;
-        top_fea[(static_cast<size_t>(c) * k + t) * D + d] = __ldg(f_proj + (static_cast<size_t>(n) * D + d) * HW + q);
+    // eight independent (scattered) loads per thread in flight
+    const int total = k * D, step = static_cast<int>(blockDim.x);
+    for (int e0 = threadIdx.x; e0 < total; e0 += 8 * step) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int e = e0 + j * step;
+            v[j] = 0.f;
+            if (e < total) {
+                const int t = e / D, d = e - t * D;
+                const uint32_t idx = 0xFFFFFFFFu - static_cast<uint32_t>(s_keys[t] & 0xFFFFFFFFull);
+                const int n = idx / HW, q = idx - n * HW;
+                v[j] = __ldg(f_proj + (static_cast<size_t>(n) * D + d) * HW + q);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int e = e0 + j * step;
+            if (e < total) top_fea[static_cast<size_t>(c) * total + e] = v[j];
+        }
     }
 }
 
@@ -469,7 +484,8 @@ struct NceView {
 };
 struct NceParams {
     NceView v[2];
-    int N, C, D, HW, P, nblk;
+    int N, C, D, HW, P;
+    int nblk, nblk_grad;       // tiles of the pixel kernel (partials 0,1) and of the gradient kernel (partial 2)
     int idx_bits;              // > 0: mining by thresholds (sel_state) instead of pairwise ranks
     const float* grad_scale;
     float* losses;
@@ -487,7 +503,7 @@ static_assert(kNcePix * kNceGroups == kNceThreads, "thread mapping");
 
 // 48 x D prototype values into shared memory, eight independent loads per thread in flight (a rolled loop of
 // dependent load->store pairs cost 48 L2 latencies, ~20 us, in both kernels)
-__device__ __forceinline__ void nce_load_protos(const NceView& V, float* s_proto, int C, int D) {
+__device__ __forceinline__ void nce_load_protos(const NceView& V, float* s_proto, int C, int D, int pstride) {
     for (int d = threadIdx.x; d < D; d += blockDim.x) {
         for (int s0 = 0; s0 < kNceSlots; s0 += 8) {
             float v[8];
@@ -498,7 +514,7 @@ __device__ __forceinline__ void nce_load_protos(const NceView& V, float* s_proto
                 v[j] = c < C ? __ldg(src + c * D + d) : 0.f;
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) s_proto[(s0 + j) * (D + 1) + d] = v[j];
+            for (int j = 0; j < 8; ++j) s_proto[(s0 + j) * pstride + d] = v[j];
         }
     }
 }
@@ -526,6 +542,54 @@ __device__ __forceinline__ void nce_load_x(const NceView& V, float* s_x, int p0,
     }
 }
 
+// x tile of NPIX (= 64) consecutive loss pixels as [D][NPIX]; float4 loads when the layout allows (a quad of pixels
+// then never straddles two images), eight independent loads per thread in flight either way
+template <int NPIX>
+__device__ __forceinline__ void nce_tile_load_x(const NceView& V, float* s_x, int p0, int D, int HW, int P) {
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    if ((HW & 3) == 0 && (reinterpret_cast<uintptr_t>(V.x) & 15) == 0) {
+        constexpr int Q = NPIX / 4;
+        const int quad = tid % Q, d0 = tid / Q, dstep = nthr / Q;
+        const int p = p0 + 4 * quad;
+        const bool live = p < P;                               // P = N*HW is a multiple of 4 too
+        const int n = live ? p / HW : 0, q = live ? p - n * HW : 0;
+        const float4* src = reinterpret_cast<const float4*>(V.x + static_cast<size_t>(n) * D * HW + q);
+        const size_t row = static_cast<size_t>(HW >> 2);
+        for (int d = d0; d < D; d += 8 * dstep) {
+            float4 v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int dd = d + j * dstep;
+                v[j] = (live && dd < D) ? __ldg(src + dd * row) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int dd = d + j * dstep;
+                if (dd < D) *reinterpret_cast<float4*>(s_x + dd * NPIX + 4 * quad) = v[j];
+            }
+        }
+    } else {
+        const int pix = tid % NPIX, d0 = tid / NPIX, dstep = nthr / NPIX;
+        const int p = p0 + pix;
+        const bool live = p < P;
+        const int n = live ? p / HW : 0, q = live ? p - n * HW : 0;
+        const float* src = V.x + static_cast<size_t>(n) * D * HW + q;
+        for (int d = d0; d < D; d += 8 * dstep) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int dd = d + j * dstep;
+                v[j] = (live && dd < D) ? __ldg(src + static_cast<size_t>(dd) * HW) : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int dd = d + j * dstep;
+                if (dd < D) s_x[dd * NPIX + pix] = v[j];
+            }
+        }
+    }
+}
+
 // ---- A: per-pixel similarities and unweighted loss terms ----------------------------------------
 __global__ void __launch_bounds__(kNceThreads) nce_pixel_kernel(NceParams prm) {
     extern __shared__ float s_dyn[];
@@ -534,7 +598,7 @@ __global__ void __launch_bounds__(kNceThreads) nce_pixel_kernel(NceParams prm) {
     float* s_proto = s_dyn;                                   // [48][D+1]
     float* s_sc = s_dyn + kNceSlots * (D + 1);                // [kNcePix][49]
     float* s_x = s_sc + kNcePix * 49 + kNcePix * kNceGroups * 4;   // [D][kNcePix] features of the CTA's pixels
-    nce_load_protos(V, s_proto, C, D);
+    nce_load_protos(V, s_proto, C, D, D + 1);
     nce_load_x(V, s_x, blockIdx.x * kNcePix, D, HW, P);
     __syncthreads();
     const int pix = threadIdx.x & (kNcePix - 1), grp = threadIdx.x / kNcePix;
@@ -621,6 +685,144 @@ __global__ void __launch_bounds__(kNceThreads) nce_pixel_kernel(NceParams prm) {
     }
 }
 
+// ---- A (large P): 64 pixels per CTA, 4 pixels x 6 slots per thread ---------------------------------
+// The prototypes are kept transposed ([d][68]: slot 6g+j at column 8g+j) so a thread reads its six as float4 + float2,
+// and its four pixels of s_x[d][64] as one float4: 3 shared-memory instructions per 24 (+4) FMAs instead of 7 per 6 in
+// the 16-pixel kernel.  Each dot product is still accumulated over d in order by one thread: same values.
+constexpr int kTilePix = 64;
+constexpr int kGradTilePix = 32;       // 256 threads, two CTAs per SM
+constexpr int kTileProtoStride = 68;
+__global__ void __launch_bounds__(kNceThreads) nce_pixel_tile_kernel(NceParams prm) {
+    extern __shared__ __align__(16) float s_dyn[];
+    const NceView& V = prm.v[blockIdx.y];
+    const int C = prm.C, D = prm.D, HW = prm.HW, P = prm.P;
+    float* s_proto = s_dyn;                                    // [D][68]
+    float* s_x = s_proto + D * kTileProtoStride;               // [D][64]
+    float* s_sc = s_x + D * kTilePix;                          // [64][49]
+    float* s_part = s_sc + kTilePix * 49;                      // [64][8][4]
+    float* s_inv = s_part + kTilePix * kNceGroups * 4;         // [64]
+    __shared__ int s_cls[kNceMaxC];                            // pixels per pseudo-class seen by this CTA
+    if (threadIdx.x < kNceMaxC) s_cls[threadIdx.x] = 0;
+    // the CTA is persistent: the prototypes are staged once (all 48 loads of a thread in flight at once)
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        float v[kNceSlots];
+#pragma unroll
+        for (int slot = 0; slot < kNceSlots; ++slot) {
+            const int c = slot % kSlotHalf;
+            const float* src = slot < kSlotHalf ? V.proto_own : V.proto_oth;
+            v[slot] = c < C ? __ldg(src + c * D + d) : 0.f;
+        }
+#pragma unroll
+        for (int slot = 0; slot < kNceSlots; ++slot)
+            s_proto[d * kTileProtoStride + 8 * (slot / 6) + slot % 6] = v[slot];
+    }
+    for (int tile = blockIdx.x; tile < prm.nblk; tile += gridDim.x) {
+    const int p0 = tile * kTilePix;
+    nce_tile_load_x<kTilePix>(V, s_x, p0, D, HW, P);
+    __syncthreads();
+    {
+        const int pg = threadIdx.x & 15, sg = threadIdx.x >> 4;       // pixels 4pg..4pg+3, slots 6sg..6sg+5
+        float acc[4][6], ss[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 6; ++j) acc[i][j] = 0.f;
+        const float* xr = s_x + 4 * pg;
+        const float* pr = s_proto + 8 * sg;
+#pragma unroll 4
+        for (int d = 0; d < D; ++d) {
+            const float4 xv = *reinterpret_cast<const float4*>(xr + d * kTilePix);
+            const float4 pa = *reinterpret_cast<const float4*>(pr + d * kTileProtoStride);
+            const float2 pb = *reinterpret_cast<const float2*>(pr + d * kTileProtoStride + 4);
+            const float x[4] = {xv.x, xv.y, xv.z, xv.w};
+            const float pv[6] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                ss[i] = fmaf(x[i], x[i], ss[i]);
+#pragma unroll
+                for (int j = 0; j < 6; ++j) acc[i][j] = fmaf(x[i], pv[j], acc[i][j]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float inv = 1.f / fmaxf(sqrtf(ss[i]), 1e-12f);          // F.normalize
+#pragma unroll
+            for (int j = 0; j < 6; ++j) s_sc[(4 * pg + i) * 49 + 6 * sg + j] = acc[i][j] * inv;
+            if (sg == 0) s_inv[4 * pg + i] = inv;
+        }
+    }
+    __syncthreads();
+    // per-pixel scalars: thread (pix, grp) owns classes grp, grp+8, grp+16 of pixel pix = (tid & 15) + 16*sub
+    const int grp = threadIdx.x >> 4;
+    for (int sub = 0; sub < kTilePix / 16; ++sub) {
+        const int pix = (threadIdx.x & 15) + 16 * sub, p = p0 + pix;
+        if (p < P) {
+            float z_own = 0.f, z_oth = 0.f, a2 = 0.f;
+            uint32_t mask = 0u;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const int c = grp + kNceGroups * j;
+                if (c < C) {
+                    const float own_c = s_sc[pix * 49 + c], oth_c = s_sc[pix * 49 + kSlotHalf + c];
+                    V.s_own[static_cast<size_t>(c) * P + p] = own_c;
+                    V.s_oth[static_cast<size_t>(c) * P + p] = oth_c;
+                    const float e_own = expf(own_c * kInvT);
+                    z_own += e_own;
+                    z_oth += expf(oth_c * kInvT);
+                    int rank = 0;
+                    for (int e = 0; e < C; ++e) {
+                        const float own_e = s_sc[pix * 49 + e];
+                        rank += (own_e > own_c || (own_e == own_c && e < c)) ? 1 : 0;
+                    }
+                    if (rank >= 3 && rank < 13) { mask |= (1u << c); a2 += e_own; }
+                }
+            }
+            float* dstp = s_part + grp * 4 * kTilePix + pix;       // [grp][4][64]: conflict-free
+            dstp[0] = z_own; dstp[kTilePix] = z_oth; dstp[2 * kTilePix] = a2; dstp[3 * kTilePix] = __uint_as_float(mask);
+        }
+    }
+    __syncthreads();
+    float cross = 0.f, cross2 = 0.f;
+    if (grp == 0) {
+        for (int sub = 0; sub < kTilePix / 16; ++sub) {
+            const int pix = threadIdx.x + 16 * sub, p = p0 + pix;
+            if (p >= P) continue;
+            float z_own = 0.f, z_oth = 0.f, a2 = 0.f;
+            uint32_t mask = 0u;
+#pragma unroll
+            for (int g = 0; g < kNceGroups; ++g) {                 // fixed order
+                const float* sp = s_part + g * 4 * kTilePix + pix;
+                z_own += sp[0]; z_oth += sp[kTilePix]; a2 += sp[2 * kTilePix]; mask |= __float_as_uint(sp[3 * kTilePix]);
+            }
+            const int lo = V.pl_own[p], lt = V.pl_oth[p];
+            const float pos_own = s_sc[pix * 49 + lo], pos_oth_lo = s_sc[pix * 49 + kSlotHalf + lo];
+            const float pos_own_lt = s_sc[pix * 49 + lt];
+            cross += logf(z_oth) - pos_oth_lo * kInvT;
+            cross2 += logf(z_own) - pos_own_lt * kInvT;
+            a2 += expf(pos_own * kInvT);
+            V.setmask[p] = mask;
+            V.ell[p] = logf(a2) - pos_own * kInvT;
+            V.sim[p] = (pos_own + 1.f) * 0.5f;
+            V.inv_norm[p] = s_inv[pix];
+            atomicAdd(&s_cls[lo], 1);
+        }
+    }
+    if (threadIdx.x < 32) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            cross += __shfl_xor_sync(0xffffffffu, cross, o);
+            cross2 += __shfl_xor_sync(0xffffffffu, cross2, o);
+        }
+        if (threadIdx.x == 0) {
+            V.partial[tile * 4 + 0] = cross;
+            V.partial[tile * 4 + 1] = cross2;
+        }
+    }
+    __syncthreads();                                           // s_x / s_sc / s_part are rewritten by the next tile
+    }
+    if (threadIdx.x < C && s_cls[threadIdx.x] > 0) atomicAdd(&V.cls_count[threadIdx.x], s_cls[threadIdx.x]);
+}
+
 // ---- B: ranks inside each pseudo-class (hard-pixel mining, :302-322) -----------------------------
 // rank_sim[p] = #{p' same class : (sim', p') < (sim, p)},  rank_rnd likewise on (key, p).  Integer atomics only.
 constexpr int kMineThreads = 256;
@@ -692,43 +894,71 @@ __global__ void mine_sel_init_kernel(NceParams prm) {       // <<<2, 96>>>
 }
 
 // ---- C: weights, loss partials and gradient w.r.t. the un-normalised features ---------------------
-__global__ void __launch_bounds__(kNceThreads) nce_grad_kernel(NceParams prm) {
-    extern __shared__ float s_dyn[];
+// NPIX = 16: 128 threads (small loss grids, one CTA per 16 pixels keeps all SMs busy at P = 2048).
+// NPIX = 64: 512 threads; the prototype rows are read as float4 along d (4 channels per thread and step), which turns the
+// shared-memory : FMA instruction ratio from 1:1 into 1:4; same per-element order of operations, so the same values.
+template <int NPIX>
+__global__ void __launch_bounds__(NPIX * kNceGroups) nce_grad_kernel(NceParams prm) {
+    constexpr bool kVec = NPIX > kNcePix;
+    extern __shared__ __align__(16) float s_dyn[];
     const NceView& V = prm.v[blockIdx.y];
     const int C = prm.C, D = prm.D, HW = prm.HW, P = prm.P;
-    float* s_proto = s_dyn;                                   // [48][D+1]
-    float* s_coef = s_dyn + kNceSlots * (D + 1);              // [kNcePix][49]: d loss / d score per slot (times 1/T)
-    __shared__ float s_qdq[kNcePix], s_scale[kNcePix];
-    float* s_x = s_coef + kNcePix * 49 + kNcePix * kNceGroups * 4;  // [D][kNcePix]
-    nce_load_protos(V, s_proto, C, D);
-    nce_load_x(V, s_x, blockIdx.x * kNcePix, D, HW, P);
-    __shared__ int s_present;
-    if (threadIdx.x == 0) {
-        int pres = 0;
-        for (int c = 0; c < C; ++c) pres += V.cls_count[c] > 0 ? 1 : 0;
-        s_present = pres;
+    const int pstride = kVec ? D + 4 : D + 1;
+    float* s_proto = s_dyn;                                   // [48][pstride]
+    float* s_x = s_dyn + kNceSlots * pstride;                 // [D][NPIX] (16-byte aligned: D % 4 == 0)
+    float* s_coef = s_x + D * NPIX;                           // [NPIX][49]: d loss / d score per slot (times 1/T)
+    __shared__ float s_qdq[NPIX], s_scale[NPIX];
+    nce_load_protos(V, s_proto, C, D, pstride);
+    __shared__ int s_present, s_len[kNceMaxC];
+    __shared__ unsigned long long s_thr[3][kNceMaxC];
+    if (threadIdx.x < kNceMaxC) {
+        s_len[threadIdx.x] = threadIdx.x < C ? V.cls_count[threadIdx.x] : 0;
+        if (prm.idx_bits > 0)
+            for (int sel = 0; sel < 3; ++sel) s_thr[sel][threadIdx.x] = V.sel_state[sel * kNceMaxC + threadIdx.x].prefix;
     }
     __syncthreads();
-    const int pix = threadIdx.x & (kNcePix - 1), grp = threadIdx.x / kNcePix;
-    const int p = blockIdx.x * kNcePix + pix;
-    float intra = 0.f;
-    // per-pixel scalars over the pixel's 8 threads (classes grp, grp+8, grp+16), reduced through shared memory in a
-    // fixed order
-    float* s_part = s_coef + kNcePix * 49;                    // [kNcePix][kNceGroups][4]
-    __shared__ float s_w[kNcePix][4];                         // w_x, w_i, lo, lt per pixel
+    if (threadIdx.x == 0) {
+        int pres = 0;
+        for (int c = 0; c < C; ++c) pres += s_len[c] > 0 ? 1 : 0;
+        s_present = pres;
+    }
+    const int pix = threadIdx.x & (NPIX - 1), grp = threadIdx.x / NPIX;
+    // NPIX = 16 is launched with one CTA per tile; the 64-pixel variant is persistent (prototypes staged once per CTA)
+    for (int tile = blockIdx.x; tile < prm.nblk_grad; tile += gridDim.x) {
+    const int p = tile * NPIX + pix;
+    // this thread's per-pixel scalars first, so their loads are in flight together with the x tile's
     float ea[3] = {0.f, 0.f, 0.f}, eb[3] = {0.f, 0.f, 0.f}, so[3] = {0.f, 0.f, 0.f}, st[3] = {0.f, 0.f, 0.f};
     uint32_t mask = 0u;
     int lo = 0, lt = 0;
+    float g_sim = 0.f, g_ell = 0.f, g_inv = 0.f;
+    uint32_t g_key = 0u;
     if (p < P) {
         lo = V.pl_own[p]; lt = V.pl_oth[p];
         mask = V.setmask[p];
-        float z_own = 0.f, z_oth = 0.f, z_set = 0.f;
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
             const int c = grp + kNceGroups * j;
             if (c < C) {
                 so[j] = V.s_own[static_cast<size_t>(c) * P + p];
                 st[j] = V.s_oth[static_cast<size_t>(c) * P + p];
+            }
+        }
+        if (grp == 0) { g_sim = V.sim[p]; g_key = V.rkey[p]; g_ell = V.ell[p]; g_inv = V.inv_norm[p]; }
+    }
+    if (kVec) nce_tile_load_x<NPIX>(V, s_x, tile * NPIX, D, HW, P);
+    else nce_load_x(V, s_x, tile * kNcePix, D, HW, P);
+    __syncthreads();
+    float intra = 0.f;
+    // per-pixel scalars over the pixel's 8 threads (classes grp, grp+8, grp+16), reduced through shared memory in a
+    // fixed order
+    float* s_part = s_coef + NPIX * 49;                       // [NPIX][kNceGroups][4]
+    __shared__ float s_w[NPIX][4];                            // w_x, w_i, lo, lt per pixel
+    if (p < P) {
+        float z_own = 0.f, z_oth = 0.f, z_set = 0.f;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const int c = grp + kNceGroups * j;
+            if (c < C) {
                 ea[j] = expf(so[j] * kInvT);
                 eb[j] = expf(st[j] * kInvT);
                 z_own += ea[j];
@@ -737,20 +967,18 @@ __global__ void __launch_bounds__(kNceThreads) nce_grad_kernel(NceParams prm) {
                 z_set += static_cast<float>(mult) * ea[j];
             }
         }
-        float* dstp = s_part + (pix * kNceGroups + grp) * 4;
-        dstp[0] = z_own; dstp[1] = z_oth; dstp[2] = z_set; dstp[3] = 0.f;
+        float* dstp = s_part + grp * 4 * NPIX + pix;           // [grp][4][NPIX]: conflict-free
+        dstp[0] = z_own; dstp[NPIX] = z_oth; dstp[2 * NPIX] = z_set; dstp[3 * NPIX] = 0.f;
     }
     if (grp == 0 && p < P) {
-        const int len = V.cls_count[lo];
+        const int len = s_len[lo];
         const int half = len >> 1;
         int cnt = 0;
         if (len >= 2) {
             if (prm.idx_bits > 0) {
-                const unsigned long long ks = mine_key(ordered_bits(V.sim[p]), p, prm.idx_bits);
-                const unsigned long long kr = mine_key(V.rkey[p], p, prm.idx_bits);
-                const SegSel* st = V.sel_state + lo;
-                cnt = (kr < st[0].prefix ? 1 : 0) +
-                      ((ks >= st[kNceMaxC].prefix && ks < st[2 * kNceMaxC].prefix) ? 1 : 0);
+                const unsigned long long ks = mine_key(ordered_bits(g_sim), p, prm.idx_bits);
+                const unsigned long long kr = mine_key(g_key, p, prm.idx_bits);
+                cnt = (kr < s_thr[0][lo] ? 1 : 0) + ((ks >= s_thr[1][lo] && ks < s_thr[2][lo]) ? 1 : 0);
             } else {
                 const int kk = static_cast<int>(static_cast<double>(len) * 0.6);  // int(len_class * 0.6)
                 const int rs = V.rank_sim[p], rr = V.rank_rnd[p];
@@ -762,9 +990,9 @@ __global__ void __launch_bounds__(kNceThreads) nce_grad_kernel(NceParams prm) {
         const float w_i = cnt ? 0.05f * static_cast<float>(cnt) /
                                     (static_cast<float>(2 * half) * static_cast<float>(s_present))
                               : 0.f;
-        intra = w_i * V.ell[p];
+        intra = w_i * g_ell;
         s_w[pix][0] = w_x; s_w[pix][1] = w_i;
-        s_scale[pix] = V.inv_norm[p];
+        s_scale[pix] = g_inv;
     }
     __syncthreads();
     float qdq_part = 0.f;
@@ -772,8 +1000,8 @@ __global__ void __launch_bounds__(kNceThreads) nce_grad_kernel(NceParams prm) {
         float z_own = 0.f, z_oth = 0.f, z_set = 0.f;
 #pragma unroll
         for (int g = 0; g < kNceGroups; ++g) {                 // fixed order, identical in all 8 threads
-            const float* sp = s_part + (pix * kNceGroups + g) * 4;
-            z_own += sp[0]; z_oth += sp[1]; z_set += sp[2];
+            const float* sp = s_part + g * 4 * NPIX + pix;
+            z_own += sp[0]; z_oth += sp[NPIX]; z_set += sp[2 * NPIX];
         }
         const float w_x = s_w[pix][0], w_i = s_w[pix][1];
 #pragma unroll
@@ -795,12 +1023,12 @@ __global__ void __launch_bounds__(kNceThreads) nce_grad_kernel(NceParams prm) {
         }
     }
     __syncthreads();           // everyone has read s_part: reuse it for the qdq partials
-    if (p < P) s_part[(pix * kNceGroups + grp) * 4 + 3] = qdq_part;
+    if (p < P) s_part[(grp * 4 + 3) * NPIX + pix] = qdq_part;
     __syncthreads();
     if (grp == 0 && p < P) {
         float qdq = 0.f;
 #pragma unroll
-        for (int g = 0; g < kNceGroups; ++g) qdq += s_part[(pix * kNceGroups + g) * 4 + 3];
+        for (int g = 0; g < kNceGroups; ++g) qdq += s_part[(g * 4 + 3) * NPIX + pix];
         s_qdq[pix] = qdq * kInvT;
     }
     __syncthreads();
@@ -812,23 +1040,56 @@ __global__ void __launch_bounds__(kNceThreads) nce_grad_kernel(NceParams prm) {
         const float qdq = s_qdq[pix], inv = s_scale[pix];
         const float gs = prm.grad_scale ? prm.grad_scale[0] : 1.f;
         float* gp = V.grad_x + static_cast<size_t>(n) * D * HW + q;
-        // channel d = grp + 8*i: the 16 pixels of a CTA are contiguous in memory for a fixed d.  Term order: own c=0,
-        // other c=0, own c=1, ...
-        for (int d = grp; d < D; d += kNceGroups) {
-            float dq = 0.f;
+        // Term order per channel: own c=0, other c=0, own c=1, ...
+        if (kVec) {
+            // channels 4*dc .. 4*dc+3 with dc = grp + 8*i: a warp is 32 consecutive pixels of one group, so the prototype
+            // reads are one broadcast float4 and the stores are 128-byte rows
+            for (int dc = grp; dc < (D >> 2); dc += kNceGroups) {
+                float dq[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int c = 0; c < kNceMaxC; ++c) {
-                dq = fmaf(coef[c], s_proto[c * (D + 1) + d], dq);
-                dq = fmaf(coef[kSlotHalf + c], s_proto[(kSlotHalf + c) * (D + 1) + d], dq);
+                for (int c = 0; c < kNceMaxC; ++c) {
+                    const float4 a = *reinterpret_cast<const float4*>(s_proto + c * pstride + 4 * dc);
+                    const float4 b = *reinterpret_cast<const float4*>(s_proto + (kSlotHalf + c) * pstride + 4 * dc);
+                    dq[0] = fmaf(coef[c], a.x, dq[0]); dq[0] = fmaf(coef[kSlotHalf + c], b.x, dq[0]);
+                    dq[1] = fmaf(coef[c], a.y, dq[1]); dq[1] = fmaf(coef[kSlotHalf + c], b.y, dq[1]);
+                    dq[2] = fmaf(coef[c], a.z, dq[2]); dq[2] = fmaf(coef[kSlotHalf + c], b.z, dq[2]);
+                    dq[3] = fmaf(coef[c], a.w, dq[3]); dq[3] = fmaf(coef[kSlotHalf + c], b.w, dq[3]);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int d = 4 * dc + u;
+                    const float qd = s_x[d * NPIX + pix] * inv;
+                    gp[static_cast<size_t>(d) * HW] = (dq[u] - qd * qdq) * inv * gs;
+                }
             }
-            const float qd = s_x[d * kNcePix + pix] * inv;
-            gp[static_cast<size_t>(d) * HW] = (dq - qd * qdq) * inv * gs;
+        } else {
+            // channel d = grp + 8*i: the 16 pixels of a CTA are contiguous in memory for a fixed d
+            for (int d = grp; d < D; d += kNceGroups) {
+                float dq = 0.f;
+#pragma unroll
+                for (int c = 0; c < kNceMaxC; ++c) {
+                    dq = fmaf(coef[c], s_proto[c * pstride + d], dq);
+                    dq = fmaf(coef[kSlotHalf + c], s_proto[(kSlotHalf + c) * pstride + d], dq);
+                }
+                const float qd = s_x[d * NPIX + pix] * inv;
+                gp[static_cast<size_t>(d) * HW] = (dq - qd * qdq) * inv * gs;
+            }
         }
     }
-    if (threadIdx.x < 32) {
+    // fixed-order block partial of the weighted intra loss: the pixel threads (grp 0) are the first NPIX threads
+    __shared__ float s_intra[NPIX / 16];
+    if (threadIdx.x < NPIX || threadIdx.x < 32) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) intra += __shfl_xor_sync(0xffffffffu, intra, o);
-        if (threadIdx.x == 0) V.partial[blockIdx.x * 4 + 2] = intra;
+        if ((threadIdx.x & 31) == 0) s_intra[threadIdx.x >> 5] = intra;
+    }
+    if (NPIX > 32) __syncthreads();
+    if (threadIdx.x == 0) {
+        float tot = s_intra[0];
+        for (int wv = 1; wv < NPIX / 32; ++wv) tot += s_intra[wv];
+        V.partial[tile * 4 + 2] = tot;
+    }
+    if (kVec) __syncthreads();                                 // the next tile rewrites s_x / s_coef / s_part
     }
 }
 
@@ -841,13 +1102,14 @@ __global__ void __launch_bounds__(192) nce_finalize_kernel(NceParams prm) {
     {
         const int v = wv / 3, j = wv - 3 * v;
         const float* part = prm.v[v].partial + j;
+        const int nblk = j == 2 ? prm.nblk_grad : prm.nblk;
         float acc = 0.f;
         int b = lane;
-        for (; b + 96 < prm.nblk; b += 128) {
+        for (; b + 96 < nblk; b += 128) {
             const float x0 = part[b * 4], x1 = part[(b + 32) * 4], x2 = part[(b + 64) * 4], x3 = part[(b + 96) * 4];
             acc += x0; acc += x1; acc += x2; acc += x3;
         }
-        for (; b < prm.nblk; b += 32) acc += part[b * 4];
+        for (; b < nblk; b += 32) acc += part[b * 4];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
         if (lane == 0) s_sum[wv] = acc;
@@ -871,6 +1133,7 @@ __global__ void __launch_bounds__(192) nce_finalize_kernel(NceParams prm) {
     L[9] = L[6] + L[7] + L[8];
 }
 
+constexpr int kNceTileMinP = 16384;           // from here on the 64-pixel-tile variants of the pixel / gradient kernels
 constexpr int kMinePairwiseMaxP = 16384;      // above this the O(P^2) pairwise ranks lose to the multi-pass select
 struct NceLayout {
     size_t per_view, total, clear_bytes;
@@ -1059,11 +1322,19 @@ extern "C" int wsegk_contrast_loss_fwd_bwd(const float* x1, const float* x2, con
     const size_t proto_smem = (static_cast<size_t>(kNceSlots) * (D + 1) + kNcePix * 49 + kNcePix * kNceGroups * 4 +
                                static_cast<size_t>(D) * kNcePix) * sizeof(float);
     WSEGK_REQUIRE(proto_smem <= 200 * 1024, WSEGK_ERR_BAD_SHAPE, "contrast_loss_fwd_bwd: D too large");
+    // large grids: 64-pixel tiles (register-tiled dot products, vector shared-memory reads) if they fit
+    const size_t tile_pix_smem = (static_cast<size_t>(D) * (kTileProtoStride + kTilePix) + kTilePix * 49 +
+                                  kTilePix * kNceGroups * 4 + kTilePix) * sizeof(float);
+    const size_t tile_grad_smem = (static_cast<size_t>(kNceSlots) * (D + 4) + static_cast<size_t>(D) * kGradTilePix +
+                                   kGradTilePix * 49 + kGradTilePix * kNceGroups * 4) * sizeof(float);
+    const bool tiled = (P >= kNceTileMinP || g_force_radix) && tile_pix_smem <= 200 * 1024 && tile_grad_smem <= 200 * 1024;
     const NceLayout L = nce_layout(N, C, h, w);
     WSEGK_REQUIRE(workspace_bytes >= L.total, WSEGK_ERR_WORKSPACE_TOO_SMALL,
                   "contrast_loss_fwd_bwd: workspace %zu < %zu", workspace_bytes, L.total);
     NceParams prm{};
-    prm.N = N; prm.C = C; prm.D = D; prm.HW = h * w; prm.P = static_cast<int>(P); prm.nblk = L.nblk;
+    prm.N = N; prm.C = C; prm.D = D; prm.HW = h * w; prm.P = static_cast<int>(P);
+    prm.nblk = tiled ? static_cast<int>((P + kTilePix - 1) / kTilePix) : L.nblk;
+    prm.nblk_grad = tiled ? static_cast<int>((P + kGradTilePix - 1) / kGradTilePix) : L.nblk;
     prm.grad_scale = grad_scale;
     prm.losses = losses;
     prm.idx_bits = radix ? index_bits(P) : 0;
@@ -1096,11 +1367,29 @@ extern "C" int wsegk_contrast_loss_fwd_bwd(const float* x1, const float* x2, con
         else
             WSEGK_CUDA_OK(cudaMemsetAsync(b + L.off_rs, 0, L.off_state - L.off_rs, stream));
     }
-    WSEGK_CUDA_OK(cudaFuncSetAttribute(nce_pixel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(proto_smem)));
-    WSEGK_CUDA_OK(cudaFuncSetAttribute(nce_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(proto_smem)));
-    nce_pixel_kernel<<<dim3(L.nblk, 2), kNceThreads, proto_smem, stream>>>(prm);
+    int grid_a = 0, grid_c = 0;
+    if (tiled) {
+        WSEGK_CUDA_OK(cudaFuncSetAttribute(nce_pixel_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(tile_pix_smem)));
+        WSEGK_CUDA_OK(cudaFuncSetAttribute(nce_grad_kernel<kGradTilePix>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(tile_grad_smem)));
+        // persistent CTAs: as many as are co-resident
+        int dev = 0, sms = 0, occ_a = 1, occ_c = 1;
+        WSEGK_CUDA_OK(cudaGetDevice(&dev));
+        WSEGK_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        WSEGK_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_a, nce_pixel_tile_kernel, kNceThreads, tile_pix_smem));
+        WSEGK_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, nce_grad_kernel<kGradTilePix>,
+                                                                    kGradTilePix * kNceGroups, tile_grad_smem));
+        grid_a = std::min(prm.nblk, std::max(1, sms * occ_a));
+        grid_c = std::min(prm.nblk_grad, std::max(1, sms * occ_c));
+        nce_pixel_tile_kernel<<<dim3(grid_a, 2), kNceThreads, tile_pix_smem, stream>>>(prm);
+    } else {
+        WSEGK_CUDA_OK(cudaFuncSetAttribute(nce_pixel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(proto_smem)));
+        WSEGK_CUDA_OK(cudaFuncSetAttribute(nce_grad_kernel<kNcePix>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(proto_smem)));
+        nce_pixel_kernel<<<dim3(L.nblk, 2), kNceThreads, proto_smem, stream>>>(prm);
+    }
     int launches = 3;
     if (radix) {
         mine_sel_init_kernel<<<2, 96, 0, stream>>>(prm);
@@ -1115,7 +1404,10 @@ extern "C" int wsegk_contrast_loss_fwd_bwd(const float* x1, const float* x2, con
                           stream>>>(prm);
         ++launches;
     }
-    nce_grad_kernel<<<dim3(L.nblk, 2), kNceThreads, proto_smem, stream>>>(prm);
+    if (tiled)
+        nce_grad_kernel<kGradTilePix><<<dim3(grid_c, 2), kGradTilePix * kNceGroups, tile_grad_smem, stream>>>(prm);
+    else
+        nce_grad_kernel<kNcePix><<<dim3(L.nblk, 2), kNceThreads, proto_smem, stream>>>(prm);
     nce_finalize_kernel<<<1, 32 * 6, 0, stream>>>(prm);
     count_launches(launches);
     WSEGK_CUDA_OK(cudaGetLastError());
