@@ -23,6 +23,6 @@ t0 = int(t[t > 0].min())
 rel = lambda x: int(x) - t0 if int(x) > 0 else -1
 print("mode", mode, "(clock64 ticks relative to first stamp)")
 print(" t | prod:empty_f ok | mma: full_f, peer_full_f (for S(t)) | loop: top, p_full ok | tmem warp: wait s_full, got, arrived")
-for i in range(16):
+for i in range(44):
     print(f"{i:2d} | {rel(t[0, i, 0]):7d} | {rel(t[1, i, 0]):7d} {rel(t[1, i, 1]):7d} | {rel(t[1, i, 2]):7d} {rel(t[1, i, 3]):7d} | "
           f"{rel(t[2, i, 0]):7d} {rel(t[2, i, 1]):7d} {rel(t[2, i, 2]):7d}")

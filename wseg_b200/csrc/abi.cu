@@ -70,17 +70,19 @@ static int pick_wb(int HW) {
 }
 
 // How many CTA pairs split one j pair's sweep over the i stages: minimise (waves x stages per CTA + fixed cost).
-static int pick_nsplit(int N, int PJ, int NS) {
-    const int slots = 74;                 // CTA pairs resident at once (148 SMs, 1 CTA per SM)
+// CTA pairs of the persistent PCM kernels: one per SM pair of a B200 (148 SMs, one 200 KB CTA per SM); every pair gets at
+// least two stages.  A constant, not a device query, so that workspace sizes do not depend on where they are asked for.
+static int pick_clusters(long long T) {
+    const long long slots = 74;
+    long long g = T / 2;
+    if (g > slots) g = slots;
+    if (g < 1) g = 1;
+    return static_cast<int>(g);
+}
+static int max_unit_segments(int units, int NS, int G) {
+    const long long T = static_cast<long long>(units) * NS;
     int best = 1;
-    double best_cost = 1e30;
-    for (int s = 1; s <= 8 && s <= NS; ++s) {
-        const long long ctas = static_cast<long long>(N) * PJ * s;
-        const long long waves = (ctas + slots - 1) / slots;
-        const int per = (NS + s - 1) / s;
-        const double cost = static_cast<double>(waves) * (per + 2.5);     // ~2.5 stage-times of prologue/epilogue
-        if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
-    }
+    for (int u = 0; u < units; ++u) best = std::max(best, pcm_unit_segments(u, NS, T, G));
     return best;
 }
 
@@ -92,7 +94,8 @@ PcmPlan make_pcm_plan(void* ws, int N, int C, int K, int h, int w, int precise) 
     p.wb = pick_wb(p.HW);
     p.NS = ceil_div(p.HW, 2 * p.wb);
     p.HWpi = p.NS * 2 * p.wb;
-    p.nsplit = pick_nsplit(N, p.PJ, p.NS);
+    p.G = pick_clusters(static_cast<long long>(N) * p.PJ * p.NS);
+    p.nsplit = max_unit_segments(N * p.PJ, p.NS, p.G);
     p.precise = precise ? 1 : 0;
     p.Ku = precise ? 3 * kAugK : kAugK;
     p.a_tile_bytes = static_cast<size_t>(kTile) * K * 2;

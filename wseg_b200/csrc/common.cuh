@@ -76,7 +76,8 @@ struct PcmPlan {
     int wb;          // B-tile rows per CTA (64, 56 or 48)
     int NS;          // stages along i: ceil(HW / (2*wb))
     int HWpi;        // NS * 2 * wb
-    int nsplit;      // CTAs (pairs) splitting one j pair's sweep
+    int G;           // CTA pairs of the persistent main kernels (stream-K over all N*PJ*NS stages)
+    int nsplit;      // partial-result slots per unit = the most CTA pairs that share one (image, j pair) sweep
     int precise;     // 1: fp16 hi+lo split operands (3 S products, 3 T products); 0: single pass
     size_t a_tile_bytes, b_tile_bytes;
     // sections
@@ -94,6 +95,21 @@ struct PcmPlan {
     int Ku;                                // 48 (fast) or 144 (precise: [hi|hi|lo] x [hi|lo|hi])
     size_t bytes;
 };
+// ---- stream-K schedule shared by the forward and backward main kernels ---------------------------------------------
+// Unit u = n*PJ + jp (one image's pair of 128-row j tiles) owns NS stages; the T = units*NS stages are cut into G equal
+// contiguous ranges, one per CTA pair, so every pair does the same number of stages whatever N, PJ and NS are (no wave
+// quantisation) and pays ONE prologue/drain.  A range crosses unit boundaries: each (pair, unit) piece is a "segment"
+// with its own A-side tile and its own partial-result slot  slot = pair - (pair owning the unit's first stage).
+__host__ __device__ __forceinline__ long long pcm_range_lo(long long T, int G, int g) { return T * g / G; }
+__host__ __device__ __forceinline__ int pcm_stage_owner(long long t, long long T, int G) {     // needs G <= T
+    const int g = static_cast<int>(t * G / T);
+    return pcm_range_lo(T, G, g + 1) > t ? g : g + 1;
+}
+__host__ __device__ __forceinline__ int pcm_unit_segments(int u, int NS, long long T, int G) {
+    const long long t0 = static_cast<long long>(u) * NS;
+    return pcm_stage_owner(t0 + NS - 1, T, G) - pcm_stage_owner(t0, T, G) + 1;
+}
+
 PcmPlan make_pcm_plan(void* ws, int N, int C, int K, int h, int w, int precise);
 int pcm_mode();     // current process-wide mode (wsegk_pcm_set_mode): 1 precise (default), 0 fast
 

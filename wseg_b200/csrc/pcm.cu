@@ -160,7 +160,7 @@ template <bool PRECISE> struct FwdCfg { static constexpr int kFStages = PRECISE 
 template <int FS>
 struct FwdBars {
     // full_* / fj of the LEADER also count one arrival relayed from the peer CTA ("my copy of this stage landed too")
-    uint64_t fj, full_f[FS], empty_f[FS], full_c[kCamStages], empty_c[kCamStages], s_full[2], p_full[2], o_full;
+    uint64_t fj, a_free, full_f[FS], empty_f[FS], full_c[kCamStages], empty_c[kCamStages], s_full[2], p_full[2], o_full;
     uint32_t tmem_base;
 };
 
@@ -178,15 +178,43 @@ __device__ __forceinline__ uint32_t relu_pack_bits(const uint32_t* r, uint32_t* 
     return bits;
 }
 
+// ---- stream-K schedule shared by the forward and backward main kernels ---------------------------------------------
+// Unit u = n*PJ + jp (one image's pair of 128-row j tiles) owns NS stages; the T = units*NS stages are cut into G equal
+// contiguous ranges, one per CTA pair, so every pair does the same number of stages whatever N, PJ and NS are (no wave
+// quantisation) and pays ONE prologue/drain.  A range crosses unit boundaries: each (pair, unit) piece is a "segment"
+// with its own A-side tile and its own partial-result slot  slot = pair - (pair owning the unit's first stage).
+// Walks the stages of a CTA pair's range without divisions (the MMA-issuing warp has ~500 spare cycles per stage).
+struct StageCursor {
+    int n, jp, st, k;          // image, j pair, stage inside the unit, segment ordinal inside this CTA pair's range
+    int i, cnt, NS, PJ;
+    __device__ __forceinline__ StageCursor(long long t_lo, int cnt_, int NS_, int PJ_) : i(0), cnt(cnt_), NS(NS_), PJ(PJ_) {
+        const int u = static_cast<int>(t_lo / NS_);
+        st = static_cast<int>(t_lo - static_cast<long long>(u) * NS_);
+        n = u / PJ_;
+        jp = u - n * PJ_;
+        k = 0;
+    }
+    __device__ __forceinline__ bool first() const { return i == 0 || st == 0; }          // first stage of its segment
+    __device__ __forceinline__ bool last() const { return i + 1 == cnt || st == NS - 1; }  // last stage of its segment
+    __device__ __forceinline__ void next() {
+        ++i;
+        if (++st == NS) {
+            st = 0;
+            ++k;
+            if (++jp == PJ) { jp = 0; ++n; }
+        }
+    }
+};
+
 template <int WB, bool PRECISE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMainThreads, 1)
 pcm_fwd_kernel(const uint8_t* __restrict__ fa_hi, const uint8_t* __restrict__ fa_lo,
                const uint8_t* __restrict__ fb_hi, const uint8_t* __restrict__ fb_lo,
                const uint8_t* __restrict__ camb, float* __restrict__ part, uint4* __restrict__ mask, int K, int PJ,
-               int NS, int nsplit, long long* __restrict__ trace) {
+               int NS, int n_units, int nslot, long long* __restrict__ trace) {
     constexpr int FS = FwdCfg<PRECISE>::kFStages;
-    // optional timeline of CTA (0,0,0): trace[role*256 + t*4 + k] = clock64()   (wsegk_debug_pcm_trace)
-    const bool tr = trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+    // optional timeline of CTA 0: trace[role*256 + t*4 + k] = clock64()   (wsegk_debug_pcm_trace)
+    const bool tr = trace != nullptr && blockIdx.x == 0;
 #define TRACE(role, t, k) do { if (tr && (t) < 64) trace[(role) * 256 + (t) * 4 + (k)] = clock64(); } while (0)
     constexpr int NCOL = 2 * WB;
     constexpr uint32_t kCamBytes = NCOL * 64;                  // (NCOL/8) groups x 32 rows x 16 B per CTA
@@ -202,14 +230,16 @@ pcm_fwd_kernel(const uint8_t* __restrict__ fa_hi, const uint8_t* __restrict__ fa
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
-    const int jp = blockIdx.x >> 1, sp = blockIdx.y, n = blockIdx.z;
+    const int G = static_cast<int>(gridDim.x >> 1), g = static_cast<int>(blockIdx.x >> 1);
+    const long long T = static_cast<long long>(n_units) * NS;
+    const long long t_lo = pcm_range_lo(T, G, g), t_hi = pcm_range_lo(T, G, g + 1);
+    const int cnt = static_cast<int>(t_hi - t_lo);             // stages this CTA pair runs
     const int HWpj = PJ * 2 * kTile;
-    const int s_begin = (NS * sp) / nsplit, s_end = (NS * (sp + 1)) / nsplit;
-    const int nt = s_end - s_begin;
 
     if (threadIdx.x == 0) {
         const uint32_t relay = rank == 0 ? 1u : 0u, nf = PRECISE ? 2u : 1u;
         mbar_init(smem_u32(&bars->fj), nf + relay);
+        mbar_init(smem_u32(&bars->a_free), 1);
         for (int s = 0; s < FS; ++s) {
             mbar_init(smem_u32(&bars->full_f[s]), nf + relay);
             mbar_init(smem_u32(&bars->empty_f[s]), 1);
@@ -235,23 +265,25 @@ pcm_fwd_kernel(const uint8_t* __restrict__ fa_hi, const uint8_t* __restrict__ fa
     tc_fence_after();
     const uint32_t tmem = bars->tmem_base;
 
-    const size_t a_tile = static_cast<size_t>(n) * 2 * PJ + 2 * jp + rank;        // this CTA's j tile
-    const size_t b_tile0 = static_cast<size_t>(n) * 2 * NS;
-    const uint8_t* g_cam = camb + (static_cast<size_t>(n) * NS) * 2 * kCamBytes;
-
     if (warp == 0 || warp == 6) {
         // ---------------------------------------------------------------- F producers: warp 0 = hi parts, warp 6 = lo parts
         const bool lo = warp == 6;
         if (lane == 0 && (!lo || PRECISE)) {
             const uint8_t* ga = lo ? fa_lo : fa_hi;
             const uint8_t* gb = lo ? fb_lo : fb_hi;
-            mbar_arrive_expect_tx(smem_u32(&bars->fj), a_bytes);
-            tma_load_1d(smem_u32(lo ? s_fj_lo : s_fj_hi), ga + a_tile * a_bytes, a_bytes, smem_u32(&bars->fj));
-            for (int t = 0; t < nt; ++t) {
-                const size_t bt = b_tile0 + 2 * (s_begin + t) + rank;
-                const int s = t % FS, u = t / FS;
+            StageCursor si(t_lo, cnt, NS, PJ);
+            for (int i = 0; i < cnt; ++i, si.next()) {
+                if (si.first()) {
+                    // a new segment: its A-side tile replaces the previous one once every S product of that segment is done
+                    if (si.k > 0) mbar_wait(smem_u32(&bars->a_free), (si.k - 1) & 1);
+                    const size_t a_tile = static_cast<size_t>(si.n) * 2 * PJ + 2 * si.jp + rank;
+                    mbar_arrive_expect_tx(smem_u32(&bars->fj), a_bytes);
+                    tma_load_1d(smem_u32(lo ? s_fj_lo : s_fj_hi), ga + a_tile * a_bytes, a_bytes, smem_u32(&bars->fj));
+                }
+                const size_t bt = static_cast<size_t>(si.n) * 2 * NS + 2 * si.st + rank;
+                const int s = i % FS, u = i / FS;
                 mbar_wait(smem_u32(&bars->empty_f[s]), (u & 1) ^ 1);
-                if (!lo) TRACE(0, t, 0);
+                if (!lo) TRACE(0, i, 0);
                 const uint32_t bar = smem_u32(&bars->full_f[s]);
                 mbar_arrive_expect_tx(bar, b_bytes);
                 tma_load_1d(smem_u32(s_f + s * f_stage + (lo ? b_bytes : 0)), gb + bt * b_bytes, b_bytes, bar);
@@ -260,28 +292,32 @@ pcm_fwd_kernel(const uint8_t* __restrict__ fa_hi, const uint8_t* __restrict__ fa
     } else if (warp == 7) {
         // ---------------------------------------------------------------- cam-block producer
         if (lane == 0) {
-            for (int t = 0; t < nt; ++t) {
-                const int s = t % kCamStages, u = t / kCamStages;
+            StageCursor si(t_lo, cnt, NS, PJ);
+            for (int i = 0; i < cnt; ++i, si.next()) {
+                const int s = i % kCamStages, u = i / kCamStages;
                 mbar_wait(smem_u32(&bars->empty_c[s]), (u & 1) ^ 1);
                 const uint32_t bar = smem_u32(&bars->full_c[s]);
                 mbar_arrive_expect_tx(bar, kCamBytes);
                 tma_load_1d(smem_u32(s_c + s * kCamBytes),
-                            g_cam + (static_cast<size_t>(s_begin + t) * 2 + rank) * kCamBytes, kCamBytes, bar);
+                            camb + ((static_cast<size_t>(si.n) * NS + si.st) * 2 + rank) * kCamBytes, kCamBytes, bar);
             }
         }
     } else if (warp == 1) {
         if (lane == 0 && rank == 1) {
             // ------------------------------------------------------------ relay: tell the leader my tiles have landed
-            mbar_wait(smem_u32(&bars->fj), 0);
-            mbar_arrive_cluster(mapa_shared(smem_u32(&bars->fj), 0));
-            for (int t = 0; t < nt; ++t) {
+            StageCursor si(t_lo, cnt, NS, PJ);
+            for (int i = 0; i < cnt; ++i, si.next()) {
+                if (si.first()) {
+                    mbar_wait(smem_u32(&bars->fj), si.k & 1);
+                    mbar_arrive_cluster(mapa_shared(smem_u32(&bars->fj), 0));
+                }
                 {
-                    const int s = t % FS, u = t / FS;
+                    const int s = i % FS, u = i / FS;
                     mbar_wait(smem_u32(&bars->full_f[s]), u & 1);
                     mbar_arrive_cluster(mapa_shared(smem_u32(&bars->full_f[s]), 0));
                 }
                 {
-                    const int s = t % kCamStages, u = t / kCamStages;
+                    const int s = i % kCamStages, u = i / kCamStages;
                     mbar_wait(smem_u32(&bars->full_c[s]), u & 1);
                     mbar_arrive_cluster(mapa_shared(smem_u32(&bars->full_c[s]), 0));
                 }
@@ -295,12 +331,16 @@ pcm_fwd_kernel(const uint8_t* __restrict__ fa_hi, const uint8_t* __restrict__ fa
             const int ksteps = K >> 4;
             const uint64_t da_hi = umma_smem_desc(smem_u32(s_fj_hi), lbo_a, 128);
             const uint64_t da_lo = umma_smem_desc(smem_u32(s_fj_lo), lbo_a, 128);
-            mbar_wait_cluster(smem_u32(&bars->fj), 0);
-            auto issue_s = [&](int t) {
-                const int s = t % FS, u = t / FS, b = t & 1;
-                if (lane == 0) TRACE(1, t, 0);
+            StageCursor cs(t_lo, cnt, NS, PJ);                 // runs two stages ahead of the PV cursor
+            auto issue_s = [&](int i) {
+                const bool seg_first = cs.first(), seg_last = cs.last();
+                const int seg = cs.k;
+                cs.next();
+                const int s = i % FS, u = i / FS, b = i & 1;
+                if (seg_first) mbar_wait_cluster(smem_u32(&bars->fj), seg & 1);
+                if (lane == 0) TRACE(1, i, 0);
                 mbar_wait_cluster(smem_u32(&bars->full_f[s]), u & 1);
-                if (lane == 0) TRACE(1, t, 1);
+                if (lane == 0) TRACE(1, i, 1);
                 tc_fence_after();
                 if (elect_one()) {
                     const uint64_t db_hi = umma_smem_desc(smem_u32(s_f + s * f_stage), lbo_b, 128);
@@ -322,44 +362,58 @@ pcm_fwd_kernel(const uint8_t* __restrict__ fa_hi, const uint8_t* __restrict__ fa
                     }
                     umma2_commit(smem_u32(&bars->s_full[b]));
                     umma2_commit(smem_u32(&bars->empty_f[s]));
+                    if (seg_last) umma2_commit(smem_u32(&bars->a_free));  // the segment's A-side tile may be replaced
                 }
                 __syncwarp();
             };
-            issue_s(0);
-            if (nt > 1) issue_s(1);
-            for (int t = 0; t < nt; ++t) {
-                const int b = t & 1, sc = t % kCamStages, uc = t / kCamStages;
-                if (lane == 0) TRACE(1, t, 2);
-                mbar_wait_cluster(smem_u32(&bars->p_full[b]), (t >> 1) & 1);
-                if (lane == 0) TRACE(1, t, 3);
+            // S runs two stages ahead of PV inside a segment.  The first S of a NEW segment has to wait for its A-side tile,
+            // which is loaded only after the old segment's last S; it is therefore issued one iteration later, after the
+            // PV that ends the old segment (whose epilogue then overlaps the tile load instead of following it).
+            int next_s = 0;
+            auto issue_upto = [&](int limit) {               // limit = index of the PV stage just issued, or -1
+                while (next_s < cnt && next_s <= limit + 2) {
+                    if (next_s == limit + 2 && next_s > 0 && cs.first()) break;
+                    issue_s(next_s);
+                    ++next_s;
+                }
+            };
+            issue_upto(-1);
+            StageCursor si(t_lo, cnt, NS, PJ);
+            for (int i = 0; i < cnt; ++i, si.next()) {
+                const int b = i & 1, sc = i % kCamStages, uc = i / kCamStages;
+                if (lane == 0) TRACE(1, i, 2);
+                mbar_wait_cluster(smem_u32(&bars->p_full[b]), (i >> 1) & 1);
+                if (lane == 0) TRACE(1, i, 3);
                 mbar_wait_cluster(smem_u32(&bars->full_c[sc]), uc & 1);
                 tc_fence_after();
                 if (elect_one()) {
                     const uint64_t dc = umma_smem_desc(smem_u32(s_c + sc * kCamBytes), lbo_c, 128);
+                    // the accumulator restarts with every segment; the TMEM warps drained the previous segment's before
+                    // they produced this stage's P
 #pragma unroll
                     for (int ks = 0; ks < NCOL / 16; ++ks)
                         umma2_ts(tmem + kColO, tmem + b * 128 + ks * 8, dc + static_cast<uint64_t>(ks * (2 * lbo_c / 16)),
-                                 id_o, (t > 0) || (ks > 0));
+                                 id_o, !si.first() || (ks > 0));
                     umma2_commit(smem_u32(&bars->empty_c[sc]));
+                    if (si.last()) umma2_commit(smem_u32(&bars->o_full));
                 }
                 __syncwarp();
-                if (t + 2 < nt) issue_s(t + 2);
+                issue_upto(i);
             }
-            if (elect_one()) umma2_commit(smem_u32(&bars->o_full));
-            __syncwarp();
         }
     } else if (warp < 6) {
         // ---------------------------------------------------------------- ReLU / sign / convert warps (own 128 lanes)
         const int q = warp & 3;                         // TMEM lane quarter this warp may touch
         const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-        const int row = jp * 2 * kTile + static_cast<int>(rank) * kTile + q * 32 + lane;
         const uint32_t p_full0 = mapa_shared(smem_u32(&bars->p_full[0]), 0);
         const uint32_t p_full1 = mapa_shared(smem_u32(&bars->p_full[1]), 0);
-        for (int t = 0; t < nt; ++t) {
-            const int b = t & 1;
-            if (warp == 2 && lane == 0) TRACE(2, t, 0);
-            mbar_wait(smem_u32(&bars->s_full[b]), (t >> 1) & 1);
-            if (warp == 2 && lane == 0) TRACE(2, t, 1);
+        StageCursor si(t_lo, cnt, NS, PJ);
+        for (int i = 0; i < cnt; ++i, si.next()) {
+            const int row = si.jp * 2 * kTile + static_cast<int>(rank) * kTile + q * 32 + lane;
+            const int b = i & 1;
+            if (warp == 2 && lane == 0) TRACE(2, i, 0);
+            mbar_wait(smem_u32(&bars->s_full[b]), (i >> 1) & 1);
+            if (warp == 2 && lane == 0) TRACE(2, i, 1);
             tc_fence_after();
             uint32_t mw[4] = {0u, 0u, 0u, 0u};
             const uint32_t base = tmem + lane_addr + b * 128;
@@ -383,22 +437,25 @@ pcm_fwd_kernel(const uint8_t* __restrict__ fa_hi, const uint8_t* __restrict__ fa
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(b ? p_full1 : p_full0);
-            if (warp == 2 && lane == 0) TRACE(2, t, 2);
-            mask[(static_cast<size_t>(n) * NS + (s_begin + t)) * HWpj + row] = make_uint4(mw[0], mw[1], mw[2], mw[3]);
-        }
-        // epilogue: accumulator rows -> partial buffer [n][sp][HWpj][64]
-        mbar_wait(smem_u32(&bars->o_full), 0);
-        tc_fence_after();
-        float4* dst = reinterpret_cast<float4*>(part + ((static_cast<size_t>(n) * nsplit + sp) * HWpj + row) * kONum);
+            if (warp == 2 && lane == 0) TRACE(2, i, 2);
+            mask[(static_cast<size_t>(si.n) * NS + si.st) * HWpj + row] = make_uint4(mw[0], mw[1], mw[2], mw[3]);
+            if (si.last()) {
+                // segment epilogue: accumulator -> partial buffer
+                const int slot = g - pcm_stage_owner(t_lo + i - si.st, T, G);
+                mbar_wait(smem_u32(&bars->o_full), si.k & 1);
+                tc_fence_after();
+                // [n][slot][64][HWpj]: for a fixed column the 32 lanes of a warp write 32 consecutive rows (one 128-byte line)
+                float* dst = part + (static_cast<size_t>(si.n) * nslot + slot) * kONum * HWpj + row;
 #pragma unroll
-        for (int c = 0; c < kONum / 16; ++c) {
-            uint32_t r[16];
-            tmem_ld16(tmem + lane_addr + kColO + c * 16, r);
-            tmem_ld_wait();
+                for (int c = 0; c < kONum / 16; ++c) {
+                    uint32_t r[16];
+                    tmem_ld16(tmem + lane_addr + kColO + c * 16, r);
+                    tmem_ld_wait();
 #pragma unroll
-            for (int v = 0; v < 4; ++v)
-                dst[c * 4 + v] = make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]),
-                                             __uint_as_float(r[4 * v + 2]), __uint_as_float(r[4 * v + 3]));
+                    for (int v = 0; v < 16; ++v) dst[static_cast<size_t>(c * 16 + v) * HWpj] = __uint_as_float(r[v]);
+                }
+                tc_fence_before();
+            }
         }
     }
     tc_fence_before();
@@ -408,43 +465,31 @@ pcm_fwd_kernel(const uint8_t* __restrict__ fa_hi, const uint8_t* __restrict__ fa
 #undef TRACE
 }
 
-// out[n,c,j] = (sum_sp hi[c] + lo[c]) / (sum_sp colsum + 1e-5)
-// One warp per 32 consecutive rows j: the 64-float partial rows are read coalesced (lane c gets hi[c] and lo[c]), a
-// 32x33 shared-memory tile transposes so the stores to the NCHW output run along j.
+// out[n,c,j] = (sum_slot hi[c] + lo[c]) / (sum_slot colsum + 1e-5)
+// The partials are column-major ([n][slot][64][HWpj]: hi rows 0..C-1, column sum at row C, lo rows 32..32+C-1), so thread
+// (c, j) reads and writes along j: no transpose.  One CTA = 32 consecutive rows j x 8 class phases.
 __global__ void __launch_bounds__(256) pcm_fwd_finalize_kernel(const float* __restrict__ part,
                                                                float* __restrict__ out,
                                                                float* __restrict__ dsum, int C, int HW,
-                                                               int HWpj, int nsplit) {
-    __shared__ float s_t[8][32][33];
-    __shared__ float s_d[8][32];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+                                                               int HWpj, int nslot, int PJ, int NS, int G) {
     const int n = blockIdx.y;
-    const int j0 = (blockIdx.x * 8 + warp) * 32;                 // HWpj is a multiple of 256
-    const size_t split_stride = static_cast<size_t>(HWpj) * kONum;
-    const float* base = part + (static_cast<size_t>(n) * nsplit * HWpj + j0) * kONum + lane;
-    for (int jj0 = 0; jj0 < 32; jj0 += 4) {                      // 4 rows x nsplit x 2 independent loads in flight
-        float hi[4] = {0.f, 0.f, 0.f, 0.f}, lo[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int sp = 0; sp < nsplit; ++sp) {
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const float* src = base + sp * split_stride + static_cast<size_t>(jj0 + r) * kONum;
-                hi[r] += __ldg(src);
-                lo[r] += __ldg(src + kCamRows);
-            }
+    const int lane = threadIdx.x & 31, ph = threadIdx.x >> 5;
+    const int j = blockIdx.x * 32 + lane;                        // HWpj is a multiple of 256
+    const int nseg = pcm_unit_segments(n * PJ + j / (2 * kTile), NS, static_cast<long long>(gridDim.y) * PJ * NS, G);
+    const size_t slot_stride = static_cast<size_t>(kONum) * HWpj;
+    const float* base = part + static_cast<size_t>(n) * nslot * slot_stride + j;
+    float d = 0.f;
+    for (int sp = 0; sp < nseg; ++sp) d += __ldg(base + sp * slot_stride + static_cast<size_t>(C) * HWpj);
+    d += 1e-5f;
+    if (ph == 0) dsum[static_cast<size_t>(n) * HWpj + j] = d;
+    if (j >= HW) return;
+    for (int c = ph; c < C; c += 8) {
+        float hi = 0.f, lo = 0.f;
+        for (int sp = 0; sp < nseg; ++sp) {
+            hi += __ldg(base + sp * slot_stride + static_cast<size_t>(c) * HWpj);
+            lo += __ldg(base + sp * slot_stride + static_cast<size_t>(kCamRows + c) * HWpj);
         }
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const float d = __shfl_sync(0xffffffffu, hi[r], C) + 1e-5f;     // lane C holds the column sum
-            s_t[warp][lane][jj0 + r] = (hi[r] + lo[r]) / d;
-            if (lane == 0) s_d[warp][jj0 + r] = d;
-        }
-    }
-    __syncwarp();
-    const int j = j0 + lane;
-    dsum[static_cast<size_t>(n) * HWpj + j] = s_d[warp][lane];
-    if (j < HW) {
-        float* dst = out + static_cast<size_t>(n) * C * HW + j;
-        for (int c = 0; c < C; ++c) dst[static_cast<size_t>(c) * HW] = s_t[warp][c][lane];
+        out[(static_cast<size_t>(n) * C + c) * HW + j] = (hi + lo) / d;
     }
 }
 
@@ -560,8 +605,8 @@ __device__ __forceinline__ float pcm_grad_scale(const float* bound) {
 constexpr int kBwdStages = 4;
 
 struct BwdBars {
-    uint64_t uj, full_v[kBwdStages], empty_v[kBwdStages], full_f[kBwdStages], empty_f[kBwdStages], t_full[2], e_full[2],
-        g_full;
+    uint64_t uj, u_free, full_v[kBwdStages], empty_v[kBwdStages], full_f[kBwdStages], empty_f[kBwdStages], t_full[2],
+        e_full[2], g_full;
     uint32_t tmem_base;
 };
 
@@ -579,7 +624,7 @@ template <int WB, bool SPLIT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMainThreads, 1)
 pcm_bwd_kernel(const uint8_t* __restrict__ ua, const uint8_t* __restrict__ vb, const uint8_t* __restrict__ fb_hi,
                const uint4* __restrict__ mask, const float* __restrict__ bound, float* __restrict__ dfhat, int K,
-               int PJ, int NS, int nsplit) {
+               int PJ, int NS, int n_units, int nslot) {
     constexpr int NCOL = 2 * WB;
     constexpr int KU = SPLIT ? 3 * kAugK : kAugK;
     constexpr uint32_t kUBytes = kTile * KU * 2, kVBytes = WB * KU * 2;
@@ -593,14 +638,17 @@ pcm_bwd_kernel(const uint8_t* __restrict__ ua, const uint8_t* __restrict__ vb, c
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
-    const int jp = blockIdx.x >> 1, sp = blockIdx.y, n = blockIdx.z;
+    // the same stream-K schedule as the forward (common.cuh): this CTA pair runs stages [t_lo, t_hi) of the N*PJ*NS
+    const int G = static_cast<int>(gridDim.x >> 1), g = static_cast<int>(blockIdx.x >> 1);
+    const long long T = static_cast<long long>(n_units) * NS;
+    const long long t_lo = pcm_range_lo(T, G, g), t_hi = pcm_range_lo(T, G, g + 1);
+    const int cnt = static_cast<int>(t_hi - t_lo);
     const int HWpj = PJ * 2 * kTile;
-    const int s_begin = (NS * sp) / nsplit, s_end = (NS * (sp + 1)) / nsplit;
-    const int nt = s_end - s_begin;
 
     if (threadIdx.x == 0) {
         const uint32_t relay = rank == 0 ? 1u : 0u;
         mbar_init(smem_u32(&bars->uj), 1 + relay);
+        mbar_init(smem_u32(&bars->u_free), 1);
         for (int s = 0; s < kBwdStages; ++s) {
             mbar_init(smem_u32(&bars->full_v[s]), 1 + relay);
             mbar_init(smem_u32(&bars->empty_v[s]), 1);
@@ -623,22 +671,25 @@ pcm_bwd_kernel(const uint8_t* __restrict__ ua, const uint8_t* __restrict__ vb, c
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem = bars->tmem_base;
-
-    const size_t a_tile = static_cast<size_t>(n) * 2 * PJ + 2 * jp + rank;
-    const size_t b_tile0 = static_cast<size_t>(n) * 2 * NS;
     const size_t b_bytes = static_cast<size_t>(WB) * K * 2;
 
     if (warp == 0) {
-        // ---------------------------------------------------------------- producer A: U tile (once) and the V tiles
+        // ---------------------------------------------------------------- producer A: the segment's U tile and the V tiles
         if (lane == 0) {
-            mbar_arrive_expect_tx(smem_u32(&bars->uj), kUBytes);
-            tma_load_1d(smem_u32(s_u), ua + a_tile * kUBytes, kUBytes, smem_u32(&bars->uj));
-            for (int t = 0; t < nt; ++t) {
-                const int st = s_begin + t, s = t % kBwdStages, u = t / kBwdStages;
+            StageCursor si(t_lo, cnt, NS, PJ);
+            for (int i = 0; i < cnt; ++i, si.next()) {
+                if (si.first()) {
+                    if (si.k > 0) mbar_wait(smem_u32(&bars->u_free), (si.k - 1) & 1);
+                    const size_t a_tile = static_cast<size_t>(si.n) * 2 * PJ + 2 * si.jp + rank;
+                    mbar_arrive_expect_tx(smem_u32(&bars->uj), kUBytes);
+                    tma_load_1d(smem_u32(s_u), ua + a_tile * kUBytes, kUBytes, smem_u32(&bars->uj));
+                }
+                const int s = i % kBwdStages, u = i / kBwdStages;
                 mbar_wait(smem_u32(&bars->empty_v[s]), (u & 1) ^ 1);
                 const uint32_t bar = smem_u32(&bars->full_v[s]);
                 mbar_arrive_expect_tx(bar, kVBytes);
-                tma_load_1d(smem_u32(s_v + s * kVBytes), vb + (b_tile0 + 2 * st + rank) * kVBytes, kVBytes, bar);
+                tma_load_1d(smem_u32(s_v + s * kVBytes),
+                            vb + (static_cast<size_t>(si.n) * 2 * NS + 2 * si.st + rank) * kVBytes, kVBytes, bar);
             }
         }
     } else if (warp >= 6) {
@@ -646,21 +697,26 @@ pcm_bwd_kernel(const uint8_t* __restrict__ ua, const uint8_t* __restrict__ vb, c
         // [rank*K/16, (rank+1)*K/16)) of the stage's X tile (warp 6) and Y tile (warp 7)
         if (lane == 0) {
             const int part = warp - 6;
-            for (int t = 0; t < nt; ++t) {
-                const int st = s_begin + t, s = t % kBwdStages, u = t / kBwdStages;
+            StageCursor si(t_lo, cnt, NS, PJ);
+            for (int i = 0; i < cnt; ++i, si.next()) {
+                const int s = i % kBwdStages, u = i / kBwdStages;
                 mbar_wait(smem_u32(&bars->empty_f[s]), (u & 1) ^ 1);
                 const uint32_t bar = smem_u32(&bars->full_f[s]);
                 mbar_arrive_expect_tx(bar, f_part);
-                const uint8_t* x = fb_hi + (b_tile0 + 2 * st + part) * b_bytes + static_cast<size_t>(rank) * f_part;
+                const uint8_t* x = fb_hi + (static_cast<size_t>(si.n) * 2 * NS + 2 * si.st + part) * b_bytes +
+                                   static_cast<size_t>(rank) * f_part;
                 tma_load_1d(smem_u32(s_f + s * f_stage + part * f_part), x, f_part, bar);
             }
         }
     } else if (warp == 1) {
         if (lane == 0 && rank == 1) {
-            mbar_wait(smem_u32(&bars->uj), 0);
-            mbar_arrive_cluster(mapa_shared(smem_u32(&bars->uj), 0));
-            for (int t = 0; t < nt; ++t) {
-                const int s = t % kBwdStages, u = t / kBwdStages;
+            StageCursor si(t_lo, cnt, NS, PJ);
+            for (int i = 0; i < cnt; ++i, si.next()) {
+                if (si.first()) {
+                    mbar_wait(smem_u32(&bars->uj), si.k & 1);
+                    mbar_arrive_cluster(mapa_shared(smem_u32(&bars->uj), 0));
+                }
+                const int s = i % kBwdStages, u = i / kBwdStages;
                 mbar_wait(smem_u32(&bars->full_v[s]), u & 1);
                 mbar_arrive_cluster(mapa_shared(smem_u32(&bars->full_v[s]), 0));
                 mbar_wait(smem_u32(&bars->full_f[s]), u & 1);
@@ -671,9 +727,13 @@ pcm_bwd_kernel(const uint8_t* __restrict__ ua, const uint8_t* __restrict__ vb, c
             const uint32_t id_g = umma_idesc_f16(0, 2 * kTile, K, 0, 1);          // fp16, B = Fi read MN-major (N = channel)
             constexpr uint32_t lbo_a = kTile * 16, lbo_b = WB * 16;
             const uint64_t du = umma_smem_desc(smem_u32(s_u), lbo_a, 128);
-            mbar_wait_cluster(smem_u32(&bars->uj), 0);
-            auto issue_t = [&](int t) {
-                const int s = t % kBwdStages, u = t / kBwdStages, b = t & 1;
+            StageCursor cs(t_lo, cnt, NS, PJ);                 // cursor of the T products (ahead of the G products)
+            auto issue_t = [&](int i) {
+                const bool seg_first = cs.first(), seg_last = cs.last();
+                const int seg = cs.k;
+                cs.next();
+                const int s = i % kBwdStages, u = i / kBwdStages, b = i & 1;
+                if (seg_first) mbar_wait_cluster(smem_u32(&bars->uj), seg & 1);
                 mbar_wait_cluster(smem_u32(&bars->full_v[s]), u & 1);
                 tc_fence_after();
                 if (elect_one()) {
@@ -684,14 +744,24 @@ pcm_bwd_kernel(const uint8_t* __restrict__ ua, const uint8_t* __restrict__ vb, c
                                  dv + static_cast<uint64_t>(ks * (2 * lbo_b / 16)), id_t, ks > 0);
                     umma2_commit(smem_u32(&bars->t_full[b]));
                     umma2_commit(smem_u32(&bars->empty_v[s]));
+                    if (seg_last) umma2_commit(smem_u32(&bars->u_free));
                 }
                 __syncwarp();
             };
-            issue_t(0);
-            if (nt > 1) issue_t(1);
-            for (int t = 0; t < nt; ++t) {
-                const int s = t % kBwdStages, u = t / kBwdStages, b = t & 1;
-                mbar_wait_cluster(smem_u32(&bars->e_full[b]), (t >> 1) & 1);
+            // two stages of lookahead inside a segment, one across a segment boundary (see the forward kernel)
+            int next_t = 0;
+            auto issue_upto = [&](int limit) {
+                while (next_t < cnt && next_t <= limit + 2) {
+                    if (next_t == limit + 2 && next_t > 0 && cs.first()) break;
+                    issue_t(next_t);
+                    ++next_t;
+                }
+            };
+            issue_upto(-1);
+            StageCursor si(t_lo, cnt, NS, PJ);
+            for (int i = 0; i < cnt; ++i, si.next()) {
+                const int s = i % kBwdStages, u = i / kBwdStages, b = i & 1;
+                mbar_wait_cluster(smem_u32(&bars->e_full[b]), (i >> 1) & 1);
                 mbar_wait_cluster(smem_u32(&bars->full_f[s]), u & 1);
                 tc_fence_after();
                 if (elect_one()) {
@@ -700,36 +770,38 @@ pcm_bwd_kernel(const uint8_t* __restrict__ ua, const uint8_t* __restrict__ vb, c
                     // MN-major: LBO = step between the two 8-pixel groups of the k-step, SBO = channel-group step
 #pragma unroll
                     for (int ks = 0; ks < NCOL / 16; ++ks) {
-                        constexpr int dummy = 0; (void)dummy;
                         const int q0 = 16 * ks, q1 = q0 + 8;
                         const uint32_t a0 = f0 + (q0 / WB) * f_part + (q0 % WB) * 16;
                         const uint32_t a1 = f0 + (q1 / WB) * f_part + (q1 % WB) * 16;
                         umma2_ts(tmem + kColG, tmem + b * 128 + ks * 8, umma_smem_desc(a0, a1 - a0, lbo_b), id_g,
-                                 (t > 0) || (ks > 0));
+                                 !si.first() || (ks > 0));
                     }
                     umma2_commit(smem_u32(&bars->empty_f[s]));
+                    if (si.last()) umma2_commit(smem_u32(&bars->g_full));
                 }
                 __syncwarp();
-                if (t + 2 < nt) issue_t(t + 2);
+                issue_upto(i);
             }
-            if (elect_one()) umma2_commit(smem_u32(&bars->g_full));
-            __syncwarp();
         }
     } else if (warp < 6) {
         const int q = warp & 3;
         const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-        const int row = jp * 2 * kTile + static_cast<int>(rank) * kTile + q * 32 + lane;
+        const int row_in = static_cast<int>(rank) * kTile + q * 32 + lane;
         const uint32_t e_full0 = mapa_shared(smem_u32(&bars->e_full[0]), 0);
         const uint32_t e_full1 = mapa_shared(smem_u32(&bars->e_full[1]), 0);
         const float scale = pcm_grad_scale(bound);
-        const uint4* mrow = mask + (static_cast<size_t>(n) * NS + s_begin) * HWpj + row;
-        uint4 mw_next = nt > 0 ? __ldg(mrow) : make_uint4(0, 0, 0, 0);
-        for (int t = 0; t < nt; ++t) {
-            const int b = t & 1;
+        StageCursor si(t_lo, cnt, NS, PJ), sn(t_lo, cnt, NS, PJ);      // this stage / the next one (mask prefetch)
+        auto mask_of = [&](const StageCursor& c) {
+            return __ldg(mask + (static_cast<size_t>(c.n) * NS + c.st) * HWpj + c.jp * 2 * kTile + row_in);
+        };
+        uint4 mw_next = cnt > 0 ? mask_of(sn) : make_uint4(0, 0, 0, 0);
+        for (int i = 0; i < cnt; ++i, si.next()) {
+            const int b = i & 1;
             const uint4 mw4 = mw_next;
-            if (t + 1 < nt) mw_next = __ldg(mrow + static_cast<size_t>(t + 1) * HWpj);
+            sn.next();
+            if (i + 1 < cnt) mw_next = mask_of(sn);
             const uint32_t mw[4] = {mw4.x, mw4.y, mw4.z, mw4.w};
-            mbar_wait(smem_u32(&bars->t_full[b]), (t >> 1) & 1);
+            mbar_wait(smem_u32(&bars->t_full[b]), (i >> 1) & 1);
             tc_fence_after();
             const uint32_t base = tmem + lane_addr + b * 128;
 #pragma unroll
@@ -752,17 +824,22 @@ pcm_bwd_kernel(const uint8_t* __restrict__ ua, const uint8_t* __restrict__ vb, c
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(b ? e_full1 : e_full0);
-        }
-        mbar_wait(smem_u32(&bars->g_full), 0);
-        tc_fence_after();
-        // dfhat [n][sp][K][HWpj]: for a fixed channel the 32 lanes of a warp write 32 consecutive pixels
-        float* dst = dfhat + ((static_cast<size_t>(n) * nsplit + sp) * K) * HWpj + row;
-        for (int c = 0; c < (K >> 4); ++c) {
-            uint32_t r[16];
-            tmem_ld16(tmem + lane_addr + kColG + c * 16, r);
-            tmem_ld_wait();
+            if (si.last()) {
+                // segment epilogue.  dfhat [n][slot][K][HWpj]: for a fixed channel the 32 lanes of a warp write 32
+                // consecutive pixels
+                const int slot = g - pcm_stage_owner(t_lo + i - si.st, T, G);
+                mbar_wait(smem_u32(&bars->g_full), si.k & 1);
+                tc_fence_after();
+                float* dst = dfhat + ((static_cast<size_t>(si.n) * nslot + slot) * K) * HWpj + si.jp * 2 * kTile + row_in;
+                for (int c = 0; c < (K >> 4); ++c) {
+                    uint32_t r[16];
+                    tmem_ld16(tmem + lane_addr + kColG + c * 16, r);
+                    tmem_ld_wait();
 #pragma unroll
-            for (int v = 0; v < 16; ++v) dst[static_cast<size_t>(c * 16 + v) * HWpj] = __uint_as_float(r[v]);
+                    for (int v = 0; v < 16; ++v) dst[static_cast<size_t>(c * 16 + v) * HWpj] = __uint_as_float(r[v]);
+                }
+                tc_fence_before();
+            }
         }
     }
     tc_fence_before();
@@ -780,7 +857,7 @@ constexpr int kPostPhases = 8;
 __global__ void __launch_bounds__(256) pcm_bwd_post_kernel(const float* __restrict__ dfhat, const float* __restrict__ f,
                                                            const float* __restrict__ inv_norm,
                                                            const float* __restrict__ bound, float* __restrict__ grad_f,
-                                                           int K, int HW, int HWpj, int nsplit) {
+                                                           int K, int HW, int HWpj, int nslot, int PJ, int NS, int G) {
     __shared__ float s_dot[kPostPhases][kPostPix];
     const int n = blockIdx.y;
     const int px = threadIdx.x & (kPostPix - 1), ph = threadIdx.x >> 5;
@@ -788,7 +865,10 @@ __global__ void __launch_bounds__(256) pcm_bwd_post_kernel(const float* __restri
     const bool live = p < HW;
     const float unscale = 1.f / pcm_grad_scale(bound);
     const size_t split_stride = static_cast<size_t>(K) * HWpj;
-    const float* gsrc = dfhat + static_cast<size_t>(n) * nsplit * split_stride + p;
+    const float* gsrc = dfhat + static_cast<size_t>(n) * nslot * split_stride + p;
+    // how many CTA pairs shared this pixel's (image, j pair) sweep (kPostPix divides 256: uniform over the CTA)
+    const int nsplit = pcm_unit_segments(n * PJ + (blockIdx.x * kPostPix) / (2 * kTile), NS,
+                                         static_cast<long long>(gridDim.y) * PJ * NS, G);
     const float* fsrc = f + static_cast<size_t>(n) * K * HW + p;
     const int per = K / kPostPhases;                      // channels per phase (K % 32 == 0 => per % 4 == 0)
     const int k0 = ph * per;
@@ -914,11 +994,11 @@ static int launch_fwd(const PcmPlan& pl, int N, wsegk_stream_t stream) {
     WSEGK_REQUIRE(smem <= 232448, WSEGK_ERR_BAD_SHAPE, "pcm_fwd: %zu bytes of shared memory needed", smem);
     WSEGK_CUDA_OK(cudaFuncSetAttribute(pcm_fwd_kernel<WB, PRECISE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem)));
-    pcm_fwd_kernel<WB, PRECISE><<<dim3(2 * pl.PJ, pl.nsplit, N), kMainThreads, smem, stream>>>(
+    pcm_fwd_kernel<WB, PRECISE><<<dim3(2 * pl.G), kMainThreads, smem, stream>>>(
         reinterpret_cast<const uint8_t*>(pl.fa_hi), reinterpret_cast<const uint8_t*>(pl.fa_lo),
         reinterpret_cast<const uint8_t*>(pl.fb_hi), reinterpret_cast<const uint8_t*>(pl.fb_lo),
         reinterpret_cast<const uint8_t*>(pl.camb), pl.part, reinterpret_cast<uint4*>(pl.mask), pl.K, pl.PJ, pl.NS,
-        pl.nsplit, g_trace);
+        N * pl.PJ, pl.nsplit, g_trace);
     return WSEGK_OK;
 }
 
@@ -928,10 +1008,10 @@ static int launch_bwd(const PcmPlan& pl, int N, wsegk_stream_t stream) {
     WSEGK_REQUIRE(smem <= 232448, WSEGK_ERR_BAD_SHAPE, "pcm_bwd: %zu bytes of shared memory needed", smem);
     WSEGK_CUDA_OK(cudaFuncSetAttribute(pcm_bwd_kernel<WB, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem)));
-    pcm_bwd_kernel<WB, SPLIT><<<dim3(2 * pl.PJ, pl.nsplit, N), kMainThreads, smem, stream>>>(
+    pcm_bwd_kernel<WB, SPLIT><<<dim3(2 * pl.G), kMainThreads, smem, stream>>>(
         reinterpret_cast<const uint8_t*>(pl.ua), reinterpret_cast<const uint8_t*>(pl.vb),
         reinterpret_cast<const uint8_t*>(pl.fb_hi), reinterpret_cast<const uint4*>(pl.mask), pl.bound, pl.dfhat, pl.K,
-        pl.PJ, pl.NS, pl.nsplit);
+        pl.PJ, pl.NS, N * pl.PJ, pl.nsplit);
     return WSEGK_OK;
 }
 
@@ -985,8 +1065,8 @@ static int pcm_fwd_impl(const float* f, const float* cam_norm, float* cam_rv, in
     prof_mark(0, stream);
     WSEGK_DISPATCH_WB(launch_fwd, precise, pl, N, stream);
     prof_mark(1, stream);
-    pcm_fwd_finalize_kernel<<<dim3(pl.HWpj / 256, N), 256, 0, stream>>>(pl.part, cam_rv, pl.dsum, C, pl.HW, pl.HWpj,
-                                                                         pl.nsplit);
+    pcm_fwd_finalize_kernel<<<dim3(pl.HWpj / 32, N), 256, 0, stream>>>(pl.part, cam_rv, pl.dsum, C, pl.HW, pl.HWpj,
+                                                                         pl.nsplit, pl.PJ, pl.NS, pl.G);
     count_launches(4);
     WSEGK_CUDA_OK(cudaGetLastError());
     return WSEGK_OK;
@@ -1021,7 +1101,7 @@ extern "C" int wsegk_pcm_bwd(const float* f, const float* cam_norm, const float*
     WSEGK_DISPATCH_WB(launch_bwd, precise, pl, N, stream);
     prof_mark(3, stream);
     pcm_bwd_post_kernel<<<dim3(ceil_div(pl.HW, kPostPix), N), 256, 0, stream>>>(
-        pl.dfhat, f, pl.inv_norm, pl.bound, grad_f, K, pl.HW, pl.HWpj, pl.nsplit);
+        pl.dfhat, f, pl.inv_norm, pl.bound, grad_f, K, pl.HW, pl.HWpj, pl.nsplit, pl.PJ, pl.NS, pl.G);
     count_launches(3);
     WSEGK_CUDA_OK(cudaGetLastError());
     return WSEGK_OK;

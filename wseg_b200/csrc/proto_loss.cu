@@ -195,12 +195,23 @@ struct TopkSrc {
     __device__ long long count() const { return total; }
     __device__ Elem load(long long e) const { return Elem{__ldg(norm_cam + e)}; }
     __device__ void get(const Elem& x, long long e, int, int& slot, unsigned long long& key) const {
-        const long long plane = static_cast<long long>(C) * HW;
-        const long long n = e / plane, r = e - n * plane;
-        const int c = static_cast<int>(r / HW), q = static_cast<int>(r - static_cast<long long>(c) * HW);
+        int c;
+        long long i;                                             // flat pixel id n*HW + q
+        if (total <= 0x7fffffffll) {                             // 32-bit divisions where they suffice
+            const uint32_t e32 = static_cast<uint32_t>(e), plane = static_cast<uint32_t>(C) * HW;
+            const uint32_t n = e32 / plane, r = e32 - n * plane;
+            const uint32_t cc = r / static_cast<uint32_t>(HW);
+            c = static_cast<int>(cc);
+            i = static_cast<long long>(n * HW + (r - cc * HW));
+        } else {
+            const long long plane = static_cast<long long>(C) * HW;
+            const long long n = e / plane, r = e - n * plane;
+            c = static_cast<int>(r / HW);
+            i = n * HW + (r - static_cast<long long>(c) * HW);
+        }
         slot = c;
         key = (static_cast<unsigned long long>(static_cast<uint32_t>(~ordered_bits(x.v))) << idx_bits) |
-              static_cast<unsigned long long>(n * HW + q);
+              static_cast<unsigned long long>(i);
     }
 };
 __global__ void topk_sel_init_kernel(SegSel* __restrict__ state, int C, int k) {
