@@ -1,4 +1,4 @@
-"""PCM main-kernel durations (CUDA events around the tcgen05 kernels) over a few shapes.  usage: python tools/pcm_times.py"""
+"""PCM main-kernel durations (CUDA events around the tcgen05 kernels) over a few shapes.  usage: python tools/pcm_times.py [large]"""
 import os
 import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -8,9 +8,14 @@ from wseg_b200 import ops, synth
 dev = torch.device("cuda:0")
 ops.pcm_profile(True)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-for n, h in ((8, 56), (16, 56), (8, 64), (8, 32), (8, 96), (2, 56)):
-    d = synth.pcm_inputs(n, h, h, seed=3)
-    cam, f, g = d["cam"].to(dev), d["f"].to(dev), d["grad_out"].to(dev)
+shapes = ((8, 56), (16, 56), (8, 64), (8, 32), (8, 96), (2, 56))
+if len(sys.argv) > 1 and sys.argv[1] == "large":
+    shapes = ((128, 56), (64, 80), (32, 96), (128, 32), (64, 64))
+for n, h in shapes:
+    gen = torch.Generator().manual_seed(3)
+    f = torch.randn(n, 192, h, h, generator=gen).to(dev)
+    cam = (0.05 * torch.randn(n, 21, h, h, generator=gen)).to(dev)
+    g = (1e-3 * torch.randn(n, 21, h, h, generator=gen)).to(dev)
     camn = ops.cam_norm(cam)
     tf, tb = [], []
     for _ in range(5):

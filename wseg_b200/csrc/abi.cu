@@ -80,9 +80,9 @@ static int pick_clusters(long long T) {
     return static_cast<int>(g);
 }
 static int max_unit_segments(int units, int NS, int G) {
-    const long long T = static_cast<long long>(units) * NS;
+    const PcmSched sc = pcm_sched(units, NS, G);
     int best = 1;
-    for (int u = 0; u < units; ++u) best = std::max(best, pcm_unit_segments(u, NS, T, G));
+    for (int u = sc.Rf * sc.G; u < units; ++u) best = std::max(best, pcm_unit_segments(sc, u));
     return best;
 }
 

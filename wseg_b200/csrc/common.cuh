@@ -95,19 +95,40 @@ struct PcmPlan {
     int Ku;                                // 48 (fast) or 144 (precise: [hi|hi|lo] x [hi|lo|hi])
     size_t bytes;
 };
-// ---- stream-K schedule shared by the forward and backward main kernels ---------------------------------------------
-// Unit u = n*PJ + jp (one image's pair of 128-row j tiles) owns NS stages; the T = units*NS stages are cut into G equal
-// contiguous ranges, one per CTA pair, so every pair does the same number of stages whatever N, PJ and NS are (no wave
-// quantisation) and pays ONE prologue/drain.  A range crosses unit boundaries: each (pair, unit) piece is a "segment"
-// with its own A-side tile and its own partial-result slot  slot = pair - (pair owning the unit's first stage).
-__host__ __device__ __forceinline__ long long pcm_range_lo(long long T, int G, int g) { return T * g / G; }
-__host__ __device__ __forceinline__ int pcm_stage_owner(long long t, long long T, int G) {     // needs G <= T
-    const int g = static_cast<int>(t * G / T);
-    return pcm_range_lo(T, G, g + 1) > t ? g : g + 1;
+// ---- schedule shared by the forward and backward main kernels: data-parallel rows + a stream-K tail ------------------
+// Unit u = n*PJ + jp (one image's pair of 128-row j tiles) owns NS stages.  G CTA pairs run persistently:
+//   * rows:  for k < Rf = U / G, pair g runs the whole unit k*G + g.  In step k all pairs sit on consecutive units, i.e. on
+//            the same few images, so the i-side tiles they stream are shared through L2;
+//   * tail:  the remaining r = U - Rf*G units have Tt = r*NS stages, cut into Gt = min(G, Tt) equal contiguous ranges, one
+//            per pair g < Gt (stream-K): every pair ends up with the same number of stages (+-1) whatever N, PJ and NS are.
+// A range crosses unit boundaries; each (pair, unit) piece is a "segment" with its own A-side tile and its own
+// partial-result slot: slot 0 for a row unit, pair - (pair owning the unit's first tail stage) for a tail unit.
+struct PcmSched {
+    int U, NS, G, Rf, r, Gt;
+    long long Tt;
+};
+__host__ __device__ __forceinline__ PcmSched pcm_sched(int U, int NS, int G) {
+    PcmSched s;
+    s.U = U; s.NS = NS; s.G = G;
+    s.Rf = U / G;
+    s.r = U - s.Rf * G;
+    s.Tt = static_cast<long long>(s.r) * NS;
+    s.Gt = s.Tt < G ? static_cast<int>(s.Tt) : G;
+    return s;
 }
-__host__ __device__ __forceinline__ int pcm_unit_segments(int u, int NS, long long T, int G) {
-    const long long t0 = static_cast<long long>(u) * NS;
-    return pcm_stage_owner(t0 + NS - 1, T, G) - pcm_stage_owner(t0, T, G) + 1;
+__host__ __device__ __forceinline__ long long pcm_tail_lo(const PcmSched& s, int g) {       // g <= Gt
+    return s.Gt > 0 ? s.Tt * g / s.Gt : 0;
+}
+__host__ __device__ __forceinline__ int pcm_tail_owner(const PcmSched& s, long long t) {    // Gt <= Tt
+    const int g = static_cast<int>(t * s.Gt / s.Tt);
+    return pcm_tail_lo(s, g + 1) > t ? g : g + 1;
+}
+// segments (= partial slots in use) of unit u
+__host__ __device__ __forceinline__ int pcm_unit_segments(const PcmSched& s, int u) {
+    const int w = u - s.Rf * s.G;
+    if (w < 0) return 1;
+    const long long t0 = static_cast<long long>(w) * s.NS;
+    return pcm_tail_owner(s, t0 + s.NS - 1) - pcm_tail_owner(s, t0) + 1;
 }
 
 PcmPlan make_pcm_plan(void* ws, int N, int C, int K, int h, int w, int precise);

@@ -183,25 +183,39 @@ __device__ __forceinline__ uint32_t relu_pack_bits(const uint32_t* r, uint32_t* 
 // contiguous ranges, one per CTA pair, so every pair does the same number of stages whatever N, PJ and NS are (no wave
 // quantisation) and pays ONE prologue/drain.  A range crosses unit boundaries: each (pair, unit) piece is a "segment"
 // with its own A-side tile and its own partial-result slot  slot = pair - (pair owning the unit's first stage).
-// Walks the stages of a CTA pair's range without divisions (the MMA-issuing warp has ~500 spare cycles per stage).
+// Walks the stages of a CTA pair's schedule (common.cuh) without per-stage divisions: the MMA-issuing warp has only
+// ~500 spare cycles per stage.
 struct StageCursor {
-    int n, jp, st, k;          // image, j pair, stage inside the unit, segment ordinal inside this CTA pair's range
-    int i, cnt, NS, PJ;
-    __device__ __forceinline__ StageCursor(long long t_lo, int cnt_, int NS_, int PJ_) : i(0), cnt(cnt_), NS(NS_), PJ(PJ_) {
-        const int u = static_cast<int>(t_lo / NS_);
-        st = static_cast<int>(t_lo - static_cast<long long>(u) * NS_);
-        n = u / PJ_;
-        jp = u - n * PJ_;
-        k = 0;
+    int n, jp, st, k;          // image, j pair, stage inside the unit, segment ordinal inside this CTA pair's schedule
+    int i, cnt;                // running stage index, stages in the schedule
+    int u, rows_left, tail_u, tail_st, tail_i, G, NS, PJ;
+    __device__ __forceinline__ void set_unit(int unit) {
+        u = unit;
+        n = unit / PJ;
+        jp = unit - n * PJ;
     }
-    __device__ __forceinline__ bool first() const { return i == 0 || st == 0; }          // first stage of its segment
-    __device__ __forceinline__ bool last() const { return i + 1 == cnt || st == NS - 1; }  // last stage of its segment
+    __device__ __forceinline__ StageCursor(const PcmSched& sc, int g, int PJ_) : k(0), i(0), G(sc.G), NS(sc.NS), PJ(PJ_) {
+        const long long lo = g < sc.Gt ? pcm_tail_lo(sc, g) : 0, hi = g < sc.Gt ? pcm_tail_lo(sc, g + 1) : 0;
+        rows_left = sc.Rf;
+        tail_i = sc.Rf * sc.NS;                                      // index of the first tail stage
+        cnt = tail_i + static_cast<int>(hi - lo);
+        const int w = static_cast<int>(lo / sc.NS);
+        tail_u = sc.Rf * sc.G + w;
+        tail_st = static_cast<int>(lo - static_cast<long long>(w) * sc.NS);
+        if (rows_left > 0) { set_unit(g); st = 0; }
+        else { set_unit(tail_u < sc.U ? tail_u : 0); st = tail_st; }
+    }
+    __device__ __forceinline__ bool first() const { return i == 0 || st == 0 || i == tail_i; }   // first stage of its segment
+    __device__ __forceinline__ bool last() const { return i + 1 == cnt || st == NS - 1; }         // last stage of its segment
+    __device__ __forceinline__ bool in_tail() const { return i >= tail_i; }
     __device__ __forceinline__ void next() {
         ++i;
-        if (++st == NS) {
-            st = 0;
+        if (i >= cnt) return;
+        if (++st == NS || i == tail_i) {
             ++k;
-            if (++jp == PJ) { jp = 0; ++n; }
+            if (i == tail_i) { set_unit(tail_u); st = tail_st; }     // rows done: jump to this pair's tail range
+            else if (i < tail_i) { st = 0; set_unit(u + G); }        // next row
+            else { st = 0; set_unit(u + 1); }                        // next tail unit
         }
     }
 };
@@ -230,10 +244,10 @@ pcm_fwd_kernel(const uint8_t* __restrict__ fa_hi, const uint8_t* __restrict__ fa
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
-    const int G = static_cast<int>(gridDim.x >> 1), g = static_cast<int>(blockIdx.x >> 1);
-    const long long T = static_cast<long long>(n_units) * NS;
-    const long long t_lo = pcm_range_lo(T, G, g), t_hi = pcm_range_lo(T, G, g + 1);
-    const int cnt = static_cast<int>(t_hi - t_lo);             // stages this CTA pair runs
+    const int g = static_cast<int>(blockIdx.x >> 1);
+    const PcmSched sched = pcm_sched(n_units, NS, static_cast<int>(gridDim.x >> 1));
+    const StageCursor c0(sched, g, PJ);                        // every role walks its own copy
+    const int cnt = c0.cnt;                                    // stages this CTA pair runs
     const int HWpj = PJ * 2 * kTile;
 
     if (threadIdx.x == 0) {
@@ -271,7 +285,7 @@ pcm_fwd_kernel(const uint8_t* __restrict__ fa_hi, const uint8_t* __restrict__ fa
         if (lane == 0 && (!lo || PRECISE)) {
             const uint8_t* ga = lo ? fa_lo : fa_hi;
             const uint8_t* gb = lo ? fb_lo : fb_hi;
-            StageCursor si(t_lo, cnt, NS, PJ);
+            StageCursor si = c0;
             for (int i = 0; i < cnt; ++i, si.next()) {
                 if (si.first()) {
                     // a new segment: its A-side tile replaces the previous one once every S product of that segment is done
@@ -292,7 +306,7 @@ pcm_fwd_kernel(const uint8_t* __restrict__ fa_hi, const uint8_t* __restrict__ fa
     } else if (warp == 7) {
         // ---------------------------------------------------------------- cam-block producer
         if (lane == 0) {
-            StageCursor si(t_lo, cnt, NS, PJ);
+            StageCursor si = c0;
             for (int i = 0; i < cnt; ++i, si.next()) {
                 const int s = i % kCamStages, u = i / kCamStages;
                 mbar_wait(smem_u32(&bars->empty_c[s]), (u & 1) ^ 1);
@@ -305,7 +319,7 @@ pcm_fwd_kernel(const uint8_t* __restrict__ fa_hi, const uint8_t* __restrict__ fa
     } else if (warp == 1) {
         if (lane == 0 && rank == 1) {
             // ------------------------------------------------------------ relay: tell the leader my tiles have landed
-            StageCursor si(t_lo, cnt, NS, PJ);
+            StageCursor si = c0;
             for (int i = 0; i < cnt; ++i, si.next()) {
                 if (si.first()) {
                     mbar_wait(smem_u32(&bars->fj), si.k & 1);
@@ -331,7 +345,7 @@ pcm_fwd_kernel(const uint8_t* __restrict__ fa_hi, const uint8_t* __restrict__ fa
             const int ksteps = K >> 4;
             const uint64_t da_hi = umma_smem_desc(smem_u32(s_fj_hi), lbo_a, 128);
             const uint64_t da_lo = umma_smem_desc(smem_u32(s_fj_lo), lbo_a, 128);
-            StageCursor cs(t_lo, cnt, NS, PJ);                 // runs two stages ahead of the PV cursor
+            StageCursor cs = c0;                 // runs two stages ahead of the PV cursor
             auto issue_s = [&](int i) {
                 const bool seg_first = cs.first(), seg_last = cs.last();
                 const int seg = cs.k;
@@ -378,7 +392,7 @@ pcm_fwd_kernel(const uint8_t* __restrict__ fa_hi, const uint8_t* __restrict__ fa
                 }
             };
             issue_upto(-1);
-            StageCursor si(t_lo, cnt, NS, PJ);
+            StageCursor si = c0;
             for (int i = 0; i < cnt; ++i, si.next()) {
                 const int b = i & 1, sc = i % kCamStages, uc = i / kCamStages;
                 if (lane == 0) TRACE(1, i, 2);
@@ -407,7 +421,7 @@ pcm_fwd_kernel(const uint8_t* __restrict__ fa_hi, const uint8_t* __restrict__ fa
         const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
         const uint32_t p_full0 = mapa_shared(smem_u32(&bars->p_full[0]), 0);
         const uint32_t p_full1 = mapa_shared(smem_u32(&bars->p_full[1]), 0);
-        StageCursor si(t_lo, cnt, NS, PJ);
+        StageCursor si = c0;
         for (int i = 0; i < cnt; ++i, si.next()) {
             const int row = si.jp * 2 * kTile + static_cast<int>(rank) * kTile + q * 32 + lane;
             const int b = i & 1;
@@ -441,7 +455,7 @@ pcm_fwd_kernel(const uint8_t* __restrict__ fa_hi, const uint8_t* __restrict__ fa
             mask[(static_cast<size_t>(si.n) * NS + si.st) * HWpj + row] = make_uint4(mw[0], mw[1], mw[2], mw[3]);
             if (si.last()) {
                 // segment epilogue: accumulator -> partial buffer
-                const int slot = g - pcm_stage_owner(t_lo + i - si.st, T, G);
+                const int slot = si.in_tail() ? g - pcm_tail_owner(sched, static_cast<long long>(si.u - sched.Rf * sched.G) * NS) : 0;
                 mbar_wait(smem_u32(&bars->o_full), si.k & 1);
                 tc_fence_after();
                 // [n][slot][64][HWpj]: for a fixed column the 32 lanes of a warp write 32 consecutive rows (one 128-byte line)
@@ -475,7 +489,7 @@ __global__ void __launch_bounds__(256) pcm_fwd_finalize_kernel(const float* __re
     const int n = blockIdx.y;
     const int lane = threadIdx.x & 31, ph = threadIdx.x >> 5;
     const int j = blockIdx.x * 32 + lane;                        // HWpj is a multiple of 256
-    const int nseg = pcm_unit_segments(n * PJ + j / (2 * kTile), NS, static_cast<long long>(gridDim.y) * PJ * NS, G);
+    const int nseg = pcm_unit_segments(pcm_sched(static_cast<int>(gridDim.y) * PJ, NS, G), n * PJ + j / (2 * kTile));
     const size_t slot_stride = static_cast<size_t>(kONum) * HWpj;
     const float* base = part + static_cast<size_t>(n) * nslot * slot_stride + j;
     float d = 0.f;
@@ -638,11 +652,11 @@ pcm_bwd_kernel(const uint8_t* __restrict__ ua, const uint8_t* __restrict__ vb, c
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
-    // the same stream-K schedule as the forward (common.cuh): this CTA pair runs stages [t_lo, t_hi) of the N*PJ*NS
-    const int G = static_cast<int>(gridDim.x >> 1), g = static_cast<int>(blockIdx.x >> 1);
-    const long long T = static_cast<long long>(n_units) * NS;
-    const long long t_lo = pcm_range_lo(T, G, g), t_hi = pcm_range_lo(T, G, g + 1);
-    const int cnt = static_cast<int>(t_hi - t_lo);
+    // the same schedule as the forward (common.cuh)
+    const int g = static_cast<int>(blockIdx.x >> 1);
+    const PcmSched sched = pcm_sched(n_units, NS, static_cast<int>(gridDim.x >> 1));
+    const StageCursor c0(sched, g, PJ);
+    const int cnt = c0.cnt;
     const int HWpj = PJ * 2 * kTile;
 
     if (threadIdx.x == 0) {
@@ -676,7 +690,7 @@ pcm_bwd_kernel(const uint8_t* __restrict__ ua, const uint8_t* __restrict__ vb, c
     if (warp == 0) {
         // ---------------------------------------------------------------- producer A: the segment's U tile and the V tiles
         if (lane == 0) {
-            StageCursor si(t_lo, cnt, NS, PJ);
+            StageCursor si = c0;
             for (int i = 0; i < cnt; ++i, si.next()) {
                 if (si.first()) {
                     if (si.k > 0) mbar_wait(smem_u32(&bars->u_free), (si.k - 1) & 1);
@@ -697,7 +711,7 @@ pcm_bwd_kernel(const uint8_t* __restrict__ ua, const uint8_t* __restrict__ vb, c
         // [rank*K/16, (rank+1)*K/16)) of the stage's X tile (warp 6) and Y tile (warp 7)
         if (lane == 0) {
             const int part = warp - 6;
-            StageCursor si(t_lo, cnt, NS, PJ);
+            StageCursor si = c0;
             for (int i = 0; i < cnt; ++i, si.next()) {
                 const int s = i % kBwdStages, u = i / kBwdStages;
                 mbar_wait(smem_u32(&bars->empty_f[s]), (u & 1) ^ 1);
@@ -710,7 +724,7 @@ pcm_bwd_kernel(const uint8_t* __restrict__ ua, const uint8_t* __restrict__ vb, c
         }
     } else if (warp == 1) {
         if (lane == 0 && rank == 1) {
-            StageCursor si(t_lo, cnt, NS, PJ);
+            StageCursor si = c0;
             for (int i = 0; i < cnt; ++i, si.next()) {
                 if (si.first()) {
                     mbar_wait(smem_u32(&bars->uj), si.k & 1);
@@ -727,7 +741,7 @@ pcm_bwd_kernel(const uint8_t* __restrict__ ua, const uint8_t* __restrict__ vb, c
             const uint32_t id_g = umma_idesc_f16(0, 2 * kTile, K, 0, 1);          // fp16, B = Fi read MN-major (N = channel)
             constexpr uint32_t lbo_a = kTile * 16, lbo_b = WB * 16;
             const uint64_t du = umma_smem_desc(smem_u32(s_u), lbo_a, 128);
-            StageCursor cs(t_lo, cnt, NS, PJ);                 // cursor of the T products (ahead of the G products)
+            StageCursor cs = c0;                 // cursor of the T products (ahead of the G products)
             auto issue_t = [&](int i) {
                 const bool seg_first = cs.first(), seg_last = cs.last();
                 const int seg = cs.k;
@@ -758,7 +772,7 @@ pcm_bwd_kernel(const uint8_t* __restrict__ ua, const uint8_t* __restrict__ vb, c
                 }
             };
             issue_upto(-1);
-            StageCursor si(t_lo, cnt, NS, PJ);
+            StageCursor si = c0;
             for (int i = 0; i < cnt; ++i, si.next()) {
                 const int s = i % kBwdStages, u = i / kBwdStages, b = i & 1;
                 mbar_wait_cluster(smem_u32(&bars->e_full[b]), (i >> 1) & 1);
@@ -790,7 +804,7 @@ pcm_bwd_kernel(const uint8_t* __restrict__ ua, const uint8_t* __restrict__ vb, c
         const uint32_t e_full0 = mapa_shared(smem_u32(&bars->e_full[0]), 0);
         const uint32_t e_full1 = mapa_shared(smem_u32(&bars->e_full[1]), 0);
         const float scale = pcm_grad_scale(bound);
-        StageCursor si(t_lo, cnt, NS, PJ), sn(t_lo, cnt, NS, PJ);      // this stage / the next one (mask prefetch)
+        StageCursor si = c0, sn = c0;      // this stage / the next one (mask prefetch)
         auto mask_of = [&](const StageCursor& c) {
             return __ldg(mask + (static_cast<size_t>(c.n) * NS + c.st) * HWpj + c.jp * 2 * kTile + row_in);
         };
@@ -827,7 +841,7 @@ pcm_bwd_kernel(const uint8_t* __restrict__ ua, const uint8_t* __restrict__ vb, c
             if (si.last()) {
                 // segment epilogue.  dfhat [n][slot][K][HWpj]: for a fixed channel the 32 lanes of a warp write 32
                 // consecutive pixels
-                const int slot = g - pcm_stage_owner(t_lo + i - si.st, T, G);
+                const int slot = si.in_tail() ? g - pcm_tail_owner(sched, static_cast<long long>(si.u - sched.Rf * sched.G) * NS) : 0;
                 mbar_wait(smem_u32(&bars->g_full), si.k & 1);
                 tc_fence_after();
                 float* dst = dfhat + ((static_cast<size_t>(si.n) * nslot + slot) * K) * HWpj + si.jp * 2 * kTile + row_in;
@@ -867,8 +881,8 @@ __global__ void __launch_bounds__(256) pcm_bwd_post_kernel(const float* __restri
     const size_t split_stride = static_cast<size_t>(K) * HWpj;
     const float* gsrc = dfhat + static_cast<size_t>(n) * nslot * split_stride + p;
     // how many CTA pairs shared this pixel's (image, j pair) sweep (kPostPix divides 256: uniform over the CTA)
-    const int nsplit = pcm_unit_segments(n * PJ + (blockIdx.x * kPostPix) / (2 * kTile), NS,
-                                         static_cast<long long>(gridDim.y) * PJ * NS, G);
+    const int nsplit = pcm_unit_segments(pcm_sched(static_cast<int>(gridDim.y) * PJ, NS, G),
+                                         n * PJ + (blockIdx.x * kPostPix) / (2 * kTile));
     const float* fsrc = f + static_cast<size_t>(n) * K * HW + p;
     const int per = K / kPostPhases;                      // channels per phase (K % 32 == 0 => per % 4 == 0)
     const int k0 = ph * per;
