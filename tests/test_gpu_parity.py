@@ -526,6 +526,22 @@ def test_pcm_inference_path(cuda_dev):
     assert torch.equal(out, out2)
 
 
+@pytest.mark.parametrize("n,h,w", [(1, 108, 108), (2, 61, 84), (1, 28, 28)])
+def test_pcm_inference_msf_sizes(cuda_dev, n, h, w):
+    """contrast_infer.py:58-80 feeds every image at scales 0.5 .. 1.5 (and flipped): stride-8 grids from ~28x28 up to
+    ~108x108 (HW = 11 664, the largest affinity the reference materialises: 544 MB).  Forward-only kernel against the
+    oracle on the same GPU; a flipped input must give the flipped output (the module is permutation-equivariant)."""
+    d = synth.pcm_inputs(n, h, w, seed=23 + h)
+    f = d["f"].to(cuda_dev)
+    camn = ops.cam_norm(d["cam"].to(cuda_dev))
+    with torch.no_grad():
+        out = ops.pcm(camn, f)
+        ref = R.pcm(camn, f)
+        assert rel_max(out, ref) <= TOL
+        flipped = ops.pcm(camn.flip(-1).contiguous(), f.flip(-1).contiguous()).flip(-1)
+    assert rel_max(flipped, out) <= 1e-4
+
+
 def test_net_training_step_end_to_end(cuda_dev):
     """configs[0] in miniature: the drop-in Net (random-init ResNet-38, eval-mode BN as in the reference's train()),
     both views, the whole loss body and its backward on the GPU — against the oracle evaluated on the SAME network
