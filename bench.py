@@ -187,72 +187,124 @@ class GraphedStep:
 class E2EPath:
     """The same path through the public, reference-facing API (autograd operators + loss.contrast_terms), from PINNED
     HOST buffers: every step copies the path's inputs host->device, runs Net.forward's tail (K1a, K2, bilinear x8 to full
-    resolution), the loss-side operators and their backward, and reads the losses back to the host.  The device part
-    (public API calls, autograd included) is captured once in a CUDA graph and replayed; `--no-graph` runs it eagerly."""
+    resolution), the loss-side operators and their backward, and reads the losses back to the host.
 
-    # the path's inputs travel host -> device every step; the synthetic upstream gradients standing in for the rest of
-    # the loss (g_*) stay resident — they would be produced on the device
-    NAMES = ["cam1", "f1", "fproj1", "cam2", "f2", "fproj2", "label"]
+    The copies run on their own stream and every operator waits only for the tensors it reads, in the order the bytes
+    arrive (small tensors first, then f of view 1, then its projection features), so PCIe and the SMs overlap inside a
+    step.  The whole step (copies, public API calls with autograd, read-back) is captured once in a CUDA graph and
+    replayed; `--no-graph` runs the same code eagerly."""
+
+    # the path's inputs travel host -> device every step, in this order; the synthetic upstream gradients standing in
+    # for the rest of the loss (g_*) stay resident — they would be produced on the device
+    NAMES = ["label", "cam1", "cam2", "f2", "fproj2", "f1", "fproj1"]
 
     def __init__(self, hp: HotPath, use_graph: bool):
         self.hp = hp
-        self.h2d_bytes = sum(hp.host[k].numel() * 4 for k in self.NAMES)
+        self.h2d_bytes = sum(hp.host[k].numel() * hp.host[k].element_size() for k in self.NAMES)
         self.out_host = torch.empty(10, dtype=torch.float32).pin_memory()
         self.d2h_bytes = 40
         self.static = {k: torch.empty_like(hp.d[k]) for k in self.NAMES}
+        self.copy_stream = torch.cuda.Stream(device=hp.dev)
+        self.side_streams = [torch.cuda.Stream(device=hp.dev), torch.cuda.Stream(device=hp.dev)]
         self.graph = None
+        self.expect = None
         self.mode = "eager"
         if use_graph:
             try:
                 side = torch.cuda.Stream(device=hp.dev)
                 side.wait_stream(torch.cuda.current_stream(hp.dev))
                 with torch.cuda.stream(side):
-                    for k in self.NAMES:
-                        self.static[k].copy_(hp.host[k], non_blocking=True)
                     for _ in range(3):
-                        self._device_part()
+                        eager = self._whole_step()
                 torch.cuda.current_stream(hp.dev).wait_stream(side)
                 torch.cuda.synchronize(hp.dev)
+                # what the eager, un-captured run of the same code produced: the replayed graph must reproduce it
+                self.expect = (eager[0].detach().cpu().clone(), [g.detach().abs().sum().item() for g in eager[1]])
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
-                    self.result = self._device_part()
+                    self.result = self._whole_step()
                 self.graph, self.mode = g, "cuda_graph"
             except Exception as exc:
                 print(f"bench.py: e2e graph capture failed ({type(exc).__name__}: {exc}); running it eagerly", file=sys.stderr)
                 self.graph = None
 
-    def _device_part(self):
+    def _whole_step(self):
+        hp = self.hp
+        main = torch.cuda.current_stream(hp.dev)
+        self.copy_stream.wait_stream(main)
+        arrived = {}
+        with torch.cuda.stream(self.copy_stream):
+            for k in self.NAMES:
+                self.static[k].copy_(hp.host[k], non_blocking=True)
+                arrived[k] = torch.cuda.Event()
+                arrived[k].record(self.copy_stream)
+        losses, grads = self._device_part(lambda stream, *names: [stream.wait_event(arrived[k]) for k in names])
+        main.wait_stream(self.copy_stream)
+        for side in self.side_streams:
+            main.wait_stream(side)
+        self.out_host.copy_(losses, non_blocking=True)
+        return losses, grads
+
+    def _device_part(self, need_on):
         from wseg_b200 import loss as L
         from wseg_b200 import ops
         hp = self.hp
         x = {k: v.detach() for k, v in self.static.items()}
         leaves = {k: x[k].requires_grad_(True) for k in ("f1", "f2", "fproj1", "fproj2", "cam1", "cam2")}
+        parts = []
+
+        def k1b(t, size, gname):
+            parts.append((ops.fullres_norm(t, x["label"], size) * hp.d[gname]).sum())
+
+        # Three independent chains, each on its own stream (autograd runs every backward node on the stream of its
+        # forward): (a) what only needs the cam logits of view 1, (b) view 2, (main) view 1's PCM chain, which has to
+        # wait for f of view 1 — the largest tensor on the bus — and then the contrast terms, which need everything.
+        main = torch.cuda.current_stream(hp.dev)
+        sa, sb = self.side_streams
+        sa.wait_stream(main)
+        sb.wait_stream(main)
+        with torch.cuda.stream(sa):
+            need_on(sa, "label", "cam1")
+            cam1_full = ops.bilinear_resize(leaves["cam1"], VIEW1)                   # Net.forward's tail (:57-59)
+            k1b(cam1_full, VIEW2, "g_n1")
+        with torch.cuda.stream(sb):
+            need_on(sb, "label", "cam2", "f2")
+            rv2 = ops.pcm(ops.cam_norm(x["cam2"]), leaves["f2"])
+            cam2_full = ops.bilinear_resize(leaves["cam2"], VIEW2)
+            rv2_full = ops.bilinear_resize(rv2, VIEW2)
+            k1b(cam2_full, None, "g_n2")
+            k1b(rv2_full, None, "g_rv2")
+        need_on(main, "label", "cam1", "f1")
         rv1 = ops.pcm(ops.cam_norm(x["cam1"]), leaves["f1"])
-        rv2 = ops.pcm(ops.cam_norm(x["cam2"]), leaves["f2"])
-        cam1_full = ops.bilinear_resize(leaves["cam1"], VIEW1)                       # Net.forward's tail (:57-59)
         rv1_full = ops.bilinear_resize(rv1, VIEW1)
-        cam2_full = ops.bilinear_resize(leaves["cam2"], VIEW2)
-        rv2_full = ops.bilinear_resize(rv2, VIEW2)
+        k1b(rv1_full, VIEW2, "g_rv1")
+        need_on(main, "fproj2", "fproj1")
+        main.wait_stream(sb)
         terms = L.contrast_terms(leaves["fproj1"], rv1, leaves["fproj2"], rv2, x["label"], BG_THRESHOLD, grid=hp.grid,
                                  group=hp.group, keys=(hp.key1, hp.key2))
+        main.wait_stream(sa)
         total = terms["loss_nce"]
-        for t, size, gname in ((cam1_full, VIEW2, "g_n1"), (rv1_full, VIEW2, "g_rv1"), (cam2_full, None, "g_n2"),
-                               (rv2_full, None, "g_rv2")):
-            total = total + (ops.fullres_norm(t, x["label"], size) * hp.d[gname]).sum()
+        for t in parts:
+            total = total + t
         grads = torch.autograd.grad(total, list(leaves.values()))
         return terms["losses_raw"].detach(), grads
 
     def step(self):
-        hp = self.hp
-        for k in self.NAMES:
-            self.static[k].copy_(hp.host[k], non_blocking=True)
         if self.graph is not None:
             self.graph.replay()
-            losses = self.result[0]
-        else:
-            losses, _ = self._device_part()
-        self.out_host.copy_(losses, non_blocking=True)
-        return losses
+            return self.result[0]
+        return self._whole_step()[0]
+
+    def verify(self):
+        """After the timed region: the losses the last replay left in the pinned host buffer, and the gradients it left
+        on the device, against the eager run of the same code (streams, copies and all) before the capture."""
+        if self.graph is None or self.expect is None:
+            return None
+        torch.cuda.synchronize(self.hp.dev)
+        ok = bool(torch.allclose(self.out_host, self.expect[0], rtol=1e-6, atol=0))
+        for g, want in zip(self.result[1], self.expect[1]):
+            ok = ok and abs(g.detach().abs().sum().item() - want) <= 1e-5 * abs(want)
+        return ok
 
 
 # ------------------------------------------------------------------------------------------------ helpers
@@ -511,6 +563,9 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = total_pix / (float(t.item()) / args.steps * 1e-3) / 1e6
+    e2e_ok = e2e.verify()
+    if e2e_ok is False:
+        raise RuntimeError("bench.py: the replayed end-to-end graph does not reproduce the eager run of the same step")
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -520,7 +575,8 @@ def run_ours(args):
             "gpu_launches_per_step": int(launches_per_step),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e.h2d_bytes,
                     "d2h_bytes_per_step": e2e.d2h_bytes, "ms_per_step": float(t.item()) / args.steps, "launch": e2e.mode,
-                    "api": "pinned host inputs (cam logits, f, f_proj, labels; both views) -> ops.cam_norm / ops.pcm / ops.bilinear_resize x8 / loss.contrast_terms / ops.fullres_norm through autograd, backward, losses -> host"},
+                    "replay_equals_eager": e2e_ok,
+                    "api": "pinned host inputs (cam logits, f, f_proj, labels; both views) -> ops.cam_norm / ops.pcm / ops.bilinear_resize x8 / loss.contrast_terms / ops.fullres_norm through autograd, backward, losses -> host; copies on their own stream, every operator waits only for the tensors it reads"},
             "roofline": roofline, "step_roofline": step_roofline, "wall_ms_per_step_incl_flush": wall_ms / args.steps}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
