@@ -98,6 +98,20 @@ int wsegk_fullres_norm_bwd(const float* p, const float* label, const float* minm
                            const float* tapsum, const float* grad_out, float* grad_p, int N, int C, int H, int W, int oh,
                            int ow, void* workspace, size_t workspace_bytes, wsegk_stream_t stream);
 
+/* K1b on a LAZY full-resolution map: the same result as wsegk_bilinear_resize_fwd(small -> H x W)
+ * followed by wsegk_fullres_norm_fwd, bit for bit, without the full-resolution tensor ever existing — i.e.
+ * network/resnet38_contrast.py:57-59 (the x8 enlargement at the end of Net.forward) fused into contrast_train.py:145-152.
+ * small [N,C,h,w] (the stride-8 cam / cam_rv), label [N,C] -> out [N,C,oh,ow]; minmax and tapsum as above (tapsum required).
+ * The backward returns the gradient w.r.t. the SMALL map (what the enlargement's backward would produce from the dense
+ * full-resolution gradient): grad_small [N,C,h,w]. */
+int wsegk_fullres_norm_up_fwd(const float* small, const float* label, float* out, float* minmax, float* tapsum, int N,
+                              int C, int h, int w, int H, int W, int oh, int ow, void* workspace,
+                              size_t workspace_bytes, wsegk_stream_t stream);
+int wsegk_fullres_norm_up_bwd(const float* small, const float* label, const float* minmax, const float* out,
+                              const float* tapsum, const float* grad_out, float* grad_small, int N, int C, int h, int w,
+                              int H, int W, int oh, int ow, void* workspace, size_t workspace_bytes,
+                              wsegk_stream_t stream);
+
 /* K1c — replaces contrast_train.py:186-197 / 215-226: relu, per-plane min/max normalisation (no outer relu),
  * channel 0 := bg_threshold, pseudo label = argmax_c(norm_cam*label) (lowest class on ties).
  * cam_rv_down [N,C,g_h,g_w], label [N,C] -> norm_cam [N,C,g_h,g_w], pseudo [N*g_h*g_w] int32. */

@@ -197,6 +197,34 @@ def test_fullres_norm_fwd_bwd(cuda_dev, n, H, W, size):
 
 
 # ------------------------------------------------------------------------------------------------ K1c / K3 / K4
+@pytest.mark.parametrize("n,hw,up,size", [(2, (24, 24), (192, 192), (128, 128)), (8, (56, 56), (448, 448), (128, 128)),
+                                          (2, (16, 16), (128, 128), None), (3, (9, 6), (70, 45), (40, 24))])
+def test_fullres_norm_on_lazy_enlargement(cuda_dev, n, hw, up, size):
+    """K1b evaluated on the x8 enlargement WITHOUT materialising it — values bit-identical to
+    bilinear_resize -> fullres_norm, gradient w.r.t. the small map equal to what the two backward kernels give."""
+    g = synth.gen(50 + n)
+    small = (0.3 * synth.smooth_field(n, 21, hw[0], hw[1], g) + 0.05 * torch.randn(n, 21, *hw, generator=g)).to(cuda_dev)
+    label = synth.label_with_bg(synth.labels(n, seed=n)).to(cuda_dev)
+    a = small.clone().requires_grad_(True)
+    b = small.clone().requires_grad_(True)
+    eager = ops.fullres_norm(ops.bilinear_resize(a, up), label, size)
+    lazy = ops.fullres_norm_up(b, label, up, size)
+    assert torch.equal(lazy, eager)
+    go = torch.randn(eager.shape, generator=synth.gen(7)).to(cuda_dev)
+    eager.backward(go)
+    lazy.backward(go)
+    assert rel_max(b.grad, a.grad) <= 1e-5
+    # and against the oracle's formulation on the same GPU
+    r = small.clone().requires_grad_(True)
+    full = F.interpolate(r, size=up, mode="bilinear", align_corners=True)
+    ref = R.max_norm(full)
+    if size is not None:
+        ref = F.interpolate(ref, size=size, mode="bilinear", align_corners=True)
+    ref = ref * label.reshape(n, -1, 1, 1)
+    ref.backward(go)
+    assert rel_max(lazy, ref) <= 1e-5 and rel_max(b.grad, r.grad) <= 1e-4
+
+
 def _views(n, hw1, hw2, seed, d=128, dev="cpu"):
     a = {k: v.to(dev) for k, v in synth.head_outputs(n, hw1, seed=seed * 10 + 1, d=d).items()}
     b = {k: v.to(dev) for k, v in synth.head_outputs(n, hw2, seed=seed * 10 + 2, d=d).items()}

@@ -31,6 +31,10 @@ _SIGNATURES = {
     "wsegk_fullres_norm_fwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
     "wsegk_fullres_norm_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P,
                                        c_size_t, _P]),
+    "wsegk_fullres_norm_up_fwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P,
+                                          c_size_t, _P]),
+    "wsegk_fullres_norm_up_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                          c_int, _P, c_size_t, _P]),
     "wsegk_bilinear_resize_fwd": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "wsegk_bilinear_resize_bwd": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "wsegk_select_kth": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, _P, c_size_t, _P]),

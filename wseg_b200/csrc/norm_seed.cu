@@ -108,6 +108,14 @@ __device__ __forceinline__ void src_coord(int o, float scale, int in_size, int& 
     l0 = 1.f - l1;
 }
 
+// hy0*(wx0*a + wx1*b) + hy1*(wx0*c + wx1*d) with the contraction into FMAs spelled out, so that every kernel that
+// evaluates a bilinear sample (the materialising resize, the lazy K1b kernels) rounds identically.
+__device__ __forceinline__ float bilerp(float hy0, float hy1, float wx0, float wx1, float a, float b, float c, float d) {
+    const float top = __fmaf_rn(wx0, a, __fmul_rn(wx1, b));
+    const float bot = __fmaf_rn(wx0, c, __fmul_rn(wx1, d));
+    return __fmaf_rn(hy0, top, __fmul_rn(hy1, bot));
+}
+
 __device__ __forceinline__ float norm_val(float p, float lo, float inv_den) {
     return fmaxf(fmaxf(p, 0.f) - lo - 1e-5f, 0.f) * inv_den;
 }
@@ -158,11 +166,11 @@ __global__ void __launch_bounds__(256) fullres_resample_kernel(const float* __re
             return fmaxf(fmaxf(__ldg(src + static_cast<size_t>(y) * W + x), 0.f) - mm.lo - 1e-5f, 0.f) / den;
         };
         const float v00 = at(y0, x0), v01 = at(y0, x1), v10 = at(y1, x0), v11 = at(y1, x1);
-        val = hy0 * (wx0 * v00 + wx1 * v01) + hy1 * (wx0 * v10 + wx1 * v11);
+        val = bilerp(hy0, hy1, wx0, wx1, v00, v01, v10, v11);
         // sum of the tap weights whose (normalised) input is positive: what the backward needs to form
         // S0 = sum_pixels gy*[z>0]/den from the OUTPUT-sized tensors alone
-        taps = hy0 * (wx0 * (v00 > 0.f ? 1.f : 0.f) + wx1 * (v01 > 0.f ? 1.f : 0.f)) +
-               hy1 * (wx0 * (v10 > 0.f ? 1.f : 0.f) + wx1 * (v11 > 0.f ? 1.f : 0.f));
+        taps = bilerp(hy0, hy1, wx0, wx1, v00 > 0.f ? 1.f : 0.f, v01 > 0.f ? 1.f : 0.f, v10 > 0.f ? 1.f : 0.f,
+                      v11 > 0.f ? 1.f : 0.f);
     }
     dst[o] = val * lab;
     if (tapsum) tapsum[static_cast<size_t>(plane) * oh * ow + o] = taps;
@@ -333,7 +341,7 @@ __global__ void __launch_bounds__(256) resize_fwd_vec4_kernel(const float* __res
             for (int j = 0; j < 4; ++j) {
                 int x0, x1; float wx0, wx1;
                 src_coord(ox0 + j, sx, W, x0, x1, wx0, wx1);
-                v[j] = hy0 * (wx0 * __ldg(r0 + x0) + wx1 * __ldg(r0 + x1)) + hy1 * (wx0 * __ldg(r1 + x0) + wx1 * __ldg(r1 + x1));
+                v[j] = bilerp(hy0, hy1, wx0, wx1, __ldg(r0 + x0), __ldg(r0 + x1), __ldg(r1 + x0), __ldg(r1 + x1));
             }
             dst[o4] = make_float4(v[0], v[1], v[2], v[3]);
         }
@@ -353,8 +361,8 @@ __global__ void __launch_bounds__(256) resize_fwd_kernel(const float* __restrict
             int y0, y1, x0, x1; float hy0, hy1, wx0, wx1;
             src_coord(oy, sy, H, y0, y1, hy0, hy1);
             src_coord(ox, sx, W, x0, x1, wx0, wx1);
-            dst[o] = hy0 * (wx0 * __ldg(src + y0 * W + x0) + wx1 * __ldg(src + y0 * W + x1)) +
-                     hy1 * (wx0 * __ldg(src + y1 * W + x0) + wx1 * __ldg(src + y1 * W + x1));
+            dst[o] = bilerp(hy0, hy1, wx0, wx1, __ldg(src + y0 * W + x0), __ldg(src + y0 * W + x1),
+                            __ldg(src + y1 * W + x0), __ldg(src + y1 * W + x1));
         }
     }
 }
@@ -520,6 +528,185 @@ __global__ void __launch_bounds__(128) seed_pixel_kernel(const float* __restrict
     pseudo[n * HW + q] = arg;
 }
 
+// ---- K1b on a LAZY full-resolution map ------------------------------------------------------------
+// Net.forward enlarges the stride-8 maps x8 (network/resnet38_contrast.py:57-59) and the loss then reads the 135 MB result
+// back to normalise and shrink it (contrast_train.py:145-152).  These kernels take the SMALL map and evaluate the enlarged
+// one on the fly — the same expression, in the same order, as resize_fwd_kernel, so every value is bit-identical to the
+// materialised tensor — and the backward gathers straight into the small map's gradient.  The full-resolution tensor, its
+// dense gradient and the zero planes of both never exist.
+struct UpGeom {
+    int h, w, H, W;
+    float sy, sx;              // (h-1)/(H-1), (w-1)/(W-1): source step of the enlargement
+};
+__device__ __forceinline__ float up_value(const float* __restrict__ sm, const UpGeom& g, int y, int x) {
+    int y0, y1, x0, x1; float hy0, hy1, wx0, wx1;
+    src_coord(y, g.sy, g.h, y0, y1, hy0, hy1);
+    src_coord(x, g.sx, g.w, x0, x1, wx0, wx1);
+    return bilerp(hy0, hy1, wx0, wx1, sm[y0 * g.w + x0], sm[y0 * g.w + x1], sm[y1 * g.w + x0], sm[y1 * g.w + x1]);
+}
+__device__ __forceinline__ void load_small_plane(const float* __restrict__ src, float* s_plane, int hw) {
+    for (int i = threadIdx.x; i < hw; i += blockDim.x) s_plane[i] = __ldg(src + i);
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(512) up_minmax_partial_kernel(const float* __restrict__ small,
+                                                                const float* __restrict__ label,
+                                                                MinMax* __restrict__ partial, UpGeom g) {
+    extern __shared__ float s_plane[];
+    const int plane = blockIdx.y, part = blockIdx.x;
+    __shared__ MinMax s_red[16];
+    MinMax v{FLT_MAX, -FLT_MAX, INT_MAX, INT_MAX};
+    if (label[plane] != 0.f) {                                 // uniform per CTA
+        load_small_plane(small + static_cast<size_t>(plane) * g.h * g.w, s_plane, g.h * g.w);
+        const int HW = g.H * g.W;
+        const int per = ceil_div_dev(HW, static_cast<int>(gridDim.x));
+        const int begin = part * per, end = min(HW, begin + per);
+        for (int i = begin + threadIdx.x; i < end; i += blockDim.x) {
+            const int y = i / g.W, x = i - y * g.W;
+            const float e = fmaxf(up_value(s_plane, g, y, x), 0.f);
+            if (e < v.lo) { v.lo = e; v.ilo = i; }
+            if (e > v.hi) { v.hi = e; v.ihi = i; }
+        }
+    }
+    v = mm_block(v, s_red);
+    if (threadIdx.x == 0) partial[plane * gridDim.x + part] = v;
+}
+
+__global__ void __launch_bounds__(256) up_resample_kernel(const float* __restrict__ small,
+                                                          const float* __restrict__ label,
+                                                          const MinMax* __restrict__ partial, float* __restrict__ out,
+                                                          float* __restrict__ minmax, float* __restrict__ tapsum,
+                                                          UpGeom g, int oh, int ow, int nsplit) {
+    extern __shared__ float s_plane[];
+    const int plane = blockIdx.y;
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    const float lab = label[plane];
+    float* dst = out + static_cast<size_t>(plane) * oh * ow;
+    if (lab == 0.f) {
+        if (o < oh * ow) {
+            dst[o] = 0.f;
+            tapsum[static_cast<size_t>(plane) * oh * ow + o] = 0.f;
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            minmax[plane * 4 + 0] = 0.f; minmax[plane * 4 + 1] = 0.f;
+            minmax[plane * 4 + 2] = __int_as_float(0); minmax[plane * 4 + 3] = __int_as_float(0);
+        }
+        return;
+    }
+    load_small_plane(small + static_cast<size_t>(plane) * g.h * g.w, s_plane, g.h * g.w);
+    const MinMax mm = plane_minmax_final(partial, plane, nsplit);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        minmax[plane * 4 + 0] = mm.lo; minmax[plane * 4 + 1] = mm.hi;
+        minmax[plane * 4 + 2] = __int_as_float(mm.ilo); minmax[plane * 4 + 3] = __int_as_float(mm.ihi);
+    }
+    if (o >= oh * ow) return;
+    const float den = mm.hi - mm.lo + 1e-5f;
+    const int H = g.H, W = g.W;
+    auto at = [&](int y, int x) { return fmaxf(fmaxf(up_value(s_plane, g, y, x), 0.f) - mm.lo - 1e-5f, 0.f) / den; };
+    float val, taps;
+    if (oh == H && ow == W) {
+        const int y = o / W, x = o - y * W;
+        val = at(y, x);
+        taps = val > 0.f ? 1.f : 0.f;
+    } else {
+        const int oy = o / ow, ox = o - oy * ow;
+        const float sy = oh > 1 ? static_cast<float>(H - 1) / static_cast<float>(oh - 1) : 0.f;
+        const float sx = ow > 1 ? static_cast<float>(W - 1) / static_cast<float>(ow - 1) : 0.f;
+        int y0, y1, x0, x1; float hy0, hy1, wx0, wx1;
+        src_coord(oy, sy, H, y0, y1, hy0, hy1);
+        src_coord(ox, sx, W, x0, x1, wx0, wx1);
+        const float v00 = at(y0, x0), v01 = at(y0, x1), v10 = at(y1, x0), v11 = at(y1, x1);
+        val = bilerp(hy0, hy1, wx0, wx1, v00, v01, v10, v11);
+        taps = bilerp(hy0, hy1, wx0, wx1, v00 > 0.f ? 1.f : 0.f, v01 > 0.f ? 1.f : 0.f, v10 > 0.f ? 1.f : 0.f,
+                      v11 > 0.f ? 1.f : 0.f);
+    }
+    dst[o] = val * lab;
+    tapsum[static_cast<size_t>(plane) * oh * ow + o] = taps;
+}
+
+// grad_small[a] = sum over the full-resolution pixels i the enlargement builds from small pixel a of  U(i,a) * d(i),
+//   d(i) = [p_i>0] * ( gy_i*[z_i>0]*lab/den + [i==argmax]*(-S1) + [i==argmin]*(S1 - S0) )        (as fullres_bwd_kernel)
+// One WARP per small pixel: the lanes split the (at most kMaxTapRange^2) full-resolution pixels of its support, then a
+// fixed shuffle tree — no atomics, deterministic.  p_i is re-evaluated from the small plane in shared memory.
+constexpr int kUpBwdWarps = 8;
+__global__ void __launch_bounds__(kUpBwdWarps * 32) up_bwd_kernel(const float* __restrict__ small,
+                                                                  const float* __restrict__ label,
+                                                                  const float* __restrict__ minmax,
+                                                                  const float* __restrict__ gout,
+                                                                  float* __restrict__ grad_small,
+                                                                  const float* __restrict__ sums, UpGeom g, int oh,
+                                                                  int ow) {
+    extern __shared__ float s_dyn_up[];
+    const int plane = blockIdx.y;
+    const int hw = g.h * g.w, H = g.H, W = g.W;
+    const float lab = label[plane];
+    float* dst = grad_small + static_cast<size_t>(plane) * hw;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lab == 0.f) {
+        for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < hw; a += gridDim.x * blockDim.x) dst[a] = 0.f;
+        return;
+    }
+    float* s_plane = s_dyn_up;
+    TapSlot* ty = reinterpret_cast<TapSlot*>(s_dyn_up + ((hw + 1) & ~1));
+    TapSlot* tx = ty + 2 * H;
+    load_small_plane(small + static_cast<size_t>(plane) * hw, s_plane, hw);
+    const bool same = (oh == H && ow == W);
+    if (!same) {
+        const float sy = oh > 1 ? static_cast<float>(H - 1) / static_cast<float>(oh - 1) : 0.f;
+        const float sx = ow > 1 ? static_cast<float>(W - 1) / static_cast<float>(ow - 1) : 0.f;
+        build_tap_table(ty, H, oh, sy);
+        build_tap_table(tx, W, ow, sx);
+    }
+    const float lo = minmax[plane * 4], hi = minmax[plane * 4 + 1];
+    const int ilo = __float_as_int(minmax[plane * 4 + 2]), ihi = __float_as_int(minmax[plane * 4 + 3]);
+    const float inv_den = 1.f / (hi - lo + 1e-5f);
+    float S0 = 0.f, S1 = 0.f;
+    for (int k = 0; k < kSumSplit; ++k) { S0 += sums[(plane * kSumSplit + k) * 2]; S1 += sums[(plane * kSumSplit + k) * 2 + 1]; }
+    S0 *= lab * inv_den;
+    S1 *= inv_den;
+    const float* gp = gout + static_cast<size_t>(plane) * oh * ow;
+    for (int a = blockIdx.x * kUpBwdWarps + warp; a < hw; a += gridDim.x * kUpBwdWarps) {
+        const int ya = a / g.w, xa = a - ya * g.w;
+        int yf, yl, xf, xl;
+        out_range(ya, g.sy, H, yf, yl);
+        out_range(xa, g.sx, W, xf, xl);
+        const int ny = yl - yf + 1, nx = xl - xf + 1;
+        float acc = 0.f;
+        for (int t = lane; t < ny * nx; t += 32) {
+            const int y = yf + t / nx, x = xf + t % nx;
+            const float u = tap_weight(y, ya, g.sy, g.h) * tap_weight(x, xa, g.sx, g.w);
+            if (u == 0.f) continue;
+            const float pv = up_value(s_plane, g, y, x);
+            if (!(pv > 0.f)) continue;
+            const int i = y * W + x;
+            const float z = pv - lo - 1e-5f;
+            float gy = 0.f;
+            if (z > 0.f) {
+                if (same) {
+                    gy = __ldg(gp + i);
+                } else {
+                    const TapSlot ya_ = ty[2 * y], yb_ = ty[2 * y + 1], xa_ = tx[2 * x], xb_ = tx[2 * x + 1];
+                    if (ya_.w != 0.f) {
+                        if (xa_.w != 0.f) gy = fmaf(ya_.w * xa_.w, __ldg(gp + ya_.o * ow + xa_.o), gy);
+                        if (xb_.w != 0.f) gy = fmaf(ya_.w * xb_.w, __ldg(gp + ya_.o * ow + xb_.o), gy);
+                    }
+                    if (yb_.w != 0.f) {
+                        if (xa_.w != 0.f) gy = fmaf(yb_.w * xa_.w, __ldg(gp + yb_.o * ow + xa_.o), gy);
+                        if (xb_.w != 0.f) gy = fmaf(yb_.w * xb_.w, __ldg(gp + yb_.o * ow + xb_.o), gy);
+                    }
+                }
+            }
+            float d = gy * lab * inv_den;
+            if (i == ihi) d -= S1;
+            if (i == ilo) d += S1 - S0;
+            acc = fmaf(u, d, acc);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) dst[a] = acc;
+    }
+}
+
 }  // namespace wsegk
 
 using namespace wsegk;
@@ -584,6 +771,71 @@ extern "C" int wsegk_fullres_norm_bwd(const float* p, const float* label, const 
                                        static_cast<int>(tab)));
     fullres_bwd_sums_kernel<<<dim3(kSumSplit, planes), 256, 0, stream>>>(label, out, tapsum, grad_out, sums, oh * ow);
     fullres_bwd_kernel<<<dim3(nblk, planes), 256, tab, stream>>>(p, label, minmax, grad_out, grad_p, sums, H, W, oh, ow);
+    count_launches(2);
+    WSEGK_CUDA_OK(cudaGetLastError());
+    return WSEGK_OK;
+}
+
+static int up_check(const char* who, int N, int C, int h, int w, int H, int W, int oh, int ow) {
+    if (int rc = fullres_check(who, N, C, H, W, oh, ow)) return rc;
+    WSEGK_REQUIRE(h > 0 && w > 0 && h <= H && w <= W, WSEGK_ERR_BAD_SHAPE,
+                  "%s: the small map (%dx%d) must not be larger than the full-resolution one (%dx%d)", who, h, w, H, W);
+    WSEGK_REQUIRE(static_cast<size_t>(h) * w * 4 + static_cast<size_t>(2) * (H + W) * sizeof(TapSlot) + 64 <= 200 * 1024,
+                  WSEGK_ERR_BAD_SHAPE, "%s: small plane + tap tables do not fit shared memory", who);
+    return WSEGK_OK;
+}
+static UpGeom up_geom(int h, int w, int H, int W) {
+    UpGeom g;
+    g.h = h; g.w = w; g.H = H; g.W = W;
+    g.sy = H > 1 ? static_cast<float>(h - 1) / static_cast<float>(H - 1) : 0.f;      // as resize_fwd_kernel
+    g.sx = W > 1 ? static_cast<float>(w - 1) / static_cast<float>(W - 1) : 0.f;
+    return g;
+}
+
+extern "C" int wsegk_fullres_norm_up_fwd(const float* small, const float* label, float* out, float* minmax, float* tapsum,
+                                         int N, int C, int h, int w, int H, int W, int oh, int ow, void* workspace,
+                                         size_t workspace_bytes, wsegk_stream_t stream) {
+    if (int rc = check_device()) return rc;
+    WSEGK_REQUIRE(small && label && out && minmax && tapsum && workspace, WSEGK_ERR_NULL, "fullres_norm_up_fwd: null pointer");
+    if (int rc = up_check("fullres_norm_up_fwd", N, C, h, w, H, W, oh, ow)) return rc;
+    WSEGK_REQUIRE(workspace_bytes >= fullres_ws_bytes(N, C), WSEGK_ERR_WORKSPACE_TOO_SMALL,
+                  "fullres_norm_up_fwd: workspace %zu < %zu", workspace_bytes, fullres_ws_bytes(N, C));
+    MinMax* partial = static_cast<MinMax*>(workspace);
+    const int planes = N * C;
+    const UpGeom g = up_geom(h, w, H, W);
+    const size_t smem = static_cast<size_t>(h) * w * sizeof(float);
+    WSEGK_CUDA_OK(cudaFuncSetAttribute(up_minmax_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    WSEGK_CUDA_OK(cudaFuncSetAttribute(up_resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    up_minmax_partial_kernel<<<dim3(kPlaneSplit, planes), 512, smem, stream>>>(small, label, partial, g);
+    up_resample_kernel<<<dim3(ceil_div(oh * ow, 256), planes), 256, smem, stream>>>(small, label, partial, out, minmax, tapsum,
+                                                                                  g, oh, ow, kPlaneSplit);
+    count_launches(2);
+    WSEGK_CUDA_OK(cudaGetLastError());
+    return WSEGK_OK;
+}
+
+extern "C" int wsegk_fullres_norm_up_bwd(const float* small, const float* label, const float* minmax, const float* out,
+                                         const float* tapsum, const float* grad_out, float* grad_small, int N, int C,
+                                         int h, int w, int H, int W, int oh, int ow, void* workspace,
+                                         size_t workspace_bytes, wsegk_stream_t stream) {
+    if (int rc = check_device()) return rc;
+    WSEGK_REQUIRE(small && label && minmax && out && tapsum && grad_out && grad_small && workspace, WSEGK_ERR_NULL,
+                  "fullres_norm_up_bwd: null pointer");
+    if (int rc = up_check("fullres_norm_up_bwd", N, C, h, w, H, W, oh, ow)) return rc;
+    WSEGK_REQUIRE(workspace_bytes >= fullres_ws_bytes(N, C), WSEGK_ERR_WORKSPACE_TOO_SMALL,
+                  "fullres_norm_up_bwd: workspace %zu < %zu", workspace_bytes, fullres_ws_bytes(N, C));
+    float* sums = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) +
+                                           align_up(static_cast<size_t>(N) * C * kPlaneSplit * sizeof(MinMax), 1024));
+    const int planes = N * C;
+    const UpGeom g = up_geom(h, w, H, W);
+    const bool same = (oh == H && ow == W);
+    const size_t smem = static_cast<size_t>((h * w + 1) & ~1) * sizeof(float) +
+                        (same ? 0 : static_cast<size_t>(2) * (H + W) * sizeof(TapSlot));
+    WSEGK_CUDA_OK(cudaFuncSetAttribute(up_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    fullres_bwd_sums_kernel<<<dim3(kSumSplit, planes), 256, 0, stream>>>(label, out, tapsum, grad_out, sums, oh * ow);
+    const int nblk = std::min(ceil_div(h * w, kUpBwdWarps), 2 * 148);
+    up_bwd_kernel<<<dim3(nblk, planes), kUpBwdWarps * 32, smem, stream>>>(small, label, minmax, grad_out, grad_small, sums, g,
+                                                                         oh, ow);
     count_launches(2);
     WSEGK_CUDA_OK(cudaGetLastError());
     return WSEGK_OK;

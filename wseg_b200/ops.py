@@ -219,6 +219,51 @@ def fullres_norm(p: torch.Tensor, label: torch.Tensor, size: Optional[Tuple[int,
     return _FullresNorm.apply(p, label, size)
 
 
+class _FullresNormUp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, small, label, up_size, size):
+        small = _require_cuda_f32("small", small.detach())
+        n, c, h, w = small.shape
+        H, W = int(up_size[0]), int(up_size[1])
+        oh, ow = (H, W) if size is None else (int(size[0]), int(size[1]))
+        lab = _label_nc(label, n, c).to(small.device)
+        out = torch.empty(n, c, oh, ow, dtype=torch.float32, device=small.device)
+        tapsum = torch.empty(n, c, oh, ow, dtype=torch.float32, device=small.device)
+        minmax = torch.empty(n, c, 4, dtype=torch.float32, device=small.device)
+        with torch.cuda.device(small.device):
+            ws = _workspace(_lib.OP_FULLRES_NORM, small.device, N=n, C=c, h=H, w=W)
+            check(_lib.lib().wsegk_fullres_norm_up_fwd(_ptr(small), _ptr(lab), _ptr(out), _ptr(minmax), _ptr(tapsum), n, c,
+                                                       h, w, H, W, oh, ow, _ptr(ws), ws.numel(), _stream(small)),
+                  "wsegk_fullres_norm_up_fwd")
+        ctx.save_for_backward(small, out, minmax, tapsum, lab)
+        ctx.dims = (H, W)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        small, out, minmax, tapsum, lab = ctx.saved_tensors
+        grad_out = _require_cuda_f32("grad_out", grad_out)
+        n, c, h, w = small.shape
+        H, W = ctx.dims
+        oh, ow = out.shape[-2:]
+        grad_small = torch.empty_like(small)
+        with torch.cuda.device(small.device):
+            ws = _workspace(_lib.OP_FULLRES_NORM, small.device, N=n, C=c, h=H, w=W)
+            check(_lib.lib().wsegk_fullres_norm_up_bwd(_ptr(small), _ptr(lab), _ptr(minmax), _ptr(out), _ptr(tapsum),
+                                                       _ptr(grad_out), _ptr(grad_small), n, c, h, w, H, W, oh, ow,
+                                                       _ptr(ws), ws.numel(), _stream(small)),
+                  "wsegk_fullres_norm_up_bwd")
+        return grad_small, None, None, None
+
+
+def fullres_norm_up(small: torch.Tensor, label: torch.Tensor, up_size: Tuple[int, int],
+                    size: Optional[Tuple[int, int]] = None) -> torch.Tensor:
+    """``fullres_norm(bilinear_resize(small, up_size), label, size)`` without the full-resolution tensor: the x8
+    enlargement at the end of ``Net.forward`` (network/resnet38_contrast.py:57-59) fused into the normalisation the loss
+    applies to it (contrast_train.py:145-152).  Same values bit for bit; the gradient comes back on the small map."""
+    return _FullresNormUp.apply(small, label, tuple(up_size), None if size is None else tuple(size))
+
+
 # --------------------------------------------------------------------------------------------- glue (:179-180)
 def resize_fwd(x: torch.Tensor, size: Tuple[int, int]) -> torch.Tensor:
     x = _require_cuda_f32("x", x.detach())
