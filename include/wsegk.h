@@ -112,6 +112,19 @@ int wsegk_fullres_norm_up_bwd(const float* small, const float* label, const floa
                               int H, int W, int oh, int ow, void* workspace, size_t workspace_bytes,
                               wsegk_stream_t stream);
 
+/* The classification (GAP + multilabel soft margin, contrast_train.py:142,159) and min-pool (:16-25,143) losses on the
+ * same lazy full-resolution map: `small` [N,C,h,w] is what Net.forward enlarges to H x W; same arguments otherwise as
+ * wsegk_gap_mlsm_fwd/_bwd and wsegk_minpool_fwd/_bwd, gradients on the small map.  m / arg are [N,H*W]. */
+int wsegk_gap_mlsm_up_fwd(const float* small, const float* label, float* gap, float* dgap, float* loss, int N, int C, int h,
+                          int w, int H, int W, void* workspace, size_t workspace_bytes, wsegk_stream_t stream);
+int wsegk_gap_mlsm_up_bwd(const float* dgap, const float* grad_loss, float* grad_small, int N, int C, int h, int w, int H,
+                          int W, wsegk_stream_t stream);
+int wsegk_minpool_up_fwd(const float* small, const float* label, float* m, int32_t* arg, float* sel, int32_t* idx_cut, int N,
+                         int C, int h, int w, int H, int W, void* workspace, size_t workspace_bytes, wsegk_stream_t stream);
+int wsegk_minpool_up_bwd(const float* m, const int32_t* arg, const float* sel, const int32_t* idx_cut, const float* label,
+                         const float* grad_loss, float* grad_small, int N, int C, int h, int w, int H, int W,
+                         wsegk_stream_t stream);
+
 /* K1c — replaces contrast_train.py:186-197 / 215-226: relu, per-plane min/max normalisation (no outer relu),
  * channel 0 := bg_threshold, pseudo label = argmax_c(norm_cam*label) (lowest class on ties).
  * cam_rv_down [N,C,g_h,g_w], label [N,C] -> norm_cam [N,C,g_h,g_w], pseudo [N*g_h*g_w] int32. */

@@ -225,6 +225,37 @@ def test_fullres_norm_on_lazy_enlargement(cuda_dev, n, hw, up, size):
     assert rel_max(lazy, ref) <= 1e-5 and rel_max(b.grad, r.grad) <= 1e-4
 
 
+def test_lazy_step_loss_equals_materialised(cuda_dev):
+    """contrast_step_loss_lazy on the small maps == contrast_step_loss on their x8 enlargements: the 8 logged scalars and
+    the gradients that reach the small maps (through ops.bilinear_resize's backward on the materialised side)."""
+    n, H, W = 4, 256, 320
+    a, b = _views(n, (H, W), (128, 128), seed=31, dev=cuda_dev)
+    g = synth.gen(77)
+    small = {"cam1": (0.05 * synth.smooth_field(n, 21, H // 8, W // 8, g) + 0.02 * torch.randn(n, 21, H // 8, W // 8, generator=g)),
+             "cam2": (0.05 * synth.smooth_field(n, 21, 16, 16, g) + 0.02 * torch.randn(n, 21, 16, 16, generator=g))}
+    label20 = synth.labels(n, seed=5).to(cuda_dev)
+
+    def leaves():
+        return {"cam1": small["cam1"].to(cuda_dev).requires_grad_(True), "cam2": small["cam2"].to(cuda_dev).requires_grad_(True),
+                "rv1": a["cam_rv_down"].clone().requires_grad_(True), "rv2": b["cam_rv_down"].clone().requires_grad_(True),
+                "f1": a["f_proj"].clone().requires_grad_(True), "f2": b["f_proj"].clone().requires_grad_(True)}
+
+    x = leaves()
+    eager = L.contrast_step_loss(ops.bilinear_resize(x["cam1"], (H, W)), ops.bilinear_resize(x["rv1"], (H, W)), x["f1"], x["rv1"],
+                                 ops.bilinear_resize(x["cam2"], (128, 128)), ops.bilinear_resize(x["rv2"], (128, 128)), x["f2"],
+                                 x["rv2"], label20, rng=3)
+    eager["loss"].backward()
+    y = leaves()
+    lazy = L.contrast_step_loss_lazy(y["cam1"], y["rv1"], y["f1"], y["cam2"], y["rv2"], y["f2"], label20, (H, W), rng=3)
+    lazy["loss"].backward()
+    for k in L.LOSS_KEYS:
+        assert float(lazy[k]) == pytest.approx(float(eager[k]), rel=2e-6), k
+    for k in ("loss_er", "loss_ecr", "loss_nce"):
+        assert float(lazy[k]) == float(eager[k]), k                  # built from bit-identical maps
+    for k in x:
+        assert rel_max(y[k].grad, x[k].grad) <= 2e-5, k
+
+
 def _views(n, hw1, hw2, seed, d=128, dev="cpu"):
     a = {k: v.to(dev) for k, v in synth.head_outputs(n, hw1, seed=seed * 10 + 1, d=d).items()}
     b = {k: v.to(dev) for k, v in synth.head_outputs(n, hw2, seed=seed * 10 + 2, d=d).items()}

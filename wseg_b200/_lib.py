@@ -35,6 +35,10 @@ _SIGNATURES = {
                                           c_size_t, _P]),
     "wsegk_fullres_norm_up_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                           c_int, _P, c_size_t, _P]),
+    "wsegk_gap_mlsm_up_fwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
+    "wsegk_gap_mlsm_up_bwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "wsegk_minpool_up_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
+    "wsegk_minpool_up_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "wsegk_bilinear_resize_fwd": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "wsegk_bilinear_resize_bwd": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "wsegk_select_kth": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, _P, c_size_t, _P]),

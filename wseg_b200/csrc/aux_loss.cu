@@ -10,6 +10,7 @@
 #include <cfloat>
 
 #include "common.cuh"
+#include "resample.cuh"
 
 namespace wsegk {
 
@@ -403,6 +404,128 @@ __global__ void __launch_bounds__(256) minpool_bwd_kernel(const float* __restric
 }
 
 // ------------------------------------------------------------------------------------------------
+// the same two losses on a LAZY full-resolution map: the small map goes in, the x8 enlargement of
+// Net.forward (network/resnet38_contrast.py:57-59) is evaluated on the fly with the shared bilerp(), nothing of size
+// N*C*H*W is read or written, and the gradients come back on the small map
+// ------------------------------------------------------------------------------------------------
+// column / row sums of the enlargement's weights: wsum[a] = sum over outputs o of tap_weight(o, a)
+__device__ __forceinline__ float up_weight_sum(int a, float scale, int in_size, int out_size) {
+    int first, last;
+    out_range(a, scale, out_size, first, last);
+    float acc = 0.f;
+    for (int o = first; o <= last; ++o) acc += tap_weight(o, a, scale, in_size);
+    return acc;
+}
+
+// GAP of the enlarged plane = sum_a wy[ya]*wx[xa]*small[a] / (H*W)  (the enlargement is linear).  One CTA per plane; the
+// result goes to partial slot 0 of the plane so gap_mlsm_kernel is reused as is.
+__global__ void __launch_bounds__(256) gap_up_kernel(const float* __restrict__ small, float* __restrict__ partial, UpGeom g) {
+    extern __shared__ float s_w[];                     // wy[h], wx[w]
+    __shared__ float s_red[32];
+    const int plane = blockIdx.x;
+    for (int i = threadIdx.x; i < g.h + g.w; i += blockDim.x)
+        s_w[i] = i < g.h ? up_weight_sum(i, g.sy, g.h, g.H) : up_weight_sum(i - g.h, g.sx, g.w, g.W);
+    __syncthreads();
+    const float* src = small + static_cast<size_t>(plane) * g.h * g.w;
+    float acc = 0.f;
+    for (int a = threadIdx.x; a < g.h * g.w; a += blockDim.x) {
+        const int ya = a / g.w, xa = a - ya * g.w;
+        acc = fmaf(s_w[ya] * s_w[g.h + xa], __ldg(src + a), acc);
+    }
+    acc = block_sum(acc, s_red);
+    if (threadIdx.x < kGapSplit) partial[plane * kGapSplit + threadIdx.x] = threadIdx.x == 0 ? acc : 0.f;
+}
+
+// grad_small[n,c,a] = dgap[n,c] * g / (H*W) * wy[ya]*wx[xa]
+__global__ void __launch_bounds__(256) gap_up_bwd_kernel(const float* __restrict__ dgap, const float* __restrict__ gl,
+                                                         float* __restrict__ grad_small, UpGeom g) {
+    extern __shared__ float s_w[];
+    const int plane = blockIdx.x;
+    for (int i = threadIdx.x; i < g.h + g.w; i += blockDim.x)
+        s_w[i] = i < g.h ? up_weight_sum(i, g.sy, g.h, g.H) : up_weight_sum(i - g.h, g.sx, g.w, g.W);
+    __syncthreads();
+    const float v = dgap[plane] * gl[0] / (static_cast<float>(g.H) * static_cast<float>(g.W));
+    float* dst = grad_small + static_cast<size_t>(plane) * g.h * g.w;
+    for (int a = threadIdx.x; a < g.h * g.w; a += blockDim.x) {
+        const int ya = a / g.w, xa = a - ya * g.w;
+        dst[a] = v * (s_w[ya] * s_w[g.h + xa]);
+    }
+}
+
+// m[n,p] = max_{c>=1} up(small[n,c])[p]*label[n,c] over the full-resolution pixels p (first class on ties), arg = class
+__global__ void __launch_bounds__(256) minpool_max_up_kernel(const float* __restrict__ small, const float* __restrict__ label,
+                                                             float* __restrict__ m, int32_t* __restrict__ arg, int C,
+                                                             UpGeom g) {
+    __shared__ float s_lab[32];
+    const int n = blockIdx.y;
+    if (threadIdx.x < C) s_lab[threadIdx.x] = label[n * C + threadIdx.x];
+    __syncthreads();
+    const int HW = g.H * g.W, hw = g.h * g.w;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= HW) return;
+    const int y = p / g.W, x = p - y * g.W;
+    int y0, y1, x0, x1; float hy0, hy1, wx0, wx1;
+    src_coord(y, g.sy, g.h, y0, y1, hy0, hy1);
+    src_coord(x, g.sx, g.w, x0, x1, wx0, wx1);
+    const int i00 = y0 * g.w + x0, i01 = y0 * g.w + x1, i10 = y1 * g.w + x0, i11 = y1 * g.w + x1;
+    const float* src = small + static_cast<size_t>(n) * C * hw;
+    float best = -FLT_MAX;
+    int bi = 1;
+    for (int c = 1; c < C; ++c) {
+        float v = 0.f;                                   // planes with label 0 contribute exactly 0 and are not read
+        if (s_lab[c] != 0.f) {
+            const float* pl = src + static_cast<size_t>(c) * hw;
+            v = bilerp(hy0, hy1, wx0, wx1, __ldg(pl + i00), __ldg(pl + i01), __ldg(pl + i10), __ldg(pl + i11)) * s_lab[c];
+        }
+        if (v > best) { best = v; bi = c; }
+    }
+    m[static_cast<size_t>(n) * HW + p] = best;
+    arg[static_cast<size_t>(n) * HW + p] = bi;
+}
+
+// grad_small[n,c,a] = sum over the full-resolution pixels p of a's support of U(p,a) * [selected(p) && m>0 && arg==c] *
+// label*g/(k*N).  One warp per small pixel, fixed shuffle tree.
+constexpr int kMinpoolUpWarps = 8;
+__global__ void __launch_bounds__(kMinpoolUpWarps * 32) minpool_up_bwd_kernel(
+    const float* __restrict__ m, const int32_t* __restrict__ arg, const float4* __restrict__ sel,
+    const int* __restrict__ cut, const float* __restrict__ label, const float* __restrict__ gl,
+    float* __restrict__ grad_small, int N, int C, UpGeom g, int k) {
+    const int plane = blockIdx.y, n = plane / C, c = plane - n * C;
+    const int hw = g.h * g.w, HW = g.H * g.W;
+    const float lab = label[plane];
+    float* dst = grad_small + static_cast<size_t>(plane) * hw;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lab == 0.f || c == 0) {
+        for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < hw; a += gridDim.x * blockDim.x) dst[a] = 0.f;
+        return;
+    }
+    const float val = lab * gl[0] / (static_cast<float>(k) * static_cast<float>(N));
+    const float thr = sel[n].x;
+    const int cu = cut[n];
+    const float* mp = m + static_cast<size_t>(n) * HW;
+    const int32_t* ap = arg + static_cast<size_t>(n) * HW;
+    for (int a = blockIdx.x * kMinpoolUpWarps + warp; a < hw; a += gridDim.x * kMinpoolUpWarps) {
+        const int ya = a / g.w, xa = a - ya * g.w;
+        int yf, yl, xf, xl;
+        out_range(ya, g.sy, g.H, yf, yl);
+        out_range(xa, g.sx, g.W, xf, xl);
+        const int ny = yl - yf + 1, nx = xl - xf + 1;
+        float acc = 0.f;
+        for (int t = lane; t < ny * nx; t += 32) {
+            const int y = yf + t / nx, x = xf + t % nx, p = y * g.W + x;
+            if (__ldg(ap + p) != c) continue;
+            const float u = tap_weight(y, ya, g.sy, g.h) * tap_weight(x, xa, g.sx, g.w);
+            if (u == 0.f) continue;
+            const float mv = __ldg(mp + p);
+            if (mv > 0.f && is_selected(mv, p, thr, cu, false)) acc = fmaf(u, val, acc);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) dst[a] = acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // ER + ECR on the 128x128 maps
 // ------------------------------------------------------------------------------------------------
 constexpr int kAuxMaxC = 24;
@@ -576,6 +699,70 @@ extern "C" int wsegk_minpool_bwd(const float* m, const int32_t* arg, const float
     const int HW = H * W;
     minpool_bwd_kernel<<<dim3(ceil_div(HW, 256), N), 256, 0, stream>>>(m, arg, reinterpret_cast<const float4*>(sel), idx_cut,
                                                                         label, grad_loss, grad_x, N, C, HW, HW / 4);
+    count_launches(1);
+    WSEGK_CUDA_OK(cudaGetLastError());
+    return WSEGK_OK;
+}
+
+static int up_dims_ok(const char* who, int N, int C, int h, int w, int H, int W) {
+    WSEGK_REQUIRE(N > 0 && C >= 2 && C <= 32 && h > 0 && w > 0 && H >= h && W >= w && static_cast<long long>(H) * W < (1ll << 30),
+                  WSEGK_ERR_BAD_SHAPE, "%s: need N > 0, 2 <= C <= 32, 0 < h <= H, 0 < w <= W (got N=%d C=%d %dx%d -> %dx%d)", who,
+                  N, C, h, w, H, W);
+    return WSEGK_OK;
+}
+
+extern "C" int wsegk_gap_mlsm_up_fwd(const float* small, const float* label, float* gap, float* dgap, float* loss, int N,
+                                     int C, int h, int w, int H, int W, void* workspace, size_t workspace_bytes,
+                                     wsegk_stream_t stream) {
+    if (int rc = check_device()) return rc;
+    WSEGK_REQUIRE(small && label && gap && dgap && loss && workspace, WSEGK_ERR_NULL, "gap_mlsm_up_fwd: null pointer");
+    if (int rc = up_dims_ok("gap_mlsm_up_fwd", N, C, h, w, H, W)) return rc;
+    WSEGK_REQUIRE(workspace_bytes >= static_cast<size_t>(N) * C * kGapSplit * sizeof(float), WSEGK_ERR_WORKSPACE_TOO_SMALL,
+                  "gap_mlsm_up_fwd: workspace too small");
+    float* partial = static_cast<float*>(workspace);
+    gap_up_kernel<<<N * C, 256, static_cast<size_t>(h + w) * sizeof(float), stream>>>(small, partial, up_geom(h, w, H, W));
+    gap_mlsm_kernel<<<1, 256, 0, stream>>>(partial, label, gap, dgap, loss, N, C, H * W);
+    count_launches(2);
+    WSEGK_CUDA_OK(cudaGetLastError());
+    return WSEGK_OK;
+}
+
+extern "C" int wsegk_gap_mlsm_up_bwd(const float* dgap, const float* grad_loss, float* grad_small, int N, int C, int h, int w,
+                                     int H, int W, wsegk_stream_t stream) {
+    if (int rc = check_device()) return rc;
+    WSEGK_REQUIRE(dgap && grad_loss && grad_small, WSEGK_ERR_NULL, "gap_mlsm_up_bwd: null pointer");
+    if (int rc = up_dims_ok("gap_mlsm_up_bwd", N, C, h, w, H, W)) return rc;
+    gap_up_bwd_kernel<<<N * C, 256, static_cast<size_t>(h + w) * sizeof(float), stream>>>(dgap, grad_loss, grad_small,
+                                                                                          up_geom(h, w, H, W));
+    count_launches(1);
+    WSEGK_CUDA_OK(cudaGetLastError());
+    return WSEGK_OK;
+}
+
+extern "C" int wsegk_minpool_up_fwd(const float* small, const float* label, float* m, int32_t* arg, float* sel,
+                                    int32_t* idx_cut, int N, int C, int h, int w, int H, int W, void* workspace,
+                                    size_t workspace_bytes, wsegk_stream_t stream) {
+    if (int rc = check_device()) return rc;
+    WSEGK_REQUIRE(small && label && m && arg && sel && idx_cut && workspace, WSEGK_ERR_NULL, "minpool_up_fwd: null pointer");
+    if (int rc = up_dims_ok("minpool_up_fwd", N, C, h, w, H, W)) return rc;
+    WSEGK_REQUIRE(H * W >= 4, WSEGK_ERR_BAD_SHAPE, "minpool_up_fwd: bad dims");
+    const int HW = H * W;
+    minpool_max_up_kernel<<<dim3(ceil_div(HW, 256), N), 256, 0, stream>>>(small, label, m, arg, C, up_geom(h, w, H, W));
+    count_launches(1);
+    WSEGK_CUDA_OK(cudaGetLastError());
+    return wsegk_select_kth(m, N, HW, HW / 4, 0, sel, idx_cut, workspace, workspace_bytes, stream);
+}
+
+extern "C" int wsegk_minpool_up_bwd(const float* m, const int32_t* arg, const float* sel, const int32_t* idx_cut,
+                                    const float* label, const float* grad_loss, float* grad_small, int N, int C, int h, int w,
+                                    int H, int W, wsegk_stream_t stream) {
+    if (int rc = check_device()) return rc;
+    WSEGK_REQUIRE(m && arg && sel && idx_cut && label && grad_loss && grad_small, WSEGK_ERR_NULL, "minpool_up_bwd: null pointer");
+    if (int rc = up_dims_ok("minpool_up_bwd", N, C, h, w, H, W)) return rc;
+    const int nblk = std::min(ceil_div(h * w, kMinpoolUpWarps), 2 * 148);
+    minpool_up_bwd_kernel<<<dim3(nblk, N * C), kMinpoolUpWarps * 32, 0, stream>>>(
+        m, arg, reinterpret_cast<const float4*>(sel), idx_cut, label, grad_loss, grad_small, N, C, up_geom(h, w, H, W),
+        (H * W) / 4);
     count_launches(1);
     WSEGK_CUDA_OK(cudaGetLastError());
     return WSEGK_OK;

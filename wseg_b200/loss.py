@@ -118,3 +118,37 @@ def contrast_step_loss(cam1, cam_rv1, f_proj1, cam_rv1_down, cam2, cam_rv2, f_pr
     out.update({'loss': loss_cls + loss_er + loss_ecr + terms['loss_nce'], 'loss_cls': loss_cls,
                 'loss_er': loss_er, 'loss_ecr': loss_ecr})
     return out
+
+
+def contrast_step_loss_lazy(cam1_small, cam_rv1_down, f_proj1, cam2_small, cam_rv2_down, f_proj2,
+                            label20: torch.Tensor, image_size: Tuple[int, int], bg_threshold: float = 0.20,
+                            view2_size: Tuple[int, int] = (128, 128),
+                            rng: Union[int, _pyrandom.Random, None] = None, mining_seed: int = 0,
+                            group=None) -> Dict[str, torch.Tensor]:
+    """``contrast_step_loss`` for a network that does NOT enlarge its maps.
+
+    ``Net.forward`` ends by enlarging the stride-8 ``cam`` and ``cam_rv_down`` x8 (network/resnet38_contrast.py:57-59: four
+    tensors of N*21*H*W floats per step, 135 MB each at N=8, 448x448) and the loss reads them back only to pool, select and
+    normalise them.  Here the loss takes the SMALL maps (``Net.forward_small``) and every consumer evaluates the enlargement
+    on the fly with the same arithmetic: the same 8 scalars (the selections and normalised maps bit-identical, the global
+    average pool to fp32 rounding), gradients on the small maps."""
+    n = label20.shape[0]
+    label = torch.cat([torch.ones(n, 1, dtype=torch.float32, device=cam1_small.device),
+                       label20.to(cam1_small.device, torch.float32)], dim=1)
+    cls1 = ops.cls_loss_up(cam1_small, label, image_size)                                 # :142,159
+    rvmin1 = ops.min_pool_loss_up(cam_rv1_down, label, image_size)                        # :143
+    n1 = ops.fullres_norm_up(cam1_small, label, image_size, view2_size)                   # :145-148
+    rv1 = ops.fullres_norm_up(cam_rv1_down, label, image_size, view2_size)                # :149-152
+    cls2 = ops.cls_loss_up(cam2_small, label, view2_size)                                 # :155,160
+    rvmin2 = ops.min_pool_loss_up(cam_rv2_down, label, view2_size)                        # :156
+    n2 = ops.fullres_norm_up(cam2_small, label, view2_size, None)                         # :157
+    rv2 = ops.fullres_norm_up(cam_rv2_down, label, view2_size, None)                      # :158
+    loss_er, loss_ecr = ops.er_ecr_loss(n1, n2, rv1, rv2)                                 # :163-172
+    loss_cls = (cls1 + cls2) / 2 + (rvmin1 + rvmin2) / 2                                  # :174
+    grid = (view2_size[0] // 8, view2_size[1] // 8)                                       # :179
+    terms = contrast_terms(f_proj1, cam_rv1_down, f_proj2, cam_rv2_down, label, bg_threshold, grid=grid,
+                           rng=rng, mining_seed=mining_seed, group=group)
+    out = dict(terms)
+    out.update({'loss': loss_cls + loss_er + loss_ecr + terms['loss_nce'], 'loss_cls': loss_cls,
+                'loss_er': loss_er, 'loss_ecr': loss_ecr})
+    return out

@@ -31,8 +31,10 @@ class Net(resnet38d.Net):
         self.from_scratch_layers = [self.f8_3, self.f8_4, self.f9, self.fc8, self.fc_proj]
         self.not_training = [self.conv1a, self.b2, self.b2_1, self.b2_2]
 
-    def head(self, x, d):
-        """Everything after the backbone (``:34-61``); split out so benchmarks can feed synthetic backbone taps."""
+    def head(self, x, d, enlarge: bool = True):
+        """Everything after the backbone (``:34-61``); split out so benchmarks can feed synthetic backbone taps.
+        ``enlarge=False`` skips the two x8 enlargements at the end and returns the small ``cam`` instead (see
+        ``forward_small``)."""
         H, W = x.shape[-2:]
         fea = self.dropout7(d['conv6'])
         f_proj = F.relu(self.fc_proj(fea), inplace=True)
@@ -44,12 +46,20 @@ class Net(resnet38d.Net):
         x_s = F.interpolate(x, (h, w), mode='bilinear', align_corners=True)
         f = torch.cat([x_s, f8_3, f8_4], dim=1)
         cam_rv_down = self.PCM(cam_d_norm, f)                                              # K2 (:63-75)
+        if not enlarge:
+            return cam, cam_rv_down, f_proj
         cam_rv = ops.bilinear_resize(cam_rv_down, (H, W))                                  # glue (:57-58)
         cam = ops.bilinear_resize(cam, (H, W))                                             # glue (:59)
         return cam, cam_rv, f_proj, cam_rv_down
 
     def forward(self, x):
         return self.head(x, super().forward_as_dict(x))
+
+    def forward_small(self, x):
+        """Extension: ``(cam_small, cam_rv_down, f_proj)`` — ``forward`` without the two x8 enlargements
+        (``:57-59``).  ``loss.contrast_step_loss_lazy`` consumes these and evaluates the enlargements on the fly, so the
+        four N*21*H*W tensors of a training step are never written or read."""
+        return self.head(x, super().forward_as_dict(x), enlarge=False)
 
     def PCM(self, cam, f):
         n, c, h, w = f.size()

@@ -563,6 +563,78 @@ def min_pool_loss(cam_rv: torch.Tensor, label: torch.Tensor) -> torch.Tensor:
     return _MinPoolLoss.apply(cam_rv, label)
 
 
+class _ClsLossUp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, small, label, up_size):
+        small = _require_cuda_f32("cam", small)
+        n, c, h, w = small.shape
+        H, W = int(up_size[0]), int(up_size[1])
+        lab = _label_nc(label, n, c).to(small.device)
+        gap = torch.empty(n, c, dtype=torch.float32, device=small.device)
+        dgap = torch.empty_like(gap)
+        loss = torch.empty(1, dtype=torch.float32, device=small.device)
+        ws = torch.empty(n * c * 8, dtype=torch.float32, device=small.device)
+        with torch.cuda.device(small.device):
+            check(_lib.lib().wsegk_gap_mlsm_up_fwd(_ptr(small), _ptr(lab), _ptr(gap), _ptr(dgap), _ptr(loss), n, c, h, w, H, W,
+                                                   _ptr(ws), ws.numel() * 4, _stream(small)), "wsegk_gap_mlsm_up_fwd")
+        ctx.save_for_backward(dgap)
+        ctx.dims = (n, c, h, w, H, W)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        (dgap,) = ctx.saved_tensors
+        n, c, h, w, H, W = ctx.dims
+        g = grad_loss.detach().reshape(1).to(torch.float32).contiguous()
+        grad_small = torch.empty(n, c, h, w, dtype=torch.float32, device=dgap.device)
+        with torch.cuda.device(dgap.device):
+            check(_lib.lib().wsegk_gap_mlsm_up_bwd(_ptr(dgap), _ptr(g), _ptr(grad_small), n, c, h, w, H, W, _stream(dgap)),
+                  "wsegk_gap_mlsm_up_bwd")
+        return grad_small, None, None
+
+
+def cls_loss_up(cam_small: torch.Tensor, label: torch.Tensor, up_size: Tuple[int, int]) -> torch.Tensor:
+    """``cls_loss(bilinear_resize(cam_small, up_size), label)`` without the full-resolution tensor."""
+    return _ClsLossUp.apply(cam_small, label, tuple(up_size))
+
+
+class _MinPoolLossUp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, small, label, up_size):
+        small = _require_cuda_f32("cam_rv", small)
+        n, c, h, w = small.shape
+        H, W = int(up_size[0]), int(up_size[1])
+        lab = _label_nc(label, n, c).to(small.device)
+        m = torch.empty(n, H * W, dtype=torch.float32, device=small.device)
+        arg = torch.empty(n, H * W, dtype=torch.int32, device=small.device)
+        sel = torch.empty(n, 4, dtype=torch.float32, device=small.device)
+        cut = torch.empty(n, dtype=torch.int32, device=small.device)
+        with torch.cuda.device(small.device):
+            ws = _workspace(_lib.OP_SELECT, small.device, N=n, h=1, w=1)
+            check(_lib.lib().wsegk_minpool_up_fwd(_ptr(small), _ptr(lab), _ptr(m), _ptr(arg), _ptr(sel), _ptr(cut), n, c, h, w,
+                                                  H, W, _ptr(ws), ws.numel(), _stream(small)), "wsegk_minpool_up_fwd")
+        ctx.save_for_backward(m, arg, sel, cut, lab)
+        ctx.dims = (n, c, h, w, H, W)
+        k = (H * W) // 4
+        return sel[:, 2].sum() / (k * n)
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        m, arg, sel, cut, lab = ctx.saved_tensors
+        n, c, h, w, H, W = ctx.dims
+        g = grad_loss.detach().reshape(1).to(torch.float32).contiguous()
+        grad_small = torch.empty(n, c, h, w, dtype=torch.float32, device=m.device)
+        with torch.cuda.device(m.device):
+            check(_lib.lib().wsegk_minpool_up_bwd(_ptr(m), _ptr(arg), _ptr(sel), _ptr(cut), _ptr(lab), _ptr(g),
+                                                  _ptr(grad_small), n, c, h, w, H, W, _stream(m)), "wsegk_minpool_up_bwd")
+        return grad_small, None, None
+
+
+def min_pool_loss_up(cam_rv_small: torch.Tensor, label: torch.Tensor, up_size: Tuple[int, int]) -> torch.Tensor:
+    """``min_pool_loss(bilinear_resize(cam_rv_small, up_size), label)`` without the full-resolution tensor."""
+    return _MinPoolLossUp.apply(cam_rv_small, label, tuple(up_size))
+
+
 class _ErEcrLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, n1, n2, rv1, rv2):
