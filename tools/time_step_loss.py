@@ -56,3 +56,49 @@ torch.cuda.synchronize(); t0 = time.time()
 for _ in range(20): g.replay()
 torch.cuda.synchronize()
 print(f"whole loss body (aux + contrast) as a CUDA graph: {(time.time() - t0) / 20 * 1e3:.3f} ms per fwd+bwd; loss {float(res[0]):.5f}")
+
+# ---- Net.forward's tail (two x8 enlargements per view) + the loss body, materialised vs lazy -------------
+small = {"cam1": (0.05 * torch.randn(n, 21, 56, 56, device=dev)).requires_grad_(True),
+         "cam2": (0.05 * torch.randn(n, 21, 16, 16, device=dev)).requires_grad_(True),
+         "rv1": v1["cam_rv_down"].detach().clone().requires_grad_(True), "rv2": v2["cam_rv_down"].detach().clone().requires_grad_(True),
+         "f1": v1["f_proj"].detach().clone().requires_grad_(True), "f2": v2["f_proj"].detach().clone().requires_grad_(True)}
+sleaves = list(small.values())
+def graph_ms(fn, reps=20):
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3): fn()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr):
+        out = fn()
+    for _ in range(3): gr.replay()
+    torch.cuda.synchronize(); t0 = time.time()
+    for _ in range(reps): gr.replay()
+    torch.cuda.synchronize()
+    return (time.time() - t0) / reps * 1e3, out
+def materialised():
+    cam1, rv1 = _ops.bilinear_resize(small["cam1"], (448, 448)), _ops.bilinear_resize(small["rv1"], (448, 448))
+    cam2, rv2 = _ops.bilinear_resize(small["cam2"], (128, 128)), _ops.bilinear_resize(small["rv2"], (128, 128))
+    cls1 = _ops.cls_loss(cam1, label); rvmin1 = _ops.min_pool_loss(rv1, label)
+    n1 = _ops.fullres_norm(cam1, label, (128, 128)); r1 = _ops.fullres_norm(rv1, label, (128, 128))
+    cls2 = _ops.cls_loss(cam2, label); rvmin2 = _ops.min_pool_loss(rv2, label)
+    n2 = _ops.fullres_norm(cam2, label, None); r2 = _ops.fullres_norm(rv2, label, None)
+    er, ecr = _ops.er_ecr_loss(n1, n2, r1, r2)
+    t = L.contrast_terms(small["f1"], small["rv1"], small["f2"], small["rv2"], label, 0.2, grid=(16, 16), keys=keys)
+    total = (cls1 + cls2) / 2 + (rvmin1 + rvmin2) / 2 + er + ecr + t["loss_nce"]
+    return total, torch.autograd.grad(total, sleaves)
+def lazy():
+    cls1 = _ops.cls_loss_up(small["cam1"], label, (448, 448)); rvmin1 = _ops.min_pool_loss_up(small["rv1"], label, (448, 448))
+    n1 = _ops.fullres_norm_up(small["cam1"], label, (448, 448), (128, 128)); r1 = _ops.fullres_norm_up(small["rv1"], label, (448, 448), (128, 128))
+    cls2 = _ops.cls_loss_up(small["cam2"], label, (128, 128)); rvmin2 = _ops.min_pool_loss_up(small["rv2"], label, (128, 128))
+    n2 = _ops.fullres_norm_up(small["cam2"], label, (128, 128), None); r2 = _ops.fullres_norm_up(small["rv2"], label, (128, 128), None)
+    er, ecr = _ops.er_ecr_loss(n1, n2, r1, r2)
+    t = L.contrast_terms(small["f1"], small["rv1"], small["f2"], small["rv2"], label, 0.2, grid=(16, 16), keys=keys)
+    total = (cls1 + cls2) / 2 + (rvmin1 + rvmin2) / 2 + er + ecr + t["loss_nce"]
+    return total, torch.autograd.grad(total, sleaves)
+ms_m, out_m = graph_ms(materialised)
+ms_l, out_l = graph_ms(lazy)
+print(f"enlargements + whole loss body as a CUDA graph: materialised {ms_m:.3f} ms (loss {float(out_m[0]):.5f}), "
+      f"lazy {ms_l:.3f} ms (loss {float(out_l[0]):.5f})")

@@ -219,10 +219,17 @@ __global__ void __launch_bounds__(1024) sel_final_kernel(const float* __restrict
     if (threadIdx.x == 0) s_cut = len;
     __syncthreads();
     if (ceq > need) {
-        int seen = 0;                                          // ties in earlier chunks (uniform across the block)
-        for (int base = 0; base < len; base += 1024) {
+        // the chunk partials already count the ties of every (contiguous) chunk: skip to the chunk holding the need-th tie
+        int seen = 0, begin = 0, end = len;
+        for (int p = 0; p < nsplit; ++p) {
+            const int ties = __float_as_int(partial[row * kSelMaxSplit + p].z);
+            sel_chunk(len, nsplit, p, begin, end);
+            if (seen + ties >= need) break;
+            seen += ties;
+        }
+        for (int base = begin; base < end; base += 1024) {
             const int i = base + threadIdx.x;
-            const int flag = (i < len && sel_key(__ldg(src + i), lg) == tkey) ? 1 : 0;
+            const int flag = (i < end && sel_key(__ldg(src + i), lg) == tkey) ? 1 : 0;
             int incl = flag;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -504,18 +511,23 @@ __global__ void __launch_bounds__(kMinpoolUpWarps * 32) minpool_up_bwd_kernel(
     const int cu = cut[n];
     const float* mp = m + static_cast<size_t>(n) * HW;
     const int32_t* ap = arg + static_cast<size_t>(n) * HW;
+    // lane = column of the support, loop = its rows (see up_bwd_kernel)
     for (int a = blockIdx.x * kMinpoolUpWarps + warp; a < hw; a += gridDim.x * kMinpoolUpWarps) {
         const int ya = a / g.w, xa = a - ya * g.w;
         int yf, yl, xf, xl;
         out_range(ya, g.sy, g.H, yf, yl);
         out_range(xa, g.sx, g.W, xf, xl);
         const int ny = yl - yf + 1, nx = xl - xf + 1;
+        const int x = xf + lane;
+        const bool col_on = lane < nx;
+        const float ux = col_on ? tap_weight(x, xa, g.sx, g.w) : 0.f;
+        const float uy_l = lane < ny ? tap_weight(yf + lane, ya, g.sy, g.h) : 0.f;
         float acc = 0.f;
-        for (int t = lane; t < ny * nx; t += 32) {
-            const int y = yf + t / nx, x = xf + t % nx, p = y * g.W + x;
+        for (int r = 0; r < ny; ++r) {
+            const float u = __shfl_sync(0xffffffffu, uy_l, r) * ux;
+            if (!col_on || u == 0.f) continue;
+            const int p = (yf + r) * g.W + x;
             if (__ldg(ap + p) != c) continue;
-            const float u = tap_weight(y, ya, g.sy, g.h) * tap_weight(x, xa, g.sx, g.w);
-            if (u == 0.f) continue;
             const float mv = __ldg(mp + p);
             if (mv > 0.f && is_selected(mv, p, thr, cu, false)) acc = fmaf(u, val, acc);
         }

@@ -612,34 +612,59 @@ __global__ void __launch_bounds__(kUpBwdWarps * 32) up_bwd_kernel(const float* _
     S0 *= lab * inv_den;
     S1 *= inv_den;
     const float* gp = gout + static_cast<size_t>(plane) * oh * ow;
+    // Lane = column of the support (at most kMaxTapRange <= 32 of them), loop = its rows: everything that depends only on
+    // the column (enlargement weight and source taps, shrink tap-table entries) is computed once per small pixel and
+    // lives in registers; the per-row values are computed by lane r for row r and broadcast with a shuffle.
     for (int a = blockIdx.x * kUpBwdWarps + warp; a < hw; a += gridDim.x * kUpBwdWarps) {
         const int ya = a / g.w, xa = a - ya * g.w;
         int yf, yl, xf, xl;
         out_range(ya, g.sy, H, yf, yl);
         out_range(xa, g.sx, W, xf, xl);
-        const int ny = yl - yf + 1, nx = xl - xf + 1;
+        const int ny = yl - yf + 1, nx = xl - xf + 1;           // both <= kMaxTapRange
+        // column data of this lane
+        const int x = xf + lane;
+        const bool col_on = lane < nx;
+        float ux = 0.f, wx0 = 0.f, wx1 = 0.f;
+        int x0 = 0, x1 = 0;
+        TapSlot cxa{0, 0.f}, cxb{0, 0.f};
+        if (col_on) {
+            ux = tap_weight(x, xa, g.sx, g.w);
+            src_coord(x, g.sx, g.w, x0, x1, wx0, wx1);
+            if (!same) { cxa = tx[2 * x]; cxb = tx[2 * x + 1]; }
+        }
+        // row data: lane r holds row yf + r
+        const int yr = yf + lane;
+        float uy_l = 0.f, hy0_l = 0.f, hy1_l = 0.f;
+        int y0_l = 0, y1_l = 0;
+        if (lane < ny) {
+            uy_l = tap_weight(yr, ya, g.sy, g.h);
+            src_coord(yr, g.sy, g.h, y0_l, y1_l, hy0_l, hy1_l);
+        }
         float acc = 0.f;
-        for (int t = lane; t < ny * nx; t += 32) {
-            const int y = yf + t / nx, x = xf + t % nx;
-            const float u = tap_weight(y, ya, g.sy, g.h) * tap_weight(x, xa, g.sx, g.w);
-            if (u == 0.f) continue;
-            const float pv = up_value(s_plane, g, y, x);
+        for (int r = 0; r < ny; ++r) {
+            const float uy = __shfl_sync(0xffffffffu, uy_l, r);
+            const float hy0 = __shfl_sync(0xffffffffu, hy0_l, r), hy1 = __shfl_sync(0xffffffffu, hy1_l, r);
+            const int y0 = __shfl_sync(0xffffffffu, y0_l, r), y1 = __shfl_sync(0xffffffffu, y1_l, r);
+            const float u = uy * ux;
+            if (!col_on || u == 0.f) continue;
+            const float pv = bilerp(hy0, hy1, wx0, wx1, s_plane[y0 * g.w + x0], s_plane[y0 * g.w + x1],
+                                    s_plane[y1 * g.w + x0], s_plane[y1 * g.w + x1]);
             if (!(pv > 0.f)) continue;
-            const int i = y * W + x;
+            const int y = yf + r, i = y * W + x;
             const float z = pv - lo - 1e-5f;
             float gy = 0.f;
             if (z > 0.f) {
                 if (same) {
                     gy = __ldg(gp + i);
                 } else {
-                    const TapSlot ya_ = ty[2 * y], yb_ = ty[2 * y + 1], xa_ = tx[2 * x], xb_ = tx[2 * x + 1];
+                    const TapSlot ya_ = ty[2 * y], yb_ = ty[2 * y + 1];
                     if (ya_.w != 0.f) {
-                        if (xa_.w != 0.f) gy = fmaf(ya_.w * xa_.w, __ldg(gp + ya_.o * ow + xa_.o), gy);
-                        if (xb_.w != 0.f) gy = fmaf(ya_.w * xb_.w, __ldg(gp + ya_.o * ow + xb_.o), gy);
+                        if (cxa.w != 0.f) gy = fmaf(ya_.w * cxa.w, __ldg(gp + ya_.o * ow + cxa.o), gy);
+                        if (cxb.w != 0.f) gy = fmaf(ya_.w * cxb.w, __ldg(gp + ya_.o * ow + cxb.o), gy);
                     }
                     if (yb_.w != 0.f) {
-                        if (xa_.w != 0.f) gy = fmaf(yb_.w * xa_.w, __ldg(gp + yb_.o * ow + xa_.o), gy);
-                        if (xb_.w != 0.f) gy = fmaf(yb_.w * xb_.w, __ldg(gp + yb_.o * ow + xb_.o), gy);
+                        if (cxa.w != 0.f) gy = fmaf(yb_.w * cxa.w, __ldg(gp + yb_.o * ow + cxa.o), gy);
+                        if (cxb.w != 0.f) gy = fmaf(yb_.w * cxb.w, __ldg(gp + yb_.o * ow + cxb.o), gy);
                     }
                 }
             }
