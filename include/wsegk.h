@@ -44,7 +44,9 @@ enum wsegk_op {
     WSEGK_OP_PROTO = 5,
     WSEGK_OP_CONTRAST_LOSS = 6,
     WSEGK_OP_SELECT = 7,     /* select_kth and minpool_fwd: N = rows */
-    WSEGK_OP_ER_ECR = 8
+    WSEGK_OP_ER_ECR = 8,
+    WSEGK_OP_LAZY_BWD = 9    /* fullres_norm_up_bwd and minpool_up_bwd: h, w = the FULL resolution H, W.  Sized for all N*C
+                              * planes; only the planes of labelled classes are ever touched. */
 };
 
 int wsegk_version(void);
@@ -123,7 +125,7 @@ int wsegk_minpool_up_fwd(const float* small, const float* label, float* m, int32
                          int C, int h, int w, int H, int W, void* workspace, size_t workspace_bytes, wsegk_stream_t stream);
 int wsegk_minpool_up_bwd(const float* m, const int32_t* arg, const float* sel, const int32_t* idx_cut, const float* label,
                          const float* grad_loss, float* grad_small, int N, int C, int h, int w, int H, int W,
-                         wsegk_stream_t stream);
+                         void* workspace, size_t workspace_bytes, wsegk_stream_t stream);
 
 /* K1c — replaces contrast_train.py:186-197 / 215-226: relu, per-plane min/max normalisation (no outer relu),
  * channel 0 := bg_threshold, pseudo label = argmax_c(norm_cam*label) (lowest class on ties).

@@ -10,6 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libwsegk.so")
 
 OP_CAM_NORM, OP_PCM, OP_FULLRES_NORM, OP_SEED_LABELS, OP_PROTO, OP_CONTRAST_LOSS, OP_SELECT, OP_ER_ECR = 1, 2, 3, 4, 5, 6, 7, 8
+OP_LAZY_BWD = 9
 
 _P = c_void_p
 _SIGNATURES = {
@@ -38,7 +39,7 @@ _SIGNATURES = {
     "wsegk_gap_mlsm_up_fwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
     "wsegk_gap_mlsm_up_bwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "wsegk_minpool_up_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
-    "wsegk_minpool_up_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "wsegk_minpool_up_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
     "wsegk_bilinear_resize_fwd": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "wsegk_bilinear_resize_bwd": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "wsegk_select_kth": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, _P, c_size_t, _P]),

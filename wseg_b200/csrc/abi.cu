@@ -138,6 +138,8 @@ extern "C" size_t wsegk_workspace_bytes(int op, int N, int C, int K, int D, int 
             return make_pcm_plan(nullptr, N, C, K, h, w, 1).bytes;   // mode-independent (sized for precise)
         case WSEGK_OP_FULLRES_NORM:
             return fullres_workspace_bytes(N, C);
+        case WSEGK_OP_LAZY_BWD:
+            return lazy_bwd_workspace_bytes(N, C, h, w);
         case WSEGK_OP_SEED_LABELS:
             return align_up(static_cast<size_t>(N) * C * 2 * sizeof(float), 1024);
         case WSEGK_OP_PROTO:

@@ -127,37 +127,45 @@ __global__ void __launch_bounds__(kSelThreads) sel_hist_kernel(const float* __re
         if (s_hist[b]) atomicAdd(g + b, s_hist[b]);
 }
 
-// one warp per row: the bin (descending) holding the need-th key; clears the histogram for the next pass
-__global__ void __launch_bounds__(32) sel_scan_kernel(SelState* __restrict__ st, uint32_t* __restrict__ hist, int width) {
-    const int row = blockIdx.x, lane = threadIdx.x;
+// one CTA per row: the bin (descending) holding the need-th key; clears the histogram for the next pass.  Thread t owns
+// the 8 bins nb-1-8t .. nb-8-8t (one warp walking all 2048 bins cost 7.6 us per pass and row set).
+__global__ void __launch_bounds__(256) sel_scan_kernel(SelState* __restrict__ st, uint32_t* __restrict__ hist, int width) {
+    __shared__ int s_warp[8];
+    const int row = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
     uint32_t* g = hist + static_cast<size_t>(row) * kSelBins;
-    const int nb = 1 << width, per = nb / 32;
-    int sum = 0;
-    for (int j = 0; j < per; ++j) sum += static_cast<int>(g[nb - 1 - (lane * per + j)]);
+    const int nb = 1 << width;
+    int local[8], sum = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int bin = nb - 1 - (8 * t + j);
+        local[j] = bin >= 0 ? static_cast<int>(g[bin]) : 0;
+        sum += local[j];
+    }
+    const int need = st[row].need;
+    const uint32_t prefix = st[row].prefix;
     int incl = sum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
     }
-    const int need = st[row].need, excl = incl - sum;
-    const uint32_t prefix = st[row].prefix;
-    __syncwarp();
-    if (excl < need && need <= incl) {
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    int excl = incl - sum;
+    for (int w = 0; w < warp; ++w) excl += s_warp[w];
+    if (excl < need && need <= excl + sum) {
         int cum = excl;
-        for (int j = 0; j < per; ++j) {
-            const int bin = nb - 1 - (lane * per + j);
-            const int h = static_cast<int>(g[bin]);
-            if (cum + h >= need) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (cum + local[j] >= need) {
                 st[row].need = need - cum;
-                st[row].prefix = (prefix << width) | static_cast<uint32_t>(bin);
+                st[row].prefix = (prefix << width) | static_cast<uint32_t>(nb - 1 - (8 * t + j));
                 break;
             }
-            cum += h;
+            cum += local[j];
         }
     }
-    __syncwarp();
-    for (int b = lane; b < kSelBins; b += 32) g[b] = 0u;
+    for (int b = t; b < kSelBins; b += 256) g[b] = 0u;
 }
 
 // per chunk: sum / relu-sum over the strictly-beyond elements and the number of ties
@@ -279,7 +287,7 @@ static int select_launch(const float* x, int rows, int len, int k, int largest, 
     for (int pass = 0; pass < 3; ++pass) {
         sel_hist_kernel<<<dim3(nsplit, rows), kSelThreads, 0, stream>>>(x, len, largest, shifts[pass], widths[pass],
                                                                         pass == 0 ? 1 : 0, st, hist);
-        sel_scan_kernel<<<rows, 32, 0, stream>>>(st, hist, widths[pass]);
+        sel_scan_kernel<<<rows, 256, 0, stream>>>(st, hist, widths[pass]);
     }
     sel_sum_kernel<<<dim3(nsplit, rows), kSelThreads, 0, stream>>>(x, len, largest, st, partial);
     sel_final_kernel<<<rows, 1024, 0, stream>>>(x, len, largest, nsplit, st, partial, reinterpret_cast<float4*>(sel), idx_cut);
@@ -490,51 +498,26 @@ __global__ void __launch_bounds__(256) minpool_max_up_kernel(const float* __rest
     arg[static_cast<size_t>(n) * HW + p] = bi;
 }
 
-// grad_small[n,c,a] = sum over the full-resolution pixels p of a's support of U(p,a) * [selected(p) && m>0 && arg==c] *
-// label*g/(k*N).  One warp per small pixel, fixed shuffle tree.
-constexpr int kMinpoolUpWarps = 8;
-__global__ void __launch_bounds__(kMinpoolUpWarps * 32) minpool_up_bwd_kernel(
-    const float* __restrict__ m, const int32_t* __restrict__ arg, const float4* __restrict__ sel,
-    const int* __restrict__ cut, const float* __restrict__ label, const float* __restrict__ gl,
-    float* __restrict__ grad_small, int N, int C, UpGeom g, int k) {
-    const int plane = blockIdx.y, n = plane / C, c = plane - n * C;
-    const int hw = g.h * g.w, HW = g.H * g.W;
-    const float lab = label[plane];
-    float* dst = grad_small + static_cast<size_t>(plane) * hw;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lab == 0.f || c == 0) {
-        for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < hw; a += gridDim.x * blockDim.x) dst[a] = 0.f;
-        return;
-    }
-    const float val = lab * gl[0] / (static_cast<float>(k) * static_cast<float>(N));
-    const float thr = sel[n].x;
-    const int cu = cut[n];
-    const float* mp = m + static_cast<size_t>(n) * HW;
-    const int32_t* ap = arg + static_cast<size_t>(n) * HW;
-    // lane = column of the support, loop = its rows (see up_bwd_kernel)
-    for (int a = blockIdx.x * kMinpoolUpWarps + warp; a < hw; a += gridDim.x * kMinpoolUpWarps) {
-        const int ya = a / g.w, xa = a - ya * g.w;
-        int yf, yl, xf, xl;
-        out_range(ya, g.sy, g.H, yf, yl);
-        out_range(xa, g.sx, g.W, xf, xl);
-        const int ny = yl - yf + 1, nx = xl - xf + 1;
-        const int x = xf + lane;
-        const bool col_on = lane < nx;
-        const float ux = col_on ? tap_weight(x, xa, g.sx, g.w) : 0.f;
-        const float uy_l = lane < ny ? tap_weight(yf + lane, ya, g.sy, g.h) : 0.f;
-        float acc = 0.f;
-        for (int r = 0; r < ny; ++r) {
-            const float u = __shfl_sync(0xffffffffu, uy_l, r) * ux;
-            if (!col_on || u == 0.f) continue;
-            const int p = (yf + r) * g.W + x;
-            if (__ldg(ap + p) != c) continue;
-            const float mv = __ldg(mp + p);
-            if (mv > 0.f && is_selected(mv, p, thr, cu, false)) acc = fmaf(u, val, acc);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) dst[a] = acc;
-    }
+// Backward: the full-resolution gradient [selected(p) && m>0 && c == arg] * label*g/(k*N) goes to a scratch tensor for the
+// planes of the LABELLED foreground classes only (the rest of the scratch is never touched), then the enlargement's
+// transpose — which skips the same planes and channel 0 — brings it onto the small map.
+__global__ void __launch_bounds__(256) minpool_dense_labelled_kernel(const float* __restrict__ m, const int32_t* __restrict__ arg,
+                                                                     const float4* __restrict__ sel, const int* __restrict__ cut,
+                                                                     const float* __restrict__ label, const float* __restrict__ gl,
+                                                                     float* __restrict__ scratch, int N, int C, int HW, int k) {
+    __shared__ float s_lab[32];
+    const int n = blockIdx.y;
+    if (threadIdx.x < C) s_lab[threadIdx.x] = label[n * C + threadIdx.x];
+    __syncthreads();
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= HW) return;
+    const float mv = m[static_cast<size_t>(n) * HW + p];
+    const int a = arg[static_cast<size_t>(n) * HW + p];
+    const bool on = mv > 0.f && is_selected(mv, p, sel[n].x, cut[n], false);
+    const float val = on ? s_lab[a] * gl[0] / (static_cast<float>(k) * static_cast<float>(N)) : 0.f;
+    float* dst = scratch + static_cast<size_t>(n) * C * HW + p;
+    for (int c = 1; c < C; ++c)
+        if (s_lab[c] != 0.f) dst[static_cast<size_t>(c) * HW] = (c == a) ? val : 0.f;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -767,15 +750,20 @@ extern "C" int wsegk_minpool_up_fwd(const float* small, const float* label, floa
 
 extern "C" int wsegk_minpool_up_bwd(const float* m, const int32_t* arg, const float* sel, const int32_t* idx_cut,
                                     const float* label, const float* grad_loss, float* grad_small, int N, int C, int h, int w,
-                                    int H, int W, wsegk_stream_t stream) {
+                                    int H, int W, void* workspace, size_t workspace_bytes, wsegk_stream_t stream) {
     if (int rc = check_device()) return rc;
-    WSEGK_REQUIRE(m && arg && sel && idx_cut && label && grad_loss && grad_small, WSEGK_ERR_NULL, "minpool_up_bwd: null pointer");
+    WSEGK_REQUIRE(m && arg && sel && idx_cut && label && grad_loss && grad_small && workspace, WSEGK_ERR_NULL,
+                  "minpool_up_bwd: null pointer");
     if (int rc = up_dims_ok("minpool_up_bwd", N, C, h, w, H, W)) return rc;
-    const int nblk = std::min(ceil_div(h * w, kMinpoolUpWarps), 2 * 148);
-    minpool_up_bwd_kernel<<<dim3(nblk, N * C), kMinpoolUpWarps * 32, 0, stream>>>(
-        m, arg, reinterpret_cast<const float4*>(sel), idx_cut, label, grad_loss, grad_small, N, C, up_geom(h, w, H, W),
-        (H * W) / 4);
+    WSEGK_REQUIRE(workspace_bytes >= lazy_bwd_workspace_bytes(N, C, H, W), WSEGK_ERR_WORKSPACE_TOO_SMALL,
+                  "minpool_up_bwd: workspace %zu < %zu (WSEGK_OP_LAZY_BWD)", workspace_bytes,
+                  lazy_bwd_workspace_bytes(N, C, H, W));
+    float* scratch = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + fullres_workspace_bytes(N, C));
+    const int HW = H * W;
+    minpool_dense_labelled_kernel<<<dim3(ceil_div(HW, 256), N), 256, 0, stream>>>(
+        m, arg, reinterpret_cast<const float4*>(sel), idx_cut, label, grad_loss, scratch, N, C, HW, HW / 4);
     count_launches(1);
+    launch_resize_bwd_labelled(scratch, label, grad_small, N * C, h, w, H, W, C, stream);
     WSEGK_CUDA_OK(cudaGetLastError());
     return WSEGK_OK;
 }

@@ -45,6 +45,11 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ inline int ceil_div_dev(int a, int b) { return (a + b - 1) / b; }
 size_t fullres_workspace_bytes(int N, int C);
+size_t lazy_bwd_workspace_bytes(int N, int C, int H, int W);
+// gx[plane] = transpose of the bilinear enlargement applied to gy[plane]; planes whose label is 0 (and, if c0_stride > 0,
+// planes with plane % c0_stride == 0) are not read: their gx is zero
+int launch_resize_bwd_labelled(const float* gy, const float* label, float* gx, int planes, int H, int W, int oh, int ow,
+                               int c0_stride, cudaStream_t stream);
 size_t proto_workspace_bytes(int N, int C, int h, int w);
 size_t contrast_workspace_bytes(int N, int C, int D, int h, int w);
 size_t select_workspace_bytes(int rows);

@@ -54,6 +54,8 @@ __device__ __forceinline__ MinMax mm_block(MinMax v, MinMax* s_red) {
 }
 
 constexpr int kPlaneSplit = 8;   // CTAs per (n,c) plane in the min/max pass
+constexpr int kUpPlaneSplit = 32;    // ... when the plane is evaluated on the fly (compute- instead of bandwidth-bound)
+constexpr int kPlaneSplitMax = 32;   // what the workspace is sized for
 
 // partial min/max (+ first arg) of relu(p) over a slice of one plane; masked planes exit immediately
 __global__ void __launch_bounds__(512) plane_minmax_partial_kernel(const float* __restrict__ p,
@@ -383,13 +385,19 @@ __global__ void __launch_bounds__(256) resize_bwd_kernel(const float* __restrict
 
 constexpr int kMaxTapRange = 24;      // outputs touching one input coordinate along one axis (x8 enlargement: 18)
 __global__ void __launch_bounds__(256) resize_bwd_gather_kernel(const float* __restrict__ gy, float* __restrict__ gx,
-                                                                int planes, int H, int W, int oh, int ow) {
+                                                                int planes, int H, int W, int oh, int ow,
+                                                                const float* __restrict__ label, int c0_stride) {
     const float sy = oh > 1 ? static_cast<float>(H - 1) / static_cast<float>(oh - 1) : 0.f;
     const float sx = ow > 1 ? static_cast<float>(W - 1) / static_cast<float>(ow - 1) : 0.f;
     const int isz = H * W;
     for (int plane = blockIdx.y; plane < planes; plane += gridDim.y) {
         const float* g = gy + static_cast<size_t>(plane) * oh * ow;
         float* dst = gx + static_cast<size_t>(plane) * isz;
+        if (label != nullptr && (label[plane] == 0.f || (c0_stride > 0 && plane % c0_stride == 0))) {
+            // an unlabelled plane: its full-resolution gradient was never written and is not read
+            for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < isz; i += gridDim.x * blockDim.x) dst[i] = 0.f;
+            continue;
+        }
         for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < isz; i += gridDim.x * blockDim.x) {
             const int yq = i / W, xq = i - yq * W;
             int oy0, oy1, ox0, ox1;
@@ -571,28 +579,19 @@ __global__ void __launch_bounds__(256) up_resample_kernel(const float* __restric
     tapsum[static_cast<size_t>(plane) * oh * ow + o] = taps;
 }
 
-// grad_small[a] = sum over the full-resolution pixels i the enlargement builds from small pixel a of  U(i,a) * d(i),
-//   d(i) = [p_i>0] * ( gy_i*[z_i>0]*lab/den + [i==argmax]*(-S1) + [i==argmin]*(S1 - S0) )        (as fullres_bwd_kernel)
-// One WARP per small pixel: the lanes split the (at most kMaxTapRange^2) full-resolution pixels of its support, then a
-// fixed shuffle tree — no atomics, deterministic.  p_i is re-evaluated from the small plane in shared memory.
-constexpr int kUpBwdWarps = 8;
-__global__ void __launch_bounds__(kUpBwdWarps * 32) up_bwd_kernel(const float* __restrict__ small,
-                                                                  const float* __restrict__ label,
-                                                                  const float* __restrict__ minmax,
-                                                                  const float* __restrict__ gout,
-                                                                  float* __restrict__ grad_small,
-                                                                  const float* __restrict__ sums, UpGeom g, int oh,
-                                                                  int ow) {
+// Backward: the full-resolution gradient d(i) = [p_i>0] * ( gy_i*[z_i>0]*lab/den + [i==argmax]*(-S1) + [i==argmin]*(S1-S0) )
+// (as fullres_bwd_kernel, with p_i re-evaluated from the small plane in shared memory) is written to a scratch tensor for
+// the LABELLED planes only — about 2.5 of 21 per image; the other planes of the scratch are never touched — and the
+// enlargement's transpose (resize_bwd_gather_kernel, which skips the same planes) brings it onto the small map.
+__global__ void __launch_bounds__(256) up_dense_grad_kernel(const float* __restrict__ small, const float* __restrict__ label,
+                                                            const float* __restrict__ minmax,
+                                                            const float* __restrict__ gout, float* __restrict__ scratch,
+                                                            const float* __restrict__ sums, UpGeom g, int oh, int ow) {
     extern __shared__ float s_dyn_up[];
     const int plane = blockIdx.y;
-    const int hw = g.h * g.w, H = g.H, W = g.W;
     const float lab = label[plane];
-    float* dst = grad_small + static_cast<size_t>(plane) * hw;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lab == 0.f) {
-        for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < hw; a += gridDim.x * blockDim.x) dst[a] = 0.f;
-        return;
-    }
+    if (lab == 0.f) return;
+    const int hw = g.h * g.w, H = g.H, W = g.W, HW = H * W;
     float* s_plane = s_dyn_up;
     TapSlot* ty = reinterpret_cast<TapSlot*>(s_dyn_up + ((hw + 1) & ~1));
     TapSlot* tx = ty + 2 * H;
@@ -612,71 +611,40 @@ __global__ void __launch_bounds__(kUpBwdWarps * 32) up_bwd_kernel(const float* _
     S0 *= lab * inv_den;
     S1 *= inv_den;
     const float* gp = gout + static_cast<size_t>(plane) * oh * ow;
-    // Lane = column of the support (at most kMaxTapRange <= 32 of them), loop = its rows: everything that depends only on
-    // the column (enlargement weight and source taps, shrink tap-table entries) is computed once per small pixel and
-    // lives in registers; the per-row values are computed by lane r for row r and broadcast with a shuffle.
-    for (int a = blockIdx.x * kUpBwdWarps + warp; a < hw; a += gridDim.x * kUpBwdWarps) {
-        const int ya = a / g.w, xa = a - ya * g.w;
-        int yf, yl, xf, xl;
-        out_range(ya, g.sy, H, yf, yl);
-        out_range(xa, g.sx, W, xf, xl);
-        const int ny = yl - yf + 1, nx = xl - xf + 1;           // both <= kMaxTapRange
-        // column data of this lane
-        const int x = xf + lane;
-        const bool col_on = lane < nx;
-        float ux = 0.f, wx0 = 0.f, wx1 = 0.f;
-        int x0 = 0, x1 = 0;
-        TapSlot cxa{0, 0.f}, cxb{0, 0.f};
-        if (col_on) {
-            ux = tap_weight(x, xa, g.sx, g.w);
-            src_coord(x, g.sx, g.w, x0, x1, wx0, wx1);
-            if (!same) { cxa = tx[2 * x]; cxb = tx[2 * x + 1]; }
-        }
-        // row data: lane r holds row yf + r
-        const int yr = yf + lane;
-        float uy_l = 0.f, hy0_l = 0.f, hy1_l = 0.f;
-        int y0_l = 0, y1_l = 0;
-        if (lane < ny) {
-            uy_l = tap_weight(yr, ya, g.sy, g.h);
-            src_coord(yr, g.sy, g.h, y0_l, y1_l, hy0_l, hy1_l);
-        }
-        float acc = 0.f;
-        for (int r = 0; r < ny; ++r) {
-            const float uy = __shfl_sync(0xffffffffu, uy_l, r);
-            const float hy0 = __shfl_sync(0xffffffffu, hy0_l, r), hy1 = __shfl_sync(0xffffffffu, hy1_l, r);
-            const int y0 = __shfl_sync(0xffffffffu, y0_l, r), y1 = __shfl_sync(0xffffffffu, y1_l, r);
-            const float u = uy * ux;
-            if (!col_on || u == 0.f) continue;
-            const float pv = bilerp(hy0, hy1, wx0, wx1, s_plane[y0 * g.w + x0], s_plane[y0 * g.w + x1],
-                                    s_plane[y1 * g.w + x0], s_plane[y1 * g.w + x1]);
-            if (!(pv > 0.f)) continue;
-            const int y = yf + r, i = y * W + x;
-            const float z = pv - lo - 1e-5f;
-            float gy = 0.f;
-            if (z > 0.f) {
-                if (same) {
-                    gy = __ldg(gp + i);
-                } else {
-                    const TapSlot ya_ = ty[2 * y], yb_ = ty[2 * y + 1];
-                    if (ya_.w != 0.f) {
-                        if (cxa.w != 0.f) gy = fmaf(ya_.w * cxa.w, __ldg(gp + ya_.o * ow + cxa.o), gy);
-                        if (cxb.w != 0.f) gy = fmaf(ya_.w * cxb.w, __ldg(gp + ya_.o * ow + cxb.o), gy);
-                    }
-                    if (yb_.w != 0.f) {
-                        if (cxa.w != 0.f) gy = fmaf(yb_.w * cxa.w, __ldg(gp + yb_.o * ow + cxa.o), gy);
-                        if (cxb.w != 0.f) gy = fmaf(yb_.w * cxb.w, __ldg(gp + yb_.o * ow + cxb.o), gy);
-                    }
+    float* dst = scratch + static_cast<size_t>(plane) * HW;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+        const int y = i / W, x = i - y * W;
+        const float pv = up_value(s_plane, g, y, x);
+        const float z = fmaxf(pv, 0.f) - lo - 1e-5f;
+        float gy = 0.f;
+        if (z > 0.f) {
+            if (same) {
+                gy = __ldg(gp + i);
+            } else {
+                const TapSlot ya = ty[2 * y], yb = ty[2 * y + 1], xa = tx[2 * x], xb = tx[2 * x + 1];
+                if (ya.w != 0.f) {
+                    if (xa.w != 0.f) gy = fmaf(ya.w * xa.w, __ldg(gp + ya.o * ow + xa.o), gy);
+                    if (xb.w != 0.f) gy = fmaf(ya.w * xb.w, __ldg(gp + ya.o * ow + xb.o), gy);
+                }
+                if (yb.w != 0.f) {
+                    if (xa.w != 0.f) gy = fmaf(yb.w * xa.w, __ldg(gp + yb.o * ow + xa.o), gy);
+                    if (xb.w != 0.f) gy = fmaf(yb.w * xb.w, __ldg(gp + yb.o * ow + xb.o), gy);
                 }
             }
-            float d = gy * lab * inv_den;
-            if (i == ihi) d -= S1;
-            if (i == ilo) d += S1 - S0;
-            acc = fmaf(u, d, acc);
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) dst[a] = acc;
+        float d = gy * lab * inv_den;
+        if (i == ihi) d -= S1;
+        if (i == ilo) d += S1 - S0;
+        dst[i] = (pv > 0.f) ? d : 0.f;
     }
+}
+
+int launch_resize_bwd_labelled(const float* gy, const float* label, float* gx, int planes, int H, int W, int oh, int ow,
+                               int c0_stride, cudaStream_t stream) {
+    const dim3 grid(std::min(ceil_div(H * W, 256), 1024), std::min(planes, 32768));
+    resize_bwd_gather_kernel<<<grid, 256, 0, stream>>>(gy, gx, planes, H, W, oh, ow, label, c0_stride);
+    count_launches(1);
+    return WSEGK_OK;
 }
 
 }  // namespace wsegk
@@ -695,12 +663,15 @@ static int fullres_check(const char* who, int N, int C, int H, int W, int oh, in
 
 static size_t fullres_ws_bytes(int N, int C) {
     // min/max partials + backward block sums
-    return align_up(static_cast<size_t>(N) * C * kPlaneSplit * sizeof(MinMax), 1024) +
+    return align_up(static_cast<size_t>(N) * C * kPlaneSplitMax * sizeof(MinMax), 1024) +
            align_up(static_cast<size_t>(N) * C * 64 * 2 * sizeof(float), 1024);
 }
 
 namespace wsegk {
 size_t fullres_workspace_bytes(int N, int C) { return fullres_ws_bytes(N, C); }
+size_t lazy_bwd_workspace_bytes(int N, int C, int H, int W) {
+    return fullres_ws_bytes(N, C) + align_up(static_cast<size_t>(N) * C * H * W * sizeof(float), 1024);
+}
 }
 
 extern "C" int wsegk_fullres_norm_fwd(const float* p, const float* label, float* out, float* minmax, float* tapsum,
@@ -733,7 +704,7 @@ extern "C" int wsegk_fullres_norm_bwd(const float* p, const float* label, const 
     WSEGK_REQUIRE(workspace_bytes >= fullres_ws_bytes(N, C), WSEGK_ERR_WORKSPACE_TOO_SMALL,
                   "fullres_norm_bwd: workspace %zu < %zu", workspace_bytes, fullres_ws_bytes(N, C));
     float* sums = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) +
-                                           align_up(static_cast<size_t>(N) * C * kPlaneSplit * sizeof(MinMax), 1024));
+                                           align_up(static_cast<size_t>(N) * C * kPlaneSplitMax * sizeof(MinMax), 1024));
     const int planes = N * C;
     const int nblk = std::min(64, ceil_div(H * W, 256 * 4));
     const size_t tab = (oh == H && ow == W) ? 0 : static_cast<size_t>(2) * (H + W) * sizeof(TapSlot);
@@ -770,9 +741,9 @@ extern "C" int wsegk_fullres_norm_up_fwd(const float* small, const float* label,
     const size_t smem = static_cast<size_t>(h) * w * sizeof(float);
     WSEGK_CUDA_OK(cudaFuncSetAttribute(up_minmax_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     WSEGK_CUDA_OK(cudaFuncSetAttribute(up_resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    up_minmax_partial_kernel<<<dim3(kPlaneSplit, planes), 512, smem, stream>>>(small, label, partial, g);
+    up_minmax_partial_kernel<<<dim3(kUpPlaneSplit, planes), 256, smem, stream>>>(small, label, partial, g);
     up_resample_kernel<<<dim3(ceil_div(oh * ow, 256), planes), 256, smem, stream>>>(small, label, partial, out, minmax, tapsum,
-                                                                                  g, oh, ow, kPlaneSplit);
+                                                                                  g, oh, ow, kUpPlaneSplit);
     count_launches(2);
     WSEGK_CUDA_OK(cudaGetLastError());
     return WSEGK_OK;
@@ -786,21 +757,23 @@ extern "C" int wsegk_fullres_norm_up_bwd(const float* small, const float* label,
     WSEGK_REQUIRE(small && label && minmax && out && tapsum && grad_out && grad_small && workspace, WSEGK_ERR_NULL,
                   "fullres_norm_up_bwd: null pointer");
     if (int rc = up_check("fullres_norm_up_bwd", N, C, h, w, H, W, oh, ow)) return rc;
-    WSEGK_REQUIRE(workspace_bytes >= fullres_ws_bytes(N, C), WSEGK_ERR_WORKSPACE_TOO_SMALL,
-                  "fullres_norm_up_bwd: workspace %zu < %zu", workspace_bytes, fullres_ws_bytes(N, C));
-    float* sums = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) +
-                                           align_up(static_cast<size_t>(N) * C * kPlaneSplit * sizeof(MinMax), 1024));
+    WSEGK_REQUIRE(workspace_bytes >= lazy_bwd_workspace_bytes(N, C, H, W), WSEGK_ERR_WORKSPACE_TOO_SMALL,
+                  "fullres_norm_up_bwd: workspace %zu < %zu (WSEGK_OP_LAZY_BWD)", workspace_bytes,
+                  lazy_bwd_workspace_bytes(N, C, H, W));
+    uint8_t* ws = static_cast<uint8_t*>(workspace);
+    float* sums = reinterpret_cast<float*>(ws + align_up(static_cast<size_t>(N) * C * kPlaneSplitMax * sizeof(MinMax), 1024));
+    float* scratch = reinterpret_cast<float*>(ws + fullres_ws_bytes(N, C));
     const int planes = N * C;
     const UpGeom g = up_geom(h, w, H, W);
     const bool same = (oh == H && ow == W);
     const size_t smem = static_cast<size_t>((h * w + 1) & ~1) * sizeof(float) +
                         (same ? 0 : static_cast<size_t>(2) * (H + W) * sizeof(TapSlot));
-    WSEGK_CUDA_OK(cudaFuncSetAttribute(up_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    WSEGK_CUDA_OK(cudaFuncSetAttribute(up_dense_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     fullres_bwd_sums_kernel<<<dim3(kSumSplit, planes), 256, 0, stream>>>(label, out, tapsum, grad_out, sums, oh * ow);
-    const int nblk = std::min(ceil_div(h * w, kUpBwdWarps), 2 * 148);
-    up_bwd_kernel<<<dim3(nblk, planes), kUpBwdWarps * 32, smem, stream>>>(small, label, minmax, grad_out, grad_small, sums, g,
-                                                                         oh, ow);
+    const int nblk = std::min(64, ceil_div(H * W, 256 * 4));
+    up_dense_grad_kernel<<<dim3(nblk, planes), 256, smem, stream>>>(small, label, minmax, grad_out, scratch, sums, g, oh, ow);
     count_launches(2);
+    launch_resize_bwd_labelled(scratch, label, grad_small, planes, h, w, H, W, 0, stream);
     WSEGK_CUDA_OK(cudaGetLastError());
     return WSEGK_OK;
 }
@@ -862,7 +835,7 @@ extern "C" int wsegk_bilinear_resize_bwd(const float* grad_y, float* grad_x, int
                                            static_cast<int>(tab)));
         resize_bwd_kernel<<<grid, 256, tab, stream>>>(grad_y, grad_x, planes, H, W, oh, ow);
     } else {
-        resize_bwd_gather_kernel<<<grid, 256, 0, stream>>>(grad_y, grad_x, planes, H, W, oh, ow);
+        resize_bwd_gather_kernel<<<grid, 256, 0, stream>>>(grad_y, grad_x, planes, H, W, oh, ow, nullptr, 0);
     }
     count_launches(1);
     WSEGK_CUDA_OK(cudaGetLastError());

@@ -56,9 +56,22 @@ __device__ __forceinline__ float up_value(const float* __restrict__ sm, const Up
     src_coord(x, g.sx, g.w, x0, x1, wx0, wx1);
     return bilerp(hy0, hy1, wx0, wx1, sm[y0 * g.w + x0], sm[y0 * g.w + x1], sm[y1 * g.w + x0], sm[y1 * g.w + x1]);
 }
-__device__ __forceinline__ void load_small_plane(const float* __restrict__ src, float* s_plane, int hw) {
-    for (int i = threadIdx.x; i < hw; i += blockDim.x) s_plane[i] = __ldg(src + i);
+// n floats global -> shared, eight independent loads per thread in flight (a rolled load->store loop costs one L2 latency
+// per iteration); ends with a __syncthreads()
+__device__ __forceinline__ void stage_plane(const float* __restrict__ src, float* dst, int n) {
+    const int step = static_cast<int>(blockDim.x);
+    for (int i0 = threadIdx.x; i0 < n; i0 += 8 * step) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = (i0 + j * step < n) ? __ldg(src + i0 + j * step) : 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (i0 + j * step < n) dst[i0 + j * step] = v[j];
+    }
     __syncthreads();
+}
+__device__ __forceinline__ void load_small_plane(const float* __restrict__ src, float* s_plane, int hw) {
+    stage_plane(src, s_plane, hw);
 }
 
 inline UpGeom up_geom(int h, int w, int H, int W) {

@@ -248,7 +248,7 @@ class _FullresNormUp(torch.autograd.Function):
         oh, ow = out.shape[-2:]
         grad_small = torch.empty_like(small)
         with torch.cuda.device(small.device):
-            ws = _workspace(_lib.OP_FULLRES_NORM, small.device, N=n, C=c, h=H, w=W)
+            ws = _workspace(_lib.OP_LAZY_BWD, small.device, N=n, C=c, h=H, w=W)   # only labelled planes are touched
             check(_lib.lib().wsegk_fullres_norm_up_bwd(_ptr(small), _ptr(lab), _ptr(minmax), _ptr(out), _ptr(tapsum),
                                                        _ptr(grad_out), _ptr(grad_small), n, c, h, w, H, W, oh, ow,
                                                        _ptr(ws), ws.numel(), _stream(small)),
@@ -625,8 +625,10 @@ class _MinPoolLossUp(torch.autograd.Function):
         g = grad_loss.detach().reshape(1).to(torch.float32).contiguous()
         grad_small = torch.empty(n, c, h, w, dtype=torch.float32, device=m.device)
         with torch.cuda.device(m.device):
+            ws = _workspace(_lib.OP_LAZY_BWD, m.device, N=n, C=c, h=H, w=W)       # only labelled planes are touched
             check(_lib.lib().wsegk_minpool_up_bwd(_ptr(m), _ptr(arg), _ptr(sel), _ptr(cut), _ptr(lab), _ptr(g),
-                                                  _ptr(grad_small), n, c, h, w, H, W, _stream(m)), "wsegk_minpool_up_bwd")
+                                                  _ptr(grad_small), n, c, h, w, H, W, _ptr(ws), ws.numel(), _stream(m)),
+                  "wsegk_minpool_up_bwd")
         return grad_small, None, None
 
 
