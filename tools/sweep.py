@@ -174,6 +174,32 @@ def sweep_fullres(rows, cases, iters, flush):
         print(json.dumps(rows[-1]), flush=True)
         del p, go, st
         torch.cuda.empty_cache()
+        # the same operator on the LAZY map: input = the stride-8 map, the x8 enlargement evaluated on the fly;
+        # compared with enlargement + K1b on the materialised tensor (forward and backward each)
+        small = torch.randn(n, 21, hw // 8, hw // 8, generator=g).to(DEV).requires_grad_(True)
+        go = torch.randn(n, 21, oh, ow, generator=g).to(DEV)
+        st = {}
+
+        def lazy_fwd():
+            st["y"] = ops.fullres_norm_up(small, label, (hw, hw), size)
+
+        def lazy_bwd():
+            st["g"] = torch.autograd.grad(st["y"], small, go, retain_graph=True)
+
+        def eager_fwd():
+            st["ye"] = ops.fullres_norm(ops.bilinear_resize(small, (hw, hw)), label, size)
+
+        def eager_bwd():
+            st["ge"] = torch.autograd.grad(st["ye"], small, go, retain_graph=True)
+
+        lf, lb = timed(lazy_fwd, iters, flush), timed(lazy_bwd, iters, flush)
+        ef, eb = timed(eager_fwd, iters, flush), timed(eager_bwd, iters, flush)
+        rows.append({"kernel": "x8 enlargement + fullres_norm: materialised vs lazy", "N": n, "H": hw, "out": [oh, ow],
+                     "materialised_fwd_ms": ef, "materialised_bwd_ms": eb, "lazy_fwd_ms": lf, "lazy_bwd_ms": lb,
+                     "speedup_fwd_bwd": (ef + eb) / (lf + lb)})
+        print(json.dumps(rows[-1]), flush=True)
+        del small, go, st
+        torch.cuda.empty_cache()
 
 
 def main():
