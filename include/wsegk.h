@@ -215,6 +215,12 @@ int wsegk_contrast_loss_fwd_bwd(const float* x1, const float* x2, const float* p
                                 int32_t* mined1, int32_t* mined2, const float* grad_scale, int N, int C, int D,
                                 int h, int w, void* workspace, size_t workspace_bytes, wsegk_stream_t stream);
 
+/* Mining keys generated on the device (stands in for the random.sample draws of contrast_train.py:316,370):
+ * keys[i] = Philox4x32-10(counter = (index0 + i, step, stream_id), key = seed)[0].  Counter-based: no state, no host work,
+ * and the same key for a pixel however the batch is sharded (index0 = the shard's first global pixel). */
+int wsegk_mining_keys(uint32_t* keys, int count, unsigned long long index0, unsigned long long seed,
+                      unsigned long long step, unsigned int stream_id, wsegk_stream_t stream);
+
 /* Diagnostics for bench.py / tests (not part of the reference-facing surface).
  *   launch_count  : kernels this library has enqueued in this process so far.
  *   pcm_profile   : when enabled (per host thread), pcm_fwd / pcm_bwd record CUDA events on `stream` around their

@@ -572,6 +572,19 @@ def test_er_ecr_losses_vs_oracle(cuda_dev, n, hw1, hw2):
         assert rel_max(mine_t.grad, ref_t.grad) <= 1e-5, name
 
 
+def test_device_mining_keys_are_philox(cuda_dev):
+    """wsegk_mining_keys == Philox4x32-10 of (global pixel, step, stream) under the seed, and is sharding-invariant."""
+    seed, step = 0x123456789ABCDEF, 7
+    keys = ops.mining_keys(300, seed, cuda_dev, step=step, stream_id=2, index0=1000).cpu().numpy().view(np.uint32)
+    for i in (0, 1, 17, 299):
+        want = ops.philox4x32_10([1000 + i, step, 0, 2], [seed & 0xFFFFFFFF, seed >> 32])[0]
+        assert int(keys[i]) == want
+    whole = ops.mining_keys(64, 5, cuda_dev)
+    halves = torch.cat([ops.mining_keys(32, 5, cuda_dev), ops.mining_keys(32, 5, cuda_dev, index0=32)])
+    assert torch.equal(whole, halves)
+    assert len(set(whole.tolist())) == 64
+
+
 def test_pcm_inference_path(cuda_dev):
     """contrast_infer.py runs Net.forward under torch.no_grad(): ops.pcm then takes the forward-only kernel."""
     d = synth.pcm_inputs(2, 44, 60, seed=17)                     # an MSF-like non-square grid

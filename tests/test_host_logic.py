@@ -75,3 +75,11 @@ def test_union_of_local_topk_contains_global_topk():
     order = np.lexsort((ci.numpy(), -cv.numpy()), axis=1)[:, :k]
     sel_i = np.take_along_axis(ci.numpy(), order, 1)
     assert np.array_equal(sel_i, gi.numpy())
+
+
+def test_philox_known_answers():
+    """The Random123 known-answer vectors of Philox4x32-10, for the host reference the GPU keys are checked against."""
+    assert ops.philox4x32_10([0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert ops.philox4x32_10([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert ops.philox4x32_10([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]

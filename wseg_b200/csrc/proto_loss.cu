@@ -1183,6 +1183,47 @@ size_t contrast_workspace_bytes(int N, int C, int, int h, int w) { return nce_la
 
 using namespace wsegk;
 
+// ---- mining keys on the device -------------------------------------------------------------------
+// The "random half" of the hard-pixel mining (contrast_train.py:316,370 draw it with Python's random.sample) only needs one
+// uniform 32-bit key per pixel and step; Philox4x32-10 (Salmon et al., SC'11; the Random123 known-answer vectors are checked
+// in tests/test_host_logic.py) is counter-based, so key i of stream `stream_id` at `step` is a pure function
+//   philox(counter = (i, step_lo, step_hi, stream_id), key = (seed_lo, seed_hi))[0]
+// — no generator state, nothing on the host, identical for any sharding of the pixels over ranks (pass the global index).
+namespace wsegk {
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+__global__ void __launch_bounds__(256) mining_keys_kernel(uint32_t* __restrict__ out, int count, unsigned long long index0,
+                                                          unsigned long long seed, unsigned long long step,
+                                                          uint32_t stream_id) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const unsigned long long gi = index0 + static_cast<unsigned long long>(i);
+    // the pixel index takes counter word 0 (and spills into the top half of word 3 beyond 2^32 pixels)
+    const uint4 c = make_uint4(static_cast<uint32_t>(gi), static_cast<uint32_t>(step), static_cast<uint32_t>(step >> 32),
+                               stream_id ^ (static_cast<uint32_t>(gi >> 32) << 16));
+    out[i] = philox4x32_10(c, make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32))).x;
+}
+}  // namespace wsegk
+
+extern "C" int wsegk_mining_keys(uint32_t* keys, int count, unsigned long long index0, unsigned long long seed,
+                                 unsigned long long step, unsigned int stream_id, wsegk_stream_t stream) {
+    if (int rc = check_device()) return rc;
+    WSEGK_REQUIRE(keys != nullptr && count > 0, WSEGK_ERR_BAD_SHAPE, "mining_keys: need a buffer and count > 0");
+    mining_keys_kernel<<<ceil_div(count, 256), 256, 0, stream>>>(keys, count, index0, seed, step, stream_id);
+    count_launches(1);
+    WSEGK_CUDA_OK(cudaGetLastError());
+    return WSEGK_OK;
+}
+
 // tests: take the large-plane (multi-CTA select) paths of K3 and K4 whatever the size (wsegk_debug_force_radix)
 static int g_force_radix = 0;
 extern "C" int wsegk_debug_force_radix(int on) {

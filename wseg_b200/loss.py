@@ -53,7 +53,7 @@ def contrast_terms(f_proj1: torch.Tensor, cam_rv1_down: torch.Tensor, f_proj2: t
                    mining_seed: int = 0, group=None, want_mined: bool = False,
                    keys: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
     """contrast_train.py:176-392.  ``label``: [N,21] (or [N,21,1,1]) with background = 1.
-    ``rng``: None -> hash mining keys (no host sync); an int / ``random.Random`` -> reproduce the reference's
+    ``rng``: None -> Philox mining keys generated on the device (no host work, no sync; ``mining_seed`` = seed); an int / ``random.Random`` -> reproduce the reference's
     Python-RNG draws.  ``keys``: two int32 [P] device tensors to use as mining keys instead (nothing is created on the host,
     so the call can be captured in a CUDA graph).  ``group``: process group over which prototypes are whole-batch (data parallel)."""
     if grid is None:
@@ -72,8 +72,14 @@ def contrast_terms(f_proj1: torch.Tensor, cam_rv1_down: torch.Tensor, f_proj2: t
         key1, key2 = keys
     elif rng is None:
         p = pl1.numel()
-        key1 = ops.hash_keys(p, 2 * mining_seed + 1, pl1.device)
-        key2 = ops.hash_keys(p, 2 * mining_seed + 2, pl1.device)
+        if pl1.is_cuda:         # generated on the device: no host RNG, no copy, no sync
+            from . import dist as _dist
+            index0 = _dist.rank_world(group)[0] * p
+            key1 = ops.mining_keys(p, mining_seed, pl1.device, stream_id=1, index0=index0)
+            key2 = ops.mining_keys(p, mining_seed, pl1.device, stream_id=2, index0=index0)
+        else:
+            key1 = ops.hash_keys(p, 2 * mining_seed + 1, pl1.device)
+            key2 = ops.hash_keys(p, 2 * mining_seed + 2, pl1.device)
     else:
         key1, key2 = reference_rng_keys(pl1, pl2, rng, proto1.shape[0])
     out: Dict[str, torch.Tensor] = {}

@@ -428,6 +428,28 @@ def hash_keys(n_pixels: int, seed: int, device) -> torch.Tensor:
     return keys.to(device)
 
 
+def mining_keys(n_pixels: int, seed: int, device, step: int = 0, stream_id: int = 0, index0: int = 0) -> torch.Tensor:
+    """Per-pixel uint32 mining keys generated ON the device (Philox4x32-10, counter = (index0 + i, step, stream_id),
+    key = seed), stored as int32 bit patterns.  Nothing is created on the host; ``index0`` = first global pixel of this
+    rank's shard, so a pixel gets the same key under any data-parallel sharding."""
+    out = torch.empty(int(n_pixels), dtype=torch.int32, device=device)
+    with torch.cuda.device(out.device):
+        check(_lib.lib().wsegk_mining_keys(_ptr(out), int(n_pixels), int(index0), int(seed) & (2 ** 64 - 1), int(step),
+                                           int(stream_id) & 0xFFFF, _stream(out)), "wsegk_mining_keys")
+    return out
+
+
+def philox4x32_10(counter, key):
+    """Host reference of the generator (Salmon et al., SC'11) for tests: 4 x uint32 counter, 2 x uint32 key -> 4 x uint32."""
+    m0, m1, w0, w1, mask = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85, 0xFFFFFFFF
+    c, k = [int(x) & mask for x in counter], [int(x) & mask for x in key]
+    for _ in range(10):
+        p0, p1 = m0 * c[0], m1 * c[2]
+        c = [(p1 >> 32) ^ c[1] ^ k[0], p1 & mask, (p0 >> 32) ^ c[3] ^ k[1], p0 & mask]
+        k = [(k[0] + w0) & mask, (k[1] + w1) & mask]
+    return c
+
+
 def contrast_loss_raw(x1, x2, proto1, proto2, pl1, pl2, key1, key2, grad_scale: Optional[torch.Tensor] = None,
                       want_mined: bool = False):
     """One call of wsegk_contrast_loss_fwd_bwd.  Returns (losses [10], grad_x1, grad_x2, mined1, mined2)."""
