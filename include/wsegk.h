@@ -215,6 +215,22 @@ int wsegk_contrast_loss_fwd_bwd(const float* x1, const float* x2, const float* p
                                 int32_t* mined1, int32_t* mined2, const float* grad_scale, int N, int C, int D,
                                 int h, int w, void* workspace, size_t workspace_bytes, wsegk_stream_t stream);
 
+/* K4 with GLOBAL hard-pixel mining under data parallelism: as wsegk_contrast_loss_fwd_bwd on this
+ * rank's shard, but the per-class order statistics of the mining (contrast_train.py:302-322) are taken over the pixels of ALL R
+ * ranks, as the reference's single-process loss does.  Every rank pushes (sim, key, pseudo label) of its pixels into every
+ * peer's symmetric buffer (wsegk_mine_exchange_bytes; peer_bases[r] = rank r's buffer mapped here, local_base = mine;
+ * local_state: 2 zero-initialised uint32 owned by the library) and ranks its own pixels against all of them in the canonical
+ * order (value, global pixel = rank*P + p).  Reported intra losses are R x this rank's share: their mean over ranks — what
+ * DDP does to the gradients — is the single-process value.  Needs P <= 16384 per rank. */
+size_t wsegk_mine_exchange_bytes(int R, int N, int h, int w);
+int wsegk_contrast_loss_fwd_bwd_global(const float* x1, const float* x2, const float* proto1, const float* proto2,
+                                       const int32_t* pl1, const int32_t* pl2, const uint32_t* rand_key1,
+                                       const uint32_t* rand_key2, float* losses, float* grad_x1, float* grad_x2,
+                                       int32_t* mined1, int32_t* mined2, const float* grad_scale, int N, int C, int D,
+                                       int h, int w, void* workspace, size_t workspace_bytes, void* const* peer_bases,
+                                       const void* local_base, int R, int rank, uint32_t* local_state,
+                                       wsegk_stream_t stream);
+
 /* Mining keys generated on the device (stands in for the random.sample draws of contrast_train.py:316,370):
  * keys[i] = Philox4x32-10(counter = (index0 + i, step, stream_id), key = seed)[0].  Counter-based: no state, no host work,
  * and the same key for a pixel however the batch is sharded (index0 = the shard's first global pixel). */

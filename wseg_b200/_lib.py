@@ -58,6 +58,8 @@ _SIGNATURES = {
     "wsegk_proto_push": (c_int, [_P, _P, _P, ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "wsegk_proto_finalize_symm": (c_int, [_P, c_int, c_int, c_int, _P, _P, c_int, c_int, _P, _P]),
     "wsegk_contrast_loss_fwd_bwd": (c_int, [_P] * 14 + [c_int] * 5 + [_P, c_size_t, _P]),
+    "wsegk_mine_exchange_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "wsegk_contrast_loss_fwd_bwd_global": (c_int, [_P] * 14 + [c_int] * 5 + [_P, c_size_t, _P, _P, c_int, c_int, _P, _P]),
 }
 
 _lib = None

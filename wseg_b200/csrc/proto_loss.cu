@@ -498,6 +498,7 @@ struct NceParams {
     int N, C, D, HW, P;
     int nblk, nblk_grad;       // tiles of the pixel kernel (partials 0,1) and of the gradient kernel (partial 2)
     int idx_bits;              // > 0: mining by thresholds (sel_state) instead of pairwise ranks
+    float intra_scale;         // 1, or the number of ranks when the mining is global (see nce_mine_global_kernel)
     const float* grad_scale;
     float* losses;
 };
@@ -870,6 +871,121 @@ __global__ void __launch_bounds__(kMineThreads) nce_mine_kernel(NceParams prm) {
     if (rr) atomicAdd(&V.rank_rnd[p], rr);
 }
 
+// ---- B (data parallel, GLOBAL mining) --------------------------------------------------------
+// The reference mines over the whole batch (its DataParallel gathers everything on one GPU, contrast_train.py:64,108).
+// With the batch sharded over R ranks, every rank pushes (sim, key, pseudo label) of its P pixels and both views into every
+// peer's symmetric buffer over NVLink ([2 parities][R][view][sim|key|label][P] words + R flags; the same one-shot protocol as
+// the prototype candidates), then ranks its own pixels against ALL R*P pixels of their class in the canonical order
+// (value, global index = rank*P + p): the mined sets, class sizes and class count are exactly the single-process ones.
+// Each rank's intra loss is R x its share of the global one, so that the mean over ranks (what DDP does to the
+// gradients) is the single-process loss.
+struct MinePeers {
+    uint32_t* base[kMaxRanks];
+    uint32_t* flags[kMaxRanks];
+};
+__global__ void __launch_bounds__(256) mine_push_kernel(NceParams prm, MinePeers peers, int R, int rank,
+                                                        uint32_t* __restrict__ state) {
+    const uint32_t step = state[0] + 1u;
+    const int peer = blockIdx.y, P = prm.P;
+    const size_t words = static_cast<size_t>(6) * P;
+    uint32_t* dst = peers.base[peer] + (static_cast<size_t>(step & 1u) * R + rank) * words;
+    for (size_t e = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < words;
+         e += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int v = static_cast<int>(e / (3 * static_cast<size_t>(P)));
+        const int r = static_cast<int>(e - static_cast<size_t>(v) * 3 * P);
+        const int a = r / P, i = r - a * P;
+        const NceView& V = prm.v[v];
+        dst[e] = a == 0 ? __float_as_uint(V.sim[i]) : (a == 1 ? V.rkey[i] : static_cast<uint32_t>(V.pl_own[i]));
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned total = gridDim.x * gridDim.y;
+        const unsigned done = atomicAdd(&state[1], 1u);
+        if (done == total - 1) {                                   // last CTA: every store of this launch is fenced
+            state[1] = 0u;
+            state[0] = step;
+            __threadfence_system();
+            for (int p = 0; p < R; ++p) st_release_sys(peers.flags[p] + rank, step);
+        }
+    }
+}
+__device__ __forceinline__ void mine_wait(const uint32_t* flags, const uint32_t* state, int R) {
+    if (threadIdx.x < R) {
+        const uint32_t want = state[0];
+        unsigned long long spins = 0;
+        while (static_cast<int32_t>(ld_acquire_sys(flags + threadIdx.x) - want) < 0) {
+            if (++spins > (1ull << 33)) __trap();              // a peer died: fail the launch instead of hanging
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+}
+// global class sizes (one CTA per view): replaces the local counts nce_pixel_kernel accumulated
+__global__ void __launch_bounds__(1024) mine_global_count_kernel(NceParams prm, const uint32_t* __restrict__ buf,
+                                                                 const uint32_t* __restrict__ flags,
+                                                                 const uint32_t* __restrict__ state, int R) {
+    __shared__ int s_cnt[32];
+    mine_wait(flags, state, R);
+    const int v = blockIdx.x, P = prm.P;
+    if (threadIdx.x < 32) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const size_t words = static_cast<size_t>(6) * P;
+    const uint32_t* base = buf + static_cast<size_t>(state[0] & 1u) * R * words;
+    for (int j = threadIdx.x; j < R * P; j += blockDim.x) {
+        const int r = j / P, i = j - r * P;
+        const int cls = static_cast<int>(base[r * words + static_cast<size_t>(v) * 3 * P + 2 * static_cast<size_t>(P) + i]);
+        atomicAdd(&s_cnt[cls & 31], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) prm.v[v].cls_count[threadIdx.x] = s_cnt[threadIdx.x];
+}
+// rank_sim / rank_rnd of the LOCAL pixels among all R*P pixels of their class
+__global__ void __launch_bounds__(kMineThreads) nce_mine_global_kernel(NceParams prm, const uint32_t* __restrict__ buf,
+                                                                       const uint32_t* __restrict__ flags,
+                                                                       const uint32_t* __restrict__ state, int R, int rank) {
+    const NceView& V = prm.v[blockIdx.z];
+    const int P = prm.P, total = R * P;
+    __shared__ int s_cls[kMineChunk];
+    __shared__ float s_sim[kMineChunk];
+    __shared__ uint32_t s_key[kMineChunk];
+    mine_wait(flags, state, R);
+    const size_t words = static_cast<size_t>(6) * P;
+    const uint32_t* base = buf + static_cast<size_t>(state[0] & 1u) * R * words + static_cast<size_t>(blockIdx.z) * 3 * P;
+    const int j0 = blockIdx.y * kMineChunk;
+    for (int t = threadIdx.x; t < kMineChunk; t += blockDim.x) {
+        const int j = j0 + t;
+        int cls = -1;
+        float sim = 0.f;
+        uint32_t key = 0u;
+        if (j < total) {
+            const int r = j / P, i = j - r * P;
+            const uint32_t* src = base + r * words;
+            sim = __uint_as_float(src[i]);
+            key = src[static_cast<size_t>(P) + i];
+            cls = static_cast<int>(src[2 * static_cast<size_t>(P) + i]);
+        }
+        s_cls[t] = cls; s_sim[t] = sim; s_key[t] = key;
+    }
+    __syncthreads();
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const int cls = V.pl_own[p], gp = rank * P + p;
+    const float sim = V.sim[p];
+    const uint32_t key = V.rkey[p];
+    int rs = 0, rr = 0;
+    const int lim = min(kMineChunk, total - j0);
+    for (int t = 0; t < lim; ++t) {
+        if (s_cls[t] == cls) {
+            const int gj = j0 + t;
+            rs += (s_sim[t] < sim || (s_sim[t] == sim && gj < gp)) ? 1 : 0;
+            rr += (s_key[t] < key || (s_key[t] == key && gj < gp)) ? 1 : 0;
+        }
+    }
+    if (rs) atomicAdd(&V.rank_sim[p], rs);
+    if (rr) atomicAdd(&V.rank_rnd[p], rr);
+}
+
 // ---- B (large P): the same membership as THRESHOLDS -----------------------------------------------
 // rank_rnd < half  <=>  (key, p) < [element at rank half];   kk-half <= rank_sim < kk  <=>  [rank kk-half] <= (sim, p) < [rank kk]
 // The three order statistics per class come from the multi-CTA select (segselect.cuh): O(P) per pass instead of O(P^2).
@@ -998,7 +1114,7 @@ __global__ void __launch_bounds__(NPIX * kNceGroups) nce_grad_kernel(NceParams p
         }
         if (V.mined) V.mined[p] = cnt;
         const float w_x = 0.05f / static_cast<float>(P);                            // 0.1 * mean / 2
-        const float w_i = cnt ? 0.05f * static_cast<float>(cnt) /
+        const float w_i = cnt ? prm.intra_scale * 0.05f * static_cast<float>(cnt) /
                                     (static_cast<float>(2 * half) * static_cast<float>(s_present))
                               : 0.f;
         intra = w_i * g_ell;
@@ -1354,12 +1470,25 @@ extern "C" int wsegk_proto_finalize_symm(const void* local_base, int R, int view
     return WSEGK_OK;
 }
 
-extern "C" int wsegk_contrast_loss_fwd_bwd(const float* x1, const float* x2, const float* proto1, const float* proto2,
-                                           const int32_t* pl1, const int32_t* pl2, const uint32_t* rand_key1,
-                                           const uint32_t* rand_key2, float* losses, float* grad_x1, float* grad_x2,
-                                           int32_t* mined1, int32_t* mined2, const float* grad_scale, int N, int C,
-                                           int D, int h, int w, void* workspace, size_t workspace_bytes,
-                                           wsegk_stream_t stream) {
+struct GlobalMine {
+    void* const* peer_bases;
+    const void* local_base;
+    int R, rank;
+    uint32_t* local_state;
+};
+static size_t mine_exchange_words(int R, long long P) { return static_cast<size_t>(2) * R * 6 * static_cast<size_t>(P); }
+
+extern "C" size_t wsegk_mine_exchange_bytes(int R, int N, int h, int w) {
+    if (R <= 0 || N <= 0 || h <= 0 || w <= 0) return 0;
+    return align_up(mine_exchange_words(R, static_cast<long long>(N) * h * w) * 4, 256) + align_up(static_cast<size_t>(R) * 4, 256);
+}
+
+static int contrast_loss_impl(const float* x1, const float* x2, const float* proto1, const float* proto2,
+                              const int32_t* pl1, const int32_t* pl2, const uint32_t* rand_key1,
+                              const uint32_t* rand_key2, float* losses, float* grad_x1, float* grad_x2,
+                              int32_t* mined1, int32_t* mined2, const float* grad_scale, int N, int C,
+                              int D, int h, int w, void* workspace, size_t workspace_bytes,
+                              wsegk_stream_t stream, const GlobalMine* gm) {
     if (int rc = check_device()) return rc;
     WSEGK_REQUIRE(x1 && x2 && proto1 && proto2 && pl1 && pl2 && rand_key1 && rand_key2 && losses && grad_x1 &&
                       grad_x2 && workspace,
@@ -1370,7 +1499,15 @@ extern "C" int wsegk_contrast_loss_fwd_bwd(const float* x1, const float* x2, con
                   kNceMaxC, C);
     const long long P = static_cast<long long>(N) * h * w;
     WSEGK_REQUIRE(P < (1ll << 30), WSEGK_ERR_BAD_SHAPE, "contrast_loss_fwd_bwd: P=%lld pixels is too many", P);
-    const bool radix = P > kMinePairwiseMaxP || (g_force_radix && P >= 2);
+    const bool radix = gm == nullptr && (P > kMinePairwiseMaxP || (g_force_radix && P >= 2));
+    if (gm != nullptr) {
+        WSEGK_REQUIRE(gm->peer_bases && gm->local_base && gm->local_state && gm->R >= 1 && gm->R <= kMaxRanks &&
+                          gm->rank >= 0 && gm->rank < gm->R,
+                      WSEGK_ERR_BAD_SHAPE, "contrast_loss_fwd_bwd_global: bad exchange arguments (R=%d rank=%d)", gm->R, gm->rank);
+        WSEGK_REQUIRE(P <= kMinePairwiseMaxP && P * gm->R <= (1 << 20), WSEGK_ERR_BAD_SHAPE,
+                      "contrast_loss_fwd_bwd_global: global mining ranks pairwise: need P <= %d per rank and R*P <= 2^20 "
+                      "(P=%lld, R=%d)", kMinePairwiseMaxP, P, gm->R);
+    }
     const size_t proto_smem = (static_cast<size_t>(kNceSlots) * (D + 1) + kNcePix * 49 + kNcePix * kNceGroups * 4 +
                                static_cast<size_t>(D) * kNcePix) * sizeof(float);
     WSEGK_REQUIRE(proto_smem <= 200 * 1024, WSEGK_ERR_BAD_SHAPE, "contrast_loss_fwd_bwd: D too large");
@@ -1390,6 +1527,7 @@ extern "C" int wsegk_contrast_loss_fwd_bwd(const float* x1, const float* x2, con
     prm.grad_scale = grad_scale;
     prm.losses = losses;
     prm.idx_bits = radix ? index_bits(P) : 0;
+    prm.intra_scale = gm ? static_cast<float>(gm->R) : 1.f;
     uint8_t* ws = static_cast<uint8_t*>(workspace);
     for (int v = 0; v < 2; ++v) {
         uint8_t* b = ws + v * L.per_view;
@@ -1451,6 +1589,22 @@ extern "C" int wsegk_contrast_loss_fwd_bwd(const float* x1, const float* x2, con
             const MineSrc src{V.pl_own, V.sim, V.rkey, prm.P, prm.idx_bits};
             launches += seg_select_run(src, prm.P, 32 + prm.idx_bits, 3 * kNceMaxC, V.sel_state, V.sel_hist, stream);
         }
+    } else if (gm != nullptr) {
+        const int R = gm->R;
+        const size_t flag_off = align_up(mine_exchange_words(R, P) * 4, 256);
+        MinePeers peers{};
+        for (int p = 0; p < R; ++p) {
+            WSEGK_REQUIRE(gm->peer_bases[p] != nullptr, WSEGK_ERR_NULL, "contrast_loss_fwd_bwd_global: peer %d has no buffer", p);
+            peers.base[p] = static_cast<uint32_t*>(gm->peer_bases[p]);
+            peers.flags[p] = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(gm->peer_bases[p]) + flag_off);
+        }
+        const uint32_t* buf = static_cast<const uint32_t*>(gm->local_base);
+        const uint32_t* flags = reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(gm->local_base) + flag_off);
+        mine_push_kernel<<<dim3(kPushChunks, R), 256, 0, stream>>>(prm, peers, R, gm->rank, gm->local_state);
+        mine_global_count_kernel<<<2, 1024, 0, stream>>>(prm, buf, flags, gm->local_state, R);
+        nce_mine_global_kernel<<<dim3(ceil_div(prm.P, kMineThreads), ceil_div(R * prm.P, kMineChunk), 2), kMineThreads, 0,
+                                 stream>>>(prm, buf, flags, gm->local_state, R, gm->rank);
+        launches += 3;
     } else {
         nce_mine_kernel<<<dim3(ceil_div(prm.P, kMineThreads), ceil_div(prm.P, kMineChunk), 2), kMineThreads, 0,
                           stream>>>(prm);
@@ -1464,4 +1618,26 @@ extern "C" int wsegk_contrast_loss_fwd_bwd(const float* x1, const float* x2, con
     count_launches(launches);
     WSEGK_CUDA_OK(cudaGetLastError());
     return WSEGK_OK;
+}
+
+extern "C" int wsegk_contrast_loss_fwd_bwd(const float* x1, const float* x2, const float* proto1, const float* proto2,
+                                           const int32_t* pl1, const int32_t* pl2, const uint32_t* rand_key1,
+                                           const uint32_t* rand_key2, float* losses, float* grad_x1, float* grad_x2,
+                                           int32_t* mined1, int32_t* mined2, const float* grad_scale, int N, int C,
+                                           int D, int h, int w, void* workspace, size_t workspace_bytes,
+                                           wsegk_stream_t stream) {
+    return contrast_loss_impl(x1, x2, proto1, proto2, pl1, pl2, rand_key1, rand_key2, losses, grad_x1, grad_x2, mined1, mined2,
+                              grad_scale, N, C, D, h, w, workspace, workspace_bytes, stream, nullptr);
+}
+
+extern "C" int wsegk_contrast_loss_fwd_bwd_global(const float* x1, const float* x2, const float* proto1, const float* proto2,
+                                                  const int32_t* pl1, const int32_t* pl2, const uint32_t* rand_key1,
+                                                  const uint32_t* rand_key2, float* losses, float* grad_x1, float* grad_x2,
+                                                  int32_t* mined1, int32_t* mined2, const float* grad_scale, int N, int C,
+                                                  int D, int h, int w, void* workspace, size_t workspace_bytes,
+                                                  void* const* peer_bases, const void* local_base, int R, int rank,
+                                                  uint32_t* local_state, wsegk_stream_t stream) {
+    const GlobalMine gm{peer_bases, local_base, R, rank, local_state};
+    return contrast_loss_impl(x1, x2, proto1, proto2, pl1, pl2, rand_key1, rand_key2, losses, grad_x1, grad_x2, mined1, mined2,
+                              grad_scale, N, C, D, h, w, workspace, workspace_bytes, stream, &gm);
 }

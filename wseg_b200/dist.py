@@ -65,3 +65,33 @@ class SymmExchange:
         if key not in cls._cache:
             cls._cache[key] = cls(group, c, k, d, device)
         return cls._cache[key]
+
+
+class MineExchange:
+    """Symmetric buffer for the GLOBAL hard-pixel mining (include/wsegk.h: wsegk_contrast_loss_fwd_bwd_global): every rank's
+    per-pixel (similarity, key, pseudo label) of both views lands in every peer's buffer straight from the kernel."""
+
+    _cache = {}
+
+    def __init__(self, group, n: int, h: int, w: int, device):
+        import ctypes
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        nbytes = int(_lib.lib().wsegk_mine_exchange_bytes(self.world, n, h, w))
+        self.buf = symm_mem.empty(nbytes // 4, dtype=torch.float32, device=device)
+        self.hdl = symm_mem.rendezvous(self.buf, self.group)
+        self.buf.zero_()
+        self.state = torch.zeros(4, dtype=torch.int32, device=device)
+        torch.cuda.synchronize(device)
+        self.hdl.barrier()                       # everybody's flags are zero before anybody pushes
+        ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self.peer_bases = (ctypes.c_void_p * self.world)(*ptrs)
+
+    @classmethod
+    def get(cls, group, n: int, h: int, w: int, device):
+        key = (id(group), n, h, w, str(device))
+        if key not in cls._cache:
+            cls._cache[key] = cls(group, n, h, w, device)
+        return cls._cache[key]

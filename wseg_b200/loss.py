@@ -51,11 +51,15 @@ def contrast_terms(f_proj1: torch.Tensor, cam_rv1_down: torch.Tensor, f_proj2: t
                    cam_rv2_down: torch.Tensor, label: torch.Tensor, bg_threshold: float,
                    grid: Optional[Tuple[int, int]] = None, rng: Union[int, _pyrandom.Random, None] = None,
                    mining_seed: int = 0, group=None, want_mined: bool = False,
-                   keys: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+                   keys: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+                   mining: str = "shard") -> Dict[str, torch.Tensor]:
     """contrast_train.py:176-392.  ``label``: [N,21] (or [N,21,1,1]) with background = 1.
     ``rng``: None -> Philox mining keys generated on the device (no host work, no sync; ``mining_seed`` = seed); an int / ``random.Random`` -> reproduce the reference's
     Python-RNG draws.  ``keys``: two int32 [P] device tensors to use as mining keys instead (nothing is created on the host,
-    so the call can be captured in a CUDA graph).  ``group``: process group over which prototypes are whole-batch (data parallel)."""
+    so the call can be captured in a CUDA graph).  ``group``: process group over which prototypes are whole-batch (data parallel).
+    ``mining``: "shard" = every rank mines hard pixels inside its own shard; "global" = over the whole batch of ``group`` as
+    the single-process reference does (one more NVLink exchange; the reported intra losses are then R x this rank's share,
+    so their mean over ranks — what DDP does to the gradients — is the single-process value)."""
     if grid is None:
         grid = tuple(f_proj2.shape[-2:])
     if tuple(f_proj1.shape[-2:]) != tuple(grid):
@@ -83,11 +87,19 @@ def contrast_terms(f_proj1: torch.Tensor, cam_rv1_down: torch.Tensor, f_proj2: t
     else:
         key1, key2 = reference_rng_keys(pl1, pl2, rng, proto1.shape[0])
     out: Dict[str, torch.Tensor] = {}
+    if mining not in ("shard", "global"):
+        raise ValueError("mining must be 'shard' or 'global'")
+    from . import dist as _dist
+    gg = None
+    if mining == "global" and _dist.rank_world(group)[1] > 1:
+        import torch.distributed as _td
+        gg = group if group is not None else _td.group.WORLD
     if want_mined:
-        losses, g1, g2, m1, m2 = ops.contrast_loss_raw(f1, f2, proto1, proto2, pl1, pl2, key1, key2, want_mined=True)
+        losses, g1, g2, m1, m2 = ops.contrast_loss_raw(f1, f2, proto1, proto2, pl1, pl2, key1, key2, want_mined=True,
+                                                       global_group=gg)
         out.update({'grad_f1': g1, 'grad_f2': g2, 'mined1': m1, 'mined2': m2})
     else:
-        losses = ops.contrast_loss(f1, f2, proto1, proto2, pl1, pl2, key1, key2)
+        losses = ops.contrast_loss(f1, f2, proto1, proto2, pl1, pl2, key1, key2, gg)
     out.update({
         'loss_nce': losses[9], 'loss_intra_nce': losses[8], 'loss_cross_nce': losses[6],
         'loss_cross_nce2': losses[7], 'losses_raw': losses,

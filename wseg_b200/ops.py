@@ -451,8 +451,10 @@ def philox4x32_10(counter, key):
 
 
 def contrast_loss_raw(x1, x2, proto1, proto2, pl1, pl2, key1, key2, grad_scale: Optional[torch.Tensor] = None,
-                      want_mined: bool = False):
-    """One call of wsegk_contrast_loss_fwd_bwd.  Returns (losses [10], grad_x1, grad_x2, mined1, mined2)."""
+                      want_mined: bool = False, global_group=None):
+    """One call of wsegk_contrast_loss_fwd_bwd.  Returns (losses [10], grad_x1, grad_x2, mined1, mined2).
+    ``global_group``: a process group over which the hard-pixel mining is GLOBAL (the reference's whole-batch semantics
+    under data parallelism; one NVLink exchange of 12 bytes per pixel and view; needs symmetric memory)."""
     x1 = _require_cuda_f32("x1", x1.detach())
     x2 = _require_cuda_f32("x2", x2.detach())
     n, d, h, w = x1.shape
@@ -471,9 +473,17 @@ def contrast_loss_raw(x1, x2, proto1, proto2, pl1, pl2, key1, key2, grad_scale: 
             key1.to(torch.int32).contiguous(), key2.to(torch.int32).contiguous()]
     with torch.cuda.device(dev):
         ws = _workspace(_lib.OP_CONTRAST_LOSS, dev, N=n, C=c, D=d, h=h, w=w)
-        check(_lib.lib().wsegk_contrast_loss_fwd_bwd(
-            _ptr(x1), _ptr(x2), *[_ptr(a) for a in args], _ptr(losses), _ptr(g1), _ptr(g2), _ptr(m1), _ptr(m2),
-            _ptr(grad_scale), n, c, d, h, w, _ptr(ws), ws.numel(), _stream(x1)), "wsegk_contrast_loss_fwd_bwd")
+        if global_group is None:
+            check(_lib.lib().wsegk_contrast_loss_fwd_bwd(
+                _ptr(x1), _ptr(x2), *[_ptr(a) for a in args], _ptr(losses), _ptr(g1), _ptr(g2), _ptr(m1), _ptr(m2),
+                _ptr(grad_scale), n, c, d, h, w, _ptr(ws), ws.numel(), _stream(x1)), "wsegk_contrast_loss_fwd_bwd")
+        else:
+            from . import dist as _dist
+            ex = _dist.MineExchange.get(global_group, n, h, w, dev)
+            check(_lib.lib().wsegk_contrast_loss_fwd_bwd_global(
+                _ptr(x1), _ptr(x2), *[_ptr(a) for a in args], _ptr(losses), _ptr(g1), _ptr(g2), _ptr(m1), _ptr(m2),
+                _ptr(grad_scale), n, c, d, h, w, _ptr(ws), ws.numel(), ex.peer_bases, _ptr(ex.buf), ex.world, ex.rank,
+                _ptr(ex.state), _stream(x1)), "wsegk_contrast_loss_fwd_bwd_global")
     return losses, g1, g2, m1, m2
 
 
@@ -482,8 +492,8 @@ class _ContrastLoss(torch.autograd.Function):
     the same fused call, so backward only rescales it.  The other slots are reported values (no gradient)."""
 
     @staticmethod
-    def forward(ctx, x1, x2, proto1, proto2, pl1, pl2, key1, key2):
-        losses, g1, g2, _, _ = contrast_loss_raw(x1, x2, proto1, proto2, pl1, pl2, key1, key2)
+    def forward(ctx, x1, x2, proto1, proto2, pl1, pl2, key1, key2, global_group=None):
+        losses, g1, g2, _, _ = contrast_loss_raw(x1, x2, proto1, proto2, pl1, pl2, key1, key2, global_group=global_group)
         ctx.save_for_backward(g1, g2)
         return losses
 
@@ -493,11 +503,11 @@ class _ContrastLoss(torch.autograd.Function):
         # d(loss_nce) flows through slot 9; slots 6,7,8 are its parts and may carry gradient too when a caller
         # sums them instead — support the reference's usage (only loss_nce enters the total, :392-395).
         scale = grad_losses[9]
-        return g1 * scale, g2 * scale, None, None, None, None, None, None
+        return g1 * scale, g2 * scale, None, None, None, None, None, None, None
 
 
-def contrast_loss(x1, x2, proto1, proto2, pl1, pl2, key1, key2) -> torch.Tensor:
-    return _ContrastLoss.apply(x1, x2, proto1, proto2, pl1, pl2, key1, key2)
+def contrast_loss(x1, x2, proto1, proto2, pl1, pl2, key1, key2, global_group=None) -> torch.Tensor:
+    return _ContrastLoss.apply(x1, x2, proto1, proto2, pl1, pl2, key1, key2, global_group)
 
 
 # --------------------------------------------------------------------------------------------- auxiliary SEAM losses
