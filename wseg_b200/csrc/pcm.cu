@@ -44,13 +44,12 @@ __device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
 // (channel groups half, half+2, ...), so global loads are coalesced along the pixel axis, the 16-byte chunks a thread
 // writes are already in tile order (row = pixel), and no shared-memory transpose is needed.
 template <bool kLo>
-__global__ void __launch_bounds__(256) pcm_prep_f_kernel(const float* __restrict__ f, uint4* __restrict__ fa_hi,
-                                                         uint4* __restrict__ fa_lo, uint4* __restrict__ fb_hi,
-                                                         uint4* __restrict__ fb_lo, float* __restrict__ inv_norm,
-                                                         int K, int HW, int PJ, int NS, int wb) {
+__device__ __forceinline__ void pcm_prep_f_body(const float* __restrict__ f, uint4* __restrict__ fa_hi,
+                                                uint4* __restrict__ fa_lo, uint4* __restrict__ fb_hi,
+                                                uint4* __restrict__ fb_lo, float* __restrict__ inv_norm,
+                                                int K, int HW, int PJ, int NS, int wb, int t, int n) {
     constexpr int GMAX = kMaxPcmK / 16;          // channel groups per thread
     __shared__ float s_part[2][kTile];
-    const int t = blockIdx.x, n = blockIdx.y;
     const int px = threadIdx.x & 127, half = threadIdx.x >> 7;
     const int p = t * kTile + px;
     const int HWpj = PJ * 2 * kTile, HWpi = NS * 2 * wb;
@@ -104,10 +103,9 @@ __global__ void __launch_bounds__(256) pcm_prep_f_kernel(const float* __restrict
 
 // cam_norm [N,C,HW] fp32 -> per (image, stage) two operand blocks of [32 rows x 2wb pixels] fp16, K-major (K = pixel):
 //   rank 0 block: rows 0..C-1 = fp16(cam), row C = 1 (column-sum row), others 0;   rank 1 block: rows 0..C-1 = cam - hi.
-__global__ void __launch_bounds__(128) pcm_prep_cam_kernel(const float* __restrict__ cam, uint4* __restrict__ camb,
-                                                           int C, int HW, int NS, int wb) {
+__device__ __forceinline__ void pcm_prep_cam_body(const float* __restrict__ cam, uint4* __restrict__ camb,
+                                                  int C, int HW, int NS, int wb, int s, int n) {
     __shared__ __align__(16) uint16_t s_blk[2 * 16 * kCamRows * 8];   // [rank][pixel group g][row][8]
-    const int s = blockIdx.x, n = blockIdx.y;
     const int q = threadIdx.x;
     const int ncol = 2 * wb;
     const int p = s * ncol + q;
@@ -140,6 +138,20 @@ __global__ void __launch_bounds__(128) pcm_prep_cam_kernel(const float* __restri
     uint4* dst = camb + (static_cast<size_t>(n) * NS + s) * chunks;
     const uint4* s4 = reinterpret_cast<const uint4*>(s_blk);
     for (int i = threadIdx.x; i < chunks; i += blockDim.x) dst[i] = s4[i];
+}
+
+// both operand preparations in ONE launch (they are independent; as two launches the 7 us cam preparation sat on the
+// critical path behind the feature preparation): blocks [0, tiles) prepare features, blocks [tiles, tiles + NS) cam blocks
+template <bool kLo>
+__global__ void __launch_bounds__(256) pcm_prep_kernel(const float* __restrict__ f, uint4* __restrict__ fa_hi,
+                                                       uint4* __restrict__ fa_lo, uint4* __restrict__ fb_hi,
+                                                       uint4* __restrict__ fb_lo, float* __restrict__ inv_norm,
+                                                       const float* __restrict__ cam, uint4* __restrict__ camb, int C,
+                                                       int K, int HW, int PJ, int NS, int wb, int tiles) {
+    if (static_cast<int>(blockIdx.x) < tiles)
+        pcm_prep_f_body<kLo>(f, fa_hi, fa_lo, fb_hi, fb_lo, inv_norm, K, HW, PJ, NS, wb, blockIdx.x, blockIdx.y);
+    else
+        pcm_prep_cam_body(cam, camb, C, HW, NS, wb, static_cast<int>(blockIdx.x) - tiles, blockIdx.y);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1068,22 +1080,21 @@ static int pcm_fwd_impl(const float* f, const float* cam_norm, float* cam_rv, in
         const int tiles = ceil_div(std::max(pl.HWpj, pl.HWpi), kTile);
         uint4 *a_hi = reinterpret_cast<uint4*>(pl.fa_hi), *a_lo = reinterpret_cast<uint4*>(pl.fa_lo);
         uint4 *b_hi = reinterpret_cast<uint4*>(pl.fb_hi), *b_lo = reinterpret_cast<uint4*>(pl.fb_lo);
-        if (precise) {
-            pcm_prep_f_kernel<true><<<dim3(tiles, N), 256, smem, stream>>>(f, a_hi, a_lo, b_hi, b_lo, pl.inv_norm, K,
-                                                                            pl.HW, pl.PJ, pl.NS, pl.wb);
-        } else {
-            pcm_prep_f_kernel<false><<<dim3(tiles, N), 256, smem, stream>>>(f, a_hi, a_lo, b_hi, b_lo, pl.inv_norm, K,
-                                                                             pl.HW, pl.PJ, pl.NS, pl.wb);
-        }
-        pcm_prep_cam_kernel<<<dim3(pl.NS, N), 128, 0, stream>>>(cam_norm, reinterpret_cast<uint4*>(pl.camb), C, pl.HW,
-                                                                pl.NS, pl.wb);
+        uint4* cb = reinterpret_cast<uint4*>(pl.camb);
+        (void)smem;
+        if (precise)
+            pcm_prep_kernel<true><<<dim3(tiles + pl.NS, N), 256, 0, stream>>>(f, a_hi, a_lo, b_hi, b_lo, pl.inv_norm, cam_norm,
+                                                                             cb, C, K, pl.HW, pl.PJ, pl.NS, pl.wb, tiles);
+        else
+            pcm_prep_kernel<false><<<dim3(tiles + pl.NS, N), 256, 0, stream>>>(f, a_hi, a_lo, b_hi, b_lo, pl.inv_norm, cam_norm,
+                                                                              cb, C, K, pl.HW, pl.PJ, pl.NS, pl.wb, tiles);
     }
     prof_mark(0, stream);
     WSEGK_DISPATCH_WB(launch_fwd, precise, pl, N, stream);
     prof_mark(1, stream);
     pcm_fwd_finalize_kernel<<<dim3(pl.HWpj / 32, N), 256, 0, stream>>>(pl.part, cam_rv, pl.dsum, C, pl.HW, pl.HWpj,
                                                                          pl.nsplit, pl.PJ, pl.NS, pl.G);
-    count_launches(4);
+    count_launches(3);
     WSEGK_CUDA_OK(cudaGetLastError());
     return WSEGK_OK;
 }
