@@ -248,6 +248,9 @@ int wsegk_debug_pcm_main_ms(float* fwd_ms, float* bwd_ms);
 /* Timeline aid: when non-null (per host thread), CTA (0,0,0) of the next pcm_fwd main kernels writes clock64() stamps
  * into this DEVICE buffer of 768 int64: [role 0 producer | 1 MMA issuer | 2 first TMEM warp][stage < 64][4 events]. */
 int wsegk_debug_pcm_trace(long long* device_buffer);
+/* Test aid (host only, no GPU needed): the (unit, stage, segment, partial slot) quadruples CTA pair g of the persistent PCM
+ * kernels runs for N images on an h x w grid; returns their number (0 for g beyond the grid). */
+int wsegk_debug_pcm_schedule(int N, int h, int w, int g, int* out, int capacity);
 /* Test aid, process-wide: when on, wsegk_proto_topk_local and wsegk_contrast_loss_fwd_bwd take their large-plane paths
  * (multi-CTA radix select, csrc/segselect.cuh) whatever the size, so both paths can be compared on the same inputs.
  * By default K3 switches above 8192 pixels and the mining of K4 above 16384. */

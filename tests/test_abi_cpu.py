@@ -49,6 +49,43 @@ def test_version_and_workspace_sizes(lib):
     assert "unknown op" in _lib.last_error()
 
 
+@pytest.mark.parametrize("n,h,w", [(8, 56, 56), (1, 16, 16), (2, 20, 13), (16, 56, 56), (3, 9, 5), (128, 32, 32), (5, 96, 96),
+                                   (1, 108, 108)])
+def test_pcm_schedule_covers_every_stage_once(lib, n, h, w):
+    """The persistent PCM kernels' schedule (rows + stream-K tail, csrc/common.cuh) as a host-side property: every stage
+    of every (image, j pair) unit is run by exactly one CTA pair, the pairs' loads differ by at most one stage, a pair's
+    segments are runs of consecutive stages of one unit, and the (unit, slot) pairs are distinct with slots below the
+    number of partial slots the workspace holds."""
+    lay = ops.pcm_layout(n, 21, 192, h, w)
+    units, ns, slots = n * lay["PJ"], lay["NS"], lay["nsplit"]
+    seen, loads, used = {}, [], set()
+    for g in range(80):
+        cap = units * ns
+        buf = (ctypes.c_int * (4 * cap))()
+        cnt = lib.wsegk_debug_pcm_schedule(n, h, w, g, buf, cap)
+        assert cnt >= 0
+        if cnt == 0:
+            continue
+        loads.append(cnt)
+        prev = None
+        for i in range(cnt):
+            u, st, k, slot = buf[4 * i], buf[4 * i + 1], buf[4 * i + 2], buf[4 * i + 3]
+            assert 0 <= u < units and 0 <= st < ns and 0 <= slot < slots
+            assert (u, st) not in seen, "stage run twice"
+            seen[(u, st)] = g
+            if prev is not None and prev[2] == k:
+                assert prev[0] == u and prev[1] + 1 == st and prev[3] == slot      # a segment: consecutive stages of a unit
+            elif prev is not None:
+                assert k == prev[2] + 1
+            if prev is None or prev[2] != k:
+                assert (u, slot) not in used, "two segments write the same partial slot"
+                used.add((u, slot))
+            prev = (u, st, k, slot)
+    assert len(seen) == units * ns
+    assert max(loads) - min(loads) <= 1 or len(loads) < 74
+    assert sum(loads) == units * ns
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU refusal path")
 def test_compute_refuses_without_gpu(lib):
     buf = (ctypes.c_float * 64)()

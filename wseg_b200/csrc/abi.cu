@@ -180,3 +180,24 @@ extern "C" int wsegk_debug_pcm_layout(int N, int C, int K, int h, int w, size_t*
     for (; k < n_out && k < 20; ++k) out[k] = v[k];
     return k;
 }
+
+// Test aid (host only): the stages CTA pair g runs under the schedule of the PCM main kernels for N images on an h x w grid,
+// as (unit, stage, segment ordinal, partial slot) quadruples; returns how many, or a negative status.
+extern "C" int wsegk_debug_pcm_schedule(int N, int h, int w, int g, int* out, int capacity) {
+    if (N <= 0 || h <= 0 || w <= 0 || g < 0) return WSEGK_ERR_BAD_SHAPE;
+    const PcmPlan pl = make_pcm_plan(nullptr, N, 1, 32, h, w, 1);
+    if (g >= pl.G) return 0;
+    const PcmSched sc = pcm_sched(N * pl.PJ, pl.NS, pl.G);
+    StageCursor c(sc, g, pl.PJ);
+    const int cnt = c.cnt;
+    for (int i = 0; i < cnt; ++i, c.next()) {
+        if (out != nullptr && i < capacity) {
+            const int slot = c.in_tail() ? g - pcm_tail_owner(sc, static_cast<long long>(c.u - sc.Rf * sc.G) * sc.NS) : 0;
+            out[4 * i + 0] = c.u;
+            out[4 * i + 1] = c.st;
+            out[4 * i + 2] = c.k;
+            out[4 * i + 3] = slot;
+        }
+    }
+    return cnt;
+}

@@ -136,6 +136,43 @@ __host__ __device__ __forceinline__ int pcm_unit_segments(const PcmSched& s, int
     return pcm_tail_owner(s, t0 + s.NS - 1) - pcm_tail_owner(s, t0) + 1;
 }
 
+// Walks the stages of a CTA pair's schedule (common.cuh) without per-stage divisions: the MMA-issuing warp has only
+// ~500 spare cycles per stage.
+struct StageCursor {
+    int n, jp, st, k;          // image, j pair, stage inside the unit, segment ordinal inside this CTA pair's schedule
+    int i, cnt;                // running stage index, stages in the schedule
+    int u, rows_left, tail_u, tail_st, tail_i, G, NS, PJ;
+    __host__ __device__ __forceinline__ void set_unit(int unit) {
+        u = unit;
+        n = unit / PJ;
+        jp = unit - n * PJ;
+    }
+    __host__ __device__ __forceinline__ StageCursor(const PcmSched& sc, int g, int PJ_) : k(0), i(0), G(sc.G), NS(sc.NS), PJ(PJ_) {
+        const long long lo = g < sc.Gt ? pcm_tail_lo(sc, g) : 0, hi = g < sc.Gt ? pcm_tail_lo(sc, g + 1) : 0;
+        rows_left = sc.Rf;
+        tail_i = sc.Rf * sc.NS;                                      // index of the first tail stage
+        cnt = tail_i + static_cast<int>(hi - lo);
+        const int w = static_cast<int>(lo / sc.NS);
+        tail_u = sc.Rf * sc.G + w;
+        tail_st = static_cast<int>(lo - static_cast<long long>(w) * sc.NS);
+        if (rows_left > 0) { set_unit(g); st = 0; }
+        else { set_unit(tail_u < sc.U ? tail_u : 0); st = tail_st; }
+    }
+    __host__ __device__ __forceinline__ bool first() const { return i == 0 || st == 0 || i == tail_i; }   // first stage of its segment
+    __host__ __device__ __forceinline__ bool last() const { return i + 1 == cnt || st == NS - 1; }         // last stage of its segment
+    __host__ __device__ __forceinline__ bool in_tail() const { return i >= tail_i; }
+    __host__ __device__ __forceinline__ void next() {
+        ++i;
+        if (i >= cnt) return;
+        if (++st == NS || i == tail_i) {
+            ++k;
+            if (i == tail_i) { set_unit(tail_u); st = tail_st; }     // rows done: jump to this pair's tail range
+            else if (i < tail_i) { st = 0; set_unit(u + G); }        // next row
+            else { st = 0; set_unit(u + 1); }                        // next tail unit
+        }
+    }
+};
+
 PcmPlan make_pcm_plan(void* ws, int N, int C, int K, int h, int w, int precise);
 int pcm_mode();     // current process-wide mode (wsegk_pcm_set_mode): 1 precise (default), 0 fast
 

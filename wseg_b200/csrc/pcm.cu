@@ -195,43 +195,6 @@ __device__ __forceinline__ uint32_t relu_pack_bits(const uint32_t* r, uint32_t* 
 // contiguous ranges, one per CTA pair, so every pair does the same number of stages whatever N, PJ and NS are (no wave
 // quantisation) and pays ONE prologue/drain.  A range crosses unit boundaries: each (pair, unit) piece is a "segment"
 // with its own A-side tile and its own partial-result slot  slot = pair - (pair owning the unit's first stage).
-// Walks the stages of a CTA pair's schedule (common.cuh) without per-stage divisions: the MMA-issuing warp has only
-// ~500 spare cycles per stage.
-struct StageCursor {
-    int n, jp, st, k;          // image, j pair, stage inside the unit, segment ordinal inside this CTA pair's schedule
-    int i, cnt;                // running stage index, stages in the schedule
-    int u, rows_left, tail_u, tail_st, tail_i, G, NS, PJ;
-    __device__ __forceinline__ void set_unit(int unit) {
-        u = unit;
-        n = unit / PJ;
-        jp = unit - n * PJ;
-    }
-    __device__ __forceinline__ StageCursor(const PcmSched& sc, int g, int PJ_) : k(0), i(0), G(sc.G), NS(sc.NS), PJ(PJ_) {
-        const long long lo = g < sc.Gt ? pcm_tail_lo(sc, g) : 0, hi = g < sc.Gt ? pcm_tail_lo(sc, g + 1) : 0;
-        rows_left = sc.Rf;
-        tail_i = sc.Rf * sc.NS;                                      // index of the first tail stage
-        cnt = tail_i + static_cast<int>(hi - lo);
-        const int w = static_cast<int>(lo / sc.NS);
-        tail_u = sc.Rf * sc.G + w;
-        tail_st = static_cast<int>(lo - static_cast<long long>(w) * sc.NS);
-        if (rows_left > 0) { set_unit(g); st = 0; }
-        else { set_unit(tail_u < sc.U ? tail_u : 0); st = tail_st; }
-    }
-    __device__ __forceinline__ bool first() const { return i == 0 || st == 0 || i == tail_i; }   // first stage of its segment
-    __device__ __forceinline__ bool last() const { return i + 1 == cnt || st == NS - 1; }         // last stage of its segment
-    __device__ __forceinline__ bool in_tail() const { return i >= tail_i; }
-    __device__ __forceinline__ void next() {
-        ++i;
-        if (i >= cnt) return;
-        if (++st == NS || i == tail_i) {
-            ++k;
-            if (i == tail_i) { set_unit(tail_u); st = tail_st; }     // rows done: jump to this pair's tail range
-            else if (i < tail_i) { st = 0; set_unit(u + G); }        // next row
-            else { st = 0; set_unit(u + 1); }                        // next tail unit
-        }
-    }
-};
-
 template <int WB, bool PRECISE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMainThreads, 1)
 pcm_fwd_kernel(const uint8_t* __restrict__ fa_hi, const uint8_t* __restrict__ fa_lo,
