@@ -861,39 +861,29 @@ __global__ void __launch_bounds__(256) pcm_bwd_post_kernel(const float* __restri
     const float* fsrc = f + static_cast<size_t>(n) * K * HW + p;
     const int per = K / kPostPhases;                      // channels per phase (K % 32 == 0 => per % 4 == 0)
     const int k0 = ph * per;
-    // this thread's channels stay in registers between the dot-product pass and the write pass (K <= 192: per <= 24)
-    constexpr int kMaxPer = kMaxPcmK / kPostPhases;
-    float gv[kMaxPer], fv[kMaxPer];
     float dot = 0.f;
     if (live) {
+        for (int kk = 0; kk < per; kk += 4) {
+            float g[4] = {0.f, 0.f, 0.f, 0.f}, fv[4];
 #pragma unroll
-        for (int kk = 0; kk < kMaxPer; kk += 4) {
-            if (kk < per) {
-                float g[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) fv[kk + j] = __ldg(fsrc + static_cast<size_t>(k0 + kk + j) * HW);
-                if (nsplit == 2) {                             // the common case: all 12 loads of the batch independent
-                    float g2[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        g[j] = __ldg(gsrc + static_cast<size_t>(k0 + kk + j) * HWpj);
-                        g2[j] = __ldg(gsrc + split_stride + static_cast<size_t>(k0 + kk + j) * HWpj);
-                    }
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) g[j] += g2[j];
-                } else {
-                    for (int sp = 0; sp < nsplit; ++sp) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            g[j] += __ldg(gsrc + sp * split_stride + static_cast<size_t>(k0 + kk + j) * HWpj);
-                    }
-                }
+            for (int j = 0; j < 4; ++j) fv[j] = __ldg(fsrc + static_cast<size_t>(k0 + kk + j) * HW);
+            if (nsplit == 2) {                             // the common case: all 12 loads of the batch independent
+                float g2[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    gv[kk + j] = g[j] * unscale;
-                    dot = fmaf(gv[kk + j], fv[kk + j], dot);
+                    g[j] = __ldg(gsrc + static_cast<size_t>(k0 + kk + j) * HWpj);
+                    g2[j] = __ldg(gsrc + split_stride + static_cast<size_t>(k0 + kk + j) * HWpj);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) g[j] += g2[j];
+            } else {
+                for (int sp = 0; sp < nsplit; ++sp) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) g[j] += __ldg(gsrc + sp * split_stride + static_cast<size_t>(k0 + kk + j) * HWpj);
                 }
             }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dot = fmaf(g[j] * unscale, fv[j], dot);
         }
     }
     s_dot[ph][px] = dot;
@@ -906,9 +896,17 @@ __global__ void __launch_bounds__(256) pcm_bwd_post_kernel(const float* __restri
     const float nrm = 1.f / inv - 1e-5f;
     const float coef = nrm > 0.f ? dot * inv * inv / nrm : 0.f;
     float* dst = grad_f + static_cast<size_t>(n) * K * HW + p;
+    for (int kk = 0; kk < per; kk += 4) {
+        float g[4] = {0.f, 0.f, 0.f, 0.f}, fv[4];
 #pragma unroll
-    for (int kk = 0; kk < kMaxPer; ++kk)
-        if (kk < per) dst[static_cast<size_t>(k0 + kk) * HW] = gv[kk] * inv - fv[kk] * coef;
+        for (int j = 0; j < 4; ++j) fv[j] = __ldg(fsrc + static_cast<size_t>(k0 + kk + j) * HW);
+        for (int sp = 0; sp < nsplit; ++sp) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) g[j] += __ldg(gsrc + sp * split_stride + static_cast<size_t>(k0 + kk + j) * HWpj);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dst[static_cast<size_t>(k0 + kk + j) * HW] = g[j] * unscale * inv - fv[j] * coef;
+    }
 }
 
 template <bool PRECISE>
