@@ -20,6 +20,12 @@
 //
 // Operands are stored by the prep kernels directly in the UMMA canonical no-swizzle layout, so every tile is one
 // contiguous bulk copy (cp.async.bulk, no tensor maps).
+//
+// Schedule.  Both main kernels are persistent: 74 CTA pairs, each running the stage list PcmSched (common.cuh) gives it —
+// whole (image, j pair) units while they divide evenly ("rows": all pairs on consecutive units, so the i-side tiles are
+// shared through L2), then an equal contiguous share of the remaining units' stages (stream-K tail).  A share that crosses
+// a unit boundary starts a new segment: new A-side tile (after the a_free / u_free commit of the old segment's last
+// product), accumulator restart, own partial slot.
 #include <algorithm>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>

@@ -3,6 +3,12 @@
 //
 // Selection semantics are canonical (value, then lowest flat index) so results are bit-reproducible; every
 // floating-point reduction is done in a fixed order (no float atomics).
+//
+// Two size regimes.  The literal loss grid (16x16, P = N*256 pixels) is latency-bound: one CTA per class for the top-k,
+// 16-pixel CTAs and pairwise in-class ranks for the mining.  Large grids (P > 8192 / 16384) switch to the multi-CTA radix
+// select of segselect.cuh (top-k and mining thresholds) and to persistent 64-/32-pixel-tile score and gradient kernels.
+// Also here: the one-shot NVLink peer-memory exchanges of the data-parallel path (prototype candidates; per-pixel mining
+// statistics for the globally exact mining) and the Philox mining keys.
 #include <algorithm>
 #include <cfloat>
 
