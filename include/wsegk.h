@@ -237,6 +237,13 @@ int wsegk_contrast_loss_fwd_bwd_global(const float* x1, const float* x2, const f
 int wsegk_mining_keys(uint32_t* keys, int count, unsigned long long index0, unsigned long long seed,
                       unsigned long long step, unsigned int stream_id, wsegk_stream_t stream);
 
+/* Fused multi-tensor SGD step (torch.optim.SGD semantics: d = grad + wd*p; buf = first ? d : momentum*buf + (1-dampening)*d;
+ * p -= lr*buf) for the reference's PolyOptimizer (tool/torchutils.py:11-33; the step after the hot path).
+ * The four tables are HOST arrays of n_tensors device pointers / element counts; tensors are contiguous fp32. */
+int wsegk_sgd_step(float* const* params, const float* const* grads, float* const* momentum_bufs, const long long* numels,
+                   int n_tensors, float lr, float weight_decay, float momentum, float dampening, int first_step,
+                   wsegk_stream_t stream);
+
 /* Diagnostics for bench.py / tests (not part of the reference-facing surface).
  *   launch_count  : kernels this library has enqueued in this process so far.
  *   pcm_profile   : when enabled (per host thread), pcm_fwd / pcm_bwd record CUDA events on `stream` around their

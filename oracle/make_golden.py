@@ -27,6 +27,23 @@ LOSS_CASE = dict(n=2, view1=(192, 192), view2=(128, 128), seed1=11, seed2=12, la
                  bg_threshold=0.2)
 PCM_CASE = dict(n=2, h=20, w=13, seed=21)
 NET_CASE = dict(n=1, size=(72, 56), seed=31)
+# tool/torchutils.py PolyOptimizer as contrast_train.py:91-96 builds it (four groups: lr, 2lr, 10lr, 20lr; weight decay on
+# the weight groups only), stepped past max_step
+OPT_CASE = dict(seed=41, shapes=((5, 3), (7,), (4, 2, 3), (6,)), lr=0.01, wt_dec=5e-4, max_step=5, steps=7)
+
+
+def optim_inputs():
+    """Initial parameters and per-step gradients of OPT_CASE (regenerated from the seed at test time)."""
+    c = OPT_CASE
+    g = synth.gen(c["seed"])
+    params = [torch.randn(*s, generator=g) for s in c["shapes"]]
+    grads = [[0.1 * torch.randn(*s, generator=g) for s in c["shapes"]] for _ in range(c["steps"])]
+    return params, grads
+
+
+def optim_groups(params, lr, wt_dec):
+    return [{'params': [params[0]], 'lr': lr, 'weight_decay': wt_dec}, {'params': [params[1]], 'lr': 2 * lr, 'weight_decay': 0},
+            {'params': [params[2]], 'lr': 10 * lr, 'weight_decay': wt_dec}, {'params': [params[3]], 'lr': 20 * lr, 'weight_decay': 0}]
 
 
 def checksum(t: torch.Tensor) -> np.ndarray:
@@ -121,6 +138,30 @@ def net_case():
     print("net case: grid", tuple(cam_rv_down.shape))
 
 
+def optim_case():
+    c = OPT_CASE
+    init, grads = optim_inputs()
+    with verbatim.reference_on_path():
+        from tool import torchutils                      # the reference's own class
+        params = [torch.nn.Parameter(p.clone()) for p in init]
+        opt = torchutils.PolyOptimizer(optim_groups(params, c["lr"], c["wt_dec"]), lr=c["lr"], weight_decay=c["wt_dec"],
+                                       max_step=c["max_step"])
+        out = {"group_momentum": np.array([g["momentum"] for g in opt.param_groups]),
+               "group_weight_decay": np.array([g["weight_decay"] for g in opt.param_groups])}
+        lrs = []
+        for step in range(c["steps"]):
+            for p, g in zip(params, grads[step]):
+                p.grad = g.clone()
+            opt.step()
+            lrs.append([g["lr"] for g in opt.param_groups])
+            for i, p in enumerate(params):
+                out[f"p{i}_step{step}"] = p.detach().numpy().copy()
+        out["lrs"] = np.array(lrs)
+        out["global_step"] = np.array(opt.global_step)
+    np.savez_compressed(os.path.join(OUT, "poly_optimizer.npz"), **out)
+    print("optimizer case: lrs", out["lrs"][:, 0])
+
+
 if __name__ == "__main__":
     if not verbatim.available():
         raise SystemExit("reference checkout not found; golden vectors can only be generated in the build container")
@@ -128,3 +169,4 @@ if __name__ == "__main__":
     loss_case()
     pcm_case()
     net_case()
+    optim_case()

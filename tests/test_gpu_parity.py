@@ -585,6 +585,43 @@ def test_device_mining_keys_are_philox(cuda_dev):
     assert len(set(whole.tolist())) == 64
 
 
+def test_poly_optimizer_golden(cuda_dev, golden_dir):
+    """The fused multi-tensor SGD step behind the PolyOptimizer drop-in against what the reference's own class did on
+    CPU (oracle/make_golden.py optim_case): parameters after every step, learning rates, step counter — including the
+    steps past max_step, where the schedule freezes."""
+    from oracle.make_golden import OPT_CASE, optim_groups, optim_inputs
+    from wseg_b200.optim import PolyOptimizer
+    gold = np.load(os.path.join(golden_dir, "poly_optimizer.npz"))
+    init, grads = optim_inputs()
+    params = [torch.nn.Parameter(p.clone().to(cuda_dev)) for p in init]
+    opt = PolyOptimizer(optim_groups(params, OPT_CASE["lr"], OPT_CASE["wt_dec"]), lr=OPT_CASE["lr"],
+                        weight_decay=OPT_CASE["wt_dec"], max_step=OPT_CASE["max_step"])
+    for step in range(OPT_CASE["steps"]):
+        for p, g in zip(params, grads[step]):
+            p.grad = g.clone().to(cuda_dev)
+        opt.step()
+        assert np.allclose([g["lr"] for g in opt.param_groups], gold["lrs"][step], rtol=1e-12)
+        for i, p in enumerate(params):
+            want = torch.from_numpy(gold[f"p{i}_step{step}"]).to(cuda_dev)
+            assert rel_max(p.detach(), want) <= 2e-7, (step, i)
+    assert opt.global_step == int(gold["global_step"])
+    # and against torch.optim.SGD with the same (quirky) hyper-parameters on many tensors of odd sizes (several launches)
+    g = synth.gen(3)
+    shapes = [(int(torch.randint(1, 40, (1,), generator=g)), int(torch.randint(1, 30, (1,), generator=g))) for _ in range(101)]
+    a = [torch.nn.Parameter(torch.randn(*s, generator=g).to(cuda_dev)) for s in shapes]
+    b = [torch.nn.Parameter(p.detach().clone()) for p in a]
+    mine = PolyOptimizer([{"params": a, "lr": 0.05, "weight_decay": 1e-3}], lr=0.05, weight_decay=5e-4, max_step=100)
+    ref = torch.optim.SGD([{"params": b, "lr": 0.05, "weight_decay": 1e-3}], lr=0.05, momentum=5e-4)
+    for step in range(3):
+        ref.param_groups[0]["lr"] = 0.05 * (1 - step / 100) ** 0.9
+        for p, q in zip(a, b):
+            p.grad = torch.randn(p.shape, generator=g).to(cuda_dev)
+            q.grad = p.grad.clone()
+        mine.step()
+        ref.step()
+    assert max(rel_max(p.detach(), q.detach()) for p, q in zip(a, b)) <= 1e-6
+
+
 def test_pcm_inference_path(cuda_dev):
     """contrast_infer.py runs Net.forward under torch.no_grad(): ops.pcm then takes the forward-only kernel."""
     d = synth.pcm_inputs(2, 44, 60, seed=17)                     # an MSF-like non-square grid

@@ -4,6 +4,7 @@ import os
 import random
 
 import numpy as np
+import pytest
 import torch
 
 from oracle import reference_fn as R
@@ -83,3 +84,24 @@ def test_philox_known_answers():
     assert ops.philox4x32_10([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
     assert ops.philox4x32_10([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
         [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_poly_optimizer_reproduces_the_reference_quirks():
+    """tool/torchutils.py:13-14 passes the weight decay positionally into SGD's momentum slot; the poly power is the
+    constructor's `momentum`; the drop-in must expose the same param_groups (golden: the reference's own class)."""
+    import numpy as np
+    import os
+    from oracle.make_golden import OPT_CASE, optim_groups, optim_inputs
+    from wseg_b200.optim import PolyOptimizer
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "poly_optimizer.npz"))
+    init, _ = optim_inputs()
+    params = [torch.nn.Parameter(p.clone()) for p in init]
+    opt = PolyOptimizer(optim_groups(params, OPT_CASE["lr"], OPT_CASE["wt_dec"]), lr=OPT_CASE["lr"],
+                        weight_decay=OPT_CASE["wt_dec"], max_step=OPT_CASE["max_step"])
+    assert [g["momentum"] for g in opt.param_groups] == list(gold["group_momentum"])
+    assert [g["weight_decay"] for g in opt.param_groups] == list(gold["group_weight_decay"])
+    assert opt.defaults["weight_decay"] == 0 and opt.defaults["momentum"] == OPT_CASE["wt_dec"]
+    for p in params:                                     # CPU parameters with gradients: there is no CPU path
+        p.grad = torch.zeros_like(p)
+    with pytest.raises(RuntimeError):
+        opt.step()

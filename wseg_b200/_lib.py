@@ -18,6 +18,7 @@ _SIGNATURES = {
     "wsegk_last_error": (c_char_p, []),
     "wsegk_workspace_bytes": (c_size_t, [c_int] * 7),
     "wsegk_mining_keys": (c_int, [_P, c_int, ctypes.c_ulonglong, ctypes.c_ulonglong, ctypes.c_ulonglong, ctypes.c_uint, _P]),
+    "wsegk_sgd_step": (c_int, [_P, _P, _P, _P, c_int, c_float, c_float, c_float, c_float, c_int, _P]),
     "wsegk_debug_launch_count": (ctypes.c_ulonglong, []),
     "wsegk_debug_pcm_profile": (c_int, [c_int]),
     "wsegk_debug_pcm_main_ms": (c_int, [ctypes.POINTER(c_float), ctypes.POINTER(c_float)]),
