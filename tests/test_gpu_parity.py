@@ -651,6 +651,44 @@ def test_pcm_inference_msf_sizes(cuda_dev, n, h, w):
     assert rel_max(flipped, out) <= 1e-4
 
 
+def test_seam_net_and_batched_msf_inference(cuda_dev):
+    """resnet38_SEAM.Net shares its head with the contrast network (same cam, cam_rv for the same weights), and
+    infer.msf_cam — image and flipped image of a scale in one forward — equals the per-variant loop of
+    contrast_infer.py:58-80."""
+    from wseg_b200 import infer
+    from wseg_b200.network import resnet38_SEAM, resnet38_contrast
+    torch.manual_seed(3)
+    a = resnet38_contrast.Net().to(cuda_dev).eval()
+    b = resnet38_SEAM.Net().to(cuda_dev).eval()
+    b.load_state_dict({k: v for k, v in a.state_dict().items() if not k.startswith("fc_proj")})
+    g = synth.gen(9)
+    scales = [torch.randn(3, 72, 88, generator=g), torch.randn(3, 104, 128, generator=g)]
+    with torch.no_grad():
+        x = scales[0].unsqueeze(0).to(cuda_dev)
+        cam_a, rv_a, _, _ = a(x)
+        cam_b, rv_b = b(x)
+        assert torch.equal(cam_a, cam_b) and torch.equal(rv_a, rv_b)
+        label20 = torch.zeros(20)
+        label20[[2, 7]] = 1
+        orig = (80, 100)
+        norm_cam, cam_dict = infer.msf_cam(a, scales, label20, orig)
+        # the script's loop: one forward per (scale, flip), numpy-style accumulation
+        total = torch.zeros(20, *orig, device=cuda_dev)
+        for img in scales:
+            for flip in (False, True):
+                xi = img.unsqueeze(0).to(cuda_dev)
+                xi = xi.flip(-1) if flip else xi
+                cam = a(xi)[1]
+                cam = F.interpolate(cam[:, 1:], orig, mode="bilinear", align_corners=False)[0] * label20.to(cuda_dev).view(20, 1, 1)
+                total += cam.flip(-1) if flip else cam
+        total = total.clamp_min(0)
+        mx, mn = total.amax(dim=(1, 2), keepdim=True), total.amin(dim=(1, 2), keepdim=True)
+        total[total < mn + 1e-5] = 0
+        want = (total - mn - 1e-5) / (mx - mn + 1e-5)
+    assert sorted(cam_dict) == [2, 7]
+    assert float((norm_cam - want).abs().max()) <= 2e-4 * float(want.abs().max())
+
+
 def test_net_training_step_end_to_end(cuda_dev):
     """configs[0] in miniature: the drop-in Net (random-init ResNet-38, eval-mode BN as in the reference's train()),
     both views, the whole loss body and its backward on the GPU — against the oracle evaluated on the SAME network

@@ -60,6 +60,19 @@ def test_net_surface_matches_reference_checkpoint_format(golden_dir):
     assert hasattr(net, "normalize") and hasattr(net, "PCM") and len(net.from_scratch_layers) == 5
 
 
+def test_seam_net_surface_matches_reference_checkpoint_format(golden_dir):
+    """network/resnet38_SEAM.py (the baseline network, same PCM): parameter names / shapes as the reference's."""
+    from wseg_b200.network import resnet38_SEAM
+    net = resnet38_SEAM.Net()
+    want = json.load(open(os.path.join(golden_dir, "state_dict_shapes_seam.json")))
+    got = {k: list(v.shape) for k, v in net.state_dict().items()}
+    assert list(got) == list(want) and got == want
+    assert [len(g) for g in net.get_parameter_groups()] == [43, 0, 4, 0]        # as the reference's, before .train()
+    net.train()
+    assert [len(g) for g in net.get_parameter_groups()] == [35, 0, 4, 0]
+    assert len(net.from_scratch_layers) == 4 and not hasattr(net, "fc_proj")
+
+
 def test_union_of_local_topk_contains_global_topk():
     """The exchange step relies on: global top-k (canonical order) is a subset of the ranks' local top-k's."""
     g = torch.Generator().manual_seed(0)
