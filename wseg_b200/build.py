@@ -21,7 +21,7 @@ STAMP = os.path.join(CSRC, ".build_stamp")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",
-]
+] + os.environ.get("WSEG_NVCC_EXTRA", "").split()          # e.g. -DWSEGK_PLANE_SPLIT=32 for an A/B build (tools/ab_bench.py)
 
 
 def _nvcc() -> str:

@@ -53,7 +53,13 @@ __device__ __forceinline__ MinMax mm_block(MinMax v, MinMax* s_red) {
     return r;
 }
 
-constexpr int kPlaneSplit = 8;   // CTAs per (n,c) plane in the min/max pass
+#ifndef WSEGK_PLANE_SPLIT
+#define WSEGK_PLANE_SPLIT 8
+#endif
+#ifndef WSEGK_BWD_NBLK
+#define WSEGK_BWD_NBLK 64
+#endif
+constexpr int kPlaneSplit = WSEGK_PLANE_SPLIT;   // CTAs per (n,c) plane in the min/max pass
 constexpr int kUpPlaneSplit = 32;    // ... when the plane is evaluated on the fly (compute- instead of bandwidth-bound)
 constexpr int kPlaneSplitMax = 32;   // what the workspace is sized for
 
@@ -685,7 +691,7 @@ extern "C" int wsegk_fullres_norm_fwd(const float* p, const float* label, float*
                   "fullres_norm_fwd: workspace %zu < %zu", workspace_bytes, fullres_ws_bytes(N, C));
     MinMax* partial = static_cast<MinMax*>(workspace);
     const int planes = N * C;
-    plane_minmax_partial_kernel<<<dim3(kPlaneSplit, planes), 512, 0, stream>>>(p, label, partial, H * W);
+    plane_minmax_partial_kernel<<<dim3(kPlaneSplit, planes), kPlaneSplit > 8 ? 256 : 512, 0, stream>>>(p, label, partial, H * W);
     fullres_resample_kernel<<<dim3(ceil_div(oh * ow, 256), planes), 256, 0, stream>>>(p, label, partial, out, minmax,
                                                                                        tapsum, H, W, oh, ow, kPlaneSplit);
     count_launches(2);
@@ -706,7 +712,7 @@ extern "C" int wsegk_fullres_norm_bwd(const float* p, const float* label, const 
     float* sums = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) +
                                            align_up(static_cast<size_t>(N) * C * kPlaneSplitMax * sizeof(MinMax), 1024));
     const int planes = N * C;
-    const int nblk = std::min(64, ceil_div(H * W, 256 * 4));
+    const int nblk = std::min(WSEGK_BWD_NBLK, ceil_div(H * W, 256 * 4));
     const size_t tab = (oh == H && ow == W) ? 0 : static_cast<size_t>(2) * (H + W) * sizeof(TapSlot);
     WSEGK_REQUIRE(tab <= 200 * 1024, WSEGK_ERR_BAD_SHAPE, "fullres_norm_bwd: H + W = %d too large for the tap tables",
                   H + W);
