@@ -114,14 +114,12 @@ class HotPath:
             return g
 
         # ---- view 1: K1a + K2 forward
-        camn1 = ops.cam_norm(d["cam1"])
-        rv1, ws1 = ops.pcm_forward(camn1, d["f1"])
+        rv1, ws1, camn1 = ops.pcm_forward_logits(d["cam1"], d["f1"])          # K1a fused into the PCM's operand preparation
         f1_done = torch.cuda.Event()
         f1_done.record(cur)
         # ---- view 2 chain: K1a, K2 forward, its seeds and prototypes, then K1b(cam_rv2) and K2 backward
         with torch.cuda.stream(s2):
-            camn2 = ops.cam_norm(d["cam2"])
-            rv2, ws2 = ops.pcm_forward(camn2, d["f2"])
+            rv2, ws2, camn2 = ops.pcm_forward_logits(d["cam2"], d["f2"])
             norm2, pl2 = ops.seed_labels(rv2, d["label"], BG_THRESHOLD)
             proto2, ti2 = ops.prototypes(norm2, d["fproj2"], group=self.group, view=1)
             v2_done = torch.cuda.Event()
@@ -269,13 +267,13 @@ class E2EPath:
             k1b(cam1_full, VIEW2, "g_n1")
         with torch.cuda.stream(sb):
             need_on(sb, "label", "cam2", "f2")
-            rv2 = ops.pcm(ops.cam_norm(x["cam2"]), leaves["f2"])
+            rv2 = ops.pcm_from_logits(x["cam2"], leaves["f2"])
             cam2_full = ops.bilinear_resize(leaves["cam2"], VIEW2)
             rv2_full = ops.bilinear_resize(rv2, VIEW2)
             k1b(cam2_full, None, "g_n2")
             k1b(rv2_full, None, "g_rv2")
         need_on(main, "label", "cam1", "f1")
-        rv1 = ops.pcm(ops.cam_norm(x["cam1"]), leaves["f1"])
+        rv1 = ops.pcm_from_logits(x["cam1"], leaves["f1"])
         rv1_full = ops.bilinear_resize(rv1, VIEW1)
         k1b(rv1_full, VIEW2, "g_rv1")
         need_on(main, "fproj2", "fproj1")
@@ -587,7 +585,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e.h2d_bytes,
                     "d2h_bytes_per_step": e2e.d2h_bytes, "ms_per_step": float(t.item()) / args.steps, "launch": e2e.mode,
                     "replay_equals_eager": e2e_ok,
-                    "api": "pinned host inputs (cam logits, f, f_proj, labels; both views) -> ops.cam_norm / ops.pcm / ops.bilinear_resize x8 / loss.contrast_terms / ops.fullres_norm through autograd, backward, losses -> host; copies on their own stream, every operator waits only for the tensors it reads"},
+                    "api": "pinned host inputs (cam logits, f, f_proj, labels; both views) -> ops.pcm_from_logits (K1a + K2) / ops.bilinear_resize x8 / loss.contrast_terms / ops.fullres_norm through autograd, backward, losses -> host; copies on their own stream, every operator waits only for the tensors it reads"},
             "roofline": roofline, "step_roofline": step_roofline, "wall_ms_per_step_incl_flush": wall_ms / args.steps}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

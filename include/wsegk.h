@@ -76,6 +76,13 @@ int wsegk_pcm_fwd(const float* f, const float* cam_norm, float* cam_rv, int N, i
 int wsegk_pcm_fwd_infer(const float* f, const float* cam_norm, float* cam_rv, int N, int C, int K, int h, int w,
                         void* workspace, size_t workspace_bytes, wsegk_stream_t stream);
 
+/* K1a + K2 forward fused: `cam_logits` [N,C,h,w] are the RAW class logits (the fc8 output); the in-network normalisation
+ * (network/resnet38_contrast.py:41-48, what wsegk_cam_norm_fwd computes) is applied inside the operand preparation of the PCM
+ * and also written to cam_norm_out [N,C,h,w] (bit-identical to wsegk_cam_norm_fwd; wsegk_pcm_bwd needs it).  Otherwise as
+ * wsegk_pcm_fwd. */
+int wsegk_pcm_fwd_logits(const float* f, const float* cam_logits, float* cam_norm_out, float* cam_rv, int N, int C, int K,
+                         int h, int w, void* workspace, size_t workspace_bytes, wsegk_stream_t stream);
+
 /* K2 backward — autograd of the lines above w.r.t. f only (cam_norm carries no gradient, :41).
  * grad_cam_rv [N,C,h,w] -> grad_f [N,K,h,w].  `workspace` must be the one pcm_fwd filled for the same
  * f / cam_norm (cam_rv is the forward output). */

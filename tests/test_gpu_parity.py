@@ -622,6 +622,22 @@ def test_poly_optimizer_golden(cuda_dev, golden_dir):
     assert max(rel_max(p.detach(), q.detach()) for p, q in zip(a, b)) <= 1e-6
 
 
+@pytest.mark.parametrize("n,h,w", [(8, 56, 56), (2, 20, 13), (1, 64, 64)])
+def test_pcm_from_logits_equals_two_calls(cuda_dev, n, h, w):
+    """K1a fused into the PCM's operand preparation: cam_norm, cam_rv and grad_f bit-identical to cam_norm + pcm."""
+    d = synth.pcm_inputs(n, h, w, seed=60 + h)
+    cam, f, go = d["cam"].to(cuda_dev), d["f"].to(cuda_dev), d["grad_out"].to(cuda_dev)
+    camn = ops.cam_norm(cam)
+    out_a, ws_a = ops.pcm_forward(camn, f)
+    out_b, ws_b, camn_b = ops.pcm_forward_logits(cam, f)
+    assert torch.equal(camn_b, camn) and torch.equal(out_b, out_a)
+    assert torch.equal(ops.pcm_backward(f, camn_b, out_b, go, ws_b), ops.pcm_backward(f, camn, out_a, go, ws_a))
+    fa, fb = f.clone().requires_grad_(True), f.clone().requires_grad_(True)
+    ops.pcm(camn, fa).backward(go)
+    ops.pcm_from_logits(cam, fb).backward(go)
+    assert torch.equal(fa.grad, fb.grad)
+
+
 def test_pcm_inference_path(cuda_dev):
     """contrast_infer.py runs Net.forward under torch.no_grad(): ops.pcm then takes the forward-only kernel."""
     d = synth.pcm_inputs(2, 44, 60, seed=17)                     # an MSF-like non-square grid

@@ -18,13 +18,11 @@ def k1b(name, size, gname):
 
 
 def chain_a():
-    state["camn1"] = ops.cam_norm(d["cam1"])
-    state["rv1"], state["ws1"] = ops.pcm_forward(state["camn1"], d["f1"])
+    state["rv1"], state["ws1"], state["camn1"] = ops.pcm_forward_logits(d["cam1"], d["f1"])
 
 
 def chain_a2():
-    state["camn2"] = ops.cam_norm(d["cam2"])
-    state["rv2"], state["ws2"] = ops.pcm_forward(state["camn2"], d["f2"])
+    state["rv2"], state["ws2"], state["camn2"] = ops.pcm_forward_logits(d["cam2"], d["f2"])
 
 
 def chain_b():
@@ -88,7 +86,7 @@ def measure(name, fn, iters=20):
     return keep
 
 
-measure("A  view 1: K1a + K2 forward (6 kernels)", chain_a)
+measure("A  view 1: K1a + K2 forward (4 kernels)", chain_a)
 measure("A2 view 2: K1a + K2 forward", chain_a2)
 measure("B  K1b fwd+bwd on cam_rv1 (448^2 -> 128^2)", chain_b)
 measure("C  K2 backward view 1 (3 kernels + memset)", chain_c)

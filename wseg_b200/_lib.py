@@ -31,6 +31,7 @@ _SIGNATURES = {
     "wsegk_cam_norm_fwd": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
     "wsegk_pcm_fwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
     "wsegk_pcm_fwd_infer": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
+    "wsegk_pcm_fwd_logits": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
     "wsegk_pcm_bwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
     "wsegk_fullres_norm_fwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
     "wsegk_fullres_norm_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P,

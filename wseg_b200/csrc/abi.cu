@@ -115,6 +115,7 @@ PcmPlan make_pcm_plan(void* ws, int N, int C, int K, int h, int w, int precise) 
     p.vb = c.take<uint16_t>(bt * p.wb * 3 * kAugK);
     p.dfhat = c.take<float>(static_cast<size_t>(N) * p.nsplit * K * p.HWpj);
     p.bound = c.take<float>(256);
+    p.peak = c.take<float>(static_cast<size_t>(N) * C);
     p.bytes = c.total();
     return p;
 }

@@ -67,6 +67,10 @@ __global__ void __launch_bounds__(128) cam_pixel_kernel(const float* __restrict_
     }
 }
 
+void launch_cam_plane_peak(const float* cam, float* peak, int planes, int HW, cudaStream_t stream) {
+    cam_plane_peak_kernel<<<planes, 256, 0, stream>>>(cam, peak, HW);
+}
+
 }  // namespace wsegk
 
 using namespace wsegk;

@@ -97,6 +97,7 @@ struct PcmPlan {
     uint16_t* vb;                          // [N][2*NS] B tiles [wb x Ku] bf16 backward factor V
     float* dfhat;                          // [N][nsplit][K][HWpj] fp32 partial gradient w.r.t. normalised features
     float* bound;                          // [1] upper bound of |T| (as float bits, atomicMax)
+    float* peak;                           // [N][C] per-plane maxima of relu(cam) + 1e-5 (pcm_fwd_logits: fused K1a)
     int Ku;                                // 48 (fast) or 144 (precise: [hi|hi|lo] x [hi|lo|hi])
     size_t bytes;
 };
@@ -172,6 +173,9 @@ struct StageCursor {
         }
     }
 };
+
+// peak[plane] = max relu(cam[plane]) + 1e-5, one CTA per (n,c) plane (cam_norm.cu)
+void launch_cam_plane_peak(const float* cam, float* peak, int planes, int HW, cudaStream_t stream);
 
 PcmPlan make_pcm_plan(void* ws, int N, int C, int K, int h, int w, int precise);
 int pcm_mode();     // current process-wide mode (wsegk_pcm_set_mode): 1 precise (default), 0 fast

@@ -109,34 +109,61 @@ __device__ __forceinline__ void pcm_prep_f_body(const float* __restrict__ f, uin
 
 // cam_norm [N,C,HW] fp32 -> per (image, stage) two operand blocks of [32 rows x 2wb pixels] fp16, K-major (K = pixel):
 //   rank 0 block: rows 0..C-1 = fp16(cam), row C = 1 (column-sum row), others 0;   rank 1 block: rows 0..C-1 = cam - hi.
-__device__ __forceinline__ void pcm_prep_cam_body(const float* __restrict__ cam, uint4* __restrict__ camb,
+// kLogits: `cam` holds the RAW class logits and `peak` the per-plane maxima (cam_plane_peak_kernel); the in-network
+// normalisation (K1a, network/resnet38_contrast.py:41-48) is applied here, with cam_pixel_kernel's arithmetic, and also
+// written to cam_norm_out — K1a's per-pixel pass leaves the critical path in front of the PCM.
+template <bool kLogits>
+__device__ __forceinline__ void pcm_prep_cam_body(const float* __restrict__ cam, const float* __restrict__ peak,
+                                                  float* __restrict__ cam_norm_out, uint4* __restrict__ camb,
                                                   int C, int HW, int NS, int wb, int s, int n) {
     __shared__ __align__(16) uint16_t s_blk[2 * 16 * kCamRows * 8];   // [rank][pixel group g][row][8]
+    __shared__ float s_peak[kCamRows];
     const int q = threadIdx.x;
     const int ncol = 2 * wb;
     const int p = s * ncol + q;
     const bool live = q < ncol && p < HW;
     const float* src = cam + static_cast<size_t>(n) * C * HW + p;
+    if (kLogits) {
+        if (threadIdx.x < kCamRows) s_peak[threadIdx.x] = threadIdx.x < C ? peak[n * C + threadIdx.x] : 1.f;
+        __syncthreads();
+    }
     if (q < ncol) {
         const int g = q >> 3, e = q & 7;
         const int G = ncol >> 3;
+        float y[kCamRows];
+#pragma unroll
         for (int c0 = 0; c0 < kCamRows; c0 += 8) {            // eight independent loads in flight
-            float v[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = (live && c0 + j < C) ? __ldg(src + static_cast<size_t>(c0 + j) * HW) : 0.f;
+            for (int j = 0; j < 8; ++j) y[c0 + j] = (live && c0 + j < C) ? __ldg(src + static_cast<size_t>(c0 + j) * HW) : 0.f;
+        }
+        if (kLogits) {
+            float fg = 0.f;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int c = c0 + j;
-                float hi = 0.f, lo = 0.f;
-                if (live && c < C) {
-                    hi = __half2float(__float2half_rn(v[j]));
-                    lo = v[j] - hi;
-                } else if (live && c == C) {
-                    hi = 1.f;
-                }
-                s_blk[((0 * G + g) * kCamRows + c) * 8 + e] = __half_as_ushort(__float2half_rn(hi));
-                s_blk[((1 * G + g) * kCamRows + c) * 8 + e] = __half_as_ushort(__float2half_rn(lo));
+            for (int c = 1; c < kCamRows; ++c) {
+                y[c] = c < C ? fmaxf(fmaxf(y[c], 0.f) - 1e-5f, 0.f) / s_peak[c] : 0.f;
+                fg = fmaxf(fg, y[c]);
             }
+            y[0] = 1.f - fg;
+#pragma unroll
+            for (int c = 1; c < kCamRows; ++c) y[c] = (y[c] < fg) ? 0.f : y[c];
+            if (live) {
+                float* dstn = cam_norm_out + static_cast<size_t>(n) * C * HW + p;
+#pragma unroll
+                for (int c = 0; c < kCamRows; ++c)
+                    if (c < C) dstn[static_cast<size_t>(c) * HW] = y[c];
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < kCamRows; ++c) {
+            float hi = 0.f, lo = 0.f;
+            if (live && c < C) {
+                hi = __half2float(__float2half_rn(y[c]));
+                lo = y[c] - hi;
+            } else if (live && c == C) {
+                hi = 1.f;
+            }
+            s_blk[((0 * G + g) * kCamRows + c) * 8 + e] = __half_as_ushort(__float2half_rn(hi));
+            s_blk[((1 * G + g) * kCamRows + c) * 8 + e] = __half_as_ushort(__float2half_rn(lo));
         }
     }
     __syncthreads();
@@ -148,16 +175,18 @@ __device__ __forceinline__ void pcm_prep_cam_body(const float* __restrict__ cam,
 
 // both operand preparations in ONE launch (they are independent; as two launches the 7 us cam preparation sat on the
 // critical path behind the feature preparation): blocks [0, tiles) prepare features, blocks [tiles, tiles + NS) cam blocks
-template <bool kLo>
+template <bool kLo, bool kLogits>
 __global__ void __launch_bounds__(256) pcm_prep_kernel(const float* __restrict__ f, uint4* __restrict__ fa_hi,
                                                        uint4* __restrict__ fa_lo, uint4* __restrict__ fb_hi,
                                                        uint4* __restrict__ fb_lo, float* __restrict__ inv_norm,
-                                                       const float* __restrict__ cam, uint4* __restrict__ camb, int C,
+                                                       const float* __restrict__ cam, const float* __restrict__ peak,
+                                                       float* __restrict__ cam_norm_out, uint4* __restrict__ camb, int C,
                                                        int K, int HW, int PJ, int NS, int wb, int tiles) {
     if (static_cast<int>(blockIdx.x) < tiles)
         pcm_prep_f_body<kLo>(f, fa_hi, fa_lo, fb_hi, fb_lo, inv_norm, K, HW, PJ, NS, wb, blockIdx.x, blockIdx.y);
     else
-        pcm_prep_cam_body(cam, camb, C, HW, NS, wb, static_cast<int>(blockIdx.x) - tiles, blockIdx.y);
+        pcm_prep_cam_body<kLogits>(cam, peak, cam_norm_out, camb, C, HW, NS, wb, static_cast<int>(blockIdx.x) - tiles,
+                                   blockIdx.y);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1020,7 +1049,8 @@ static int launch_bwd(const PcmPlan& pl, int N, wsegk_stream_t stream) {
     } while (0)
 
 static int pcm_fwd_impl(const float* f, const float* cam_norm, float* cam_rv, int N, int C, int K, int h, int w,
-                        void* workspace, size_t workspace_bytes, wsegk_stream_t stream, int precise);
+                        void* workspace, size_t workspace_bytes, wsegk_stream_t stream, int precise,
+                        float* cam_norm_out = nullptr);
 
 extern "C" int wsegk_pcm_fwd(const float* f, const float* cam_norm, float* cam_rv, int N, int C, int K, int h,
                              int w, void* workspace, size_t workspace_bytes, wsegk_stream_t stream) {
@@ -1032,8 +1062,15 @@ extern "C" int wsegk_pcm_fwd_infer(const float* f, const float* cam_norm, float*
     return pcm_fwd_impl(f, cam_norm, cam_rv, N, C, K, h, w, workspace, workspace_bytes, stream, 0);
 }
 
+// cam_norm_out != nullptr: `cam_norm` holds raw logits; K1a is fused into the operand preparation
+extern "C" int wsegk_pcm_fwd_logits(const float* f, const float* cam_logits, float* cam_norm_out, float* cam_rv, int N, int C,
+                                    int K, int h, int w, void* workspace, size_t workspace_bytes, wsegk_stream_t stream) {
+    WSEGK_REQUIRE(cam_norm_out != nullptr, WSEGK_ERR_NULL, "pcm_fwd_logits: null pointer");
+    return pcm_fwd_impl(f, cam_logits, cam_rv, N, C, K, h, w, workspace, workspace_bytes, stream, pcm_mode(), cam_norm_out);
+}
+
 static int pcm_fwd_impl(const float* f, const float* cam_norm, float* cam_rv, int N, int C, int K, int h, int w,
-                        void* workspace, size_t workspace_bytes, wsegk_stream_t stream, int precise) {
+                        void* workspace, size_t workspace_bytes, wsegk_stream_t stream, int precise, float* cam_norm_out) {
     if (int rc = check_device()) return rc;
     WSEGK_REQUIRE(f && cam_norm && cam_rv && workspace, WSEGK_ERR_NULL, "pcm_fwd: null pointer");
     if (int rc = pcm_check("pcm_fwd", N, C, K, h, w)) return rc;
@@ -1049,12 +1086,23 @@ static int pcm_fwd_impl(const float* f, const float* cam_norm, float* cam_rv, in
         uint4 *b_hi = reinterpret_cast<uint4*>(pl.fb_hi), *b_lo = reinterpret_cast<uint4*>(pl.fb_lo);
         uint4* cb = reinterpret_cast<uint4*>(pl.camb);
         (void)smem;
-        if (precise)
-            pcm_prep_kernel<true><<<dim3(tiles + pl.NS, N), 256, 0, stream>>>(f, a_hi, a_lo, b_hi, b_lo, pl.inv_norm, cam_norm,
-                                                                             cb, C, K, pl.HW, pl.PJ, pl.NS, pl.wb, tiles);
-        else
-            pcm_prep_kernel<false><<<dim3(tiles + pl.NS, N), 256, 0, stream>>>(f, a_hi, a_lo, b_hi, b_lo, pl.inv_norm, cam_norm,
-                                                                              cb, C, K, pl.HW, pl.PJ, pl.NS, pl.wb, tiles);
+        const dim3 grid(tiles + pl.NS, N);
+        if (cam_norm_out != nullptr) {
+            launch_cam_plane_peak(cam_norm, pl.peak, N * C, pl.HW, stream);
+            count_launches(1);
+            if (precise)
+                pcm_prep_kernel<true, true><<<grid, 256, 0, stream>>>(f, a_hi, a_lo, b_hi, b_lo, pl.inv_norm, cam_norm, pl.peak,
+                                                                      cam_norm_out, cb, C, K, pl.HW, pl.PJ, pl.NS, pl.wb, tiles);
+            else
+                pcm_prep_kernel<false, true><<<grid, 256, 0, stream>>>(f, a_hi, a_lo, b_hi, b_lo, pl.inv_norm, cam_norm, pl.peak,
+                                                                       cam_norm_out, cb, C, K, pl.HW, pl.PJ, pl.NS, pl.wb, tiles);
+        } else if (precise) {
+            pcm_prep_kernel<true, false><<<grid, 256, 0, stream>>>(f, a_hi, a_lo, b_hi, b_lo, pl.inv_norm, cam_norm, nullptr,
+                                                                   nullptr, cb, C, K, pl.HW, pl.PJ, pl.NS, pl.wb, tiles);
+        } else {
+            pcm_prep_kernel<false, false><<<grid, 256, 0, stream>>>(f, a_hi, a_lo, b_hi, b_lo, pl.inv_norm, cam_norm, nullptr,
+                                                                    nullptr, cb, C, K, pl.HW, pl.PJ, pl.NS, pl.wb, tiles);
+        }
     }
     prof_mark(0, stream);
     WSEGK_DISPATCH_WB(launch_fwd, precise, pl, N, stream);

@@ -40,12 +40,12 @@ class Net(resnet38d.Net):
         f_proj = F.relu(self.fc_proj(fea), inplace=True)
         cam = self.fc8(fea)
         h, w = cam.shape[-2:]
-        cam_d_norm = ops.cam_norm(cam)                                                     # K1a (:41-48)
         f8_3 = F.relu(self.f8_3(d['conv4'].detach()), inplace=True)
         f8_4 = F.relu(self.f8_4(d['conv5'].detach()), inplace=True)
         x_s = F.interpolate(x, (h, w), mode='bilinear', align_corners=True)
         f = torch.cat([x_s, f8_3, f8_4], dim=1)
-        cam_rv_down = self.PCM(cam_d_norm, f)                                              # K2 (:63-75)
+        # K1a (:41-48) + K2 (:63-75): self.PCM(cam_d_norm, f) with the normalisation fused into the PCM's operand preparation
+        cam_rv_down = ops.pcm_from_logits(cam, self.f9(f))
         if not enlarge:
             return cam, cam_rv_down, f_proj
         cam_rv = ops.bilinear_resize(cam_rv_down, (H, W))                                  # glue (:57-58)

@@ -71,6 +71,25 @@ def pcm_forward(cam_norm_t: torch.Tensor, f: torch.Tensor, inference: bool = Fal
     return out, ws
 
 
+def pcm_forward_logits(cam_logits: torch.Tensor, f: torch.Tensor):
+    """K1a + K2 forward in one call (network/resnet38_contrast.py:41-48 fused into :70-73): the normalisation of the raw
+    class logits happens inside the PCM's operand preparation.  Returns (cam_rv, workspace, cam_norm) — ``cam_norm`` is
+    bit-identical to ``cam_norm(cam_logits)`` and is what ``pcm_backward`` needs."""
+    f = _require_cuda_f32("f", f)
+    cam_logits = _require_cuda_f32("cam", cam_logits)
+    n, k, h, w = f.shape
+    c = cam_logits.shape[1]
+    if cam_logits.shape[0] != n or tuple(cam_logits.shape[2:]) != (h, w):
+        raise RuntimeError(f"pcm: cam {tuple(cam_logits.shape)} does not match f {tuple(f.shape)}")
+    out = torch.empty(n, c, h, w, dtype=torch.float32, device=f.device)
+    camn = torch.empty_like(cam_logits)
+    with torch.cuda.device(f.device):
+        ws = _workspace(_lib.OP_PCM, f.device, N=n, C=c, K=k, h=h, w=w)
+        check(_lib.lib().wsegk_pcm_fwd_logits(_ptr(f), _ptr(cam_logits), _ptr(camn), _ptr(out), n, c, k, h, w, _ptr(ws),
+                                              ws.numel(), _stream(f)), "wsegk_pcm_fwd_logits")
+    return out, ws, camn
+
+
 def pcm_backward(f: torch.Tensor, cam_norm_t: torch.Tensor, cam_rv: torch.Tensor, grad_out: torch.Tensor,
                  ws: torch.Tensor) -> torch.Tensor:
     f = _require_cuda_f32("f", f)
@@ -98,6 +117,30 @@ class _PCMFunction(torch.autograd.Function):
         grad_f = pcm_backward(f, cam_norm_t, out, grad_out, ctx.ws)
         ctx.ws = None
         return None, grad_f
+
+
+class _PCMFromLogits(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cam_logits, f):
+        out, ws, camn = pcm_forward_logits(cam_logits, f)
+        ctx.save_for_backward(f, camn, out)
+        ctx.ws = ws
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        f, camn, out = ctx.saved_tensors
+        grad_f = pcm_backward(f, camn, out, grad_out, ctx.ws)
+        ctx.ws = None
+        return None, grad_f
+
+
+def pcm_from_logits(cam_logits: torch.Tensor, f: torch.Tensor) -> torch.Tensor:
+    """``pcm(cam_norm(cam_logits), f)`` with the normalisation fused into the PCM's operand preparation (same values bit for
+    bit; no gradient flows to the logits, as in the reference, which normalises under ``torch.no_grad()``)."""
+    if not (torch.is_grad_enabled() and f.requires_grad):
+        return pcm_forward(cam_norm(cam_logits.detach()), f.detach(), inference=True)[0]
+    return _PCMFromLogits.apply(cam_logits.detach(), f)
 
 
 def pcm(cam_norm_t: torch.Tensor, f: torch.Tensor) -> torch.Tensor:
