@@ -578,7 +578,7 @@ def run_ours(args):
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16 tensor-core operands, fp32 accumulate (PCM); f32 elsewhere", "data": "synthetic",
+            "dtype": "f16 hi+lo (forward) / bf16 hi+lo (backward factors) tensor-core operands, f32 accumulate (PCM, precise mode); f32 elsewhere", "data": "synthetic",
             "config": dict(config_dict(world), launch=mode), "image_mpix_per_s": value * 64,
             "clocks": clk.summary(), "gpu_launches": int(launches_per_step * args.steps),
             "gpu_launches_per_step": int(launches_per_step),
