@@ -196,8 +196,9 @@ class E2EPath:
     # for the rest of the loss (g_*) stay resident — they would be produced on the device
     NAMES = ["label", "cam1", "cam2", "f2", "fproj2", "f1", "fproj1"]
 
-    def __init__(self, hp: HotPath, use_graph: bool):
+    def __init__(self, hp: HotPath, use_graph: bool, lazy: bool = False):
         self.hp = hp
+        self.lazy = lazy          # True: ops.fullres_norm_up on the small maps instead of x8 enlargement + ops.fullres_norm
         self.h2d_bytes = sum(hp.host[k].numel() * hp.host[k].element_size() for k in self.NAMES)
         self.out_host = torch.empty(10, dtype=torch.float32).pin_memory()
         self.d2h_bytes = 40
@@ -251,8 +252,14 @@ class E2EPath:
         leaves = {k: x[k].requires_grad_(True) for k in ("f1", "f2", "fproj1", "fproj2", "cam1", "cam2")}
         parts = []
 
-        def k1b(t, size, gname):
-            parts.append((ops.fullres_norm(t, x["label"], size) * hp.d[gname]).sum())
+        def k1b(t, up, size, gname):
+            """K1b on the full-resolution map of the small map t: materialised (Net.forward's tail, :57-59, then
+            contrast_train.py:145-152) or lazy (bit-identical values)."""
+            if self.lazy:
+                y = ops.fullres_norm_up(t, x["label"], up, size)
+            else:
+                y = ops.fullres_norm(ops.bilinear_resize(t, up), x["label"], size)
+            parts.append((y * hp.d[gname]).sum())
 
         # Three independent chains, each on its own stream (autograd runs every backward node on the stream of its
         # forward): (a) what only needs the cam logits of view 1, (b) view 2, (main) view 1's PCM chain, which has to
@@ -263,19 +270,15 @@ class E2EPath:
         sb.wait_stream(main)
         with torch.cuda.stream(sa):
             need_on(sa, "label", "cam1")
-            cam1_full = ops.bilinear_resize(leaves["cam1"], VIEW1)                   # Net.forward's tail (:57-59)
-            k1b(cam1_full, VIEW2, "g_n1")
+            k1b(leaves["cam1"], VIEW1, VIEW2, "g_n1")
         with torch.cuda.stream(sb):
             need_on(sb, "label", "cam2", "f2")
             rv2 = ops.pcm_from_logits(x["cam2"], leaves["f2"])
-            cam2_full = ops.bilinear_resize(leaves["cam2"], VIEW2)
-            rv2_full = ops.bilinear_resize(rv2, VIEW2)
-            k1b(cam2_full, None, "g_n2")
-            k1b(rv2_full, None, "g_rv2")
+            k1b(leaves["cam2"], VIEW2, None, "g_n2")
+            k1b(rv2, VIEW2, None, "g_rv2")
         need_on(main, "label", "cam1", "f1")
         rv1 = ops.pcm_from_logits(x["cam1"], leaves["f1"])
-        rv1_full = ops.bilinear_resize(rv1, VIEW1)
-        k1b(rv1_full, VIEW2, "g_rv1")
+        k1b(rv1, VIEW1, VIEW2, "g_rv1")
         need_on(main, "fproj2", "fproj1")
         main.wait_stream(sb)
         terms = L.contrast_terms(leaves["fproj1"], rv1, leaves["fproj2"], rv2, x["label"], BG_THRESHOLD, grid=hp.grid,
@@ -575,6 +578,17 @@ def run_ours(args):
     e2e_ok = e2e.verify()
     if e2e_ok is False:
         raise RuntimeError("bench.py: the replayed end-to-end graph does not reproduce the eager run of the same step")
+    # the same end-to-end step with the lazy full-resolution maps of the extended API (Net.forward_small +
+    # ops.fullres_norm_up; same values, the four N*21*H*W tensors never exist) — reported beside the drop-in number
+    e2e_lazy = E2EPath(hp, use_graph=not args.no_graph, lazy=True)
+    lazy_ms, _ = time_steps(e2e_lazy.step, args.steps, args.warmup, dev, flush, barrier)
+    tl = torch.tensor([lazy_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tl, op=dist.ReduceOp.MAX)
+    lazy_ok = e2e_lazy.verify()
+    if lazy_ok is False:
+        raise RuntimeError("bench.py: the replayed lazy end-to-end graph does not reproduce its eager run")
+    same = bool(torch.allclose(e2e_lazy.out_host, e2e.out_host, rtol=1e-6, atol=0))
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -586,6 +600,12 @@ def run_ours(args):
                     "d2h_bytes_per_step": e2e.d2h_bytes, "ms_per_step": float(t.item()) / args.steps, "launch": e2e.mode,
                     "replay_equals_eager": e2e_ok,
                     "api": "pinned host inputs (cam logits, f, f_proj, labels; both views) -> ops.pcm_from_logits (K1a + K2) / ops.bilinear_resize x8 / loss.contrast_terms / ops.fullres_norm through autograd, backward, losses -> host; copies on their own stream, every operator waits only for the tensors it reads"},
+            "e2e_lazy": {"value": total_pix / (float(tl.item()) / args.steps * 1e-3) / 1e6, "unit": UNIT,
+                         "ms_per_step": float(tl.item()) / args.steps, "h2d_bytes_per_step": e2e_lazy.h2d_bytes,
+                         "d2h_bytes_per_step": e2e_lazy.d2h_bytes, "launch": e2e_lazy.mode,
+                         "replay_equals_eager": lazy_ok, "losses_equal_e2e": same,
+                         "api": "as e2e, with ops.fullres_norm_up on the stride-8 maps (Net.forward_small) instead of the x8 "
+                                "enlargement + ops.fullres_norm"},
             "roofline": roofline, "step_roofline": step_roofline, "wall_ms_per_step_incl_flush": wall_ms / args.steps}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -600,6 +620,7 @@ def run_ours(args):
         # graph, drain, agree that everyone is done, and leave without the communicator destructor.
         del stepper
         e2e.graph = None
+        e2e_lazy.graph = None
         torch.cuda.synchronize(dev)
         dist.barrier()
         sys.stdout.flush()
