@@ -70,10 +70,16 @@ static int pick_wb(int HW) {
 }
 
 // How many CTA pairs split one j pair's sweep over the i stages: minimise (waves x stages per CTA + fixed cost).
-// CTA pairs of the persistent PCM kernels: one per SM pair of a B200 (148 SMs, one 200 KB CTA per SM); every pair gets at
-// least two stages.  A constant, not a device query, so that workspace sizes do not depend on where they are asked for.
+// CTA pairs of the persistent PCM kernels.  A B200 has 74 SM pairs and a PCM CTA takes a whole SM (213 KB of shared memory),
+// so 74 pairs is the fastest PCM in isolation — but in the training step the other chains (K1b, seeds, prototypes, NCE) then
+// cannot make progress while a PCM kernel runs.  72 pairs leave 4 SMs to them: the PCM kernels get ~3 % slower, the whole
+// step 1.7 % faster (A/B on one box, 68 / 70 / 72 within noise of each other, 66 and 74 slower; profiles/README.md).
+// A constant, not a device query, so that workspace sizes do not depend on where they are asked for.
 static int pick_clusters(long long T) {
-    const long long slots = 74;
+#ifndef WSEGK_PCM_PAIRS
+#define WSEGK_PCM_PAIRS 72
+#endif
+    const long long slots = WSEGK_PCM_PAIRS;
     long long g = T / 2;
     if (g > slots) g = slots;
     if (g < 1) g = 1;
