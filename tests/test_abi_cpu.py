@@ -49,9 +49,7 @@ def test_version_and_workspace_sizes(lib):
     assert "unknown op" in _lib.last_error()
 
 
-@pytest.mark.parametrize("n,h,w", [(8, 56, 56), (1, 16, 16), (2, 20, 13), (16, 56, 56), (3, 9, 5), (128, 32, 32), (5, 96, 96),
-                                   (1, 108, 108)])
-def test_pcm_schedule_covers_every_stage_once(lib, n, h, w):
+def _check_schedule(lib, n, h, w):
     """The persistent PCM kernels' schedule (rows + stream-K tail, csrc/common.cuh) as a host-side property: every stage
     of every (image, j pair) unit is run by exactly one CTA pair, the pairs' loads differ by at most one stage, a pair's
     segments are runs of consecutive stages of one unit, and the (unit, slot) pairs are distinct with slots below the
@@ -82,8 +80,25 @@ def test_pcm_schedule_covers_every_stage_once(lib, n, h, w):
                 used.add((u, slot))
             prev = (u, st, k, slot)
     assert len(seen) == units * ns
-    assert max(loads) - min(loads) <= 1 or len(loads) < 74
+    assert max(loads) - min(loads) <= 1 or len(loads) < 72
     assert sum(loads) == units * ns
+
+
+@pytest.mark.parametrize("n,h,w", [(8, 56, 56), (1, 16, 16), (2, 20, 13), (16, 56, 56), (3, 9, 5), (128, 32, 32), (5, 96, 96),
+                                   (1, 108, 108)])
+def test_pcm_schedule_covers_every_stage_once(lib, n, h, w):
+    _check_schedule(lib, n, h, w)
+
+
+def test_pcm_schedule_random_shapes(lib):
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.integers(1, 40), st.integers(1, 70), st.integers(1, 70))
+    def run(n, h, w):
+        _check_schedule(lib, n, h, w)
+
+    run()
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU refusal path")
