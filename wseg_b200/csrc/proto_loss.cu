@@ -703,14 +703,16 @@ __global__ void __launch_bounds__(kNceThreads) nce_pixel_kernel(NceParams prm) {
     }
 }
 
-// ---- A (large P): 64 pixels per CTA, 4 pixels x 6 slots per thread ---------------------------------
-// The prototypes are kept transposed ([d][68]: slot 6g+j at column 8g+j) so a thread reads its six as float4 + float2,
-// and its four pixels of s_x[d][64] as one float4: 3 shared-memory instructions per 24 (+4) FMAs instead of 7 per 6 in
-// the 16-pixel kernel.  Each dot product is still accumulated over d in order by one thread: same values.
+// ---- A (large P): 64 pixels per CTA, 256 threads, 4 pixels x 3 slots per thread ------------------------------------
+// The prototypes are kept transposed ([d][68]: slot 3g+j at column 4g+j) so a thread reads its three as one float4, and its
+// four pixels of s_x[d][64] as another: 2 shared-memory instructions per 12 FMAs instead of 7 per 6 in the 16-pixel kernel,
+// with 16 warps per SM (two 89 KB CTAs) to hide their latency.  Each dot product is still accumulated over d in order by one
+// thread: same values.
 constexpr int kTilePix = 64;
 constexpr int kGradTilePix = 32;       // 256 threads, two CTAs per SM
 constexpr int kTileProtoStride = 68;
-__global__ void __launch_bounds__(kNceThreads) nce_pixel_tile_kernel(NceParams prm) {
+constexpr int kPixTileThreads = 256;
+__global__ void __launch_bounds__(kPixTileThreads) nce_pixel_tile_kernel(NceParams prm) {
     extern __shared__ __align__(16) float s_dyn[];
     const NceView& V = prm.v[blockIdx.y];
     const int C = prm.C, D = prm.D, HW = prm.HW, P = prm.P;
@@ -720,6 +722,7 @@ __global__ void __launch_bounds__(kNceThreads) nce_pixel_tile_kernel(NceParams p
     float* s_part = s_sc + kTilePix * 49;                      // [64][8][4]
     float* s_inv = s_part + kTilePix * kNceGroups * 4;         // [64]
     __shared__ int s_cls[kNceMaxC];                            // pixels per pseudo-class seen by this CTA
+    __shared__ float s_cross[2][2];
     if (threadIdx.x < kNceMaxC) s_cls[threadIdx.x] = 0;
     // the CTA is persistent: the prototypes are staged once (all 48 loads of a thread in flight at once)
     for (int d = threadIdx.x; d < D; d += blockDim.x) {
@@ -732,48 +735,55 @@ __global__ void __launch_bounds__(kNceThreads) nce_pixel_tile_kernel(NceParams p
         }
 #pragma unroll
         for (int slot = 0; slot < kNceSlots; ++slot)
-            s_proto[d * kTileProtoStride + 8 * (slot / 6) + slot % 6] = v[slot];
+            s_proto[d * kTileProtoStride + 4 * (slot / 3) + slot % 3] = v[slot];
     }
+    // scalar-phase mapping: the 256 threads serve two 16-pixel groups at a time, 8 threads (class groups) per pixel
+    const int half = threadIdx.x >> 7, t7 = threadIdx.x & 127;
+    const int grp = t7 >> 4;
     for (int tile = blockIdx.x; tile < prm.nblk; tile += gridDim.x) {
     const int p0 = tile * kTilePix;
     nce_tile_load_x<kTilePix>(V, s_x, p0, D, HW, P);
     __syncthreads();
+    const int pg = threadIdx.x & 15, sg = threadIdx.x >> 4;           // pixels 4pg..4pg+3, slots 3sg..3sg+2
+    float acc[4][3];
     {
-        const int pg = threadIdx.x & 15, sg = threadIdx.x >> 4;       // pixels 4pg..4pg+3, slots 6sg..6sg+5
-        float acc[4][6], ss[4] = {0.f, 0.f, 0.f, 0.f};
+        float ss[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 6; ++j) acc[i][j] = 0.f;
+            for (int j = 0; j < 3; ++j) acc[i][j] = 0.f;
         const float* xr = s_x + 4 * pg;
-        const float* pr = s_proto + 8 * sg;
+        const float* pr = s_proto + 4 * sg;
+        const bool norm_warp = threadIdx.x < 32;                      // warp 0 also accumulates |x|^2 (lanes 0-15 publish it)
 #pragma unroll 4
         for (int d = 0; d < D; ++d) {
             const float4 xv = *reinterpret_cast<const float4*>(xr + d * kTilePix);
             const float4 pa = *reinterpret_cast<const float4*>(pr + d * kTileProtoStride);
-            const float2 pb = *reinterpret_cast<const float2*>(pr + d * kTileProtoStride + 4);
             const float x[4] = {xv.x, xv.y, xv.z, xv.w};
-            const float pv[6] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y};
+            const float pv[3] = {pa.x, pa.y, pa.z};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                ss[i] = fmaf(x[i], x[i], ss[i]);
+                if (norm_warp) ss[i] = fmaf(x[i], x[i], ss[i]);
 #pragma unroll
-                for (int j = 0; j < 6; ++j) acc[i][j] = fmaf(x[i], pv[j], acc[i][j]);
+                for (int j = 0; j < 3; ++j) acc[i][j] = fmaf(x[i], pv[j], acc[i][j]);
             }
         }
+        if (sg == 0) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float inv = 1.f / fmaxf(sqrtf(ss[i]), 1e-12f);          // F.normalize
-#pragma unroll
-            for (int j = 0; j < 6; ++j) s_sc[(4 * pg + i) * 49 + 6 * sg + j] = acc[i][j] * inv;
-            if (sg == 0) s_inv[4 * pg + i] = inv;
+            for (int i = 0; i < 4; ++i) s_inv[4 * pg + i] = 1.f / fmaxf(sqrtf(ss[i]), 1e-12f);      // F.normalize
         }
     }
     __syncthreads();
-    // per-pixel scalars: thread (pix, grp) owns classes grp, grp+8, grp+16 of pixel pix = (tid & 15) + 16*sub
-    const int grp = threadIdx.x >> 4;
-    for (int sub = 0; sub < kTilePix / 16; ++sub) {
-        const int pix = (threadIdx.x & 15) + 16 * sub, p = p0 + pix;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float inv = s_inv[4 * pg + i];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) s_sc[(4 * pg + i) * 49 + 3 * sg + j] = acc[i][j] * inv;
+    }
+    __syncthreads();
+    // per-pixel scalars: thread (pix, grp) owns classes grp, grp+8, grp+16 of its pixel
+    for (int it = 0; it < kTilePix / 32; ++it) {
+        const int pix = (t7 & 15) + 16 * (2 * it + half), p = p0 + pix;
         if (p < P) {
             float z_own = 0.f, z_oth = 0.f, a2 = 0.f;
             uint32_t mask = 0u;
@@ -802,8 +812,8 @@ __global__ void __launch_bounds__(kNceThreads) nce_pixel_tile_kernel(NceParams p
     __syncthreads();
     float cross = 0.f, cross2 = 0.f;
     if (grp == 0) {
-        for (int sub = 0; sub < kTilePix / 16; ++sub) {
-            const int pix = threadIdx.x + 16 * sub, p = p0 + pix;
+        for (int it = 0; it < kTilePix / 32; ++it) {
+            const int pix = t7 + 16 * (2 * it + half), p = p0 + pix;
             if (p >= P) continue;
             float z_own = 0.f, z_oth = 0.f, a2 = 0.f;
             uint32_t mask = 0u;
@@ -825,18 +835,20 @@ __global__ void __launch_bounds__(kNceThreads) nce_pixel_tile_kernel(NceParams p
             atomicAdd(&s_cls[lo], 1);
         }
     }
-    if (threadIdx.x < 32) {
+    // the pixel threads are lanes 0-15 of warps 0 and 4: a shuffle tree in each, then a fixed-order add
+    if (t7 < 32) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             cross += __shfl_xor_sync(0xffffffffu, cross, o);
             cross2 += __shfl_xor_sync(0xffffffffu, cross2, o);
         }
-        if (threadIdx.x == 0) {
-            V.partial[tile * 4 + 0] = cross;
-            V.partial[tile * 4 + 1] = cross2;
-        }
+        if (t7 == 0) { s_cross[half][0] = cross; s_cross[half][1] = cross2; }
     }
-    __syncthreads();                                           // s_x / s_sc / s_part are rewritten by the next tile
+    __syncthreads();                                           // also: s_x / s_sc / s_part are rewritten by the next tile
+    if (threadIdx.x == 0) {
+        V.partial[tile * 4 + 0] = s_cross[0][0] + s_cross[1][0];
+        V.partial[tile * 4 + 1] = s_cross[0][1] + s_cross[1][1];
+    }
     }
     if (threadIdx.x < C && s_cls[threadIdx.x] > 0) atomicAdd(&V.cls_count[threadIdx.x], s_cls[threadIdx.x]);
 }
@@ -1573,12 +1585,12 @@ static int contrast_loss_impl(const float* x1, const float* x2, const float* pro
         int dev = 0, sms = 0, occ_a = 1, occ_c = 1;
         WSEGK_CUDA_OK(cudaGetDevice(&dev));
         WSEGK_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        WSEGK_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_a, nce_pixel_tile_kernel, kNceThreads, tile_pix_smem));
+        WSEGK_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_a, nce_pixel_tile_kernel, kPixTileThreads, tile_pix_smem));
         WSEGK_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, nce_grad_kernel<kGradTilePix>,
                                                                     kGradTilePix * kNceGroups, tile_grad_smem));
         grid_a = std::min(prm.nblk, std::max(1, sms * occ_a));
         grid_c = std::min(prm.nblk_grad, std::max(1, sms * occ_c));
-        nce_pixel_tile_kernel<<<dim3(grid_a, 2), kNceThreads, tile_pix_smem, stream>>>(prm);
+        nce_pixel_tile_kernel<<<dim3(grid_a, 2), kPixTileThreads, tile_pix_smem, stream>>>(prm);
     } else {
         WSEGK_CUDA_OK(cudaFuncSetAttribute(nce_pixel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            static_cast<int>(proto_smem)));
