@@ -28,9 +28,6 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_fence_init() {
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
-}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes)
                  : "memory");
@@ -116,44 +113,7 @@ __device__ __forceinline__ void tma_load_1d(uint32_t dst_smem, const void* src, 
 #ifndef WSEGK_TMA_SPLIT
 #define WSEGK_TMA_SPLIT 2048u
 #endif
-__device__ __forceinline__ void tma_load_1d_split(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
-    const uint8_t* s = static_cast<const uint8_t*>(src);
-    uint32_t off = 0;
-    while (off < bytes) {
-        const uint32_t n = (bytes - off < WSEGK_TMA_SPLIT) ? (bytes - off) : WSEGK_TMA_SPLIT;
-        tma_load_1d(dst_smem + off, s + off, n, bar);
-        off += n;
-    }
-}
-// shared -> global bulk store (bulk async-group completion)
-__device__ __forceinline__ void tma_store_1d(void* dst, uint32_t src_smem, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(dst),
-                 "r"(src_smem), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() {
-    asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
-}
-__device__ __forceinline__ void tma_store_wait_all() {
-    asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
-}
-__device__ __forceinline__ void fence_proxy_async_smem() {
-    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-}
 
-// ------------------------------------------------------------------ TMEM allocation
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(dst_smem),
-                 "r"(ncols)
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_relinquish() {
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(ncols)
-                 : "memory");
-}
 __device__ __forceinline__ void tc_fence_before() {
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
 }
@@ -187,31 +147,6 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_ma
            (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
-// D[tmem] (+)= A[smem] * B[smem]        (issued by ONE thread)
-__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
-                                        uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
-        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// D[tmem] (+)= A[tmem] * B[smem]
-__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
-                                        uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
-        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// mbarrier arrive once every tcgen05 op previously issued by this thread has completed
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar)
-                 : "memory");
-}
 
 // ------------------------------------------------------------------ CTA-pair (cta_group::2) variants
 // TMEM allocation for a CTA pair: one warp of EACH CTA executes it with the same shared-memory offset.
@@ -306,11 +241,6 @@ __device__ __forceinline__ void tmem_st_wait() {
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     uint32_t d;
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;\n" : "=r"(d) : "f"(hi), "f"(lo));
-    return d;
-}
-__device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
-    uint32_t d;
-    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;\n" : "=r"(d) : "f"(hi), "f"(lo));
     return d;
 }
 
