@@ -96,12 +96,12 @@ class HotPath:
             prio = int(os.environ.get("WSEG_BENCH_PRIO", "1"))
             # the view-1 chain (K1a -> K2 fwd -> K1b -> K2 bwd) is the critical path: its stream gets the higher priority
             self._streams = [torch.cuda.Stream(device=self.dev, priority=-1 if prio else 0)] + \
-                            [torch.cuda.Stream(device=self.dev) for _ in range(3)]
-        s1, s2, s3, s4 = self._streams
+                            [torch.cuda.Stream(device=self.dev) for _ in range(4)]
+        s1, s2, s3, s4, s5 = self._streams
         outer = torch.cuda.current_stream(self.dev)
         fork = torch.cuda.Event()
         fork.record(outer)
-        for s in (s1, s2, s3, s4):
+        for s in (s1, s2, s3, s4, s5):
             s.wait_event(fork)
         keep = []
         cur = s1
@@ -114,9 +114,18 @@ class HotPath:
             return g
 
         # ---- view 1: K1a + K2 forward
-        rv1, ws1, camn1 = ops.pcm_forward_logits(d["cam1"], d["f1"])          # K1a fused into the PCM's operand preparation
+        # K1a fused into the PCM's operand preparation.  In precise mode the sign fix-up of the forward (the fp32
+        # re-evaluation of the near-zero entries of S, only the backward needs it) runs on its own stream beside K1b
+        defer = ops.get_pcm_mode() == "precise" and os.environ.get("WSEG_BENCH_DEFER_FIXUP", "1") == "1"
+        rv1, ws1, camn1 = ops.pcm_forward_logits(d["cam1"], d["f1"], defer_fixup=defer)
         f1_done = torch.cuda.Event()
         f1_done.record(cur)
+        fix1_done = torch.cuda.Event()
+        with torch.cuda.stream(s5):
+            if defer:
+                s5.wait_event(f1_done)
+                ops.pcm_sign_fixup(ws1, self.n, C_CLS, K_PCM, VIEW1[0] // 8, VIEW1[1] // 8)
+            fix1_done.record(s5)
         # ---- view 2 chain: K1a, K2 forward, its seeds and prototypes, then K1b(cam_rv2) and K2 backward
         with torch.cuda.stream(s2):
             rv2, ws2, camn2 = ops.pcm_forward_logits(d["cam2"], d["f2"])
@@ -149,6 +158,7 @@ class HotPath:
             s4_done.record(s4)
         # ---- view 1: K1b on cam_rv, then K2 backward
         g_rv1 = k1b("rv1_full", VIEW2, "g_rv1")
+        s1.wait_event(fix1_done)
         gf1 = ops.pcm_backward(d["f1"], camn1, rv1, d["g_rv_down1"], ws1)
         s1_done = torch.cuda.Event()
         s1_done.record(s1)

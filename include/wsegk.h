@@ -64,15 +64,15 @@ int wsegk_cam_norm_fwd(const float* cam, float* cam_norm, int N, int C, int h, i
 /* K2 forward — replaces network/resnet38_contrast.py:70-73 (PCM after the f9 conv):
  *   fh = f/(|f|_2+1e-5); aff = relu(fh^T fh); aff /= colsum(aff)+1e-5; cam_rv = cam_norm @ aff.
  * f [N,K,h,w], cam_norm [N,C,h,w] -> cam_rv [N,C,h,w].  The HWxHW affinity lives only in TMEM.
- * FP16 tensor-core operands (hi+lo pairs in precise mode, see wsegk_pcm_set_mode), FP32 accumulation.
+ * FP16 tensor-core operands, FP32 accumulation; in precise mode (see wsegk_pcm_set_mode) the entries of S too close to
+ * zero for their sign to survive the FP16 rounding are re-evaluated in fp32 before the sign mask is handed to pcm_bwd.
  * K % 32 == 0, K <= 192, C <= 23.  The workspace is left holding what pcm_bwd needs (normalised features,
  * norms, column sums and the sign bits of S). */
 int wsegk_pcm_fwd(const float* f, const float* cam_norm, float* cam_rv, int N, int C, int K, int h, int w,
                   void* workspace, size_t workspace_bytes, wsegk_stream_t stream);
 
-/* K2 forward when NO backward will follow (contrast_infer.py, torch.no_grad): always single FP16 products — the sign
- * mask that the split products protect is only consumed by pcm_bwd; cam_rv is within 1e-3 either way.  The workspace
- * it leaves must not be handed to pcm_bwd. */
+/* K2 forward when NO backward will follow (contrast_infer.py, torch.no_grad): no sign mask is produced (only pcm_bwd
+ * consumes it); cam_rv is identical.  The workspace it leaves must not be handed to pcm_bwd. */
 int wsegk_pcm_fwd_infer(const float* f, const float* cam_norm, float* cam_rv, int N, int C, int K, int h, int w,
                         void* workspace, size_t workspace_bytes, wsegk_stream_t stream);
 
@@ -89,6 +89,24 @@ int wsegk_pcm_fwd_logits(const float* f, const float* cam_logits, float* cam_nor
 int wsegk_pcm_bwd(const float* f, const float* cam_norm, const float* cam_rv, const float* grad_cam_rv,
                   float* grad_f, int N, int C, int K, int h, int w, void* workspace, size_t workspace_bytes,
                   wsegk_stream_t stream);
+
+/* The same two operations with the precision mode given PER CALL instead of through the calling thread's default
+ * (wsegk_pcm_set_mode) — what a caller with several host threads (torch.nn.DataParallel's parallel_apply,
+ * contrast_train.py:108; the thread pool of contrast_infer.py:58-71) should use.
+ *   flags: WSEGK_PCM_PRECISE      exact sign mask + split backward factors (the default mode); 0 = "fast"
+ *          WSEGK_PCM_DEFER_FIXUP  (forward, precise only) do not run the sign fix-up inside this call: the caller enqueues
+ *                                 wsegk_pcm_sign_fixup on the same workspace — e.g. on a side stream, off the critical path —
+ *                                 any time after this call and before pcm_bwd.
+ *   pcm_fwd_ex: cam_norm_out == NULL: `cam` is the normalised CAM (as wsegk_pcm_fwd); otherwise `cam` holds the raw logits
+ *               and cam_norm_out receives the normalised CAM (as wsegk_pcm_fwd_logits).
+ *   pcm_bwd_ex: pass the flags of the forward that filled the workspace. */
+enum wsegk_pcm_flags { WSEGK_PCM_PRECISE = 1, WSEGK_PCM_DEFER_FIXUP = 2 };
+int wsegk_pcm_fwd_ex(const float* f, const float* cam, float* cam_norm_out, float* cam_rv, int N, int C, int K, int h, int w,
+                     void* workspace, size_t workspace_bytes, int flags, wsegk_stream_t stream);
+int wsegk_pcm_sign_fixup(int N, int C, int K, int h, int w, void* workspace, size_t workspace_bytes, wsegk_stream_t stream);
+int wsegk_pcm_bwd_ex(const float* f, const float* cam_norm, const float* cam_rv, const float* grad_cam_rv, float* grad_f,
+                     int N, int C, int K, int h, int w, void* workspace, size_t workspace_bytes, int flags,
+                     wsegk_stream_t stream);
 
 /* K1b forward — replaces tool/visualization.py:62-67 + contrast_train.py:145-152 / 157-158:
  *   y = relu(relu(p)-min-1e-5)/(max-min+1e-5) per (n,c) plane; bilinear(align_corners) to (oh,ow); * label.
@@ -259,26 +277,28 @@ int wsegk_sgd_step(float* const* params, const float* const* grads, float* const
 unsigned long long wsegk_debug_launch_count(void);
 int wsegk_debug_pcm_profile(int enable);
 int wsegk_debug_pcm_main_ms(float* fwd_ms, float* bwd_ms);
+int wsegk_debug_pcm_fixup_ms(float* fix_ms);   /* the same for the sign fix-up kernel of the precise forward */
 /* Timeline aid: when non-null (per host thread), CTA (0,0,0) of the next pcm_fwd main kernels writes clock64() stamps
  * into this DEVICE buffer of 768 int64: [role 0 producer | 1 MMA issuer | 2 first TMEM warp][stage < 64][4 events]. */
 int wsegk_debug_pcm_trace(long long* device_buffer);
 /* Test aid (host only, no GPU needed): the (unit, stage, segment, partial slot) quadruples CTA pair g of the persistent PCM
  * kernels runs for N images on an h x w grid; returns their number (0 for g beyond the grid). */
 int wsegk_debug_pcm_schedule(int N, int h, int w, int g, int* out, int capacity);
-/* Test aid, process-wide: when on, wsegk_proto_topk_local and wsegk_contrast_loss_fwd_bwd take their large-plane paths
+/* Test aid, per host thread: when on, wsegk_proto_topk_local and wsegk_contrast_loss_fwd_bwd take their large-plane paths
  * (multi-CTA radix select, csrc/segselect.cuh) whatever the size, so both paths can be compared on the same inputs.
  * By default K3 switches above 8192 pixels and the mining of K4 above 16384. */
 int wsegk_debug_force_radix(int on);
 
-/* PCM precision mode, process-wide (default 1):
- *   1 "precise": FP16 hi+lo split operands, S = hi.hi + hi.lo + lo.hi (~2^-21), backward factors split in BF16;
- *                the sign mask of S that the backward consumes then agrees with an FP32 evaluation.
- *   0 "fast"   : single FP16 / BF16 products (cam_rv still within 1e-3; gradient terms with |S| < ~1e-4 may flip). */
+/* PCM precision mode used by the entry points without a `flags` argument, per HOST THREAD (default 1):
+ *   1 "precise": S from single FP16 products; the entries with |S| below the bound of the operand-rounding error (~0.2 %)
+ *                are re-evaluated in fp32 (pcm_sign_fixup_kernel), so the sign mask of S that the backward consumes agrees
+ *                with an FP32 evaluation; backward factors split in BF16 (hi + lo).
+ *   0 "fast"   : no re-evaluation, single BF16 factor products (cam_rv identical; gradient terms with |S| < ~1e-4 may flip). */
 int wsegk_pcm_set_mode(int mode);
 int wsegk_pcm_get_mode(void);
 
 /* Test aid: byte offsets of the PCM workspace sections, in the order
- * {fa_hi, fa_lo, fb_hi, fb_lo, camb, inv_norm, dsum, part, mask, ua, vb, dfhat, bound, total_bytes, nsplit, PJ, HWpj,
+ * {fa, fh32, fb, nzmask, camb, inv_norm, dsum, part, mask, ua, vb, dfhat, bound, total_bytes, nsplit, PJ, HWpj,
  *  wb, NS, HWpi}.  Returns how many were written. */
 int wsegk_debug_pcm_layout(int N, int C, int K, int h, int w, size_t* out, int n_out);
 

@@ -41,7 +41,8 @@ def test_version_and_workspace_sizes(lib):
     lay = ops.pcm_layout(8, 21, 192, 56, 56)
     # 56x56 = 3136 pixels: 13 CTA pairs of 256 rows, B tiles of 56 rows -> 28 stages of 112 columns, no padding along i
     assert (lay["PJ"], lay["HWpj"], lay["wb"], lay["NS"], lay["HWpi"]) == (13, 3328, 56, 28, 3136)
-    assert lay["bytes"] == pcm and lay["fa_lo"] - lay["fa_hi"] == 8 * 26 * 128 * 192 * 2
+    assert lay["bytes"] == pcm and lay["fh32"] - lay["fa"] == 8 * 26 * 128 * 192 * 2
+    assert lay["fb"] - lay["fh32"] == 8 * 3328 * 192 * 4 and lay["camb"] - lay["nzmask"] == 8 * 28 * 3328 * 16
     lay = ops.pcm_layout(1, 21, 192, 64, 64)
     assert (lay["wb"], lay["NS"], lay["HWpi"]) == (64, 32, 4096)
     assert _lib.workspace_bytes(_lib.OP_CONTRAST_LOSS, N=8, C=21, D=128, h=16, w=16) > 2 * 2048 * 4 * 42

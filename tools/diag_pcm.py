@@ -37,12 +37,22 @@ def run(n, h, w, k=192, c=21, seed=0, positive=False, time_it=True):
     fhp = torch.zeros(n, max(HWpj, HWpi), k, device=dev, dtype=torch.float64)
     fhp[:, :HW] = fh.transpose(1, 2)
     hi = fhp.float().half().double()
-    a_hi = decode_tiles(section(ws, lay, "fa_hi", n * 2 * PJ * 128 * k * 2), n, 2 * PJ, 128, k).double()
-    b_hi = decode_tiles(section(ws, lay, "fb_hi", n * 2 * NS * wb * k * 2), n, 2 * NS, wb, k).double()
-    print(f"  prep: A-hi err {(a_hi - hi[:, :HWpj]).abs().max().item():.2e}  B-hi err {(b_hi - hi[:, :HWpi]).abs().max().item():.2e}")
+    a_hi = decode_tiles(section(ws, lay, "fa", n * 2 * PJ * 128 * k * 2), n, 2 * PJ, 128, k).double()
+    b_hi = decode_tiles(section(ws, lay, "fb", n * 2 * NS * wb * k * 2), n, 2 * NS, wb, k).double()
+    print(f"  prep: A err {(a_hi - hi[:, :HWpj]).abs().max().item():.2e}  B err {(b_hi - hi[:, :HWpi]).abs().max().item():.2e}")
     if mode == "precise":
-        a_lo = decode_tiles(section(ws, lay, "fa_lo", n * 2 * PJ * 128 * k * 2), n, 2 * PJ, 128, k).double()
-        print(f"  prep: hi+lo residual {(a_hi + a_lo - fhp[:, :HWpj]).abs().max().item():.2e} (hi alone {(a_hi - fhp[:, :HWpj]).abs().max().item():.2e})")
+        f32 = section(ws, lay, "fh32", n * HWpj * k * 4).view(torch.float32).reshape(n, HWpj, k).double()
+        print(f"  prep: fh32 err {(f32 - fhp[:, :HWpj]).abs().max().item():.2e} (fp16 alone {(a_hi - fhp[:, :HWpj]).abs().max().item():.2e})")
+        nz = section(ws, lay, "nzmask", n * NS * HWpj * 16).view(torch.int32).reshape(n, NS, HWpj, 4)
+        order0 = torch.stack([torch.arange(16), torch.arange(16) + 16], 1).reshape(-1).to(dev).int()
+        nzb = ((nz.unsqueeze(-1) >> order0) & 1).reshape(n, NS, HWpj, 128)[..., :2 * wb].permute(0, 2, 1, 3).reshape(n, HWpj, HWpi).bool()
+        Sh = torch.matmul(hi[:, :HWpj], hi[:, :HWpi].transpose(1, 2))
+        S0 = torch.matmul(fhp[:, :HWpj], fhp[:, :HWpi].transpose(1, 2))
+        inside = torch.zeros_like(nzb); inside[:, :HW, :HW] = True
+        print(f"  near-zero mask: {int(nzb.sum())} entries marked ({int(nzb.sum()) / (n * HW * HW):.2e}); outside the image {int((nzb & ~inside).sum())}; "
+              f"max |S_fp16| marked {Sh[nzb].abs().max().item() if int(nzb.sum()) else 0:.2e}; "
+              f"min |S_fp16| unmarked inside {Sh[~nzb & inside].abs().min().item():.2e}; max |S_fp16 - S| {(Sh - S0)[inside].abs().max().item():.2e}")
+        del Sh, S0, nzb
     # ---- S sign mask
     S = torch.matmul(fhp[:, :HWpj], fhp[:, :HWpi].transpose(1, 2))              # [n, j, i] fp64
     mask_raw = section(ws, lay, "mask", n * NS * HWpj * 16).view(torch.int32).reshape(n, NS, HWpj, 4)
@@ -90,7 +100,8 @@ def run(n, h, w, k=192, c=21, seed=0, positive=False, time_it=True):
         ops.pcm_profile(False)
         fl_f = 2.0 * n * HW * HW * (k + c); fl_b = 2.0 * n * HW * HW * (2 * k + c)
         a, b = sum(fw) / len(fw), sum(bw) / len(bw)
-        print(f"  main kernels: fwd {a * 1e3:.1f} us ({fl_f / a / 1e9:.0f} TF/s alg)  bwd {b * 1e3:.1f} us ({fl_b / b / 1e9:.0f} TF/s alg)")
+        print(f"  main kernels: fwd {a * 1e3:.1f} us ({fl_f / a / 1e9:.0f} TF/s alg)  bwd {b * 1e3:.1f} us ({fl_b / b / 1e9:.0f} TF/s alg)"
+              f"  sign fix-up {ops.pcm_fixup_ms() * 1e3:.1f} us")
 
 
 CASES = {

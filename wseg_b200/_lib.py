@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libwsegk.so")
 
 OP_CAM_NORM, OP_PCM, OP_FULLRES_NORM, OP_SEED_LABELS, OP_PROTO, OP_CONTRAST_LOSS, OP_SELECT, OP_ER_ECR = 1, 2, 3, 4, 5, 6, 7, 8
 OP_LAZY_BWD = 9
+PCM_PRECISE, PCM_DEFER_FIXUP = 1, 2
 
 _P = c_void_p
 _SIGNATURES = {
@@ -22,6 +23,7 @@ _SIGNATURES = {
     "wsegk_debug_launch_count": (ctypes.c_ulonglong, []),
     "wsegk_debug_pcm_profile": (c_int, [c_int]),
     "wsegk_debug_pcm_main_ms": (c_int, [ctypes.POINTER(c_float), ctypes.POINTER(c_float)]),
+    "wsegk_debug_pcm_fixup_ms": (c_int, [ctypes.POINTER(c_float)]),
     "wsegk_debug_pcm_trace": (c_int, [_P]),
     "wsegk_debug_force_radix": (c_int, [c_int]),
     "wsegk_debug_pcm_schedule": (c_int, [c_int, c_int, c_int, c_int, _P, c_int]),
@@ -32,6 +34,9 @@ _SIGNATURES = {
     "wsegk_pcm_fwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
     "wsegk_pcm_fwd_infer": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
     "wsegk_pcm_fwd_logits": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
+    "wsegk_pcm_fwd_ex": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, c_int, _P]),
+    "wsegk_pcm_sign_fixup": (c_int, [c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
+    "wsegk_pcm_bwd_ex": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, c_int, _P]),
     "wsegk_pcm_bwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
     "wsegk_fullres_norm_fwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
     "wsegk_fullres_norm_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P,

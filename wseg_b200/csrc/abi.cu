@@ -53,8 +53,10 @@ int check_device() {
     return WSEGK_OK;
 }
 
-static std::atomic<int> g_pcm_mode{1};
-int pcm_mode() { return g_pcm_mode.load(std::memory_order_relaxed); }
+// default mode of the entry points that do not take flags: per HOST THREAD, so that concurrent callers (DataParallel's
+// parallel_apply, the thread pool of contrast_infer.py) cannot change each other's mode
+static thread_local int g_pcm_mode = 1;
+int pcm_mode() { return g_pcm_mode; }
 
 // B-tile rows per CTA: the candidate that pads the i sweep least (ties: the larger tile, fewer stages).
 static int pick_wb(int HW) {
@@ -108,10 +110,10 @@ PcmPlan make_pcm_plan(void* ws, int N, int C, int K, int h, int w, int precise) 
     p.b_tile_bytes = static_cast<size_t>(p.wb) * K * 2;
     Carver c(ws);
     const size_t at = static_cast<size_t>(N) * 2 * p.PJ, bt = static_cast<size_t>(N) * 2 * p.NS;
-    p.fa_hi = c.take<uint16_t>(at * kTile * K);
-    p.fa_lo = c.take<uint16_t>(at * kTile * K);
-    p.fb_hi = c.take<uint16_t>(bt * p.wb * K);
-    p.fb_lo = c.take<uint16_t>(bt * p.wb * K);
+    p.fa = c.take<uint16_t>(at * kTile * K);
+    p.fh32 = c.take<float>(static_cast<size_t>(N) * p.HWpj * K);
+    p.fb = c.take<uint16_t>(bt * p.wb * K);
+    p.nzmask = c.take<uint32_t>(static_cast<size_t>(N) * p.NS * p.HWpj * kMaskWords);
     p.camb = c.take<uint16_t>(static_cast<size_t>(N) * p.NS * 2 * (2 * p.wb) * kCamRows);
     p.inv_norm = c.take<float>(static_cast<size_t>(N) * p.HWpj);
     p.dsum = c.take<float>(static_cast<size_t>(N) * p.HWpj);
@@ -168,7 +170,7 @@ extern "C" int wsegk_pcm_set_mode(int mode) {
         set_error("pcm_set_mode: mode must be 0 (fast) or 1 (precise), got %d", mode);
         return WSEGK_ERR_BAD_SHAPE;
     }
-    g_pcm_mode.store(mode, std::memory_order_relaxed);
+    g_pcm_mode = mode;
     return WSEGK_OK;
 }
 
@@ -178,7 +180,7 @@ extern "C" int wsegk_debug_pcm_layout(int N, int C, int K, int h, int w, size_t*
     if (!out || N <= 0 || h <= 0 || w <= 0) return 0;
     PcmPlan p = make_pcm_plan(nullptr, N, C, K, h, w, 1);
     auto off = [](const void* q) { return reinterpret_cast<size_t>(q); };   // base is nullptr => offsets
-    const size_t v[20] = {off(p.fa_hi), off(p.fa_lo), off(p.fb_hi), off(p.fb_lo), off(p.camb), off(p.inv_norm),
+    const size_t v[20] = {off(p.fa), off(p.fh32), off(p.fb), off(p.nzmask), off(p.camb), off(p.inv_norm),
                           off(p.dsum), off(p.part), off(p.mask), off(p.ua), off(p.vb), off(p.dfhat), off(p.bound),
                           p.bytes, static_cast<size_t>(p.nsplit), static_cast<size_t>(p.PJ),
                           static_cast<size_t>(p.HWpj), static_cast<size_t>(p.wb), static_cast<size_t>(p.NS),

@@ -18,6 +18,9 @@ constexpr int kAugK = 48;         // PCM backward rank-(2C+2) factor, padded to 
 constexpr int kMaxClasses = 23;   // 2C + 2 <= kAugK
 constexpr int kMaxPcmK = 192;
 constexpr int kMaskWords = 4;     // sign-mask words per (stage, row): up to 128 columns
+constexpr int kBoundLo2 = 8;      // slot of PcmPlan::bound holding the largest squared fp16 rounding residual of a pixel
+// PCM call flags (include/wsegk.h: WSEGK_PCM_*)
+constexpr int kPcmPrecise = 1, kPcmDeferFixup = 2;
 
 void set_error(const char* fmt, ...);
 void count_launches(int n);   // diagnostics: wsegk_debug_launch_count()
@@ -83,11 +86,13 @@ struct PcmPlan {
     int HWpi;        // NS * 2 * wb
     int G;           // CTA pairs of the persistent main kernels (stream-K over all N*PJ*NS stages)
     int nsplit;      // partial-result slots per unit = the most CTA pairs that share one (image, j pair) sweep
-    int precise;     // 1: fp16 hi+lo split operands (3 S products, 3 T products); 0: single pass
+    int precise;     // 1: exact sign mask (near-zero entries of S re-evaluated in fp32) + split backward factors; 0: single pass
     size_t a_tile_bytes, b_tile_bytes;
     // sections
-    uint16_t* fa_hi;  uint16_t* fa_lo;    // [N][2*PJ] A tiles of normalised features (fp16 hi / residual)
-    uint16_t* fb_hi;  uint16_t* fb_lo;    // [N][2*NS] B tiles (wb rows) of the same
+    uint16_t* fa;                          // [N][2*PJ] A tiles (128 rows) of the normalised features, fp16
+    uint16_t* fb;                          // [N][2*NS] B tiles (wb rows) of the same
+    float* fh32;                           // [N][HWpj][K] normalised features, fp32, pixel-major (precise mode: sign fix-up)
+    uint32_t* nzmask;                      // [N][NS][HWpj][4] bit = |S| below the fp16-rounding threshold (precise mode)
     uint16_t* camb;                        // [N][NS][2 ranks][2wb/8][32 rows][8] fp16 cam operand blocks
     float* inv_norm;                       // [N][HWpj]   1/(|f|+1e-5)
     float* dsum;                           // [N][HWpj]   column sums of relu(S) + 1e-5
@@ -96,7 +101,7 @@ struct PcmPlan {
     uint16_t* ua;                          // [N][2*PJ] A tiles [128 x Ku] bf16 backward factor U
     uint16_t* vb;                          // [N][2*NS] B tiles [wb x Ku] bf16 backward factor V
     float* dfhat;                          // [N][nsplit][K][HWpj] fp32 partial gradient w.r.t. normalised features
-    float* bound;                          // [1] upper bound of |T| (as float bits, atomicMax)
+    float* bound;                          // [0] upper bound of |T|, [kBoundLo2] max_p |fh_p - fp16(fh_p)|^2 (float bits, atomicMax)
     float* peak;                           // [N][C] per-plane maxima of relu(cam) + 1e-5 (pcm_fwd_logits: fused K1a)
     int Ku;                                // 48 (fast) or 144 (precise: [hi|hi|lo] x [hi|lo|hi])
     size_t bytes;

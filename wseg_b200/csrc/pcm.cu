@@ -45,17 +45,20 @@ __device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
     return static_cast<uint32_t>(__half_as_ushort(a)) | (static_cast<uint32_t>(__half_as_ushort(b)) << 16);
 }
 
-// f [N,K,HW] fp32 -> normalised features as A tiles (128 rows) and B tiles (wb rows), FP16 hi (+ lo), + inv_norm.
+// f [N,K,HW] fp32 -> normalised features as A tiles (128 rows) and B tiles (wb rows) in FP16, + inv_norm.
 // One CTA per (128 pixels, image), 256 threads: thread (pixel, half) keeps its K/2 channel values in registers
 // (channel groups half, half+2, ...), so global loads are coalesced along the pixel axis, the 16-byte chunks a thread
 // writes are already in tile order (row = pixel), and no shared-memory transpose is needed.
-template <bool kLo>
-__device__ __forceinline__ void pcm_prep_f_body(const float* __restrict__ f, uint4* __restrict__ fa_hi,
-                                                uint4* __restrict__ fa_lo, uint4* __restrict__ fb_hi,
-                                                uint4* __restrict__ fb_lo, float* __restrict__ inv_norm,
-                                                int K, int HW, int PJ, int NS, int wb, int t, int n) {
+// kPrecise: also the fp32 values pixel-major (fh32 [n][p][K], what pcm_sign_fixup_kernel re-evaluates S from) and the
+// batch maximum of |fh_p - fp16(fh_p)|^2 (lo2max, atomicMax on the float bits) that sets the fix-up threshold.
+template <bool kPrecise>
+__device__ __forceinline__ void pcm_prep_f_body(const float* __restrict__ f, uint4* __restrict__ fa, uint4* __restrict__ fb,
+                                                float* __restrict__ fh32, unsigned int* __restrict__ lo2max,
+                                                float* __restrict__ inv_norm, int K, int HW, int PJ, int NS, int wb,
+                                                int t, int n) {
     constexpr int GMAX = kMaxPcmK / 16;          // channel groups per thread
     __shared__ float s_part[2][kTile];
+    __shared__ float s_lo2[2][kTile];
     const int px = threadIdx.x & 127, half = threadIdx.x >> 7;
     const int p = t * kTile + px;
     const int HWpj = PJ * 2 * kTile, HWpi = NS * 2 * wb;
@@ -81,28 +84,40 @@ __device__ __forceinline__ void pcm_prep_f_body(const float* __restrict__ f, uin
     const int tb = p / wb, rb = p - tb * wb;
     const size_t base_a = (static_cast<size_t>(n) * 2 * PJ + t) * groups * kTile + px;
     const size_t base_b = (static_cast<size_t>(n) * 2 * NS + tb) * groups * wb + rb;
+    float4* dst32 = reinterpret_cast<float4*>(fh32 + (static_cast<size_t>(n) * HWpj + p) * K);
+    float lo2 = 0.f;
 #pragma unroll
     for (int gi = 0; gi < GMAX; ++gi) {
         const int g = half + 2 * gi;
         if (g >= groups) break;
-        __half hi[8], lo[8];
+        __half hi[8];
+        float x[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            const float x = v[gi][e] * inv;
-            hi[e] = __float2half_rn(x);
-            lo[e] = __float2half_rn(x - __half2float(hi[e]));
+            x[e] = v[gi][e] * inv;
+            hi[e] = __float2half_rn(x[e]);
+            const float lo = x[e] - __half2float(hi[e]);
+            lo2 = fmaf(lo, lo, lo2);
         }
         const uint4 ohi = make_uint4(pack_h2(hi[0], hi[1]), pack_h2(hi[2], hi[3]), pack_h2(hi[4], hi[5]),
                                      pack_h2(hi[6], hi[7]));
-        const uint4 olo = make_uint4(pack_h2(lo[0], lo[1]), pack_h2(lo[2], lo[3]), pack_h2(lo[4], lo[5]),
-                                     pack_h2(lo[6], lo[7]));
         if (in_a) {
-            fa_hi[base_a + static_cast<size_t>(g) * kTile] = ohi;
-            if (kLo) fa_lo[base_a + static_cast<size_t>(g) * kTile] = olo;
+            fa[base_a + static_cast<size_t>(g) * kTile] = ohi;
+            if (kPrecise) {
+                dst32[2 * g] = make_float4(x[0], x[1], x[2], x[3]);
+                dst32[2 * g + 1] = make_float4(x[4], x[5], x[6], x[7]);
+            }
         }
-        if (in_b) {
-            fb_hi[base_b + static_cast<size_t>(g) * wb] = ohi;
-            if (kLo) fb_lo[base_b + static_cast<size_t>(g) * wb] = olo;
+        if (in_b) fb[base_b + static_cast<size_t>(g) * wb] = ohi;
+    }
+    if (kPrecise) {
+        s_lo2[half][px] = lo2;
+        __syncthreads();
+        if (half == 0) {
+            float m = s_lo2[0][px] + s_lo2[1][px];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(lo2max, __float_as_uint(m));   // non-negative floats order like their bits
         }
     }
 }
@@ -175,15 +190,15 @@ __device__ __forceinline__ void pcm_prep_cam_body(const float* __restrict__ cam,
 
 // both operand preparations in ONE launch (they are independent; as two launches the 7 us cam preparation sat on the
 // critical path behind the feature preparation): blocks [0, tiles) prepare features, blocks [tiles, tiles + NS) cam blocks
-template <bool kLo, bool kLogits>
-__global__ void __launch_bounds__(256) pcm_prep_kernel(const float* __restrict__ f, uint4* __restrict__ fa_hi,
-                                                       uint4* __restrict__ fa_lo, uint4* __restrict__ fb_hi,
-                                                       uint4* __restrict__ fb_lo, float* __restrict__ inv_norm,
+template <bool kPrecise, bool kLogits>
+__global__ void __launch_bounds__(256) pcm_prep_kernel(const float* __restrict__ f, uint4* __restrict__ fa,
+                                                       uint4* __restrict__ fb, float* __restrict__ fh32,
+                                                       unsigned int* __restrict__ lo2max, float* __restrict__ inv_norm,
                                                        const float* __restrict__ cam, const float* __restrict__ peak,
                                                        float* __restrict__ cam_norm_out, uint4* __restrict__ camb, int C,
                                                        int K, int HW, int PJ, int NS, int wb, int tiles) {
     if (static_cast<int>(blockIdx.x) < tiles)
-        pcm_prep_f_body<kLo>(f, fa_hi, fa_lo, fb_hi, fb_lo, inv_norm, K, HW, PJ, NS, wb, blockIdx.x, blockIdx.y);
+        pcm_prep_f_body<kPrecise>(f, fa, fb, fh32, lo2max, inv_norm, K, HW, PJ, NS, wb, blockIdx.x, blockIdx.y);
     else
         pcm_prep_cam_body<kLogits>(cam, peak, cam_norm_out, camb, C, HW, NS, wb, static_cast<int>(blockIdx.x) - tiles,
                                    blockIdx.y);
@@ -192,37 +207,101 @@ __global__ void __launch_bounds__(256) pcm_prep_kernel(const float* __restrict__
 // ------------------------------------------------------------------------------------------------
 // forward main kernel (CTA pair)
 // ------------------------------------------------------------------------------------------------
-// warp 0: bulk-copy producer A, warp 1: MMA issuer (leader CTA) / relay (peer CTA), warps 2-5: TMEM warps,
-// warps 6-7: bulk-copy producers B and C.  One warp keeps only ~2 bulk copies in flight (tools/ubench/bulkcp2.cu:
-// 630 clk per copy per issuing warp whatever its size, perfectly overlapped across warps), so every stream of
-// tiles gets its own issuing warp.
-constexpr int kMainThreads = 256;
+// 12 warps.  warp 0: bulk-copy producer of the feature tiles, warp 1: MMA issuer (leader CTA) / relay (peer CTA),
+// warp 2: bulk-copy producer of the cam blocks, warp 3: idle, warps 4-11: TMEM warps — two per TMEM lane quarter
+// (a warp may only touch lanes 32*(warp%4) ..), the first converts S columns [0,64) of its 32 rows, the second the rest.
+// One warp keeps only ~2 bulk copies in flight (tools/ubench/bulkcp2.cu: 630 clk per copy per issuing warp whatever its
+// size, perfectly overlapped across warps), so every stream of tiles gets its own issuing warp.
+//
+// MODE 0 (inference): P = relu(S) only.  MODE 1 ("fast"): + the sign bits of S for the backward.  MODE 2 ("precise"):
+// + a second bit per entry, |S| < tau, where tau bounds what the FP16 rounding of the operands can do to S; those entries
+// (~0.2 %) are re-evaluated in fp32 by pcm_sign_fixup_kernel, which patches the sign mask.  Round 1 got the same signs from
+// three MMA chains (hi*hi + hi*lo + lo*hi): 3x the tensor work for a correction that matters for 1e-4 of the entries.
+constexpr int kMainThreads = 256;      // backward main kernel
+constexpr int kFwdThreads = 384;
+constexpr int kFwdTmemWarp0 = 4;       // first TMEM warp of the forward kernel
+constexpr int kFStages = 4;
 constexpr int kCamStages = 4;
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColO = 256;     // forward: 64 fp32 columns [num_hi | colsum | num_lo]
 constexpr uint32_t kColG = 256;     // backward: K (<= 192) fp32 columns dFh accumulator
+constexpr int kSplitCol = 64;       // S columns [0,64) belong to the first TMEM warp of a quarter, [64, NCOL) to the second
 
-template <bool PRECISE> struct FwdCfg { static constexpr int kFStages = PRECISE ? 2 : 4; };
-
-template <int FS>
 struct FwdBars {
     // full_* / fj of the LEADER also count one arrival relayed from the peer CTA ("my copy of this stage landed too")
-    uint64_t fj, a_free, full_f[FS], empty_f[FS], full_c[kCamStages], empty_c[kCamStages], s_full[2], p_full[2], o_full;
+    uint64_t fj, a_free, full_f[kFStages], empty_f[kFStages], full_c[kCamStages], empty_c[kCamStages], s_full[2], p_full[2],
+        o_full;
     uint32_t tmem_base;
 };
 
-// relu + fp16 pack of NV fp32 accumulator values, and their sign bits: bit m = [value 2m > 0], bit 16+m = [value 2m+1 > 0].
-// The bits are taken from the packed halves (adding 0x7fff carries into bit 15 iff the half is non-zero), i.e. "S rounds
-// to a positive fp16" — values below 2^-25 count as zero, far inside the accumulation error of S.
-template <int NV>
-__device__ __forceinline__ uint32_t relu_pack_bits(const uint32_t* r, uint32_t* pk) {
-    uint32_t bits = 0;
+__device__ __forceinline__ __half2 as_half2(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
+
+// NV fp32 accumulator values -> relu as packed fp16 (pk), and per value one bit in `sbits` ([S > 0]) and one in `nbits`
+// ([|S| < tau]): bit m belongs to value 2m, bit 16+m to value 2m+1.  Both tests are made on the fp16-rounded value h
+// (the half2 compares give 0xffff per true half, so a bit is one AND): "S rounds to a positive fp16" — values below
+// 2^-25 count as zero, far inside the accumulation error of S.
+template <int NV, int MODE>
+__device__ __forceinline__ void relu_pack_bits(const uint32_t* r, uint32_t* pk, uint32_t tau2, uint32_t& sbits,
+                                               uint32_t& nbits) {
+    sbits = 0;
+    nbits = 0;
 #pragma unroll
     for (int m = 0; m < NV / 2; ++m) {
-        pk[m] = pack_f16x2_relu(__uint_as_float(r[2 * m]), __uint_as_float(r[2 * m + 1]));
-        bits |= ((pk[m] + 0x7fff7fffu) >> (15 - m)) & (0x00010001u << m);
+        if (MODE == 0) {
+            pk[m] = pack_f16x2_relu(__uint_as_float(r[2 * m]), __uint_as_float(r[2 * m + 1]));
+        } else {
+            const uint32_t h = pack_f16x2(__uint_as_float(r[2 * m]), __uint_as_float(r[2 * m + 1]));
+            const uint32_t pos = __hgt2_mask(as_half2(h), as_half2(0u));
+            pk[m] = h & pos;
+            sbits |= pos & (0x00010001u << m);
+            if (MODE == 2) {
+                const uint32_t far = __hge2_mask(__habs2(as_half2(h)), as_half2(tau2));
+                nbits |= ~far & (0x00010001u << m);
+            }
+        }
     }
-    return bits;
+}
+
+// One TMEM warp's share of a stage: NC (64, 48 or 32) fp32 columns of S at `base` -> packed fp16 relu(S) IN PLACE over the
+// first NC/2 of them (each warp only overwrites columns it has itself loaded, so the two warps of a quarter need no
+// ordering between them), sign / near-zero bits of chunk c (32 columns) in sw[c] / nw[c].
+template <int NC, int MODE>
+__device__ __forceinline__ void convert_cols(uint32_t base, uint32_t tau2, uint32_t (&sw)[2], uint32_t (&nw)[2]) {
+    static_assert(NC == 64 || NC == 48 || NC == 32, "column split");
+    sw[1] = 0;
+    nw[1] = 0;
+    uint32_t r0[32];
+    tmem_ld32(base, r0);
+    if (NC == 64) {
+        uint32_t r1[32], pk[16];
+        tmem_ld32(base + 32, r1);
+        tmem_ld_wait();
+        relu_pack_bits<32, MODE>(r0, pk, tau2, sw[0], nw[0]);
+        tmem_st16(base, pk);
+        relu_pack_bits<32, MODE>(r1, pk, tau2, sw[1], nw[1]);
+        tmem_st16(base + 16, pk);
+    } else if (NC == 48) {
+        uint32_t r1[16], pk[16], pk1[8];
+        tmem_ld16(base + 32, r1);
+        tmem_ld_wait();
+        relu_pack_bits<32, MODE>(r0, pk, tau2, sw[0], nw[0]);
+        tmem_st16(base, pk);
+        relu_pack_bits<16, MODE>(r1, pk1, tau2, sw[1], nw[1]);
+        tmem_st8(base + 16, pk1);
+    } else {
+        uint32_t pk[16];
+        tmem_ld_wait();
+        relu_pack_bits<32, MODE>(r0, pk, tau2, sw[0], nw[0]);
+        tmem_st16(base, pk);
+    }
+}
+
+// bits of a mask word (32 columns, bit m = column 2m, bit 16+m = column 2m+1) whose column is below `nvalid`
+__device__ __forceinline__ uint32_t valid_bits(int nvalid) {
+    if (nvalid >= 32) return 0xffffffffu;
+    if (nvalid <= 0) return 0u;
+    const uint32_t even = (1u << ((nvalid + 1) >> 1)) - 1u, odd = (1u << (nvalid >> 1)) - 1u;
+    return even | (odd << 16);
 }
 
 // ---- stream-K schedule shared by the forward and backward main kernels ---------------------------------------------
@@ -230,26 +309,24 @@ __device__ __forceinline__ uint32_t relu_pack_bits(const uint32_t* r, uint32_t* 
 // contiguous ranges, one per CTA pair, so every pair does the same number of stages whatever N, PJ and NS are (no wave
 // quantisation) and pays ONE prologue/drain.  A range crosses unit boundaries: each (pair, unit) piece is a "segment"
 // with its own A-side tile and its own partial-result slot  slot = pair - (pair owning the unit's first stage).
-template <int WB, bool PRECISE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMainThreads, 1)
-pcm_fwd_kernel(const uint8_t* __restrict__ fa_hi, const uint8_t* __restrict__ fa_lo,
-               const uint8_t* __restrict__ fb_hi, const uint8_t* __restrict__ fb_lo,
-               const uint8_t* __restrict__ camb, float* __restrict__ part, uint4* __restrict__ mask, int K, int PJ,
-               int NS, int n_units, int nslot, long long* __restrict__ trace) {
-    constexpr int FS = FwdCfg<PRECISE>::kFStages;
+template <int WB, int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFwdThreads, 1)
+pcm_fwd_kernel(const uint8_t* __restrict__ fa, const uint8_t* __restrict__ fb, const uint8_t* __restrict__ camb,
+               float* __restrict__ part, uint2* __restrict__ mask, uint2* __restrict__ nzmask,
+               const float* __restrict__ lo2max, int K, int HW, int PJ, int NS, int n_units, int nslot,
+               long long* __restrict__ trace) {
+    constexpr int FS = kFStages;
     // optional timeline of CTA 0: trace[role*256 + t*4 + k] = clock64()   (wsegk_debug_pcm_trace)
     const bool tr = trace != nullptr && blockIdx.x == 0;
 #define TRACE(role, t, k) do { if (tr && (t) < 64) trace[(role) * 256 + (t) * 4 + (k)] = clock64(); } while (0)
     constexpr int NCOL = 2 * WB;
     constexpr uint32_t kCamBytes = NCOL * 64;                  // (NCOL/8) groups x 32 rows x 16 B per CTA
-    using Bars = FwdBars<FS>;
+    using Bars = FwdBars;
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t a_bytes = kTile * K * 2, b_bytes = WB * K * 2;
-    const uint32_t f_stage = PRECISE ? 2 * b_bytes : b_bytes;
-    uint8_t* s_fj_hi = smem;
-    uint8_t* s_fj_lo = smem + a_bytes;                         // only PRECISE
-    uint8_t* s_f = smem + (PRECISE ? 2 : 1) * a_bytes;         // FS x [Fi_hi | Fi_lo]
-    uint8_t* s_c = s_f + FS * f_stage;                         // kCamStages x cam block
+    uint8_t* s_fj = smem;
+    uint8_t* s_f = smem + a_bytes;                             // FS x Fi tile
+    uint8_t* s_c = s_f + FS * b_bytes;                         // kCamStages x cam block
     Bars* bars = reinterpret_cast<Bars*>(s_c + kCamStages * kCamBytes);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -261,11 +338,11 @@ pcm_fwd_kernel(const uint8_t* __restrict__ fa_hi, const uint8_t* __restrict__ fa
     const int HWpj = PJ * 2 * kTile;
 
     if (threadIdx.x == 0) {
-        const uint32_t relay = rank == 0 ? 1u : 0u, nf = PRECISE ? 2u : 1u;
-        mbar_init(smem_u32(&bars->fj), nf + relay);
+        const uint32_t relay = rank == 0 ? 1u : 0u;
+        mbar_init(smem_u32(&bars->fj), 1 + relay);
         mbar_init(smem_u32(&bars->a_free), 1);
         for (int s = 0; s < FS; ++s) {
-            mbar_init(smem_u32(&bars->full_f[s]), nf + relay);
+            mbar_init(smem_u32(&bars->full_f[s]), 1 + relay);
             mbar_init(smem_u32(&bars->empty_f[s]), 1);
         }
         for (int s = 0; s < kCamStages; ++s) {
@@ -274,7 +351,7 @@ pcm_fwd_kernel(const uint8_t* __restrict__ fa_hi, const uint8_t* __restrict__ fa
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(smem_u32(&bars->s_full[b]), 1);
-            mbar_init(smem_u32(&bars->p_full[b]), 8);          // 4 warps x 2 CTAs
+            mbar_init(smem_u32(&bars->p_full[b]), 16);         // 8 warps x 2 CTAs
         }
         mbar_init(smem_u32(&bars->o_full), 1);
         mbar_fence_init();
@@ -289,12 +366,9 @@ pcm_fwd_kernel(const uint8_t* __restrict__ fa_hi, const uint8_t* __restrict__ fa
     tc_fence_after();
     const uint32_t tmem = bars->tmem_base;
 
-    if (warp == 0 || warp == 6) {
-        // ---------------------------------------------------------------- F producers: warp 0 = hi parts, warp 6 = lo parts
-        const bool lo = warp == 6;
-        if (lane == 0 && (!lo || PRECISE)) {
-            const uint8_t* ga = lo ? fa_lo : fa_hi;
-            const uint8_t* gb = lo ? fb_lo : fb_hi;
+    if (warp == 0) {
+        // ---------------------------------------------------------------- feature-tile producer
+        if (lane == 0) {
             StageCursor si = c0;
             for (int i = 0; i < cnt; ++i, si.next()) {
                 if (si.first()) {
@@ -302,18 +376,18 @@ pcm_fwd_kernel(const uint8_t* __restrict__ fa_hi, const uint8_t* __restrict__ fa
                     if (si.k > 0) mbar_wait(smem_u32(&bars->a_free), (si.k - 1) & 1);
                     const size_t a_tile = static_cast<size_t>(si.n) * 2 * PJ + 2 * si.jp + rank;
                     mbar_arrive_expect_tx(smem_u32(&bars->fj), a_bytes);
-                    tma_load_1d(smem_u32(lo ? s_fj_lo : s_fj_hi), ga + a_tile * a_bytes, a_bytes, smem_u32(&bars->fj));
+                    tma_load_1d(smem_u32(s_fj), fa + a_tile * a_bytes, a_bytes, smem_u32(&bars->fj));
                 }
                 const size_t bt = static_cast<size_t>(si.n) * 2 * NS + 2 * si.st + rank;
                 const int s = i % FS, u = i / FS;
                 mbar_wait(smem_u32(&bars->empty_f[s]), (u & 1) ^ 1);
-                if (!lo) TRACE(0, i, 0);
+                TRACE(0, i, 0);
                 const uint32_t bar = smem_u32(&bars->full_f[s]);
                 mbar_arrive_expect_tx(bar, b_bytes);
-                tma_load_1d(smem_u32(s_f + s * f_stage + (lo ? b_bytes : 0)), gb + bt * b_bytes, b_bytes, bar);
+                tma_load_1d(smem_u32(s_f + s * b_bytes), fb + bt * b_bytes, b_bytes, bar);
             }
         }
-    } else if (warp == 7) {
+    } else if (warp == 2) {
         // ---------------------------------------------------------------- cam-block producer
         if (lane == 0) {
             StageCursor si = c0;
@@ -353,8 +427,7 @@ pcm_fwd_kernel(const uint8_t* __restrict__ fa_hi, const uint8_t* __restrict__ fa
             const uint32_t id_o = umma_idesc_f16(0, 2 * kTile, kONum, 0, 0);
             constexpr uint32_t lbo_a = kTile * 16, lbo_b = WB * 16, lbo_c = kCamRows * 16;
             const int ksteps = K >> 4;
-            const uint64_t da_hi = umma_smem_desc(smem_u32(s_fj_hi), lbo_a, 128);
-            const uint64_t da_lo = umma_smem_desc(smem_u32(s_fj_lo), lbo_a, 128);
+            const uint64_t da = umma_smem_desc(smem_u32(s_fj), lbo_a, 128);
             StageCursor cs = c0;                 // runs two stages ahead of the PV cursor
             auto issue_s = [&](int i) {
                 const bool seg_first = cs.first(), seg_last = cs.last();
@@ -367,23 +440,12 @@ pcm_fwd_kernel(const uint8_t* __restrict__ fa_hi, const uint8_t* __restrict__ fa
                 if (lane == 0) TRACE(1, i, 1);
                 tc_fence_after();
                 if (elect_one()) {
-                    const uint64_t db_hi = umma_smem_desc(smem_u32(s_f + s * f_stage), lbo_b, 128);
-                    const uint64_t db_lo = umma_smem_desc(smem_u32(s_f + s * f_stage) + b_bytes, lbo_b, 128);
+                    const uint64_t db = umma_smem_desc(smem_u32(s_f + s * b_bytes), lbo_b, 128);
                     const uint32_t d = tmem + b * 128;
 #pragma unroll 4
                     for (int ks = 0; ks < ksteps; ++ks)
-                        umma2_ss(d, da_hi + static_cast<uint64_t>(ks * (2 * lbo_a / 16)),
-                                 db_hi + static_cast<uint64_t>(ks * (2 * lbo_b / 16)), id_s, ks > 0);
-                    if (PRECISE) {
-#pragma unroll 4
-                        for (int ks = 0; ks < ksteps; ++ks)
-                            umma2_ss(d, da_hi + static_cast<uint64_t>(ks * (2 * lbo_a / 16)),
-                                     db_lo + static_cast<uint64_t>(ks * (2 * lbo_b / 16)), id_s, 1);
-#pragma unroll 4
-                        for (int ks = 0; ks < ksteps; ++ks)
-                            umma2_ss(d, da_lo + static_cast<uint64_t>(ks * (2 * lbo_a / 16)),
-                                     db_hi + static_cast<uint64_t>(ks * (2 * lbo_b / 16)), id_s, 1);
-                    }
+                        umma2_ss(d, da + static_cast<uint64_t>(ks * (2 * lbo_a / 16)),
+                                 db + static_cast<uint64_t>(ks * (2 * lbo_b / 16)), id_s, ks > 0);
                     umma2_commit(smem_u32(&bars->s_full[b]));
                     umma2_commit(smem_u32(&bars->empty_f[s]));
                     if (seg_last) umma2_commit(smem_u32(&bars->a_free));  // the segment's A-side tile may be replaced
@@ -413,11 +475,14 @@ pcm_fwd_kernel(const uint8_t* __restrict__ fa_hi, const uint8_t* __restrict__ fa
                 if (elect_one()) {
                     const uint64_t dc = umma_smem_desc(smem_u32(s_c + sc * kCamBytes), lbo_c, 128);
                     // the accumulator restarts with every segment; the TMEM warps drained the previous segment's before
-                    // they produced this stage's P
+                    // they produced this stage's P.  P of S columns [0,64) sits at packed columns [0,32) of the buffer, P of
+                    // the columns from 64 on at [64, ...) (convert_cols)
 #pragma unroll
-                    for (int ks = 0; ks < NCOL / 16; ++ks)
-                        umma2_ts(tmem + kColO, tmem + b * 128 + ks * 8, dc + static_cast<uint64_t>(ks * (2 * lbo_c / 16)),
+                    for (int ks = 0; ks < NCOL / 16; ++ks) {
+                        const uint32_t pcol = ks < kSplitCol / 16 ? ks * 8 : kSplitCol + (ks - kSplitCol / 16) * 8;
+                        umma2_ts(tmem + kColO, tmem + b * 128 + pcol, dc + static_cast<uint64_t>(ks * (2 * lbo_c / 16)),
                                  id_o, !si.first() || (ks > 0));
+                    }
                     umma2_commit(smem_u32(&bars->empty_c[sc]));
                     if (si.last()) umma2_commit(smem_u32(&bars->o_full));
                 }
@@ -425,55 +490,60 @@ pcm_fwd_kernel(const uint8_t* __restrict__ fa_hi, const uint8_t* __restrict__ fa
                 issue_upto(i);
             }
         }
-    } else if (warp < 6) {
-        // ---------------------------------------------------------------- ReLU / sign / convert warps (own 128 lanes)
+    } else if (warp >= kFwdTmemWarp0) {
+        // ---------------------------------------------------------------- ReLU / sign / convert warps
         const int q = warp & 3;                         // TMEM lane quarter this warp may touch
+        const int hf = (warp - kFwdTmemWarp0) >> 2;     // column half
         const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
         const uint32_t p_full0 = mapa_shared(smem_u32(&bars->p_full[0]), 0);
         const uint32_t p_full1 = mapa_shared(smem_u32(&bars->p_full[1]), 0);
+        uint32_t tau2 = 0;
+        if (MODE == 2) {
+            // |S(fp16 operands) - S| <= |lo_j| + |lo_i| (+ second order); statistically sigma ~ lo_max / 12 (the residuals
+            // of K channels add like a random walk), so 0.625 lo_max is ~7 sigma: no entry beyond it has the wrong sign
+            const float tau = 0.625f * sqrtf(__ldg(lo2max)) + 1e-6f;
+            const uint32_t th = __half_as_ushort(__float2half_ru(tau));
+            tau2 = th | (th << 16);
+        }
         StageCursor si = c0;
         for (int i = 0; i < cnt; ++i, si.next()) {
             const int row = si.jp * 2 * kTile + static_cast<int>(rank) * kTile + q * 32 + lane;
             const int b = i & 1;
-            if (warp == 2 && lane == 0) TRACE(2, i, 0);
+            if (warp == kFwdTmemWarp0 && lane == 0) TRACE(2, i, 0);
             mbar_wait(smem_u32(&bars->s_full[b]), (i >> 1) & 1);
-            if (warp == 2 && lane == 0) TRACE(2, i, 1);
+            if (warp == kFwdTmemWarp0 && lane == 0) TRACE(2, i, 1);
             tc_fence_after();
-            uint32_t mw[4] = {0u, 0u, 0u, 0u};
-            const uint32_t base = tmem + lane_addr + b * 128;
-#pragma unroll
-            for (int c = 0; c < NCOL / 32; ++c) {
-                uint32_t r[32], pk[16];
-                tmem_ld32(base + c * 32, r);
-                tmem_ld_wait();
-                mw[c] = relu_pack_bits<32>(r, pk);
-                tmem_st16(base + c * 16, pk);
-            }
-            if (NCOL % 32) {
-                constexpr int c = NCOL / 32;
-                uint32_t r[16], pk[8];
-                tmem_ld16(base + c * 32, r);
-                tmem_ld_wait();
-                mw[c & 3] = relu_pack_bits<16>(r, pk);
-                tmem_st8(base + c * 16, pk);
-            }
+            uint32_t sw[2], nw[2];
+            const uint32_t base = tmem + lane_addr + b * 128 + hf * kSplitCol;
+            if (hf == 0) convert_cols<kSplitCol, MODE>(base, tau2, sw, nw);
+            else convert_cols<NCOL - kSplitCol, MODE>(base, tau2, sw, nw);
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(b ? p_full1 : p_full0);
-            if (warp == 2 && lane == 0) TRACE(2, i, 2);
-            mask[(static_cast<size_t>(si.n) * NS + si.st) * HWpj + row] = make_uint4(mw[0], mw[1], mw[2], mw[3]);
+            if (warp == kFwdTmemWarp0 && lane == 0) TRACE(2, i, 2);
+            if (MODE >= 1) {
+                const size_t mi = ((static_cast<size_t>(si.n) * NS + si.st) * HWpj + row) * 2 + hf;
+                mask[mi] = make_uint2(sw[0], sw[1]);
+                if (MODE == 2) {
+                    // padding rows / columns are all-zero vectors: S = 0 there, nothing to re-evaluate
+                    const int vc = HW - si.st * NCOL - hf * kSplitCol;          // valid columns of my half in this stage
+                    if (row >= HW) { nw[0] = 0; nw[1] = 0; }
+                    else if (vc < kSplitCol) { nw[0] &= valid_bits(vc); nw[1] &= valid_bits(vc - 32); }
+                    nzmask[mi] = make_uint2(nw[0], nw[1]);
+                }
+            }
             if (si.last()) {
-                // segment epilogue: accumulator -> partial buffer
+                // segment epilogue: accumulator -> partial buffer (this warp: 32 of the 64 columns)
                 const int slot = si.in_tail() ? g - pcm_tail_owner(sched, static_cast<long long>(si.u - sched.Rf * sched.G) * NS) : 0;
                 mbar_wait(smem_u32(&bars->o_full), si.k & 1);
                 tc_fence_after();
                 // [n][slot][64][HWpj]: for a fixed column the 32 lanes of a warp write 32 consecutive rows (one 128-byte line)
-                float* dst = part + (static_cast<size_t>(si.n) * nslot + slot) * kONum * HWpj + row;
+                float* dst = part + ((static_cast<size_t>(si.n) * nslot + slot) * kONum + hf * 32) * HWpj + row;
 #pragma unroll
-                for (int c = 0; c < kONum / 16; ++c) {
+                for (int c = 0; c < 2; ++c) {
                     uint32_t r[16];
-                    tmem_ld16(tmem + lane_addr + kColO + c * 16, r);
+                    tmem_ld16(tmem + lane_addr + kColO + hf * 32 + c * 16, r);
                     tmem_ld_wait();
 #pragma unroll
                     for (int v = 0; v < 16; ++v) dst[static_cast<size_t>(c * 16 + v) * HWpj] = __uint_as_float(r[v]);
@@ -487,6 +557,107 @@ pcm_fwd_kernel(const uint8_t* __restrict__ fa_hi, const uint8_t* __restrict__ fa
     cluster_sync_all();
     if (warp == 1) tmem_dealloc_2cta(tmem, kTmemCols);
 #undef TRACE
+}
+
+// ------------------------------------------------------------------------------------------------
+// sign fix-up (precise mode)
+// ------------------------------------------------------------------------------------------------
+// The forward marked the entries (j, i) with |S_ji| < tau in nzmask; here each is re-evaluated as an fp32 dot product of
+// the fp32 normalised features (what the reference's fp32 matmul computes, network/resnet38_contrast.py:71) and its bit of
+// the sign mask is set to [S > 0].  One CTA = 128 rows j (their features in shared memory) x a range of stages; the
+// marked entries go through a shared-memory queue so that a warp works on four entries at a time (24 independent 128-byte
+// loads in flight per warp); each entry costs one K-float row from L2.
+constexpr int kFixThreads = 256;
+constexpr int kFixQueue = 2048;
+constexpr int kFixBatch = 512;          // entries that make a flush worthwhile
+
+__global__ void __launch_bounds__(kFixThreads) pcm_sign_fixup_kernel(const float* __restrict__ fh32,
+                                                                    const uint4* __restrict__ nzmask,
+                                                                    uint32_t* __restrict__ mask, int K, int HWpj, int NS,
+                                                                    int ncol, int parts) {
+    extern __shared__ __align__(16) uint8_t fix_smem[];
+    float* s_fj = reinterpret_cast<float*>(fix_smem);                          // [128][K]
+    uint32_t* s_q = reinterpret_cast<uint32_t*>(fix_smem + static_cast<size_t>(kTile) * K * 4);
+    __shared__ int s_cnt;
+    const int n = blockIdx.y, j0 = blockIdx.x * kTile;
+    const int s_begin = static_cast<int>(static_cast<long long>(NS) * blockIdx.z / parts);
+    const int s_end = static_cast<int>(static_cast<long long>(NS) * (blockIdx.z + 1) / parts);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const float* fn = fh32 + static_cast<size_t>(n) * HWpj * K;
+    {
+        const float4* src = reinterpret_cast<const float4*>(fn + static_cast<size_t>(j0) * K);
+        float4* dst = reinterpret_cast<float4*>(s_fj);
+        for (int i = tid; i < kTile * K / 4; i += kFixThreads) dst[i] = __ldg(src + i);
+    }
+    if (tid == 0) s_cnt = 0;
+    __syncthreads();
+    const int my_row = tid & (kTile - 1), my_sub = tid >> 7;                   // two stages are scanned per pass
+    uint32_t pend[4] = {0u, 0u, 0u, 0u};
+    int pend_stage = 0;
+    int s = s_begin;
+    bool any_pend = false;
+    while (true) {
+        if (!any_pend && s < s_end) {
+            const int st = s + my_sub;
+            if (st < s_end) {
+                const uint4 w = __ldg(nzmask + (static_cast<size_t>(n) * NS + st) * HWpj + j0 + my_row);
+                pend[0] = w.x; pend[1] = w.y; pend[2] = w.z; pend[3] = w.w;
+                pend_stage = st;
+            }
+            s += kFixThreads / kTile;
+        }
+        // push my marked entries: [row:7 | column:7 | stage:18]
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            while (pend[c]) {
+                const int slot = atomicAdd(&s_cnt, 1);
+                if (slot >= kFixQueue) break;
+                const int bit = __ffs(pend[c]) - 1;
+                pend[c] &= pend[c] - 1;
+                const int col = 32 * c + ((bit & 15) << 1) + (bit >> 4);
+                s_q[slot] = (static_cast<uint32_t>(my_row) << 25) | (static_cast<uint32_t>(col) << 18) |
+                            static_cast<uint32_t>(pend_stage);
+            }
+        }
+        any_pend = __syncthreads_or((pend[0] | pend[1] | pend[2] | pend[3]) != 0u);
+        const int cnt = min(s_cnt, kFixQueue);
+        const bool done = !any_pend && s >= s_end;
+        if (any_pend || cnt >= kFixBatch || done) {
+            for (int e0 = warp * 4; e0 < cnt; e0 += (kFixThreads / 32) * 4) {
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                uint32_t ent[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    ent[u] = e0 + u < cnt ? s_q[e0 + u] : 0xffffffffu;
+                    if (ent[u] != 0xffffffffu) {
+                        const int row = ent[u] >> 25, col = (ent[u] >> 18) & 127, st = ent[u] & 0x3ffff;
+                        const float* fi = fn + (static_cast<size_t>(st) * ncol + col) * K + lane;
+                        const float* fj = s_fj + row * K + lane;
+                        for (int t = 0; t < K; t += 32) acc[u] = fmaf(__ldg(fi + t), fj[t], acc[u]);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
+                }
+                const uint32_t en = lane == 0 ? ent[0] : lane == 1 ? ent[1] : lane == 2 ? ent[2] : ent[3];
+                if (lane < 4 && en != 0xffffffffu) {
+                    const float sv = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3];
+                    const int row = en >> 25, col = (en >> 18) & 127, st = en & 0x3ffff;
+                    const int c = col >> 5, b = col & 31;
+                    const uint32_t bitv = 1u << ((b >> 1) + ((b & 1) << 4));
+                    uint32_t* wp = mask + ((static_cast<size_t>(n) * NS + st) * HWpj + j0 + row) * kMaskWords + c;
+                    if (sv > 0.f) atomicOr(wp, bitv);
+                    else atomicAnd(wp, ~bitv);
+                }
+            }
+            __syncthreads();
+            if (tid == 0) s_cnt = 0;
+            __syncthreads();
+            if (done) break;
+        }
+    }
 }
 
 // out[n,c,j] = (sum_slot hi[c] + lo[c]) / (sum_slot colsum + 1e-5)
@@ -646,7 +817,7 @@ __device__ __forceinline__ void mask_scale_pack(const uint32_t* r, uint32_t bits
 
 template <int WB, bool SPLIT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMainThreads, 1)
-pcm_bwd_kernel(const uint8_t* __restrict__ ua, const uint8_t* __restrict__ vb, const uint8_t* __restrict__ fb_hi,
+pcm_bwd_kernel(const uint8_t* __restrict__ ua, const uint8_t* __restrict__ vb, const uint8_t* __restrict__ fb,
                const uint4* __restrict__ mask, const float* __restrict__ bound, float* __restrict__ dfhat, int K,
                int PJ, int NS, int n_units, int nslot) {
     constexpr int NCOL = 2 * WB;
@@ -727,7 +898,7 @@ pcm_bwd_kernel(const uint8_t* __restrict__ ua, const uint8_t* __restrict__ vb, c
                 mbar_wait(smem_u32(&bars->empty_f[s]), (u & 1) ^ 1);
                 const uint32_t bar = smem_u32(&bars->full_f[s]);
                 mbar_arrive_expect_tx(bar, f_part);
-                const uint8_t* x = fb_hi + (static_cast<size_t>(si.n) * 2 * NS + 2 * si.st + part) * b_bytes +
+                const uint8_t* x = fb + (static_cast<size_t>(si.n) * 2 * NS + 2 * si.st + part) * b_bytes +
                                    static_cast<size_t>(rank) * f_part;
                 tma_load_1d(smem_u32(s_f + s * f_stage + part * f_part), x, f_part, bar);
             }
@@ -944,12 +1115,9 @@ __global__ void __launch_bounds__(256) pcm_bwd_post_kernel(const float* __restri
     }
 }
 
-template <bool PRECISE>
 static size_t fwd_smem_bytes(int K, int wb) {
-    constexpr int FS = FwdCfg<PRECISE>::kFStages;
     const size_t a = static_cast<size_t>(kTile) * K * 2, b = static_cast<size_t>(wb) * K * 2;
-    return (PRECISE ? 2 : 1) * a + FS * (PRECISE ? 2 : 1) * b + kCamStages * static_cast<size_t>(2 * wb) * 64 +
-           sizeof(FwdBars<FS>) + 64;
+    return a + kFStages * b + kCamStages * static_cast<size_t>(2 * wb) * 64 + sizeof(FwdBars) + 64;
 }
 
 static size_t bwd_smem_bytes(int K, int wb, bool split) {
@@ -966,8 +1134,8 @@ using namespace wsegk;
 namespace {
 struct PcmProf {
     bool on = false;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // fwd start/stop, bwd start/stop
-    bool have[2] = {false, false};
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // fwd start/stop, bwd start/stop, fix-up
+    bool have[3] = {false, false, false};
 };
 thread_local PcmProf g_prof;
 thread_local long long* g_trace = nullptr;   // device buffer of 768 int64 for the forward kernel's timeline, or null
@@ -989,17 +1157,21 @@ extern "C" int wsegk_debug_pcm_trace(long long* device_buffer) {
     return WSEGK_OK;
 }
 
-extern "C" int wsegk_debug_pcm_main_ms(float* fwd_ms, float* bwd_ms) {
-    float* out[2] = {fwd_ms, bwd_ms};
-    for (int k = 0; k < 2; ++k) {
-        if (!out[k]) continue;
-        *out[k] = -1.f;
-        if (!g_prof.have[k]) continue;
-        WSEGK_CUDA_OK(cudaEventSynchronize(g_prof.ev[2 * k + 1]));
-        WSEGK_CUDA_OK(cudaEventElapsedTime(out[k], g_prof.ev[2 * k], g_prof.ev[2 * k + 1]));
-    }
+static int prof_read(int k, float* out) {
+    if (!out) return WSEGK_OK;
+    *out = -1.f;
+    if (!g_prof.have[k]) return WSEGK_OK;
+    WSEGK_CUDA_OK(cudaEventSynchronize(g_prof.ev[2 * k + 1]));
+    WSEGK_CUDA_OK(cudaEventElapsedTime(out, g_prof.ev[2 * k], g_prof.ev[2 * k + 1]));
     return WSEGK_OK;
 }
+
+extern "C" int wsegk_debug_pcm_main_ms(float* fwd_ms, float* bwd_ms) {
+    if (int rc = prof_read(0, fwd_ms)) return rc;
+    return prof_read(1, bwd_ms);
+}
+
+extern "C" int wsegk_debug_pcm_fixup_ms(float* fix_ms) { return prof_read(2, fix_ms); }
 
 static int pcm_check(const char* who, int N, int C, int K, int h, int w) {
     WSEGK_REQUIRE(N > 0 && h > 0 && w > 0, WSEGK_ERR_BAD_SHAPE, "%s: N,h,w must be positive", who);
@@ -1012,17 +1184,16 @@ static int pcm_check(const char* who, int N, int C, int K, int h, int w) {
     return WSEGK_OK;
 }
 
-template <int WB, bool PRECISE>
+template <int WB, int MODE>
 static int launch_fwd(const PcmPlan& pl, int N, wsegk_stream_t stream) {
-    const size_t smem = fwd_smem_bytes<PRECISE>(pl.K, WB);
+    const size_t smem = fwd_smem_bytes(pl.K, WB);
     WSEGK_REQUIRE(smem <= 232448, WSEGK_ERR_BAD_SHAPE, "pcm_fwd: %zu bytes of shared memory needed", smem);
-    WSEGK_CUDA_OK(cudaFuncSetAttribute(pcm_fwd_kernel<WB, PRECISE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    WSEGK_CUDA_OK(cudaFuncSetAttribute(pcm_fwd_kernel<WB, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem)));
-    pcm_fwd_kernel<WB, PRECISE><<<dim3(2 * pl.G), kMainThreads, smem, stream>>>(
-        reinterpret_cast<const uint8_t*>(pl.fa_hi), reinterpret_cast<const uint8_t*>(pl.fa_lo),
-        reinterpret_cast<const uint8_t*>(pl.fb_hi), reinterpret_cast<const uint8_t*>(pl.fb_lo),
-        reinterpret_cast<const uint8_t*>(pl.camb), pl.part, reinterpret_cast<uint4*>(pl.mask), pl.K, pl.PJ, pl.NS,
-        N * pl.PJ, pl.nsplit, g_trace);
+    pcm_fwd_kernel<WB, MODE><<<dim3(2 * pl.G), kFwdThreads, smem, stream>>>(
+        reinterpret_cast<const uint8_t*>(pl.fa), reinterpret_cast<const uint8_t*>(pl.fb),
+        reinterpret_cast<const uint8_t*>(pl.camb), pl.part, reinterpret_cast<uint2*>(pl.mask),
+        reinterpret_cast<uint2*>(pl.nzmask), pl.bound + kBoundLo2, pl.K, pl.HW, pl.PJ, pl.NS, N * pl.PJ, pl.nsplit, g_trace);
     return WSEGK_OK;
 }
 
@@ -1034,96 +1205,158 @@ static int launch_bwd(const PcmPlan& pl, int N, wsegk_stream_t stream) {
                                        static_cast<int>(smem)));
     pcm_bwd_kernel<WB, SPLIT><<<dim3(2 * pl.G), kMainThreads, smem, stream>>>(
         reinterpret_cast<const uint8_t*>(pl.ua), reinterpret_cast<const uint8_t*>(pl.vb),
-        reinterpret_cast<const uint8_t*>(pl.fb_hi), reinterpret_cast<const uint4*>(pl.mask), pl.bound, pl.dfhat, pl.K,
+        reinterpret_cast<const uint8_t*>(pl.fb), reinterpret_cast<const uint4*>(pl.mask), pl.bound, pl.dfhat, pl.K,
         pl.PJ, pl.NS, N * pl.PJ, pl.nsplit);
     return WSEGK_OK;
 }
 
-#define WSEGK_DISPATCH_WB(fn, flag, ...)                                                                 \
-    do {                                                                                                 \
-        int _rc;                                                                                         \
-        if (pl.wb == 64) _rc = (flag) ? fn<64, true>(__VA_ARGS__) : fn<64, false>(__VA_ARGS__);          \
-        else if (pl.wb == 56) _rc = (flag) ? fn<56, true>(__VA_ARGS__) : fn<56, false>(__VA_ARGS__);     \
-        else _rc = (flag) ? fn<48, true>(__VA_ARGS__) : fn<48, false>(__VA_ARGS__);                      \
-        if (_rc) return _rc;                                                                             \
-    } while (0)
+static int dispatch_fwd(const PcmPlan& pl, int N, int mode, wsegk_stream_t stream) {
+#define WSEGK_FWD_CASE(WBV)                                            \
+    case WBV:                                                          \
+        return mode == 2 ? launch_fwd<WBV, 2>(pl, N, stream)           \
+               : mode == 1 ? launch_fwd<WBV, 1>(pl, N, stream)         \
+                           : launch_fwd<WBV, 0>(pl, N, stream);
+    switch (pl.wb) {
+        WSEGK_FWD_CASE(64)
+        WSEGK_FWD_CASE(56)
+        default:
+            WSEGK_FWD_CASE(48)
+    }
+#undef WSEGK_FWD_CASE
+}
 
+static int dispatch_bwd(const PcmPlan& pl, int N, bool split, wsegk_stream_t stream) {
+#define WSEGK_BWD_CASE(WBV) \
+    case WBV:               \
+        return split ? launch_bwd<WBV, true>(pl, N, stream) : launch_bwd<WBV, false>(pl, N, stream);
+    switch (pl.wb) {
+        WSEGK_BWD_CASE(64)
+        WSEGK_BWD_CASE(56)
+        default:
+            WSEGK_BWD_CASE(48)
+    }
+#undef WSEGK_BWD_CASE
+}
+
+// the sign fix-up of the precise mode on a workspace the forward has filled
+static int launch_fixup(const PcmPlan& pl, int N, wsegk_stream_t stream) {
+    const size_t smem = static_cast<size_t>(kTile) * pl.K * 4 + static_cast<size_t>(kFixQueue) * 4;
+    WSEGK_CUDA_OK(cudaFuncSetAttribute(pcm_sign_fixup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem)));
+    const int tiles = pl.HWpj / kTile;
+    // enough CTAs for two per SM; a part is at least two stages (the scan reads two stages per pass)
+    int parts = ceil_div(2 * 148, tiles * N);
+    parts = std::max(1, std::min(parts, std::max(1, pl.NS / 2)));
+    prof_mark(4, stream);
+    pcm_sign_fixup_kernel<<<dim3(tiles, N, parts), kFixThreads, smem, stream>>>(
+        pl.fh32, reinterpret_cast<const uint4*>(pl.nzmask), pl.mask, pl.K, pl.HWpj, pl.NS, 2 * pl.wb, parts);
+    prof_mark(5, stream);
+    count_launches(1);
+    return WSEGK_OK;
+}
+
+// mode: 0 inference (no masks), 1 fast (sign mask from the FP16 products), 2 precise (+ near-zero mask and fix-up)
 static int pcm_fwd_impl(const float* f, const float* cam_norm, float* cam_rv, int N, int C, int K, int h, int w,
-                        void* workspace, size_t workspace_bytes, wsegk_stream_t stream, int precise,
-                        float* cam_norm_out = nullptr);
+                        void* workspace, size_t workspace_bytes, wsegk_stream_t stream, int mode, bool defer_fixup,
+                        float* cam_norm_out) {
+    if (int rc = check_device()) return rc;
+    WSEGK_REQUIRE(f && cam_norm && cam_rv && workspace, WSEGK_ERR_NULL, "pcm_fwd: null pointer");
+    if (int rc = pcm_check("pcm_fwd", N, C, K, h, w)) return rc;
+    WSEGK_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, WSEGK_ERR_BAD_ALIGN,
+                  "pcm_fwd: workspace must be 1024-byte aligned");
+    PcmPlan pl = make_pcm_plan(workspace, N, C, K, h, w, mode == 2);
+    WSEGK_REQUIRE(workspace_bytes >= pl.bytes, WSEGK_ERR_WORKSPACE_TOO_SMALL, "pcm_fwd: workspace %zu < %zu",
+                  workspace_bytes, pl.bytes);
+    {
+        const int tiles = ceil_div(std::max(pl.HWpj, pl.HWpi), kTile);
+        uint4 *fa = reinterpret_cast<uint4*>(pl.fa), *fb = reinterpret_cast<uint4*>(pl.fb);
+        uint4* cb = reinterpret_cast<uint4*>(pl.camb);
+        unsigned int* lo2 = reinterpret_cast<unsigned int*>(pl.bound + kBoundLo2);
+        const dim3 grid(tiles + pl.NS, N);
+        const bool logits = cam_norm_out != nullptr;
+        if (logits) {
+            launch_cam_plane_peak(cam_norm, pl.peak, N * C, pl.HW, stream);
+            count_launches(1);
+        }
+        if (mode == 2) {
+            WSEGK_CUDA_OK(cudaMemsetAsync(lo2, 0, sizeof(float), stream));
+            if (logits)
+                pcm_prep_kernel<true, true><<<grid, 256, 0, stream>>>(f, fa, fb, pl.fh32, lo2, pl.inv_norm, cam_norm, pl.peak,
+                                                                      cam_norm_out, cb, C, K, pl.HW, pl.PJ, pl.NS, pl.wb, tiles);
+            else
+                pcm_prep_kernel<true, false><<<grid, 256, 0, stream>>>(f, fa, fb, pl.fh32, lo2, pl.inv_norm, cam_norm, nullptr,
+                                                                       nullptr, cb, C, K, pl.HW, pl.PJ, pl.NS, pl.wb, tiles);
+        } else if (logits) {
+            pcm_prep_kernel<false, true><<<grid, 256, 0, stream>>>(f, fa, fb, pl.fh32, lo2, pl.inv_norm, cam_norm, pl.peak,
+                                                                   cam_norm_out, cb, C, K, pl.HW, pl.PJ, pl.NS, pl.wb, tiles);
+        } else {
+            pcm_prep_kernel<false, false><<<grid, 256, 0, stream>>>(f, fa, fb, pl.fh32, lo2, pl.inv_norm, cam_norm, nullptr,
+                                                                    nullptr, cb, C, K, pl.HW, pl.PJ, pl.NS, pl.wb, tiles);
+        }
+    }
+    prof_mark(0, stream);
+    if (int rc = dispatch_fwd(pl, N, mode, stream)) return rc;
+    prof_mark(1, stream);
+    pcm_fwd_finalize_kernel<<<dim3(pl.HWpj / 32, N), 256, 0, stream>>>(pl.part, cam_rv, pl.dsum, C, pl.HW, pl.HWpj,
+                                                                         pl.nsplit, pl.PJ, pl.NS, pl.G);
+    count_launches(3);
+    if (mode == 2 && !defer_fixup)
+        if (int rc = launch_fixup(pl, N, stream)) return rc;
+    WSEGK_CUDA_OK(cudaGetLastError());
+    return WSEGK_OK;
+}
 
 extern "C" int wsegk_pcm_fwd(const float* f, const float* cam_norm, float* cam_rv, int N, int C, int K, int h,
                              int w, void* workspace, size_t workspace_bytes, wsegk_stream_t stream) {
-    return pcm_fwd_impl(f, cam_norm, cam_rv, N, C, K, h, w, workspace, workspace_bytes, stream, pcm_mode());
+    return pcm_fwd_impl(f, cam_norm, cam_rv, N, C, K, h, w, workspace, workspace_bytes, stream, pcm_mode() ? 2 : 1, false,
+                        nullptr);
 }
 
 extern "C" int wsegk_pcm_fwd_infer(const float* f, const float* cam_norm, float* cam_rv, int N, int C, int K, int h,
                                    int w, void* workspace, size_t workspace_bytes, wsegk_stream_t stream) {
-    return pcm_fwd_impl(f, cam_norm, cam_rv, N, C, K, h, w, workspace, workspace_bytes, stream, 0);
+    return pcm_fwd_impl(f, cam_norm, cam_rv, N, C, K, h, w, workspace, workspace_bytes, stream, 0, false, nullptr);
 }
 
 // cam_norm_out != nullptr: `cam_norm` holds raw logits; K1a is fused into the operand preparation
 extern "C" int wsegk_pcm_fwd_logits(const float* f, const float* cam_logits, float* cam_norm_out, float* cam_rv, int N, int C,
                                     int K, int h, int w, void* workspace, size_t workspace_bytes, wsegk_stream_t stream) {
     WSEGK_REQUIRE(cam_norm_out != nullptr, WSEGK_ERR_NULL, "pcm_fwd_logits: null pointer");
-    return pcm_fwd_impl(f, cam_logits, cam_rv, N, C, K, h, w, workspace, workspace_bytes, stream, pcm_mode(), cam_norm_out);
+    return pcm_fwd_impl(f, cam_logits, cam_rv, N, C, K, h, w, workspace, workspace_bytes, stream, pcm_mode() ? 2 : 1, false,
+                        cam_norm_out);
 }
 
-static int pcm_fwd_impl(const float* f, const float* cam_norm, float* cam_rv, int N, int C, int K, int h, int w,
-                        void* workspace, size_t workspace_bytes, wsegk_stream_t stream, int precise, float* cam_norm_out) {
+extern "C" int wsegk_pcm_fwd_ex(const float* f, const float* cam, float* cam_norm_out, float* cam_rv, int N, int C, int K,
+                                int h, int w, void* workspace, size_t workspace_bytes, int flags, wsegk_stream_t stream) {
+    WSEGK_REQUIRE((flags & ~(WSEGK_PCM_PRECISE | WSEGK_PCM_DEFER_FIXUP)) == 0, WSEGK_ERR_BAD_SHAPE,
+                  "pcm_fwd_ex: unknown flags 0x%x", flags);
+    return pcm_fwd_impl(f, cam, cam_rv, N, C, K, h, w, workspace, workspace_bytes, stream,
+                        (flags & WSEGK_PCM_PRECISE) ? 2 : 1, (flags & WSEGK_PCM_DEFER_FIXUP) != 0, cam_norm_out);
+}
+
+extern "C" int wsegk_pcm_sign_fixup(int N, int C, int K, int h, int w, void* workspace, size_t workspace_bytes,
+                                    wsegk_stream_t stream) {
     if (int rc = check_device()) return rc;
-    WSEGK_REQUIRE(f && cam_norm && cam_rv && workspace, WSEGK_ERR_NULL, "pcm_fwd: null pointer");
-    if (int rc = pcm_check("pcm_fwd", N, C, K, h, w)) return rc;
+    WSEGK_REQUIRE(workspace, WSEGK_ERR_NULL, "pcm_sign_fixup: null pointer");
+    if (int rc = pcm_check("pcm_sign_fixup", N, C, K, h, w)) return rc;
     WSEGK_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, WSEGK_ERR_BAD_ALIGN,
-                  "pcm_fwd: workspace must be 1024-byte aligned");
-    PcmPlan pl = make_pcm_plan(workspace, N, C, K, h, w, precise);
-    WSEGK_REQUIRE(workspace_bytes >= pl.bytes, WSEGK_ERR_WORKSPACE_TOO_SMALL, "pcm_fwd: workspace %zu < %zu",
+                  "pcm_sign_fixup: workspace must be 1024-byte aligned");
+    PcmPlan pl = make_pcm_plan(workspace, N, C, K, h, w, 1);
+    WSEGK_REQUIRE(workspace_bytes >= pl.bytes, WSEGK_ERR_WORKSPACE_TOO_SMALL, "pcm_sign_fixup: workspace %zu < %zu",
                   workspace_bytes, pl.bytes);
-    {
-        const size_t smem = 0;
-        const int tiles = ceil_div(std::max(pl.HWpj, pl.HWpi), kTile);
-        uint4 *a_hi = reinterpret_cast<uint4*>(pl.fa_hi), *a_lo = reinterpret_cast<uint4*>(pl.fa_lo);
-        uint4 *b_hi = reinterpret_cast<uint4*>(pl.fb_hi), *b_lo = reinterpret_cast<uint4*>(pl.fb_lo);
-        uint4* cb = reinterpret_cast<uint4*>(pl.camb);
-        (void)smem;
-        const dim3 grid(tiles + pl.NS, N);
-        if (cam_norm_out != nullptr) {
-            launch_cam_plane_peak(cam_norm, pl.peak, N * C, pl.HW, stream);
-            count_launches(1);
-            if (precise)
-                pcm_prep_kernel<true, true><<<grid, 256, 0, stream>>>(f, a_hi, a_lo, b_hi, b_lo, pl.inv_norm, cam_norm, pl.peak,
-                                                                      cam_norm_out, cb, C, K, pl.HW, pl.PJ, pl.NS, pl.wb, tiles);
-            else
-                pcm_prep_kernel<false, true><<<grid, 256, 0, stream>>>(f, a_hi, a_lo, b_hi, b_lo, pl.inv_norm, cam_norm, pl.peak,
-                                                                       cam_norm_out, cb, C, K, pl.HW, pl.PJ, pl.NS, pl.wb, tiles);
-        } else if (precise) {
-            pcm_prep_kernel<true, false><<<grid, 256, 0, stream>>>(f, a_hi, a_lo, b_hi, b_lo, pl.inv_norm, cam_norm, nullptr,
-                                                                   nullptr, cb, C, K, pl.HW, pl.PJ, pl.NS, pl.wb, tiles);
-        } else {
-            pcm_prep_kernel<false, false><<<grid, 256, 0, stream>>>(f, a_hi, a_lo, b_hi, b_lo, pl.inv_norm, cam_norm, nullptr,
-                                                                    nullptr, cb, C, K, pl.HW, pl.PJ, pl.NS, pl.wb, tiles);
-        }
-    }
-    prof_mark(0, stream);
-    WSEGK_DISPATCH_WB(launch_fwd, precise, pl, N, stream);
-    prof_mark(1, stream);
-    pcm_fwd_finalize_kernel<<<dim3(pl.HWpj / 32, N), 256, 0, stream>>>(pl.part, cam_rv, pl.dsum, C, pl.HW, pl.HWpj,
-                                                                         pl.nsplit, pl.PJ, pl.NS, pl.G);
-    count_launches(3);
+    if (int rc = launch_fixup(pl, N, stream)) return rc;
     WSEGK_CUDA_OK(cudaGetLastError());
     return WSEGK_OK;
 }
 
-extern "C" int wsegk_pcm_bwd(const float* f, const float* cam_norm, const float* cam_rv, const float* grad_cam_rv,
-                             float* grad_f, int N, int C, int K, int h, int w, void* workspace,
-                             size_t workspace_bytes, wsegk_stream_t stream) {
+static int pcm_bwd_impl(const float* f, const float* cam_norm, const float* cam_rv, const float* grad_cam_rv,
+                        float* grad_f, int N, int C, int K, int h, int w, void* workspace, size_t workspace_bytes,
+                        int precise, wsegk_stream_t stream) {
     if (int rc = check_device()) return rc;
     WSEGK_REQUIRE(f && cam_norm && cam_rv && grad_cam_rv && grad_f && workspace, WSEGK_ERR_NULL,
                   "pcm_bwd: null pointer");
     if (int rc = pcm_check("pcm_bwd", N, C, K, h, w)) return rc;
     WSEGK_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, WSEGK_ERR_BAD_ALIGN,
                   "pcm_bwd: workspace must be 1024-byte aligned");
-    const int precise = pcm_mode();
     PcmPlan pl = make_pcm_plan(workspace, N, C, K, h, w, precise);
     WSEGK_REQUIRE(workspace_bytes >= pl.bytes, WSEGK_ERR_WORKSPACE_TOO_SMALL, "pcm_bwd: workspace %zu < %zu",
                   workspace_bytes, pl.bytes);
@@ -1140,11 +1373,27 @@ extern "C" int wsegk_pcm_bwd(const float* f, const float* cam_norm, const float*
                 reinterpret_cast<unsigned int*>(pl.bound), C, pl.HW, pl.PJ, pl.NS, pl.wb);
     }
     prof_mark(2, stream);
-    WSEGK_DISPATCH_WB(launch_bwd, precise, pl, N, stream);
+    if (int rc = dispatch_bwd(pl, N, precise != 0, stream)) return rc;
     prof_mark(3, stream);
     pcm_bwd_post_kernel<<<dim3(ceil_div(pl.HW, kPostPix), N), 256, 0, stream>>>(
         pl.dfhat, f, pl.inv_norm, pl.bound, grad_f, K, pl.HW, pl.HWpj, pl.nsplit, pl.PJ, pl.NS, pl.G);
     count_launches(3);
     WSEGK_CUDA_OK(cudaGetLastError());
     return WSEGK_OK;
+}
+
+extern "C" int wsegk_pcm_bwd(const float* f, const float* cam_norm, const float* cam_rv, const float* grad_cam_rv,
+                             float* grad_f, int N, int C, int K, int h, int w, void* workspace,
+                             size_t workspace_bytes, wsegk_stream_t stream) {
+    return pcm_bwd_impl(f, cam_norm, cam_rv, grad_cam_rv, grad_f, N, C, K, h, w, workspace, workspace_bytes, pcm_mode(),
+                        stream);
+}
+
+extern "C" int wsegk_pcm_bwd_ex(const float* f, const float* cam_norm, const float* cam_rv, const float* grad_cam_rv,
+                                float* grad_f, int N, int C, int K, int h, int w, void* workspace, size_t workspace_bytes,
+                                int flags, wsegk_stream_t stream) {
+    WSEGK_REQUIRE((flags & ~(WSEGK_PCM_PRECISE | WSEGK_PCM_DEFER_FIXUP)) == 0, WSEGK_ERR_BAD_SHAPE,
+                  "pcm_bwd_ex: unknown flags 0x%x", flags);
+    return pcm_bwd_impl(f, cam_norm, cam_rv, grad_cam_rv, grad_f, N, C, K, h, w, workspace, workspace_bytes,
+                        (flags & WSEGK_PCM_PRECISE) ? 1 : 0, stream);
 }

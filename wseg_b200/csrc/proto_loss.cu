@@ -1359,7 +1359,7 @@ extern "C" int wsegk_mining_keys(uint32_t* keys, int count, unsigned long long i
 }
 
 // tests: take the large-plane (multi-CTA select) paths of K3 and K4 whatever the size (wsegk_debug_force_radix)
-static int g_force_radix = 0;
+static thread_local int g_force_radix = 0;   // per host thread: concurrent callers do not see each other's test switches
 extern "C" int wsegk_debug_force_radix(int on) {
     g_force_radix = on ? 1 : 0;
     return WSEGK_OK;

@@ -53,9 +53,24 @@ def cam_norm(cam: torch.Tensor) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------------------------- K2
-def pcm_forward(cam_norm_t: torch.Tensor, f: torch.Tensor, inference: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
+def _pcm_flags(mode: Optional[str], defer_fixup: bool = False) -> int:
+    """Flags of the per-call PCM entry points (include/wsegk.h).  ``mode=None``: the calling thread's default
+    (``set_pcm_mode``); the mode travels with the call, so threads cannot change each other's."""
+    if mode is None:
+        mode = get_pcm_mode()
+    if mode not in ("precise", "fast"):
+        raise ValueError("mode must be 'precise' or 'fast'")
+    flags = _lib.PCM_PRECISE if mode == "precise" else 0
+    if defer_fixup and flags:
+        flags |= _lib.PCM_DEFER_FIXUP
+    return flags
+
+
+def pcm_forward(cam_norm_t: torch.Tensor, f: torch.Tensor, inference: bool = False, mode: Optional[str] = None,
+                defer_fixup: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
     """network/resnet38_contrast.py:70-73.  Returns (cam_rv [N,C,h,w], workspace kept for the backward).
-    ``inference=True``: no backward will follow (single-product kernel, workspace not reusable for pcm_backward)."""
+    ``inference=True``: no backward will follow (no sign mask; workspace not reusable for pcm_backward).
+    ``defer_fixup=True`` (precise mode): the caller runs ``pcm_sign_fixup(ws, ...)`` itself before the backward."""
     f = _require_cuda_f32("f", f)
     cam_norm_t = _require_cuda_f32("cam_norm", cam_norm_t)
     n, k, h, w = f.shape
@@ -65,13 +80,16 @@ def pcm_forward(cam_norm_t: torch.Tensor, f: torch.Tensor, inference: bool = Fal
     out = torch.empty(n, c, h, w, dtype=torch.float32, device=f.device)
     with torch.cuda.device(f.device):
         ws = _workspace(_lib.OP_PCM, f.device, N=n, C=c, K=k, h=h, w=w)
-        fn = _lib.lib().wsegk_pcm_fwd_infer if inference else _lib.lib().wsegk_pcm_fwd
-        check(fn(_ptr(f), _ptr(cam_norm_t), _ptr(out), n, c, k, h, w, _ptr(ws), ws.numel(), _stream(f)),
-              "wsegk_pcm_fwd_infer" if inference else "wsegk_pcm_fwd")
+        if inference:
+            check(_lib.lib().wsegk_pcm_fwd_infer(_ptr(f), _ptr(cam_norm_t), _ptr(out), n, c, k, h, w, _ptr(ws), ws.numel(),
+                                                 _stream(f)), "wsegk_pcm_fwd_infer")
+        else:
+            check(_lib.lib().wsegk_pcm_fwd_ex(_ptr(f), _ptr(cam_norm_t), None, _ptr(out), n, c, k, h, w, _ptr(ws),
+                                              ws.numel(), _pcm_flags(mode, defer_fixup), _stream(f)), "wsegk_pcm_fwd_ex")
     return out, ws
 
 
-def pcm_forward_logits(cam_logits: torch.Tensor, f: torch.Tensor):
+def pcm_forward_logits(cam_logits: torch.Tensor, f: torch.Tensor, mode: Optional[str] = None, defer_fixup: bool = False):
     """K1a + K2 forward in one call (network/resnet38_contrast.py:41-48 fused into :70-73): the normalisation of the raw
     class logits happens inside the PCM's operand preparation.  Returns (cam_rv, workspace, cam_norm) — ``cam_norm`` is
     bit-identical to ``cam_norm(cam_logits)`` and is what ``pcm_backward`` needs."""
@@ -85,28 +103,39 @@ def pcm_forward_logits(cam_logits: torch.Tensor, f: torch.Tensor):
     camn = torch.empty_like(cam_logits)
     with torch.cuda.device(f.device):
         ws = _workspace(_lib.OP_PCM, f.device, N=n, C=c, K=k, h=h, w=w)
-        check(_lib.lib().wsegk_pcm_fwd_logits(_ptr(f), _ptr(cam_logits), _ptr(camn), _ptr(out), n, c, k, h, w, _ptr(ws),
-                                              ws.numel(), _stream(f)), "wsegk_pcm_fwd_logits")
+        check(_lib.lib().wsegk_pcm_fwd_ex(_ptr(f), _ptr(cam_logits), _ptr(camn), _ptr(out), n, c, k, h, w, _ptr(ws),
+                                          ws.numel(), _pcm_flags(mode, defer_fixup), _stream(f)), "wsegk_pcm_fwd_ex")
     return out, ws, camn
 
 
+def pcm_sign_fixup(ws: torch.Tensor, n: int, c: int, k: int, h: int, w: int) -> None:
+    """The sign fix-up of a precise forward that was called with ``defer_fixup=True``, on torch's current stream (the
+    caller orders it after the forward and before ``pcm_backward``, e.g. on a side stream off the critical path)."""
+    with torch.cuda.device(ws.device):
+        check(_lib.lib().wsegk_pcm_sign_fixup(n, c, k, h, w, _ptr(ws), ws.numel(),
+                                              torch.cuda.current_stream(ws.device).cuda_stream), "wsegk_pcm_sign_fixup")
+
+
 def pcm_backward(f: torch.Tensor, cam_norm_t: torch.Tensor, cam_rv: torch.Tensor, grad_out: torch.Tensor,
-                 ws: torch.Tensor) -> torch.Tensor:
+                 ws: torch.Tensor, mode: Optional[str] = None) -> torch.Tensor:
+    """``mode`` must be the mode of the forward that filled ``ws`` (None: the calling thread's default)."""
     f = _require_cuda_f32("f", f)
     grad_out = _require_cuda_f32("grad_cam_rv", grad_out)
     n, k, h, w = f.shape
     c = cam_norm_t.shape[1]
     grad_f = torch.empty_like(f)
     with torch.cuda.device(f.device):
-        check(_lib.lib().wsegk_pcm_bwd(_ptr(f), _ptr(cam_norm_t), _ptr(cam_rv), _ptr(grad_out), _ptr(grad_f),
-                                       n, c, k, h, w, _ptr(ws), ws.numel(), _stream(f)), "wsegk_pcm_bwd")
+        check(_lib.lib().wsegk_pcm_bwd_ex(_ptr(f), _ptr(cam_norm_t), _ptr(cam_rv), _ptr(grad_out), _ptr(grad_f),
+                                          n, c, k, h, w, _ptr(ws), ws.numel(), _pcm_flags(mode), _stream(f)),
+              "wsegk_pcm_bwd_ex")
     return grad_f
 
 
 class _PCMFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, cam_norm_t, f):
-        out, ws = pcm_forward(cam_norm_t, f)
+        ctx.mode = get_pcm_mode()            # the backward may run on another (autograd) thread: the mode travels in ctx
+        out, ws = pcm_forward(cam_norm_t, f, mode=ctx.mode)
         ctx.save_for_backward(f, cam_norm_t, out)
         ctx.ws = ws
         return out
@@ -114,7 +143,7 @@ class _PCMFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         f, cam_norm_t, out = ctx.saved_tensors
-        grad_f = pcm_backward(f, cam_norm_t, out, grad_out, ctx.ws)
+        grad_f = pcm_backward(f, cam_norm_t, out, grad_out, ctx.ws, mode=ctx.mode)
         ctx.ws = None
         return None, grad_f
 
@@ -122,7 +151,8 @@ class _PCMFunction(torch.autograd.Function):
 class _PCMFromLogits(torch.autograd.Function):
     @staticmethod
     def forward(ctx, cam_logits, f):
-        out, ws, camn = pcm_forward_logits(cam_logits, f)
+        ctx.mode = get_pcm_mode()
+        out, ws, camn = pcm_forward_logits(cam_logits, f, mode=ctx.mode)
         ctx.save_for_backward(f, camn, out)
         ctx.ws = ws
         return out
@@ -130,7 +160,7 @@ class _PCMFromLogits(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         f, camn, out = ctx.saved_tensors
-        grad_f = pcm_backward(f, camn, out, grad_out, ctx.ws)
+        grad_f = pcm_backward(f, camn, out, grad_out, ctx.ws, mode=ctx.mode)
         ctx.ws = None
         return None, grad_f
 
@@ -173,6 +203,14 @@ def pcm_profile(enable: bool) -> None:
     check(_lib.lib().wsegk_debug_pcm_profile(1 if enable else 0), "wsegk_debug_pcm_profile")
 
 
+def pcm_fixup_ms() -> float:
+    """Duration in ms of the last profiled sign fix-up kernel (precise forward), or -1."""
+    import ctypes
+    a = ctypes.c_float(-1.0)
+    check(_lib.lib().wsegk_debug_pcm_fixup_ms(ctypes.byref(a)), "wsegk_debug_pcm_fixup_ms")
+    return float(a.value)
+
+
 def pcm_main_ms() -> Tuple[float, float]:
     """(forward, backward) duration in ms of the last profiled tcgen05 main kernels (CUDA events, launching stream)."""
     import ctypes
@@ -182,7 +220,8 @@ def pcm_main_ms() -> Tuple[float, float]:
 
 
 def set_pcm_mode(mode: str) -> None:
-    """'precise' (default): split-FP16 operands, sign mask of S exact to ~2^-21; 'fast': single products."""
+    """Default mode of the calling THREAD.  'precise' (default): the near-zero entries of S are re-evaluated in fp32, so the
+    sign mask the backward consumes is exact; 'fast': signs straight from the FP16 products."""
     if mode not in ("precise", "fast"):
         raise ValueError("mode must be 'precise' or 'fast'")
     check(_lib.lib().wsegk_pcm_set_mode(1 if mode == "precise" else 0), "wsegk_pcm_set_mode")
@@ -197,7 +236,7 @@ def pcm_layout(n: int, c: int, k: int, h: int, w: int) -> dict:
     import ctypes
     buf = (ctypes.c_size_t * 20)()
     got = _lib.lib().wsegk_debug_pcm_layout(n, c, k, h, w, buf, 20)
-    names = ["fa_hi", "fa_lo", "fb_hi", "fb_lo", "camb", "inv_norm", "dsum", "part", "mask", "ua", "vb", "dfhat",
+    names = ["fa", "fh32", "fb", "nzmask", "camb", "inv_norm", "dsum", "part", "mask", "ua", "vb", "dfhat",
              "bound", "bytes", "nsplit", "PJ", "HWpj", "wb", "NS", "HWpi"]
     return {names[i]: int(buf[i]) for i in range(got)}
 
