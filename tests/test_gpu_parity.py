@@ -84,7 +84,9 @@ def test_network_head_golden(cuda_dev, golden_dir):
 
 def pcm_backward_compare(cuda_dev, n, h, w, positive, seed, mode="precise"):
     """grad_f of ops.pcm against the fp32 oracle's autograd in the MAX-ABS metric.  The entries of S whose sign is undecidable
-    in fp32 (|S| < 1e-6 in an fp64 evaluation; the oracle's own cuBLAS product is ambiguous there) are listed, their number is
+    in fp32 (|S| < 5e-7 in an fp64 evaluation — a few times the rounding error of an fp32 product of 192 terms; the oracle's
+    own cuBLAS product is ambiguous there; for random unit vectors in 192 dimensions S has density ~5.5 at zero, so these are
+    ~5.5e-6 of the entries whatever the kernel does) are listed, their number is
     bounded, and the gradient term of each is taken out of BOTH gradients with the sign decision that side actually took
     (ours: the mask in the workspace; the oracle's: the sign of its fp32 product) — every other entry must have been decided
     like the oracle did, or the 1e-3 bar fails (one flipped term is ~2e-2 of the largest gradient element)."""
@@ -98,8 +100,8 @@ def pcm_backward_compare(cuda_dev, n, h, w, positive, seed, mode="precise"):
     grad = ops.pcm_backward(f, camn, out, g, ws, mode=mode)
     raw = rel_max(grad, f_ref.grad)
     ref64 = PcmRef64(camn, f, g)
-    idx, share = ref64.ambiguous(1e-6)
-    assert share <= 1e-5, (share, "share of entries with |S| < 1e-6")
+    idx, share = ref64.ambiguous(5e-7)
+    assert share <= 1e-5, (share, "share of entries with |S| < 5e-7")
     ni, a, b = idx
     k = f.shape[1]
     ff = f.reshape(n, k, h * w)

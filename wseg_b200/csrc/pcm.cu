@@ -499,9 +499,11 @@ pcm_fwd_kernel(const uint8_t* __restrict__ fa, const uint8_t* __restrict__ fb, c
         const uint32_t p_full1 = mapa_shared(smem_u32(&bars->p_full[1]), 0);
         uint32_t tau2 = 0;
         if (MODE == 2) {
-            // |S(fp16 operands) - S| <= |lo_j| + |lo_i| (+ second order); statistically sigma ~ lo_max / 12 (the residuals
-            // of K channels add like a random walk), so 0.625 lo_max is ~7 sigma: no entry beyond it has the wrong sign
-            const float tau = 0.625f * sqrtf(__ldg(lo2max)) + 1e-6f;
+            // |S(fp16 operands) - S| <= |lo_j| + |lo_i| <= 2 lo_max is the strict bound; the residuals of the K channels add
+            // like a random walk, sigma ~ lo_max / 6 (measured: max over 8e7 entries 0.95 lo_max at 5.7 sigma), so an entry
+            // beyond tau = lo_max with the wrong sign is a > 6 sigma event that also needs |S| to sit just above tau:
+            // ~1e-13 per entry
+            const float tau = sqrtf(__ldg(lo2max)) + 1e-6f;
             const uint32_t th = __half_as_ushort(__float2half_ru(tau));
             tau2 = th | (th << 16);
         }
@@ -564,45 +566,65 @@ pcm_fwd_kernel(const uint8_t* __restrict__ fa, const uint8_t* __restrict__ fb, c
 // ------------------------------------------------------------------------------------------------
 // The forward marked the entries (j, i) with |S_ji| < tau in nzmask; here each is re-evaluated as an fp32 dot product of
 // the fp32 normalised features (what the reference's fp32 matmul computes, network/resnet38_contrast.py:71) and its bit of
-// the sign mask is set to [S > 0].  One CTA = 128 rows j (their features in shared memory) x a range of stages; the
-// marked entries go through a shared-memory queue so that a warp works on four entries at a time (24 independent 128-byte
-// loads in flight per warp); each entry costs one K-float row from L2.
+// the sign mask is set to [S > 0].  S is symmetric and so (up to entries sitting exactly on tau, whose fp16 sign is
+// reliable by the definition of tau) is its near-zero mask: only the entries ABOVE the diagonal (i > j) are evaluated
+// and each result patches both (j, i) and (i, j) — half the row gathers, which are what this kernel costs (one K-float
+// row from L2 per entry).  One CTA = 128 rows j (their features in shared memory, one bulk copy) x a chunk of stages;
+// marked entries go through a shared-memory queue; a warp evaluates eight entries at a time, four lanes per entry with
+// all 12 float4 loads of the lane in flight at once (the first version walked one entry per warp with dependent loads:
+// 104 us at N = 8, 56x56).
 constexpr int kFixThreads = 256;
 constexpr int kFixQueue = 2048;
-constexpr int kFixBatch = 512;          // entries that make a flush worthwhile
 
+template <int KG>      // K / 16
 __global__ void __launch_bounds__(kFixThreads) pcm_sign_fixup_kernel(const float* __restrict__ fh32,
                                                                     const uint4* __restrict__ nzmask,
-                                                                    uint32_t* __restrict__ mask, int K, int HWpj, int NS,
-                                                                    int ncol, int parts) {
-    extern __shared__ __align__(16) uint8_t fix_smem[];
+                                                                    uint32_t* __restrict__ mask, int HWpj, int NS,
+                                                                    int ncol, int chunk) {
+    constexpr int K = 16 * KG;
+    extern __shared__ __align__(128) uint8_t fix_smem[];
     float* s_fj = reinterpret_cast<float*>(fix_smem);                          // [128][K]
     uint32_t* s_q = reinterpret_cast<uint32_t*>(fix_smem + static_cast<size_t>(kTile) * K * 4);
     __shared__ int s_cnt;
-    const int n = blockIdx.y, j0 = blockIdx.x * kTile;
-    const int s_begin = static_cast<int>(static_cast<long long>(NS) * blockIdx.z / parts);
-    const int s_end = static_cast<int>(static_cast<long long>(NS) * (blockIdx.z + 1) / parts);
+    __shared__ __align__(8) uint64_t s_bar;
+    const int n = blockIdx.z, j0 = blockIdx.x * kTile;
+    // stages of this CTA: its chunk, minus the stages that lie entirely below the diagonal (columns <= j0)
+    const int s_begin = max(static_cast<int>(blockIdx.y) * chunk, j0 / ncol);
+    const int s_end = min(NS, (static_cast<int>(blockIdx.y) + 1) * chunk);
+    if (s_begin >= s_end) return;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const float* fn = fh32 + static_cast<size_t>(n) * HWpj * K;
-    {
-        const float4* src = reinterpret_cast<const float4*>(fn + static_cast<size_t>(j0) * K);
-        float4* dst = reinterpret_cast<float4*>(s_fj);
-        for (int i = tid; i < kTile * K / 4; i += kFixThreads) dst[i] = __ldg(src + i);
+    if (tid == 0) {
+        s_cnt = 0;
+        mbar_init(smem_u32(&s_bar), 1);
+        mbar_fence_init();
+        const uint32_t bytes = static_cast<uint32_t>(kTile) * K * 4;
+        mbar_arrive_expect_tx(smem_u32(&s_bar), bytes);
+        // two halves: the copy engine streams one operation with only a few requests in flight
+        tma_load_1d(smem_u32(s_fj), fn + static_cast<size_t>(j0) * K, bytes / 2, smem_u32(&s_bar));
+        tma_load_1d(smem_u32(s_fj) + bytes / 2, fn + static_cast<size_t>(j0) * K + bytes / 8, bytes / 2, smem_u32(&s_bar));
     }
-    if (tid == 0) s_cnt = 0;
     __syncthreads();
     const int my_row = tid & (kTile - 1), my_sub = tid >> 7;                   // two stages are scanned per pass
+    const int my_j = j0 + my_row;
     uint32_t pend[4] = {0u, 0u, 0u, 0u};
     int pend_stage = 0;
     int s = s_begin;
-    bool any_pend = false;
+    bool any_pend = false, tile_ready = false;
+    const int sub = lane >> 2, l4 = lane & 3;                                  // entry of the warp's batch, lane inside it
     while (true) {
         if (!any_pend && s < s_end) {
             const int st = s + my_sub;
             if (st < s_end) {
-                const uint4 w = __ldg(nzmask + (static_cast<size_t>(n) * NS + st) * HWpj + j0 + my_row);
+                const uint4 w = __ldg(nzmask + (static_cast<size_t>(n) * NS + st) * HWpj + my_j);
                 pend[0] = w.x; pend[1] = w.y; pend[2] = w.z; pend[3] = w.w;
                 pend_stage = st;
+                // keep only the entries above the diagonal: column index i = st*ncol + col > j
+                const int lim = my_j - st * ncol;                                  // columns <= lim are dropped
+                if (lim >= 0) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) pend[c] &= ~valid_bits(lim + 1 - 32 * c);
+                }
             }
             s += kFixThreads / kTile;
         }
@@ -622,33 +644,49 @@ __global__ void __launch_bounds__(kFixThreads) pcm_sign_fixup_kernel(const float
         any_pend = __syncthreads_or((pend[0] | pend[1] | pend[2] | pend[3]) != 0u);
         const int cnt = min(s_cnt, kFixQueue);
         const bool done = !any_pend && s >= s_end;
-        if (any_pend || cnt >= kFixBatch || done) {
-            for (int e0 = warp * 4; e0 < cnt; e0 += (kFixThreads / 32) * 4) {
-                float acc[4] = {0.f, 0.f, 0.f, 0.f};
-                uint32_t ent[4];
+        if (any_pend || done) {
+            if (!tile_ready) {
+                mbar_wait(smem_u32(&s_bar), 0);
+                tile_ready = true;
+            }
+            for (int e0 = warp * 8; e0 < cnt; e0 += (kFixThreads / 32) * 8) {
+                const bool live = e0 + sub < cnt;
+                const uint32_t ent = live ? s_q[e0 + sub] : 0u;
+                const int row = ent >> 25, col = (ent >> 18) & 127, st = ent & 0x3ffff;
+                const int i = st * ncol + col;
+                const float4* fi = reinterpret_cast<const float4*>(fn + static_cast<size_t>(i) * K) + l4;
+                const uint32_t fj_s = smem_u32(s_fj + row * K + 4 * l4);
+                // a dead lane group reads row 0 (entry 0): every load is unconditional, so all KG of them are in flight at once
+                float4 x[KG];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    ent[u] = e0 + u < cnt ? s_q[e0 + u] : 0xffffffffu;
-                    if (ent[u] != 0xffffffffu) {
-                        const int row = ent[u] >> 25, col = (ent[u] >> 18) & 127, st = ent[u] & 0x3ffff;
-                        const float* fi = fn + (static_cast<size_t>(st) * ncol + col) * K + lane;
-                        const float* fj = s_fj + row * K + lane;
-                        for (int t = 0; t < K; t += 32) acc[u] = fmaf(__ldg(fi + t), fj[t], acc[u]);
-                    }
+                for (int t = 0; t < KG; ++t)      // volatile asm: ptxas otherwise keeps only two of the loads in flight
+                    asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];\n"
+                                 : "=f"(x[t].x), "=f"(x[t].y), "=f"(x[t].z), "=f"(x[t].w)
+                                 : "l"(fi + 4 * t));
+                __syncwarp();                     // a scheduling fence: the loads above stay above it
+                float acc = 0.f;
+#pragma unroll
+                for (int t = 0; t < KG; ++t) {
+                    float4 y;                     // volatile as well: keeps the shared-memory reads (and the FMAs) behind ALL the loads
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n"
+                                 : "=f"(y.x), "=f"(y.y), "=f"(y.z), "=f"(y.w)
+                                 : "r"(fj_s + 64u * t));
+                    acc = fmaf(x[t].x, y.x, acc);
+                    acc = fmaf(x[t].y, y.y, acc);
+                    acc = fmaf(x[t].z, y.z, acc);
+                    acc = fmaf(x[t].w, y.w, acc);
                 }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
-                }
-                const uint32_t en = lane == 0 ? ent[0] : lane == 1 ? ent[1] : lane == 2 ? ent[2] : ent[3];
-                if (lane < 4 && en != 0xffffffffu) {
-                    const float sv = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3];
-                    const int row = en >> 25, col = (en >> 18) & 127, st = en & 0x3ffff;
-                    const int c = col >> 5, b = col & 31;
+                acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+                if (live && l4 < 2) {
+                    // l4 = 0 patches (j, i), l4 = 1 the mirrored entry (i, j)
+                    const int j = j0 + row;
+                    const int pr = l4 == 0 ? j : i, pc = l4 == 0 ? i : j;
+                    const int pst = pc / ncol, pcol = pc - pst * ncol;
+                    const int b = pcol & 31;
                     const uint32_t bitv = 1u << ((b >> 1) + ((b & 1) << 4));
-                    uint32_t* wp = mask + ((static_cast<size_t>(n) * NS + st) * HWpj + j0 + row) * kMaskWords + c;
-                    if (sv > 0.f) atomicOr(wp, bitv);
+                    uint32_t* wp = mask + ((static_cast<size_t>(n) * NS + pst) * HWpj + pr) * kMaskWords + (pcol >> 5);
+                    if (acc > 0.f) atomicOr(wp, bitv);
                     else atomicAnd(wp, ~bitv);
                 }
             }
@@ -1241,15 +1279,31 @@ static int dispatch_bwd(const PcmPlan& pl, int N, bool split, wsegk_stream_t str
 // the sign fix-up of the precise mode on a workspace the forward has filled
 static int launch_fixup(const PcmPlan& pl, int N, wsegk_stream_t stream) {
     const size_t smem = static_cast<size_t>(kTile) * pl.K * 4 + static_cast<size_t>(kFixQueue) * 4;
-    WSEGK_CUDA_OK(cudaFuncSetAttribute(pcm_sign_fixup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(smem)));
     const int tiles = pl.HWpj / kTile;
-    // enough CTAs for two per SM; a part is at least two stages (the scan reads two stages per pass)
-    int parts = ceil_div(2 * 148, tiles * N);
-    parts = std::max(1, std::min(parts, std::max(1, pl.NS / 2)));
+    // CTA = (row tile, chunk of stages, image); the chunks below the diagonal exit at once, so about half of the grid
+    // works: aim at ~3 working CTAs per SM (two are resident), chunks of at least two stages (the scan reads two per pass)
+    const long long cells = static_cast<long long>(tiles) * N * pl.NS;
+    int chunk = static_cast<int>(std::min<long long>(std::max<long long>(2, cells / (2 * 3 * 148)), 64));
+    chunk = std::min(chunk, std::max(1, pl.NS));
+    const dim3 grid(tiles, ceil_div(pl.NS, chunk), N);
     prof_mark(4, stream);
-    pcm_sign_fixup_kernel<<<dim3(tiles, N, parts), kFixThreads, smem, stream>>>(
-        pl.fh32, reinterpret_cast<const uint4*>(pl.nzmask), pl.mask, pl.K, pl.HWpj, pl.NS, 2 * pl.wb, parts);
+#define WSEGK_FIX_CASE(KGV)                                                                                              \
+    case KGV:                                                                                                            \
+        WSEGK_CUDA_OK(cudaFuncSetAttribute(pcm_sign_fixup_kernel<KGV>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                           static_cast<int>(smem)));                                                     \
+        pcm_sign_fixup_kernel<KGV><<<grid, kFixThreads, smem, stream>>>(                                                 \
+            pl.fh32, reinterpret_cast<const uint4*>(pl.nzmask), pl.mask, pl.HWpj, pl.NS, 2 * pl.wb, chunk);              \
+        break;
+    switch (pl.K / 16) {           // K is a multiple of 32 (pcm_check)
+        WSEGK_FIX_CASE(2)
+        WSEGK_FIX_CASE(4)
+        WSEGK_FIX_CASE(6)
+        WSEGK_FIX_CASE(8)
+        WSEGK_FIX_CASE(10)
+        default:
+            WSEGK_FIX_CASE(12)
+    }
+#undef WSEGK_FIX_CASE
     prof_mark(5, stream);
     count_launches(1);
     return WSEGK_OK;

@@ -9,6 +9,7 @@ margin), min-pool, ER and ECR, the two top-k's done by value with a radix select
 """
 from __future__ import annotations
 
+import itertools
 import random as _pyrandom
 from typing import Dict, Optional, Tuple, Union
 
@@ -16,6 +17,11 @@ import torch
 import torch.nn.functional as F
 
 from . import ops
+
+# step number of the device-generated mining keys when the caller does not pass one: advances with every call, so that the
+# "random 50 %" of the hard-pixel mining is a fresh draw per training step, as the reference's random.sample calls are
+# (contrast_train.py:316,370)
+_AUTO_STEP = itertools.count()
 
 LOSS_KEYS = ('loss', 'loss_cls', 'loss_er', 'loss_ecr', 'loss_nce', 'loss_intra_nce',
              'loss_cross_nce', 'loss_cross_nce2')          # contrast_train.py:111-118
@@ -52,11 +58,15 @@ def contrast_terms(f_proj1: torch.Tensor, cam_rv1_down: torch.Tensor, f_proj2: t
                    grid: Optional[Tuple[int, int]] = None, rng: Union[int, _pyrandom.Random, None] = None,
                    mining_seed: int = 0, group=None, want_mined: bool = False,
                    keys: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
-                   mining: str = "shard") -> Dict[str, torch.Tensor]:
+                   mining: str = "shard", step: Optional[int] = None) -> Dict[str, torch.Tensor]:
     """contrast_train.py:176-392.  ``label``: [N,21] (or [N,21,1,1]) with background = 1.
-    ``rng``: None -> Philox mining keys generated on the device (no host work, no sync; ``mining_seed`` = seed); an int / ``random.Random`` -> reproduce the reference's
-    Python-RNG draws.  ``keys``: two int32 [P] device tensors to use as mining keys instead (nothing is created on the host,
-    so the call can be captured in a CUDA graph).  ``group``: process group over which prototypes are whole-batch (data parallel).
+    ``rng``: None -> Philox mining keys generated on the device (no host work, no sync): key = Philox(global pixel index,
+    ``step``, ``mining_seed``).  ``step`` is the training-step number — every rank of a data-parallel job must pass the same
+    one; None = a process-local counter that advances with every call (identical on all ranks as long as they make the same
+    calls), so consecutive steps mine different random halves.  An int / ``random.Random`` ``rng`` -> reproduce the
+    reference's Python-RNG draws.  ``keys``: two int32 [P] device tensors to use as mining keys instead (nothing is created
+    on the host, so the call can be captured in a CUDA graph; the caller refreshes them between replays, e.g. with
+    ``ops.mining_keys(step=...)`` into the same tensors).  ``group``: process group over which prototypes are whole-batch (data parallel).
     ``mining``: "shard" = every rank mines hard pixels inside its own shard; "global" = over the whole batch of ``group`` as
     the single-process reference does (one more NVLink exchange; the reported intra losses are then R x this rank's share,
     so their mean over ranks — what DDP does to the gradients — is the single-process value)."""
@@ -76,11 +86,13 @@ def contrast_terms(f_proj1: torch.Tensor, cam_rv1_down: torch.Tensor, f_proj2: t
         key1, key2 = keys
     elif rng is None:
         p = pl1.numel()
+        if step is None:
+            step = next(_AUTO_STEP)
         if pl1.is_cuda:         # generated on the device: no host RNG, no copy, no sync
             from . import dist as _dist
             index0 = _dist.rank_world(group)[0] * p
-            key1 = ops.mining_keys(p, mining_seed, pl1.device, stream_id=1, index0=index0)
-            key2 = ops.mining_keys(p, mining_seed, pl1.device, stream_id=2, index0=index0)
+            key1 = ops.mining_keys(p, mining_seed, pl1.device, step=step, stream_id=1, index0=index0)
+            key2 = ops.mining_keys(p, mining_seed, pl1.device, step=step, stream_id=2, index0=index0)
         else:
             key1 = ops.hash_keys(p, 2 * mining_seed + 1, pl1.device)
             key2 = ops.hash_keys(p, 2 * mining_seed + 2, pl1.device)
@@ -99,9 +111,10 @@ def contrast_terms(f_proj1: torch.Tensor, cam_rv1_down: torch.Tensor, f_proj2: t
                                                        global_group=gg)
         out.update({'grad_f1': g1, 'grad_f2': g2, 'mined1': m1, 'mined2': m2})
     else:
-        losses = ops.contrast_loss(f1, f2, proto1, proto2, pl1, pl2, key1, key2, gg)
+        loss_nce, losses = ops.contrast_loss(f1, f2, proto1, proto2, pl1, pl2, key1, key2, gg)
+        out['loss_nce'] = loss_nce                    # the only differentiable entry (its parts are reported values)
     out.update({
-        'loss_nce': losses[9], 'loss_intra_nce': losses[8], 'loss_cross_nce': losses[6],
+        'loss_nce': out.get('loss_nce', losses[9]), 'loss_intra_nce': losses[8], 'loss_cross_nce': losses[6],
         'loss_cross_nce2': losses[7], 'losses_raw': losses,
         'pseudo_label1': pl1, 'pseudo_label2': pl2, 'norm_cam1': norm1, 'norm_cam2': norm2,
         'top_indices1': ti1, 'top_indices2': ti2, 'prototypes1': proto1, 'prototypes2': proto2,
@@ -113,9 +126,10 @@ def contrast_step_loss(cam1, cam_rv1, f_proj1, cam_rv1_down, cam2, cam_rv2, f_pr
                        label20: torch.Tensor, bg_threshold: float = 0.20,
                        view2_size: Tuple[int, int] = (128, 128),
                        rng: Union[int, _pyrandom.Random, None] = None, mining_seed: int = 0,
-                       group=None) -> Dict[str, torch.Tensor]:
+                       group=None, step: Optional[int] = None) -> Dict[str, torch.Tensor]:
     """Everything in contrast_train.py:138-395 given both views' network outputs.  ``label20``: [N,20] multi-hot.
-    Differentiable w.r.t. the eight network outputs; returns the 8 logged scalars (plus diagnostics)."""
+    Differentiable w.r.t. the eight network outputs; returns the 8 logged scalars (plus diagnostics).  ``step``: the
+    training-step number for the device-generated mining keys (see ``contrast_terms``; None = auto-advancing)."""
     n = label20.shape[0]
     label = torch.cat([torch.ones(n, 1, dtype=torch.float32, device=cam1.device),
                        label20.to(cam1.device, torch.float32)], dim=1)
@@ -131,7 +145,7 @@ def contrast_step_loss(cam1, cam_rv1, f_proj1, cam_rv1_down, cam2, cam_rv2, f_pr
     loss_cls = (cls1 + cls2) / 2 + (rvmin1 + rvmin2) / 2                                  # :174
     grid = (view2_size[0] // 8, view2_size[1] // 8)                                       # :179
     terms = contrast_terms(f_proj1, cam_rv1_down, f_proj2, cam_rv2_down, label, bg_threshold, grid=grid,
-                           rng=rng, mining_seed=mining_seed, group=group)
+                           rng=rng, mining_seed=mining_seed, group=group, step=step)
     out = dict(terms)
     out.update({'loss': loss_cls + loss_er + loss_ecr + terms['loss_nce'], 'loss_cls': loss_cls,
                 'loss_er': loss_er, 'loss_ecr': loss_ecr})
@@ -142,7 +156,7 @@ def contrast_step_loss_lazy(cam1_small, cam_rv1_down, f_proj1, cam2_small, cam_r
                             label20: torch.Tensor, image_size: Tuple[int, int], bg_threshold: float = 0.20,
                             view2_size: Tuple[int, int] = (128, 128),
                             rng: Union[int, _pyrandom.Random, None] = None, mining_seed: int = 0,
-                            group=None) -> Dict[str, torch.Tensor]:
+                            group=None, step: Optional[int] = None) -> Dict[str, torch.Tensor]:
     """``contrast_step_loss`` for a network that does NOT enlarge its maps.
 
     ``Net.forward`` ends by enlarging the stride-8 ``cam`` and ``cam_rv_down`` x8 (network/resnet38_contrast.py:57-59: four
@@ -165,7 +179,7 @@ def contrast_step_loss_lazy(cam1_small, cam_rv1_down, f_proj1, cam2_small, cam_r
     loss_cls = (cls1 + cls2) / 2 + (rvmin1 + rvmin2) / 2                                  # :174
     grid = (view2_size[0] // 8, view2_size[1] // 8)                                       # :179
     terms = contrast_terms(f_proj1, cam_rv1_down, f_proj2, cam_rv2_down, label, bg_threshold, grid=grid,
-                           rng=rng, mining_seed=mining_seed, group=group)
+                           rng=rng, mining_seed=mining_seed, group=group, step=step)
     out = dict(terms)
     out.update({'loss': loss_cls + loss_er + loss_ecr + terms['loss_nce'], 'loss_cls': loss_cls,
                 'loss_er': loss_er, 'loss_ecr': loss_ecr})

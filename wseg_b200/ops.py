@@ -467,21 +467,32 @@ def prototypes(norm_cam: torch.Tensor, f_proj: torch.Tensor, k: Optional[int] = 
     return proto_finalize(tv, ti, tf, k)
 
 
-_SYMM_FAILED = False
+_SYMM_MODE = {}            # (group, dims, device) -> SymmExchange, or None = every rank agreed to use NCCL
 
 
 def _symm_exchange(group, c, k, d, device):
-    global _SYMM_FAILED
-    if _SYMM_FAILED:
-        return None
+    """The NVLink exchange object, or None if ANY rank of the group could not set it up.  The decision is collective (one
+    all_reduce(MIN) of a success flag at set-up time): a rank that fell back to NCCL on its own would sit in an all-gather
+    while its peers spin on NVLink flags that never arrive."""
+    key = (id(group), c, k, d, str(device))
+    if key in _SYMM_MODE:
+        return _SYMM_MODE[key]
+    import torch.distributed as _td
     from . import dist as _dist
+    ex, err = None, None
     try:
-        return _dist.SymmExchange.get(group, c, k, d, device)
-    except Exception as exc:          # no peer access / no symmetric-memory support on this stack: NCCL all-gather instead
+        ex = _dist.SymmExchange.get(group, c, k, d, device)
+    except Exception as exc:          # no peer access / no symmetric-memory support on this stack
+        err = exc
+    ok = torch.tensor([1 if ex is not None else 0], dtype=torch.int32, device=device)
+    _td.all_reduce(ok, op=_td.ReduceOp.MIN, group=group)
+    if int(ok.item()) == 0:
         import warnings
-        warnings.warn(f"wseg_b200: NVLink symmetric exchange unavailable ({type(exc).__name__}: {exc}); using NCCL")
-        _SYMM_FAILED = True
-        return None
+        why = f"{type(err).__name__}: {err}" if err is not None else "a peer rank could not set it up"
+        warnings.warn(f"wseg_b200: NVLink symmetric exchange unavailable ({why}); every rank uses NCCL")
+        ex = None
+    _SYMM_MODE[key] = ex
+    return ex
 
 
 def _prototypes_nvlink(ex, tv, ti, tf, k: int, view: int):
@@ -570,25 +581,25 @@ def contrast_loss_raw(x1, x2, proto1, proto2, pl1, pl2, key1, key2, grad_scale: 
 
 
 class _ContrastLoss(torch.autograd.Function):
-    """losses[10] as a differentiable function of (x1, x2); the gradient of ``loss_nce`` (slot 9) is produced by
-    the same fused call, so backward only rescales it.  The other slots are reported values (no gradient)."""
+    """(loss_nce, losses[10]) as a function of (x1, x2).  Only ``loss_nce`` is differentiable — its gradient is produced by
+    the same fused call, so backward only rescales it; the 10 reported values are marked non-differentiable, so summing or
+    re-weighting the parts instead of using ``loss_nce`` raises instead of silently yielding a zero gradient."""
 
     @staticmethod
     def forward(ctx, x1, x2, proto1, proto2, pl1, pl2, key1, key2, global_group=None):
         losses, g1, g2, _, _ = contrast_loss_raw(x1, x2, proto1, proto2, pl1, pl2, key1, key2, global_group=global_group)
         ctx.save_for_backward(g1, g2)
-        return losses
+        ctx.mark_non_differentiable(losses)
+        return losses[9].clone(), losses
 
     @staticmethod
-    def backward(ctx, grad_losses):
+    def backward(ctx, grad_nce, _grad_losses):
         g1, g2 = ctx.saved_tensors
-        # d(loss_nce) flows through slot 9; slots 6,7,8 are its parts and may carry gradient too when a caller
-        # sums them instead — support the reference's usage (only loss_nce enters the total, :392-395).
-        scale = grad_losses[9]
-        return g1 * scale, g2 * scale, None, None, None, None, None, None, None
+        return g1 * grad_nce, g2 * grad_nce, None, None, None, None, None, None, None
 
 
-def contrast_loss(x1, x2, proto1, proto2, pl1, pl2, key1, key2, global_group=None) -> torch.Tensor:
+def contrast_loss(x1, x2, proto1, proto2, pl1, pl2, key1, key2, global_group=None):
+    """Returns (loss_nce — differentiable w.r.t. x1, x2 —, losses [10] reported values without gradient)."""
     return _ContrastLoss.apply(x1, x2, proto1, proto2, pl1, pl2, key1, key2, global_group)
 
 
