@@ -45,19 +45,19 @@ def peaks():
 
 
 # ------------------------------------------------------------------------------------------------ workload
-def host_inputs(n: int, seed: int):
+def host_inputs(n: int, seed: int, view1=VIEW1, view2=VIEW2):
     """Head-level synthetic inputs on the host (pinned), per SURVEY.md 8d."""
     from wseg_b200 import synth
     g = synth.gen(seed)
     out = {}
-    for v, (H, W) in (("1", VIEW1), ("2", VIEW2)):
+    for v, (H, W) in (("1", view1), ("2", view2)):
         h, w = H // 8, W // 8
         out["cam" + v] = 0.05 * torch.randn(n, C_CLS, h, w, generator=g)
         out["f" + v] = torch.randn(n, K_PCM, h, w, generator=g)
         out["fproj" + v] = F.relu(0.02 * torch.randn(n, D_PROJ, h, w, generator=g) + 0.01)
         out["g_rv_down" + v] = 1e-3 * torch.randn(n, C_CLS, h, w, generator=g)
     for name in ("g_n1", "g_rv1", "g_n2", "g_rv2"):
-        out[name] = 1e-3 * torch.randn(n, C_CLS, VIEW2[0], VIEW2[1], generator=g)
+        out[name] = 1e-3 * torch.randn(n, C_CLS, view2[0], view2[1], generator=g)
     out["label"] = synth.label_with_bg(synth.labels(n, seed + 1))
     return {k: v.contiguous().pin_memory() if torch.cuda.is_available() else v.contiguous() for k, v in out.items()}
 
@@ -65,10 +65,12 @@ def host_inputs(n: int, seed: int):
 class HotPath:
     """One step of the hot path on resident inputs, straight through the C-ABI operators (wseg_b200.ops)."""
 
-    def __init__(self, n: int, dev, seed: int, group=None):
+    def __init__(self, n: int, dev, seed: int, group=None, view1=VIEW1, view2=VIEW2):
         from wseg_b200 import ops
         self.ops, self.n, self.dev, self.group = ops, n, dev, group
-        self.host = host_inputs(n, seed)
+        self.view1, self.view2 = view1, view2
+        VIEW1, VIEW2 = view1, view2
+        self.host = host_inputs(n, seed, view1, view2)
         self.d = {k: v.to(dev) for k, v in self.host.items()}
         d = self.d
         # full-resolution cam / cam_rv as Net.forward emits them (bilinear x8 of the stride-8 maps), resident
@@ -81,9 +83,9 @@ class HotPath:
             camn = ops.cam_norm(d["cam2"])
             rv, _ = ops.pcm_forward(camn, d["f2"])
             d["rv2_full"] = F.interpolate(rv, VIEW2, mode="bilinear", align_corners=True)
-        self.key1 = ops.hash_keys(n * 256, 2 * seed + 1, dev)
-        self.key2 = ops.hash_keys(n * 256, 2 * seed + 2, dev)
         self.grid = (VIEW2[0] // 8, VIEW2[1] // 8)
+        self.key1 = ops.hash_keys(n * self.grid[0] * self.grid[1], 2 * seed + 1, dev)
+        self.key2 = ops.hash_keys(n * self.grid[0] * self.grid[1], 2 * seed + 2, dev)
         self.pixels = n * (VIEW1[0] // 8) * (VIEW1[1] // 8)
 
     def step(self):
@@ -92,6 +94,7 @@ class HotPath:
         view 2, the seed/prototype/NCE chain after both K2 forwards, and K1b on the two `cam` maps (which do not depend
         on the PCM).  Every intermediate is returned so nothing is recycled before the join."""
         ops, d = self.ops, self.d
+        VIEW1, VIEW2 = self.view1, self.view2
         if not hasattr(self, "_streams"):
             prio = int(os.environ.get("WSEG_BENCH_PRIO", "1"))
             # the view-1 chain (K1a -> K2 fwd -> K1b -> K2 bwd) is the critical path: its stream gets the higher priority
@@ -439,12 +442,105 @@ def config_dict(n_gpus):
             "pcm_mode": os.environ.get("WSEGK_PCM_MODE", "default")}
 
 
+def pcm_roofline(hp, pk, flush, args):
+    """Roofline of the dominant kernel: the PCM main kernels on view 1 of `hp`, timed alone with CUDA events on the launching
+    stream (inside the library, around the kernel), L2 flushed before every launch -> burst peak."""
+    ops, d, n = hp.ops, hp.d, hp.n
+    h, w = hp.view1[0] // 8, hp.view1[1] // 8
+    fwd_ms, bwd_ms, fix_ms = [], [], []
+    camn1 = ops.cam_norm(d["cam1"])
+    ops.pcm_profile(True)
+    for _ in range(max(3, args.warmup)):
+        rv1, ws1 = ops.pcm_forward(camn1, d["f1"])
+        ops.pcm_backward(d["f1"], camn1, rv1, d["g_rv_down1"], ws1)
+    for _ in range(max(5, args.steps)):
+        flush.zero_()
+        rv1, ws1 = ops.pcm_forward(camn1, d["f1"])
+        ops.pcm_backward(d["f1"], camn1, rv1, d["g_rv_down1"], ws1)
+        a, b = ops.pcm_main_ms()
+        fwd_ms.append(a)
+        bwd_ms.append(b)
+        fix_ms.append(ops.pcm_fixup_ms())
+    ops.pcm_profile(False)
+    hw = h * w
+    fl_fwd = 2.0 * n * hw * hw * (K_PCM + C_CLS)
+    fl_bwd = 2.0 * n * hw * hw * (2 * K_PCM + C_CLS)
+    avg = lambda v: sum(v) / len(v)
+    tf_fwd = fl_fwd / (avg(fwd_ms) * 1e-3) / 1e12
+    tf_bwd = fl_bwd / (avg(bwd_ms) * 1e-3) / 1e12
+    dom = "pcm_bwd_kernel" if avg(bwd_ms) >= avg(fwd_ms) else "pcm_fwd_kernel"
+    ach = tf_bwd if dom == "pcm_bwd_kernel" else tf_fwd
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath) and (n, h, w) == (N_PER_GPU, VIEW1[0] // 8, VIEW1[1] // 8):
+        traffic = json.load(open(tpath)).get(dom)
+    roofline = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": ach / pk["bf16_tflops"], "traffic": traffic, "peak_source": pk["source"] + " (burst)",
+                "algorithmic_flops_per_launch": fl_bwd if dom == "pcm_bwd_kernel" else fl_fwd,
+                "ms_per_launch": avg(bwd_ms) if dom == "pcm_bwd_kernel" else avg(fwd_ms),
+                "other": {"pcm_fwd_kernel": {"ms": avg(fwd_ms), "tflops": tf_fwd, "frac": tf_fwd / pk["bf16_tflops"]},
+                          "pcm_bwd_kernel": {"ms": avg(bwd_ms), "tflops": tf_bwd, "frac": tf_bwd / pk["bf16_tflops"]},
+                          "pcm_fwd+bwd": {"ms": avg(fwd_ms) + avg(bwd_ms),
+                                          "frac": (fl_fwd + fl_bwd) / ((avg(fwd_ms) + avg(bwd_ms)) * 1e-3) / 1e12 / pk["bf16_tflops"]}}}
+    if ops.get_pcm_mode() == "precise":
+        # what the tensor cores actually execute (DESIGN.md 3) over the padded tiles: forward = ONE fp16 S product + a
+        # 64-column P V product per stage (the near-zero signs are re-evaluated in fp32 by the fix-up kernel, off the
+        # tensor cores); backward = a K=144 split-factor product + the K=192 gradient product
+        lay = ops.pcm_layout(n, C_CLS, K_PCM, h, w)
+        tiles = 2.0 * n * lay["HWpi"] * lay["HWpj"]
+        ex_fwd, ex_bwd = tiles * (K_PCM + 64), tiles * (144 + K_PCM)
+        for name, ex, ms in (("pcm_fwd_kernel", ex_fwd, avg(fwd_ms)), ("pcm_bwd_kernel", ex_bwd, avg(bwd_ms))):
+            roofline["other"][name]["executed_tflops"] = ex / (ms * 1e-3) / 1e12
+            roofline["other"][name]["executed_frac"] = ex / (ms * 1e-3) / 1e12 / pk["bf16_tflops"]
+        if fix_ms and fix_ms[-1] > 0:
+            roofline["other"]["pcm_sign_fixup_kernel"] = {"ms": avg(fix_ms), "note": "fp32 re-evaluation of the near-zero entries of S "
+                                                          "(CUDA cores, L2 gathers); off the critical path in the step (own stream)"}
+        roofline["note"] = ("frac = ALGORITHMIC flops (SURVEY 8d) / measured bf16 peak; executed_* counts the MMA flops really "
+                            "issued over the padded tiles")
+    return roofline, fl_fwd, fl_bwd
+
+
+def step_roofline_of(hp, pk, ms_per_step, fl_fwd1, fl_bwd1):
+    """Whole-step roofline: PCM flops of BOTH views / sustained tensor peak + HBM bytes / measured HBM bandwidth, with the
+    bytes counted two ways: (a) SURVEY 8d's formula (every one of the N*C full-resolution planes read and written), (b) the
+    bytes the step really has to move — K1b reads only the planes of LABELLED classes (the others are multiplied by a zero
+    label: their output and gradient are zero whatever they hold) but still writes the dense outputs and gradients."""
+    n = hp.n
+    V1, V2 = hp.view1, hp.view2
+    hw1, hw2 = (V1[0] // 8) * (V1[1] // 8), (V2[0] // 8) * (V2[1] // 8)
+    g = hp.grid[0] * hp.grid[1]
+    fl = fl_fwd1 + fl_bwd1 + 2.0 * n * hw2 * hw2 * ((K_PCM + C_CLS) + (2 * K_PCM + C_CLS))
+    lab = float(hp.d["label"].reshape(n, -1).sum().item()) / (n * C_CLS)      # share of labelled planes (background included)
+    px1, px2 = V1[0] * V1[1], V2[0] * V2[1]
+
+    maps = ((px1, px2), (px1, px2), (px2, px2), (px2, px2))                   # cam1, cam_rv1 (full res -> loss size), cam2, cam_rv2
+    # (a) SURVEY 8d: N*C*(H*W + out)*4 per tensor forward, the same again backward
+    k1b_survey = sum(2.0 * n * C_CLS * 4 * (src + dst) for src, dst in maps)
+    # (b) forward reads the labelled input planes and writes the output; backward reads the labelled input planes, grad_out
+    # and out, and writes the DENSE input gradient (zeros for the unlabelled planes)
+    k1b_required = sum(n * C_CLS * 4 * ((lab * src + dst) + (lab * src + 2 * dst + src)) for src, dst in maps)
+    pcm_io = sum(n * hw * (K_PCM + 2 * C_CLS) * 4 + n * hw * (2 * K_PCM + 3 * C_CLS) * 4 for hw in (hw1, hw2))
+    small = 2 * (2 * n * C_CLS * g * 4 + 2 * n * g * D_PROJ * 4 * 2) + 2 * n * C_CLS * (hw1 + hw2) * 4
+    t_tensor = fl / (pk["bf16_tflops_sustained"] * 1e12)
+    out = {}
+    for name, k1b in (("survey_formula", k1b_survey), ("bytes_required", k1b_required)):
+        by = k1b + pcm_io + small
+        t = t_tensor + by / (pk["hbm_gbs"] * 1e9)
+        out[name] = {"t_roof_ms": t * 1e3, "frac": t * 1e3 / ms_per_step, "hbm_mb": by / 1e6}
+    out["t_roof_ms"] = out["survey_formula"]["t_roof_ms"]
+    out["frac"] = out["survey_formula"]["frac"]
+    out["labelled_plane_share"] = lab
+    out["note"] = ("t_roof = PCM algorithmic flops (both views) / sustained bf16 peak + HBM bytes / measured HBM bandwidth; "
+                   "survey_formula charges K1b with all N*C planes (SURVEY 8d), bytes_required only with the labelled ones it has to read")
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ arms
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_sample = 1
+    n_sample = N_PER_GPU                     # the same configuration as the GPU arm: one step = one batch of 8 images
     for _ in range(args.warmup):
         cpu_reference_sample(n_sample, 1234, 1)
     t0 = time.perf_counter()
@@ -461,7 +557,7 @@ def run_reference(args):
             "config": config_dict(args.gpus),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"oracle/reference_fn.py (restated reference, ATen fp32 on {cores} host threads), "
-                                       f"{n_sample} image of the workload per step"},
+                                       f"{n_sample} images (the GPU arm's per-GPU batch) per step", "same_config": True},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -495,7 +591,6 @@ def run_ours(args):
     l0 = ops.launch_count()
     hp.step()
     launches_per_step = ops.launch_count() - l0
-    fwd_ms, bwd_ms = [], []
     stepper, mode = hp, "eager"
     if not args.no_graph:
         try:
@@ -517,58 +612,8 @@ def run_ours(args):
     total_pix = hp.pixels * world
     value = total_pix / (ms_per_step * 1e-3) / 1e6
 
-    # -------- roofline of the dominant kernel: PCM main kernels on view 1, timed alone (burst peak)
-    d = hp.d
-    camn1 = ops.cam_norm(d["cam1"])
-    ops.pcm_profile(True)
-    for _ in range(max(3, args.warmup)):
-        rv1, ws1 = ops.pcm_forward(camn1, d["f1"])
-        ops.pcm_backward(d["f1"], camn1, rv1, d["g_rv_down1"], ws1)
-    for _ in range(max(5, args.steps)):
-        flush.zero_()
-        rv1, ws1 = ops.pcm_forward(camn1, d["f1"])
-        ops.pcm_backward(d["f1"], camn1, rv1, d["g_rv_down1"], ws1)
-        a, b = ops.pcm_main_ms()
-        fwd_ms.append(a)
-        bwd_ms.append(b)
-    ops.pcm_profile(False)
-    hw = (VIEW1[0] // 8) * (VIEW1[1] // 8)
-    fl_fwd = 2.0 * N_PER_GPU * hw * hw * (K_PCM + C_CLS)
-    fl_bwd = 2.0 * N_PER_GPU * hw * hw * (2 * K_PCM + C_CLS)
-    avg = lambda v: sum(v) / len(v)
-    tf_fwd = fl_fwd / (avg(fwd_ms) * 1e-3) / 1e12
-    tf_bwd = fl_bwd / (avg(bwd_ms) * 1e-3) / 1e12
-    dom = "pcm_bwd_kernel" if avg(bwd_ms) >= avg(fwd_ms) else "pcm_fwd_kernel"
-    ach = tf_bwd if dom == "pcm_bwd_kernel" else tf_fwd
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(dom)
-    roofline = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": ach / pk["bf16_tflops"], "traffic": traffic, "peak_source": pk["source"] + " (burst)",
-                "algorithmic_flops_per_launch": fl_bwd if dom == "pcm_bwd_kernel" else fl_fwd,
-                "ms_per_launch": avg(bwd_ms) if dom == "pcm_bwd_kernel" else avg(fwd_ms),
-                "other": {"pcm_fwd_kernel": {"ms": avg(fwd_ms), "tflops": tf_fwd, "frac": tf_fwd / pk["bf16_tflops"]},
-                          "pcm_bwd_kernel": {"ms": avg(bwd_ms), "tflops": tf_bwd, "frac": tf_bwd / pk["bf16_tflops"]}}}
-    if ops.get_pcm_mode() == "precise":
-        # what the tensor cores actually execute: the split-precision forward runs 3 S products + a 64-column
-        # PV product per stage over the padded tiles, the backward a K=144 factor product + the K=192 gradient product
-        lay = ops.pcm_layout(N_PER_GPU, C_CLS, K_PCM, VIEW1[0] // 8, VIEW1[1] // 8)
-        tiles = 2.0 * N_PER_GPU * lay["HWpi"] * lay["HWpj"]
-        ex_fwd, ex_bwd = tiles * (3 * K_PCM + 64), tiles * (144 + K_PCM)
-        for name, ex, ms in (("pcm_fwd_kernel", ex_fwd, avg(fwd_ms)), ("pcm_bwd_kernel", ex_bwd, avg(bwd_ms))):
-            roofline["other"][name]["executed_tflops"] = ex / (ms * 1e-3) / 1e12
-            roofline["other"][name]["executed_frac"] = ex / (ms * 1e-3) / 1e12 / pk["bf16_tflops"]
-        roofline["note"] = ("frac = ALGORITHMIC flops (SURVEY 8d) / measured bf16 peak; executed_* counts the MMA flops the "
-                            "split-precision scheme really issues (3 S products for the 1e-3 gradient bar)")
-    # whole-step roofline: PCM flops / tensor peak + algorithmic HBM bytes / measured HBM bandwidth
-    n = N_PER_GPU
-    k1b = 2 * 2 * n * C_CLS * (VIEW1[0] * VIEW1[1] + VIEW2[0] * VIEW2[1]) * 4 + 2 * 2 * n * C_CLS * 2 * VIEW2[0] * VIEW2[1] * 4
-    pcm_b = n * hw * (K_PCM + 2 * C_CLS) * 4 + n * hw * (2 * K_PCM + 3 * C_CLS) * 4
-    small = 2 * (2 * n * C_CLS * 256 * 4 + 2 * n * 256 * D_PROJ * 4 * 2)
-    t_roof = (fl_fwd + fl_bwd) / (pk["bf16_tflops_sustained"] * 1e12) + (k1b + pcm_b + small + 2 * n * C_CLS * hw * 4) / (pk["hbm_gbs"] * 1e9)
-    step_roofline = {"t_roof_ms": t_roof * 1e3, "frac": t_roof * 1e3 / ms_per_step,
-                     "note": "PCM flops / sustained bf16 peak + algorithmic bytes of K1a,K1b,K1c,K3,K4,K2 io / measured HBM"}
+    roofline, fl_fwd, fl_bwd = pcm_roofline(hp, pk, flush, args)
+    step_roofline = step_roofline_of(hp, pk, ms_per_step, fl_fwd, fl_bwd)
 
     # -------- end-to-end arm: host buffers, public API
     clk._stop.set()                                  # pause sampling outside the timed regions
@@ -618,11 +663,31 @@ def run_ours(args):
                                 "enlargement + ops.fullres_norm"},
             "roofline": roofline, "step_roofline": step_roofline, "wall_ms_per_step_incl_flush": wall_ms / args.steps}
 
+    if world == 1 and not args.no_extra:
+        # configs[3] of BASELINE.json beside the headline: batch 16 @512x512 (64x64 features), view 2 = 0.5x (256x256 ->
+        # 32x32 loss grid, P = 16 384 loss pixels), hard-pixel mining on — resident inputs, CUDA graph, same timing rules
+        del stepper, e2e, e2e_lazy
+        torch.cuda.empty_cache()
+        try:
+            hp3 = HotPath(16, dev, seed=4321, view1=(512, 512), view2=(256, 256))
+            st3 = GraphedStep(hp3) if not args.no_graph else hp3
+            ms3, _ = time_steps(st3.step, args.steps, args.warmup, dev, flush, barrier)
+            ms3 /= args.steps
+            rf3, f3, b3 = pcm_roofline(hp3, pk, flush, args)
+            line["extra_configs"] = {"configs[3]": {
+                "workload": "batch 16 @512x512 (64x64 stride-8 features, K=192, D=128), view 2 256x256 (0.5x) -> 32x32 loss grid, mining on",
+                "value": hp3.pixels / (ms3 * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms3,
+                "gpu_launches_per_step": int(getattr(st3, "launches", 0)), "roofline": rf3,
+                "step_roofline": step_roofline_of(hp3, pk, ms3, f3, b3)}}
+            del st3, hp3
+        except Exception as exc:
+            line["extra_configs"] = {"configs[3]": {"error": f"{type(exc).__name__}: {exc}"}}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        best, pix = cpu_reference_sample(1, 1234, 2)
+        best, pix = cpu_reference_sample(N_PER_GPU, 1234, 2)
         line["cpu_baseline"] = {"value": pix / best / 1e6, "unit": UNIT, "cores": torch.get_num_threads(),
-                                "kind": "port", "sample": "oracle/reference_fn.py on host threads, 1 image of the "
-                                                          "workload (PCM fwd+bwd at 56x56, K1b at 448x448, losses), best of 2"}
+                                "kind": "port", "same_config": True,
+                                "sample": f"oracle/reference_fn.py on host threads, one step of the workload = {N_PER_GPU} images "
+                                          "(PCM fwd+bwd at 56x56, K1b at 448x448, losses), best of 2"}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -657,6 +722,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the configs[3] line")
     ap.add_argument("--no-graph", action="store_true", help="time the resident step eagerly instead of as a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":

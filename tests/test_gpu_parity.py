@@ -803,3 +803,75 @@ def test_net_training_step_end_to_end(cuda_dev):
     grads = [p.grad for p in (net.fc8.weight, net.f9.weight, net.fc_proj.weight, net.f8_3.weight)]
     assert all(gr is not None and bool(torch.isfinite(gr).all()) and float(gr.abs().max()) > 0 for gr in grads)
     assert net.conv1a.weight.grad is None                                   # frozen layers (not_training) stay frozen
+
+
+def test_mining_keys_advance_with_the_step(cuda_dev):
+    """The device-generated 'random 50 %' of the hard-pixel mining is a fresh draw per training step, as the reference's
+    random.sample calls are (contrast_train.py:316,370): two steps mine different sets, the same step number reproduces
+    the same sets, and the auto-advancing default never repeats the previous call."""
+    n = 4
+    a, b = _views(n, (192, 192), (128, 128), seed=5, dev=cuda_dev)
+    label = synth.label_with_bg(synth.labels(n, seed=5)).to(cuda_dev)
+    run = lambda **kw: L.contrast_terms(a["f_proj"], a["cam_rv_down"], b["f_proj"], b["cam_rv_down"], label, 0.2,
+                                        grid=(16, 16), want_mined=True, **kw)
+    s3, s3b, s4 = run(step=3), run(step=3), run(step=4)
+    assert torch.equal(s3["mined1"], s3b["mined1"]) and torch.equal(s3["mined2"], s3b["mined2"])
+    assert not torch.equal(s3["mined1"], s4["mined1"]) and not torch.equal(s3["mined2"], s4["mined2"])
+    assert int(s3["mined1"].sum()) == int(s4["mined1"].sum())                   # same set SIZES (they depend on the seeds only)
+    auto1, auto2 = run(), run()
+    assert not torch.equal(auto1["mined1"], auto2["mined1"])
+
+
+def test_concurrent_host_threads(cuda_dev):
+    """The ABI is re-entrant across host threads and streams, as DataParallel.parallel_apply (contrast_train.py:108) and the
+    per-device threads of contrast_infer.py:47,58-71 need: two Python threads, each on its own stream, run the PCM forward /
+    backward and the contrast terms concurrently (different inputs, one of them in the other precision mode for part of
+    the time) — every result is bit-identical to the same call made serially."""
+    import threading
+    jobs = []
+    for t in range(2):
+        d = synth.pcm_inputs(2 + t, 40, 36 + 4 * t, seed=31 + t)
+        a, b = _views(2 + t, (192, 192), (128, 128), seed=40 + t, dev=cuda_dev)
+        jobs.append(dict(cam=d["cam"].to(cuda_dev), f=d["f"].to(cuda_dev), g=d["grad_out"].to(cuda_dev), a=a, b=b,
+                         label=synth.label_with_bg(synth.labels(2 + t, seed=50 + t)).to(cuda_dev)))
+
+    def work(j, reps):
+        res = None
+        for _ in range(reps):
+            camn = ops.cam_norm(j["cam"])
+            out, ws = ops.pcm_forward(camn, j["f"], mode="precise")
+            grad = ops.pcm_backward(j["f"], camn, out, j["g"], ws, mode="precise")
+            out_fast, _ = ops.pcm_forward(camn, j["f"], mode="fast")
+            terms = L.contrast_terms(j["a"]["f_proj"], j["a"]["cam_rv_down"], j["b"]["f_proj"], j["b"]["cam_rv_down"],
+                                     j["label"], 0.2, grid=(16, 16), rng=7, want_mined=True)
+            res = (out, grad, out_fast, terms["loss_nce"], terms["grad_f1"], terms["grad_f2"], terms["mined1"])
+        return res
+
+    serial = [work(j, 1) for j in jobs]
+    torch.cuda.synchronize()
+    got, errs = [None, None], []
+
+    def runner(t):
+        try:
+            stream = torch.cuda.Stream(device=cuda_dev)
+            with torch.cuda.stream(stream):
+                if t == 1:
+                    ops.set_pcm_mode("fast")                # thread-local: must not leak into thread 0's default-mode calls
+                got[t] = work(jobs[t], 6)
+                if t == 0:
+                    assert ops.get_pcm_mode() == "precise"
+            stream.synchronize()
+        except Exception as exc:                            # surfaced in the main thread
+            errs.append(exc)
+
+    threads = [threading.Thread(target=runner, args=(t,)) for t in range(2)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    torch.cuda.synchronize()
+    assert not errs, errs
+    assert ops.get_pcm_mode() == "precise"
+    for t in range(2):
+        for x, y in zip(serial[t], got[t]):
+            assert torch.equal(x, y)

@@ -207,8 +207,9 @@ __global__ void __launch_bounds__(256) pcm_prep_kernel(const float* __restrict__
 // ------------------------------------------------------------------------------------------------
 // forward main kernel (CTA pair)
 // ------------------------------------------------------------------------------------------------
-// 12 warps.  warp 0: bulk-copy producer of the feature tiles, warp 1: MMA issuer (leader CTA) / relay (peer CTA),
-// warp 2: bulk-copy producer of the cam blocks, warp 3: idle, warps 4-11: TMEM warps — two per TMEM lane quarter
+// 12 warps.  warps 0-7: TMEM warps — two per TMEM lane quarter; warp 8: bulk-copy producer of the feature tiles, warp 9:
+// issuer of the S products (leader CTA) / relay (peer CTA), warp 10: bulk-copy producer of the cam blocks, warp 11: issuer
+// of the P V products (leader CTA)
 // (a warp may only touch lanes 32*(warp%4) ..), the first converts S columns [0,64) of its 32 rows, the second the rest.
 // One warp keeps only ~2 bulk copies in flight (tools/ubench/bulkcp2.cu: 630 clk per copy per issuing warp whatever its
 // size, perfectly overlapped across warps), so every stream of tiles gets its own issuing warp.
@@ -219,80 +220,115 @@ __global__ void __launch_bounds__(256) pcm_prep_kernel(const float* __restrict__
 // three MMA chains (hi*hi + hi*lo + lo*hi): 3x the tensor work for a correction that matters for 1e-4 of the entries.
 constexpr int kMainThreads = 256;      // backward main kernel
 constexpr int kFwdThreads = 384;
-constexpr int kFwdTmemWarp0 = 4;       // first TMEM warp of the forward kernel
+// forward kernel roles.  The TMEM warps come FIRST: the sub-partition arbiter favours the higher warp ids, and the two ALU-dense
+// TMEM warps of a sub-partition otherwise starve the producer / issuer warp that shares it (trace r2: the S issuer needed
+// 380 clk after its product had completed to get to its next wait)
+constexpr int kFwdTmemWarp0 = 0;       // TMEM warps 0..7
+constexpr int kFwdWarpProdF = 8, kFwdWarpS = 9, kFwdWarpProdC = 10, kFwdWarpPV = 11;
 constexpr int kFStages = 4;
 constexpr int kCamStages = 4;
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kColO = 256;     // forward: 64 fp32 columns [num_hi | colsum | num_lo]
+constexpr int kSBuf = 3;            // forward: S / P buffers of 128 TMEM columns each (the S products run up to three stages ahead)
+constexpr uint32_t kColO = 128 * kSBuf;   // forward: 64 fp32 columns [num_hi | colsum | num_lo]
 constexpr uint32_t kColG = 256;     // backward: K (<= 192) fp32 columns dFh accumulator
 constexpr int kSplitCol = 64;       // S columns [0,64) belong to the first TMEM warp of a quarter, [64, NCOL) to the second
 
 struct FwdBars {
     // full_* / fj of the LEADER also count one arrival relayed from the peer CTA ("my copy of this stage landed too")
-    uint64_t fj, a_free, full_f[kFStages], empty_f[kFStages], full_c[kCamStages], empty_c[kCamStages], s_full[2], p_full[2],
-        o_full;
+    uint64_t fj, a_free, full_f[kFStages], empty_f[kFStages], full_c[kCamStages], empty_c[kCamStages], s_full[kSBuf],
+        p_full[kSBuf], o_full;
     uint32_t tmem_base;
 };
 
 __device__ __forceinline__ __half2 as_half2(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
 
+__device__ __forceinline__ uint32_t hfma2_relu_u(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t hfma2_u(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t hmin2_u(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("min.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+// 1.0 / 0.0 per half: a > |b|
+__device__ __forceinline__ uint32_t hset_gt_abs_u(uint32_t a, uint32_t b) {
+    uint32_t d, t;
+    asm("abs.f16x2 %0, %1;" : "=r"(t) : "r"(b));              // ptxas folds it into the compare's operand modifier
+    asm("set.gt.f16x2.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(t));
+    return d;
+}
+
 // NV fp32 accumulator values -> relu as packed fp16 (pk), and per value one bit in `sbits` ([S > 0]) and one in `nbits`
-// ([|S| < tau]): bit m belongs to value 2m, bit 16+m to value 2m+1.  Both tests are made on the fp16-rounded value h
-// (the half2 compares give 0xffff per true half, so a bit is one AND): "S rounds to a positive fp16" — values below
-// 2^-25 count as zero, far inside the accumulation error of S.
+// ([|S| < tau]): bit m belongs to value 2m, bit 16+m to value 2m+1.  Both tests are made on the fp16-rounded value h:
+// "S rounds to a positive fp16" — values below 2^-25 count as zero, far inside the accumulation error of S.
+// The two TMEM warps of a sub-partition are bound by its ALU pipe (one warp instruction per 2 clk; tools/ubench/alu_rates.cu:
+// the first sequence — cvt, 2 compares to masks, 3 LOP3 — cost 12 clk per pair), so the work is spread over BOTH pipes,
+// 3 + 3 instructions per pair (6-7 clk):
+//   ALU pipe: cvt h;  ind = min(p, 2^-24) = 0x0001 per positive half;  near = set(tau > |h|) = 1.0 / 0.0 per half
+//   FMA pipe: p = fma.relu(h, 1, 0);  sbits += ind << m (IMAD);  nacc += near * 2^(m mod 8) (HFMA2, exact fp16 integers < 256)
 template <int NV, int MODE>
 __device__ __forceinline__ void relu_pack_bits(const uint32_t* r, uint32_t* pk, uint32_t tau2, uint32_t& sbits,
                                                uint32_t& nbits) {
     sbits = 0;
     nbits = 0;
+    uint32_t nacc[2] = {0u, 0u};
 #pragma unroll
     for (int m = 0; m < NV / 2; ++m) {
         if (MODE == 0) {
             pk[m] = pack_f16x2_relu(__uint_as_float(r[2 * m]), __uint_as_float(r[2 * m + 1]));
+        } else if (MODE == 1) {
+            const uint32_t p = pack_f16x2_relu(__uint_as_float(r[2 * m]), __uint_as_float(r[2 * m + 1]));
+            pk[m] = p;
+            sbits = hmin2_u(p, 0x00010001u) * (1u << m) + sbits;
         } else {
             const uint32_t h = pack_f16x2(__uint_as_float(r[2 * m]), __uint_as_float(r[2 * m + 1]));
-            const uint32_t pos = __hgt2_mask(as_half2(h), as_half2(0u));
-            pk[m] = h & pos;
-            sbits |= pos & (0x00010001u << m);
-            if (MODE == 2) {
-                const uint32_t far = __hge2_mask(__habs2(as_half2(h)), as_half2(tau2));
-                nbits |= ~far & (0x00010001u << m);
-            }
+            const uint32_t p = hfma2_relu_u(h, 0x3c003c00u, 0u);
+            pk[m] = p;
+            sbits = hmin2_u(p, 0x00010001u) * (1u << m) + sbits;
+            const uint32_t w = (0x3c00u + (static_cast<uint32_t>(m & 7) << 10)) * 0x00010001u;      // 2^(m mod 8) in both halves
+            nacc[m >> 3] = hfma2_u(hset_gt_abs_u(tau2, h), w, nacc[m >> 3]);
         }
+    }
+    if (MODE == 2) {
+        // fp16 integers 0..255 -> bits: adding 1024 leaves the integer in the low mantissa bits
+        const uint32_t k1024 = 0x64006400u, one = 0x3c003c00u;
+        nbits = hfma2_u(nacc[0], one, k1024) & 0x00ff00ffu;
+        if (NV > 16) nbits |= (hfma2_u(nacc[1], one, k1024) & 0x00ff00ffu) << 8;
     }
 }
 
 // One TMEM warp's share of a stage: NC (64, 48 or 32) fp32 columns of S at `base` -> packed fp16 relu(S) IN PLACE over the
 // first NC/2 of them (each warp only overwrites columns it has itself loaded, so the two warps of a quarter need no
-// ordering between them), sign / near-zero bits of chunk c (32 columns) in sw[c] / nw[c].
-template <int NC, int MODE>
-__device__ __forceinline__ void convert_cols(uint32_t base, uint32_t tau2, uint32_t (&sw)[2], uint32_t (&nw)[2]) {
+// ordering between them), sign / near-zero bits of chunk c (32 columns) in sw[c] / nw[c].  The loads are issued separately
+// (load_cols) so that the next stage's can be in flight while this stage's masks are being stored.
+template <int NC>
+__device__ __forceinline__ void load_cols(uint32_t base, uint32_t (&r0)[32], uint32_t (&r1)[32]) {
     static_assert(NC == 64 || NC == 48 || NC == 32, "column split");
+    tmem_ld32(base, r0);
+    if (NC == 64) tmem_ld32(base + 32, r1);
+    if (NC == 48) tmem_ld16(base + 32, reinterpret_cast<uint32_t(&)[16]>(r1));
+}
+template <int NC, int MODE>
+__device__ __forceinline__ void convert_cols(uint32_t base, const uint32_t (&r0)[32], const uint32_t (&r1)[32], uint32_t tau2,
+                                             uint32_t (&sw)[2], uint32_t (&nw)[2]) {
     sw[1] = 0;
     nw[1] = 0;
-    uint32_t r0[32];
-    tmem_ld32(base, r0);
+    uint32_t pk[16];
+    relu_pack_bits<32, MODE>(r0, pk, tau2, sw[0], nw[0]);
+    tmem_st16(base, pk);
     if (NC == 64) {
-        uint32_t r1[32], pk[16];
-        tmem_ld32(base + 32, r1);
-        tmem_ld_wait();
-        relu_pack_bits<32, MODE>(r0, pk, tau2, sw[0], nw[0]);
-        tmem_st16(base, pk);
         relu_pack_bits<32, MODE>(r1, pk, tau2, sw[1], nw[1]);
         tmem_st16(base + 16, pk);
     } else if (NC == 48) {
-        uint32_t r1[16], pk[16], pk1[8];
-        tmem_ld16(base + 32, r1);
-        tmem_ld_wait();
-        relu_pack_bits<32, MODE>(r0, pk, tau2, sw[0], nw[0]);
-        tmem_st16(base, pk);
-        relu_pack_bits<16, MODE>(r1, pk1, tau2, sw[1], nw[1]);
-        tmem_st8(base + 16, pk1);
-    } else {
-        uint32_t pk[16];
-        tmem_ld_wait();
-        relu_pack_bits<32, MODE>(r0, pk, tau2, sw[0], nw[0]);
-        tmem_st16(base, pk);
+        relu_pack_bits<16, MODE>(r1, pk, tau2, sw[1], nw[1]);
+        tmem_st8(base + 16, reinterpret_cast<uint32_t(&)[8]>(pk));
     }
 }
 
@@ -319,6 +355,16 @@ pcm_fwd_kernel(const uint8_t* __restrict__ fa, const uint8_t* __restrict__ fb, c
     // optional timeline of CTA 0: trace[role*256 + t*4 + k] = clock64()   (wsegk_debug_pcm_trace)
     const bool tr = trace != nullptr && blockIdx.x == 0;
 #define TRACE(role, t, k) do { if (tr && (t) < 64) trace[(role) * 256 + (t) * 4 + (k)] = clock64(); } while (0)
+    const bool trp = trace != nullptr && blockIdx.x == 1;          // the peer CTA of pair 0 (its own clock64: same SM pair, clocks differ by a constant)
+#define TRACEP(role, t, k) do { if (trp && (t) < 64) trace[(role) * 256 + (t) * 4 + (k)] = clock64(); } while (0)
+        // slots 1024 + 2*cta, +1: globaltimer at the start / end of every CTA (the buffer holds 1024 + 2*gridDim.x + 2 words)
+    // (CTA 0's pair goes to slots 1024 + 2*gridDim.x ..: the slots of role 0 are all taken by the issuers' stamps)
+    if (trace != nullptr && threadIdx.x == 0) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(gt));
+        trace[1024 + 2 * blockIdx.x] = static_cast<long long>(gt);
+        if (tr) trace[1024 + 2 * gridDim.x] = clock64();
+    }
     constexpr int NCOL = 2 * WB;
     constexpr uint32_t kCamBytes = NCOL * 64;                  // (NCOL/8) groups x 32 rows x 16 B per CTA
     using Bars = FwdBars;
@@ -349,14 +395,14 @@ pcm_fwd_kernel(const uint8_t* __restrict__ fa, const uint8_t* __restrict__ fb, c
             mbar_init(smem_u32(&bars->full_c[s]), 1 + relay);
             mbar_init(smem_u32(&bars->empty_c[s]), 1);
         }
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < kSBuf; ++b) {
             mbar_init(smem_u32(&bars->s_full[b]), 1);
             mbar_init(smem_u32(&bars->p_full[b]), 16);         // 8 warps x 2 CTAs
         }
         mbar_init(smem_u32(&bars->o_full), 1);
         mbar_fence_init();
     }
-    if (warp == 1) {
+    if (warp == kFwdWarpS) {
         tmem_alloc_2cta(smem_u32(&bars->tmem_base), kTmemCols);
         tmem_relinquish_2cta();
     }
@@ -366,7 +412,7 @@ pcm_fwd_kernel(const uint8_t* __restrict__ fa, const uint8_t* __restrict__ fb, c
     tc_fence_after();
     const uint32_t tmem = bars->tmem_base;
 
-    if (warp == 0) {
+    if (warp == kFwdWarpProdF) {
         // ---------------------------------------------------------------- feature-tile producer
         if (lane == 0) {
             StageCursor si = c0;
@@ -387,7 +433,7 @@ pcm_fwd_kernel(const uint8_t* __restrict__ fa, const uint8_t* __restrict__ fb, c
                 tma_load_1d(smem_u32(s_f + s * b_bytes), fb + bt * b_bytes, b_bytes, bar);
             }
         }
-    } else if (warp == 2) {
+    } else if (warp == kFwdWarpProdC) {
         // ---------------------------------------------------------------- cam-block producer
         if (lane == 0) {
             StageCursor si = c0;
@@ -400,7 +446,7 @@ pcm_fwd_kernel(const uint8_t* __restrict__ fa, const uint8_t* __restrict__ fb, c
                             camb + ((static_cast<size_t>(si.n) * NS + si.st) * 2 + rank) * kCamBytes, kCamBytes, bar);
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == kFwdWarpS) {
         if (lane == 0 && rank == 1) {
             // ------------------------------------------------------------ relay: tell the leader my tiles have landed
             StageCursor si = c0;
@@ -421,82 +467,103 @@ pcm_fwd_kernel(const uint8_t* __restrict__ fa, const uint8_t* __restrict__ fb, c
                 }
             }
         } else if (rank == 0) {
-            // ------------------------------------------------------------ MMA issuer: the whole warp of the leader CTA
-            // stays converged (waits), one ELECTED lane issues; descriptors advance by adding to their address field.
-            const uint32_t id_s = umma_idesc_f16(0, 2 * kTile, NCOL, 0, 0);
-            const uint32_t id_o = umma_idesc_f16(0, 2 * kTile, kONum, 0, 0);
-            constexpr uint32_t lbo_a = kTile * 16, lbo_b = WB * 16, lbo_c = kCamRows * 16;
-            const int ksteps = K >> 4;
-            const uint64_t da = umma_smem_desc(smem_u32(s_fj), lbo_a, 128);
-            StageCursor cs = c0;                 // runs two stages ahead of the PV cursor
-            auto issue_s = [&](int i) {
-                const bool seg_first = cs.first(), seg_last = cs.last();
-                const int seg = cs.k;
-                cs.next();
-                const int s = i % FS, u = i / FS, b = i & 1;
-                if (seg_first) mbar_wait_cluster(smem_u32(&bars->fj), seg & 1);
-                if (lane == 0) TRACE(1, i, 0);
-                mbar_wait_cluster(smem_u32(&bars->full_f[s]), u & 1);
-                if (lane == 0) TRACE(1, i, 1);
-                tc_fence_after();
-                if (elect_one()) {
-                    const uint64_t db = umma_smem_desc(smem_u32(s_f + s * b_bytes), lbo_b, 128);
+            // ------------------------------------------------------------ S issuer (leader CTA): S(i) = Fj Fi^T into buffer i % 3.
+            // ONE elected lane runs the whole loop inside a single divergent branch: re-electing per stage (elect.sync + the
+            // reconvergence around it) cost ~700 clk per stage, and 32 lanes polling an mbarrier ~150 clk per wait even when
+            // the phase is complete (tools/ubench/mma_*.cu, trace r2).  The P V products have their own issuing warp: one
+            // thread issuing both kinds, with its three waits per stage, left the tensor pipe idle 40 % of the time.
+            // Issue itself is cheap (~8 clk per MMA with precomputed descriptors; the queue holds ~24 MMAs).
+            if (elect_one()) {
+                const uint32_t id_s = umma_idesc_f16(0, 2 * kTile, NCOL, 0, 0);
+                constexpr uint32_t lbo_a = kTile * 16, lbo_b = WB * 16;
+                const int ksteps = K >> 4;
+                const uint64_t da = umma_smem_desc(smem_u32(s_fj), lbo_a, 128);
+                const uint64_t db0 = umma_smem_desc(smem_u32(s_f), lbo_b, 128);
+                StageCursor cs = c0;
+                int b = 0, s = 0, fph = 0;
+                for (int i = 0; i < cnt; ++i) {
+                    const bool seg_first = cs.first(), seg_last = cs.last();
+                    const int seg = cs.k;
+                    cs.next();
+                    if (seg_first) mbar_wait(smem_u32(&bars->fj), seg & 1);
+                    TRACE(1, i, 0);
+                    // the stage's tile has landed (in both CTAs), and buffer b is free: P V(i - 3) has read it — that product's
+                    // commit on empty_c (P V(i + 1), the next completion of the same barrier, needs S(i + 1), which this thread
+                    // has not issued yet).  Both polls are in flight together.
+                    if (i >= kSBuf)
+                        mbar_wait2(smem_u32(&bars->full_f[s]), fph, smem_u32(&bars->empty_c[(i - kSBuf) % kCamStages]),
+                                   ((i - kSBuf) / kCamStages) & 1);
+                    else
+                        mbar_wait(smem_u32(&bars->full_f[s]), fph);
+                    TRACE(1, i, 1);
+                    tc_fence_after();
+                    const uint64_t db = db0 + static_cast<uint64_t>((s * b_bytes) >> 4);
                     const uint32_t d = tmem + b * 128;
-#pragma unroll 4
-                    for (int ks = 0; ks < ksteps; ++ks)
-                        umma2_ss(d, da + static_cast<uint64_t>(ks * (2 * lbo_a / 16)),
-                                 db + static_cast<uint64_t>(ks * (2 * lbo_b / 16)), id_s, ks > 0);
+#ifndef WSEGK_ABL_NOS
+#pragma unroll
+                    for (int ks = 0; ks < kMaxPcmK / 16; ++ks)
+                        if (ks < ksteps)
+                            umma2_ss(d, da + static_cast<uint64_t>(ks * (2 * lbo_a / 16)),
+                                     db + static_cast<uint64_t>(ks * (2 * lbo_b / 16)), id_s, ks > 0);
+#endif
+                    TRACE(0, i, 1);
                     umma2_commit(smem_u32(&bars->s_full[b]));
                     umma2_commit(smem_u32(&bars->empty_f[s]));
                     if (seg_last) umma2_commit(smem_u32(&bars->a_free));  // the segment's A-side tile may be replaced
+                    TRACE(0, i, 2);
+                    b = b + 1 == kSBuf ? 0 : b + 1;
+                    if (++s == FS) { s = 0; fph ^= 1; }
                 }
-                __syncwarp();
-            };
-            // S runs two stages ahead of PV inside a segment.  The first S of a NEW segment has to wait for its A-side tile,
-            // which is loaded only after the old segment's last S; it is therefore issued one iteration later, after the
-            // PV that ends the old segment (whose epilogue then overlaps the tile load instead of following it).
-            int next_s = 0;
-            auto issue_upto = [&](int limit) {               // limit = index of the PV stage just issued, or -1
-                while (next_s < cnt && next_s <= limit + 2) {
-                    if (next_s == limit + 2 && next_s > 0 && cs.first()) break;
-                    issue_s(next_s);
-                    ++next_s;
-                }
-            };
-            issue_upto(-1);
-            StageCursor si = c0;
-            for (int i = 0; i < cnt; ++i, si.next()) {
-                const int b = i & 1, sc = i % kCamStages, uc = i / kCamStages;
-                if (lane == 0) TRACE(1, i, 2);
-                mbar_wait_cluster(smem_u32(&bars->p_full[b]), (i >> 1) & 1);
-                if (lane == 0) TRACE(1, i, 3);
-                mbar_wait_cluster(smem_u32(&bars->full_c[sc]), uc & 1);
-                tc_fence_after();
-                if (elect_one()) {
-                    const uint64_t dc = umma_smem_desc(smem_u32(s_c + sc * kCamBytes), lbo_c, 128);
+            }
+            __syncwarp();
+        }
+    } else if (warp == kFwdWarpPV) {
+        if (rank == 0) {
+            // ------------------------------------------------------------ P V issuer (leader CTA), one lane, one branch
+            if (elect_one()) {
+                const uint32_t id_o = umma_idesc_f16(0, 2 * kTile, kONum, 0, 0);
+                constexpr uint32_t lbo_c = kCamRows * 16;
+                const uint64_t dc0 = umma_smem_desc(smem_u32(s_c), lbo_c, 128);
+                StageCursor si = c0;
+                int b = 0, bph = 0, sc = 0, cph = 0;
+                for (int i = 0; i < cnt; ++i, si.next()) {
+                    TRACE(1, i, 2);
+                    if (tr) {                                   // diagnosis: which of the two is late
+                        mbar_wait(smem_u32(&bars->p_full[b]), bph);
+                        TRACE(3, i, 3);
+                    }
+                    mbar_wait2(smem_u32(&bars->p_full[b]), bph, smem_u32(&bars->full_c[sc]), cph);
+                    TRACE(1, i, 3);
+                    tc_fence_after();
+                    const uint64_t dc = dc0 + static_cast<uint64_t>((sc * kCamBytes) >> 4);
+                    const uint32_t acc0 = si.first() ? 0u : 1u;
                     // the accumulator restarts with every segment; the TMEM warps drained the previous segment's before
                     // they produced this stage's P.  P of S columns [0,64) sits at packed columns [0,32) of the buffer, P of
                     // the columns from 64 on at [64, ...) (convert_cols)
+#ifndef WSEGK_ABL_NOPV
 #pragma unroll
                     for (int ks = 0; ks < NCOL / 16; ++ks) {
-                        const uint32_t pcol = ks < kSplitCol / 16 ? ks * 8 : kSplitCol + (ks - kSplitCol / 16) * 8;
+                        constexpr int kHalf = kSplitCol / 16;
+                        const uint32_t pcol = ks < kHalf ? ks * 8 : kSplitCol + (ks - kHalf) * 8;
                         umma2_ts(tmem + kColO, tmem + b * 128 + pcol, dc + static_cast<uint64_t>(ks * (2 * lbo_c / 16)),
-                                 id_o, !si.first() || (ks > 0));
+                                 id_o, ks > 0 ? 1u : acc0);
                     }
+#endif
+                    TRACE(0, i, 3);
                     umma2_commit(smem_u32(&bars->empty_c[sc]));
                     if (si.last()) umma2_commit(smem_u32(&bars->o_full));
+                    if (++b == kSBuf) { b = 0; bph ^= 1; }
+                    if (++sc == kCamStages) { sc = 0; cph ^= 1; }
                 }
-                __syncwarp();
-                issue_upto(i);
             }
+            __syncwarp();
         }
-    } else if (warp >= kFwdTmemWarp0) {
+    } else if (warp < kFwdTmemWarp0 + 8) {
         // ---------------------------------------------------------------- ReLU / sign / convert warps
         const int q = warp & 3;                         // TMEM lane quarter this warp may touch
         const int hf = (warp - kFwdTmemWarp0) >> 2;     // column half
         const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
         const uint32_t p_full0 = mapa_shared(smem_u32(&bars->p_full[0]), 0);
-        const uint32_t p_full1 = mapa_shared(smem_u32(&bars->p_full[1]), 0);
         uint32_t tau2 = 0;
         if (MODE == 2) {
             // |S(fp16 operands) - S| <= |lo_j| + |lo_i| <= 2 lo_max is the strict bound; the residuals of the K channels add
@@ -508,24 +575,51 @@ pcm_fwd_kernel(const uint8_t* __restrict__ fa, const uint8_t* __restrict__ fb, c
             tau2 = th | (th << 16);
         }
         StageCursor si = c0;
+        int b = 0, bph = 0;
+        uint32_t r0[32], r1[32];                       // this warp's S columns of the stage being converted / being loaded
+        auto fetch = [&](int buf, int phase) {         // wait for S of the stage in `buf` and start loading my columns
+            mbar_wait(smem_u32(&bars->s_full[buf]), phase);
+            tc_fence_after();
+            const uint32_t base = tmem + lane_addr + buf * 128 + hf * kSplitCol;
+            if (hf == 0) load_cols<kSplitCol>(base, r0, r1);
+            else load_cols<NCOL - kSplitCol>(base, r0, r1);
+        };
+        if (warp == kFwdTmemWarp0 && lane == 0) TRACE(2, 0, 0);
+        if (cnt > 0) fetch(0, 0);
         for (int i = 0; i < cnt; ++i, si.next()) {
             const int row = si.jp * 2 * kTile + static_cast<int>(rank) * kTile + q * 32 + lane;
-            const int b = i & 1;
-            if (warp == kFwdTmemWarp0 && lane == 0) TRACE(2, i, 0);
-            mbar_wait(smem_u32(&bars->s_full[b]), (i >> 1) & 1);
+            tmem_ld_wait();
             if (warp == kFwdTmemWarp0 && lane == 0) TRACE(2, i, 1);
-            tc_fence_after();
+            if (warp == kFwdTmemWarp0 && lane == 0) TRACEP(3, i, 0);
             uint32_t sw[2], nw[2];
             const uint32_t base = tmem + lane_addr + b * 128 + hf * kSplitCol;
-            if (hf == 0) convert_cols<kSplitCol, MODE>(base, tau2, sw, nw);
-            else convert_cols<NCOL - kSplitCol, MODE>(base, tau2, sw, nw);
+#if defined(WSEGK_ABL_NOALU)
+            tmem_st16(base, reinterpret_cast<uint32_t(&)[16]>(r0));
+            sw[0] = r0[0]; sw[1] = r1[0]; nw[0] = r0[1]; nw[1] = r1[1];
+#else
+            if (hf == 0) convert_cols<kSplitCol, MODE>(base, r0, r1, tau2, sw, nw);
+            else convert_cols<NCOL - kSplitCol, MODE>(base, r0, r1, tau2, sw, nw);
+#endif
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(b ? p_full1 : p_full0);
+            if (lane == 0) mbar_arrive_cluster_relaxed(p_full0 + static_cast<uint32_t>(b) * 8u);
             if (warp == kFwdTmemWarp0 && lane == 0) TRACE(2, i, 2);
+            if (warp == kFwdTmemWarp0 + 7 && lane == 0) TRACE(3, i, 2);
+            if (warp == kFwdTmemWarp0 && lane == 0) TRACEP(3, i, 1);
+            // the next stage's S is normally complete by now (the S products run up to three stages ahead): start loading it
+            // before this stage's masks are stored, so the barrier poll (~150 clk) and the TMEM load latency hide behind them
+            const int nb = b + 1 == kSBuf ? 0 : b + 1, nph = b + 1 == kSBuf ? bph ^ 1 : bph;
+            if (warp == kFwdTmemWarp0 && lane == 0) TRACE(2, i + 1, 0);
+            if (i + 1 < cnt) fetch(nb, nph);
+#if !defined(WSEGK_ABL_NOMASK) && !defined(WSEGK_ABL_NOMASK_LANE0)
             if (MODE >= 1) {
-                const size_t mi = ((static_cast<size_t>(si.n) * NS + si.st) * HWpj + row) * 2 + hf;
+#elif defined(WSEGK_ABL_NOMASK_LANE0)
+            if (MODE >= 1 && lane != 0) {
+#else
+            if (MODE >= 1 && sw[0] == 0x12345u) {
+#endif
+                const size_t mi = static_cast<size_t>(si.n * NS + si.st) * (2 * HWpj) + 2 * row + hf;
                 mask[mi] = make_uint2(sw[0], sw[1]);
                 if (MODE == 2) {
                     // padding rows / columns are all-zero vectors: S = 0 there, nothing to re-evaluate
@@ -552,13 +646,22 @@ pcm_fwd_kernel(const uint8_t* __restrict__ fa, const uint8_t* __restrict__ fb, c
                 }
                 tc_fence_before();
             }
+            b = nb;
+            bph = nph;
         }
     }
     tc_fence_before();
     __syncthreads();
+    if (trace != nullptr && threadIdx.x == 0) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(gt));
+        trace[1024 + 2 * blockIdx.x + 1] = static_cast<long long>(gt);
+        if (tr) trace[1024 + 2 * gridDim.x + 1] = clock64();
+    }
     cluster_sync_all();
-    if (warp == 1) tmem_dealloc_2cta(tmem, kTmemCols);
+    if (warp == kFwdWarpS) tmem_dealloc_2cta(tmem, kTmemCols);
 #undef TRACE
+#undef TRACEP
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1176,7 +1279,7 @@ struct PcmProf {
     bool have[3] = {false, false, false};
 };
 thread_local PcmProf g_prof;
-thread_local long long* g_trace = nullptr;   // device buffer of 768 int64 for the forward kernel's timeline, or null
+thread_local long long* g_trace = nullptr;   // device buffer of 1024 + 2 * 148 + 2 int64 for the forward kernel's timeline, or null
 void prof_mark(int which, wsegk_stream_t stream) {
     if (!g_prof.on) return;
     if (!g_prof.ev[which]) cudaEventCreate(&g_prof.ev[which]);

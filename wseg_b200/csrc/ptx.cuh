@@ -54,6 +54,30 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
 }
 
+// wait for two barriers with both polls in flight (a poll costs ~150 clk even when the phase is complete)
+__device__ __forceinline__ void mbar_wait2(uint32_t bar_a, uint32_t parity_a, uint32_t bar_b, uint32_t parity_b) {
+    uint32_t spins = 0;
+    while (true) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred pa, pb;\n\t"
+#ifdef WSEGK_EXP_TEST_WAIT
+            "mbarrier.test_wait.parity.shared::cta.b64 pa, [%1], %2;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 pb, [%3], %4;\n\t"
+#else
+            "mbarrier.try_wait.parity.shared::cta.b64 pa, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 pb, [%3], %4;\n\t"
+#endif
+            "and.pred pa, pa, pb;\n\t"
+            "selp.b32 %0, 1, 0, pa;\n\t}\n"
+            : "=r"(ok)
+            : "r"(bar_a), "r"(parity_a), "r"(bar_b), "r"(parity_b)
+            : "memory");
+        if (ok) return;
+        if (++spins > WSEGK_SPIN_LIMIT) __trap();
+    }
+}
+
 // ------------------------------------------------------------------ thread-block clusters (CTA pairs)
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -76,6 +100,12 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
 // lives in TMEM / shared memory and is ordered by tcgen05.fence / the async proxy, not by this fence.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
+}
+// the same without release semantics: even the default (CTA-scope) release holds the arrive back until the thread's earlier
+// GLOBAL stores have been acknowledged (trace r2: the forward's "P is ready" arrive reached the leader ~1000 clk late behind
+// the previous stage's sign-mask stores).  For barriers that guard TMEM contents only (ordered by tcgen05.wait / fence).
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
     uint32_t ok;

@@ -34,13 +34,16 @@ class Net(resnet38d.Net):
         d = super().forward_as_dict(x)
         cam = self.fc8(self.dropout7(d['conv6']))
         h, w = cam.shape[-2:]
-        cam_d_norm = ops.cam_norm(cam)                                                     # K1a (:35-43)
-        f8_3 = F.relu(self.f8_3(d['conv4'].detach()), inplace=True)
-        f8_4 = F.relu(self.f8_4(d['conv5'].detach()), inplace=True)
-        x_s = F.interpolate(x, (h, w), mode='bilinear', align_corners=True)
-        f = torch.cat([x_s, f8_3, f8_4], dim=1)
-        cam_rv = ops.bilinear_resize(self.PCM(cam_d_norm, f), (H, W))                      # K2 (:55-67) + glue (:51)
-        cam = ops.bilinear_resize(cam, (H, W))
+        # the reference runs its whole tail — the final enlargement of `cam` included — under no_grad (:36-52): neither
+        # output carries a graph, in train mode too
+        with torch.no_grad():
+            cam_d_norm = ops.cam_norm(cam.detach())                                        # K1a (:37-43)
+            f8_3 = F.relu(self.f8_3(d['conv4'].detach()), inplace=True)
+            f8_4 = F.relu(self.f8_4(d['conv5'].detach()), inplace=True)
+            x_s = F.interpolate(x, (h, w), mode='bilinear', align_corners=True)
+            f = torch.cat([x_s, f8_3, f8_4], dim=1)
+            cam_rv = ops.bilinear_resize(self.PCM(cam_d_norm, f), (H, W))                  # K2 (:55-67) + glue (:51)
+            cam = ops.bilinear_resize(cam, (H, W))                                         # :52
         return cam, cam_rv
 
     PCM = _ContrastNet.PCM
