@@ -672,12 +672,13 @@ pcm_fwd_kernel(const uint8_t* __restrict__ fa, const uint8_t* __restrict__ fb, c
 // the sign mask is set to [S > 0].  S is symmetric and so (up to entries sitting exactly on tau, whose fp16 sign is
 // reliable by the definition of tau) is its near-zero mask: only the entries ABOVE the diagonal (i > j) are evaluated
 // and each result patches both (j, i) and (i, j) — half the row gathers, which are what this kernel costs (one K-float
-// row from L2 per entry).  One CTA = 128 rows j (their features in shared memory, one bulk copy) x a chunk of stages;
+// row from L2 per entry).  One CTA = 64 rows j (their features in shared memory, bulk copies) x a chunk of stages;
 // marked entries go through a shared-memory queue; a warp evaluates eight entries at a time, four lanes per entry with
 // all 12 float4 loads of the lane in flight at once (the first version walked one entry per warp with dependent loads:
 // 104 us at N = 8, 56x56).
 constexpr int kFixThreads = 256;
-constexpr int kFixQueue = 2048;
+constexpr int kFixQueue = 1024;
+constexpr int kFixTile = 64;            // rows j per CTA: 48 KB of shared memory at K = 192 -> four CTAs per SM keep the L2 gathers in flight
 
 template <int KG>      // K / 16
 __global__ void __launch_bounds__(kFixThreads) pcm_sign_fixup_kernel(const float* __restrict__ fh32,
@@ -686,11 +687,11 @@ __global__ void __launch_bounds__(kFixThreads) pcm_sign_fixup_kernel(const float
                                                                     int ncol, int chunk) {
     constexpr int K = 16 * KG;
     extern __shared__ __align__(128) uint8_t fix_smem[];
-    float* s_fj = reinterpret_cast<float*>(fix_smem);                          // [128][K]
-    uint32_t* s_q = reinterpret_cast<uint32_t*>(fix_smem + static_cast<size_t>(kTile) * K * 4);
+    float* s_fj = reinterpret_cast<float*>(fix_smem);                          // [kFixTile][K]
+    uint32_t* s_q = reinterpret_cast<uint32_t*>(fix_smem + static_cast<size_t>(kFixTile) * K * 4);
     __shared__ int s_cnt;
     __shared__ __align__(8) uint64_t s_bar;
-    const int n = blockIdx.z, j0 = blockIdx.x * kTile;
+    const int n = blockIdx.z, j0 = blockIdx.x * kFixTile;
     // stages of this CTA: its chunk, minus the stages that lie entirely below the diagonal (columns <= j0)
     const int s_begin = max(static_cast<int>(blockIdx.y) * chunk, j0 / ncol);
     const int s_end = min(NS, (static_cast<int>(blockIdx.y) + 1) * chunk);
@@ -701,14 +702,14 @@ __global__ void __launch_bounds__(kFixThreads) pcm_sign_fixup_kernel(const float
         s_cnt = 0;
         mbar_init(smem_u32(&s_bar), 1);
         mbar_fence_init();
-        const uint32_t bytes = static_cast<uint32_t>(kTile) * K * 4;
+        const uint32_t bytes = static_cast<uint32_t>(kFixTile) * K * 4;
         mbar_arrive_expect_tx(smem_u32(&s_bar), bytes);
         // two halves: the copy engine streams one operation with only a few requests in flight
         tma_load_1d(smem_u32(s_fj), fn + static_cast<size_t>(j0) * K, bytes / 2, smem_u32(&s_bar));
         tma_load_1d(smem_u32(s_fj) + bytes / 2, fn + static_cast<size_t>(j0) * K + bytes / 8, bytes / 2, smem_u32(&s_bar));
     }
     __syncthreads();
-    const int my_row = tid & (kTile - 1), my_sub = tid >> 7;                   // two stages are scanned per pass
+    const int my_row = tid & (kFixTile - 1), my_sub = tid / kFixTile;          // kFixThreads / kFixTile stages are scanned per pass
     const int my_j = j0 + my_row;
     uint32_t pend[4] = {0u, 0u, 0u, 0u};
     int pend_stage = 0;
@@ -729,7 +730,7 @@ __global__ void __launch_bounds__(kFixThreads) pcm_sign_fixup_kernel(const float
                     for (int c = 0; c < 4; ++c) pend[c] &= ~valid_bits(lim + 1 - 32 * c);
                 }
             }
-            s += kFixThreads / kTile;
+            s += kFixThreads / kFixTile;
         }
         // push my marked entries: [row:7 | column:7 | stage:18]
 #pragma unroll
@@ -1059,21 +1060,24 @@ pcm_bwd_kernel(const uint8_t* __restrict__ ua, const uint8_t* __restrict__ vb, c
                 mbar_arrive_cluster(mapa_shared(smem_u32(&bars->full_f[s]), 0));
             }
         } else if (rank == 0) {
-            const uint32_t id_t = umma_idesc_f16(1, 2 * kTile, NCOL, 0, 0);       // bf16 factors
-            const uint32_t id_g = umma_idesc_f16(0, 2 * kTile, K, 0, 1);          // fp16, B = Fi read MN-major (N = channel)
-            constexpr uint32_t lbo_a = kTile * 16, lbo_b = WB * 16;
-            const uint64_t du = umma_smem_desc(smem_u32(s_u), lbo_a, 128);
-            StageCursor cs = c0;                 // cursor of the T products (ahead of the G products)
-            auto issue_t = [&](int i) {
-                const bool seg_first = cs.first(), seg_last = cs.last();
-                const int seg = cs.k;
-                cs.next();
-                const int s = i % kBwdStages, u = i / kBwdStages, b = i & 1;
-                if (seg_first) mbar_wait_cluster(smem_u32(&bars->uj), seg & 1);
-                mbar_wait_cluster(smem_u32(&bars->full_v[s]), u & 1);
-                tc_fence_after();
-                if (elect_one()) {
-                    const uint64_t dv = umma_smem_desc(smem_u32(s_v + s * kVBytes), lbo_b, 128);
+            // ONE elected lane runs the whole issue loop inside a single branch (see the forward kernel: re-electing per stage
+            // and polling with 32 lanes cost the issuer more than the tensor pipe needs for the stage's products)
+            if (elect_one()) {
+                const uint32_t id_t = umma_idesc_f16(1, 2 * kTile, NCOL, 0, 0);       // bf16 factors
+                const uint32_t id_g = umma_idesc_f16(0, 2 * kTile, K, 0, 1);          // fp16, B = Fi read MN-major (N = channel)
+                constexpr uint32_t lbo_a = kTile * 16, lbo_b = WB * 16;
+                const uint64_t du = umma_smem_desc(smem_u32(s_u), lbo_a, 128);
+                const uint64_t dv0 = umma_smem_desc(smem_u32(s_v), lbo_b, 128);
+                StageCursor cs = c0;                 // cursor of the T products (ahead of the G products)
+                auto issue_t = [&](int i) {
+                    const bool seg_first = cs.first(), seg_last = cs.last();
+                    const int seg = cs.k;
+                    cs.next();
+                    const int s = i % kBwdStages, u = i / kBwdStages, b = i & 1;
+                    if (seg_first) mbar_wait(smem_u32(&bars->uj), seg & 1);
+                    mbar_wait(smem_u32(&bars->full_v[s]), u & 1);
+                    tc_fence_after();
+                    const uint64_t dv = dv0 + static_cast<uint64_t>((s * kVBytes) >> 4);
 #pragma unroll
                     for (int ks = 0; ks < KU / 16; ++ks)
                         umma2_ss(tmem + b * 128, du + static_cast<uint64_t>(ks * (2 * lbo_a / 16)),
@@ -1081,27 +1085,24 @@ pcm_bwd_kernel(const uint8_t* __restrict__ ua, const uint8_t* __restrict__ vb, c
                     umma2_commit(smem_u32(&bars->t_full[b]));
                     umma2_commit(smem_u32(&bars->empty_v[s]));
                     if (seg_last) umma2_commit(smem_u32(&bars->u_free));
-                }
-                __syncwarp();
-            };
-            // two stages of lookahead inside a segment, one across a segment boundary (see the forward kernel)
-            int next_t = 0;
-            auto issue_upto = [&](int limit) {
-                while (next_t < cnt && next_t <= limit + 2) {
-                    if (next_t == limit + 2 && next_t > 0 && cs.first()) break;
-                    issue_t(next_t);
-                    ++next_t;
-                }
-            };
-            issue_upto(-1);
-            StageCursor si = c0;
-            for (int i = 0; i < cnt; ++i, si.next()) {
-                const int s = i % kBwdStages, u = i / kBwdStages, b = i & 1;
-                mbar_wait_cluster(smem_u32(&bars->e_full[b]), (i >> 1) & 1);
-                mbar_wait_cluster(smem_u32(&bars->full_f[s]), u & 1);
-                tc_fence_after();
-                if (elect_one()) {
+                };
+                // two stages of lookahead inside a segment, one across a segment boundary (see the forward kernel)
+                int next_t = 0;
+                auto issue_upto = [&](int limit) {
+                    while (next_t < cnt && next_t <= limit + 2) {
+                        if (next_t == limit + 2 && next_t > 0 && cs.first()) break;
+                        issue_t(next_t);
+                        ++next_t;
+                    }
+                };
+                issue_upto(-1);
+                StageCursor si = c0;
+                for (int i = 0; i < cnt; ++i, si.next()) {
+                    const int s = i % kBwdStages, u = i / kBwdStages, b = i & 1;
+                    mbar_wait2(smem_u32(&bars->e_full[b]), (i >> 1) & 1, smem_u32(&bars->full_f[s]), u & 1);
+                    tc_fence_after();
                     const uint32_t f0 = smem_u32(s_f + s * f_stage);
+                    const uint32_t acc0 = si.first() ? 0u : 1u;
                     // dFh[j, ch] += E[j, q] * F[q, ch] over the stage's pixels q = [X(0:WB) | Y(0:WB)]; B is N(ch) x K(q),
                     // MN-major: LBO = step between the two 8-pixel groups of the k-step, SBO = channel-group step
 #pragma unroll
@@ -1110,14 +1111,14 @@ pcm_bwd_kernel(const uint8_t* __restrict__ ua, const uint8_t* __restrict__ vb, c
                         const uint32_t a0 = f0 + (q0 / WB) * f_part + (q0 % WB) * 16;
                         const uint32_t a1 = f0 + (q1 / WB) * f_part + (q1 % WB) * 16;
                         umma2_ts(tmem + kColG, tmem + b * 128 + ks * 8, umma_smem_desc(a0, a1 - a0, lbo_b), id_g,
-                                 !si.first() || (ks > 0));
+                                 ks > 0 ? 1u : acc0);
                     }
                     umma2_commit(smem_u32(&bars->empty_f[s]));
                     if (si.last()) umma2_commit(smem_u32(&bars->g_full));
+                    issue_upto(i);
                 }
-                __syncwarp();
-                issue_upto(i);
             }
+            __syncwarp();
         }
     } else if (warp < 6) {
         const int q = warp & 3;
@@ -1159,7 +1160,7 @@ pcm_bwd_kernel(const uint8_t* __restrict__ ua, const uint8_t* __restrict__ vb, c
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(b ? e_full1 : e_full0);
+            if (lane == 0) mbar_arrive_cluster_relaxed(b ? e_full1 : e_full0);
             if (si.last()) {
                 // segment epilogue.  dfhat [n][slot][K][HWpj]: for a fixed channel the 32 lanes of a warp write 32
                 // consecutive pixels
@@ -1254,6 +1255,82 @@ __global__ void __launch_bounds__(256) pcm_bwd_post_kernel(const float* __restri
 #pragma unroll
         for (int j = 0; j < 4; ++j) dst[static_cast<size_t>(k0 + kk + j) * HW] = g[j] * unscale * inv - fv[j] * coef;
     }
+}
+
+// The same in ONE pass for HW % 4 == 0: a CTA = 32 pixels (8 float4 lanes) x 32 channel groups of PER = K/32 channels; a
+// thread keeps its PER x 4 gradient and feature values in registers between the dot product and the write, and has all of
+// its 16-byte loads (PER x (1 + segments)) in flight at once.  For a fixed channel 8 lanes read / write one 128-byte line.
+// (The two-pass kernel above re-read dfhat from L2 and held 12 four-byte loads per thread: 39 us at N = 8, 56x56.)
+template <int PER>
+__global__ void __launch_bounds__(256) pcm_bwd_post_vec_kernel(const float* __restrict__ dfhat, const float* __restrict__ f,
+                                                               const float* __restrict__ inv_norm,
+                                                               const float* __restrict__ bound, float* __restrict__ grad_f,
+                                                               int HW, int HWpj, int nslot, int PJ, int NS, int G) {
+    constexpr int K = 32 * PER;
+    __shared__ float4 s_dot[32][8];
+    const int n = blockIdx.y;
+    const int q = threadIdx.x & 7, cg = threadIdx.x >> 3;
+    const int p = blockIdx.x * 32 + 4 * q;
+    const bool live = p < HW;                                   // HW % 4 == 0: a quad is inside or outside as a whole
+    const float unscale = 1.f / pcm_grad_scale(bound);
+    const size_t split_stride = static_cast<size_t>(K) * HWpj;
+    const int nsplit = pcm_unit_segments(pcm_sched(static_cast<int>(gridDim.y) * PJ, NS, G),
+                                         n * PJ + (blockIdx.x * 32) / (2 * kTile));
+    const float* gsrc = dfhat + static_cast<size_t>(n) * nslot * split_stride + static_cast<size_t>(cg * PER) * HWpj + p;
+    const float* fsrc = f + (static_cast<size_t>(n) * K + cg * PER) * HW + p;
+    float4 g[PER], fv[PER];
+    float4 dot = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) {
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            fv[j] = __ldg(reinterpret_cast<const float4*>(fsrc + static_cast<size_t>(j) * HW));
+            g[j] = __ldg(reinterpret_cast<const float4*>(gsrc + static_cast<size_t>(j) * HWpj));
+        }
+        if (nsplit == 2) {                                      // the common multi-segment case: everything in flight together
+            float4 g2[PER];
+#pragma unroll
+            for (int j = 0; j < PER; ++j) g2[j] = __ldg(reinterpret_cast<const float4*>(gsrc + split_stride + static_cast<size_t>(j) * HWpj));
+#pragma unroll
+            for (int j = 0; j < PER; ++j) { g[j].x += g2[j].x; g[j].y += g2[j].y; g[j].z += g2[j].z; g[j].w += g2[j].w; }
+        } else {
+            for (int sp = 1; sp < nsplit; ++sp) {
+#pragma unroll
+                for (int j = 0; j < PER; ++j) {
+                    const float4 t = __ldg(reinterpret_cast<const float4*>(gsrc + sp * split_stride + static_cast<size_t>(j) * HWpj));
+                    g[j].x += t.x; g[j].y += t.y; g[j].z += t.z; g[j].w += t.w;
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            g[j].x *= unscale; g[j].y *= unscale; g[j].z *= unscale; g[j].w *= unscale;
+            dot.x = fmaf(g[j].x, fv[j].x, dot.x);
+            dot.y = fmaf(g[j].y, fv[j].y, dot.y);
+            dot.z = fmaf(g[j].z, fv[j].z, dot.z);
+            dot.w = fmaf(g[j].w, fv[j].w, dot.w);
+        }
+    }
+    s_dot[cg][q] = dot;
+    __syncthreads();
+    if (!live) return;
+    dot = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+    for (int i = 0; i < 32; ++i) {                              // fixed order: deterministic
+        const float4 t = s_dot[i][q];
+        dot.x += t.x; dot.y += t.y; dot.z += t.z; dot.w += t.w;
+    }
+    const float4 inv = *reinterpret_cast<const float4*>(inv_norm + static_cast<size_t>(n) * HWpj + p);
+    auto coef_of = [](float d, float iv) {
+        const float nrm = 1.f / iv - 1e-5f;
+        return nrm > 0.f ? d * iv * iv / nrm : 0.f;
+    };
+    const float4 coef = make_float4(coef_of(dot.x, inv.x), coef_of(dot.y, inv.y), coef_of(dot.z, inv.z), coef_of(dot.w, inv.w));
+    float* dst = grad_f + (static_cast<size_t>(n) * K + cg * PER) * HW + p;
+#pragma unroll
+    for (int j = 0; j < PER; ++j)
+        *reinterpret_cast<float4*>(dst + static_cast<size_t>(j) * HW) =
+            make_float4(g[j].x * inv.x - fv[j].x * coef.x, g[j].y * inv.y - fv[j].y * coef.y,
+                        g[j].z * inv.z - fv[j].z * coef.z, g[j].w * inv.w - fv[j].w * coef.w);
 }
 
 static size_t fwd_smem_bytes(int K, int wb) {
@@ -1381,12 +1458,12 @@ static int dispatch_bwd(const PcmPlan& pl, int N, bool split, wsegk_stream_t str
 
 // the sign fix-up of the precise mode on a workspace the forward has filled
 static int launch_fixup(const PcmPlan& pl, int N, wsegk_stream_t stream) {
-    const size_t smem = static_cast<size_t>(kTile) * pl.K * 4 + static_cast<size_t>(kFixQueue) * 4;
-    const int tiles = pl.HWpj / kTile;
+    const size_t smem = static_cast<size_t>(kFixTile) * pl.K * 4 + static_cast<size_t>(kFixQueue) * 4;
+    const int tiles = pl.HWpj / kFixTile;
     // CTA = (row tile, chunk of stages, image); the chunks below the diagonal exit at once, so about half of the grid
-    // works: aim at ~3 working CTAs per SM (two are resident), chunks of at least two stages (the scan reads two per pass)
+    // works: aim at ~8 working CTAs per SM (four are resident), chunks of at least four stages (the scan reads four per pass)
     const long long cells = static_cast<long long>(tiles) * N * pl.NS;
-    int chunk = static_cast<int>(std::min<long long>(std::max<long long>(2, cells / (2 * 3 * 148)), 64));
+    int chunk = static_cast<int>(std::min<long long>(std::max<long long>(4, cells / (2 * 8 * 148)), 64));
     chunk = std::min(chunk, std::max(1, pl.NS));
     const dim3 grid(tiles, ceil_div(pl.NS, chunk), N);
     prof_mark(4, stream);
@@ -1532,8 +1609,27 @@ static int pcm_bwd_impl(const float* f, const float* cam_norm, const float* cam_
     prof_mark(2, stream);
     if (int rc = dispatch_bwd(pl, N, precise != 0, stream)) return rc;
     prof_mark(3, stream);
-    pcm_bwd_post_kernel<<<dim3(ceil_div(pl.HW, kPostPix), N), 256, 0, stream>>>(
-        pl.dfhat, f, pl.inv_norm, pl.bound, grad_f, K, pl.HW, pl.HWpj, pl.nsplit, pl.PJ, pl.NS, pl.G);
+    if ((pl.HW & 3) == 0 && (reinterpret_cast<uintptr_t>(f) & 15) == 0 && (reinterpret_cast<uintptr_t>(grad_f) & 15) == 0) {
+        const dim3 grid(ceil_div(pl.HW, 32), N);
+#define WSEGK_POST_CASE(PERV)                                                                                   \
+    case PERV:                                                                                                  \
+        pcm_bwd_post_vec_kernel<PERV><<<grid, 256, 0, stream>>>(pl.dfhat, f, pl.inv_norm, pl.bound, grad_f, pl.HW, \
+                                                                pl.HWpj, pl.nsplit, pl.PJ, pl.NS, pl.G);         \
+        break;
+        switch (K / 32) {
+            WSEGK_POST_CASE(1)
+            WSEGK_POST_CASE(2)
+            WSEGK_POST_CASE(3)
+            WSEGK_POST_CASE(4)
+            WSEGK_POST_CASE(5)
+            default:
+                WSEGK_POST_CASE(6)
+        }
+#undef WSEGK_POST_CASE
+    } else {
+        pcm_bwd_post_kernel<<<dim3(ceil_div(pl.HW, kPostPix), N), 256, 0, stream>>>(
+            pl.dfhat, f, pl.inv_norm, pl.bound, grad_f, K, pl.HW, pl.HWpj, pl.nsplit, pl.PJ, pl.NS, pl.G);
+    }
     count_launches(3);
     WSEGK_CUDA_OK(cudaGetLastError());
     return WSEGK_OK;
