@@ -281,6 +281,8 @@ int wsegk_debug_pcm_fixup_ms(float* fix_ms);   /* the same for the sign fix-up k
 /* Timeline aid: when non-null (per host thread), CTA (0,0,0) of the next pcm_fwd main kernels writes clock64() stamps
  * into this DEVICE buffer of 768 int64: [role 0 producer | 1 MMA issuer | 2 first TMEM warp][stage < 64][4 events]. */
 int wsegk_debug_pcm_trace(long long* device_buffer);
+/* the same for the backward main kernel (768 int64) */
+int wsegk_debug_pcm_trace_bwd(long long* device_buffer);
 /* Test aid (host only, no GPU needed): the (unit, stage, segment, partial slot) quadruples CTA pair g of the persistent PCM
  * kernels runs for N images on an h x w grid; returns their number (0 for g beyond the grid). */
 int wsegk_debug_pcm_schedule(int N, int h, int w, int g, int* out, int capacity);

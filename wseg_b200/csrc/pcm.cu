@@ -218,7 +218,8 @@ __global__ void __launch_bounds__(256) pcm_prep_kernel(const float* __restrict__
 // + a second bit per entry, |S| < tau, where tau bounds what the FP16 rounding of the operands can do to S; those entries
 // (~0.2 %) are re-evaluated in fp32 by pcm_sign_fixup_kernel, which patches the sign mask.  Round 1 got the same signs from
 // three MMA chains (hi*hi + hi*lo + lo*hi): 3x the tensor work for a correction that matters for 1e-4 of the entries.
-constexpr int kMainThreads = 256;      // backward main kernel
+constexpr int kMainThreads = 384;      // backward main kernel: TMEM warps 0-7, producers 8 / 10 / 11, issuer 9
+constexpr int kBwdWarpProdUV = 8, kBwdWarpIssue = 9, kBwdWarpProdX = 10;
 constexpr int kFwdThreads = 384;
 // forward kernel roles.  The TMEM warps come FIRST: the sub-partition arbiter favours the higher warp ids, and the two ALU-dense
 // TMEM warps of a sub-partition otherwise starve the producer / issuer warp that shares it (trace r2: the S issuer needed
@@ -947,13 +948,17 @@ struct BwdBars {
     uint32_t tmem_base;
 };
 
+// NV values of T (fp32) -> E = [sign bit set] * T * scale as packed fp16.  The sign word has bit m = column 2m, bit 16+m =
+// column 2m+1.  Per pair: two FMUL and one IMAD on the FMA pipe (the 0 / 0xffff half masks come from a multiply), the
+// convert, one shift and two LOP3 on the ALU pipe — the predicated-select form the compiler made of the obvious code put
+// five ALU-pipe instructions on every pair, and the ALU pipe is what bounds a TMEM warp (tools/ubench/alu_rates.cu).
 template <int NV>
 __device__ __forceinline__ void mask_scale_pack(const uint32_t* r, uint32_t bits, float scale, uint32_t* pk) {
 #pragma unroll
     for (int m = 0; m < NV / 2; ++m) {
-        const float a = ((bits >> m) & 1u) ? __uint_as_float(r[2 * m]) * scale : 0.f;
-        const float b = ((bits >> (16 + m)) & 1u) ? __uint_as_float(r[2 * m + 1]) * scale : 0.f;
-        pk[m] = pack_f16x2(a, b);
+        const uint32_t h = pack_f16x2(__uint_as_float(r[2 * m]) * scale, __uint_as_float(r[2 * m + 1]) * scale);
+        const uint32_t keep = ((bits >> m) & 0x00010001u) * 0xffffu;
+        pk[m] = h & keep;
     }
 }
 
@@ -961,7 +966,10 @@ template <int WB, bool SPLIT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMainThreads, 1)
 pcm_bwd_kernel(const uint8_t* __restrict__ ua, const uint8_t* __restrict__ vb, const uint8_t* __restrict__ fb,
                const uint4* __restrict__ mask, const float* __restrict__ bound, float* __restrict__ dfhat, int K,
-               int PJ, int NS, int n_units, int nslot) {
+               int PJ, int NS, int n_units, int nslot, long long* __restrict__ trace) {
+    // optional timeline of CTA 0 (wsegk_debug_pcm_trace): trace[role*256 + t*4 + k] = clock64()
+    const bool tr = trace != nullptr && blockIdx.x == 0;
+#define TRACE(role, t, k) do { if (tr && (t) < 64) trace[(role) * 256 + (t) * 4 + (k)] = clock64(); } while (0)
     constexpr int NCOL = 2 * WB;
     constexpr int KU = SPLIT ? 3 * kAugK : kAugK;
     constexpr uint32_t kUBytes = kTile * KU * 2, kVBytes = WB * KU * 2;
@@ -994,12 +1002,12 @@ pcm_bwd_kernel(const uint8_t* __restrict__ ua, const uint8_t* __restrict__ vb, c
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(smem_u32(&bars->t_full[b]), 1);
-            mbar_init(smem_u32(&bars->e_full[b]), 8);
+            mbar_init(smem_u32(&bars->e_full[b]), 16);        // 8 TMEM warps x 2 CTAs
         }
         mbar_init(smem_u32(&bars->g_full), 1);
         mbar_fence_init();
     }
-    if (warp == 1) {
+    if (warp == kBwdWarpIssue) {
         tmem_alloc_2cta(smem_u32(&bars->tmem_base), kTmemCols);
         tmem_relinquish_2cta();
     }
@@ -1010,7 +1018,7 @@ pcm_bwd_kernel(const uint8_t* __restrict__ ua, const uint8_t* __restrict__ vb, c
     const uint32_t tmem = bars->tmem_base;
     const size_t b_bytes = static_cast<size_t>(WB) * K * 2;
 
-    if (warp == 0) {
+    if (warp == kBwdWarpProdUV) {
         // ---------------------------------------------------------------- producer A: the segment's U tile and the V tiles
         if (lane == 0) {
             StageCursor si = c0;
@@ -1023,21 +1031,23 @@ pcm_bwd_kernel(const uint8_t* __restrict__ ua, const uint8_t* __restrict__ vb, c
                 }
                 const int s = i % kBwdStages, u = i / kBwdStages;
                 mbar_wait(smem_u32(&bars->empty_v[s]), (u & 1) ^ 1);
+                TRACE(0, i, 0);
                 const uint32_t bar = smem_u32(&bars->full_v[s]);
                 mbar_arrive_expect_tx(bar, kVBytes);
                 tma_load_1d(smem_u32(s_v + s * kVBytes),
                             vb + (static_cast<size_t>(si.n) * 2 * NS + 2 * si.st + rank) * kVBytes, kVBytes, bar);
             }
         }
-    } else if (warp >= 6) {
+    } else if (warp >= kBwdWarpProdX) {
         // ---------------------------------------------------------------- producers B, C: my half of the channels (groups
         // [rank*K/16, (rank+1)*K/16)) of the stage's X tile (warp 6) and Y tile (warp 7)
         if (lane == 0) {
-            const int part = warp - 6;
+            const int part = warp - kBwdWarpProdX;
             StageCursor si = c0;
             for (int i = 0; i < cnt; ++i, si.next()) {
                 const int s = i % kBwdStages, u = i / kBwdStages;
                 mbar_wait(smem_u32(&bars->empty_f[s]), (u & 1) ^ 1);
+                if (part == 0) TRACE(0, i, 1);
                 const uint32_t bar = smem_u32(&bars->full_f[s]);
                 mbar_arrive_expect_tx(bar, f_part);
                 const uint8_t* x = fb + (static_cast<size_t>(si.n) * 2 * NS + 2 * si.st + part) * b_bytes +
@@ -1045,7 +1055,7 @@ pcm_bwd_kernel(const uint8_t* __restrict__ ua, const uint8_t* __restrict__ vb, c
                 tma_load_1d(smem_u32(s_f + s * f_stage + part * f_part), x, f_part, bar);
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == kBwdWarpIssue) {
         if (lane == 0 && rank == 1) {
             StageCursor si = c0;
             for (int i = 0; i < cnt; ++i, si.next()) {
@@ -1075,13 +1085,17 @@ pcm_bwd_kernel(const uint8_t* __restrict__ ua, const uint8_t* __restrict__ vb, c
                     cs.next();
                     const int s = i % kBwdStages, u = i / kBwdStages, b = i & 1;
                     if (seg_first) mbar_wait(smem_u32(&bars->uj), seg & 1);
+                    TRACE(1, i, 0);
                     mbar_wait(smem_u32(&bars->full_v[s]), u & 1);
+                    TRACE(1, i, 1);
                     tc_fence_after();
                     const uint64_t dv = dv0 + static_cast<uint64_t>((s * kVBytes) >> 4);
+#ifndef WSEGK_ABL_NOT
 #pragma unroll
                     for (int ks = 0; ks < KU / 16; ++ks)
                         umma2_ss(tmem + b * 128, du + static_cast<uint64_t>(ks * (2 * lbo_a / 16)),
                                  dv + static_cast<uint64_t>(ks * (2 * lbo_b / 16)), id_t, ks > 0);
+#endif
                     umma2_commit(smem_u32(&bars->t_full[b]));
                     umma2_commit(smem_u32(&bars->empty_v[s]));
                     if (seg_last) umma2_commit(smem_u32(&bars->u_free));
@@ -1099,20 +1113,32 @@ pcm_bwd_kernel(const uint8_t* __restrict__ ua, const uint8_t* __restrict__ vb, c
                 StageCursor si = c0;
                 for (int i = 0; i < cnt; ++i, si.next()) {
                     const int s = i % kBwdStages, u = i / kBwdStages, b = i & 1;
+                    TRACE(1, i, 2);
+                    if (tr) {
+                        mbar_wait(smem_u32(&bars->e_full[b]), (i >> 1) & 1);
+                        TRACE(0, i, 2);
+                    }
                     mbar_wait2(smem_u32(&bars->e_full[b]), (i >> 1) & 1, smem_u32(&bars->full_f[s]), u & 1);
+                    TRACE(1, i, 3);
                     tc_fence_after();
                     const uint32_t f0 = smem_u32(s_f + s * f_stage);
                     const uint32_t acc0 = si.first() ? 0u : 1u;
                     // dFh[j, ch] += E[j, q] * F[q, ch] over the stage's pixels q = [X(0:WB) | Y(0:WB)]; B is N(ch) x K(q),
                     // MN-major: LBO = step between the two 8-pixel groups of the k-step, SBO = channel-group step
+#ifndef WSEGK_ABL_NOG
 #pragma unroll
                     for (int ks = 0; ks < NCOL / 16; ++ks) {
                         const int q0 = 16 * ks, q1 = q0 + 8;
                         const uint32_t a0 = f0 + (q0 / WB) * f_part + (q0 % WB) * 16;
                         const uint32_t a1 = f0 + (q1 / WB) * f_part + (q1 % WB) * 16;
-                        umma2_ts(tmem + kColG, tmem + b * 128 + ks * 8, umma_smem_desc(a0, a1 - a0, lbo_b), id_g,
+                        // E of the T columns [0,64) sits at packed columns [0,32) of the buffer, E of the columns from 64 on at
+                        // [64, ...) (the two TMEM warps of a quarter each overwrite only what they loaded)
+                        constexpr int kHalf = kSplitCol / 16;
+                        const uint32_t ecol = ks < kHalf ? ks * 8 : kSplitCol + (ks - kHalf) * 8;
+                        umma2_ts(tmem + kColG, tmem + b * 128 + ecol, umma_smem_desc(a0, a1 - a0, lbo_b), id_g,
                                  ks > 0 ? 1u : acc0);
                     }
+#endif
                     umma2_commit(smem_u32(&bars->empty_f[s]));
                     if (si.last()) umma2_commit(smem_u32(&bars->g_full));
                     issue_upto(i);
@@ -1120,55 +1146,67 @@ pcm_bwd_kernel(const uint8_t* __restrict__ ua, const uint8_t* __restrict__ vb, c
             }
             __syncwarp();
         }
-    } else if (warp < 6) {
-        const int q = warp & 3;
+    } else if (warp < 8) {
+        // ---------------------------------------------------------------- TMEM warps: two per lane quarter, the first takes the
+        // T columns [0,64) of its 32 rows, the second the rest (as in the forward kernel); each loads the NEXT stage's columns
+        // as soon as it has handed this stage's E over, so the barrier poll and the TMEM load latency overlap
+        const int q = warp & 3, hf = warp >> 2;
+        constexpr int NC1 = NCOL - kSplitCol;            // 64, 48 or 32 columns for the second warp
         const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
         const int row_in = static_cast<int>(rank) * kTile + q * 32 + lane;
         const uint32_t e_full0 = mapa_shared(smem_u32(&bars->e_full[0]), 0);
-        const uint32_t e_full1 = mapa_shared(smem_u32(&bars->e_full[1]), 0);
         const float scale = pcm_grad_scale(bound);
         StageCursor si = c0, sn = c0;      // this stage / the next one (mask prefetch)
-        auto mask_of = [&](const StageCursor& c) {
-            return __ldg(mask + (static_cast<size_t>(c.n) * NS + c.st) * HWpj + c.jp * 2 * kTile + row_in);
+        const uint2* mask2 = reinterpret_cast<const uint2*>(mask);
+        auto mask_of = [&](const StageCursor& c) {       // my two sign words of the row
+            return __ldg(mask2 + ((static_cast<size_t>(c.n) * NS + c.st) * HWpj + c.jp * 2 * kTile + row_in) * 2 + hf);
         };
-        uint4 mw_next = cnt > 0 ? mask_of(sn) : make_uint4(0, 0, 0, 0);
+        uint32_t r0[32], r1[32];
+        auto fetch = [&](int i) {
+            if (warp == 0 && lane == 0) TRACE(2, i, 0);
+            mbar_wait(smem_u32(&bars->t_full[i & 1]), (i >> 1) & 1);
+            tc_fence_after();
+            const uint32_t base = tmem + lane_addr + (i & 1) * 128 + hf * kSplitCol;
+            if (hf == 0) load_cols<kSplitCol>(base, r0, r1);
+            else load_cols<NC1>(base, r0, r1);
+        };
+        uint2 mw_next = cnt > 0 ? mask_of(sn) : make_uint2(0, 0);
+        if (cnt > 0) fetch(0);
         for (int i = 0; i < cnt; ++i, si.next()) {
             const int b = i & 1;
-            const uint4 mw4 = mw_next;
-            sn.next();
-            if (i + 1 < cnt) mw_next = mask_of(sn);
-            const uint32_t mw[4] = {mw4.x, mw4.y, mw4.z, mw4.w};
-            mbar_wait(smem_u32(&bars->t_full[b]), (i >> 1) & 1);
-            tc_fence_after();
-            const uint32_t base = tmem + lane_addr + b * 128;
-#pragma unroll
-            for (int c = 0; c < NCOL / 32; ++c) {
-                uint32_t r[32], pk[16];
-                tmem_ld32(base + c * 32, r);
-                tmem_ld_wait();
-                mask_scale_pack<32>(r, mw[c], scale, pk);
-                tmem_st16(base + c * 16, pk);
-            }
-            if (NCOL % 32) {
-                constexpr int c = NCOL / 32;
-                uint32_t r[16], pk[8];
-                tmem_ld16(base + c * 32, r);
-                tmem_ld_wait();
-                mask_scale_pack<16>(r, mw[c & 3], scale, pk);
-                tmem_st8(base + c * 16, pk);
+            const uint2 mw = mw_next;
+            tmem_ld_wait();
+            if (warp == 0 && lane == 0) TRACE(2, i, 1);
+            const uint32_t base = tmem + lane_addr + b * 128 + hf * kSplitCol;
+            uint32_t pk[16];
+            mask_scale_pack<32>(r0, mw.x, scale, pk);
+            tmem_st16(base, pk);
+            if (hf == 0 || NC1 == 64) {
+                mask_scale_pack<32>(r1, mw.y, scale, pk);
+                tmem_st16(base + 16, pk);
+            } else if (NC1 == 48) {
+                mask_scale_pack<16>(r1, mw.y, scale, pk);
+                tmem_st8(base + 16, reinterpret_cast<uint32_t(&)[8]>(pk));
             }
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster_relaxed(b ? e_full1 : e_full0);
+            if (lane == 0) mbar_arrive_cluster_relaxed(e_full0 + static_cast<uint32_t>(b) * 8u);
+            if (warp == 0 && lane == 0) TRACE(2, i, 2);
+            // the next stage's sign words are requested only now: an arrive is held back behind the warp's outstanding
+            // global accesses (trace r2 of the forward kernel), and "E is ready" is on the critical path
+            sn.next();
+            if (i + 1 < cnt) mw_next = mask_of(sn);
+            if (i + 1 < cnt) fetch(i + 1);
             if (si.last()) {
                 // segment epilogue.  dfhat [n][slot][K][HWpj]: for a fixed channel the 32 lanes of a warp write 32
-                // consecutive pixels
+                // consecutive pixels; the two warps of a quarter take half of the channels each
                 const int slot = si.in_tail() ? g - pcm_tail_owner(sched, static_cast<long long>(si.u - sched.Rf * sched.G) * NS) : 0;
                 mbar_wait(smem_u32(&bars->g_full), si.k & 1);
                 tc_fence_after();
                 float* dst = dfhat + ((static_cast<size_t>(si.n) * nslot + slot) * K) * HWpj + si.jp * 2 * kTile + row_in;
-                for (int c = 0; c < (K >> 4); ++c) {
+                const int cgroups = K >> 4, c_begin = hf * ((cgroups + 1) >> 1), c_end = hf ? cgroups : ((cgroups + 1) >> 1);
+                for (int c = c_begin; c < c_end; ++c) {
                     uint32_t r[16];
                     tmem_ld16(tmem + lane_addr + kColG + c * 16, r);
                     tmem_ld_wait();
@@ -1182,7 +1220,8 @@ pcm_bwd_kernel(const uint8_t* __restrict__ ua, const uint8_t* __restrict__ vb, c
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();
-    if (warp == 1) tmem_dealloc_2cta(tmem, kTmemCols);
+    if (warp == kBwdWarpIssue) tmem_dealloc_2cta(tmem, kTmemCols);
+#undef TRACE
 }
 
 // grad_f[n,k,p] = dfh[k] * inv - f[k] * (sum_k dfh[k] f[k]) * inv^2 / |f|,  inv = 1/(|f| + 1e-5)
@@ -1356,6 +1395,7 @@ struct PcmProf {
     bool have[3] = {false, false, false};
 };
 thread_local PcmProf g_prof;
+thread_local long long* g_trace_bwd = nullptr; // the same for the backward kernel (768 int64)
 thread_local long long* g_trace = nullptr;   // device buffer of 1024 + 2 * 148 + 2 int64 for the forward kernel's timeline, or null
 void prof_mark(int which, wsegk_stream_t stream) {
     if (!g_prof.on) return;
@@ -1372,6 +1412,11 @@ extern "C" int wsegk_debug_pcm_profile(int enable) {
 
 extern "C" int wsegk_debug_pcm_trace(long long* device_buffer) {
     g_trace = device_buffer;
+    return WSEGK_OK;
+}
+
+extern "C" int wsegk_debug_pcm_trace_bwd(long long* device_buffer) {
+    g_trace_bwd = device_buffer;
     return WSEGK_OK;
 }
 
@@ -1424,7 +1469,7 @@ static int launch_bwd(const PcmPlan& pl, int N, wsegk_stream_t stream) {
     pcm_bwd_kernel<WB, SPLIT><<<dim3(2 * pl.G), kMainThreads, smem, stream>>>(
         reinterpret_cast<const uint8_t*>(pl.ua), reinterpret_cast<const uint8_t*>(pl.vb),
         reinterpret_cast<const uint8_t*>(pl.fb), reinterpret_cast<const uint4*>(pl.mask), pl.bound, pl.dfhat, pl.K,
-        pl.PJ, pl.NS, N * pl.PJ, pl.nsplit);
+        pl.PJ, pl.NS, N * pl.PJ, pl.nsplit, g_trace_bwd);
     return WSEGK_OK;
 }
 
