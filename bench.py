@@ -96,15 +96,24 @@ class HotPath:
         ops, d = self.ops, self.d
         VIEW1, VIEW2 = self.view1, self.view2
         if not hasattr(self, "_streams"):
-            prio = int(os.environ.get("WSEG_BENCH_PRIO", "1"))
-            # the view-1 chain (K1a -> K2 fwd -> K1b -> K2 bwd) is the critical path: its stream gets the higher priority
-            self._streams = [torch.cuda.Stream(device=self.dev, priority=-1 if prio else 0)] + \
-                            [torch.cuda.Stream(device=self.dev) for _ in range(4)]
-        s1, s2, s3, s4, s5 = self._streams
+            prio = int(os.environ.get("WSEG_BENCH_PRIO", "3"))
+            lo, hi = torch.cuda.Stream.priority_range() if hasattr(torch.cuda.Stream, "priority_range") else (0, -1)
+            # the view-1 chain (K1a -> K2 fwd -> K1b -> K2 bwd) is the critical path at one GPU: high priority (prio >= 1).
+            # The loss chain (s3: a dozen small latency-bound kernels) ends the step once the prototypes travel between ranks:
+            # served first as well (prio >= 2), and so is what gates it — view 2's short forward + seeds + prototypes, on
+            # their own stream s6 ahead of everything (prio >= 3) instead of queueing behind the K1b kernels of s2 / s4
+            p1 = -1 if prio >= 1 else 0
+            p3 = -1 if prio >= 2 else 0
+            p6 = max(hi, -2) if prio >= 3 else 0
+            p1, p3, p6 = (int(os.environ.get(k, v)) for k, v in (("WSEG_BENCH_P1", p1), ("WSEG_BENCH_P3", p3), ("WSEG_BENCH_P6", p6)))
+            self._streams = [torch.cuda.Stream(device=self.dev, priority=p1), torch.cuda.Stream(device=self.dev),
+                             torch.cuda.Stream(device=self.dev, priority=p3), torch.cuda.Stream(device=self.dev),
+                             torch.cuda.Stream(device=self.dev), torch.cuda.Stream(device=self.dev, priority=p6)]
+        s1, s2, s3, s4, s5, s6 = self._streams
         outer = torch.cuda.current_stream(self.dev)
         fork = torch.cuda.Event()
         fork.record(outer)
-        for s in (s1, s2, s3, s4, s5):
+        for s in (s1, s2, s3, s4, s5, s6):
             s.wait_event(fork)
         keep = []
         cur = s1
@@ -130,12 +139,14 @@ class HotPath:
                 ops.pcm_sign_fixup(ws1, self.n, C_CLS, K_PCM, VIEW1[0] // 8, VIEW1[1] // 8)
             fix1_done.record(s5)
         # ---- view 2 chain: K1a, K2 forward, its seeds and prototypes, then K1b(cam_rv2) and K2 backward
-        with torch.cuda.stream(s2):
+        with torch.cuda.stream(s6):
             rv2, ws2, camn2 = ops.pcm_forward_logits(d["cam2"], d["f2"])
             norm2, pl2 = ops.seed_labels(rv2, d["label"], BG_THRESHOLD)
             proto2, ti2 = ops.prototypes(norm2, d["fproj2"], group=self.group, view=1)
             v2_done = torch.cuda.Event()
-            v2_done.record(s2)
+            v2_done.record(s6)
+        with torch.cuda.stream(s2):
+            s2.wait_event(v2_done)
             g_rv2 = k1b("rv2_full", None, "g_rv2")
             gf2 = ops.pcm_backward(d["f2"], camn2, rv2, d["g_rv_down2"], ws2)
             s2_done = torch.cuda.Event()

@@ -281,6 +281,11 @@ int wsegk_debug_pcm_fixup_ms(float* fix_ms);   /* the same for the sign fix-up k
 /* Timeline aid: when non-null (per host thread), CTA (0,0,0) of the next pcm_fwd main kernels writes clock64() stamps
  * into this DEVICE buffer of 768 int64: [role 0 producer | 1 MMA issuer | 2 first TMEM warp][stage < 64][4 events]. */
 int wsegk_debug_pcm_trace(long long* device_buffer);
+/* diagnostics of the NVLink prototype exchange: device buffer of 2 x 17 uint64 globaltimer stamps per view — [0] the rank
+   started waiting for its peers' pushes, [1 + r] it saw rank r's flag; NULL switches it off (thread-local) */
+int wsegk_debug_exchange_stamps(unsigned long long* device_buffer);
+/* diagnostics: *dst = %globaltimer (ns) when `stream` reaches this point */
+int wsegk_debug_stamp(unsigned long long* dst, wsegk_stream_t stream);
 /* the same for the backward main kernel (768 int64) */
 int wsegk_debug_pcm_trace_bwd(long long* device_buffer);
 /* Test aid (host only, no GPU needed): the (unit, stage, segment, partial slot) quadruples CTA pair g of the persistent PCM

@@ -25,6 +25,8 @@ _SIGNATURES = {
     "wsegk_debug_pcm_main_ms": (c_int, [ctypes.POINTER(c_float), ctypes.POINTER(c_float)]),
     "wsegk_debug_pcm_fixup_ms": (c_int, [ctypes.POINTER(c_float)]),
     "wsegk_debug_pcm_trace": (c_int, [_P]),
+    "wsegk_debug_exchange_stamps": (c_int, [_P]),
+    "wsegk_debug_stamp": (c_int, [_P, _P]),
     "wsegk_debug_pcm_trace_bwd": (c_int, [_P]),
     "wsegk_debug_force_radix": (c_int, [c_int]),
     "wsegk_debug_pcm_schedule": (c_int, [c_int, c_int, c_int, c_int, _P, c_int]),

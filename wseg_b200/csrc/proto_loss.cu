@@ -422,6 +422,31 @@ __global__ void __launch_bounds__(1024) proto_finalize_kernel(CandSrc src, int n
 // and stores it into slot (parity, view, my rank) of EVERY peer's buffer (plain stores to mapped peer addresses), fences,
 // and the last CTA to finish releases flag[view][my rank] = step on every peer.  proto_finalize then only waits for R flags
 // in its own memory.  No NCCL kernel, no host involvement, graph-capturable; the step number lives on the device.
+// The wait for the peers' pushes, in a kernel of ONE warp that fits beside anything (32 threads, < 32 registers): while
+// the 21 CTAs x 1024 threads of proto_finalize_kernel did the spinning themselves they held 21 SMs for as long as the slowest
+// peer was behind, and the persistent PCM kernels (one whole-SM CTA on 144 of the 148 SMs) could not be placed until the
+// spin ended — the step lost the ranks' skew (~40 us) from 2 GPUs on (SCALE_r01).
+__global__ void __launch_bounds__(32) proto_wait_flags_kernel(const uint32_t* wait_flags, const uint32_t* wait_step,
+                                                              int n_ranks, unsigned long long* stamp) {
+    if (static_cast<int>(threadIdx.x) < n_ranks) {
+        const uint32_t want = *wait_step;
+        unsigned long long t0 = 0;
+        if (stamp != nullptr && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t0));
+        unsigned long long spins = 0;
+        while (static_cast<int32_t>(ld_acquire_sys(wait_flags + threadIdx.x) - want) < 0) {
+            if (++spins > (1ull << 33)) __trap();          // a peer died: fail the launch instead of hanging
+            __nanosleep(64);
+        }
+        if (stamp != nullptr) {
+            // diagnostics (wsegk_debug_exchange_stamps): [0] when this rank started waiting, [1 + r] when rank r's flag was seen
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t1));
+            if (threadIdx.x == 0) stamp[0] = t0;
+            stamp[1 + threadIdx.x] = t1;
+        }
+    }
+}
+
 constexpr int kMaxRanks = 16;
 struct PushPeers {
     float* cand[kMaxRanks];
@@ -1464,6 +1489,26 @@ extern "C" int wsegk_proto_push(const float* top_val, const int32_t* top_idx, co
     return WSEGK_OK;
 }
 
+// optional device buffer of 2 x (1 + 16) uint64 globaltimer stamps written by the flag-wait kernel of each view
+static thread_local unsigned long long* g_exchange_stamps = nullptr;
+extern "C" int wsegk_debug_exchange_stamps(unsigned long long* device_buffer) {
+    g_exchange_stamps = device_buffer;
+    return WSEGK_OK;
+}
+
+__global__ void stamp_kernel(unsigned long long* dst) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+    *dst = t;
+}
+// diagnostics: *dst = %globaltimer (ns, one clock for all GPUs of a box) when the stream reaches this point
+extern "C" int wsegk_debug_stamp(unsigned long long* dst, wsegk_stream_t stream) {
+    WSEGK_REQUIRE(dst, WSEGK_ERR_NULL, "debug_stamp: null pointer");
+    stamp_kernel<<<1, 1, 0, stream>>>(dst);
+    WSEGK_CUDA_OK(cudaGetLastError());
+    return WSEGK_OK;
+}
+
 extern "C" int wsegk_proto_finalize_symm(const void* local_base, int R, int view, int k, float* proto, int32_t* sel_idx,
                                          int C, int D, const uint32_t* local_state, wsegk_stream_t stream) {
     if (int rc = check_device()) return rc;
@@ -1482,8 +1527,10 @@ extern "C" int wsegk_proto_finalize_symm(const void* local_base, int R, int view
     const uint32_t* flags = reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(local_base) + flag_off) + view * R;
     // parity offset is applied inside the kernel (the step number is only known on the device)
     CandSrc src{nullptr, nullptr, nullptr, base + static_cast<size_t>(view) * R * slot_floats, n_cand, C, k, D};
+    proto_wait_flags_kernel<<<1, 32, 0, stream>>>(flags, local_state + view * 2, R,
+                                                  g_exchange_stamps ? g_exchange_stamps + view * (1 + kMaxRanks) : nullptr);
     proto_finalize_kernel<<<C, 1024, smem, stream>>>(src, npad, proto, sel_idx, flags, local_state + view * 2, R);
-    count_launches(1);
+    count_launches(2);
     WSEGK_CUDA_OK(cudaGetLastError());
     return WSEGK_OK;
 }
