@@ -118,6 +118,14 @@ class HotPath:
         keep = []
         cur = s1
         torch.cuda.set_stream(s1)
+        marks = getattr(self, "marks", None)          # tools/step_timeline.py: %globaltimer stamps at the milestones of the step
+
+        def mark(name, stream):
+            if marks is not None:
+                from wseg_b200 import _lib
+                idx = marks["names"].setdefault(name, len(marks["names"]))
+                _lib.lib().wsegk_debug_stamp(marks["buf"].data_ptr() + 8 * idx, stream.cuda_stream)
+        mark("start", s1)
 
         def k1b(name, size, gname):
             y, saved = ops.fullres_norm_fwd(d[name], d["label"], size)
@@ -130,6 +138,7 @@ class HotPath:
         # re-evaluation of the near-zero entries of S, only the backward needs it) runs on its own stream beside K1b
         defer = ops.get_pcm_mode() == "precise" and os.environ.get("WSEG_BENCH_DEFER_FIXUP", "1") == "1"
         rv1, ws1, camn1 = ops.pcm_forward_logits(d["cam1"], d["f1"], defer_fixup=defer)
+        mark("fwd1 done", s1)
         f1_done = torch.cuda.Event()
         f1_done.record(cur)
         fix1_done = torch.cuda.Event()
@@ -137,18 +146,23 @@ class HotPath:
             if defer:
                 s5.wait_event(f1_done)
                 ops.pcm_sign_fixup(ws1, self.n, C_CLS, K_PCM, VIEW1[0] // 8, VIEW1[1] // 8)
+            mark("fixup1 done", s5)
             fix1_done.record(s5)
         # ---- view 2 chain: K1a, K2 forward, its seeds and prototypes, then K1b(cam_rv2) and K2 backward
         with torch.cuda.stream(s6):
             rv2, ws2, camn2 = ops.pcm_forward_logits(d["cam2"], d["f2"])
+            mark("fwd2 done", s6)
             norm2, pl2 = ops.seed_labels(rv2, d["label"], BG_THRESHOLD)
             proto2, ti2 = ops.prototypes(norm2, d["fproj2"], group=self.group, view=1)
+            mark("proto2 done", s6)
             v2_done = torch.cuda.Event()
             v2_done.record(s6)
         with torch.cuda.stream(s2):
             s2.wait_event(v2_done)
             g_rv2 = k1b("rv2_full", None, "g_rv2")
+            mark("K1b rv2 done", s2)
             gf2 = ops.pcm_backward(d["f2"], camn2, rv2, d["g_rv_down2"], ws2)
+            mark("bwd2 done", s2)
             s2_done = torch.cuda.Event()
             s2_done.record(s2)
         # ---- loss chain: shrink view 1 to the loss grid (contrast_train.py:179-180), K1c, K3 (whole batch across
@@ -158,22 +172,29 @@ class HotPath:
             f1 = ops.resize_fwd(d["fproj1"], self.grid)
             c1 = ops.resize_fwd(rv1, self.grid)
             norm1, pl1 = ops.seed_labels(c1, d["label"], BG_THRESHOLD)
+            mark("seeds1 done", s3)
             proto1, ti1 = ops.prototypes(norm1, f1, group=self.group, view=0)
+            mark("proto1 done", s3)
             s3.wait_event(v2_done)
             losses, g1, g2, _, _ = ops.contrast_loss_raw(f1, d["fproj2"], proto1, proto2, pl1, pl2, self.key1, self.key2)
             keep.extend([f1, c1, norm1, pl1, norm2, pl2, proto1, ti1, proto2, ti2])
+            mark("K4 done", s3)
             s3_done = torch.cuda.Event()
             s3_done.record(s3)
         # ---- K1b on the plain CAMs (independent of the PCM)
         with torch.cuda.stream(s4):
             g_n1 = k1b("cam1_full", VIEW2, "g_n1")
+            mark("K1b cam1 done", s4)
             g_n2 = k1b("cam2_full", None, "g_n2")
+            mark("K1b cam2 done", s4)
             s4_done = torch.cuda.Event()
             s4_done.record(s4)
         # ---- view 1: K1b on cam_rv, then K2 backward
         g_rv1 = k1b("rv1_full", VIEW2, "g_rv1")
+        mark("K1b rv1 done", s1)
         s1.wait_event(fix1_done)
         gf1 = ops.pcm_backward(d["f1"], camn1, rv1, d["g_rv_down1"], ws1)
+        mark("bwd1 done", s1)
         s1_done = torch.cuda.Event()
         s1_done.record(s1)
         torch.cuda.set_stream(outer)
@@ -458,21 +479,31 @@ def pcm_roofline(hp, pk, flush, args):
     stream (inside the library, around the kernel), L2 flushed before every launch -> burst peak."""
     ops, d, n = hp.ops, hp.d, hp.n
     h, w = hp.view1[0] // 8, hp.view1[1] // 8
-    fwd_ms, bwd_ms, fix_ms = [], [], []
     camn1 = ops.cam_norm(d["cam1"])
-    ops.pcm_profile(True)
-    for _ in range(max(3, args.warmup)):
-        rv1, ws1 = ops.pcm_forward(camn1, d["f1"])
-        ops.pcm_backward(d["f1"], camn1, rv1, d["g_rv_down1"], ws1)
-    for _ in range(max(5, args.steps)):
-        flush.zero_()
-        rv1, ws1 = ops.pcm_forward(camn1, d["f1"])
-        ops.pcm_backward(d["f1"], camn1, rv1, d["g_rv_down1"], ws1)
-        a, b = ops.pcm_main_ms()
-        fwd_ms.append(a)
-        bwd_ms.append(b)
-        fix_ms.append(ops.pcm_fixup_ms())
-    ops.pcm_profile(False)
+
+    def measure():
+        fwd_ms, bwd_ms, fix_ms = [], [], []
+        ops.pcm_profile(True)
+        for _ in range(max(3, args.warmup)):
+            rv1, ws1 = ops.pcm_forward(camn1, d["f1"])
+            ops.pcm_backward(d["f1"], camn1, rv1, d["g_rv_down1"], ws1)
+        for _ in range(max(5, args.steps)):
+            flush.zero_()
+            rv1, ws1 = ops.pcm_forward(camn1, d["f1"])
+            ops.pcm_backward(d["f1"], camn1, rv1, d["g_rv_down1"], ws1)
+            a, b = ops.pcm_main_ms()
+            fwd_ms.append(a)
+            bwd_ms.append(b)
+            fix_ms.append(ops.pcm_fixup_ms())
+        ops.pcm_profile(False)
+        return fwd_ms, bwd_ms, fix_ms
+
+    fwd_ms, bwd_ms, fix_ms = measure()            # as shipped: the CTA-pair counts the step runs with (64 / 52)
+    ops.set_pcm_pairs(72, 72)                     # and on 72 / 72 pairs: what the kernels reach with the GPU to themselves
+    try:
+        fwd72, bwd72, _ = measure()
+    finally:
+        ops.set_pcm_pairs(0, 0)
     hw = h * w
     fl_fwd = 2.0 * n * hw * hw * (K_PCM + C_CLS)
     fl_bwd = 2.0 * n * hw * hw * (2 * K_PCM + C_CLS)
@@ -492,7 +523,12 @@ def pcm_roofline(hp, pk, flush, args):
                 "other": {"pcm_fwd_kernel": {"ms": avg(fwd_ms), "tflops": tf_fwd, "frac": tf_fwd / pk["bf16_tflops"]},
                           "pcm_bwd_kernel": {"ms": avg(bwd_ms), "tflops": tf_bwd, "frac": tf_bwd / pk["bf16_tflops"]},
                           "pcm_fwd+bwd": {"ms": avg(fwd_ms) + avg(bwd_ms),
-                                          "frac": (fl_fwd + fl_bwd) / ((avg(fwd_ms) + avg(bwd_ms)) * 1e-3) / 1e12 / pk["bf16_tflops"]}}}
+                                          "frac": (fl_fwd + fl_bwd) / ((avg(fwd_ms) + avg(bwd_ms)) * 1e-3) / 1e12 / pk["bf16_tflops"]},
+                          "on_72_of_74_sm_pairs": {
+                              "note": "the same kernels with the GPU to themselves (ops.set_pcm_pairs(72, 72)); the step runs them on "
+                                      "64 / 52 pairs because the SMs they leave free run the other chains (bench A/B: step 0.334 -> 0.31 ms)",
+                              "pcm_fwd_kernel": {"ms": avg(fwd72), "frac": fl_fwd / (avg(fwd72) * 1e-3) / 1e12 / pk["bf16_tflops"]},
+                              "pcm_bwd_kernel": {"ms": avg(bwd72), "frac": fl_bwd / (avg(bwd72) * 1e-3) / 1e12 / pk["bf16_tflops"]}}}}
     if ops.get_pcm_mode() == "precise":
         # what the tensor cores actually execute over the padded tiles: forward = ONE fp16 S product + a
         # 64-column P V product per stage (the near-zero signs are re-evaluated in fp32 by the fix-up kernel, off the

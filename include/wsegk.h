@@ -303,6 +303,11 @@ int wsegk_debug_force_radix(int on);
  *   0 "fast"   : no re-evaluation, single BF16 factor products (cam_rv identical; gradient terms with |S| < ~1e-4 may flip). */
 int wsegk_pcm_set_mode(int mode);
 int wsegk_pcm_get_mode(void);
+/* CTA pairs (1 .. 74; 0 = the default) the persistent PCM forward / backward main kernels of the calling THREAD run on.
+ * The defaults (64 / 52) are tuned for the whole training step, where the SMs a PCM kernel leaves free run the other chains'
+ * kernels; a PCM call on an otherwise idle GPU is fastest with 72 / 72.  The workspace layout depends on the setting: do not
+ * change it between wsegk_workspace_bytes, a forward and its backward. */
+int wsegk_pcm_set_pairs(int fwd_pairs, int bwd_pairs);
 
 /* Test aid: byte offsets of the PCM workspace sections, in the order
  * {fa, fh32, fb, nzmask, camb, inv_norm, dsum, part, mask, ua, vb, dfhat, bound, total_bytes, nsplit, PJ, HWpj,

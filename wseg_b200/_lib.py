@@ -32,6 +32,7 @@ _SIGNATURES = {
     "wsegk_debug_pcm_schedule": (c_int, [c_int, c_int, c_int, c_int, _P, c_int]),
     "wsegk_pcm_set_mode": (c_int, [c_int]),
     "wsegk_pcm_get_mode": (c_int, []),
+    "wsegk_pcm_set_pairs": (c_int, [c_int, c_int]),
     "wsegk_debug_pcm_layout": (c_int, [c_int] * 5 + [ctypes.POINTER(c_size_t), c_int]),
     "wsegk_cam_norm_fwd": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
     "wsegk_pcm_fwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),

@@ -77,11 +77,30 @@ static int pick_wb(int HW) {
 // cannot make progress while a PCM kernel runs.  72 pairs leave 4 SMs to them: the PCM kernels get ~3 % slower, the whole
 // step 1.7 % faster (A/B on one box, 68 / 70 / 72 within noise of each other, 66 and 74 slower; profiles/README.md).
 // A constant, not a device query, so that workspace sizes do not depend on where they are asked for.
-static int pick_clusters(long long T) {
-#ifndef WSEGK_PCM_PAIRS
-#define WSEGK_PCM_PAIRS 72
+// Defaults tuned on the whole training step (A/B on one box, profiles/README.md round 2): a B200 has 74 SM pairs and a PCM
+// CTA takes a whole SM, so every pair a PCM kernel does not use is two SMs on which the HBM- and latency-bound kernels of the
+// step's other chains run meanwhile.  In isolation 72 pairs are fastest (forward 46 us, backward 54 us at N = 8, 56x56); in
+// the step 64 / 52 pairs are (0.334 -> 0.31 ms; anything in 52..64 / 48..56 is within noise) although the two kernels alone
+// then take 51 / 64 us.  52 divides the 104 units of the headline shape: the backward then has no stream-K tail and one partial slot.
+#ifndef WSEGK_PCM_PAIRS_FWD
+#define WSEGK_PCM_PAIRS_FWD 64
 #endif
-    const long long slots = WSEGK_PCM_PAIRS;
+#ifndef WSEGK_PCM_PAIRS_BWD
+#define WSEGK_PCM_PAIRS_BWD 52
+#endif
+static thread_local int g_pcm_pairs[2] = {WSEGK_PCM_PAIRS_FWD, WSEGK_PCM_PAIRS_BWD};
+
+extern "C" int wsegk_pcm_set_pairs(int fwd_pairs, int bwd_pairs) {
+    if (fwd_pairs < 0 || fwd_pairs > 74 || bwd_pairs < 0 || bwd_pairs > 74) {
+        set_error("pcm_set_pairs: need 0 (default) .. 74 CTA pairs, got %d / %d", fwd_pairs, bwd_pairs);
+        return WSEGK_ERR_BAD_SHAPE;
+    }
+    g_pcm_pairs[0] = fwd_pairs ? fwd_pairs : WSEGK_PCM_PAIRS_FWD;
+    g_pcm_pairs[1] = bwd_pairs ? bwd_pairs : WSEGK_PCM_PAIRS_BWD;
+    return WSEGK_OK;
+}
+
+static int pick_clusters(long long T, long long slots) {
     long long g = T / 2;
     if (g > slots) g = slots;
     if (g < 1) g = 1;
@@ -102,8 +121,11 @@ PcmPlan make_pcm_plan(void* ws, int N, int C, int K, int h, int w, int precise) 
     p.wb = pick_wb(p.HW);
     p.NS = ceil_div(p.HW, 2 * p.wb);
     p.HWpi = p.NS * 2 * p.wb;
-    p.G = pick_clusters(static_cast<long long>(N) * p.PJ * p.NS);
-    p.nsplit = max_unit_segments(N * p.PJ, p.NS, p.G);
+    // forward and backward main kernels may run on different numbers of CTA pairs (round 2: with the step re-ordered the
+    // optimum moved down — what the other chains gain from the SMs a PCM kernel leaves free outweighs what the PCM loses)
+    p.G = pick_clusters(static_cast<long long>(N) * p.PJ * p.NS, g_pcm_pairs[0]);
+    p.Gb = pick_clusters(static_cast<long long>(N) * p.PJ * p.NS, g_pcm_pairs[1]);
+    p.nsplit = std::max(max_unit_segments(N * p.PJ, p.NS, p.G), max_unit_segments(N * p.PJ, p.NS, p.Gb));
     p.precise = precise ? 1 : 0;
     p.Ku = precise ? 3 * kAugK : kAugK;
     p.a_tile_bytes = static_cast<size_t>(kTile) * K * 2;

@@ -84,7 +84,7 @@ struct PcmPlan {
     int wb;          // B-tile rows per CTA (64, 56 or 48)
     int NS;          // stages along i: ceil(HW / (2*wb))
     int HWpi;        // NS * 2 * wb
-    int G;           // CTA pairs of the persistent main kernels (stream-K over all N*PJ*NS stages)
+    int G, Gb;       // CTA pairs of the persistent forward / backward main kernels (stream-K over all N*PJ*NS stages)
     int nsplit;      // partial-result slots per unit = the most CTA pairs that share one (image, j pair) sweep
     int precise;     // 1: exact sign mask (near-zero entries of S re-evaluated in fp32) + split backward factors; 0: single pass
     size_t a_tile_bytes, b_tile_bytes;

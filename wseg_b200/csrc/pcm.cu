@@ -1466,7 +1466,7 @@ static int launch_bwd(const PcmPlan& pl, int N, wsegk_stream_t stream) {
     WSEGK_REQUIRE(smem <= 232448, WSEGK_ERR_BAD_SHAPE, "pcm_bwd: %zu bytes of shared memory needed", smem);
     WSEGK_CUDA_OK(cudaFuncSetAttribute(pcm_bwd_kernel<WB, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem)));
-    pcm_bwd_kernel<WB, SPLIT><<<dim3(2 * pl.G), kMainThreads, smem, stream>>>(
+    pcm_bwd_kernel<WB, SPLIT><<<dim3(2 * pl.Gb), kMainThreads, smem, stream>>>(
         reinterpret_cast<const uint8_t*>(pl.ua), reinterpret_cast<const uint8_t*>(pl.vb),
         reinterpret_cast<const uint8_t*>(pl.fb), reinterpret_cast<const uint4*>(pl.mask), pl.bound, pl.dfhat, pl.K,
         pl.PJ, pl.NS, N * pl.PJ, pl.nsplit, g_trace_bwd);
@@ -1659,7 +1659,7 @@ static int pcm_bwd_impl(const float* f, const float* cam_norm, const float* cam_
 #define WSEGK_POST_CASE(PERV)                                                                                   \
     case PERV:                                                                                                  \
         pcm_bwd_post_vec_kernel<PERV><<<grid, 256, 0, stream>>>(pl.dfhat, f, pl.inv_norm, pl.bound, grad_f, pl.HW, \
-                                                                pl.HWpj, pl.nsplit, pl.PJ, pl.NS, pl.G);         \
+                                                                pl.HWpj, pl.nsplit, pl.PJ, pl.NS, pl.Gb);        \
         break;
         switch (K / 32) {
             WSEGK_POST_CASE(1)
@@ -1673,7 +1673,7 @@ static int pcm_bwd_impl(const float* f, const float* cam_norm, const float* cam_
 #undef WSEGK_POST_CASE
     } else {
         pcm_bwd_post_kernel<<<dim3(ceil_div(pl.HW, kPostPix), N), 256, 0, stream>>>(
-            pl.dfhat, f, pl.inv_norm, pl.bound, grad_f, K, pl.HW, pl.HWpj, pl.nsplit, pl.PJ, pl.NS, pl.G);
+            pl.dfhat, f, pl.inv_norm, pl.bound, grad_f, K, pl.HW, pl.HWpj, pl.nsplit, pl.PJ, pl.NS, pl.Gb);
     }
     count_launches(3);
     WSEGK_CUDA_OK(cudaGetLastError());

@@ -227,6 +227,12 @@ def set_pcm_mode(mode: str) -> None:
     check(_lib.lib().wsegk_pcm_set_mode(1 if mode == "precise" else 0), "wsegk_pcm_set_mode")
 
 
+def set_pcm_pairs(fwd: int = 0, bwd: int = 0) -> None:
+    """CTA pairs (of the GPU's 74) the PCM main kernels of the calling thread occupy; 0 = the default (tuned for the whole
+    training step: 64 / 52).  72 / 72 is fastest for a PCM call on an otherwise idle GPU.  Set it before sizing workspaces."""
+    check(_lib.lib().wsegk_pcm_set_pairs(int(fwd), int(bwd)), "wsegk_pcm_set_pairs")
+
+
 def get_pcm_mode() -> str:
     return "precise" if _lib.lib().wsegk_pcm_get_mode() == 1 else "fast"
 
