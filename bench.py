@@ -229,60 +229,93 @@ class GraphedStep:
 
 class E2EPath:
     """The same path through the public, reference-facing API (autograd operators + loss.contrast_terms), from PINNED
-    HOST buffers: every step copies the path's inputs host->device, runs Net.forward's tail (K1a, K2, bilinear x8 to full
+    HOST buffers: every step copies a step's inputs host->device, runs Net.forward's tail (K1a, K2, bilinear x8 to full
     resolution), the loss-side operators and their backward, and reads the losses back to the host.
 
-    The copies run on their own stream and every operator waits only for the tensors it reads, in the order the bytes
-    arrive (small tensors first, then f of view 1, then its projection features), so PCIe and the SMs overlap inside a
-    step.  The whole step (copies, public API calls with autograd, read-back) is captured once in a CUDA graph and
-    replayed; `--no-graph` runs the same code eagerly."""
+    Input pipeline (round 2): the device holds TWO sets of input buffers.  Step i computes on the set that was filled while
+    step i-1 ran, and meanwhile its copy stream brings the next step's inputs into the other set — what a training loop
+    with a prefetching loader does — so a step costs max(copies, compute) instead of their (partly overlapped) sum.  One
+    H2D copy of all inputs (37 MB) and one D2H read of the losses happen inside every timed step; `prefetch=False` is the
+    round-1 arrangement (a step waits for its own copies, operator by operator).  The whole step (copies, public API
+    calls with autograd, read-back) is captured in CUDA graphs (one per buffer set) and replayed; `--no-graph` runs the
+    same code eagerly."""
 
     # the path's inputs travel host -> device every step, in this order; the synthetic upstream gradients standing in
     # for the rest of the loss (g_*) stay resident — they would be produced on the device
     NAMES = ["label", "cam1", "cam2", "f2", "fproj2", "f1", "fproj1"]
 
-    def __init__(self, hp: HotPath, use_graph: bool, lazy: bool = False):
+    def __init__(self, hp: HotPath, use_graph: bool, lazy: bool = False, prefetch: bool = True):
         self.hp = hp
         self.lazy = lazy          # True: ops.fullres_norm_up on the small maps instead of x8 enlargement + ops.fullres_norm
+        self.prefetch = prefetch
         self.h2d_bytes = sum(hp.host[k].numel() * hp.host[k].element_size() for k in self.NAMES)
         self.out_host = torch.empty(10, dtype=torch.float32).pin_memory()
         self.d2h_bytes = 40
-        self.static = {k: torch.empty_like(hp.d[k]) for k in self.NAMES}
+        self.sets = [{k: torch.empty_like(hp.d[k]) for k in self.NAMES} for _ in range(2 if prefetch else 1)]
+        self.static = self.sets[0]
         self.copy_stream = torch.cuda.Stream(device=hp.dev)
         self.side_streams = [torch.cuda.Stream(device=hp.dev), torch.cuda.Stream(device=hp.dev)]
-        self.graph = None
+        self.graphs = None
+        self.results = None
         self.expect = None
         self.mode = "eager"
+        self.turn = 0
+        if prefetch:                                   # the first step's inputs: filled before anything is timed
+            for k in self.NAMES:
+                self.sets[0][k].copy_(hp.host[k], non_blocking=True)
+            torch.cuda.synchronize(hp.dev)
         if use_graph:
             try:
                 side = torch.cuda.Stream(device=hp.dev)
                 side.wait_stream(torch.cuda.current_stream(hp.dev))
                 with torch.cuda.stream(side):
-                    for _ in range(3):
-                        eager = self._whole_step()
+                    for i in range(4):
+                        eager = self._whole_step(i & 1)
                 torch.cuda.current_stream(hp.dev).wait_stream(side)
                 torch.cuda.synchronize(hp.dev)
-                # what the eager, un-captured run of the same code produced: the replayed graph must reproduce it
+                # what the eager, un-captured run of the same code produced: the replayed graphs must reproduce it
                 self.expect = (eager[0].detach().cpu().clone(), [g.detach().abs().sum().item() for g in eager[1]])
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    self.result = self._whole_step()
-                self.graph, self.mode = g, "cuda_graph"
+                graphs, results = [], []
+                for cur in range(len(self.sets)):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        results.append(self._whole_step(cur))
+                    graphs.append(g)
+                self.graphs, self.results, self.mode = graphs, results, "cuda_graph"
+                self.turn = 0
             except Exception as exc:
                 print(f"bench.py: e2e graph capture failed ({type(exc).__name__}: {exc}); running it eagerly", file=sys.stderr)
-                self.graph = None
+                self.graphs = None
 
-    def _whole_step(self):
+    @property
+    def graph(self):
+        return self.graphs
+
+    @graph.setter
+    def graph(self, value):
+        self.graphs = value
+
+    def _whole_step(self, cur: int = 0):
         hp = self.hp
         main = torch.cuda.current_stream(hp.dev)
         self.copy_stream.wait_stream(main)
         arrived = {}
-        with torch.cuda.stream(self.copy_stream):
-            for k in self.NAMES:
-                self.static[k].copy_(hp.host[k], non_blocking=True)
-                arrived[k] = torch.cuda.Event()
-                arrived[k].record(self.copy_stream)
-        losses, grads = self._device_part(lambda stream, *names: [stream.wait_event(arrived[k]) for k in names])
+        if self.prefetch:
+            # compute on set `cur` (complete: the previous step joined its copy stream); fill the other set meanwhile
+            self.static = self.sets[cur]
+            with torch.cuda.stream(self.copy_stream):
+                for k in self.NAMES:
+                    self.sets[1 - cur][k].copy_(hp.host[k], non_blocking=True)
+            need = lambda stream, *names: None
+        else:
+            self.static = self.sets[0]
+            with torch.cuda.stream(self.copy_stream):
+                for k in self.NAMES:
+                    self.static[k].copy_(hp.host[k], non_blocking=True)
+                    arrived[k] = torch.cuda.Event()
+                    arrived[k].record(self.copy_stream)
+            need = lambda stream, *names: [stream.wait_event(arrived[k]) for k in names]
+        losses, grads = self._device_part(need)
         main.wait_stream(self.copy_stream)
         for side in self.side_streams:
             main.wait_stream(side)
@@ -336,19 +369,23 @@ class E2EPath:
         return terms["losses_raw"].detach(), grads
 
     def step(self):
-        if self.graph is not None:
-            self.graph.replay()
-            return self.result[0]
-        return self._whole_step()[0]
+        cur = self.turn
+        self.turn = (cur + 1) % len(self.sets)
+        if self.graphs is not None:
+            self.graphs[cur].replay()
+            self.last = self.results[cur]
+            return self.last[0]
+        self.last = self._whole_step(cur)
+        return self.last[0]
 
     def verify(self):
         """After the timed region: the losses the last replay left in the pinned host buffer, and the gradients it left
         on the device, against the eager run of the same code (streams, copies and all) before the capture."""
-        if self.graph is None or self.expect is None:
+        if self.graphs is None or self.expect is None:
             return None
         torch.cuda.synchronize(self.hp.dev)
         ok = bool(torch.allclose(self.out_host, self.expect[0], rtol=1e-6, atol=0))
-        for g, want in zip(self.result[1], self.expect[1]):
+        for g, want in zip(self.last[1], self.expect[1]):
             ok = ok and abs(g.detach().abs().sum().item() - want) <= 1e-5 * abs(want)
         return ok
 
@@ -464,6 +501,45 @@ def cpu_reference_sample(n_sample: int, seed: int, repeats: int):
         one()
         best = min(best, time.perf_counter() - t0)
     return best, n_sample * (VIEW1[0] // 8) * (VIEW1[1] // 8)
+
+
+def cpu_config0_step(seed: int = 1234):
+    """BASELINE.json configs[0]: ONE whole contrast_train.py step on the host cores — random-init ResNet-38, batch 2 @448x448,
+    view 2 = 128x128, forward of both views, the whole loss body (contrast_train.py:129-395 as restated by the oracle) and
+    backward to the parameters.  The network is the drop-in's own (same modules and parameter names as the reference's) with
+    its head evaluated by the oracle's ATen functions, because the wsegk operators have no CPU path.  Returns seconds."""
+    from oracle import reference_fn as R
+    from wseg_b200 import synth
+    from wseg_b200.network import resnet38_contrast
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(seed)
+    net = resnet38_contrast.Net()
+    net.train()
+    g = synth.gen(seed)
+    img1 = torch.randn(2, 3, 448, 448, generator=g)
+    img2 = F.interpolate(img1, size=(128, 128), mode="bilinear", align_corners=True)     # contrast_train.py:131-134
+    lab20 = synth.labels(2, seed + 1)
+
+    def forward(x):                                                                       # resnet38_contrast.py:31-61 on CPU
+        H, W = x.shape[-2:]
+        d = net.forward_as_dict(x)
+        fea = net.dropout7(d["conv6"])
+        f_proj = F.relu(net.fc_proj(fea))
+        cam = net.fc8(fea)
+        h, w = cam.shape[-2:]
+        with torch.no_grad():
+            camn = R.cam_d_norm(cam.detach())
+        f = torch.cat([F.interpolate(x, (h, w), mode="bilinear", align_corners=True),
+                       F.relu(net.f8_3(d["conv4"].detach())), F.relu(net.f8_4(d["conv5"].detach()))], dim=1)
+        rv_down = R.pcm(camn, net.f9(f))
+        return (F.interpolate(cam, (H, W), mode="bilinear", align_corners=True),
+                F.interpolate(rv_down, (H, W), mode="bilinear", align_corners=True), f_proj, rv_down)
+
+    t0 = time.perf_counter()
+    out1, out2 = forward(img1), forward(img2)
+    losses = R.contrast_step_loss(*out1, *out2, lab20, BG_THRESHOLD, VIEW2, sampler=R.ReferenceSampler(seed))
+    losses["loss"].backward()
+    return time.perf_counter() - t0
 
 
 def config_dict(n_gpus):
@@ -606,6 +682,11 @@ def run_reference(args):
                              "sample": f"oracle/reference_fn.py (restated reference, ATen fp32 on {cores} host threads), "
                                        f"{n_sample} images (the GPU arm's per-GPU batch) per step", "same_config": True},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if args.config0:
+        secs = cpu_config0_step()
+        line["configs[0]"] = {"workload": "one whole contrast_train.py step on CPU: random-init ResNet-38, batch 2 @448x448 + 128x128 view, "
+                                          "forward, loss body, backward", "seconds_per_step": secs, "cores": torch.get_num_threads(),
+                              "mpix_per_s_of_stride8_features": 2 * 56 * 56 / secs / 1e6, "kind": "port (oracle head + drop-in backbone)"}
     print(json.dumps(line), flush=True)
 
 
@@ -680,6 +761,14 @@ def run_ours(args):
     e2e_ok = e2e.verify()
     if e2e_ok is False:
         raise RuntimeError("bench.py: the replayed end-to-end graph does not reproduce the eager run of the same step")
+    # the round-1 arrangement for comparison: every step waits for its OWN copies (operator by operator)
+    e2e_np = E2EPath(hp, use_graph=not args.no_graph, prefetch=False)
+    np_ms, _ = time_steps(e2e_np.step, args.steps, args.warmup, dev, flush, barrier)
+    tn = torch.tensor([np_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tn, op=dist.ReduceOp.MAX)
+    np_ok = e2e_np.verify()
+    e2e_np.graph = None
     # the same end-to-end step with the lazy full-resolution maps of the extended API (Net.forward_small +
     # ops.fullres_norm_up; same values, the four N*21*H*W tensors never exist) — reported beside the drop-in number
     e2e_lazy = E2EPath(hp, use_graph=not args.no_graph, lazy=True)
@@ -701,7 +790,10 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e.h2d_bytes,
                     "d2h_bytes_per_step": e2e.d2h_bytes, "ms_per_step": float(t.item()) / args.steps, "launch": e2e.mode,
                     "replay_equals_eager": e2e_ok,
-                    "api": "pinned host inputs (cam logits, f, f_proj, labels; both views) -> ops.pcm_from_logits (K1a + K2) / ops.bilinear_resize x8 / loss.contrast_terms / ops.fullres_norm through autograd, backward, losses -> host; copies on their own stream, every operator waits only for the tensors it reads"},
+                    "unpipelined": {"ms_per_step": float(tn.item()) / args.steps, "replay_equals_eager": np_ok,
+                                    "note": "the same step waiting for its own copies (round 1's arrangement)"},
+                    "input_pipeline": "double-buffered: the next step's inputs are copied while this step computes (one 37 MB H2D copy and one D2H read inside every timed step)",
+                    "api": "pinned host inputs (cam logits, f, f_proj, labels; both views) -> ops.pcm_from_logits (K1a + K2) / ops.bilinear_resize x8 / loss.contrast_terms / ops.fullres_norm through autograd, backward, losses -> host; copies on their own stream"},
             "e2e_lazy": {"value": total_pix / (float(tl.item()) / args.steps * 1e-3) / 1e6, "unit": UNIT,
                          "ms_per_step": float(tl.item()) / args.steps, "h2d_bytes_per_step": e2e_lazy.h2d_bytes,
                          "d2h_bytes_per_step": e2e_lazy.d2h_bytes, "launch": e2e_lazy.mode,
@@ -770,6 +862,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the configs[3] line")
+    ap.add_argument("--config0", action="store_true", help="--impl reference: also time ONE whole configs[0] step on the CPU")
     ap.add_argument("--no-graph", action="store_true", help="time the resident step eagerly instead of as a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -746,6 +746,13 @@ def test_seam_net_and_batched_msf_inference(cuda_dev):
         label20[[2, 7]] = 1
         orig = (80, 100)
         norm_cam, cam_dict = infer.msf_cam(a, scales, label20, orig)
+        serial, _ = infer.msf_cam(a, scales, label20, orig, concurrent=False)
+        assert torch.equal(norm_cam, serial)                    # one stream per scale: same arithmetic, same order of the sum
+        # the SEAM net's outputs carry no graph even in train mode (its tail runs under no_grad, resnet38_SEAM.py:36-52)
+        b.train()
+        cam_t, rv_t = b(x)
+        b.eval()
+        assert not cam_t.requires_grad and not rv_t.requires_grad
         # the script's loop: one forward per (scale, flip), numpy-style accumulation
         total = torch.zeros(20, *orig, device=cuda_dev)
         for img in scales:
@@ -875,3 +882,79 @@ def test_concurrent_host_threads(cuda_dev):
     for t in range(2):
         for x, y in zip(serial[t], got[t]):
             assert torch.equal(x, y)
+
+
+# ------------------------------------------------------------------------------------------------ memory-safety evidence
+# compute-sanitizer is closed on this GPU pool (profiles/r02_safety.txt), so the two properties it would have checked are
+# tested directly: no write outside the caller's buffers (guard zones), no data race that shows as run-to-run differences.
+@pytest.mark.parametrize("n,h,w", [(1, 16, 16), (2, 20, 13), (3, 9, 5), (2, 56, 56), (1, 75, 61)])
+def test_pcm_writes_stay_inside_callers_buffers(cuda_dev, n, h, w):
+    """Raw C-ABI calls of the PCM forward (precise mode, fix-up included) and backward with every output and the
+    workspace carved out of ONE arena between guard zones of a known pattern: after the calls every guard byte is intact
+    (the tcgen05 / bulk-copy kernels take raw addresses; an out-of-range tile, partial slot or mask row would land here)."""
+    import ctypes
+    from wseg_b200 import _lib
+    lib = _lib.lib()
+    k, c = 192, 21
+    d = synth.pcm_inputs(n, h, w, seed=5)
+    f, g = d["f"].to(cuda_dev).contiguous(), d["grad_out"].to(cuda_dev).contiguous()
+    camn = ops.cam_norm(d["cam"].to(cuda_dev)).contiguous()
+    ws_bytes = _lib.workspace_bytes(_lib.OP_PCM, N=n, C=c, K=k, h=h, w=w)
+    guard = 1 << 16
+    sizes = [n * c * h * w * 4, n * k * h * w * 4, ws_bytes]                 # cam_rv, grad_f, workspace
+    offs, total = [], guard
+    for sz in sizes:
+        offs.append(total)
+        total += (sz + 1023) // 1024 * 1024 + guard
+    arena = torch.full((total + 1024,), 0xA5, dtype=torch.uint8, device=cuda_dev)
+    base = (arena.data_ptr() + 1023) // 1024 * 1024
+    ptr = lambda i: ctypes.c_void_p(base + offs[i])
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    stream = ctypes.c_void_p(torch.cuda.current_stream(cuda_dev).cuda_stream)
+    assert lib.wsegk_pcm_fwd(P(f), P(camn), ptr(0), n, c, k, h, w, ptr(2), ctypes.c_size_t(ws_bytes), stream) == 0, _lib.last_error()
+    assert lib.wsegk_pcm_bwd(P(f), P(camn), ptr(0), P(g), ptr(1), n, c, k, h, w, ptr(2), ctypes.c_size_t(ws_bytes), stream) == 0, _lib.last_error()
+    torch.cuda.synchronize()
+    shift = base - arena.data_ptr()
+    keep = torch.ones(total, dtype=torch.bool, device=cuda_dev)
+    for o, sz in zip(offs, sizes):
+        keep[o:o + sz] = False                                               # the buffers themselves (the workspace's tail padding stays guarded)
+    body = arena[shift:shift + total]
+    assert bool((body[keep] == 0xA5).all()), "a PCM kernel wrote outside the caller's buffers"
+    # and the results are the ones the wrapper produces
+    out, ws = ops.pcm_forward(camn, f)
+    got = body[offs[0]:offs[0] + sizes[0]].view(torch.float32).reshape(n, c, h, w)
+    assert torch.equal(got, out)
+    grad = ops.pcm_backward(f, camn, out, g, ws)
+    assert torch.equal(body[offs[1]:offs[1] + sizes[1]].view(torch.float32).reshape(n, k, h, w), grad)
+
+
+def test_pcm_bitwise_reproducible(cuda_dev):
+    """The hand-rolled 2-CTA mbarrier / TMEM protocols hand tiles between five kinds of warps; a missing wait shows as
+    run-to-run differences.  Ten forward + backward passes at the headline shape, on two different CTA-pair counts (different
+    schedules): outputs, sign masks and gradients are bit-identical across the runs of a configuration, and the forward
+    result and the masks do not depend on the schedule at all."""
+    n, h, w, k, c = 8, 56, 56, 192, 21
+    d = synth.pcm_inputs(n, h, w, seed=17)
+    f, g = d["f"].to(cuda_dev), d["grad_out"].to(cuda_dev)
+    camn = ops.cam_norm(d["cam"].to(cuda_dev))
+    lay = ops.pcm_layout(n, c, k, h, w)
+    sl = slice(lay["mask"], lay["mask"] + n * lay["NS"] * lay["HWpj"] * 16)
+    first = {}
+    try:
+        for pairs in ((0, 0), (72, 37)):
+            ops.set_pcm_pairs(*pairs)
+            for it in range(5):
+                out, ws = ops.pcm_forward(camn, f)
+                grad = ops.pcm_backward(f, camn, out, g, ws)
+                lay2 = ops.pcm_layout(n, c, k, h, w)
+                m = ws[lay2["mask"]:lay2["mask"] + n * lay2["NS"] * lay2["HWpj"] * 16].clone()
+                if pairs not in first:
+                    first[pairs] = (out.clone(), m, grad.clone())
+                else:
+                    for a, b in zip(first[pairs], (out, m, grad)):
+                        assert torch.equal(a, b), (pairs, it)
+    finally:
+        ops.set_pcm_pairs(0, 0)
+    assert torch.equal(first[(0, 0)][1], first[(72, 37)][1])                 # the sign masks do not depend on the schedule
+    assert rel_max(first[(0, 0)][0], first[(72, 37)][0]) <= 2e-5              # fp32 partial sums are added in another order
+    assert rel_max(first[(0, 0)][2], first[(72, 37)][2]) <= 1e-4
