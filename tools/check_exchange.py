@@ -34,7 +34,7 @@ for it in range(6):                                   # several steps: exercises
 flag = torch.tensor([1 if ok else 0], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
-    print("EXCHANGE PARITY", "OK" if int(flag) == 1 else "FAILED", f"(world {world}, symmetric path active: {not ops._SYMM_FAILED})", flush=True)
+    print("EXCHANGE PARITY", "OK" if int(flag) == 1 else "FAILED", f"(world {world}, symmetric path active: {any(v is not None for v in ops._SYMM_MODE.values())})", flush=True)
 torch.cuda.synchronize()
 dist.barrier()
 os._exit(0 if int(flag) == 1 else 1)
