@@ -1,6 +1,7 @@
 // wsegk C ABI: version, error text, device gate, workspace sizing.
 #include <algorithm>
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -88,22 +89,39 @@ static int pick_wb(int HW) {
 #ifndef WSEGK_PCM_PAIRS_BWD
 #define WSEGK_PCM_PAIRS_BWD 52
 #endif
-static thread_local int g_pcm_pairs[2] = {WSEGK_PCM_PAIRS_FWD, WSEGK_PCM_PAIRS_BWD};
+// WSEGK_PCM_PAIRS_FWD / _BWD in the environment override the built-in defaults (A/B runs of the whole step)
+static int default_pairs(int which) {
+    static const int v[2] = {[] { const char* e = getenv("WSEGK_PCM_PAIRS_FWD"); const int x = e ? atoi(e) : 0;
+                                  return x >= 1 && x <= 74 ? x : WSEGK_PCM_PAIRS_FWD; }(),
+                             [] { const char* e = getenv("WSEGK_PCM_PAIRS_BWD"); const int x = e ? atoi(e) : 0;
+                                  return x >= 1 && x <= 74 ? x : WSEGK_PCM_PAIRS_BWD; }()};
+    return v[which];
+}
+static thread_local int g_pcm_pairs[2] = {default_pairs(0), default_pairs(1)};
 
 extern "C" int wsegk_pcm_set_pairs(int fwd_pairs, int bwd_pairs) {
     if (fwd_pairs < 0 || fwd_pairs > 74 || bwd_pairs < 0 || bwd_pairs > 74) {
         set_error("pcm_set_pairs: need 0 (default) .. 74 CTA pairs, got %d / %d", fwd_pairs, bwd_pairs);
         return WSEGK_ERR_BAD_SHAPE;
     }
-    g_pcm_pairs[0] = fwd_pairs ? fwd_pairs : WSEGK_PCM_PAIRS_FWD;
-    g_pcm_pairs[1] = bwd_pairs ? bwd_pairs : WSEGK_PCM_PAIRS_BWD;
+    g_pcm_pairs[0] = fwd_pairs ? fwd_pairs : default_pairs(0);
+    g_pcm_pairs[1] = bwd_pairs ? bwd_pairs : default_pairs(1);
     return WSEGK_OK;
 }
 
-static int pick_clusters(long long T, long long slots) {
-    long long g = T / 2;
+// U units of NS stages on at most `slots` CTA pairs.  If a pair count in [3/4 slots, slots] divides U, the largest such is
+// taken: every unit is then swept by ONE pair — no stream-K tail, no partial slots, and the forward needs no finalize pass
+// (104 units of the headline shape: 52 pairs instead of 64; the kernel alone 51 -> 57 us, the finalize kernel's 10 us and
+// its launch leave the chain, and 24 more SMs stay free for the step's other kernels).
+static int pick_clusters(long long U, long long NS, long long slots) {
+    long long g = U * NS / 2;
     if (g > slots) g = slots;
     if (g < 1) g = 1;
+#ifndef WSEGK_PCM_NO_DIVISOR
+    if (g == slots && U > g)
+        for (long long d = g; 4 * d >= 3 * g; --d)
+            if (U % d == 0) return static_cast<int>(d);
+#endif
     return static_cast<int>(g);
 }
 static int max_unit_segments(int units, int NS, int G) {
@@ -123,9 +141,11 @@ PcmPlan make_pcm_plan(void* ws, int N, int C, int K, int h, int w, int precise) 
     p.HWpi = p.NS * 2 * p.wb;
     // forward and backward main kernels may run on different numbers of CTA pairs (round 2: with the step re-ordered the
     // optimum moved down — what the other chains gain from the SMs a PCM kernel leaves free outweighs what the PCM loses)
-    p.G = pick_clusters(static_cast<long long>(N) * p.PJ * p.NS, g_pcm_pairs[0]);
-    p.Gb = pick_clusters(static_cast<long long>(N) * p.PJ * p.NS, g_pcm_pairs[1]);
-    p.nsplit = std::max(max_unit_segments(N * p.PJ, p.NS, p.G), max_unit_segments(N * p.PJ, p.NS, p.Gb));
+    p.G = pick_clusters(static_cast<long long>(N) * p.PJ, p.NS, g_pcm_pairs[0]);
+    p.Gb = pick_clusters(static_cast<long long>(N) * p.PJ, p.NS, g_pcm_pairs[1]);
+    const int seg_f = max_unit_segments(N * p.PJ, p.NS, p.G);
+    p.fwd_shared_units = seg_f > 1;
+    p.nsplit = std::max(seg_f, max_unit_segments(N * p.PJ, p.NS, p.Gb));
     p.precise = precise ? 1 : 0;
     p.Ku = precise ? 3 * kAugK : kAugK;
     p.a_tile_bytes = static_cast<size_t>(kTile) * K * 2;

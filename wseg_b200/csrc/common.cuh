@@ -103,6 +103,8 @@ struct PcmPlan {
     float* dfhat;                          // [N][nsplit][K][HWpj] fp32 partial gradient w.r.t. normalised features
     float* bound;                          // [0] upper bound of |T|, [kBoundLo2] max_p |fh_p - fp16(fh_p)|^2 (float bits, atomicMax)
     float* peak;                           // [N][C] per-plane maxima of relu(cam) + 1e-5 (pcm_fwd_logits: fused K1a)
+    float* out;                            // forward: the caller's cam_rv [N][C][HW] (not part of the workspace)
+    int fwd_shared_units;                  // forward schedule: some unit is swept by more than one CTA pair (finalize kernel needed)
     int Ku;                                // 48 (fast) or 144 (precise: [hi|hi|lo] x [hi|lo|hi])
     size_t bytes;
 };

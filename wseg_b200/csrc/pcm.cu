@@ -229,15 +229,44 @@ constexpr int kFwdWarpProdF = 8, kFwdWarpS = 9, kFwdWarpProdC = 10, kFwdWarpPV =
 constexpr int kFStages = 4;
 constexpr int kCamStages = 4;
 constexpr uint32_t kTmemCols = 512;
-constexpr int kSBuf = 3;            // forward: S / P buffers of 128 TMEM columns each (the S products run up to three stages ahead)
-constexpr uint32_t kColO = 128 * kSBuf;   // forward: 64 fp32 columns [num_hi | colsum | num_lo]
+// forward: S / P buffers in TMEM.  The hand-off chain S(i) -> convert -> "P ready" arrive -> P V(i) -> commit -> S(i + SB) takes
+// ~4200 clk (trace r2/r3: the remote arrive alone ~1400 behind the warp's mask stores) against ~1020 clk of tensor-pipe work
+// per stage, so the ring needs FOUR buffers to keep the pipe fed; four fit beside the 64 accumulator columns when a buffer
+// is exactly its 2*WB columns wide (4 x 112 + 64 = 512 for 56-row tiles, 4 x 96 + 64 for 48), three of 128 otherwise.
+constexpr int kSBufMax = 4;
+// forward TMEM warps: true = the two warps of a lane quarter take ALTERNATE STAGES (each converts all 2*WB columns of its
+// stage), false = both work on every stage, splitting its columns (round 2).  A stage costs a TMEM warp ~1300 clk of mostly
+// latency (barrier poll, tcgen05.ld, the dependent convert chain, tcgen05.st + wait, the arrive) against ~1020 clk of
+// tensor-pipe work, and with all eight warps on the same stage those latencies are serial; with two stages in flight per
+// sub-partition they overlap.
+#ifdef WSEGK_FWD_NOPP
+constexpr bool kFwdPingPong = false;
+#else
+constexpr bool kFwdPingPong = true;
+#endif
+#ifdef WSEGK_FWD_A1
+constexpr int kABuf = 1;            // ablation: one A-side tile buffer
+#else
+constexpr int kABuf = 2;            // A-side (j) tile buffers: segment k uses slot k % 2
+#endif
+template <int WB>
+struct FwdTmem {
+#ifdef WSEGK_FWD_SBUF3
+    static constexpr int SB = 3;
+#else
+    static constexpr int SB = (2 * WB <= 112) ? 4 : 3;
+#endif
+    static constexpr uint32_t STRIDE = SB == 4 ? 2 * WB : 128;     // TMEM columns between consecutive S / P buffers
+    static constexpr uint32_t COL_O = SB * STRIDE;                  // 64 fp32 columns [num_hi | colsum | num_lo]
+    static_assert(COL_O + 64 <= 512, "TMEM columns");
+};
 constexpr uint32_t kColG = 256;     // backward: K (<= 192) fp32 columns dFh accumulator
 constexpr int kSplitCol = 64;       // S columns [0,64) belong to the first TMEM warp of a quarter, [64, NCOL) to the second
 
 struct FwdBars {
     // full_* / fj of the LEADER also count one arrival relayed from the peer CTA ("my copy of this stage landed too")
-    uint64_t fj, a_free, full_f[kFStages], empty_f[kFStages], full_c[kCamStages], empty_c[kCamStages], s_full[kSBuf],
-        p_full[kSBuf], o_full;
+    uint64_t fj[2], a_free[2], full_f[kFStages], empty_f[kFStages], full_c[kCamStages], empty_c[kCamStages], s_full[kSBufMax],
+        p_full[kSBufMax], o_full, o_free;
     uint32_t tmem_base;
 };
 
@@ -341,6 +370,54 @@ __device__ __forceinline__ uint32_t valid_bits(int nvalid) {
     return even | (odd << 16);
 }
 
+// Segment epilogue of the forward kernel, one TMEM warp's share (rows 32 q .. of the CTA's tile, column half hf).
+//   out[n,c,j] = (hi[c] + lo[c]) / (colsum + 1e-5)                     (network/resnet38_contrast.py:72-73)
+// A unit swept by ONE CTA pair (every row unit, and every unit when the pair count divides the unit count: nseg == 1) goes
+// straight from TMEM to `out` — no partials, no finalize pass (round 1/2 ran a finalize kernel over all units: 10 us + a
+// launch on the critical path of both views).  A unit shared by several pairs leaves column-major partials
+// ([n][slot][64][HWpj]: for a fixed column the 32 lanes of a warp write one 128-byte line) for pcm_fwd_finalize_kernel.
+// The quotient is one reciprocal and a multiply per class in both places.
+// NOT inlined, few arguments, few registers: this kernel sits at the 168-register limit and anything that perturbs the
+// allocation of the stage loop costs 15-60 % (measured round 3: inlined epilogue 1370 -> 1600 clk per stage; an in-kernel
+// "last segment to arrive adds the slots" reduction made the loop spill: 50 -> 110 us).
+__device__ __noinline__ void fwd_epilogue(uint32_t o_addr, float* __restrict__ orow, float* __restrict__ dsum_row,
+                                          float* __restrict__ part_row, int C, int HW, int HWpj, bool row_live, int hf,
+                                          bool whole) {
+    if (whole) {
+        const int dch = C >> 4;                             // 16-column chunk holding the column-sum column C
+        uint32_t r[16], l[16];
+        float d = 0.f;
+        tmem_ld16(o_addr + dch * 16, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int v = 0; v < 16; ++v) d = (dch * 16 + v == C) ? __uint_as_float(r[v]) : d;
+        d += 1e-5f;
+        if (hf == 0) *dsum_row = d;
+        if (hf * 16 < C) {                                  // this warp's classes: [16 hf, 16 hf + 16)
+            tmem_ld16(o_addr + hf * 16, r);
+            tmem_ld16(o_addr + kCamRows + hf * 16, l);
+            tmem_ld_wait();
+            const float rd = __frcp_rn(d);
+            if (row_live) {
+#pragma unroll
+                for (int v = 0; v < 16; ++v)
+                    if (hf * 16 + v < C)
+                        orow[static_cast<size_t>(hf * 16 + v) * HW] = (__uint_as_float(r[v]) + __uint_as_float(l[v])) * rd;
+            }
+        }
+        return;
+    }
+    float* dst = part_row + static_cast<size_t>(hf * 32) * HWpj;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        uint32_t r[16];
+        tmem_ld16(o_addr + hf * 32 + c * 16, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int v = 0; v < 16; ++v) dst[static_cast<size_t>(c * 16 + v) * HWpj] = __uint_as_float(r[v]);
+    }
+}
+
 // ---- stream-K schedule shared by the forward and backward main kernels ---------------------------------------------
 // Unit u = n*PJ + jp (one image's pair of 128-row j tiles) owns NS stages; the T = units*NS stages are cut into G equal
 // contiguous ranges, one per CTA pair, so every pair does the same number of stages whatever N, PJ and NS are (no wave
@@ -350,7 +427,7 @@ template <int WB, int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFwdThreads, 1)
 pcm_fwd_kernel(const uint8_t* __restrict__ fa, const uint8_t* __restrict__ fb, const uint8_t* __restrict__ camb,
                float* __restrict__ part, uint2* __restrict__ mask, uint2* __restrict__ nzmask,
-               const float* __restrict__ lo2max, int K, int HW, int PJ, int NS, int n_units, int nslot,
+               const float* __restrict__ lo2max, float* __restrict__ out, float* __restrict__ dsum, int C, int K, int HW, int PJ, int NS, int n_units, int nslot,
                long long* __restrict__ trace) {
     constexpr int FS = kFStages;
     // optional timeline of CTA 0: trace[role*256 + t*4 + k] = clock64()   (wsegk_debug_pcm_trace)
@@ -367,12 +444,15 @@ pcm_fwd_kernel(const uint8_t* __restrict__ fa, const uint8_t* __restrict__ fb, c
         if (tr) trace[1024 + 2 * gridDim.x] = clock64();
     }
     constexpr int NCOL = 2 * WB;
+    constexpr int kSBuf = FwdTmem<WB>::SB;
+    constexpr uint32_t kSStride = FwdTmem<WB>::STRIDE, kColO = FwdTmem<WB>::COL_O;
     constexpr uint32_t kCamBytes = NCOL * 64;                  // (NCOL/8) groups x 32 rows x 16 B per CTA
     using Bars = FwdBars;
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t a_bytes = kTile * K * 2, b_bytes = WB * K * 2;
-    uint8_t* s_fj = smem;
-    uint8_t* s_f = smem + a_bytes;                             // FS x Fi tile
+    uint8_t* s_fj = smem;                                      // 2 x Fj tile: segment k uses slot k & 1, so the next segment's
+                                                               // A-side tile is loaded while this one's products still run
+    uint8_t* s_f = smem + kABuf * a_bytes;                         // FS x Fi tile
     uint8_t* s_c = s_f + FS * b_bytes;                         // kCamStages x cam block
     Bars* bars = reinterpret_cast<Bars*>(s_c + kCamStages * kCamBytes);
 
@@ -386,8 +466,10 @@ pcm_fwd_kernel(const uint8_t* __restrict__ fa, const uint8_t* __restrict__ fb, c
 
     if (threadIdx.x == 0) {
         const uint32_t relay = rank == 0 ? 1u : 0u;
-        mbar_init(smem_u32(&bars->fj), 1 + relay);
-        mbar_init(smem_u32(&bars->a_free), 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(smem_u32(&bars->fj[s]), 1 + relay);
+            mbar_init(smem_u32(&bars->a_free[s]), 1);
+        }
         for (int s = 0; s < FS; ++s) {
             mbar_init(smem_u32(&bars->full_f[s]), 1 + relay);
             mbar_init(smem_u32(&bars->empty_f[s]), 1);
@@ -398,9 +480,10 @@ pcm_fwd_kernel(const uint8_t* __restrict__ fa, const uint8_t* __restrict__ fb, c
         }
         for (int b = 0; b < kSBuf; ++b) {
             mbar_init(smem_u32(&bars->s_full[b]), 1);
-            mbar_init(smem_u32(&bars->p_full[b]), 16);         // 8 warps x 2 CTAs
+            mbar_init(smem_u32(&bars->p_full[b]), kFwdPingPong ? 8 : 16);   // TMEM warps converting a stage x 2 CTAs
         }
         mbar_init(smem_u32(&bars->o_full), 1);
+        mbar_init(smem_u32(&bars->o_free), 16);                // 8 TMEM warps x 2 CTAs have drained the accumulator
         mbar_fence_init();
     }
     if (warp == kFwdWarpS) {
@@ -419,11 +502,12 @@ pcm_fwd_kernel(const uint8_t* __restrict__ fa, const uint8_t* __restrict__ fb, c
             StageCursor si = c0;
             for (int i = 0; i < cnt; ++i, si.next()) {
                 if (si.first()) {
-                    // a new segment: its A-side tile replaces the previous one once every S product of that segment is done
-                    if (si.k > 0) mbar_wait(smem_u32(&bars->a_free), (si.k - 1) & 1);
+                    // a new segment: its A-side tile goes to slot k & 1, free once every S product of segment k - 2 is done
+                    const int as = si.k % kABuf;
+                    if (si.k >= kABuf) mbar_wait(smem_u32(&bars->a_free[as]), ((si.k - kABuf) / kABuf) & 1);
                     const size_t a_tile = static_cast<size_t>(si.n) * 2 * PJ + 2 * si.jp + rank;
-                    mbar_arrive_expect_tx(smem_u32(&bars->fj), a_bytes);
-                    tma_load_1d(smem_u32(s_fj), fa + a_tile * a_bytes, a_bytes, smem_u32(&bars->fj));
+                    mbar_arrive_expect_tx(smem_u32(&bars->fj[as]), a_bytes);
+                    tma_load_1d(smem_u32(s_fj + as * a_bytes), fa + a_tile * a_bytes, a_bytes, smem_u32(&bars->fj[as]));
                 }
                 const size_t bt = static_cast<size_t>(si.n) * 2 * NS + 2 * si.st + rank;
                 const int s = i % FS, u = i / FS;
@@ -453,8 +537,8 @@ pcm_fwd_kernel(const uint8_t* __restrict__ fa, const uint8_t* __restrict__ fb, c
             StageCursor si = c0;
             for (int i = 0; i < cnt; ++i, si.next()) {
                 if (si.first()) {
-                    mbar_wait(smem_u32(&bars->fj), si.k & 1);
-                    mbar_arrive_cluster(mapa_shared(smem_u32(&bars->fj), 0));
+                    mbar_wait(smem_u32(&bars->fj[si.k % kABuf]), (si.k / kABuf) & 1);
+                    mbar_arrive_cluster(mapa_shared(smem_u32(&bars->fj[si.k % kABuf]), 0));
                 }
                 {
                     const int s = i % FS, u = i / FS;
@@ -478,15 +562,19 @@ pcm_fwd_kernel(const uint8_t* __restrict__ fa, const uint8_t* __restrict__ fb, c
                 const uint32_t id_s = umma_idesc_f16(0, 2 * kTile, NCOL, 0, 0);
                 constexpr uint32_t lbo_a = kTile * 16, lbo_b = WB * 16;
                 const int ksteps = K >> 4;
-                const uint64_t da = umma_smem_desc(smem_u32(s_fj), lbo_a, 128);
+                const uint64_t da0 = umma_smem_desc(smem_u32(s_fj), lbo_a, 128);
                 const uint64_t db0 = umma_smem_desc(smem_u32(s_f), lbo_b, 128);
                 StageCursor cs = c0;
                 int b = 0, s = 0, fph = 0;
+                uint64_t da = da0;
                 for (int i = 0; i < cnt; ++i) {
                     const bool seg_first = cs.first(), seg_last = cs.last();
                     const int seg = cs.k;
                     cs.next();
-                    if (seg_first) mbar_wait(smem_u32(&bars->fj), seg & 1);
+                    if (seg_first) {
+                        mbar_wait(smem_u32(&bars->fj[seg % kABuf]), (seg / kABuf) & 1);
+                        da = da0 + static_cast<uint64_t>(((seg % kABuf) * a_bytes) >> 4);
+                    }
                     TRACE(1, i, 0);
                     // the stage's tile has landed (in both CTAs), and buffer b is free: P V(i - 3) has read it — that product's
                     // commit on empty_c (P V(i + 1), the next completion of the same barrier, needs S(i + 1), which this thread
@@ -499,7 +587,7 @@ pcm_fwd_kernel(const uint8_t* __restrict__ fa, const uint8_t* __restrict__ fb, c
                     TRACE(1, i, 1);
                     tc_fence_after();
                     const uint64_t db = db0 + static_cast<uint64_t>((s * b_bytes) >> 4);
-                    const uint32_t d = tmem + b * 128;
+                    const uint32_t d = tmem + b * kSStride;
 #ifndef WSEGK_ABL_NOS
 #pragma unroll
                     for (int ks = 0; ks < kMaxPcmK / 16; ++ks)
@@ -510,7 +598,7 @@ pcm_fwd_kernel(const uint8_t* __restrict__ fa, const uint8_t* __restrict__ fb, c
                     TRACE(0, i, 1);
                     umma2_commit(smem_u32(&bars->s_full[b]));
                     umma2_commit(smem_u32(&bars->empty_f[s]));
-                    if (seg_last) umma2_commit(smem_u32(&bars->a_free));  // the segment's A-side tile may be replaced
+                    if (seg_last) umma2_commit(smem_u32(&bars->a_free[seg % kABuf]));  // the segment's A-side tile may be replaced
                     TRACE(0, i, 2);
                     b = b + 1 == kSBuf ? 0 : b + 1;
                     if (++s == FS) { s = 0; fph ^= 1; }
@@ -533,6 +621,7 @@ pcm_fwd_kernel(const uint8_t* __restrict__ fa, const uint8_t* __restrict__ fb, c
                         mbar_wait(smem_u32(&bars->p_full[b]), bph);
                         TRACE(3, i, 3);
                     }
+                    if (kFwdPingPong && si.first() && si.k > 0) mbar_wait(smem_u32(&bars->o_free), (si.k - 1) & 1);
                     mbar_wait2(smem_u32(&bars->p_full[b]), bph, smem_u32(&bars->full_c[sc]), cph);
                     TRACE(1, i, 3);
                     tc_fence_after();
@@ -546,7 +635,7 @@ pcm_fwd_kernel(const uint8_t* __restrict__ fa, const uint8_t* __restrict__ fb, c
                     for (int ks = 0; ks < NCOL / 16; ++ks) {
                         constexpr int kHalf = kSplitCol / 16;
                         const uint32_t pcol = ks < kHalf ? ks * 8 : kSplitCol + (ks - kHalf) * 8;
-                        umma2_ts(tmem + kColO, tmem + b * 128 + pcol, dc + static_cast<uint64_t>(ks * (2 * lbo_c / 16)),
+                        umma2_ts(tmem + kColO, tmem + b * kSStride + pcol, dc + static_cast<uint64_t>(ks * (2 * lbo_c / 16)),
                                  id_o, ks > 0 ? 1u : acc0);
                     }
 #endif
@@ -559,8 +648,107 @@ pcm_fwd_kernel(const uint8_t* __restrict__ fa, const uint8_t* __restrict__ fb, c
             }
             __syncwarp();
         }
+    } else if (kFwdPingPong && warp < kFwdTmemWarp0 + 8) {
+        // ---------------------------------------------------------------- ReLU / sign / convert warps, alternate stages
+        const int q = warp & 3;                         // TMEM lane quarter this warp may touch
+        const int par = (warp - kFwdTmemWarp0) >> 2;    // stages j = par (mod 2) are mine
+        const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+        const uint32_t p_full0 = mapa_shared(smem_u32(&bars->p_full[0]), 0);
+        const uint32_t o_free0 = mapa_shared(smem_u32(&bars->o_free), 0);
+        uint32_t tau2 = 0;
+        if (MODE == 2) {                                // see the column-split branch below
+            const float tau = sqrtf(__ldg(lo2max)) + 1e-6f;
+            const uint32_t th = __half_as_ushort(__float2half_ru(tau));
+            tau2 = th | (th << 16);
+        }
+        constexpr int NC1 = NCOL - kSplitCol;           // columns behind the first 64: 64, 48 or 32
+        StageCursor si = c0;
+        uint32_t r0[32], r1[32];
+        auto fetch0 = [&](int j) {                      // wait for S(j) and start loading its first 64 columns
+            const int fb = j % kSBuf;
+            if (q == 0 && lane == 0) TRACE(2, j, 0);
+            mbar_wait(smem_u32(&bars->s_full[fb]), (j / kSBuf) & 1);
+            tc_fence_after();
+            const uint32_t base = tmem + lane_addr + fb * kSStride;
+            tmem_ld32(base, r0);
+            tmem_ld32(base + 32, r1);
+        };
+        if (par < cnt) fetch0(par);
+        for (int j = 0; j < cnt; ++j, si.next()) {
+            const int row = si.jp * 2 * kTile + static_cast<int>(rank) * kTile + q * 32 + lane;
+            if ((j & 1) == par) {
+                const int b = j % kSBuf;
+                const uint32_t base = tmem + lane_addr + b * kSStride;
+                uint32_t sw[4] = {0u, 0u, 0u, 0u}, nw[4] = {0u, 0u, 0u, 0u};
+                uint32_t pk[16];
+                tmem_ld_wait();
+                if (q == 0 && lane == 0) { TRACE(2, j, 1); TRACEP(3, j, 0); }
+                // P = relu(S) as packed fp16 IN PLACE: columns [0,64) -> packed columns [0,32), columns [64, NCOL) -> [64, ..);
+                // every store lands on columns this warp has already loaded, and the loads of the second part are issued as
+                // soon as the registers of the first are free
+                relu_pack_bits<32, MODE>(r0, pk, tau2, sw[0], nw[0]);
+                tmem_st16(base, pk);
+                tmem_ld32(base + kSplitCol, r0);
+                relu_pack_bits<32, MODE>(r1, pk, tau2, sw[1], nw[1]);
+                tmem_st16(base + 16, pk);
+                if (NC1 == 64) tmem_ld32(base + kSplitCol + 32, r1);
+                if (NC1 == 48) tmem_ld16(base + kSplitCol + 32, reinterpret_cast<uint32_t(&)[16]>(r1));
+                tmem_ld_wait();
+                relu_pack_bits<32, MODE>(r0, pk, tau2, sw[2], nw[2]);
+                tmem_st16(base + kSplitCol, pk);
+                if (NC1 == 64) {
+                    relu_pack_bits<32, MODE>(r1, pk, tau2, sw[3], nw[3]);
+                    tmem_st16(base + kSplitCol + 16, pk);
+                } else if (NC1 == 48) {
+                    relu_pack_bits<16, MODE>(r1, pk, tau2, sw[3], nw[3]);
+                    tmem_st8(base + kSplitCol + 16, reinterpret_cast<uint32_t(&)[8]>(pk));
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster_relaxed(p_full0 + static_cast<uint32_t>(b) * 8u);
+                if (q == 0 && lane == 0) { TRACE(2, j, 2); TRACEP(3, j, 1); }
+                if (q == 3 && lane == 0) TRACE(3, j, 2);
+                // my next stage's S is normally complete by now: start loading it before this stage's masks are stored
+                if (j + 2 < cnt) fetch0(j + 2);
+                if (MODE >= 1) {
+                    const size_t mi = static_cast<size_t>(si.n * NS + si.st) * HWpj + row;    // [n][stage][row] x 4 words
+                    reinterpret_cast<uint4*>(mask)[mi] = make_uint4(sw[0], sw[1], sw[2], sw[3]);
+                    if (MODE == 2) {
+                        // padding rows / columns are all-zero vectors: S = 0 there, nothing to re-evaluate
+                        const int vc = HW - si.st * NCOL;                               // valid columns of this stage
+                        if (row >= HW) { nw[0] = 0; nw[1] = 0; nw[2] = 0; nw[3] = 0; }
+                        else if (vc < NCOL) {
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) nw[c] &= valid_bits(vc - 32 * c);
+                        }
+                        reinterpret_cast<uint4*>(nzmask)[mi] = make_uint4(nw[0], nw[1], nw[2], nw[3]);
+                    }
+                }
+            }
+            if (si.last()) {
+                // segment epilogue (fwd_epilogue above), both warps of the quarter: half of the classes / columns each.  The
+                // P V issuer starts the next segment's accumulation only when all 16 warps of the pair have drained this one
+#ifdef WSEGK_FWD_NOFUSE
+                const int nseg = 0;
+#else
+                const int nseg = pcm_unit_segments(sched, si.u);
+#endif
+                const int slot = (nseg != 1 && si.in_tail())
+                                     ? g - pcm_tail_owner(sched, static_cast<long long>(si.u - sched.Rf * sched.G) * NS) : 0;
+                mbar_wait(smem_u32(&bars->o_full), si.k & 1);
+                tc_fence_after();
+                fwd_epilogue(tmem + lane_addr + kColO, out + static_cast<size_t>(si.n) * C * HW + row,
+                             dsum + static_cast<size_t>(si.n) * HWpj + row,
+                             part + (static_cast<size_t>(si.n) * nslot + slot) * kONum * HWpj + row, C, HW, HWpj, row < HW, par,
+                             nseg == 1);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster_relaxed(o_free0);
+            }
+        }
     } else if (warp < kFwdTmemWarp0 + 8) {
-        // ---------------------------------------------------------------- ReLU / sign / convert warps
+        // ---------------------------------------------------------------- ReLU / sign / convert warps, column split
         const int q = warp & 3;                         // TMEM lane quarter this warp may touch
         const int hf = (warp - kFwdTmemWarp0) >> 2;     // column half
         const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
@@ -581,7 +769,7 @@ pcm_fwd_kernel(const uint8_t* __restrict__ fa, const uint8_t* __restrict__ fb, c
         auto fetch = [&](int buf, int phase) {         // wait for S of the stage in `buf` and start loading my columns
             mbar_wait(smem_u32(&bars->s_full[buf]), phase);
             tc_fence_after();
-            const uint32_t base = tmem + lane_addr + buf * 128 + hf * kSplitCol;
+            const uint32_t base = tmem + lane_addr + buf * kSStride + hf * kSplitCol;
             if (hf == 0) load_cols<kSplitCol>(base, r0, r1);
             else load_cols<NCOL - kSplitCol>(base, r0, r1);
         };
@@ -593,7 +781,7 @@ pcm_fwd_kernel(const uint8_t* __restrict__ fa, const uint8_t* __restrict__ fb, c
             if (warp == kFwdTmemWarp0 && lane == 0) TRACE(2, i, 1);
             if (warp == kFwdTmemWarp0 && lane == 0) TRACEP(3, i, 0);
             uint32_t sw[2], nw[2];
-            const uint32_t base = tmem + lane_addr + b * 128 + hf * kSplitCol;
+            const uint32_t base = tmem + lane_addr + b * kSStride + hf * kSplitCol;
 #if defined(WSEGK_ABL_NOALU)
             tmem_st16(base, reinterpret_cast<uint32_t(&)[16]>(r0));
             sw[0] = r0[0]; sw[1] = r1[0]; nw[0] = r0[1]; nw[1] = r1[1];
@@ -612,7 +800,9 @@ pcm_fwd_kernel(const uint8_t* __restrict__ fa, const uint8_t* __restrict__ fb, c
             // before this stage's masks are stored, so the barrier poll (~150 clk) and the TMEM load latency hide behind them
             const int nb = b + 1 == kSBuf ? 0 : b + 1, nph = b + 1 == kSBuf ? bph ^ 1 : bph;
             if (warp == kFwdTmemWarp0 && lane == 0) TRACE(2, i + 1, 0);
-            if (i + 1 < cnt) fetch(nb, nph);
+            // (not across a segment's end: the epilogue is a call, and the 64 prefetched values would have to survive it)
+            const bool seg_end = si.last();
+            if (i + 1 < cnt && !seg_end) fetch(nb, nph);
 #if !defined(WSEGK_ABL_NOMASK) && !defined(WSEGK_ABL_NOMASK_LANE0)
             if (MODE >= 1) {
 #elif defined(WSEGK_ABL_NOMASK_LANE0)
@@ -630,22 +820,23 @@ pcm_fwd_kernel(const uint8_t* __restrict__ fa, const uint8_t* __restrict__ fb, c
                     nzmask[mi] = make_uint2(nw[0], nw[1]);
                 }
             }
-            if (si.last()) {
-                // segment epilogue: accumulator -> partial buffer (this warp: 32 of the 64 columns)
-                const int slot = si.in_tail() ? g - pcm_tail_owner(sched, static_cast<long long>(si.u - sched.Rf * sched.G) * NS) : 0;
+            if (seg_end) {
+                // segment epilogue (fwd_epilogue above): the accumulator becomes `out` directly, or a partial slot
+#ifdef WSEGK_FWD_NOFUSE
+                const int nseg = 0;
+#else
+                const int nseg = pcm_unit_segments(sched, si.u);
+#endif
+                const int slot = (nseg != 1 && si.in_tail())
+                                     ? g - pcm_tail_owner(sched, static_cast<long long>(si.u - sched.Rf * sched.G) * NS) : 0;
                 mbar_wait(smem_u32(&bars->o_full), si.k & 1);
                 tc_fence_after();
-                // [n][slot][64][HWpj]: for a fixed column the 32 lanes of a warp write 32 consecutive rows (one 128-byte line)
-                float* dst = part + ((static_cast<size_t>(si.n) * nslot + slot) * kONum + hf * 32) * HWpj + row;
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    uint32_t r[16];
-                    tmem_ld16(tmem + lane_addr + kColO + hf * 32 + c * 16, r);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int v = 0; v < 16; ++v) dst[static_cast<size_t>(c * 16 + v) * HWpj] = __uint_as_float(r[v]);
-                }
+                fwd_epilogue(tmem + lane_addr + kColO, out + static_cast<size_t>(si.n) * C * HW + row,
+                             dsum + static_cast<size_t>(si.n) * HWpj + row,
+                             part + (static_cast<size_t>(si.n) * nslot + slot) * kONum * HWpj + row, C, HW, HWpj, row < HW, hf,
+                             nseg == 1);
                 tc_fence_before();
+                if (i + 1 < cnt) fetch(nb, nph);
             }
             b = nb;
             bph = nph;
@@ -804,16 +995,19 @@ __global__ void __launch_bounds__(kFixThreads) pcm_sign_fixup_kernel(const float
 }
 
 // out[n,c,j] = (sum_slot hi[c] + lo[c]) / (sum_slot colsum + 1e-5)
+// for the units that were swept by more than one CTA pair (the others were finished by the main kernel's epilogue; `all`:
+// the ablation build, where the main kernel leaves partials for every unit).
 // The partials are column-major ([n][slot][64][HWpj]: hi rows 0..C-1, column sum at row C, lo rows 32..32+C-1), so thread
 // (c, j) reads and writes along j: no transpose.  One CTA = 32 consecutive rows j x 8 class phases.
 __global__ void __launch_bounds__(256) pcm_fwd_finalize_kernel(const float* __restrict__ part,
                                                                float* __restrict__ out,
                                                                float* __restrict__ dsum, int C, int HW,
-                                                               int HWpj, int nslot, int PJ, int NS, int G) {
+                                                               int HWpj, int nslot, int PJ, int NS, int G, int all) {
     const int n = blockIdx.y;
     const int lane = threadIdx.x & 31, ph = threadIdx.x >> 5;
     const int j = blockIdx.x * 32 + lane;                        // HWpj is a multiple of 256
     const int nseg = pcm_unit_segments(pcm_sched(static_cast<int>(gridDim.y) * PJ, NS, G), n * PJ + j / (2 * kTile));
+    if (nseg == 1 && !all) return;                               // uniform over the CTA (32 divides 256)
     const size_t slot_stride = static_cast<size_t>(kONum) * HWpj;
     const float* base = part + static_cast<size_t>(n) * nslot * slot_stride + j;
     float d = 0.f;
@@ -827,9 +1021,10 @@ __global__ void __launch_bounds__(256) pcm_fwd_finalize_kernel(const float* __re
             hi += __ldg(base + sp * slot_stride + static_cast<size_t>(c) * HWpj);
             lo += __ldg(base + sp * slot_stride + static_cast<size_t>(kCamRows + c) * HWpj);
         }
-        out[(static_cast<size_t>(n) * C + c) * HW + j] = (hi + lo) / d;
+        out[(static_cast<size_t>(n) * C + c) * HW + j] = (hi + lo) * __frcp_rn(d);
     }
 }
+
 
 // ------------------------------------------------------------------------------------------------
 // backward
@@ -1206,12 +1401,24 @@ pcm_bwd_kernel(const uint8_t* __restrict__ ua, const uint8_t* __restrict__ vb, c
                 tc_fence_after();
                 float* dst = dfhat + ((static_cast<size_t>(si.n) * nslot + slot) * K) * HWpj + si.jp * 2 * kTile + row_in;
                 const int cgroups = K >> 4, c_begin = hf * ((cgroups + 1) >> 1), c_end = hf ? cgroups : ((cgroups + 1) >> 1);
-                for (int c = c_begin; c < c_end; ++c) {
-                    uint32_t r[16];
-                    tmem_ld16(tmem + lane_addr + kColG + c * 16, r);
-                    tmem_ld_wait();
+                // two 16-column chunks in flight: the next chunk's TMEM load is issued before this chunk's stores (the drain
+                // is latency-bound — trace r3: ~5000 clk per segment with one load -> wait -> 16 stores at a time — and the
+                // G products of the next segment wait for it)
+                uint32_t ra[16], rb[16];
+                auto put = [&](int c, const uint32_t (&r)[16]) {
 #pragma unroll
                     for (int v = 0; v < 16; ++v) dst[static_cast<size_t>(c * 16 + v) * HWpj] = __uint_as_float(r[v]);
+                };
+                if (c_begin < c_end) tmem_ld16(tmem + lane_addr + kColG + c_begin * 16, ra);
+                for (int c = c_begin; c < c_end; c += 2) {
+                    tmem_ld_wait();
+                    if (c + 1 < c_end) tmem_ld16(tmem + lane_addr + kColG + (c + 1) * 16, rb);
+                    put(c, ra);
+                    if (c + 1 < c_end) {
+                        tmem_ld_wait();
+                        if (c + 2 < c_end) tmem_ld16(tmem + lane_addr + kColG + (c + 2) * 16, ra);
+                        put(c + 1, rb);
+                    }
                 }
                 tc_fence_before();
             }
@@ -1374,7 +1581,7 @@ __global__ void __launch_bounds__(256) pcm_bwd_post_vec_kernel(const float* __re
 
 static size_t fwd_smem_bytes(int K, int wb) {
     const size_t a = static_cast<size_t>(kTile) * K * 2, b = static_cast<size_t>(wb) * K * 2;
-    return a + kFStages * b + kCamStages * static_cast<size_t>(2 * wb) * 64 + sizeof(FwdBars) + 64;
+    return kABuf * a + kFStages * b + kCamStages * static_cast<size_t>(2 * wb) * 64 + sizeof(FwdBars) + 64;
 }
 
 static size_t bwd_smem_bytes(int K, int wb, bool split) {
@@ -1456,7 +1663,8 @@ static int launch_fwd(const PcmPlan& pl, int N, wsegk_stream_t stream) {
     pcm_fwd_kernel<WB, MODE><<<dim3(2 * pl.G), kFwdThreads, smem, stream>>>(
         reinterpret_cast<const uint8_t*>(pl.fa), reinterpret_cast<const uint8_t*>(pl.fb),
         reinterpret_cast<const uint8_t*>(pl.camb), pl.part, reinterpret_cast<uint2*>(pl.mask),
-        reinterpret_cast<uint2*>(pl.nzmask), pl.bound + kBoundLo2, pl.K, pl.HW, pl.PJ, pl.NS, N * pl.PJ, pl.nsplit, g_trace);
+        reinterpret_cast<uint2*>(pl.nzmask), pl.bound + kBoundLo2, pl.out, pl.dsum, pl.C, pl.K, pl.HW, pl.PJ,
+        pl.NS, N * pl.PJ, pl.nsplit, g_trace);
     return WSEGK_OK;
 }
 
@@ -1574,11 +1782,20 @@ static int pcm_fwd_impl(const float* f, const float* cam_norm, float* cam_rv, in
         }
     }
     prof_mark(0, stream);
+    pl.out = cam_rv;
     if (int rc = dispatch_fwd(pl, N, mode, stream)) return rc;
     prof_mark(1, stream);
-    pcm_fwd_finalize_kernel<<<dim3(pl.HWpj / 32, N), 256, 0, stream>>>(pl.part, cam_rv, pl.dsum, C, pl.HW, pl.HWpj,
-                                                                         pl.nsplit, pl.PJ, pl.NS, pl.G);
-    count_launches(3);
+#ifdef WSEGK_FWD_NOFUSE
+    const int fin_all = 1;
+#else
+    const int fin_all = 0;
+#endif
+    if (fin_all || pl.fwd_shared_units) {
+        pcm_fwd_finalize_kernel<<<dim3(pl.HWpj / 32, N), 256, 0, stream>>>(pl.part, cam_rv, pl.dsum, C, pl.HW, pl.HWpj,
+                                                                             pl.nsplit, pl.PJ, pl.NS, pl.G, fin_all);
+        count_launches(1);
+    }
+    count_launches(2);
     if (mode == 2 && !defer_fixup)
         if (int rc = launch_fixup(pl, N, stream)) return rc;
     WSEGK_CUDA_OK(cudaGetLastError());

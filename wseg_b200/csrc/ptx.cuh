@@ -127,6 +127,11 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
     }
 }
 
+// named barrier over `threads` threads of the CTA (a multiple of 32): the warps that reach it, not the whole CTA
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t threads) {
+    asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(threads) : "memory");
+}
+
 // ------------------------------------------------------------------ bulk TMA (1-D, no tensor map)
 // global -> shared, completion signalled on an mbarrier via complete_tx::bytes.
 // size must be a multiple of 16 bytes, both addresses 16-byte aligned.
