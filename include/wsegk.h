@@ -246,7 +246,9 @@ int wsegk_contrast_loss_fwd_bwd(const float* x1, const float* x2, const float* p
  * peer's symmetric buffer (wsegk_mine_exchange_bytes; peer_bases[r] = rank r's buffer mapped here, local_base = mine;
  * local_state: 2 zero-initialised uint32 owned by the library) and ranks its own pixels against all of them in the canonical
  * order (value, global pixel = rank*P + p).  Reported intra losses are R x this rank's share: their mean over ranks — what
- * DDP does to the gradients — is the single-process value.  Needs P <= 16384 per rank. */
+ * DDP does to the gradients — is the single-process value.  Up to 16 384 loss pixels per rank the local pixels are ranked
+ * pairwise against the gathered batch; above that every rank runs the multi-CTA select over all R*P gathered pixels (three
+ * threshold keys per class, the same on every rank) and membership is two comparisons per pixel. */
 size_t wsegk_mine_exchange_bytes(int R, int N, int h, int w);
 int wsegk_contrast_loss_fwd_bwd_global(const float* x1, const float* x2, const float* proto1, const float* proto2,
                                        const int32_t* pl1, const int32_t* pl2, const uint32_t* rand_key1,
@@ -295,6 +297,11 @@ int wsegk_debug_pcm_schedule(int N, int h, int w, int g, int* out, int capacity)
  * (multi-CTA radix select, csrc/segselect.cuh) whatever the size, so both paths can be compared on the same inputs.
  * By default K3 switches above 8192 pixels and the mining of K4 above 16384. */
 int wsegk_debug_force_radix(int on);
+/* Test aid, per host thread: which part of wsegk_contrast_loss_fwd_bwd_global the next calls run — bit 0: everything up to
+ * and including the push of this rank's (sim, key, label) to its peers; bit 1: the rest (wait for the peers, mining, gradient).
+ * Default 3.  With 1 then 2 (same arguments, same workspace) ONE process can drive several "ranks" of one GPU on one stream:
+ * all pushes first, then all second halves — no kernel ever spins on a flag that a later launch of the same queue sets. */
+int wsegk_debug_mine_phases(int mask);
 
 /* PCM precision mode used by the entry points without a `flags` argument, per HOST THREAD (default 1):
  *   1 "precise": S from single FP16 products; the entries with |S| below the bound of the operand-rounding error (~0.2 %)

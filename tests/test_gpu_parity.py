@@ -423,6 +423,80 @@ def test_large_plane_paths_equal_small_plane_paths(cuda_dev, n, g, d, rng):
     assert int(out[0][3]["mined1"].sum()) > 0
 
 
+@pytest.mark.parametrize("n_local,g,forced", [(2, 16, False), (2, 16, True), (4, 72, False)])
+def test_global_mining_virtual_ranks(cuda_dev, n_local, g, forced):
+    """GLOBAL hard-pixel mining (the reference mines over the whole batch, contrast_train.py:301-334) with TWO
+    ranks driven from one process: each "rank" gets its half of the batch, its own workspace and exchange buffer (plain
+    device memory standing in for the NVLink-mapped symmetric buffers; the kernels and the flag protocol are the ones
+    tools/check_global_mining.py runs under torchrun on 2 and 8 GPUs) and must mine exactly the pixels the single-process
+    call on the whole batch mines, with gradients equal to R times its share.  The call is run in its two halves
+    (wsegk_debug_mine_phases): all pushes, then all second halves, on one stream — two kernels of one GPU must not spin on
+    each other's flags.  Pairwise ranks at P = 512 per rank, the threshold path forced at the same size, and the threshold
+    path proper at P = 20 736 per rank (> 16 384: refused before round 2's last session)."""
+    import ctypes
+    from wseg_b200 import _lib
+    lib = _lib.lib()
+    RANKS, d, c = 2, 128, 21
+    n = RANKS * n_local
+    gen = torch.Generator().manual_seed(100 + g)
+    x1 = torch.relu(0.02 * torch.randn(n, d, g, g, generator=gen) + 0.01).to(cuda_dev)
+    x2 = torch.relu(0.02 * torch.randn(n, d, g, g, generator=gen) + 0.01).to(cuda_dev)
+    p1 = F.normalize(torch.randn(c, d, generator=gen), dim=1).to(cuda_dev)
+    p2 = F.normalize(torch.randn(c, d, generator=gen), dim=1).to(cuda_dev)
+    P, Pl = n * g * g, n_local * g * g
+    pl1 = torch.randint(0, c, (P,), generator=gen, dtype=torch.int32).to(cuda_dev)
+    pl2 = torch.randint(0, c, (P,), generator=gen, dtype=torch.int32).to(cuda_dev)
+    pl2[: P // 3] = 5                                           # one big class, sizes far from equal between the halves
+    k1, k2 = ops.mining_keys(P, 9, cuda_dev, step=3, stream_id=1), ops.mining_keys(P, 9, cuda_dev, step=3, stream_id=2)
+    stream = torch.cuda.current_stream(cuda_dev).cuda_stream
+    ops.force_radix(forced)
+    try:
+        one = ops.contrast_loss_raw(x1, x2, p1, p2, pl1, pl2, k1, k2, want_mined=True)
+        torch.cuda.synchronize()
+        nbytes = int(lib.wsegk_mine_exchange_bytes(RANKS, n_local, g, g))
+        bufs = [torch.zeros(nbytes // 4, dtype=torch.float32, device=cuda_dev) for _ in range(RANKS)]
+        peer_bases = (ctypes.c_void_p * RANKS)(*[b.data_ptr() for b in bufs])
+        ranks = []
+        for r in range(RANKS):
+            sl, ps = slice(r * n_local, (r + 1) * n_local), slice(r * Pl, (r + 1) * Pl)
+            t = dict(x1=x1[sl].contiguous(), x2=x2[sl].contiguous(), pl1=pl1[ps].contiguous(), pl2=pl2[ps].contiguous(),
+                     k1=k1[ps].contiguous(), k2=k2[ps].contiguous(), losses=torch.zeros(10, device=cuda_dev),
+                     m1=torch.zeros(Pl, dtype=torch.int32, device=cuda_dev), m2=torch.zeros(Pl, dtype=torch.int32, device=cuda_dev),
+                     state=torch.zeros(4, dtype=torch.int32, device=cuda_dev),
+                     ws=ops._workspace(_lib.OP_CONTRAST_LOSS, cuda_dev, N=n_local, C=c, D=d, h=g, w=g))
+            t["g1"], t["g2"] = torch.zeros_like(t["x1"]), torch.zeros_like(t["x2"])
+            ranks.append(t)
+
+        def call(r, mask):
+            t = ranks[r]
+            ops.check(lib.wsegk_debug_mine_phases(mask), "wsegk_debug_mine_phases")
+            try:
+                ops.check(lib.wsegk_contrast_loss_fwd_bwd_global(
+                    t["x1"].data_ptr(), t["x2"].data_ptr(), p1.data_ptr(), p2.data_ptr(), t["pl1"].data_ptr(), t["pl2"].data_ptr(),
+                    t["k1"].data_ptr(), t["k2"].data_ptr(), t["losses"].data_ptr(), t["g1"].data_ptr(), t["g2"].data_ptr(),
+                    t["m1"].data_ptr(), t["m2"].data_ptr(), None, n_local, c, d, g, g, t["ws"].data_ptr(), t["ws"].numel(),
+                    peer_bases, bufs[r].data_ptr(), RANKS, r, t["state"].data_ptr(), stream), "wsegk_contrast_loss_fwd_bwd_global")
+            finally:
+                lib.wsegk_debug_mine_phases(3)
+
+        for step in range(3):                                   # consecutive steps: both parity halves, the step counter
+            for r in range(RANKS):
+                call(r, 1)
+            for r in range(RANKS):
+                call(r, 2)
+            torch.cuda.synchronize()
+            losses = sum(t["losses"] for t in ranks) / RANKS
+            assert torch.allclose(losses[6:10], one[0][6:10], rtol=2e-5, atol=0), (step, losses, one[0])
+            for r, t in enumerate(ranks):
+                sl, ps = slice(r * n_local, (r + 1) * n_local), slice(r * Pl, (r + 1) * Pl)
+                assert torch.equal(t["m1"], one[3][ps]) and torch.equal(t["m2"], one[4][ps]), (step, r)
+                for gs, gr in ((one[1][sl], t["g1"] / RANKS), (one[2][sl], t["g2"] / RANKS)):
+                    assert float((gs - gr).abs().max()) <= 1e-6 * float(gs.abs().max()), (step, r)
+        assert int(one[3].sum()) > 0 and int(one[4].sum()) > 0
+    finally:
+        ops.force_radix(False)
+
+
 def test_topk_large_plane_vs_torch(cuda_dev):
     """P = 8 * 64 * 64 = 32768 pixels per class plane (above the single-CTA limit): indices against torch.topk on the
     GPU (distinct values) and with heavy ties against the canonical (value, lowest index) order."""

@@ -29,6 +29,7 @@ _SIGNATURES = {
     "wsegk_debug_stamp": (c_int, [_P, _P]),
     "wsegk_debug_pcm_trace_bwd": (c_int, [_P]),
     "wsegk_debug_force_radix": (c_int, [c_int]),
+    "wsegk_debug_mine_phases": (c_int, [c_int]),
     "wsegk_debug_pcm_schedule": (c_int, [c_int, c_int, c_int, c_int, _P, c_int]),
     "wsegk_pcm_set_mode": (c_int, [c_int]),
     "wsegk_pcm_get_mode": (c_int, []),

@@ -529,6 +529,7 @@ struct NceParams {
     int N, C, D, HW, P;
     int nblk, nblk_grad;       // tiles of the pixel kernel (partials 0,1) and of the gradient kernel (partial 2)
     int idx_bits;              // > 0: mining by thresholds (sel_state) instead of pairwise ranks
+    int idx_off;               // index of this rank's first pixel in the keys of the thresholds (global mining: rank * P)
     float intra_scale;         // 1, or the number of ranks when the mining is global (see nce_mine_global_kernel)
     const float* grad_scale;
     float* losses;
@@ -1052,6 +1053,29 @@ struct MineSrc {
         key = s == 0 ? x.kr : x.ks;
     }
 };
+// the same over the (sim, key, label) of ALL ranks' pixels as they lie in the exchange buffer (global mining on large loss
+// grids): element e = r * P + i is pixel i of rank r, and e is also its index in the canonical (value, global pixel) order
+struct MineGlobalSrc {
+    const uint32_t* buf;       // this rank's exchange buffer: [2 parities][R][view][sim | key | label][P]
+    const uint32_t* state;     // state[0] = step of the current exchange (its parity selects the half)
+    size_t words, view_off;    // words per rank (6 P), offset of the view's block (3 P v)
+    int P, R, idx_bits;
+    static constexpr int kSel = 3;
+    struct Elem { int cls; unsigned long long ks, kr; };
+    __device__ long long count() const { return static_cast<long long>(R) * P; }
+    __device__ Elem load(long long e) const {
+        const int r = static_cast<int>(e / P), i = static_cast<int>(e - static_cast<long long>(r) * P);
+        const uint32_t* src = buf + (static_cast<size_t>(state[0] & 1u) * R + r) * words + view_off;
+        const int ge = static_cast<int>(e);
+        return Elem{static_cast<int>(src[2 * static_cast<size_t>(P) + i]),
+                    mine_key(ordered_bits(__uint_as_float(src[i])), ge, idx_bits),
+                    mine_key(src[static_cast<size_t>(P) + i], ge, idx_bits)};
+    }
+    __device__ void get(const Elem& x, long long, int s, int& slot, unsigned long long& key) const {
+        slot = s * kNceMaxC + x.cls;
+        key = s == 0 ? x.kr : x.ks;
+    }
+};
 __global__ void mine_sel_init_kernel(NceParams prm) {       // <<<2, 96>>>
     const NceView& V = prm.v[blockIdx.x];
     const int sel = threadIdx.x >> 5, c = threadIdx.x & 31;
@@ -1146,8 +1170,8 @@ __global__ void __launch_bounds__(NPIX * kNceGroups) nce_grad_kernel(NceParams p
         int cnt = 0;
         if (len >= 2) {
             if (prm.idx_bits > 0) {
-                const unsigned long long ks = mine_key(ordered_bits(g_sim), p, prm.idx_bits);
-                const unsigned long long kr = mine_key(g_key, p, prm.idx_bits);
+                const unsigned long long ks = mine_key(ordered_bits(g_sim), p + prm.idx_off, prm.idx_bits);
+                const unsigned long long kr = mine_key(g_key, p + prm.idx_off, prm.idx_bits);
                 cnt = (kr < s_thr[0][lo] ? 1 : 0) + ((ks >= s_thr[1][lo] && ks < s_thr[2][lo]) ? 1 : 0);
             } else {
                 const int kk = static_cast<int>(static_cast<double>(len) * 0.6);  // int(len_class * 0.6)
@@ -1385,6 +1409,16 @@ extern "C" int wsegk_mining_keys(uint32_t* keys, int count, unsigned long long i
 
 // tests: take the large-plane (multi-CTA select) paths of K3 and K4 whatever the size (wsegk_debug_force_radix)
 static thread_local int g_force_radix = 0;   // per host thread: concurrent callers do not see each other's test switches
+// tests: run only the first / second half of the global-mining call (wsegk_debug_mine_phases)
+static thread_local int g_mine_phases = 3;
+extern "C" int wsegk_debug_mine_phases(int mask) {
+    if (mask < 1 || mask > 3) {
+        set_error("debug_mine_phases: mask must be 1, 2 or 3 (got %d)", mask);
+        return WSEGK_ERR_BAD_SHAPE;
+    }
+    g_mine_phases = mask;
+    return WSEGK_OK;
+}
 extern "C" int wsegk_debug_force_radix(int on) {
     g_force_radix = on ? 1 : 0;
     return WSEGK_OK;
@@ -1564,14 +1598,13 @@ static int contrast_loss_impl(const float* x1, const float* x2, const float* pro
                   kNceMaxC, C);
     const long long P = static_cast<long long>(N) * h * w;
     WSEGK_REQUIRE(P < (1ll << 30), WSEGK_ERR_BAD_SHAPE, "contrast_loss_fwd_bwd: P=%lld pixels is too many", P);
-    const bool radix = gm == nullptr && (P > kMinePairwiseMaxP || (g_force_radix && P >= 2));
+    const bool radix = P > kMinePairwiseMaxP || (g_force_radix && P >= 2);
     if (gm != nullptr) {
         WSEGK_REQUIRE(gm->peer_bases && gm->local_base && gm->local_state && gm->R >= 1 && gm->R <= kMaxRanks &&
                           gm->rank >= 0 && gm->rank < gm->R,
                       WSEGK_ERR_BAD_SHAPE, "contrast_loss_fwd_bwd_global: bad exchange arguments (R=%d rank=%d)", gm->R, gm->rank);
-        WSEGK_REQUIRE(P <= kMinePairwiseMaxP && P * gm->R <= (1 << 20), WSEGK_ERR_BAD_SHAPE,
-                      "contrast_loss_fwd_bwd_global: global mining ranks pairwise: need P <= %d per rank and R*P <= 2^20 "
-                      "(P=%lld, R=%d)", kMinePairwiseMaxP, P, gm->R);
+        WSEGK_REQUIRE(P * gm->R < (1ll << 30), WSEGK_ERR_BAD_SHAPE,
+                      "contrast_loss_fwd_bwd_global: R*P = %lld pixels is too many", P * gm->R);
     }
     const size_t proto_smem = (static_cast<size_t>(kNceSlots) * (D + 1) + kNcePix * 49 + kNcePix * kNceGroups * 4 +
                                static_cast<size_t>(D) * kNcePix) * sizeof(float);
@@ -1585,13 +1618,15 @@ static int contrast_loss_impl(const float* x1, const float* x2, const float* pro
     const NceLayout L = nce_layout(N, C, h, w);
     WSEGK_REQUIRE(workspace_bytes >= L.total, WSEGK_ERR_WORKSPACE_TOO_SMALL,
                   "contrast_loss_fwd_bwd: workspace %zu < %zu", workspace_bytes, L.total);
+    const bool phase_a = gm == nullptr || (g_mine_phases & 1), phase_b = gm == nullptr || (g_mine_phases & 2);
     NceParams prm{};
     prm.N = N; prm.C = C; prm.D = D; prm.HW = h * w; prm.P = static_cast<int>(P);
     prm.nblk = tiled ? static_cast<int>((P + kTilePix - 1) / kTilePix) : L.nblk;
     prm.nblk_grad = tiled ? static_cast<int>((P + kGradTilePix - 1) / kGradTilePix) : L.nblk;
     prm.grad_scale = grad_scale;
     prm.losses = losses;
-    prm.idx_bits = radix ? index_bits(P) : 0;
+    prm.idx_bits = radix ? index_bits(gm ? P * gm->R : P) : 0;
+    prm.idx_off = (radix && gm) ? gm->rank * static_cast<int>(P) : 0;
     prm.intra_scale = gm ? static_cast<float>(gm->R) : 1.f;
     uint8_t* ws = static_cast<uint8_t*>(workspace);
     for (int v = 0; v < 2; ++v) {
@@ -1617,6 +1652,7 @@ static int contrast_loss_impl(const float* x1, const float* x2, const float* pro
         V.sel_state = reinterpret_cast<SegSel*>(b + L.off_state);
         V.sel_hist = reinterpret_cast<uint32_t*>(b + L.off_hist);
         V.partial = reinterpret_cast<float*>(b + L.off_part);
+        if (!phase_a) continue;
         if (radix)
             WSEGK_CUDA_OK(cudaMemsetAsync(b + L.off_cls, 0, L.clear_bytes - L.off_cls, stream));
         else
@@ -1637,24 +1673,18 @@ static int contrast_loss_impl(const float* x1, const float* x2, const float* pro
                                                                     kGradTilePix * kNceGroups, tile_grad_smem));
         grid_a = std::min(prm.nblk, std::max(1, sms * occ_a));
         grid_c = std::min(prm.nblk_grad, std::max(1, sms * occ_c));
-        nce_pixel_tile_kernel<<<dim3(grid_a, 2), kPixTileThreads, tile_pix_smem, stream>>>(prm);
+        if (phase_a) nce_pixel_tile_kernel<<<dim3(grid_a, 2), kPixTileThreads, tile_pix_smem, stream>>>(prm);
     } else {
         WSEGK_CUDA_OK(cudaFuncSetAttribute(nce_pixel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            static_cast<int>(proto_smem)));
         WSEGK_CUDA_OK(cudaFuncSetAttribute(nce_grad_kernel<kNcePix>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            static_cast<int>(proto_smem)));
-        nce_pixel_kernel<<<dim3(L.nblk, 2), kNceThreads, proto_smem, stream>>>(prm);
+        if (phase_a) nce_pixel_kernel<<<dim3(L.nblk, 2), kNceThreads, proto_smem, stream>>>(prm);
     }
     int launches = 3;
-    if (radix) {
-        mine_sel_init_kernel<<<2, 96, 0, stream>>>(prm);
-        ++launches;
-        for (int v = 0; v < 2; ++v) {
-            const NceView& V = prm.v[v];
-            const MineSrc src{V.pl_own, V.sim, V.rkey, prm.P, prm.idx_bits};
-            launches += seg_select_run(src, prm.P, 32 + prm.idx_bits, 3 * kNceMaxC, V.sel_state, V.sel_hist, stream);
-        }
-    } else if (gm != nullptr) {
+    const uint32_t* gbuf = nullptr;
+    if (gm != nullptr) {
+        // every rank's (sim, key, label) into every peer's buffer; global class sizes
         const int R = gm->R;
         const size_t flag_off = align_up(mine_exchange_words(R, P) * 4, 256);
         MinePeers peers{};
@@ -1663,14 +1693,40 @@ static int contrast_loss_impl(const float* x1, const float* x2, const float* pro
             peers.base[p] = static_cast<uint32_t*>(gm->peer_bases[p]);
             peers.flags[p] = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(gm->peer_bases[p]) + flag_off);
         }
-        const uint32_t* buf = static_cast<const uint32_t*>(gm->local_base);
+        gbuf = static_cast<const uint32_t*>(gm->local_base);
         const uint32_t* flags = reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(gm->local_base) + flag_off);
-        mine_push_kernel<<<dim3(kPushChunks, R), 256, 0, stream>>>(prm, peers, R, gm->rank, gm->local_state);
-        mine_global_count_kernel<<<2, 1024, 0, stream>>>(prm, buf, flags, gm->local_state, R);
-        nce_mine_global_kernel<<<dim3(ceil_div(prm.P, kMineThreads), ceil_div(R * prm.P, kMineChunk), 2), kMineThreads, 0,
-                                 stream>>>(prm, buf, flags, gm->local_state, R, gm->rank);
-        launches += 3;
-    } else {
+        if (phase_a) mine_push_kernel<<<dim3(kPushChunks, R), 256, 0, stream>>>(prm, peers, R, gm->rank, gm->local_state);
+        if (!phase_b) {
+            count_launches(2);
+            WSEGK_CUDA_OK(cudaGetLastError());
+            return WSEGK_OK;
+        }
+        mine_global_count_kernel<<<2, 1024, 0, stream>>>(prm, gbuf, flags, gm->local_state, R);   // waits for the peers' flags
+        launches += 2;
+        if (!radix) {
+            nce_mine_global_kernel<<<dim3(ceil_div(prm.P, kMineThreads), ceil_div(R * prm.P, kMineChunk), 2), kMineThreads, 0,
+                                     stream>>>(prm, gbuf, flags, gm->local_state, R, gm->rank);
+            ++launches;
+        }
+    }
+    if (radix) {
+        mine_sel_init_kernel<<<2, 96, 0, stream>>>(prm);
+        ++launches;
+        for (int v = 0; v < 2; ++v) {
+            const NceView& V = prm.v[v];
+            if (gm != nullptr) {
+                // thresholds over ALL ranks' pixels (every rank derives the same three keys per class); the parity half of
+                // the buffer is a device-side value (step counter), so the source takes it from there
+                const MineGlobalSrc src{gbuf, gm->local_state, static_cast<size_t>(6) * prm.P, static_cast<size_t>(3) * prm.P * v,
+                                        prm.P, gm->R, prm.idx_bits};
+                launches += seg_select_run(src, static_cast<long long>(gm->R) * prm.P, 32 + prm.idx_bits, 3 * kNceMaxC,
+                                           V.sel_state, V.sel_hist, stream);
+            } else {
+                const MineSrc src{V.pl_own, V.sim, V.rkey, prm.P, prm.idx_bits};
+                launches += seg_select_run(src, prm.P, 32 + prm.idx_bits, 3 * kNceMaxC, V.sel_state, V.sel_hist, stream);
+            }
+        }
+    } else if (gm == nullptr) {
         nce_mine_kernel<<<dim3(ceil_div(prm.P, kMineThreads), ceil_div(prm.P, kMineChunk), 2), kMineThreads, 0,
                           stream>>>(prm);
         ++launches;

@@ -550,10 +550,12 @@ def philox4x32_10(counter, key):
 
 
 def contrast_loss_raw(x1, x2, proto1, proto2, pl1, pl2, key1, key2, grad_scale: Optional[torch.Tensor] = None,
-                      want_mined: bool = False, global_group=None):
+                      want_mined: bool = False, global_group=None, global_exchange=None):
     """One call of wsegk_contrast_loss_fwd_bwd.  Returns (losses [10], grad_x1, grad_x2, mined1, mined2).
     ``global_group``: a process group over which the hard-pixel mining is GLOBAL (the reference's whole-batch semantics
-    under data parallelism; one NVLink exchange of 12 bytes per pixel and view; needs symmetric memory)."""
+    under data parallelism; one NVLink exchange of 12 bytes per pixel and view; needs symmetric memory).
+    ``global_exchange``: the exchange itself (an object with peer_bases, buf, world, rank, state as dist.MineExchange has
+    them) instead of a group — lets one process drive several "ranks" whose buffers are plain device memory (tests)."""
     x1 = _require_cuda_f32("x1", x1.detach())
     x2 = _require_cuda_f32("x2", x2.detach())
     n, d, h, w = x1.shape
@@ -572,13 +574,15 @@ def contrast_loss_raw(x1, x2, proto1, proto2, pl1, pl2, key1, key2, grad_scale: 
             key1.to(torch.int32).contiguous(), key2.to(torch.int32).contiguous()]
     with torch.cuda.device(dev):
         ws = _workspace(_lib.OP_CONTRAST_LOSS, dev, N=n, C=c, D=d, h=h, w=w)
-        if global_group is None:
+        if global_group is None and global_exchange is None:
             check(_lib.lib().wsegk_contrast_loss_fwd_bwd(
                 _ptr(x1), _ptr(x2), *[_ptr(a) for a in args], _ptr(losses), _ptr(g1), _ptr(g2), _ptr(m1), _ptr(m2),
                 _ptr(grad_scale), n, c, d, h, w, _ptr(ws), ws.numel(), _stream(x1)), "wsegk_contrast_loss_fwd_bwd")
         else:
-            from . import dist as _dist
-            ex = _dist.MineExchange.get(global_group, n, h, w, dev)
+            ex = global_exchange
+            if ex is None:
+                from . import dist as _dist
+                ex = _dist.MineExchange.get(global_group, n, h, w, dev)
             check(_lib.lib().wsegk_contrast_loss_fwd_bwd_global(
                 _ptr(x1), _ptr(x2), *[_ptr(a) for a in args], _ptr(losses), _ptr(g1), _ptr(g2), _ptr(m1), _ptr(m2),
                 _ptr(grad_scale), n, c, d, h, w, _ptr(ws), ws.numel(), ex.peer_bases, _ptr(ex.buf), ex.world, ex.rank,
