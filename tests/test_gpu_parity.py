@@ -283,6 +283,38 @@ def test_fullres_norm_on_lazy_enlargement(cuda_dev, n, hw, up, size):
     assert rel_max(lazy, ref) <= 1e-5 and rel_max(b.grad, r.grad) <= 1e-4
 
 
+def test_fullres_norm_takes_the_small_map_of_a_remembered_enlargement(cuda_dev):
+    """ops.bilinear_resize leaves a note on an enlarged map (the x8 maps Net.forward returns, resnet38_contrast.py:57-59);
+    ops.fullres_norm on such a map (contrast_train.py:145-152) then works from the small map: same values bit for bit,
+    same gradient on the small map as the materialised chain, and any operation in between falls back to that chain."""
+    n, c, h, w = 3, 21, 20, 13
+    g = torch.Generator().manual_seed(5)
+    small = (0.05 * torch.randn(n, c, h, w, generator=g)).to(cuda_dev)
+    label = synth.label_with_bg(synth.labels(n, seed=2)).to(cuda_dev)
+    gout = torch.randn(n, c, 40, 26, generator=g).to(cuda_dev)
+    res = {}
+    for name, remember, touch in (("noted", True, False), ("plain", False, False), ("touched", True, True)):
+        ops.remember_enlargements(remember)
+        try:
+            x = small.clone().requires_grad_(True)
+            up = ops.bilinear_resize(x, (8 * h, 8 * w))
+            assert (ops._enlarged_from(up) is not None) == remember
+            if touch:
+                up = up * 1.0
+                assert ops._enlarged_from(up) is None
+            y = ops.fullres_norm(up, label, (40, 26))
+            (gx,) = torch.autograd.grad((y * gout).sum(), x)
+            res[name] = (y.detach(), gx)
+        finally:
+            ops.remember_enlargements(True)
+    assert torch.equal(res["noted"][0], res["plain"][0]) and torch.equal(res["touched"][0], res["plain"][0])
+    assert torch.equal(res["touched"][1], res["plain"][1])
+    assert rel_max(res["noted"][1], res["plain"][1]) <= 2e-5
+    up = ops.bilinear_resize(small, (8 * h, 8 * w))
+    up.mul_(2.0)                                                # in place: the version counter gives it away
+    assert ops._enlarged_from(up) is None
+
+
 def test_lazy_step_loss_equals_materialised(cuda_dev):
     """contrast_step_loss_lazy on the small maps == contrast_step_loss on their x8 enlargements: the 8 logged scalars and
     the gradients that reach the small maps (through ops.bilinear_resize's backward on the materialised side)."""

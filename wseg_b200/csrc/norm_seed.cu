@@ -339,6 +339,42 @@ __global__ void __launch_bounds__(256) resize_fwd_vec4_kernel(const float* __res
     }
 }
 
+// The same for oh % RB == 0, a thread = four consecutive outputs of RB consecutive rows: the column taps and weights are
+// computed once per thread and the row taps once per row, so a value costs ~12 instructions instead of ~40 and the kernel is
+// bound by its store stream (the x8 enlargements at the end of Net.forward, network/resnet38_contrast.py:57-59, write
+// 135 MB each at N = 8, 448x448: 85 -> ~25 us).  Same src_coord / bilerp arithmetic: bit-identical values.
+template <int RB>
+__global__ void __launch_bounds__(256) resize_fwd_rows_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                              int planes, int H, int W, int oh, int ow) {
+    const float sy = oh > 1 ? static_cast<float>(H - 1) / static_cast<float>(oh - 1) : 0.f;
+    const float sx = ow > 1 ? static_cast<float>(W - 1) / static_cast<float>(ow - 1) : 0.f;
+    const int ow4 = ow >> 2, items = (oh / RB) * ow4;
+    for (int plane = blockIdx.y; plane < planes; plane += gridDim.y) {
+        const float* src = x + static_cast<size_t>(plane) * H * W;
+        float4* dst = reinterpret_cast<float4*>(y + static_cast<size_t>(plane) * oh * ow);
+        for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < items; it += gridDim.x * blockDim.x) {
+            const int rg = it / ow4, q = it - rg * ow4;
+            int x0[4], x1[4];
+            float wx0[4], wx1[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) src_coord(4 * q + j, sx, W, x0[j], x1[j], wx0[j], wx1[j]);
+#pragma unroll
+            for (int r = 0; r < RB; ++r) {
+                const int oy = rg * RB + r;
+                int y0, y1; float hy0, hy1;
+                src_coord(oy, sy, H, y0, y1, hy0, hy1);
+                const float* r0 = src + y0 * W;
+                const float* r1 = src + y1 * W;
+                float v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    v[j] = bilerp(hy0, hy1, wx0[j], wx1[j], __ldg(r0 + x0[j]), __ldg(r0 + x1[j]), __ldg(r1 + x0[j]), __ldg(r1 + x1[j]));
+                dst[oy * ow4 + q] = make_float4(v[0], v[1], v[2], v[3]);
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) resize_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int planes,
                                                          int H, int W, int oh, int ow) {
     const float sy = oh > 1 ? static_cast<float>(H - 1) / static_cast<float>(oh - 1) : 0.f;
@@ -817,7 +853,10 @@ extern "C" int wsegk_bilinear_resize_fwd(const float* x, float* y, int planes, i
     if (int rc = check_device()) return rc;
     WSEGK_REQUIRE(x && y, WSEGK_ERR_NULL, "bilinear_resize_fwd: null pointer");
     if (int rc = resize_check("bilinear_resize_fwd", planes, H, W, oh, ow)) return rc;
-    if ((ow & 3) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 && oh * ow >= 4096) {
+    if ((ow & 3) == 0 && (oh & 7) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 && oh * ow >= 4096 && oh >= H && ow >= W) {
+        const dim3 grid(std::min(ceil_div((oh >> 3) * (ow >> 2), 256), 1024), std::min(planes, 32768));
+        resize_fwd_rows_kernel<8><<<grid, 256, 0, stream>>>(x, y, planes, H, W, oh, ow);
+    } else if ((ow & 3) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 && oh * ow >= 4096) {
         const dim3 grid(std::min(ceil_div(oh * (ow >> 2), 256), 1024), std::min(planes, 32768));
         resize_fwd_vec4_kernel<<<grid, 256, 0, stream>>>(x, y, planes, H, W, oh, ow);
     } else {

@@ -303,7 +303,16 @@ class _FullresNorm(torch.autograd.Function):
 
 def fullres_norm(p: torch.Tensor, label: torch.Tensor, size: Optional[Tuple[int, int]] = None) -> torch.Tensor:
     """visualization.max_norm(p) -> bilinear(align_corners) to ``size`` -> * label
-    (tool/visualization.py:62-67, contrast_train.py:145-152,157-158).  label: [N,C] or [N,C,1,1]."""
+    (tool/visualization.py:62-67, contrast_train.py:145-152,157-158).  label: [N,C] or [N,C,1,1].
+
+    If ``p`` is the untouched output of :func:`bilinear_resize` enlarging a small map (what ``Net.forward`` returns as
+    ``cam`` / ``cam_rv``, network/resnet38_contrast.py:57-59), the normalisation is evaluated from the SMALL map
+    (:func:`fullres_norm_up`: bit-identical values) and the gradient goes straight back to it: the dense full-resolution
+    gradient (135 MB per map at N = 8, 448x448: written by this op's backward, read again by the enlargement's) never
+    exists.  Any operation on ``p`` in between, in place or not, gives a tensor without the note and the plain path."""
+    src = _enlarged_from(p)
+    if src is not None:
+        return _FullresNormUp.apply(src, label, tuple(p.shape[-2:]), None if size is None else tuple(size))
     return _FullresNorm.apply(p, label, size)
 
 
@@ -382,11 +391,41 @@ class _Resize(torch.autograd.Function):
         return gx, None
 
 
+_REMEMBER_ENLARGEMENT = os.environ.get("WSEG_REMEMBER_ENLARGEMENT", "1") == "1"
+
+
+def remember_enlargements(on: bool) -> None:
+    """Switch the note :func:`bilinear_resize` leaves on an enlarged map (see :func:`fullres_norm`); tests compare both."""
+    global _REMEMBER_ENLARGEMENT
+    _REMEMBER_ENLARGEMENT = bool(on)
+
+
+def _enlarged_from(p: torch.Tensor) -> Optional[torch.Tensor]:
+    """The small map ``p`` was enlarged from, if ``p`` and that map are still what they were when it was made."""
+    note = getattr(p, "_wseg_enlarged", None)
+    if note is None or not _REMEMBER_ENLARGEMENT:
+        return None
+    small, v_small, v_self = note
+    if p._version != v_self or small._version != v_small or not p.is_cuda:
+        return None
+    h, w = small.shape[-2:]
+    H, W = p.shape[-2:]
+    if h * w * 4 + 2 * (H + W) * 8 + 64 > 200 * 1024:           # the fused kernels keep the small plane in shared memory
+        return None
+    return small
+
+
 def bilinear_resize(x: torch.Tensor, size: Tuple[int, int]) -> torch.Tensor:
     """F.interpolate(x, size, mode='bilinear', align_corners=True), differentiable (contrast_train.py:179-180,
     network/resnet38_contrast.py:57-59).  ATen's NCHW kernel loops over N*C inside each thread: 0.3 ms for
-    [8,128,56,56] -> 16x16 and 0.5 ms (0.8 ms backward) for [8,21,56,56] -> 448x448 on a B200."""
-    return _Resize.apply(x, size)
+    [8,128,56,56] -> 16x16 and 0.5 ms (0.8 ms backward) for [8,21,56,56] -> 448x448 on a B200.
+    An ENLARGED map carries a note of the map it came from (a Python attribute, lost by any further operation), which
+    lets :func:`fullres_norm` skip the full-resolution gradient."""
+    y = _Resize.apply(x, size)
+    if _REMEMBER_ENLARGEMENT and x.dim() == 4 and y.shape[-2] >= x.shape[-2] and y.shape[-1] >= x.shape[-1] \
+            and x.dtype == torch.float32:
+        y._wseg_enlarged = (x, x._version, y._version)
+    return y
 
 
 # --------------------------------------------------------------------------------------------- K1c
