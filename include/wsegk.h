@@ -76,6 +76,17 @@ int wsegk_pcm_fwd(const float* f, const float* cam_norm, float* cam_rv, int N, i
 int wsegk_pcm_fwd_infer(const float* f, const float* cam_norm, float* cam_rv, int N, int C, int K, int h, int w,
                         void* workspace, size_t workspace_bytes, wsegk_stream_t stream);
 
+/* Several forward-only K2 problems of different sizes in ONE launch of the tcgen05 kernel (multi-scale +
+ * flip inference, contrast_infer.py:58-71 — the 4 scales x {image, flip} of one image are 4 problems of batch 2).  Item i:
+ * f[i] [N[i],K,h[i],w[i]], cam_norm[i] [N[i],C,h[i],w[i]] -> cam_rv[i] (same shape as cam_norm[i]); the arrays f, cam_norm,
+ * cam_rv, N, h, w, workspaces, workspace_bytes are HOST arrays of n_items (<= 8) entries.  Every item needs its own
+ * workspace of the size wsegk_pcm_multi_workspace_bytes reports for it (it depends on how the grid is split between the
+ * items).  Results equal wsegk_pcm_fwd_infer's to fp32 rounding (the stage width is 128 pixels for every item). */
+int wsegk_pcm_multi_workspace_bytes(int n_items, const int* N, const int* h, const int* w, int C, int K, size_t* bytes_out);
+int wsegk_pcm_fwd_infer_multi(int n_items, const float* const* f, const float* const* cam_norm, float* const* cam_rv,
+                              const int* N, const int* h, const int* w, int C, int K, void* const* workspaces,
+                              const size_t* workspace_bytes, wsegk_stream_t stream);
+
 /* K1a + K2 forward fused: `cam_logits` [N,C,h,w] are the RAW class logits (the fc8 output); the in-network normalisation
  * (network/resnet38_contrast.py:41-48, what wsegk_cam_norm_fwd computes) is applied inside the operand preparation of the PCM
  * and also written to cam_norm_out [N,C,h,w] (bit-identical to wsegk_cam_norm_fwd; wsegk_pcm_bwd needs it).  Otherwise as

@@ -831,6 +831,27 @@ def test_pcm_inference_msf_sizes(cuda_dev, n, h, w):
     assert rel_max(flipped, out) <= 1e-4
 
 
+@pytest.mark.parametrize("shapes", [[(2, 20, 30), (2, 40, 60), (2, 60, 90), (2, 80, 120)], [(1, 28, 28)],
+                                    [(1, 16, 16)] * 8, [(2, 13, 7), (3, 56, 56)]])
+def test_pcm_inference_many_grids_in_one_launch(cuda_dev, shapes):
+    """the variants of multi-scale + flip inference (contrast_infer.py:58-71) have different grids; one launch of
+    the forward kernel runs them all, every problem on its share of the CTA pairs.  Each result against the single-problem
+    forward-only call (different stage width, so fp32 rounding differs) and, for the small ones, against the oracle."""
+    cams, fs = [], []
+    for i, (n, h, w) in enumerate(shapes):
+        d = synth.pcm_inputs(n, h, w, seed=70 + i)
+        cams.append(ops.cam_norm(d["cam"].to(cuda_dev)))
+        fs.append(d["f"].to(cuda_dev))
+    outs = ops.pcm_infer_multi(cams, fs)
+    assert len(outs) == len(shapes)
+    for (n, h, w), cam, f, out in zip(shapes, cams, fs, outs):
+        one, _ = ops.pcm_forward(cam, f, inference=True)
+        assert out.shape == one.shape
+        assert rel_max(out, one) <= 1e-4, (n, h, w)            # P = relu(S) is fp16: its rounding follows the stage partition
+        if h * w <= 2400:
+            assert rel_max(out, R.pcm(cam, f)) <= TOL, (n, h, w)
+
+
 def test_seam_net_and_batched_msf_inference(cuda_dev):
     """resnet38_SEAM.Net shares its head with the contrast network (same cam, cam_rv for the same weights), and
     infer.msf_cam — image and flipped image of a scale in one forward — equals the per-variant loop of
@@ -851,9 +872,15 @@ def test_seam_net_and_batched_msf_inference(cuda_dev):
         label20 = torch.zeros(20)
         label20[[2, 7]] = 1
         orig = (80, 100)
-        norm_cam, cam_dict = infer.msf_cam(a, scales, label20, orig)
-        serial, _ = infer.msf_cam(a, scales, label20, orig, concurrent=False)
+        norm_cam, cam_dict = infer.msf_cam(a, scales, label20, orig, one_pcm_launch=False)
+        serial, _ = infer.msf_cam(a, scales, label20, orig, concurrent=False, one_pcm_launch=False)
         assert torch.equal(norm_cam, serial)                    # one stream per scale: same arithmetic, same order of the sum
+        # the PCM of all scales in ONE launch (every scale on its share of the CTA pairs; stage width 128 for all of them)
+        fused, fused_dict = infer.msf_cam(a, scales, label20, orig)
+        assert sorted(fused_dict) == [2, 7]
+        assert float((fused - norm_cam).abs().max()) <= 1e-4 * float(norm_cam.abs().max())
+        fused_b, _ = infer.msf_cam(b, scales, label20, orig)    # the SEAM drop-in borrows pcm_inputs
+        assert float((fused_b - norm_cam).abs().max()) <= 1e-4 * float(norm_cam.abs().max())
         # the SEAM net's outputs carry no graph even in train mode (its tail runs under no_grad, resnet38_SEAM.py:36-52)
         b.train()
         cam_t, rv_t = b(x)

@@ -47,7 +47,8 @@ def timed(fn, reps=5):
 
 
 t0 = timed(script_loop)
-t1 = timed(lambda: infer.msf_cam(net, scales, label20, (H, W), concurrent=False))
-t2 = timed(lambda: infer.msf_cam(net, scales, label20, (H, W), concurrent=True))
+t1 = timed(lambda: infer.msf_cam(net, scales, label20, (H, W), concurrent=False, one_pcm_launch=False))
+t2 = timed(lambda: infer.msf_cam(net, scales, label20, (H, W), concurrent=True, one_pcm_launch=False))
+t3 = timed(lambda: infer.msf_cam(net, scales, label20, (H, W), concurrent=True, one_pcm_launch=True))
 print(f"image {H}x{W}, scales 0.5/1/1.5/2 x flip, random-init ResNet-38 (eval): per-variant loop {t0:.1f} ms | image+flip batched per scale, "
-      f"sequential {t1:.1f} ms | one stream per scale {t2:.1f} ms")
+      f"sequential {t1:.1f} ms | one stream per scale {t2:.1f} ms | + the PCM of all scales in one launch {t3:.1f} ms")

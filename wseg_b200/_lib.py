@@ -34,6 +34,8 @@ _SIGNATURES = {
     "wsegk_pcm_set_mode": (c_int, [c_int]),
     "wsegk_pcm_get_mode": (c_int, []),
     "wsegk_pcm_set_pairs": (c_int, [c_int, c_int]),
+    "wsegk_pcm_multi_workspace_bytes": (c_int, [c_int, _P, _P, _P, c_int, c_int, _P]),
+    "wsegk_pcm_fwd_infer_multi": (c_int, [c_int, _P, _P, _P, _P, _P, _P, c_int, c_int, _P, _P, _P]),
     "wsegk_debug_pcm_layout": (c_int, [c_int] * 5 + [ctypes.POINTER(c_size_t), c_int]),
     "wsegk_cam_norm_fwd": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
     "wsegk_pcm_fwd": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),

@@ -131,18 +131,19 @@ static int max_unit_segments(int units, int NS, int G) {
     return best;
 }
 
-PcmPlan make_pcm_plan(void* ws, int N, int C, int K, int h, int w, int precise) {
+PcmPlan make_pcm_plan(void* ws, int N, int C, int K, int h, int w, int precise, int wb_force, int pairs_force) {
     PcmPlan p{};
     p.N = N; p.C = C; p.K = K; p.HW = h * w;
     p.PJ = ceil_div(p.HW, 2 * kTile);
     p.HWpj = p.PJ * 2 * kTile;
-    p.wb = pick_wb(p.HW);
+    p.wb = wb_force > 0 ? wb_force : pick_wb(p.HW);
     p.NS = ceil_div(p.HW, 2 * p.wb);
     p.HWpi = p.NS * 2 * p.wb;
     // forward and backward main kernels may run on different numbers of CTA pairs (round 2: with the step re-ordered the
     // optimum moved down — what the other chains gain from the SMs a PCM kernel leaves free outweighs what the PCM loses)
     p.G = pick_clusters(static_cast<long long>(N) * p.PJ, p.NS, g_pcm_pairs[0]);
     p.Gb = pick_clusters(static_cast<long long>(N) * p.PJ, p.NS, g_pcm_pairs[1]);
+    if (pairs_force > 0) p.G = p.Gb = pairs_force;
     const int seg_f = max_unit_segments(N * p.PJ, p.NS, p.G);
     p.fwd_shared_units = seg_f > 1;
     p.nsplit = std::max(seg_f, max_unit_segments(N * p.PJ, p.NS, p.Gb));

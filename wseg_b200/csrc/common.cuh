@@ -184,7 +184,9 @@ struct StageCursor {
 // peak[plane] = max relu(cam[plane]) + 1e-5, one CTA per (n,c) plane (cam_norm.cu)
 void launch_cam_plane_peak(const float* cam, float* peak, int planes, int HW, cudaStream_t stream);
 
-PcmPlan make_pcm_plan(void* ws, int N, int C, int K, int h, int w, int precise);
+// wb_force / pairs_force > 0: that B-tile height / exactly that many forward CTA pairs (the multi-problem forward, whose
+// problems share one kernel instantiation and split the grid between them) instead of the per-shape choices
+PcmPlan make_pcm_plan(void* ws, int N, int C, int K, int h, int w, int precise, int wb_force = 0, int pairs_force = 0);
 int pcm_mode();     // current process-wide mode (wsegk_pcm_set_mode): 1 precise (default), 0 fast
 
 }  // namespace wsegk

@@ -423,12 +423,14 @@ __device__ __noinline__ void fwd_epilogue(uint32_t o_addr, float* __restrict__ o
 // contiguous ranges, one per CTA pair, so every pair does the same number of stages whatever N, PJ and NS are (no wave
 // quantisation) and pays ONE prologue/drain.  A range crosses unit boundaries: each (pair, unit) piece is a "segment"
 // with its own A-side tile and its own partial-result slot  slot = pair - (pair owning the unit's first stage).
+// The kernel body: CTA pair `g` of the `G` pairs that share this problem (pcm_fwd_kernel: the whole grid; pcm_fwd_multi_kernel:
+// the pairs allotted to one of several problems of different sizes).
 template <int WB, int MODE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFwdThreads, 1)
-pcm_fwd_kernel(const uint8_t* __restrict__ fa, const uint8_t* __restrict__ fb, const uint8_t* __restrict__ camb,
-               float* __restrict__ part, uint2* __restrict__ mask, uint2* __restrict__ nzmask,
-               const float* __restrict__ lo2max, float* __restrict__ out, float* __restrict__ dsum, int C, int K, int HW, int PJ, int NS, int n_units, int nslot,
-               long long* __restrict__ trace) {
+__device__ __forceinline__ void
+pcm_fwd_body(const uint8_t* __restrict__ fa, const uint8_t* __restrict__ fb, const uint8_t* __restrict__ camb,
+             float* __restrict__ part, uint2* __restrict__ mask, uint2* __restrict__ nzmask,
+             const float* __restrict__ lo2max, float* __restrict__ out, float* __restrict__ dsum, int C, int K, int HW, int PJ, int NS, int n_units, int nslot,
+             long long* __restrict__ trace, const int g, const int G) {
     constexpr int FS = kFStages;
     // optional timeline of CTA 0: trace[role*256 + t*4 + k] = clock64()   (wsegk_debug_pcm_trace)
     const bool tr = trace != nullptr && blockIdx.x == 0;
@@ -458,8 +460,7 @@ pcm_fwd_kernel(const uint8_t* __restrict__ fa, const uint8_t* __restrict__ fb, c
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
-    const int g = static_cast<int>(blockIdx.x >> 1);
-    const PcmSched sched = pcm_sched(n_units, NS, static_cast<int>(gridDim.x >> 1));
+    const PcmSched sched = pcm_sched(n_units, NS, G);
     const StageCursor c0(sched, g, PJ);                        // every role walks its own copy
     const int cnt = c0.cnt;                                    // stages this CTA pair runs
     const int HWpj = PJ * 2 * kTile;
@@ -856,6 +857,43 @@ pcm_fwd_kernel(const uint8_t* __restrict__ fa, const uint8_t* __restrict__ fb, c
 #undef TRACEP
 }
 
+template <int WB, int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFwdThreads, 1)
+pcm_fwd_kernel(const uint8_t* __restrict__ fa, const uint8_t* __restrict__ fb, const uint8_t* __restrict__ camb,
+               float* __restrict__ part, uint2* __restrict__ mask, uint2* __restrict__ nzmask,
+               const float* __restrict__ lo2max, float* __restrict__ out, float* __restrict__ dsum, int C, int K, int HW, int PJ, int NS, int n_units, int nslot,
+               long long* __restrict__ trace) {
+    pcm_fwd_body<WB, MODE>(fa, fb, camb, part, mask, nzmask, lo2max, out, dsum, C, K, HW, PJ, NS, n_units, nslot, trace,
+                           static_cast<int>(blockIdx.x >> 1), static_cast<int>(gridDim.x >> 1));
+}
+
+// Several forward-only problems of DIFFERENT sizes in ONE launch (the 4 scales x {image, flip} of
+// contrast_infer.py:58-71 are 4 problems of batch 2): every problem owns a contiguous range of the grid's CTA pairs, in
+// proportion to its stages, and runs the schedule of the single-problem kernel inside it.  Per-scale launches leave the GPU to
+// one problem at a time — the 0.5x scale (600 pixels: 30 stages in all) cannot fill it, and every launch pays its own
+// prologue and tail.
+constexpr int kMaxFwdItems = 8;
+struct FwdItem {
+    const uint8_t *fa, *fb, *camb;
+    float *part, *out, *dsum;
+    int HW, PJ, NS, n_units, nslot, g0, G;
+};
+struct FwdItems {
+    int n, C, K;
+    FwdItem it[kMaxFwdItems];
+};
+template <int WB>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFwdThreads, 1)
+pcm_fwd_multi_kernel(const __grid_constant__ FwdItems items) {
+    const int gp = static_cast<int>(blockIdx.x >> 1);
+    int idx = 0;
+    for (int i = 1; i < items.n; ++i)
+        if (gp >= items.it[i].g0) idx = i;
+    const FwdItem& it = items.it[idx];
+    pcm_fwd_body<WB, 0>(it.fa, it.fb, it.camb, it.part, nullptr, nullptr, nullptr, it.out, it.dsum, items.C, items.K, it.HW,
+                        it.PJ, it.NS, it.n_units, it.nslot, nullptr, gp - it.g0, it.G);
+}
+
 // ------------------------------------------------------------------------------------------------
 // sign fix-up (precise mode)
 // ------------------------------------------------------------------------------------------------
@@ -999,14 +1037,12 @@ __global__ void __launch_bounds__(kFixThreads) pcm_sign_fixup_kernel(const float
 // the ablation build, where the main kernel leaves partials for every unit).
 // The partials are column-major ([n][slot][64][HWpj]: hi rows 0..C-1, column sum at row C, lo rows 32..32+C-1), so thread
 // (c, j) reads and writes along j: no transpose.  One CTA = 32 consecutive rows j x 8 class phases.
-__global__ void __launch_bounds__(256) pcm_fwd_finalize_kernel(const float* __restrict__ part,
-                                                               float* __restrict__ out,
-                                                               float* __restrict__ dsum, int C, int HW,
-                                                               int HWpj, int nslot, int PJ, int NS, int G, int all) {
-    const int n = blockIdx.y;
+__device__ __forceinline__ void pcm_fwd_finalize_body(const float* __restrict__ part, float* __restrict__ out,
+                                                      float* __restrict__ dsum, int C, int HW, int HWpj, int nslot, int PJ,
+                                                      int NS, int G, int all, int N, int bx, int n) {
     const int lane = threadIdx.x & 31, ph = threadIdx.x >> 5;
-    const int j = blockIdx.x * 32 + lane;                        // HWpj is a multiple of 256
-    const int nseg = pcm_unit_segments(pcm_sched(static_cast<int>(gridDim.y) * PJ, NS, G), n * PJ + j / (2 * kTile));
+    const int j = bx * 32 + lane;                                // HWpj is a multiple of 256
+    const int nseg = pcm_unit_segments(pcm_sched(N * PJ, NS, G), n * PJ + j / (2 * kTile));
     if (nseg == 1 && !all) return;                               // uniform over the CTA (32 divides 256)
     const size_t slot_stride = static_cast<size_t>(kONum) * HWpj;
     const float* base = part + static_cast<size_t>(n) * nslot * slot_stride + j;
@@ -1023,6 +1059,12 @@ __global__ void __launch_bounds__(256) pcm_fwd_finalize_kernel(const float* __re
         }
         out[(static_cast<size_t>(n) * C + c) * HW + j] = (hi + lo) * __frcp_rn(d);
     }
+}
+__global__ void __launch_bounds__(256) pcm_fwd_finalize_kernel(const float* __restrict__ part,
+                                                               float* __restrict__ out,
+                                                               float* __restrict__ dsum, int C, int HW,
+                                                               int HWpj, int nslot, int PJ, int NS, int G, int all) {
+    pcm_fwd_finalize_body(part, out, dsum, C, HW, HWpj, nslot, PJ, NS, G, all, static_cast<int>(gridDim.y), blockIdx.x, blockIdx.y);
 }
 
 
@@ -1806,6 +1848,163 @@ extern "C" int wsegk_pcm_fwd(const float* f, const float* cam_norm, float* cam_r
                              int w, void* workspace, size_t workspace_bytes, wsegk_stream_t stream) {
     return pcm_fwd_impl(f, cam_norm, cam_rv, N, C, K, h, w, workspace, workspace_bytes, stream, pcm_mode() ? 2 : 1, false,
                         nullptr);
+}
+
+namespace wsegk {
+// operand preparation and finalize pass of several problems in one launch each: block -> (problem, block of the problem)
+struct PrepItem {
+    const float *f, *cam;
+    uint4 *fa, *fb, *camb;
+    float *fh32, *inv_norm;
+    unsigned int* lo2max;
+    int HW, PJ, NS, tiles, bx, block0;      // bx = tiles + NS blocks per image; block0 = first block of the problem
+};
+struct PrepItems {
+    int n, C, K, wb;
+    PrepItem it[kMaxFwdItems];
+};
+__global__ void __launch_bounds__(256) pcm_prep_multi_kernel(const __grid_constant__ PrepItems items) {
+    int idx = 0;
+    for (int i = 1; i < items.n; ++i)
+        if (static_cast<int>(blockIdx.x) >= items.it[i].block0) idx = i;
+    const PrepItem& it = items.it[idx];
+    const int lb = static_cast<int>(blockIdx.x) - it.block0, n = lb / it.bx, b = lb - n * it.bx;
+    if (b < it.tiles)
+        pcm_prep_f_body<false>(it.f, it.fa, it.fb, it.fh32, it.lo2max, it.inv_norm, items.K, it.HW, it.PJ, it.NS, items.wb, b, n);
+    else
+        pcm_prep_cam_body<false>(it.cam, nullptr, nullptr, it.camb, items.C, it.HW, it.NS, items.wb, b - it.tiles, n);
+}
+struct FinItem {
+    const float* part;
+    float *out, *dsum;
+    int HW, HWpj, nslot, PJ, NS, G, N, bx, block0;   // bx = HWpj / 32 blocks per image
+};
+struct FinItems {
+    int n, C;
+    FinItem it[kMaxFwdItems];
+};
+__global__ void __launch_bounds__(256) pcm_fwd_finalize_multi_kernel(const __grid_constant__ FinItems items) {
+    int idx = 0;
+    for (int i = 1; i < items.n; ++i)
+        if (static_cast<int>(blockIdx.x) >= items.it[i].block0) idx = i;
+    const FinItem& it = items.it[idx];
+    const int lb = static_cast<int>(blockIdx.x) - it.block0, n = lb / it.bx, b = lb - n * it.bx;
+    pcm_fwd_finalize_body(it.part, it.out, it.dsum, items.C, it.HW, it.HWpj, it.nslot, it.PJ, it.NS, it.G, 0, it.N, b, n);
+}
+}  // namespace wsegk
+
+// ---- several forward-only problems in one launch -----------------------------------------------------
+namespace {
+constexpr int kMultiWb = 64;         // one kernel instantiation for all problems
+constexpr int kMultiPairs = 72;      // inference: the PCM has the GPU to itself
+// CTA pairs per problem, in proportion to its stages (at least one; at most half its stages, as for a single problem)
+int multi_split(int n_items, const int* N, const int* h, const int* w, int* pairs) {
+    long long T[kMaxFwdItems], tot = 0;
+    for (int i = 0; i < n_items; ++i) {
+        const long long HW = static_cast<long long>(h[i]) * w[i];
+        T[i] = N[i] * ((HW + 2 * kTile - 1) / (2 * kTile)) * ((HW + 2 * kMultiWb - 1) / (2 * kMultiWb));
+        tot += T[i];
+    }
+    // every problem starts with one pair; each further pair goes to the problem whose pairs have the most stages to run
+    // (greedy min-max: 30 / 380 / 1892 / 5700 stages of the MSF variants of a 320x480 image -> 1 / 4 / 17 / 50 pairs)
+    int sum = 0;
+    for (int i = 0; i < n_items; ++i) { pairs[i] = 1; ++sum; }
+    while (sum < kMultiPairs) {
+        int best = -1;
+        for (int i = 0; i < n_items; ++i)
+            if (pairs[i] < std::max<long long>(1, T[i] / 2) &&
+                (best < 0 || T[i] * pairs[best] > T[best] * pairs[i]))
+                best = i;
+        if (best < 0) break;
+        ++pairs[best];
+        ++sum;
+    }
+    return sum;
+}
+int multi_check(const char* who, int n_items, const int* N, const int* h, const int* w, int C, int K) {
+    WSEGK_REQUIRE(N && h && w, WSEGK_ERR_NULL, "%s: null pointer", who);
+    WSEGK_REQUIRE(n_items >= 1 && n_items <= kMaxFwdItems, WSEGK_ERR_BAD_SHAPE, "%s: need 1 <= n_items <= %d (got %d)", who,
+                  kMaxFwdItems, n_items);
+    for (int i = 0; i < n_items; ++i)
+        if (int rc = pcm_check(who, N[i], C, K, h[i], w[i])) return rc;
+    return WSEGK_OK;
+}
+}  // namespace
+
+extern "C" int wsegk_pcm_multi_workspace_bytes(int n_items, const int* N, const int* h, const int* w, int C, int K,
+                                               size_t* bytes_out) {
+    if (int rc = multi_check("pcm_multi_workspace_bytes", n_items, N, h, w, C, K)) return rc;
+    WSEGK_REQUIRE(bytes_out, WSEGK_ERR_NULL, "pcm_multi_workspace_bytes: null pointer");
+    int pairs[kMaxFwdItems];
+    multi_split(n_items, N, h, w, pairs);
+    for (int i = 0; i < n_items; ++i) bytes_out[i] = make_pcm_plan(nullptr, N[i], C, K, h[i], w[i], 0, kMultiWb, pairs[i]).bytes;
+    return WSEGK_OK;
+}
+
+extern "C" int wsegk_pcm_fwd_infer_multi(int n_items, const float* const* f, const float* const* cam_norm,
+                                         float* const* cam_rv, const int* N, const int* h, const int* w, int C, int K,
+                                         void* const* workspaces, const size_t* workspace_bytes, wsegk_stream_t stream) {
+    if (int rc = check_device()) return rc;
+    WSEGK_REQUIRE(f && cam_norm && cam_rv && workspaces && workspace_bytes, WSEGK_ERR_NULL, "pcm_fwd_infer_multi: null pointer");
+    if (int rc = multi_check("pcm_fwd_infer_multi", n_items, N, h, w, C, K)) return rc;
+    int pairs[kMaxFwdItems];
+    const int total_pairs = multi_split(n_items, N, h, w, pairs);
+    FwdItems items{};
+    items.n = n_items; items.C = C; items.K = K;
+    PrepItems prep{};
+    prep.n = n_items; prep.C = C; prep.K = K; prep.wb = kMultiWb;
+    FinItems fin{};
+    fin.C = C;
+    int prep_blocks = 0, fin_blocks = 0;
+    PcmPlan plans[kMaxFwdItems];
+    int g0 = 0;
+    for (int i = 0; i < n_items; ++i) {
+        WSEGK_REQUIRE(f[i] && cam_norm[i] && cam_rv[i] && workspaces[i], WSEGK_ERR_NULL, "pcm_fwd_infer_multi: null pointer (item %d)", i);
+        WSEGK_REQUIRE((reinterpret_cast<uintptr_t>(workspaces[i]) & 1023) == 0, WSEGK_ERR_BAD_ALIGN,
+                      "pcm_fwd_infer_multi: workspace %d must be 1024-byte aligned", i);
+        PcmPlan& pl = plans[i];
+        pl = make_pcm_plan(workspaces[i], N[i], C, K, h[i], w[i], 0, kMultiWb, pairs[i]);
+        WSEGK_REQUIRE(workspace_bytes[i] >= pl.bytes, WSEGK_ERR_WORKSPACE_TOO_SMALL, "pcm_fwd_infer_multi: workspace %d: %zu < %zu",
+                      i, workspace_bytes[i], pl.bytes);
+        const int tiles = ceil_div(std::max(pl.HWpj, pl.HWpi), kTile);
+        PrepItem& pi = prep.it[i];
+        pi.f = f[i]; pi.cam = cam_norm[i];
+        pi.fa = reinterpret_cast<uint4*>(pl.fa); pi.fb = reinterpret_cast<uint4*>(pl.fb); pi.camb = reinterpret_cast<uint4*>(pl.camb);
+        pi.fh32 = pl.fh32; pi.inv_norm = pl.inv_norm; pi.lo2max = reinterpret_cast<unsigned int*>(pl.bound + kBoundLo2);
+        pi.HW = pl.HW; pi.PJ = pl.PJ; pi.NS = pl.NS; pi.tiles = tiles; pi.bx = tiles + pl.NS; pi.block0 = prep_blocks;
+        prep_blocks += pi.bx * N[i];
+        if (pl.fwd_shared_units) {
+            FinItem& fi = fin.it[fin.n++];
+            fi.part = pl.part; fi.out = cam_rv[i]; fi.dsum = pl.dsum;
+            fi.HW = pl.HW; fi.HWpj = pl.HWpj; fi.nslot = pl.nsplit; fi.PJ = pl.PJ; fi.NS = pl.NS; fi.G = pl.G; fi.N = N[i];
+            fi.bx = pl.HWpj / 32; fi.block0 = fin_blocks;
+            fin_blocks += fi.bx * N[i];
+        }
+        FwdItem& it = items.it[i];
+        it.fa = reinterpret_cast<const uint8_t*>(pl.fa);
+        it.fb = reinterpret_cast<const uint8_t*>(pl.fb);
+        it.camb = reinterpret_cast<const uint8_t*>(pl.camb);
+        it.part = pl.part; it.out = cam_rv[i]; it.dsum = pl.dsum;
+        it.HW = pl.HW; it.PJ = pl.PJ; it.NS = pl.NS; it.n_units = N[i] * pl.PJ; it.nslot = pl.nsplit;
+        it.g0 = g0; it.G = pairs[i];
+        g0 += pairs[i];
+    }
+    const size_t smem = fwd_smem_bytes(K, kMultiWb);
+    WSEGK_REQUIRE(smem <= 232448, WSEGK_ERR_BAD_SHAPE, "pcm_fwd_infer_multi: %zu bytes of shared memory needed", smem);
+    WSEGK_CUDA_OK(cudaFuncSetAttribute(pcm_fwd_multi_kernel<kMultiWb>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem)));
+    pcm_prep_multi_kernel<<<prep_blocks, 256, 0, stream>>>(prep);
+    prof_mark(0, stream);
+    pcm_fwd_multi_kernel<kMultiWb><<<dim3(2 * total_pairs), kFwdThreads, smem, stream>>>(items);
+    prof_mark(1, stream);
+    int launches = 2;
+    if (fin.n > 0) {
+        pcm_fwd_finalize_multi_kernel<<<fin_blocks, 256, 0, stream>>>(fin);
+        ++launches;
+    }
+    count_launches(launches);
+    WSEGK_CUDA_OK(cudaGetLastError());
+    return WSEGK_OK;
 }
 
 extern "C" int wsegk_pcm_fwd_infer(const float* f, const float* cam_norm, float* cam_rv, int N, int C, int K, int h,

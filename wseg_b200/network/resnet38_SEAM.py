@@ -47,4 +47,5 @@ class Net(resnet38d.Net):
         return cam, cam_rv
 
     PCM = _ContrastNet.PCM
+    pcm_inputs = _ContrastNet.pcm_inputs
     get_parameter_groups = _ContrastNet.get_parameter_groups

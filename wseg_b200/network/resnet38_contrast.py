@@ -55,6 +55,19 @@ class Net(resnet38d.Net):
     def forward(self, x):
         return self.head(x, super().forward_as_dict(x))
 
+    @torch.no_grad()
+    def pcm_inputs(self, x):
+        """Inference aid: ``(cam_logits, f9(f))`` on the stride-8 grid — the network up to, not including,
+        the PCM.  ``infer.msf_cam`` collects these for all scales of an image and runs ONE PCM launch over them
+        (``ops.pcm_infer_multi``); ``ops.bilinear_resize(ops.pcm(cam, f), x.shape[-2:])`` of the pair is ``forward(x)[1]``."""
+        d = resnet38d.Net.forward_as_dict(self, x)       # (not super(): resnet38_SEAM.Net borrows this method)
+        cam = self.fc8(self.dropout7(d['conv6']))
+        h, w = cam.shape[-2:]
+        f8_3 = F.relu(self.f8_3(d['conv4']), inplace=True)
+        f8_4 = F.relu(self.f8_4(d['conv5']), inplace=True)
+        x_s = F.interpolate(x, (h, w), mode='bilinear', align_corners=True)
+        return cam, self.f9(torch.cat([x_s, f8_3, f8_4], dim=1))
+
     def forward_small(self, x):
         """Extension: ``(cam_small, cam_rv_down, f_proj)`` — ``forward`` without the two x8 enlargements
         (``:57-59``).  ``loss.contrast_step_loss_lazy`` consumes these and evaluates the enlargements on the fly, so the

@@ -89,6 +89,39 @@ def pcm_forward(cam_norm_t: torch.Tensor, f: torch.Tensor, inference: bool = Fal
     return out, ws
 
 
+def pcm_infer_multi(cam_norms, fs):
+    """Forward-only PCM of several problems of DIFFERENT grids in ONE launch of the tcgen05 kernel (the 4
+    scales x {image, flip} of contrast_infer.py:58-71).  ``cam_norms[i]`` [N_i,C,h_i,w_i] (already normalised, K1a),
+    ``fs[i]`` [N_i,K,h_i,w_i]; returns the list of ``cam_rv`` maps.  No backward."""
+    import ctypes
+    n_items = len(fs)
+    if n_items == 0 or len(cam_norms) != n_items:
+        raise RuntimeError("pcm_infer_multi: need as many cam maps as feature maps (at least one)")
+    fs = [_require_cuda_f32("f", t.detach()) for t in fs]
+    cams = [_require_cuda_f32("cam_norm", t.detach()) for t in cam_norms]
+    dev = fs[0].device
+    k, c = fs[0].shape[1], cams[0].shape[1]
+    for f, cam in zip(fs, cams):
+        if f.shape[1] != k or cam.shape[1] != c or cam.shape[0] != f.shape[0] or tuple(cam.shape[2:]) != tuple(f.shape[2:]) \
+                or f.device != dev:
+            raise RuntimeError(f"pcm_infer_multi: cam {tuple(cam.shape)} does not match f {tuple(f.shape)}")
+    ints = lambda vals: (ctypes.c_int * n_items)(*vals)
+    ptrs = lambda ts: (ctypes.c_void_p * n_items)(*[t.data_ptr() for t in ts])
+    ns, hs, ws_ = ints([f.shape[0] for f in fs]), ints([f.shape[2] for f in fs]), ints([f.shape[3] for f in fs])
+    sizes = (ctypes.c_size_t * n_items)()
+    check(_lib.lib().wsegk_pcm_multi_workspace_bytes(n_items, ns, hs, ws_, c, k, sizes), "wsegk_pcm_multi_workspace_bytes")
+    outs = [torch.empty_like(cam) for cam in cams]
+    with torch.cuda.device(dev):
+        spaces = []
+        for i in range(n_items):
+            raw = torch.empty(int(sizes[i]) + 1024, dtype=torch.uint8, device=dev)
+            shift = (-raw.data_ptr()) % 1024
+            spaces.append(raw[shift:shift + int(sizes[i])])
+        check(_lib.lib().wsegk_pcm_fwd_infer_multi(n_items, ptrs(fs), ptrs(cams), ptrs(outs), ns, hs, ws_, c, k, ptrs(spaces),
+                                                   sizes, _stream(fs[0])), "wsegk_pcm_fwd_infer_multi")
+    return outs
+
+
 def pcm_forward_logits(cam_logits: torch.Tensor, f: torch.Tensor, mode: Optional[str] = None, defer_fixup: bool = False):
     """K1a + K2 forward in one call (network/resnet38_contrast.py:41-48 fused into :70-73): the normalisation of the raw
     class logits happens inside the PCM's operand preparation.  Returns (cam_rv, workspace, cam_norm) — ``cam_norm`` is
