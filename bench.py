@@ -574,7 +574,7 @@ def pcm_roofline(hp, pk, flush, args):
         ops.pcm_profile(False)
         return fwd_ms, bwd_ms, fix_ms
 
-    fwd_ms, bwd_ms, fix_ms = measure()            # as shipped: the CTA-pair counts the step runs with (64 / 52)
+    fwd_ms, bwd_ms, fix_ms = measure()            # as shipped: the CTA-pair counts the step runs with (52 / 52 at 104 units)
     ops.set_pcm_pairs(72, 72)                     # and on 72 / 72 pairs: what the kernels reach with the GPU to themselves
     try:
         fwd72, bwd72, _ = measure()
@@ -602,7 +602,8 @@ def pcm_roofline(hp, pk, flush, args):
                                           "frac": (fl_fwd + fl_bwd) / ((avg(fwd_ms) + avg(bwd_ms)) * 1e-3) / 1e12 / pk["bf16_tflops"]},
                           "on_72_of_74_sm_pairs": {
                               "note": "the same kernels with the GPU to themselves (ops.set_pcm_pairs(72, 72)); the step runs them on "
-                                      "64 / 52 pairs because the SMs they leave free run the other chains (bench A/B: step 0.334 -> 0.31 ms)",
+                                      "fewer pairs (at most 64 / 52, snapped to a divisor of the unit count: 52 / 52 at 8 x 56x56) "
+                                      "because the SMs they leave free run the other chains (bench A/B: step 0.312 vs 0.330 ms)",
                               "pcm_fwd_kernel": {"ms": avg(fwd72), "frac": fl_fwd / (avg(fwd72) * 1e-3) / 1e12 / pk["bf16_tflops"]},
                               "pcm_bwd_kernel": {"ms": avg(bwd72), "frac": fl_bwd / (avg(bwd72) * 1e-3) / 1e12 / pk["bf16_tflops"]}}}}
     if ops.get_pcm_mode() == "precise":
@@ -821,6 +822,12 @@ def run_ours(args):
             del st3, hp3
         except Exception as exc:
             line["extra_configs"] = {"configs[3]": {"error": f"{type(exc).__name__}: {exc}"}}
+        # the inference side of the path (contrast_infer.py:46-80): multi-scale + flip CAMs of one image
+        try:
+            torch.cuda.empty_cache()
+            line["extra_configs"]["msf_inference"] = msf_inference(dev, flush)
+        except Exception as exc:
+            line["extra_configs"]["msf_inference"] = {"error": f"{type(exc).__name__}: {exc}"}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         best, pix = cpu_reference_sample(N_PER_GPU, 1234, 2)
         line["cpu_baseline"] = {"value": pix / best / 1e6, "unit": UNIT, "cores": torch.get_num_threads(),
@@ -840,6 +847,69 @@ def run_ours(args):
         sys.stdout.flush()
         sys.stderr.flush()
         os._exit(0)
+
+
+def msf_inference(dev, flush):
+    """contrast_infer.py's per-image work on one GPU: a 320x480 image at scales 0.5 / 1 / 1.5 / 2 x {image, flip} through a
+    random-init ResNet-38 + head (eval), as the script's per-variant loop and as infer.msf_cam does it; and the PCM of the 8
+    variants alone, per scale and as ONE launch (ops.pcm_infer_multi)."""
+    from wseg_b200 import infer, ops, synth
+    from wseg_b200.network import resnet38_contrast
+    H, W = 320, 480
+    torch.manual_seed(0)
+    net = resnet38_contrast.Net().to(dev).eval()
+    g = torch.Generator().manual_seed(1)
+    img = torch.randn(3, H, W, generator=g)
+    scales = [F.interpolate(img[None], scale_factor=s, mode="bilinear", align_corners=False)[0].to(dev) for s in (0.5, 1.0, 1.5, 2.0)]
+    label20 = torch.zeros(20)
+    label20[[1, 6, 14]] = 1
+    lab = label20.to(dev).view(20, 1, 1)
+
+    def script_loop():
+        total = None
+        with torch.no_grad():
+            for im in scales:
+                for flip in (False, True):
+                    x = im[None].flip(-1) if flip else im[None]
+                    cam = F.interpolate(net(x)[1][:, 1:], (H, W), mode="bilinear", align_corners=False)[0] * lab
+                    cam = cam.flip(-1) if flip else cam
+                    total = cam if total is None else total + cam
+        return total
+
+    def timed(fn, reps, with_flush=False):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize(dev)
+        ts = []
+        for _ in range(reps):
+            if with_flush:
+                flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            torch.cuda.synchronize(dev)
+            ts.append(a.elapsed_time(b))
+        ts.sort()
+        return ts[len(ts) // 2]
+
+    t_loop = timed(script_loop, 5)
+    t_ours = timed(lambda: infer.msf_cam(net, scales, label20, (H, W)), 5)
+    del net
+    shapes = [(2, 20, 30), (2, 40, 60), (2, 60, 90), (2, 80, 120)]
+    cams, fs = [], []
+    for i, (n, h, w) in enumerate(shapes):
+        d = synth.pcm_inputs(n, h, w, seed=i)
+        cams.append(ops.cam_norm(d["cam"].to(dev)))
+        fs.append(d["f"].to(dev))
+    t_seq = timed(lambda: [ops.pcm_forward(c, f, inference=True)[0] for c, f in zip(cams, fs)], 9, True)
+    t_one = timed(lambda: ops.pcm_infer_multi(cams, fs), 9, True)
+    flops = sum(2.0 * n * (h * w) ** 2 * (K_PCM + C_CLS) for n, h, w in shapes)
+    return {"workload": "one 320x480 image, scales 0.5/1/1.5/2 x flip (8 variants), random-init ResNet-38 + head, eval",
+            "ms_per_image_script_loop": t_loop, "ms_per_image": t_ours,
+            "note": "ms_per_image: infer.msf_cam (image + flip as one batch, one stream per scale, the PCM of all scales in one launch); "
+                    "script_loop: one forward per variant as contrast_infer.py:58-71, same network and kernels",
+            "pcm_of_the_8_variants": {"per_scale_launches_us": t_seq * 1e3, "one_launch_us": t_one * 1e3,
+                                      "algorithmic_tflops_one_launch": flops / (t_one * 1e-3) / 1e12,
+                                      "grids": "20x30, 40x60, 60x90, 80x120 (batch 2 each)", "timing": "eager, L2 flushed, median of 9"}}
 
 
 def _watchdog(seconds: float):
