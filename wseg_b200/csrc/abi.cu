@@ -60,15 +60,28 @@ static thread_local int g_pcm_mode = 1;
 int pcm_mode() { return g_pcm_mode; }
 
 // B-tile rows per CTA: the candidate that pads the i sweep least (ties: the larger tile, fewer stages).
+// WSEGK_WB48_SLACK_PCT >= 0 (build flag or environment; A/B aid) prefers 48-row tiles whenever they pad at most that many per
+// cent more than the best: only with 96-column stages do three T / E buffers fit beside the backward's accumulator in TMEM
+// (pcm.cu: BwdTmem).  Measured round 3 at N = 8, 56x56: the backward does NOT get faster with the third buffer (61.5 us both
+// ways — its TMEM warps, not the buffer ring, bound it) and the forward loses 4 us to the 18 % more stages: off by default.
+#ifndef WSEGK_WB48_SLACK_PCT
+#define WSEGK_WB48_SLACK_PCT (-1)
+#endif
+static int wb48_slack_pct() {
+    static const int v = [] { const char* e = getenv("WSEGK_WB48_SLACK_PCT"); return e ? atoi(e) : WSEGK_WB48_SLACK_PCT; }();
+    return v;
+}
 static int pick_wb(int HW) {
     const int cands[3] = {64, 56, 48};
     int best = 64;
-    long long best_pad = -1;
+    long long best_pad = -1, pad48 = 0;
     for (int wb : cands) {
         const long long ns = (HW + 2 * wb - 1) / (2 * wb);
         const long long padded = ns * 2 * wb;
+        if (wb == 48) pad48 = padded;
         if (best_pad < 0 || padded < best_pad) { best_pad = padded; best = wb; }
     }
+    if (wb48_slack_pct() >= 0 && pad48 * 100 <= best_pad * (100 + wb48_slack_pct())) return 48;
     return best;
 }
 

@@ -1180,9 +1180,23 @@ __device__ __forceinline__ float pcm_grad_scale(const float* bound) {
 constexpr int kBwdStages = 4;
 
 struct BwdBars {
-    uint64_t uj, u_free, full_v[kBwdStages], empty_v[kBwdStages], full_f[kBwdStages], empty_f[kBwdStages], t_full[2],
-        e_full[2], g_full;
+    uint64_t uj, u_free, full_v[kBwdStages], empty_v[kBwdStages], full_f[kBwdStages], empty_f[kBwdStages], t_full[3],
+        e_full[3], g_full;
     uint32_t tmem_base;
+};
+// backward: T / E buffers in TMEM.  The loop T(i) -> convert -> G(i) issued -> T(i + NT) takes ~2900 clk (trace r3) against
+// 1283 clk of tensor-pipe work per stage with two buffers; THREE buffers make it pipe-bound, and three fit beside the 192
+// accumulator columns only for 48-row tiles (3 x 96 + 192 = 480 <= 512; 56-row tiles would need 528)
+template <int WB>
+struct BwdTmem {
+#ifdef WSEGK_BWD_TBUF2
+    static constexpr int NT = 2;
+#else
+    static constexpr int NT = (3 * 2 * WB + kMaxPcmK <= 512) ? 3 : 2;
+#endif
+    static constexpr uint32_t STRIDE = NT == 3 ? 2 * WB : 128;
+    static constexpr uint32_t COL_G = NT == 3 ? 320 : 256;
+    static_assert(NT * STRIDE <= COL_G && COL_G + kMaxPcmK <= 512, "TMEM columns");
 };
 
 // NV values of T (fp32) -> E = [sign bit set] * T * scale as packed fp16.  The sign word has bit m = column 2m, bit 16+m =
@@ -1208,6 +1222,8 @@ pcm_bwd_kernel(const uint8_t* __restrict__ ua, const uint8_t* __restrict__ vb, c
     const bool tr = trace != nullptr && blockIdx.x == 0;
 #define TRACE(role, t, k) do { if (tr && (t) < 64) trace[(role) * 256 + (t) * 4 + (k)] = clock64(); } while (0)
     constexpr int NCOL = 2 * WB;
+    constexpr int NT = BwdTmem<WB>::NT;
+    constexpr uint32_t kTStride = BwdTmem<WB>::STRIDE, kColG = BwdTmem<WB>::COL_G;
     constexpr int KU = SPLIT ? 3 * kAugK : kAugK;
     constexpr uint32_t kUBytes = kTile * KU * 2, kVBytes = WB * KU * 2;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -1237,7 +1253,7 @@ pcm_bwd_kernel(const uint8_t* __restrict__ ua, const uint8_t* __restrict__ vb, c
             mbar_init(smem_u32(&bars->full_f[s]), 2 + relay);        // two producer warps (X part, Y part)
             mbar_init(smem_u32(&bars->empty_f[s]), 1);
         }
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < NT; ++b) {
             mbar_init(smem_u32(&bars->t_full[b]), 1);
             mbar_init(smem_u32(&bars->e_full[b]), 16);        // 8 TMEM warps x 2 CTAs
         }
@@ -1320,7 +1336,7 @@ pcm_bwd_kernel(const uint8_t* __restrict__ ua, const uint8_t* __restrict__ vb, c
                     const bool seg_first = cs.first(), seg_last = cs.last();
                     const int seg = cs.k;
                     cs.next();
-                    const int s = i % kBwdStages, u = i / kBwdStages, b = i & 1;
+                    const int s = i % kBwdStages, u = i / kBwdStages, b = i % NT;
                     if (seg_first) mbar_wait(smem_u32(&bars->uj), seg & 1);
                     TRACE(1, i, 0);
                     mbar_wait(smem_u32(&bars->full_v[s]), u & 1);
@@ -1330,18 +1346,19 @@ pcm_bwd_kernel(const uint8_t* __restrict__ ua, const uint8_t* __restrict__ vb, c
 #ifndef WSEGK_ABL_NOT
 #pragma unroll
                     for (int ks = 0; ks < KU / 16; ++ks)
-                        umma2_ss(tmem + b * 128, du + static_cast<uint64_t>(ks * (2 * lbo_a / 16)),
+                        umma2_ss(tmem + b * kTStride, du + static_cast<uint64_t>(ks * (2 * lbo_a / 16)),
                                  dv + static_cast<uint64_t>(ks * (2 * lbo_b / 16)), id_t, ks > 0);
 #endif
                     umma2_commit(smem_u32(&bars->t_full[b]));
                     umma2_commit(smem_u32(&bars->empty_v[s]));
                     if (seg_last) umma2_commit(smem_u32(&bars->u_free));
                 };
-                // two stages of lookahead inside a segment, one across a segment boundary (see the forward kernel)
+                // NT stages of lookahead inside a segment (T(i + NT) overwrites the buffer G(i) reads: issued behind it by this
+                // same thread, the tensor pipe keeps the order), one less across a segment boundary (see the forward kernel)
                 int next_t = 0;
                 auto issue_upto = [&](int limit) {
-                    while (next_t < cnt && next_t <= limit + 2) {
-                        if (next_t == limit + 2 && next_t > 0 && cs.first()) break;
+                    while (next_t < cnt && next_t <= limit + NT) {
+                        if (next_t == limit + NT && next_t > 0 && cs.first()) break;
                         issue_t(next_t);
                         ++next_t;
                     }
@@ -1349,13 +1366,13 @@ pcm_bwd_kernel(const uint8_t* __restrict__ ua, const uint8_t* __restrict__ vb, c
                 issue_upto(-1);
                 StageCursor si = c0;
                 for (int i = 0; i < cnt; ++i, si.next()) {
-                    const int s = i % kBwdStages, u = i / kBwdStages, b = i & 1;
+                    const int s = i % kBwdStages, u = i / kBwdStages, b = i % NT;
                     TRACE(1, i, 2);
                     if (tr) {
-                        mbar_wait(smem_u32(&bars->e_full[b]), (i >> 1) & 1);
+                        mbar_wait(smem_u32(&bars->e_full[b]), (i / NT) & 1);
                         TRACE(0, i, 2);
                     }
-                    mbar_wait2(smem_u32(&bars->e_full[b]), (i >> 1) & 1, smem_u32(&bars->full_f[s]), u & 1);
+                    mbar_wait2(smem_u32(&bars->e_full[b]), (i / NT) & 1, smem_u32(&bars->full_f[s]), u & 1);
                     TRACE(1, i, 3);
                     tc_fence_after();
                     const uint32_t f0 = smem_u32(s_f + s * f_stage);
@@ -1372,7 +1389,7 @@ pcm_bwd_kernel(const uint8_t* __restrict__ ua, const uint8_t* __restrict__ vb, c
                         // [64, ...) (the two TMEM warps of a quarter each overwrite only what they loaded)
                         constexpr int kHalf = kSplitCol / 16;
                         const uint32_t ecol = ks < kHalf ? ks * 8 : kSplitCol + (ks - kHalf) * 8;
-                        umma2_ts(tmem + kColG, tmem + b * 128 + ecol, umma_smem_desc(a0, a1 - a0, lbo_b), id_g,
+                        umma2_ts(tmem + kColG, tmem + b * kTStride + ecol, umma_smem_desc(a0, a1 - a0, lbo_b), id_g,
                                  ks > 0 ? 1u : acc0);
                     }
 #endif
@@ -1401,20 +1418,20 @@ pcm_bwd_kernel(const uint8_t* __restrict__ ua, const uint8_t* __restrict__ vb, c
         uint32_t r0[32], r1[32];
         auto fetch = [&](int i) {
             if (warp == 0 && lane == 0) TRACE(2, i, 0);
-            mbar_wait(smem_u32(&bars->t_full[i & 1]), (i >> 1) & 1);
+            mbar_wait(smem_u32(&bars->t_full[i % NT]), (i / NT) & 1);
             tc_fence_after();
-            const uint32_t base = tmem + lane_addr + (i & 1) * 128 + hf * kSplitCol;
+            const uint32_t base = tmem + lane_addr + (i % NT) * kTStride + hf * kSplitCol;
             if (hf == 0) load_cols<kSplitCol>(base, r0, r1);
             else load_cols<NC1>(base, r0, r1);
         };
         uint2 mw_next = cnt > 0 ? mask_of(sn) : make_uint2(0, 0);
         if (cnt > 0) fetch(0);
         for (int i = 0; i < cnt; ++i, si.next()) {
-            const int b = i & 1;
+            const int b = i % NT;
             const uint2 mw = mw_next;
             tmem_ld_wait();
             if (warp == 0 && lane == 0) TRACE(2, i, 1);
-            const uint32_t base = tmem + lane_addr + b * 128 + hf * kSplitCol;
+            const uint32_t base = tmem + lane_addr + b * kTStride + hf * kSplitCol;
             uint32_t pk[16];
             mask_scale_pack<32>(r0, mw.x, scale, pk);
             tmem_st16(base, pk);
