@@ -218,8 +218,21 @@ __global__ void __launch_bounds__(256) pcm_prep_kernel(const float* __restrict__
 // + a second bit per entry, |S| < tau, where tau bounds what the FP16 rounding of the operands can do to S; those entries
 // (~0.2 %) are re-evaluated in fp32 by pcm_sign_fixup_kernel, which patches the sign mask.  Round 1 got the same signs from
 // three MMA chains (hi*hi + hi*lo + lo*hi): 3x the tensor work for a correction that matters for 1e-4 of the entries.
-constexpr int kMainThreads = 384;      // backward main kernel: TMEM warps 0-7, producers 8 / 10 / 11, issuer 9
-constexpr int kBwdWarpProdUV = 8, kBwdWarpIssue = 9, kBwdWarpProdX = 10;
+// backward main kernel: 4 TW TMEM warps (TW per TMEM lane quarter), then the U/V producer, the issuer (relay in the peer CTA) and
+// the two producers of the channel halves of F.  TW = 2 (default): each warp converts half of a stage's columns.  TW = 4
+// (-DWSEGK_BWD_TW=4, 640 threads, 96 registers): a quarter each.  Measured round 3 at N = 8, 56x56: the SAME 63-65 us — a TMEM
+// warp's stage costs ~1300 clk whether it owns 64 or 32 columns (mbarrier poll, tcgen05.ld, tcgen05.st + wait, arrive:
+// fixed latencies), and with two T / E buffers the ring T(i) -> convert -> G(i) -> T(i + 2) costs the same ~3000 clk per two
+// stages.  A third buffer alone (48-row tiles) changed nothing either: both limits sit at ~1470 clk per stage against 1283
+// of tensor-pipe work, so only three buffers AND two stages in flight in the TMEM warps (as in the forward) would
+// reach the pipe, and three buffers need 96-column stages, which cost the forward 4 us.  Left as it is.
+#ifndef WSEGK_BWD_TW
+#define WSEGK_BWD_TW 2
+#endif
+constexpr int kBwdTW = WSEGK_BWD_TW;
+constexpr int kBwdTmemWarps = 4 * kBwdTW;
+constexpr int kMainThreads = (kBwdTmemWarps + 4) * 32;
+constexpr int kBwdWarpProdUV = kBwdTmemWarps, kBwdWarpIssue = kBwdTmemWarps + 1, kBwdWarpProdX = kBwdTmemWarps + 2;
 constexpr int kFwdThreads = 384;
 // forward kernel roles.  The TMEM warps come FIRST: the sub-partition arbiter favours the higher warp ids, and the two ALU-dense
 // TMEM warps of a sub-partition otherwise starve the producer / issuer warp that shares it (trace r2: the S issuer needed
@@ -1255,7 +1268,8 @@ pcm_bwd_kernel(const uint8_t* __restrict__ ua, const uint8_t* __restrict__ vb, c
         }
         for (int b = 0; b < NT; ++b) {
             mbar_init(smem_u32(&bars->t_full[b]), 1);
-            mbar_init(smem_u32(&bars->e_full[b]), 16);        // 8 TMEM warps x 2 CTAs
+            // the TMEM warps that own columns of a stage, in both CTAs
+            mbar_init(smem_u32(&bars->e_full[b]), kBwdTW == 4 ? 2 * 4 * ((NCOL + 31) / 32) : 16);
         }
         mbar_init(smem_u32(&bars->g_full), 1);
         mbar_fence_init();
@@ -1387,8 +1401,10 @@ pcm_bwd_kernel(const uint8_t* __restrict__ ua, const uint8_t* __restrict__ vb, c
                         const uint32_t a1 = f0 + (q1 / WB) * f_part + (q1 % WB) * 16;
                         // E of the T columns [0,64) sits at packed columns [0,32) of the buffer, E of the columns from 64 on at
                         // [64, ...) (the two TMEM warps of a quarter each overwrite only what they loaded)
+                        // (TW = 4: a warp owns 32 T columns and leaves their E at the first 16 columns of its quarter)
                         constexpr int kHalf = kSplitCol / 16;
-                        const uint32_t ecol = ks < kHalf ? ks * 8 : kSplitCol + (ks - kHalf) * 8;
+                        const uint32_t ecol = kBwdTW == 4 ? static_cast<uint32_t>((ks >> 1) * 32 + (ks & 1) * 8)
+                                                          : (ks < kHalf ? ks * 8 : kSplitCol + (ks - kHalf) * 8);
                         umma2_ts(tmem + kColG, tmem + b * kTStride + ecol, umma_smem_desc(a0, a1 - a0, lbo_b), id_g,
                                  ks > 0 ? 1u : acc0);
                     }
@@ -1400,7 +1416,76 @@ pcm_bwd_kernel(const uint8_t* __restrict__ ua, const uint8_t* __restrict__ vb, c
             }
             __syncwarp();
         }
-    } else if (warp < 8) {
+    } else if (kBwdTW == 4 && warp < kBwdTmemWarps) {
+        // ---------------------------------------------------------------- TMEM warps, four per lane quarter: warp (q, cq)
+        // owns the T columns [32 cq, 32 cq + 32) of its 32 rows (the last chunk of a 112-column stage has 16, of a 96-column
+        // stage none: that warp only helps with the epilogue) and one sign word per row and stage
+        const int q = warp & 3, cq = warp >> 2;
+        const int cw = NCOL - 32 * cq >= 32 ? 32 : (NCOL - 32 * cq > 0 ? NCOL - 32 * cq : 0);
+        const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+        const int row_in = static_cast<int>(rank) * kTile + q * 32 + lane;
+        const uint32_t e_full0 = mapa_shared(smem_u32(&bars->e_full[0]), 0);
+        const float scale = pcm_grad_scale(bound);
+        StageCursor si = c0, sn = c0;      // this stage / the next one (mask prefetch)
+        auto mask_of = [&](const StageCursor& c) {       // my sign word of the row
+            return __ldg(reinterpret_cast<const uint32_t*>(mask) +
+                         ((static_cast<size_t>(c.n) * NS + c.st) * HWpj + c.jp * 2 * kTile + row_in) * kMaskWords + cq);
+        };
+        uint32_t r0[32];
+        auto fetch = [&](int i) {
+            if (warp == 0 && lane == 0) TRACE(2, i, 0);
+            mbar_wait(smem_u32(&bars->t_full[i % NT]), (i / NT) & 1);
+            tc_fence_after();
+            const uint32_t base = tmem + lane_addr + (i % NT) * kTStride + 32 * cq;
+            if (cw == 32) tmem_ld32(base, r0);
+            else tmem_ld16(base, reinterpret_cast<uint32_t(&)[16]>(r0));
+        };
+        uint32_t mw_next = (cnt > 0 && cw > 0) ? mask_of(sn) : 0u;
+        if (cnt > 0 && cw > 0) fetch(0);
+        for (int i = 0; i < cnt; ++i, si.next()) {
+            if (cw > 0) {
+                const int b = i % NT;
+                const uint32_t mw = mw_next;
+                tmem_ld_wait();
+                if (warp == 0 && lane == 0) TRACE(2, i, 1);
+                const uint32_t base = tmem + lane_addr + b * kTStride + 32 * cq;
+                uint32_t pk[16];
+                if (cw == 32) {
+                    mask_scale_pack<32>(r0, mw, scale, pk);
+                    tmem_st16(base, pk);
+                } else {
+                    mask_scale_pack<16>(r0, mw, scale, pk);
+                    tmem_st8(base, reinterpret_cast<uint32_t(&)[8]>(pk));
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster_relaxed(e_full0 + static_cast<uint32_t>(b) * 8u);
+                if (warp == 0 && lane == 0) TRACE(2, i, 2);
+                sn.next();
+                if (i + 1 < cnt) mw_next = mask_of(sn);
+                if (i + 1 < cnt) fetch(i + 1);
+            }
+            if (si.last()) {
+                // segment epilogue.  dfhat [n][slot][K][HWpj]: for a fixed channel the 32 lanes of a warp write 32
+                // consecutive pixels; the four warps of a quarter take a quarter of the channel groups each
+                const int slot = si.in_tail() ? g - pcm_tail_owner(sched, static_cast<long long>(si.u - sched.Rf * sched.G) * NS) : 0;
+                mbar_wait(smem_u32(&bars->g_full), si.k & 1);
+                tc_fence_after();
+                float* dst = dfhat + ((static_cast<size_t>(si.n) * nslot + slot) * K) * HWpj + si.jp * 2 * kTile + row_in;
+                const int cgroups = K >> 4, per = (cgroups + 3) >> 2;
+                const int c_begin = cq * per, c_end = min(cgroups, c_begin + per);
+                for (int c = c_begin; c < c_end; ++c) {
+                    uint32_t ra[16];
+                    tmem_ld16(tmem + lane_addr + kColG + c * 16, ra);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int v = 0; v < 16; ++v) dst[static_cast<size_t>(c * 16 + v) * HWpj] = __uint_as_float(ra[v]);
+                }
+                tc_fence_before();
+            }
+        }
+    } else if (warp < kBwdTmemWarps) {
         // ---------------------------------------------------------------- TMEM warps: two per lane quarter, the first takes the
         // T columns [0,64) of its 32 rows, the second the rest (as in the forward kernel); each loads the NEXT stage's columns
         // as soon as it has handed this stage's E over, so the barrier poll and the TMEM load latency overlap
