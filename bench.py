@@ -106,7 +106,8 @@ class HotPath:
             p3 = -1 if prio >= 2 else 0
             p6 = max(hi, -2) if prio >= 3 else 0
             p1, p3, p6 = (int(os.environ.get(k, v)) for k, v in (("WSEG_BENCH_P1", p1), ("WSEG_BENCH_P3", p3), ("WSEG_BENCH_P6", p6)))
-            self._streams = [torch.cuda.Stream(device=self.dev, priority=p1), torch.cuda.Stream(device=self.dev),
+            p2 = int(os.environ.get("WSEG_BENCH_P2", "0"))
+            self._streams = [torch.cuda.Stream(device=self.dev, priority=p1), torch.cuda.Stream(device=self.dev, priority=p2),
                              torch.cuda.Stream(device=self.dev, priority=p3), torch.cuda.Stream(device=self.dev),
                              torch.cuda.Stream(device=self.dev), torch.cuda.Stream(device=self.dev, priority=p6)]
         s1, s2, s3, s4, s5, s6 = self._streams
@@ -152,13 +153,16 @@ class HotPath:
         with torch.cuda.stream(s6):
             rv2, ws2, camn2 = ops.pcm_forward_logits(d["cam2"], d["f2"])
             mark("fwd2 done", s6)
+            f2_done = torch.cuda.Event()
+            f2_done.record(s6)
             norm2, pl2 = ops.seed_labels(rv2, d["label"], BG_THRESHOLD)
             proto2, ti2 = ops.prototypes(norm2, d["fproj2"], group=self.group, view=1)
             mark("proto2 done", s6)
             v2_done = torch.cuda.Event()
             v2_done.record(s6)
         with torch.cuda.stream(s2):
-            s2.wait_event(v2_done)
+            # K1b(cam_rv2) and view 2's backward need view 2's forward only (seeds and prototypes carry no gradient)
+            s2.wait_event(v2_done if os.environ.get("WSEG_BENCH_S2_AFTER", "fwd2") == "proto2" else f2_done)
             g_rv2 = k1b("rv2_full", None, "g_rv2")
             mark("K1b rv2 done", s2)
             gf2 = ops.pcm_backward(d["f2"], camn2, rv2, d["g_rv_down2"], ws2)

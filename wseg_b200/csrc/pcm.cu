@@ -27,6 +27,7 @@
 // a unit boundary starts a new segment: new A-side tile (after the a_free / u_free commit of the old segment's last
 // product), accumulator restart, own partial slot.
 #include <algorithm>
+#include <cstdlib>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -919,12 +920,15 @@ pcm_fwd_multi_kernel(const __grid_constant__ FwdItems items) {
 // marked entries go through a shared-memory queue; a warp evaluates eight entries at a time, four lanes per entry with
 // all 12 float4 loads of the lane in flight at once (the first version walked one entry per warp with dependent loads:
 // 104 us at N = 8, 56x56).
+#ifndef WSEGK_FIX_MINBLOCKS
+#define WSEGK_FIX_MINBLOCKS 3
+#endif
 constexpr int kFixThreads = 256;
 constexpr int kFixQueue = 1024;
 constexpr int kFixTile = 64;            // rows j per CTA: 48 KB of shared memory at K = 192 -> four CTAs per SM keep the L2 gathers in flight
 
 template <int KG>      // K / 16
-__global__ void __launch_bounds__(kFixThreads) pcm_sign_fixup_kernel(const float* __restrict__ fh32,
+__global__ void __launch_bounds__(kFixThreads, WSEGK_FIX_MINBLOCKS) pcm_sign_fixup_kernel(const float* __restrict__ fh32,
                                                                     const uint4* __restrict__ nzmask,
                                                                     uint32_t* __restrict__ mask, int HWpj, int NS,
                                                                     int ncol, int chunk) {
@@ -1861,6 +1865,10 @@ static int launch_fixup(const PcmPlan& pl, int N, wsegk_stream_t stream) {
     // works: aim at ~8 working CTAs per SM (four are resident), chunks of at least four stages (the scan reads four per pass)
     const long long cells = static_cast<long long>(tiles) * N * pl.NS;
     int chunk = static_cast<int>(std::min<long long>(std::max<long long>(4, cells / (2 * 8 * 148)), 64));
+    {
+        static const int forced = [] { const char* e = getenv("WSEGK_FIX_CHUNK"); return e ? atoi(e) : 0; }();   // A/B aid
+        if (forced > 0) chunk = forced;
+    }
     chunk = std::min(chunk, std::max(1, pl.NS));
     const dim3 grid(tiles, ceil_div(pl.NS, chunk), N);
     prof_mark(4, stream);
