@@ -203,6 +203,7 @@ def sweep_fullres(rows, cases, iters, flush):
 
 
 def main():
+    ops.set_pcm_pairs(72, 72)      # kernels alone on the GPU: 72 of the 74 SM pairs (the training step runs them on fewer, bench.py)
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default="gpurun_out/sweep.json")
     ap.add_argument("--quick", action="store_true")

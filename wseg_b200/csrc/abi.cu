@@ -122,8 +122,8 @@ extern "C" int wsegk_pcm_set_pairs(int fwd_pairs, int bwd_pairs) {
     return WSEGK_OK;
 }
 
-// U units of NS stages on at most `slots` CTA pairs.  If a pair count in [3/4 slots, slots] divides U, the largest such is
-// taken: every unit is then swept by ONE pair — no stream-K tail, no partial slots, and the forward needs no finalize pass
+// U units of NS stages on at most `slots` CTA pairs.  If U < 3 slots and a pair count in [3/4 slots, slots] divides U, the
+// largest such is taken: every unit is then swept by ONE pair — no stream-K tail, no partial slots, and the forward needs no finalize pass
 // (104 units of the headline shape: 52 pairs instead of 64; the kernel alone 51 -> 57 us, the finalize kernel's 10 us and
 // its launch leave the chain, and 24 more SMs stay free for the step's other kernels).
 static int pick_clusters(long long U, long long NS, long long slots) {
@@ -131,8 +131,8 @@ static int pick_clusters(long long U, long long NS, long long slots) {
     if (g > slots) g = slots;
     if (g < 1) g = 1;
 #ifndef WSEGK_PCM_NO_DIVISOR
-    if (g == slots && U > g)
-        for (long long d = g; 4 * d >= 3 * g; --d)
+    if (g == slots && U > g && U < 3 * g)      // only while a unit is a large part of a pair's work: with many units per pair the
+        for (long long d = g; 4 * d >= 3 * g; --d)   // stream-K tail is a small share and fewer pairs only cost time
             if (U % d == 0) return static_cast<int>(d);
 #endif
     return static_cast<int>(g);
