@@ -117,7 +117,7 @@ def sweep_loss(rows, sizes, batches, dims, iters, flush):
     for hw in sizes:
         for n in batches:
             for d in dims:
-                if n * hw * hw > (1 << 17):          # wsegk_contrast_loss_fwd_bwd: pairwise mining limit
+                if n * hw * hw > (1 << 17):          # keeps the sweep short (no size limit in the kernels)
                     continue
                 g = torch.Generator(device=DEV).manual_seed(5 + hw + n + d)
                 a = {"f_proj": F.relu(0.02 * torch.randn(n, d, hw, hw, generator=g, device=DEV) + 0.01),
@@ -136,6 +136,24 @@ def sweep_loss(rows, sizes, batches, dims, iters, flush):
                     torch.autograd.grad(t["loss_nce"], (f1, f2))
 
                 ms = timed(run, iters, flush)
+                # the same as ONE CUDA graph (what a training step replays; the eager number includes the host's launch
+                # overhead of the chain's ~45 small kernels)
+                ms_graph = None
+                try:
+                    side = torch.cuda.Stream(device=DEV)
+                    side.wait_stream(torch.cuda.current_stream(DEV))
+                    with torch.cuda.stream(side):
+                        for _ in range(3):
+                            run()
+                    torch.cuda.current_stream(DEV).wait_stream(side)
+                    torch.cuda.synchronize()
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph):
+                        run()
+                    ms_graph = timed(graph.replay, iters, flush)
+                    del graph
+                except Exception as exc:                      # keep the sweep going; the eager number stands
+                    print(f"# graph capture failed at N={n} grid={hw} D={d}: {type(exc).__name__}: {exc}", flush=True)
                 # algorithmic bytes: K1c + K3 + K4 of both views
                 c = 21
                 g2 = hw * hw
@@ -144,6 +162,9 @@ def sweep_loss(rows, sizes, batches, dims, iters, flush):
                     + (2 * P * d * 4 * 2 + 2 * c * d * 4 + P * 4 * 2)
                 row = {"kernel": "seed+proto+nce (K1c,K3,K4 fwd+bwd, both views)", "N": n, "grid": hw, "D": d,
                        "ms": ms, "algorithmic_MB": by / 1e6, "GBps": by / ms / 1e6, "frac_of_hbm": by / ms / 1e6 / HBM_GBS}
+                if ms_graph:
+                    row.update({"ms_graph": ms_graph, "GBps_graph": by / ms_graph / 1e6,
+                                "frac_of_hbm_graph": by / ms_graph / 1e6 / HBM_GBS})
                 rows.append(row)
                 print(json.dumps(row), flush=True)
                 del a, b, f1, f2
