@@ -52,15 +52,23 @@ __device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
 // writes are already in tile order (row = pixel), and no shared-memory transpose is needed.
 // kPrecise: also the fp32 values pixel-major (fh32 [n][p][K], what pcm_sign_fixup_kernel re-evaluates S from) and the
 // batch maximum of |fh_p - fp16(fh_p)|^2 (lo2max, atomicMax on the float bits) that sets the fix-up threshold.
+// channel parts per pixel of the feature preparation = CTA size / 128.  Two parts: 256 threads, 96 values per thread at
+// K = 192, ~3 CTAs of 8 warps per SM.  -DWSEGK_PREP_PARTS=4 (512 threads, 48 values per thread) was measured and is no
+// faster (view-1 forward chain 107.4 vs 109.2 us, step 0.301 vs 0.309 ms): the kernel is not short of warps.
+#ifndef WSEGK_PREP_PARTS
+#define WSEGK_PREP_PARTS 2
+#endif
+constexpr int kPrepParts = WSEGK_PREP_PARTS;
+constexpr int kPrepThreads = 128 * kPrepParts;
 template <bool kPrecise>
 __device__ __forceinline__ void pcm_prep_f_body(const float* __restrict__ f, uint4* __restrict__ fa, uint4* __restrict__ fb,
                                                 float* __restrict__ fh32, unsigned int* __restrict__ lo2max,
                                                 float* __restrict__ inv_norm, int K, int HW, int PJ, int NS, int wb,
                                                 int t, int n) {
-    constexpr int GMAX = kMaxPcmK / 16;          // channel groups per thread
-    __shared__ float s_part[2][kTile];
-    __shared__ float s_lo2[2][kTile];
-    const int px = threadIdx.x & 127, half = threadIdx.x >> 7;
+    constexpr int GMAX = kMaxPcmK / (8 * kPrepParts);          // channel groups per thread
+    __shared__ float s_part[kPrepParts][kTile];
+    __shared__ float s_lo2[kPrepParts][kTile];
+    const int px = threadIdx.x & 127, half = threadIdx.x >> 7;  // "half": which of the kPrepParts interleaved sets of channel groups
     const int p = t * kTile + px;
     const int HWpj = PJ * 2 * kTile, HWpi = NS * 2 * wb;
     const int groups = K >> 3;
@@ -69,7 +77,7 @@ __device__ __forceinline__ void pcm_prep_f_body(const float* __restrict__ f, uin
     float ss = 0.f;
 #pragma unroll
     for (int gi = 0; gi < GMAX; ++gi) {
-        const int g = half + 2 * gi;
+        const int g = half + kPrepParts * gi;
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             v[gi][e] = (g < groups && p < HW) ? __ldg(src + static_cast<size_t>(g * 8 + e) * HW) : 0.f;
@@ -78,7 +86,10 @@ __device__ __forceinline__ void pcm_prep_f_body(const float* __restrict__ f, uin
     }
     s_part[half][px] = ss;
     __syncthreads();
-    const float nrm = sqrtf(s_part[0][px] + s_part[1][px]);
+    float ssum = 0.f;
+#pragma unroll
+    for (int q = 0; q < kPrepParts; ++q) ssum += s_part[q][px];        // fixed order
+    const float nrm = sqrtf(ssum);
     const float inv = 1.f / (nrm + 1e-5f);
     if (half == 0 && p < HWpj) inv_norm[static_cast<size_t>(n) * HWpj + p] = (p < HW) ? inv : 0.f;
     const bool in_a = p < HWpj, in_b = p < HWpi;
@@ -89,7 +100,7 @@ __device__ __forceinline__ void pcm_prep_f_body(const float* __restrict__ f, uin
     float lo2 = 0.f;
 #pragma unroll
     for (int gi = 0; gi < GMAX; ++gi) {
-        const int g = half + 2 * gi;
+        const int g = half + kPrepParts * gi;
         if (g >= groups) break;
         __half hi[8];
         float x[8];
@@ -115,7 +126,9 @@ __device__ __forceinline__ void pcm_prep_f_body(const float* __restrict__ f, uin
         s_lo2[half][px] = lo2;
         __syncthreads();
         if (half == 0) {
-            float m = s_lo2[0][px] + s_lo2[1][px];
+            float m = 0.f;
+#pragma unroll
+            for (int q = 0; q < kPrepParts; ++q) m += s_lo2[q][px];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
             if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(lo2max, __float_as_uint(m));   // non-negative floats order like their bits
@@ -192,7 +205,7 @@ __device__ __forceinline__ void pcm_prep_cam_body(const float* __restrict__ cam,
 // both operand preparations in ONE launch (they are independent; as two launches the 7 us cam preparation sat on the
 // critical path behind the feature preparation): blocks [0, tiles) prepare features, blocks [tiles, tiles + NS) cam blocks
 template <bool kPrecise, bool kLogits>
-__global__ void __launch_bounds__(256) pcm_prep_kernel(const float* __restrict__ f, uint4* __restrict__ fa,
+__global__ void __launch_bounds__(kPrepThreads) pcm_prep_kernel(const float* __restrict__ f, uint4* __restrict__ fa,
                                                        uint4* __restrict__ fb, float* __restrict__ fh32,
                                                        unsigned int* __restrict__ lo2max, float* __restrict__ inv_norm,
                                                        const float* __restrict__ cam, const float* __restrict__ peak,
@@ -1920,16 +1933,16 @@ static int pcm_fwd_impl(const float* f, const float* cam_norm, float* cam_rv, in
         if (mode == 2) {
             WSEGK_CUDA_OK(cudaMemsetAsync(lo2, 0, sizeof(float), stream));
             if (logits)
-                pcm_prep_kernel<true, true><<<grid, 256, 0, stream>>>(f, fa, fb, pl.fh32, lo2, pl.inv_norm, cam_norm, pl.peak,
+                pcm_prep_kernel<true, true><<<grid, kPrepThreads, 0, stream>>>(f, fa, fb, pl.fh32, lo2, pl.inv_norm, cam_norm, pl.peak,
                                                                       cam_norm_out, cb, C, K, pl.HW, pl.PJ, pl.NS, pl.wb, tiles);
             else
-                pcm_prep_kernel<true, false><<<grid, 256, 0, stream>>>(f, fa, fb, pl.fh32, lo2, pl.inv_norm, cam_norm, nullptr,
+                pcm_prep_kernel<true, false><<<grid, kPrepThreads, 0, stream>>>(f, fa, fb, pl.fh32, lo2, pl.inv_norm, cam_norm, nullptr,
                                                                        nullptr, cb, C, K, pl.HW, pl.PJ, pl.NS, pl.wb, tiles);
         } else if (logits) {
-            pcm_prep_kernel<false, true><<<grid, 256, 0, stream>>>(f, fa, fb, pl.fh32, lo2, pl.inv_norm, cam_norm, pl.peak,
+            pcm_prep_kernel<false, true><<<grid, kPrepThreads, 0, stream>>>(f, fa, fb, pl.fh32, lo2, pl.inv_norm, cam_norm, pl.peak,
                                                                    cam_norm_out, cb, C, K, pl.HW, pl.PJ, pl.NS, pl.wb, tiles);
         } else {
-            pcm_prep_kernel<false, false><<<grid, 256, 0, stream>>>(f, fa, fb, pl.fh32, lo2, pl.inv_norm, cam_norm, nullptr,
+            pcm_prep_kernel<false, false><<<grid, kPrepThreads, 0, stream>>>(f, fa, fb, pl.fh32, lo2, pl.inv_norm, cam_norm, nullptr,
                                                                     nullptr, cb, C, K, pl.HW, pl.PJ, pl.NS, pl.wb, tiles);
         }
     }
@@ -1973,7 +1986,7 @@ struct PrepItems {
     int n, C, K, wb;
     PrepItem it[kMaxFwdItems];
 };
-__global__ void __launch_bounds__(256) pcm_prep_multi_kernel(const __grid_constant__ PrepItems items) {
+__global__ void __launch_bounds__(kPrepThreads) pcm_prep_multi_kernel(const __grid_constant__ PrepItems items) {
     int idx = 0;
     for (int i = 1; i < items.n; ++i)
         if (static_cast<int>(blockIdx.x) >= items.it[i].block0) idx = i;
@@ -2103,7 +2116,7 @@ extern "C" int wsegk_pcm_fwd_infer_multi(int n_items, const float* const* f, con
     WSEGK_REQUIRE(smem <= 232448, WSEGK_ERR_BAD_SHAPE, "pcm_fwd_infer_multi: %zu bytes of shared memory needed", smem);
     WSEGK_CUDA_OK(cudaFuncSetAttribute(pcm_fwd_multi_kernel<kMultiWb>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem)));
-    pcm_prep_multi_kernel<<<prep_blocks, 256, 0, stream>>>(prep);
+    pcm_prep_multi_kernel<<<prep_blocks, kPrepThreads, 0, stream>>>(prep);
     prof_mark(0, stream);
     pcm_fwd_multi_kernel<kMultiWb><<<dim3(2 * total_pairs), kFwdThreads, smem, stream>>>(items);
     prof_mark(1, stream);
