@@ -82,6 +82,12 @@ static int pick_wb(int HW) {
         if (best_pad < 0 || padded < best_pad) { best_pad = padded; best = wb; }
     }
     if (wb48_slack_pct() >= 0 && pad48 * 100 <= best_pad * (100 + wb48_slack_pct())) return 48;
+    {
+        // the same switch for 64-row tiles (128-column stages: fewer stages, full-width MMAs, but only three S buffers)
+        static const int s64 = [] { const char* e = getenv("WSEGK_WB64_SLACK_PCT"); return e ? atoi(e) : -1; }();
+        const long long pad64 = ((HW + 127) / 128) * 128;
+        if (s64 >= 0 && pad64 * 100 <= best_pad * (100 + s64)) return 64;
+    }
     return best;
 }
 
