@@ -452,7 +452,7 @@ struct PushPeers {
     float* cand[kMaxRanks];
     uint32_t* flags[kMaxRanks];
 };
-constexpr int kPushChunks = 8;
+constexpr int kPushChunks = 16;
 
 __global__ void __launch_bounds__(256) proto_push_kernel(const float* __restrict__ top_val, const int32_t* __restrict__ top_idx,
                                                          const float* __restrict__ top_fea, PushPeers peers, int R, int rank,
@@ -465,18 +465,35 @@ __global__ void __launch_bounds__(256) proto_push_kernel(const float* __restrict
     const int rows = C * k, pairs = (D + 2) >> 1;                  // D even: a row is (D+2)/2 float2
     const int per = ceil_div_dev(rows, static_cast<int>(gridDim.x));
     const int r0 = blockIdx.x * per, r1 = min(rows, r0 + per);
-    for (int e = r0 * pairs + threadIdx.x; e < r1 * pairs; e += blockDim.x) {
-        const int row = e / pairs, u = e - row * pairs;
-        float2 v;
-        if (u == 0) {
-            v.x = top_val[row];
-            v.y = __int_as_float(top_idx[row]);
-        } else {
-            const float* f = top_fea + static_cast<size_t>(row) * D + 2 * (u - 1);
-            v.x = f[0];
-            v.y = f[1];
+    // eight elements per thread and pass, all loads before the first (remote) store: rolled, every iteration paid one L2
+    // round trip for its load before its store could leave (r02 timeline at 8 GPUs: ~40 us between the top-k and the
+    // first flag)
+    const int e_end = r1 * pairs;
+    for (int e0 = r0 * pairs + threadIdx.x; e0 < e_end; e0 += 8 * blockDim.x) {
+        float2 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int e = e0 + j * static_cast<int>(blockDim.x);
+            v[j] = make_float2(0.f, 0.f);
+            if (e < e_end) {
+                const int row = e / pairs, u = e - row * pairs;
+                if (u == 0) {
+                    v[j].x = __ldg(top_val + row);
+                    v[j].y = __int_as_float(__ldg(top_idx + row));
+                } else {
+                    const float2 f2 = __ldg(reinterpret_cast<const float2*>(top_fea + static_cast<size_t>(row) * D) + (u - 1));
+                    v[j] = f2;
+                }
+            }
         }
-        reinterpret_cast<float2*>(dst + static_cast<size_t>(row) * (D + 2))[u] = v;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int e = e0 + j * static_cast<int>(blockDim.x);
+            if (e < e_end) {
+                const int row = e / pairs, u = e - row * pairs;
+                reinterpret_cast<float2*>(dst + static_cast<size_t>(row) * (D + 2))[u] = v[j];
+            }
+        }
     }
     __threadfence_system();
     __syncthreads();
