@@ -189,17 +189,25 @@ class HotPath:
             mark("K4 done", s3)
             s3_done = torch.cuda.Event()
             s3_done.record(s3)
+        # ---- view 1: K1b on cam_rv (the K2 backward follows below)
+        g_rv1 = k1b("rv1_full", VIEW2, "g_rv1")
+        mark("K1b rv1 done", s1)
+        rv1_k1b_done = torch.cuda.Event()
+        rv1_k1b_done.record(s1)
         # ---- K1b on the plain CAMs (independent of the PCM)
+        # K1b(cam2) waits until the critical chain's K1b(cam_rv1) is through: both are bound by their dense gradient stores, and
+        # cam2's has 100 us of slack (A/B on one box, ms per step: plain 0.2995, gap 0.2960; all of stream 4 behind the event
+        # 0.329; only cam1's backward behind it 0.316 — profiles/README.md).  WSEG_BENCH_S4=plain switches it off.
+        s4_mode = os.environ.get("WSEG_BENCH_S4", "gap")
         with torch.cuda.stream(s4):
             g_n1 = k1b("cam1_full", VIEW2, "g_n1")
             mark("K1b cam1 done", s4)
+            if s4_mode == "gap":
+                s4.wait_event(rv1_k1b_done)
             g_n2 = k1b("cam2_full", None, "g_n2")
             mark("K1b cam2 done", s4)
             s4_done = torch.cuda.Event()
             s4_done.record(s4)
-        # ---- view 1: K1b on cam_rv, then K2 backward
-        g_rv1 = k1b("rv1_full", VIEW2, "g_rv1")
-        mark("K1b rv1 done", s1)
         s1.wait_event(fix1_done)
         gf1 = ops.pcm_backward(d["f1"], camn1, rv1, d["g_rv_down1"], ws1)
         mark("bwd1 done", s1)
