@@ -50,6 +50,26 @@ def test_version_and_workspace_sizes(lib):
     assert "unknown op" in _lib.last_error()
 
 
+def test_multi_problem_forward_workspace_sizes(lib):
+    """wsegk_pcm_multi_workspace_bytes (host only): the forward-only PCM of several grids in one launch splits the grid's CTA
+    pairs between the problems and sizes every problem's workspace for its share; bad argument lists are refused."""
+    def sizes(shapes):
+        n = len(shapes)
+        arr = lambda k: (ctypes.c_int * n)(*[s[k] for s in shapes])
+        out = (ctypes.c_size_t * max(n, 1))()
+        rc = lib.wsegk_pcm_multi_workspace_bytes(n, arr(0), arr(1), arr(2), 21, 192, out)
+        return rc, [int(v) for v in out[:n]]
+    rc, four = sizes([(2, 20, 30), (2, 40, 60), (2, 60, 90), (2, 80, 120)])     # the MSF variants of a 320x480 image
+    assert rc == 0 and all(v % 1024 == 0 and v > 0 for v in four)
+    assert four == sorted(four)                                                  # bigger grid, bigger workspace
+    rc, one = sizes([(2, 80, 120)])
+    assert rc == 0 and one[0] > 0
+    rc, _ = sizes([(1, 16, 16)] * 9)                                             # at most 8 problems
+    assert rc != 0 and "n_items" in _lib.last_error()
+    rc, _ = sizes([(0, 16, 16)])
+    assert rc != 0
+
+
 def _check_schedule(lib, n, h, w):
     """The persistent PCM kernels' schedule (rows + stream-K tail, csrc/common.cuh) as a host-side property: every stage
     of every (image, j pair) unit is run by exactly one CTA pair, the pairs' loads differ by at most one stage, a pair's
