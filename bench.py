@@ -200,6 +200,8 @@ class HotPath:
         # 0.329; only cam1's backward behind it 0.316 — profiles/README.md).  WSEG_BENCH_S4=plain switches it off.
         s4_mode = os.environ.get("WSEG_BENCH_S4", "gap")
         with torch.cuda.stream(s4):
+            if os.environ.get("WSEG_BENCH_S4_START", "0") == "fwd2":     # A/B: keep the first 40 us free for the forwards' preparation
+                s4.wait_event(f2_done)
             g_n1 = k1b("cam1_full", VIEW2, "g_n1")
             mark("K1b cam1 done", s4)
             if s4_mode == "gap":
