@@ -788,6 +788,23 @@ def run_ours(args):
         dist.all_reduce(tn, op=dist.ReduceOp.MAX)
     np_ok = e2e_np.verify()
     e2e_np.graph = None
+    # for transparency: the same step with the library's "remembered enlargement" switched off, i.e. fullres_norm reading the
+    # materialised x8 maps and autograd carrying the dense full-resolution gradients back through the enlargement (what the
+    # public operators did until the last session of round 2); same losses and gradients, only the route differs
+    from wseg_b200 import ops as _ops
+    _ops.remember_enlargements(False)
+    try:
+        e2e_dense = E2EPath(hp, use_graph=not args.no_graph)
+        dense_ms, _ = time_steps(e2e_dense.step, args.steps, args.warmup, dev, flush, barrier)
+        td = torch.tensor([dense_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(td, op=dist.ReduceOp.MAX)
+        dense_ok = e2e_dense.verify()
+        dense_same = bool(torch.allclose(e2e_dense.out_host, e2e.out_host, rtol=1e-6, atol=0))
+        e2e_dense.graph = None
+        del e2e_dense
+    finally:
+        _ops.remember_enlargements(True)
     # the same end-to-end step with the lazy full-resolution maps of the extended API (Net.forward_small +
     # ops.fullres_norm_up; same values, the four N*21*H*W tensors never exist) — reported beside the drop-in number
     e2e_lazy = E2EPath(hp, use_graph=not args.no_graph, lazy=True)
@@ -809,6 +826,10 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e.h2d_bytes,
                     "d2h_bytes_per_step": e2e.d2h_bytes, "ms_per_step": float(t.item()) / args.steps, "launch": e2e.mode,
                     "replay_equals_eager": e2e_ok,
+                    "with_dense_fullres_gradients": {"ms_per_step": float(td.item()) / args.steps, "replay_equals_eager": dense_ok,
+                                                     "losses_equal_e2e": dense_same,
+                                                     "note": "ops.remember_enlargements(False): K1b reads the materialised x8 maps, "
+                                                             "the dense gradients travel back through the enlargement"},
                     "unpipelined": {"ms_per_step": float(tn.item()) / args.steps, "replay_equals_eager": np_ok,
                                     "note": "the same step waiting for its own copies (round 1's arrangement)"},
                     "input_pipeline": "double-buffered: the next step's inputs are copied while this step computes (one 37 MB H2D copy and one D2H read inside every timed step)",
