@@ -12,8 +12,16 @@
 namespace wsegk {
 
 constexpr int kTile = 128;        // pixels per A-side (j) PCM tile = rows one CTA owns (UMMA M = 256 over the CTA pair)
-constexpr int kCamRows = 32;      // PCM forward: cam operand rows per CTA (rank 0: cam hi + ones row, rank 1: cam lo)
-constexpr int kONum = 64;         // forward accumulator columns (2 x kCamRows)
+#ifndef WSEGK_CAM_ROWS
+#define WSEGK_CAM_ROWS 32
+#endif
+// PCM forward: cam operand rows per CTA (rank 0: cam hi + the ones row, rank 1: cam lo).  -DWSEGK_CAM_ROWS=24 (the smallest
+// multiple of 8 that holds kMaxClasses + 1 rows) makes the P V product 256 x 48 x 16 instead of 256 x 64 x 16: 6 % less
+// tensor-pipe work per stage, parity-green, and measured no faster (forward 47-49 us either way on 52 pairs: the kernel is
+// not quite pipe-bound), so the profiled configuration stays.
+constexpr int kCamRows = WSEGK_CAM_ROWS;
+constexpr int kONum = 2 * kCamRows;   // forward accumulator columns = rows of a partial slot
+static_assert(kCamRows % 8 == 0 && kCamRows >= 24 && kCamRows <= 32, "cam operand rows");
 constexpr int kAugK = 48;         // PCM backward rank-(2C+2) factor, padded to a multiple of 16
 constexpr int kMaxClasses = 23;   // 2C + 2 <= kAugK
 constexpr int kMaxPcmK = 192;

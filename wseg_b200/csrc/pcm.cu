@@ -437,6 +437,7 @@ __device__ __noinline__ void fwd_epilogue(uint32_t o_addr, float* __restrict__ o
     float* dst = part_row + static_cast<size_t>(hf * 32) * HWpj;
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
+        if (hf * 32 + c * 16 >= kONum) break;              // the accumulator has kONum (48 or 64) columns
         uint32_t r[16];
         tmem_ld16(o_addr + hf * 32 + c * 16, r);
         tmem_ld_wait();
@@ -475,7 +476,7 @@ pcm_fwd_body(const uint8_t* __restrict__ fa, const uint8_t* __restrict__ fb, con
     constexpr int NCOL = 2 * WB;
     constexpr int kSBuf = FwdTmem<WB>::SB;
     constexpr uint32_t kSStride = FwdTmem<WB>::STRIDE, kColO = FwdTmem<WB>::COL_O;
-    constexpr uint32_t kCamBytes = NCOL * 64;                  // (NCOL/8) groups x 32 rows x 16 B per CTA
+    constexpr uint32_t kCamBytes = NCOL * 2 * kCamRows;        // (NCOL/8) groups x kCamRows rows x 16 B per CTA
     using Bars = FwdBars;
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t a_bytes = kTile * K * 2, b_bytes = WB * K * 2;
@@ -1742,7 +1743,7 @@ __global__ void __launch_bounds__(256) pcm_bwd_post_vec_kernel(const float* __re
 
 static size_t fwd_smem_bytes(int K, int wb) {
     const size_t a = static_cast<size_t>(kTile) * K * 2, b = static_cast<size_t>(wb) * K * 2;
-    return kABuf * a + kFStages * b + kCamStages * static_cast<size_t>(2 * wb) * 64 + sizeof(FwdBars) + 64;
+    return kABuf * a + kFStages * b + kCamStages * static_cast<size_t>(2 * wb) * 2 * kCamRows + sizeof(FwdBars) + 64;
 }
 
 static size_t bwd_smem_bytes(int K, int wb, bool split) {
